@@ -1,0 +1,196 @@
+/* maplab_lc_b200.h — C-ABI of the B200-native loop-closure query path.
+ *
+ * Drop-in boundary for maplab's loop-closure query path. Every entry point
+ * replaces one call of the reference (paths relative to the maplab checkout):
+ *
+ *   MBL = algorithms/loopclosure/matching-based-loopclosure
+ *   LCH = algorithms/loopclosure/loop-closure-handler
+ *   DP  = algorithms/loopclosure/descriptor-projection
+ *
+ * Conventions
+ *  - plain pointers and sizes only; the library never keeps a caller pointer past the call;
+ *  - every function returns 0 on success, non-zero on failure (mlc_last_error() has the text).
+ *    The reference aborts (glog CHECK) where this library returns an error; the C++ shim
+ *    (maplab_b200/csrc/loop_detector.h) turns non-zero into an exception / abort;
+ *  - descriptors are one per row: `bits` is n x bytes_per_desc (== a column-major
+ *    (bytes_per_desc x n) aslam DescriptorsT), projected descriptors are n x dim float
+ *    (== column-major dim x n Eigen::MatrixXf);
+ *  - 128-bit maplab ids (vertex / mission / landmark HashIds) cross the boundary as dense
+ *    int64 numbers assigned by the shim;
+ *  - there is NO CPU fallback: without a CUDA device / the sm_100a kernels every compute call fails.
+ */
+#ifndef MAPLAB_LC_B200_H_
+#define MAPLAB_LC_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct mlc_detector mlc_detector; /* opaque */
+
+/* Flags that change results (SURVEY.md §8b "Flags"); defaults = the reference's gflags. */
+typedef struct mlc_settings {
+  int32_t num_closest_words;       /* --lc_num_words_for_nn_search (10), MBL/src/detector-settings.cc:40 */
+  int32_t num_nearest_neighbors;   /* --lc_num_neighbors (-1 = auto), MBL/src/detector-settings.cc:36 */
+  int32_t scoring;                 /* --lc_scoring_function: 0 accumulation, 1 probabilistic */
+  int32_t engine;                  /* --lc_detector_engine: 0 imi, 1 imipq */
+  double min_image_time_seconds;   /* --lc_min_image_time_seconds (10.0) */
+  uint64_t min_verify_matches_num; /* --lc_min_verify_matches_num (10) */
+  float fraction_best_scores;      /* --lc_fraction_best_scores (0.25) */
+  float knn_epsilon;               /* --lc_knn_epsilon (2.0), loopclosure-common/src/flags.cc:9 */
+  float knn_max_radius;            /* --lc_knn_max_radius (20.0), loopclosure-common/src/flags.cc:12 */
+  int32_t device;                  /* CUDA device ordinal; -1 = current device */
+  int32_t shard_rank;              /* this process' shard of the inverted lists (0 .. shard_count-1) */
+  int32_t shard_count;             /* number of shards (GPUs); descriptor i lives on shard i % count */
+} mlc_settings;
+
+/* One query (or database) frame header. */
+typedef struct mlc_frame {
+  int64_t timestamp_ns;  /* ProjectedImage::timestamp_nanoseconds, DP/.../descriptor-projection.h:23-31 */
+  int64_t vertex_id;     /* dense number of ProjectedImage::keyframe_id.vertex_id */
+  int64_t mission_id;    /* dense number of ProjectedImage::mission_id */
+  int32_t frame_index;   /* ProjectedImage::keyframe_id.frame_index */
+  int32_t num_descriptors;
+} mlc_frame;
+
+/* One structure match (vi_map::FrameKeyPointToStructureMatch, vi-map/loop-constraint.h:15-30). */
+typedef struct mlc_match {
+  int32_t query_frame;    /* index of the query frame in the batch */
+  int32_t query_keypoint; /* keypoint_id_query.keypoint_index */
+  int32_t db_descriptor;  /* global descriptor index in the database */
+  int32_t db_keyframe;    /* insertion number of keyframe_id_result */
+  int64_t db_vertex;      /* keyframe_id_result.vertex_id */
+  int64_t landmark;       /* landmark_result */
+} mlc_match;
+
+/* Pinhole camera of the query n-camera rig (aslam::PinholeCamera + T_B_C). */
+typedef struct mlc_camera {
+  double fu, fv, cu, cv;
+  int32_t distortion; /* 0 none, 1 fisheye(FOV) */
+  int32_t pad_;
+  double dist[4];
+  double R_B_C[9]; /* row-major */
+  double t_B_C[3];
+} mlc_camera;
+
+typedef struct mlc_ransac_settings {
+  int32_t min_inlier_count;  /* --lc_min_inlier_count (10), LCH/src/loop-closure-handler.cc:10-16 */
+  int32_t num_ransac_iters;  /* --lc_num_ransac_iters (100) */
+  double min_inlier_ratio;   /* --lc_min_inlier_ratio (0.0) */
+  double ransac_pixel_sigma; /* --lc_ransac_pixel_sigma (2.0) */
+  uint32_t seed;             /* opengv seed when --lc_use_random_pnp_seed=false: 12345 */
+  int32_t rng_mapping;       /* libstdc++ uniform_int_distribution mapping: 1 = GCC>=11, 0 = GCC<=10 */
+} mlc_ransac_settings;
+
+/* Per-query result of geometric verification (LCH/src/loop-closure-handler.cc:235-550). */
+typedef struct mlc_pose_result {
+  int32_t accepted;      /* handleLoopClosure() return value */
+  int32_t ransac_success;
+  int32_t num_inliers;   /* best-per-keypoint inliers */
+  int32_t num_ransac_inliers;
+  int32_t iterations;
+  int32_t model_indices[4];
+  int32_t pad_;
+  double inlier_ratio;
+  double T_G_I[12]; /* 3x4 row-major [R|t] */
+} mlc_pose_result;
+
+const char* mlc_last_error(void);
+int mlc_version(void);
+/* Number of CUDA kernels this library has launched in this process (bench.py: gpu_launches). */
+uint64_t mlc_kernel_launch_count(void);
+
+void mlc_default_settings(mlc_settings* s);
+void mlc_default_ransac_settings(mlc_ransac_settings* s);
+
+/* LoopDetector::LoopDetector(settings) + vocabulary load
+ * (MBL/src/matching-based-engine.cc:28-36, :287-317; InvertedMultiIndexVocabulary::Load,
+ * MBL/include/matching-based-loopclosure/inverted-multi-index-interface.h:37-47, :72-88).
+ * vocab_blob = bytes of the quantizer file named by --lc_projected_quantizer_filename. */
+int mlc_create(const mlc_settings* settings, const void* vocab_blob, size_t vocab_size,
+               mlc_detector** out);
+void mlc_destroy(mlc_detector* d);
+
+/* LoopDetector::Clear, MBL/src/matching-based-engine.cc:255-262 */
+int mlc_clear(mlc_detector* d);
+/* LoopDetector::NumEntries / NumDescriptors, MBL/include/.../matching-based-engine.h:44-50 */
+int64_t mlc_num_entries(const mlc_detector* d);
+int64_t mlc_num_descriptors(const mlc_detector* d);
+/* getNumNeighborsToSearch, MBL/src/matching-based-engine.cc:319-338 */
+int mlc_num_neighbors(const mlc_detector* d);
+int mlc_target_dim(const mlc_detector* d);
+
+/* LoopDetector::ProjectDescriptors -> descriptor_projection::ProjectDescriptorBlock
+ * (MBL/src/matching-based-engine.cc:38-42, DP/src/descriptor-projection.cc:15-50).
+ * bits: n x bytes_per_desc (host); out: n x dim (host). Kernel 1 (tcgen05 GEMM). */
+int mlc_project(mlc_detector* d, const uint8_t* bits, int bytes_per_desc, int64_t n, float* out);
+/* Same with device pointers on `stream` (cudaStream_t as void*); no host sync. */
+int mlc_project_device(mlc_detector* d, const uint8_t* d_bits, int bytes_per_desc, int64_t n,
+                       float* d_out, void* stream);
+
+/* LoopDetector::Insert(ProjectedImage::Ptr), MBL/src/matching-based-engine.cc:217-253.
+ * proj: num_descriptors x dim floats (host); landmarks: num_descriptors ids (may be NULL). */
+int mlc_insert(mlc_detector* d, const mlc_frame* frame, const float* proj, const int64_t* landmarks);
+/* Bulk variant: `num_frames` frames whose descriptors are concatenated in `proj`/`landmarks`. */
+int mlc_insert_batch(mlc_detector* d, const mlc_frame* frames, int64_t num_frames, const float* proj,
+                     const int64_t* landmarks);
+
+/* LoopDetector::Initialize (MBL/include/.../matching-based-engine.h:24) — here: freeze the
+ * inserted keyframes and build the device index (cell assignment = FindClosestWords(desc, 1),
+ * imilib/inverted-multi-index.h:77-94, then cell-sorted inverted lists). Called implicitly by
+ * the first query after an insert. */
+int mlc_initialize(mlc_detector* d);
+
+/* IndexInterface::GetNNearestNeighborsForFeatures (MBL/include/.../index-interface.h:27-35;
+ * imilib/inverted-multi-index.h:100-161): q n_q x dim, idx/dist n_q x k (host, caller-sized).
+ * Missing neighbours are (-1, +inf), trailing. Kernels 2a + 2b. */
+int mlc_knn(mlc_detector* d, const float* q, int64_t n_q, int k, int32_t* idx, float* dist);
+int mlc_knn_device(mlc_detector* d, const float* d_q, int64_t n_q, int k, int32_t* d_idx,
+                   float* d_dist, void* stream);
+/* Parity checkpoints P2/P3: cell of each descriptor at insert (nw = 1) / visited cells per query
+ * (nw = settings.num_closest_words; -1 for pairs with a missing word). cells: n x nw (host). */
+int mlc_coarse_cells(mlc_detector* d, const float* q, int64_t n, int nw, int32_t* cells);
+/* Merge `num_lists` per-shard top-k lists (each n_q x k, concatenated list-major, device) into
+ * the k smallest by (distance, index) — the consumer of the NCCL all-gather. */
+int mlc_merge_topk_device(mlc_detector* d, const int32_t* d_idx_lists, const float* d_dist_lists,
+                          int num_lists, int64_t n_q, int k, int32_t* d_idx, float* d_dist,
+                          void* stream);
+
+/* Algorithmic bytes the last mlc_knn* call scanned: sum over (query, visited cell present in
+ * this shard) of list_length * bytes_per_entry (44 imi / 9 imipq) — SURVEY.md §8d. */
+int mlc_last_scan_stats(mlc_detector* d, uint64_t* algorithmic_bytes, uint64_t* entries_scanned,
+                        double* scan_kernel_ms);
+
+/* Batched LoopDetector::Find (MBL/src/matching-based-engine.cc:48-168) for `num_frames` query
+ * frames (frames of one vertex must be adjacent). proj: concatenated projected descriptors.
+ * Output: matches in canonical order, match_offsets[num_vertices+1] (per query vertex, in order
+ * of first appearance), written up to `capacity` entries; *num_matches = total found. */
+int mlc_find_batch(mlc_detector* d, const mlc_frame* frames, int64_t num_frames, const float* proj,
+                   mlc_match* matches, int64_t capacity, int64_t* match_offsets,
+                   int64_t* num_vertices, int64_t* num_matches);
+/* Same, starting from binary descriptors (project -> kNN -> vote/cluster on the device). */
+int mlc_find_batch_bits(mlc_detector* d, const mlc_frame* frames, int64_t num_frames,
+                        const uint8_t* bits, int bytes_per_desc, mlc_match* matches,
+                        int64_t capacity, int64_t* match_offsets, int64_t* num_vertices,
+                        int64_t* num_matches);
+
+/* Batched geometric verification: LoopClosureHandler::handleLoopClosure gates +
+ * PnpPoseEstimator::absoluteMultiPoseRansacPinholeCam (LCH/src/loop-closure-handler.cc:235-480,
+ * aslam_cv2/aslam_cv_geometric_vision/src/pnp-pose-estimator.cc:75-132, :193-280).
+ * Problem p covers correspondences [offsets[p], offsets[p+1]): keypoints 2 x n (u,v per match),
+ * camera index, keypoint index, landmark position G_p (3 per match).
+ * inlier_flags (may be NULL): per correspondence 0 = outlier, 1 = RANSAC inlier,
+ * 3 = RANSAC inlier kept as best match of its keypoint. */
+int mlc_pnp_ransac_batch(mlc_detector* d, const mlc_ransac_settings* rs, const mlc_camera* cams,
+                         int num_cams, int64_t num_problems, const int64_t* offsets,
+                         const double* keypoints, const int32_t* camera_index,
+                         const int32_t* keypoint_index, const double* landmarks,
+                         mlc_pose_result* results, uint8_t* inlier_flags);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MAPLAB_LC_B200_H_ */

@@ -1,0 +1,271 @@
+"""ctypes binding of libmaplab_lc_b200.so (include/maplab_lc_b200.h).
+
+The library is built in-tree by ``maplab_b200.build.build()`` (``__graft_entry__.build``). There
+is no CPU fallback: if the shared library or a CUDA device is missing every call fails loudly.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmaplab_lc_b200.so")
+_lib = None
+
+EXPORTS = [
+    "mlc_last_error", "mlc_version", "mlc_kernel_launch_count", "mlc_default_settings",
+    "mlc_default_ransac_settings", "mlc_create", "mlc_destroy", "mlc_clear", "mlc_num_entries",
+    "mlc_num_descriptors", "mlc_num_neighbors", "mlc_target_dim", "mlc_project",
+    "mlc_project_device", "mlc_insert", "mlc_insert_batch", "mlc_initialize", "mlc_knn",
+    "mlc_knn_device", "mlc_coarse_cells", "mlc_merge_topk_device", "mlc_last_scan_stats",
+    "mlc_find_batch", "mlc_find_batch_bits", "mlc_pnp_ransac_batch",
+]
+
+
+class Settings(C.Structure):
+    _fields_ = [("num_closest_words", C.c_int32), ("num_nearest_neighbors", C.c_int32),
+                ("scoring", C.c_int32), ("engine", C.c_int32),
+                ("min_image_time_seconds", C.c_double), ("min_verify_matches_num", C.c_uint64),
+                ("fraction_best_scores", C.c_float), ("knn_epsilon", C.c_float),
+                ("knn_max_radius", C.c_float), ("device", C.c_int32), ("shard_rank", C.c_int32),
+                ("shard_count", C.c_int32)]
+
+
+class Frame(C.Structure):
+    _fields_ = [("timestamp_ns", C.c_int64), ("vertex_id", C.c_int64), ("mission_id", C.c_int64),
+                ("frame_index", C.c_int32), ("num_descriptors", C.c_int32)]
+
+
+FRAME_DTYPE = np.dtype([("timestamp_ns", "<i8"), ("vertex_id", "<i8"), ("mission_id", "<i8"),
+                        ("frame_index", "<i4"), ("num_descriptors", "<i4")])
+MATCH_DTYPE = np.dtype([("query_frame", "<i4"), ("query_keypoint", "<i4"), ("db_descriptor", "<i4"),
+                        ("db_keyframe", "<i4"), ("db_vertex", "<i8"), ("landmark", "<i8")])
+CAMERA_DTYPE = np.dtype([("fu", "<f8"), ("fv", "<f8"), ("cu", "<f8"), ("cv", "<f8"),
+                         ("distortion", "<i4"), ("pad_", "<i4"), ("dist", "<f8", (4,)),
+                         ("R_B_C", "<f8", (9,)), ("t_B_C", "<f8", (3,))])
+POSE_DTYPE = np.dtype([("accepted", "<i4"), ("ransac_success", "<i4"), ("num_inliers", "<i4"),
+                       ("num_ransac_inliers", "<i4"), ("iterations", "<i4"),
+                       ("model_indices", "<i4", (4,)), ("pad_", "<i4"), ("inlier_ratio", "<f8"),
+                       ("T_G_I", "<f8", (12,))])
+
+
+class RansacSettings(C.Structure):
+    _fields_ = [("min_inlier_count", C.c_int32), ("num_ransac_iters", C.c_int32),
+                ("min_inlier_ratio", C.c_double), ("ransac_pixel_sigma", C.c_double),
+                ("seed", C.c_uint32), ("rng_mapping", C.c_int32)]
+
+
+class MlcError(RuntimeError):
+    pass
+
+
+def lib():
+    """Load the shared library (raises if it has not been built — no fallback)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise MlcError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; "
+                           "g.build()'` (needs nvcc); there is no CPU fallback")
+        _lib = C.CDLL(LIB_PATH)
+        _lib.mlc_last_error.restype = C.c_char_p
+        _lib.mlc_kernel_launch_count.restype = C.c_uint64
+        _lib.mlc_num_entries.restype = C.c_int64
+        _lib.mlc_num_descriptors.restype = C.c_int64
+        _lib.mlc_destroy.restype = None
+        _lib.mlc_default_settings.restype = None
+        _lib.mlc_default_ransac_settings.restype = None
+    return _lib
+
+
+def _check(rc):
+    if rc != 0:
+        raise MlcError(lib().mlc_last_error().decode())
+
+
+def _ptr(a):
+    return C.c_void_p(a.ctypes.data) if a is not None and a.size else C.c_void_p(0)
+
+
+def default_settings(**kw):
+    s = Settings()
+    lib().mlc_default_settings(C.byref(s))
+    for k, v in kw.items():
+        if not hasattr(s, k):
+            raise AttributeError(k)
+        setattr(s, k, v)
+    return s
+
+
+def default_ransac_settings(**kw):
+    s = RansacSettings()
+    lib().mlc_default_ransac_settings(C.byref(s))
+    for k, v in kw.items():
+        if not hasattr(s, k):
+            raise AttributeError(k)
+        setattr(s, k, v)
+    return s
+
+
+def kernel_launch_count():
+    return int(lib().mlc_kernel_launch_count())
+
+
+def make_frames(ts, vertex, mission, frame_index, num_descriptors):
+    n = len(num_descriptors)
+    f = np.zeros(n, FRAME_DTYPE)
+    f["timestamp_ns"] = ts
+    f["vertex_id"] = vertex
+    f["mission_id"] = mission
+    f["frame_index"] = frame_index
+    f["num_descriptors"] = num_descriptors
+    return f
+
+
+def make_cameras(cams):
+    """cams: list of dicts(fu, fv, cu, cv, R_B_C(3x3), t_B_C(3), distortion, dist)."""
+    out = np.zeros(len(cams), CAMERA_DTYPE)
+    for i, c in enumerate(cams):
+        out[i]["fu"], out[i]["fv"], out[i]["cu"], out[i]["cv"] = c["fu"], c["fv"], c["cu"], c["cv"]
+        out[i]["distortion"] = c.get("distortion", 0)
+        out[i]["dist"] = np.asarray(c.get("dist", (0, 0, 0, 0)), np.float64)
+        out[i]["R_B_C"] = np.asarray(c.get("R_B_C", np.eye(3)), np.float64).reshape(-1)
+        out[i]["t_B_C"] = np.asarray(c.get("t_B_C", np.zeros(3)), np.float64)
+    return out
+
+
+class Detector:
+    """Thin owner of an ``mlc_detector*``; numpy in, numpy out."""
+
+    def __init__(self, vocab_blob, settings=None):
+        self.settings = settings or default_settings()
+        blob = bytes(vocab_blob)
+        self._h = C.c_void_p()
+        _check(lib().mlc_create(C.byref(self.settings), blob, C.c_size_t(len(blob)),
+                                C.byref(self._h)))
+        self.dim = int(lib().mlc_target_dim(self._h))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().mlc_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- LoopDetector surface -------------------------------------------------
+    def clear(self):
+        _check(lib().mlc_clear(self._h))
+
+    def num_entries(self):
+        return int(lib().mlc_num_entries(self._h))
+
+    def num_descriptors(self):
+        return int(lib().mlc_num_descriptors(self._h))
+
+    def num_neighbors(self):
+        return int(lib().mlc_num_neighbors(self._h))
+
+    def project(self, bits):
+        bits = np.ascontiguousarray(bits, np.uint8)
+        n, nbytes = bits.shape
+        out = np.empty((n, self.dim), np.float32)
+        _check(lib().mlc_project(self._h, _ptr(bits), nbytes, C.c_int64(n), _ptr(out)))
+        return out
+
+    def insert_batch(self, frames, proj, landmarks=None):
+        frames = np.ascontiguousarray(frames, FRAME_DTYPE)
+        proj = np.ascontiguousarray(proj, np.float32).reshape(-1, self.dim)
+        assert int(frames["num_descriptors"].sum()) == proj.shape[0]
+        lm = None if landmarks is None else np.ascontiguousarray(landmarks, np.int64)
+        _check(lib().mlc_insert_batch(self._h, _ptr(frames), C.c_int64(len(frames)), _ptr(proj),
+                                      _ptr(lm) if lm is not None else C.c_void_p(0)))
+
+    def insert(self, ts, vertex, frame_index, mission, proj, landmarks=None):
+        proj = np.ascontiguousarray(proj, np.float32).reshape(-1, self.dim)
+        self.insert_batch(make_frames([ts], [vertex], [mission], [frame_index], [proj.shape[0]]),
+                          proj, landmarks)
+
+    def initialize(self):
+        _check(lib().mlc_initialize(self._h))
+
+    def knn(self, q, k):
+        q = np.ascontiguousarray(q, np.float32).reshape(-1, self.dim)
+        n = q.shape[0]
+        idx = np.empty((n, k), np.int32)
+        dist = np.empty((n, k), np.float32)
+        _check(lib().mlc_knn(self._h, _ptr(q), C.c_int64(n), k, _ptr(idx), _ptr(dist)))
+        return idx, dist
+
+    def coarse_cells(self, q, nw):
+        q = np.ascontiguousarray(q, np.float32).reshape(-1, self.dim)
+        cells = np.empty((q.shape[0], nw), np.int32)
+        _check(lib().mlc_coarse_cells(self._h, _ptr(q), C.c_int64(q.shape[0]), nw, _ptr(cells)))
+        return cells
+
+    def last_scan_stats(self):
+        b, e, ms = C.c_uint64(), C.c_uint64(), C.c_double()
+        _check(lib().mlc_last_scan_stats(self._h, C.byref(b), C.byref(e), C.byref(ms)))
+        return dict(algorithmic_bytes=b.value, entries=e.value, scan_ms=ms.value)
+
+    # device-pointer variants (plumbing by torch: pass tensor.data_ptr())
+    def project_device(self, bits_ptr, bytes_per_desc, n, out_ptr, stream=0):
+        _check(lib().mlc_project_device(self._h, C.c_void_p(bits_ptr), bytes_per_desc, C.c_int64(n),
+                                        C.c_void_p(out_ptr), C.c_void_p(stream)))
+
+    def knn_device(self, q_ptr, n, k, idx_ptr, dist_ptr, stream=0):
+        _check(lib().mlc_knn_device(self._h, C.c_void_p(q_ptr), C.c_int64(n), k, C.c_void_p(idx_ptr),
+                                    C.c_void_p(dist_ptr), C.c_void_p(stream)))
+
+    def merge_topk_device(self, idx_lists_ptr, dist_lists_ptr, num_lists, n, k, idx_ptr, dist_ptr,
+                          stream=0):
+        _check(lib().mlc_merge_topk_device(self._h, C.c_void_p(idx_lists_ptr),
+                                           C.c_void_p(dist_lists_ptr), num_lists, C.c_int64(n), k,
+                                           C.c_void_p(idx_ptr), C.c_void_p(dist_ptr),
+                                           C.c_void_p(stream)))
+
+    def find_batch(self, frames, proj=None, bits=None, capacity=None):
+        """Returns (matches[MATCH_DTYPE], offsets[num_vertices+1])."""
+        frames = np.ascontiguousarray(frames, FRAME_DTYPE)
+        nf = len(frames)
+        total = int(frames["num_descriptors"].sum())
+        k = max(self.num_neighbors(), 1)
+        cap = capacity if capacity is not None else total * k + 16
+        matches = np.zeros(cap, MATCH_DTYPE)
+        offsets = np.zeros(nf + 1, np.int64)
+        nv, nm = C.c_int64(), C.c_int64()
+        if bits is not None:
+            bits = np.ascontiguousarray(bits, np.uint8)
+            assert bits.shape[0] == total
+            _check(lib().mlc_find_batch_bits(self._h, _ptr(frames), C.c_int64(nf), _ptr(bits),
+                                             bits.shape[1], _ptr(matches), C.c_int64(cap),
+                                             _ptr(offsets), C.byref(nv), C.byref(nm)))
+        else:
+            proj = np.ascontiguousarray(proj, np.float32).reshape(-1, self.dim)
+            assert proj.shape[0] == total
+            _check(lib().mlc_find_batch(self._h, _ptr(frames), C.c_int64(nf), _ptr(proj),
+                                        _ptr(matches), C.c_int64(cap), _ptr(offsets), C.byref(nv),
+                                        C.byref(nm)))
+        if nm.value > cap:
+            raise MlcError(f"match capacity {cap} too small for {nm.value} matches")
+        return matches[:nm.value], offsets[:nv.value + 1]
+
+    def pnp_ransac_batch(self, cams, offsets, keypoints, camera_index, keypoint_index, landmarks,
+                         rs=None, want_flags=True):
+        rs = rs or default_ransac_settings()
+        cams = np.ascontiguousarray(cams, CAMERA_DTYPE)
+        offsets = np.ascontiguousarray(offsets, np.int64)
+        nprob = len(offsets) - 1
+        kp = np.ascontiguousarray(keypoints, np.float64).reshape(-1, 2)
+        ci = np.ascontiguousarray(camera_index, np.int32)
+        ki = np.ascontiguousarray(keypoint_index, np.int32)
+        lm = np.ascontiguousarray(landmarks, np.float64).reshape(-1, 3)
+        res = np.zeros(nprob, POSE_DTYPE)
+        flags = np.zeros(max(len(ci), 1), np.uint8) if want_flags else None
+        _check(lib().mlc_pnp_ransac_batch(self._h, C.byref(rs), _ptr(cams), len(cams),
+                                          C.c_int64(nprob), _ptr(offsets), _ptr(kp), _ptr(ci),
+                                          _ptr(ki), _ptr(lm), _ptr(res),
+                                          _ptr(flags) if flags is not None else C.c_void_p(0)))
+        return res, (flags[:len(ci)] if flags is not None else None)

@@ -1,0 +1,187 @@
+// extern "C" surface of libmaplab_lc_b200.so (include/maplab_lc_b200.h).
+#include <cstring>
+#include <new>
+#include <string>
+
+#include "../../include/maplab_lc_b200.h"
+#include "detector.h"
+
+struct mlc_detector {
+  mlc::Detector impl;
+};
+
+namespace {
+thread_local std::string g_last_error;
+int Fail(const std::string& msg) {
+  g_last_error = msg;
+  return 1;
+}
+#define MLC_REQUIRE(cond, msg) \
+  do {                         \
+    if (!(cond)) return Fail(msg); \
+  } while (0)
+}  // namespace
+
+extern "C" {
+
+const char* mlc_last_error(void) { return g_last_error.c_str(); }
+int mlc_version(void) { return 100; }
+uint64_t mlc_kernel_launch_count(void) { return mlc::g_kernel_launches.load(); }
+
+void mlc_default_settings(mlc_settings* s) {
+  s->num_closest_words = 10;
+  s->num_nearest_neighbors = -1;
+  s->scoring = 0;
+  s->engine = 0;
+  s->min_image_time_seconds = 10.0;
+  s->min_verify_matches_num = 10;
+  s->fraction_best_scores = 0.25f;
+  s->knn_epsilon = 2.0f;
+  s->knn_max_radius = 20.0f;
+  s->device = -1;
+  s->shard_rank = 0;
+  s->shard_count = 1;
+}
+
+void mlc_default_ransac_settings(mlc_ransac_settings* s) {
+  s->min_inlier_count = 10;
+  s->num_ransac_iters = 100;
+  s->min_inlier_ratio = 0.0;
+  s->ransac_pixel_sigma = 2.0;
+  s->seed = 12345u;
+  s->rng_mapping = 1;
+}
+
+int mlc_create(const mlc_settings* settings, const void* vocab_blob, size_t vocab_size,
+               mlc_detector** out) {
+  MLC_REQUIRE(settings && vocab_blob && out, "mlc_create: null argument");
+  *out = nullptr;
+  mlc_detector* d = new (std::nothrow) mlc_detector();
+  MLC_REQUIRE(d, "out of memory");
+  std::string err;
+  if (!d->impl.Create(*settings, vocab_blob, vocab_size, &err)) {
+    delete d;
+    return Fail(err);
+  }
+  *out = d;
+  return 0;
+}
+
+void mlc_destroy(mlc_detector* d) { delete d; }
+
+int mlc_clear(mlc_detector* d) {
+  MLC_REQUIRE(d, "null detector");
+  std::string err;
+  return d->impl.Clear(&err) ? 0 : Fail(err);
+}
+int64_t mlc_num_entries(const mlc_detector* d) { return d ? d->impl.NumEntries() : -1; }
+int64_t mlc_num_descriptors(const mlc_detector* d) { return d ? d->impl.NumDescriptors() : -1; }
+int mlc_num_neighbors(const mlc_detector* d) { return d ? d->impl.NumNeighbors() : -1; }
+int mlc_target_dim(const mlc_detector* d) { return d ? d->impl.dim() : -1; }
+
+int mlc_project(mlc_detector* d, const uint8_t* bits, int bytes_per_desc, int64_t n, float* out) {
+  MLC_REQUIRE(d && (n == 0 || (bits && out)), "mlc_project: null argument");
+  std::string err;
+  return d->impl.Project(bits, bytes_per_desc, n, out, &err) ? 0 : Fail(err);
+}
+int mlc_project_device(mlc_detector* d, const uint8_t* d_bits, int bytes_per_desc, int64_t n,
+                       float* d_out, void* stream) {
+  MLC_REQUIRE(d && (n == 0 || (d_bits && d_out)), "mlc_project_device: null argument");
+  MLC_REQUIRE(bytes_per_desc > 0 && bytes_per_desc % 16 == 0, "bytes per descriptor must be a multiple of 16");
+  std::string err;
+  return d->impl.ProjectDevice(d_bits, bytes_per_desc, n, d_out, static_cast<cudaStream_t>(stream), &err)
+             ? 0
+             : Fail(err);
+}
+
+int mlc_insert(mlc_detector* d, const mlc_frame* frame, const float* proj, const int64_t* landmarks) {
+  return mlc_insert_batch(d, frame, 1, proj, landmarks);
+}
+int mlc_insert_batch(mlc_detector* d, const mlc_frame* frames, int64_t num_frames, const float* proj,
+                     const int64_t* landmarks) {
+  MLC_REQUIRE(d && frames && num_frames >= 0, "mlc_insert: null argument");
+  std::string err;
+  return d->impl.InsertBatch(frames, num_frames, proj, landmarks, &err) ? 0 : Fail(err);
+}
+int mlc_initialize(mlc_detector* d) {
+  MLC_REQUIRE(d, "null detector");
+  std::string err;
+  return d->impl.Initialize(&err) ? 0 : Fail(err);
+}
+
+int mlc_knn(mlc_detector* d, const float* q, int64_t n_q, int k, int32_t* idx, float* dist) {
+  MLC_REQUIRE(d && (n_q == 0 || (q && idx && dist)), "mlc_knn: null argument");
+  std::string err;
+  return d->impl.Knn(q, n_q, k, idx, dist, &err) ? 0 : Fail(err);
+}
+int mlc_knn_device(mlc_detector* d, const float* d_q, int64_t n_q, int k, int32_t* d_idx,
+                   float* d_dist, void* stream) {
+  MLC_REQUIRE(d && (n_q == 0 || (d_q && d_idx && d_dist)), "mlc_knn_device: null argument");
+  std::string err;
+  return d->impl.KnnDevice(d_q, n_q, k, d_idx, d_dist, static_cast<cudaStream_t>(stream), &err)
+             ? 0
+             : Fail(err);
+}
+int mlc_coarse_cells(mlc_detector* d, const float* q, int64_t n, int nw, int32_t* cells) {
+  MLC_REQUIRE(d && (n == 0 || (q && cells)), "mlc_coarse_cells: null argument");
+  std::string err;
+  return d->impl.CoarseCells(q, n, nw, cells, &err) ? 0 : Fail(err);
+}
+int mlc_merge_topk_device(mlc_detector* d, const int32_t* d_idx_lists, const float* d_dist_lists,
+                          int num_lists, int64_t n_q, int k, int32_t* d_idx, float* d_dist,
+                          void* stream) {
+  MLC_REQUIRE(d && d_idx_lists && d_dist_lists && d_idx && d_dist, "mlc_merge_topk_device: null argument");
+  std::string err;
+  return d->impl.MergeTopkDevice(d_idx_lists, d_dist_lists, num_lists, n_q, k, d_idx, d_dist,
+                                 static_cast<cudaStream_t>(stream), &err)
+             ? 0
+             : Fail(err);
+}
+int mlc_last_scan_stats(mlc_detector* d, uint64_t* algorithmic_bytes, uint64_t* entries_scanned,
+                        double* scan_kernel_ms) {
+  MLC_REQUIRE(d && algorithmic_bytes && entries_scanned && scan_kernel_ms, "null argument");
+  std::string err;
+  return d->impl.LastScanStats(algorithmic_bytes, entries_scanned, scan_kernel_ms, &err) ? 0 : Fail(err);
+}
+
+int mlc_find_batch(mlc_detector* d, const mlc_frame* frames, int64_t num_frames, const float* proj,
+                   mlc_match* matches, int64_t capacity, int64_t* match_offsets,
+                   int64_t* num_vertices, int64_t* num_matches) {
+  MLC_REQUIRE(d && num_vertices && num_matches && (num_frames == 0 || (frames && match_offsets)),
+              "mlc_find_batch: null argument");
+  std::string err;
+  return d->impl.FindBatch(frames, num_frames, proj, nullptr, 0, matches, capacity, match_offsets,
+                           num_vertices, num_matches, &err)
+             ? 0
+             : Fail(err);
+}
+int mlc_find_batch_bits(mlc_detector* d, const mlc_frame* frames, int64_t num_frames,
+                        const uint8_t* bits, int bytes_per_desc, mlc_match* matches,
+                        int64_t capacity, int64_t* match_offsets, int64_t* num_vertices,
+                        int64_t* num_matches) {
+  MLC_REQUIRE(d && num_vertices && num_matches && (num_frames == 0 || (frames && match_offsets)),
+              "mlc_find_batch_bits: null argument");
+  MLC_REQUIRE(bytes_per_desc > 0 && bytes_per_desc % 16 == 0, "bytes per descriptor must be a multiple of 16");
+  std::string err;
+  return d->impl.FindBatch(frames, num_frames, nullptr, bits, bytes_per_desc, matches, capacity,
+                           match_offsets, num_vertices, num_matches, &err)
+             ? 0
+             : Fail(err);
+}
+
+int mlc_pnp_ransac_batch(mlc_detector* d, const mlc_ransac_settings* rs, const mlc_camera* cams,
+                         int num_cams, int64_t num_problems, const int64_t* offsets,
+                         const double* keypoints, const int32_t* camera_index,
+                         const int32_t* keypoint_index, const double* landmarks,
+                         mlc_pose_result* results, uint8_t* inlier_flags) {
+  MLC_REQUIRE(d && rs && cams && num_cams > 0 && num_problems >= 0, "mlc_pnp_ransac_batch: bad argument");
+  MLC_REQUIRE(num_problems == 0 || (offsets && keypoints && camera_index && keypoint_index && landmarks && results),
+              "mlc_pnp_ransac_batch: null argument");
+  std::string err;
+  return d->impl.PnpRansacBatch(*rs, cams, num_cams, num_problems, offsets, keypoints, camera_index,
+                                keypoint_index, landmarks, results, inlier_flags, &err)
+             ? 0
+             : Fail(err);
+}
+
+}  // extern "C"

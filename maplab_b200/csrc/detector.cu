@@ -1,0 +1,383 @@
+#include "detector.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+namespace mlc {
+
+std::atomic<uint64_t> g_kernel_launches{0};
+
+namespace {
+size_t Align16(size_t x) { return (x + 15) & ~static_cast<size_t>(15); }
+}  // namespace
+
+bool Detector::Cuda(cudaError_t e, const char* what, std::string* err) const {
+  if (e == cudaSuccess) return true;
+  *err = std::string(what) + ": " + cudaGetErrorString(e);
+  return false;
+}
+
+Detector::~Detector() {
+  if (d_tree_blob_) cudaFree(d_tree_blob_);
+  if (proj_.b_image) cudaFree(proj_.b_image);
+  lists_.Free();
+  DevBuf* bufs[] = {&d_db_cells_, &d_desc_kf_, &d_desc_lm_, &d_kf_meta_, &d_q_,    &d_cells_,
+                    &d_idx_,      &d_dist_,    &d_bits_,    &d_stats_};
+  for (DevBuf* b : bufs) b->Free();
+  for (DevBuf& b : d_covis_) b.Free();
+  if (ev0_) cudaEventDestroy(ev0_);
+  if (ev1_) cudaEventDestroy(ev1_);
+  if (stream_) cudaStreamDestroy(stream_);
+}
+
+bool Detector::Create(const mlc_settings& s, const void* blob, size_t size, std::string* err) {
+  s_ = s;
+  if (s_.shard_count <= 0) s_.shard_count = 1;
+  if (s_.shard_rank < 0 || s_.shard_rank >= s_.shard_count) {
+    *err = "shard_rank out of range";
+    return false;
+  }
+  if (s_.num_closest_words <= 0 || s_.num_closest_words > 16) {
+    *err = "num_closest_words must be in 1..16";
+    return false;
+  }
+  if (s_.engine != 0) {
+    *err = "detector engine not built: only 'imi' (0) is available in this build";
+    return false;
+  }
+  if (!vocab_.Parse(blob, size, s_.engine == 1, err)) return false;
+  if (vocab_.target_dim / 2 > 8) {
+    *err = "target dimensionality > 16 is not supported";
+    return false;
+  }
+  int count = 0;
+  if (!Cuda(cudaGetDeviceCount(&count), "cudaGetDeviceCount", err)) return false;
+  if (count == 0) {
+    *err = "no CUDA device: the B200 loop-closure path has no CPU fallback";
+    return false;
+  }
+  if (s_.device >= 0) {
+    if (!Cuda(cudaSetDevice(s_.device), "cudaSetDevice", err)) return false;
+  }
+  if (!Cuda(cudaGetDevice(&device_), "cudaGetDevice", err)) return false;
+  cudaDeviceProp prop;
+  if (!Cuda(cudaGetDeviceProperties(&prop, device_), "cudaGetDeviceProperties", err)) return false;
+  if (prop.major != 10) {
+    *err = "device is not sm_100 (Blackwell B200); kernels are built for sm_100a only";
+    return false;
+  }
+  sm_count_ = prop.multiProcessorCount;
+  if (!Cuda(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking), "cudaStreamCreate", err))
+    return false;
+  if (!Cuda(cudaEventCreate(&ev0_), "cudaEventCreate", err)) return false;
+  if (!Cuda(cudaEventCreate(&ev1_), "cudaEventCreate", err)) return false;
+
+  fp_.Build(vocab_.projection, vocab_.target_dim);
+  if (fp_.kp <= 512 && fp_.dim <= 12) {
+    if (!Cuda(BuildProjectionDevice(fp_, &proj_), "BuildProjectionDevice", err)) return false;
+  }
+  tree1_.Build(vocab_.words1);
+  tree2_.Build(vocab_.words2);
+  if (tree1_.max_depth > 47 || tree2_.max_depth > 47) {
+    *err = "vocabulary kd-tree deeper than the device traversal stack";
+    return false;
+  }
+  return UploadTrees(err);
+}
+
+bool Detector::UploadTrees(std::string* err) {
+  CoarseParams& c = coarse_;
+  size_t off = 0;
+  auto place = [&](size_t bytes) {
+    const size_t at = off;
+    off = Align16(off + bytes);
+    return static_cast<uint32_t>(at);
+  };
+  c.off_nodes1 = place(tree1_.nodes.size() * sizeof(KdNodeDev));
+  c.off_buckets1 = place(tree1_.bucket_points.size() * 4);
+  c.off_cloud1 = place(tree1_.cloud.size() * 4);
+  c.off_nodes2 = place(tree2_.nodes.size() * sizeof(KdNodeDev));
+  c.off_buckets2 = place(tree2_.bucket_points.size() * 4);
+  c.off_cloud2 = place(tree2_.cloud.size() * 4);
+  c.packed_bytes = static_cast<uint32_t>(off);
+  std::vector<unsigned char> blob(off, 0);
+  std::memcpy(blob.data() + c.off_nodes1, tree1_.nodes.data(), tree1_.nodes.size() * sizeof(KdNodeDev));
+  std::memcpy(blob.data() + c.off_buckets1, tree1_.bucket_points.data(), tree1_.bucket_points.size() * 4);
+  std::memcpy(blob.data() + c.off_cloud1, tree1_.cloud.data(), tree1_.cloud.size() * 4);
+  std::memcpy(blob.data() + c.off_nodes2, tree2_.nodes.data(), tree2_.nodes.size() * sizeof(KdNodeDev));
+  std::memcpy(blob.data() + c.off_buckets2, tree2_.bucket_points.data(), tree2_.bucket_points.size() * 4);
+  std::memcpy(blob.data() + c.off_cloud2, tree2_.cloud.data(), tree2_.cloud.size() * 4);
+  if (!Cuda(cudaMalloc(&d_tree_blob_, off), "cudaMalloc(trees)", err)) return false;
+  if (!Cuda(cudaMemcpy(d_tree_blob_, blob.data(), off, cudaMemcpyHostToDevice), "upload trees", err))
+    return false;
+  const unsigned char* base = static_cast<const unsigned char*>(d_tree_blob_);
+  c.packed = d_tree_blob_;
+  c.nodes1 = reinterpret_cast<const KdNodeDev*>(base + c.off_nodes1);
+  c.buckets1 = reinterpret_cast<const int32_t*>(base + c.off_buckets1);
+  c.cloud1 = reinterpret_cast<const float*>(base + c.off_cloud1);
+  c.nodes2 = reinterpret_cast<const KdNodeDev*>(base + c.off_nodes2);
+  c.buckets2 = reinterpret_cast<const int32_t*>(base + c.off_buckets2);
+  c.cloud2 = reinterpret_cast<const float*>(base + c.off_cloud2);
+  c.sub_dim = vocab_.target_dim / 2;
+  c.num_words1 = vocab_.words1.cols;
+  c.num_words2 = vocab_.words2.cols;
+  c.max_radius2 = s_.knn_max_radius * s_.knn_max_radius;
+  c.max_error2 = (1 + s_.knn_epsilon) * (1 + s_.knn_epsilon);
+  c.stage_in_smem = off <= 160 * 1024 ? 1 : 0;
+  return true;
+}
+
+bool Detector::Clear(std::string* err) {
+  std::lock_guard<std::recursive_mutex> lock(mu_);
+  keyframes_.clear();
+  desc_.clear();
+  landmarks_.clear();
+  desc_kf_.clear();
+  lists_.Free();
+  index_dirty_ = true;
+  last_valid_ = false;
+  (void)err;
+  return true;
+}
+
+// getNumNeighborsToSearch, matching-based-engine.cc:319-338 (int size compared against doubles).
+int Detector::NumNeighbors() const {
+  int k = s_.num_nearest_neighbors;
+  if (k == -1) {
+    const int n = static_cast<int>(NumDescriptors());
+    if (n < 1e4)
+      k = 1;
+    else if (n < 1e5)
+      k = 2;
+    else if (n < 1e6)
+      k = 3;
+    else if (n < 1e7)
+      k = 6;
+    else
+      k = 8;
+  }
+  return k;
+}
+
+bool Detector::ProjectDevice(const uint8_t* d_bits, int bytes_per_desc, int64_t n, float* d_out,
+                             cudaStream_t stream, std::string* err) {
+  if (!proj_.b_image) {
+    *err = "projection matrix shape unsupported by the tensor-core kernel (need <= 512 columns, <= 12 rows)";
+    return false;
+  }
+  // ProjectDescriptorBlock: CHECK the matrix consumes no more bits than a descriptor has
+  // (471-column FREAK matrices use the first 471 of 512 bits, descriptor-projection.cc:35-43).
+  if (bytes_per_desc * 8 < proj_.kp) {
+    *err = "descriptor shorter than the projection matrix";
+    return false;
+  }
+  return Cuda(LaunchProjection(proj_, d_bits, bytes_per_desc, n, d_out, sm_count_, stream),
+              "projection kernel", err);
+}
+
+bool Detector::Project(const uint8_t* bits, int bytes_per_desc, int64_t n, float* out,
+                       std::string* err) {
+  std::lock_guard<std::recursive_mutex> lock(mu_);
+  if (n == 0) return true;  // descriptor-projection.cc:20-22
+  if (n < 0 || bytes_per_desc <= 0 || bytes_per_desc % 16 != 0) {
+    *err = "bad descriptor block shape (bytes per descriptor must be a multiple of 16)";
+    return false;
+  }
+  const size_t in_bytes = static_cast<size_t>(n) * bytes_per_desc;
+  const size_t out_bytes = static_cast<size_t>(n) * dim() * sizeof(float);
+  if (!Cuda(d_bits_.Reserve(in_bytes), "alloc bits", err)) return false;
+  if (!Cuda(d_q_.Reserve(out_bytes), "alloc proj", err)) return false;
+  if (!Cuda(cudaMemcpyAsync(d_bits_.p, bits, in_bytes, cudaMemcpyHostToDevice, stream_), "H2D bits", err))
+    return false;
+  if (!ProjectDevice(d_bits_.as<uint8_t>(), bytes_per_desc, n, d_q_.as<float>(), stream_, err))
+    return false;
+  if (!Cuda(cudaMemcpyAsync(out, d_q_.p, out_bytes, cudaMemcpyDeviceToHost, stream_), "D2H proj", err))
+    return false;
+  return Cuda(cudaStreamSynchronize(stream_), "projection", err);
+}
+
+bool Detector::InsertBatch(const mlc_frame* frames, int64_t num_frames, const float* proj,
+                           const int64_t* landmarks, std::string* err) {
+  std::lock_guard<std::recursive_mutex> lock(mu_);
+  const int d = dim();
+  int64_t total = 0;
+  for (int64_t f = 0; f < num_frames; ++f) {
+    if (frames[f].num_descriptors < 0) {
+      *err = "negative descriptor count";
+      return false;
+    }
+    total += frames[f].num_descriptors;
+  }
+  if (NumDescriptors() + total > 2147483647LL) {
+    *err = "descriptor indices are int (SURVEY H7): database would exceed 2^31-1 descriptors";
+    return false;
+  }
+  int64_t at = 0;
+  for (int64_t f = 0; f < num_frames; ++f) {
+    KeyframeMeta m;
+    m.ts = frames[f].timestamp_ns;
+    m.vertex = frames[f].vertex_id;
+    m.mission = frames[f].mission_id;
+    m.frame_index = frames[f].frame_index;
+    m.first_descriptor = static_cast<int32_t>(desc_kf_.size());
+    m.num_descriptors = frames[f].num_descriptors;
+    const int32_t kf_number = static_cast<int32_t>(keyframes_.size());
+    keyframes_.push_back(m);
+    desc_kf_.insert(desc_kf_.end(), m.num_descriptors, kf_number);
+    for (int i = 0; i < m.num_descriptors; ++i)
+      landmarks_.push_back(landmarks ? landmarks[at + i] : -1);
+    at += m.num_descriptors;
+  }
+  desc_.insert(desc_.end(), proj, proj + static_cast<size_t>(total) * d);
+  index_dirty_ = true;
+  return true;
+}
+
+bool Detector::Initialize(std::string* err) {
+  std::lock_guard<std::recursive_mutex> lock(mu_);
+  return EnsureIndex(err);
+}
+
+// Build the device index: cell of every descriptor = FindClosestWords(desc, 1) (kernel 2a with one
+// word), then cell-sorted block-SoA lists of this shard's descriptors.
+bool Detector::EnsureIndex(std::string* err) {
+  if (!index_dirty_) return true;
+  const int64_t n = NumDescriptors();
+  const int d = dim();
+  const uint64_t cells64 = static_cast<uint64_t>(vocab_.words1.cols) * vocab_.words2.cols;
+  if (cells64 > (1ull << 28)) {
+    *err = "too many cells for the dense cell table";
+    return false;
+  }
+  float* d_desc = nullptr;
+  if (n > 0) {
+    if (!Cuda(cudaMalloc(&d_desc, static_cast<size_t>(n) * d * 4), "alloc db descriptors", err))
+      return false;
+    if (!Cuda(cudaMemcpyAsync(d_desc, desc_.data(), static_cast<size_t>(n) * d * 4,
+                              cudaMemcpyHostToDevice, stream_),
+              "H2D db descriptors", err))
+      return false;
+    if (!Cuda(d_db_cells_.Reserve(static_cast<size_t>(n) * 4), "alloc cells", err)) return false;
+    if (!Cuda(LaunchCoarseWords(coarse_, d_desc, n, 1, d_db_cells_.as<int32_t>(), sm_count_, stream_),
+              "cell assignment", err))
+      return false;
+  }
+  bool ok = Cuda(BuildImiLists(d_db_cells_.as<int32_t>(), d_desc, n, d, static_cast<uint32_t>(cells64),
+                               s_.shard_rank, s_.shard_count, &lists_, stream_),
+                 "build inverted lists", err);
+  if (d_desc) cudaFree(d_desc);
+  if (!ok) return false;
+  // metadata replicas for voting / clustering (kernel 3)
+  if (n > 0) {
+    if (!Cuda(d_desc_kf_.Reserve(static_cast<size_t>(n) * 4), "alloc", err)) return false;
+    if (!Cuda(d_desc_lm_.Reserve(static_cast<size_t>(n) * 8), "alloc", err)) return false;
+    if (!Cuda(d_kf_meta_.Reserve(keyframes_.size() * sizeof(KeyframeMeta)), "alloc", err)) return false;
+    if (!Cuda(cudaMemcpyAsync(d_desc_kf_.p, desc_kf_.data(), static_cast<size_t>(n) * 4,
+                              cudaMemcpyHostToDevice, stream_), "H2D", err)) return false;
+    if (!Cuda(cudaMemcpyAsync(d_desc_lm_.p, landmarks_.data(), static_cast<size_t>(n) * 8,
+                              cudaMemcpyHostToDevice, stream_), "H2D", err)) return false;
+    if (!Cuda(cudaMemcpyAsync(d_kf_meta_.p, keyframes_.data(), keyframes_.size() * sizeof(KeyframeMeta),
+                              cudaMemcpyHostToDevice, stream_), "H2D", err)) return false;
+  }
+  if (!Cuda(cudaStreamSynchronize(stream_), "index build", err)) return false;
+  index_dirty_ = false;
+  return true;
+}
+
+bool Detector::KnnDevice(const float* d_q, int64_t n_q, int k, int32_t* d_idx, float* d_dist,
+                         cudaStream_t stream, std::string* err) {
+  std::lock_guard<std::recursive_mutex> lock(mu_);
+  if (k <= 0 || k > 16) {
+    *err = "k must be in 1..16";
+    return false;
+  }
+  if (!EnsureIndex(err)) return false;
+  if (n_q == 0) return true;
+  const int nw = s_.num_closest_words;
+  if (!Cuda(d_cells_.Reserve(static_cast<size_t>(n_q) * nw * 4), "alloc visit list", err)) return false;
+  if (!Cuda(LaunchCoarseWords(coarse_, d_q, n_q, nw, d_cells_.as<int32_t>(), sm_count_, stream),
+            "coarse word search", err))
+    return false;
+  cudaEventRecord(ev0_, stream);
+  if (!Cuda(LaunchImiScan(dim(), d_q, n_q, d_cells_.as<int32_t>(), nw, lists_.cell_info, lists_.lists,
+                          k, d_idx, d_dist, sm_count_, stream),
+            "list scan", err))
+    return false;
+  cudaEventRecord(ev1_, stream);
+  last_nq_ = n_q;
+  last_nw_ = nw;
+  last_valid_ = true;
+  return true;
+}
+
+bool Detector::Knn(const float* q, int64_t n_q, int k, int32_t* idx, float* dist, std::string* err) {
+  std::lock_guard<std::recursive_mutex> lock(mu_);
+  if (n_q < 0) {
+    *err = "negative query count";
+    return false;
+  }
+  if (n_q == 0) return true;
+  const size_t qb = static_cast<size_t>(n_q) * dim() * 4, rb = static_cast<size_t>(n_q) * k * 4;
+  if (!Cuda(d_q_.Reserve(qb), "alloc", err) || !Cuda(d_idx_.Reserve(rb), "alloc", err) ||
+      !Cuda(d_dist_.Reserve(rb), "alloc", err))
+    return false;
+  if (!Cuda(cudaMemcpyAsync(d_q_.p, q, qb, cudaMemcpyHostToDevice, stream_), "H2D queries", err))
+    return false;
+  if (!KnnDevice(d_q_.as<float>(), n_q, k, d_idx_.as<int32_t>(), d_dist_.as<float>(), stream_, err))
+    return false;
+  if (!Cuda(cudaMemcpyAsync(idx, d_idx_.p, rb, cudaMemcpyDeviceToHost, stream_), "D2H", err)) return false;
+  if (!Cuda(cudaMemcpyAsync(dist, d_dist_.p, rb, cudaMemcpyDeviceToHost, stream_), "D2H", err)) return false;
+  return Cuda(cudaStreamSynchronize(stream_), "knn", err);
+}
+
+bool Detector::CoarseCells(const float* q, int64_t n, int nw, int32_t* cells, std::string* err) {
+  std::lock_guard<std::recursive_mutex> lock(mu_);
+  if (nw <= 0 || nw > 16 || n < 0) {
+    *err = "bad arguments";
+    return false;
+  }
+  if (n == 0) return true;
+  const size_t qb = static_cast<size_t>(n) * dim() * 4, cb = static_cast<size_t>(n) * nw * 4;
+  if (!Cuda(d_q_.Reserve(qb), "alloc", err) || !Cuda(d_cells_.Reserve(cb), "alloc", err)) return false;
+  if (!Cuda(cudaMemcpyAsync(d_q_.p, q, qb, cudaMemcpyHostToDevice, stream_), "H2D", err)) return false;
+  if (!Cuda(LaunchCoarseWords(coarse_, d_q_.as<float>(), n, nw, d_cells_.as<int32_t>(), sm_count_, stream_),
+            "coarse word search", err))
+    return false;
+  if (!Cuda(cudaMemcpyAsync(cells, d_cells_.p, cb, cudaMemcpyDeviceToHost, stream_), "D2H", err)) return false;
+  last_valid_ = false;
+  return Cuda(cudaStreamSynchronize(stream_), "coarse cells", err);
+}
+
+bool Detector::MergeTopkDevice(const int32_t* d_idx_lists, const float* d_dist_lists, int num_lists,
+                               int64_t n_q, int k, int32_t* d_idx, float* d_dist, cudaStream_t stream,
+                               std::string* err) {
+  return Cuda(LaunchMergeTopk(d_idx_lists, d_dist_lists, num_lists, n_q, k, d_idx, d_dist, stream),
+              "top-k merge", err);
+}
+
+bool Detector::LastScanStats(uint64_t* bytes, uint64_t* entries, double* ms, std::string* err) {
+  std::lock_guard<std::recursive_mutex> lock(mu_);
+  if (!last_valid_) {
+    *err = "no kNN call to report on";
+    return false;
+  }
+  if (!Cuda(d_stats_.Reserve(8), "alloc", err)) return false;
+  if (!Cuda(cudaMemsetAsync(d_stats_.p, 0, 8, stream_), "memset", err)) return false;
+  if (!Cuda(LaunchScanEntries(d_cells_.as<int32_t>(), last_nq_ * last_nw_, lists_.cell_info,
+                              d_stats_.as<unsigned long long>(), stream_),
+            "scan stats", err))
+    return false;
+  unsigned long long total = 0;
+  if (!Cuda(cudaMemcpyAsync(&total, d_stats_.p, 8, cudaMemcpyDeviceToHost, stream_), "D2H", err)) return false;
+  if (!Cuda(cudaStreamSynchronize(stream_), "scan stats", err)) return false;
+  float msf = 0.f;
+  cudaEventSynchronize(ev1_);
+  if (cudaEventElapsedTime(&msf, ev0_, ev1_) != cudaSuccess) msf = 0.f;
+  *entries = total;
+  *bytes = total * static_cast<uint64_t>(4 * (dim() + 1));
+  *ms = msf;
+  return true;
+}
+
+}  // namespace mlc

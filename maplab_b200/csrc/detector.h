@@ -1,0 +1,126 @@
+// Host-side engine of the B200 loop-closure path: the state behind the C-ABI handle. Mirrors
+// matching_based_loopclosure::LoopDetector (matching-based-loopclosure/src/matching-based-engine.cc)
+// with the database resident in HBM.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/maplab_lc_b200.h"
+#include "device_index.h"
+#include "vocabulary.h"
+
+namespace mlc {
+
+// Grow-only device buffer.
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t Reserve(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = bytes + bytes / 4 + 256;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void Free() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+  template <typename T>
+  T* as() const {
+    return static_cast<T*>(p);
+  }
+};
+
+struct KeyframeMeta {
+  int64_t ts, vertex, mission;
+  int32_t frame_index, first_descriptor, num_descriptors;
+};
+
+class Detector {
+ public:
+  Detector() = default;
+  ~Detector();
+  bool Create(const mlc_settings& s, const void* blob, size_t size, std::string* err);
+
+  bool Clear(std::string* err);
+  int64_t NumEntries() const { return static_cast<int64_t>(keyframes_.size()); }
+  int64_t NumDescriptors() const { return static_cast<int64_t>(desc_kf_.size()); }
+  int NumNeighbors() const;
+  int dim() const { return vocab_.target_dim; }
+
+  bool Project(const uint8_t* bits, int bytes_per_desc, int64_t n, float* out, std::string* err);
+  bool ProjectDevice(const uint8_t* d_bits, int bytes_per_desc, int64_t n, float* d_out,
+                     cudaStream_t stream, std::string* err);
+  bool InsertBatch(const mlc_frame* frames, int64_t num_frames, const float* proj,
+                   const int64_t* landmarks, std::string* err);
+  bool Initialize(std::string* err);
+  bool Knn(const float* q, int64_t n_q, int k, int32_t* idx, float* dist, std::string* err);
+  bool KnnDevice(const float* d_q, int64_t n_q, int k, int32_t* d_idx, float* d_dist,
+                 cudaStream_t stream, std::string* err);
+  bool CoarseCells(const float* q, int64_t n, int nw, int32_t* cells, std::string* err);
+  bool MergeTopkDevice(const int32_t* d_idx_lists, const float* d_dist_lists, int num_lists,
+                       int64_t n_q, int k, int32_t* d_idx, float* d_dist, cudaStream_t stream,
+                       std::string* err);
+  bool LastScanStats(uint64_t* bytes, uint64_t* entries, double* ms, std::string* err);
+  bool FindBatch(const mlc_frame* frames, int64_t num_frames, const float* proj,
+                 const uint8_t* bits, int bytes_per_desc, mlc_match* matches, int64_t capacity,
+                 int64_t* match_offsets, int64_t* num_vertices, int64_t* num_matches,
+                 std::string* err);
+  bool PnpRansacBatch(const mlc_ransac_settings& rs, const mlc_camera* cams, int num_cams,
+                      int64_t num_problems, const int64_t* offsets, const double* keypoints,
+                      const int32_t* camera_index, const int32_t* keypoint_index,
+                      const double* landmarks, mlc_pose_result* results, uint8_t* inlier_flags,
+                      std::string* err);
+
+ private:
+  bool Cuda(cudaError_t e, const char* what, std::string* err) const;
+  bool EnsureIndex(std::string* err);
+  bool UploadTrees(std::string* err);
+
+  mlc_settings s_{};
+  VocabularyFile vocab_;
+  FixedProjection fp_;
+  KdTreeHost tree1_, tree2_;
+  int device_ = 0, sm_count_ = 148;
+  cudaStream_t stream_ = nullptr;
+  cudaEvent_t ev0_ = nullptr, ev1_ = nullptr;
+  std::recursive_mutex mu_;  // queries are serialised on the detector's stream (SURVEY §8b Threading)
+
+  ProjectionDevice proj_;
+  void* d_tree_blob_ = nullptr;
+  CoarseParams coarse_{};
+
+  // database (host mirror of what Insert keeps, matching-based-engine.cc:227-251)
+  std::vector<KeyframeMeta> keyframes_;
+  std::vector<float> desc_;          // n x dim
+  std::vector<int64_t> landmarks_;   // n
+  std::vector<int32_t> desc_kf_;     // n: descriptor -> keyframe number
+  bool index_dirty_ = true;
+
+  // database (device)
+  DeviceLists lists_;
+  DevBuf d_db_cells_;    // int32 cell per descriptor (P2)
+  DevBuf d_desc_kf_;     // int32
+  DevBuf d_desc_lm_;     // int64
+  DevBuf d_kf_meta_;     // KeyframeMeta
+
+  // per-call scratch
+  DevBuf d_q_, d_cells_, d_idx_, d_dist_, d_bits_, d_stats_;
+  DevBuf d_covis_[8];
+  int64_t last_nq_ = 0;
+  int last_nw_ = 0;
+  bool last_valid_ = false;
+  double last_scan_ms_ = 0;
+  friend struct DetectorAccess;
+};
+
+}  // namespace mlc

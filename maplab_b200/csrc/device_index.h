@@ -1,0 +1,78 @@
+// Device-side data structures and kernel launchers of the B200 loop-closure path.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdint>
+
+#include "vocabulary.h"
+
+namespace mlc {
+
+// Launch counter (bench.py reports it as gpu_launches).
+extern std::atomic<uint64_t> g_kernel_launches;
+inline void CountLaunch() { g_kernel_launches.fetch_add(1, std::memory_order_relaxed); }
+
+// ---- kernel 2a -------------------------------------------------------------------------------
+// Both kd-trees live in one packed, 16-byte aligned device blob so that a CTA can stage them in
+// shared memory with one vectorised copy.
+struct CoarseParams {
+  const void* packed;
+  uint32_t packed_bytes;
+  uint32_t off_nodes1, off_buckets1, off_cloud1, off_nodes2, off_buckets2, off_cloud2;
+  const KdNodeDev *nodes1, *nodes2;  // global-memory views of the same blob
+  const int32_t *buckets1, *buckets2;
+  const float *cloud1, *cloud2;
+  int sub_dim, num_words1, num_words2;
+  float max_radius2, max_error2;
+  int stage_in_smem;
+};
+cudaError_t LaunchCoarseWords(const CoarseParams& p, const float* d_q, int64_t n, int num_words,
+                              int32_t* d_cells, int sm_count, cudaStream_t stream);
+
+// ---- kernel 2b -------------------------------------------------------------------------------
+// Inverted lists in HBM. Cell c owns `len` entries starting at byte 16 * start16 of `lists`:
+// consecutive blocks of 32 entries, each block stored as [dim + 1][block size] 32-bit words
+// (dim float rows, then the row of global descriptor indices); the last block of a cell holds
+// len % 32 entries. 4 * (dim + 1) bytes per entry (44 B at dim 10), cells padded to 16 B.
+struct DeviceLists {
+  uint2* cell_info = nullptr;  // {start16, len} per cell
+  uint32_t* lists = nullptr;
+  size_t list_bytes = 0;
+  uint32_t num_cells = 0;
+  int dim = 0;
+  void Free() {
+    if (cell_info) cudaFree(cell_info);
+    if (lists) cudaFree(lists);
+    cell_info = nullptr;
+    lists = nullptr;
+    list_bytes = 0;
+  }
+};
+cudaError_t BuildImiLists(const int32_t* d_cells, const float* d_desc, int64_t n, int dim,
+                          uint32_t num_cells, int shard_rank, int shard_count, DeviceLists* out,
+                          cudaStream_t stream);
+cudaError_t LaunchImiScan(int dim, const float* q, int64_t n_q, const int32_t* cells, int nw,
+                          const uint2* cell_info, const uint32_t* lists, int k, int32_t* out_idx,
+                          float* out_dist, int sm_count, cudaStream_t stream);
+cudaError_t LaunchScanEntries(const int32_t* cells, int64_t n_visits, const uint2* cell_info,
+                              unsigned long long* d_total, cudaStream_t stream);
+cudaError_t LaunchMergeTopk(const int32_t* idx_lists, const float* dist_lists, int num_lists,
+                            int64_t n_q, int k, int32_t* out_idx, float* out_dist,
+                            cudaStream_t stream);
+
+// ---- kernel 1 --------------------------------------------------------------------------------
+// B operand image of the projection GEMM: kProjNPad rows x (kp_padded bytes), already arranged in
+// the shared-memory core-matrix layout the kernel uses (see projection_kernel.cu).
+struct ProjectionDevice {
+  int8_t* b_image = nullptr;  // device
+  uint32_t b_bytes = 0;
+  int dim = 0;
+  int kp = 0;               // descriptor bits consumed
+  int32_t shift[16] = {0};  // per output dim
+};
+cudaError_t BuildProjectionDevice(const FixedProjection& fp, ProjectionDevice* out);
+cudaError_t LaunchProjection(const ProjectionDevice& pd, const uint8_t* d_bits, int bytes_per_desc,
+                             int64_t n, float* d_out, int sm_count, cudaStream_t stream);
+
+}  // namespace mlc

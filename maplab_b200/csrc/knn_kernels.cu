@@ -1,0 +1,704 @@
+// Kernel 2 of the loop-closure path: inverted-multi-index kNN.
+//   2a  coarse_words_kernel   — FindClosestWords: two ε-approximate kd-tree searches (libnabo
+//                               traversal order, fp32, no FMA contraction) + multi-sequence
+//                               (imilib/inverted-multi-index-common.h:84-134, :148-188;
+//                               nabo/kdtree_cpu.cpp:368-447, nabo/index_heap.h:263-363)
+//   2b  imi_scan_kernel       — InvertedMultiIndex::GetNNearestNeighbors: stream the visited
+//                               cells' inverted lists, squared L2 in the canonical fp32 order,
+//                               top-k by (distance, index) (imilib/inverted-multi-index.h:100-161,
+//                               inverted-multi-index-common.h:54-72)
+//   index build                — cell assignment (2a with one word), radix sort by cell, blocked
+//                               SoA inverted lists (imilib/inverted-multi-index.h:77-94)
+#include <cub/cub.cuh>
+
+#include "device_index.h"
+#include "ptx.cuh"
+
+namespace mlc {
+
+// =============================================================================================
+// 2a: coarse word search
+// =============================================================================================
+namespace {
+
+constexpr int kMaxSubDim = 8;
+constexpr int kMaxWords = 16;   // nw <= 16
+constexpr int kMaxStack = 96;   // 2 * max tree depth
+
+struct TreeView {
+  const KdNodeDev* nodes;
+  const int32_t* buckets;
+  const float* cloud;  // dim x n column-major
+};
+
+// libnabo IndexHeapBruteForceVector: ascending array, head = last element.
+struct LinearHeap {
+  int k;
+  int32_t idx[kMaxWords];
+  float val[kMaxWords];
+  __device__ void Reset() {
+    for (int i = 0; i < k; ++i) {
+      idx[i] = -1;
+      val[i] = __int_as_float(0x7f800000);
+    }
+  }
+  __device__ float Head() const { return val[k - 1]; }
+  __device__ void ReplaceHead(int index, float value) {
+    int i = k - 1;
+    for (; i > 0; --i) {
+      if (val[i - 1] > value) {
+        val[i] = val[i - 1];
+        idx[i] = idx[i - 1];
+      } else {
+        break;
+      }
+    }
+    val[i] = value;
+    idx[i] = index;
+  }
+};
+
+// Frame kinds of the explicit DFS stack.
+constexpr uint32_t kFrameFar = 1u << 30;      // deferred far-child test
+constexpr uint32_t kFrameRestore = 2u << 30;  // restore off[cd] after the far subtree
+
+// recurseKnn (allowSelfMatch, no statistics) as an explicit-stack DFS. The pruning test of a far
+// child is evaluated when its frame is popped, i.e. after the near subtree has been searched —
+// exactly when the recursive reference evaluates it.
+__device__ void KdKnn(const TreeView& t, int dim, const float* q, float max_radius2,
+                      float max_error2, LinearHeap* heap) {
+  heap->Reset();
+  float off[kMaxSubDim];
+#pragma unroll
+  for (int d = 0; d < kMaxSubDim; ++d) off[d] = 0.f;
+  uint32_t st_node[kMaxStack];
+  float st_rd[kMaxStack], st_new[kMaxStack], st_old[kMaxStack];
+  int sp = 0;
+  uint32_t n = 0;
+  float rd = 0.f;
+  bool descend = true;
+  for (;;) {
+    if (!descend) {
+      if (sp == 0) break;
+      --sp;
+      const uint32_t tag = st_node[sp];
+      const uint32_t cd = (tag >> 20) & 0xFu;
+      if (tag & kFrameRestore) {
+        off[cd] = st_old[sp];
+        continue;
+      }
+      // far child
+      const float frd = st_rd[sp];
+      if (!((frd <= max_radius2) && (__fmul_rn(frd, max_error2) < heap->Head()))) continue;
+      off[cd] = st_new[sp];
+      st_node[sp] = kFrameRestore | (cd << 20);  // st_old[sp] already holds the old offset
+      ++sp;
+      n = tag & 0xFFFFFu;
+      rd = frd;
+    }
+    descend = false;
+    // walk down to a leaf, deferring the far children
+    for (;;) {
+      const KdNodeDev node = t.nodes[n];
+      if (node.dim == static_cast<uint32_t>(dim)) {
+        const uint32_t bs = node.child_or_size;
+        for (uint32_t i = 0; i < bs; ++i) {
+          const int pidx = t.buckets[node.cut_or_bucket + i];
+          const float* p = t.cloud + static_cast<size_t>(pidx) * dim;
+          float dist = 0.f;
+          for (int j = 0; j < dim; ++j) {
+            const float diff = __fsub_rn(q[j], p[j]);
+            dist = __fadd_rn(dist, __fmul_rn(diff, diff));
+          }
+          if ((dist <= max_radius2) && (dist < heap->Head())) heap->ReplaceHead(pidx, dist);
+        }
+        break;
+      }
+      const uint32_t cd = node.dim;
+      const float old_off = off[cd];
+      const float new_off = __fsub_rn(q[cd], __uint_as_float(node.cut_or_bucket));
+      // rd += -old_off * old_off + new_off * new_off;
+      const float frd = __fadd_rn(
+          rd, __fadd_rn(__fmul_rn(-old_off, old_off), __fmul_rn(new_off, new_off)));
+      const uint32_t right = node.child_or_size;
+      uint32_t near_child, far_child;
+      if (new_off > 0.f) {
+        near_child = right;
+        far_child = n + 1;
+      } else {
+        near_child = n + 1;
+        far_child = right;
+      }
+      st_node[sp] = kFrameFar | (cd << 20) | far_child;
+      st_rd[sp] = frd;
+      st_new[sp] = new_off;
+      st_old[sp] = old_off;
+      ++sp;
+      n = near_child;
+    }
+  }
+}
+
+// MultiSequenceAlgorithm: pop the pairs (i1, i2) in ascending (d1[i1] + d2[i2], i1, i2).
+__device__ int MultiSequence(const LinearHeap& h1, const LinearHeap& h2, int num_words, int w2,
+                             int32_t* cells_out) {
+  const int n1 = h1.k, n2 = h2.k;
+  uint32_t used[(kMaxWords * kMaxWords) / 32];
+#pragma unroll
+  for (int i = 0; i < (kMaxWords * kMaxWords) / 32; ++i) used[i] = 0;
+  float pq_sum[kMaxWords + 4];
+  int pq_i1[kMaxWords + 4], pq_i2[kMaxWords + 4];
+  int pq_n = 0;
+  pq_sum[0] = __fadd_rn(h1.val[0], h2.val[0]);
+  pq_i1[0] = 0;
+  pq_i2[0] = 0;
+  pq_n = 1;
+  int emitted = 0;
+  while (pq_n > 0 && emitted < num_words) {
+    int best = 0;
+    for (int i = 1; i < pq_n; ++i) {
+      const bool less = (pq_sum[i] < pq_sum[best]) ||
+                        (!(pq_sum[best] < pq_sum[i]) &&
+                         ((pq_i1[i] < pq_i1[best]) ||
+                          (pq_i1[i] == pq_i1[best] && pq_i2[i] < pq_i2[best])));
+      if (less) best = i;
+    }
+    const int i1 = pq_i1[best], i2 = pq_i2[best];
+    --pq_n;
+    pq_sum[best] = pq_sum[pq_n];
+    pq_i1[best] = pq_i1[pq_n];
+    pq_i2[best] = pq_i2[pq_n];
+    const int word_index = i1 * n2 + i2;
+    used[word_index >> 5] |= 1u << (word_index & 31);
+    const int a = h1.idx[i1], b = h2.idx[i2];
+    // A pair with a missing word (fewer than nw words inside the radius) is skipped (-1).
+    cells_out[emitted++] = (a < 0 || b < 0) ? -1 : a * w2 + b;
+    if (i1 + 1 < n1) {
+      const int nb = word_index + n2 - 1;
+      if (i2 == 0 || ((used[nb >> 5] >> (nb & 31)) & 1u)) {
+        pq_sum[pq_n] = __fadd_rn(h1.val[i1 + 1], h2.val[i2]);
+        pq_i1[pq_n] = i1 + 1;
+        pq_i2[pq_n] = i2;
+        ++pq_n;
+      }
+    }
+    if (i2 + 1 < n2) {
+      const int nb = word_index - n2 + 1;
+      if (i1 == 0 || ((used[nb >> 5] >> (nb & 31)) & 1u)) {
+        pq_sum[pq_n] = __fadd_rn(h1.val[i1], h2.val[i2 + 1]);
+        pq_i1[pq_n] = i1;
+        pq_i2[pq_n] = i2 + 1;
+        ++pq_n;
+      }
+    }
+  }
+  return emitted;
+}
+
+__global__ void __launch_bounds__(128)
+coarse_words_kernel(CoarseParams p, const float* __restrict__ q, int64_t n, int num_words,
+                    int32_t* __restrict__ cells) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  TreeView t1{p.nodes1, p.buckets1, p.cloud1};
+  TreeView t2{p.nodes2, p.buckets2, p.cloud2};
+  if (p.stage_in_smem) {
+    // Stage both trees (nodes, buckets, word coordinates) in shared memory.
+    unsigned char* dst = smem_raw;
+    const unsigned char* src = reinterpret_cast<const unsigned char*>(p.packed);
+    for (uint32_t i = threadIdx.x * 16; i < p.packed_bytes; i += blockDim.x * 16)
+      *reinterpret_cast<uint4*>(dst + i) = *reinterpret_cast<const uint4*>(src + i);
+    __syncthreads();
+    t1.nodes = reinterpret_cast<const KdNodeDev*>(dst + p.off_nodes1);
+    t1.buckets = reinterpret_cast<const int32_t*>(dst + p.off_buckets1);
+    t1.cloud = reinterpret_cast<const float*>(dst + p.off_cloud1);
+    t2.nodes = reinterpret_cast<const KdNodeDev*>(dst + p.off_nodes2);
+    t2.buckets = reinterpret_cast<const int32_t*>(dst + p.off_buckets2);
+    t2.cloud = reinterpret_cast<const float*>(dst + p.off_cloud2);
+  }
+  const int dim = p.sub_dim;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    float qa[kMaxSubDim], qb[kMaxSubDim];
+    const float* qp = q + i * (2 * dim);
+#pragma unroll
+    for (int d = 0; d < kMaxSubDim; ++d) {
+      qa[d] = d < dim ? qp[d] : 0.f;
+      qb[d] = d < dim ? qp[dim + d] : 0.f;
+    }
+    LinearHeap h1, h2;
+    h1.k = min(p.num_words1, num_words);
+    h2.k = min(p.num_words2, num_words);
+    KdKnn(t1, dim, qa, p.max_radius2, p.max_error2, &h1);
+    KdKnn(t2, dim, qb, p.max_radius2, p.max_error2, &h2);
+    int32_t out[kMaxWords];
+    const int got = MultiSequence(h1, h2, num_words, p.num_words2, out);
+    int32_t* dst = cells + i * num_words;
+    for (int j = 0; j < num_words; ++j) dst[j] = j < got ? out[j] : -1;
+  }
+}
+
+}  // namespace
+
+cudaError_t LaunchCoarseWords(const CoarseParams& p, const float* d_q, int64_t n, int num_words,
+                              int32_t* d_cells, int sm_count, cudaStream_t stream) {
+  if (n <= 0) return cudaSuccess;
+  const int threads = 128;
+  const size_t smem = p.stage_in_smem ? p.packed_bytes : 0;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(coarse_words_kernel,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  int64_t blocks = (n + threads - 1) / threads;
+  const int64_t cap = static_cast<int64_t>(sm_count) * 8;
+  if (blocks > cap) blocks = cap;
+  coarse_words_kernel<<<static_cast<unsigned>(blocks), threads, smem, stream>>>(p, d_q, n, num_words,
+                                                                                d_cells);
+  CountLaunch();
+  return cudaGetLastError();
+}
+
+// =============================================================================================
+// 2b: inverted-list scan
+// =============================================================================================
+namespace {
+
+constexpr uint64_t kEmptyKey = 0x7f800000FFFFFFFFull;  // (+inf, idx -1): sorts after every entry
+
+// (stored - query).squaredNorm() in the canonical fp32 order of the oracle (packets of four
+// squared differences accumulated lane-wise, (l0+l1)+(l2+l3), scalar remainder added last).
+template <int DIM>
+__device__ __forceinline__ float SquaredDistanceCanonical(const float (&a)[DIM],
+                                                          const float (&b)[DIM]) {
+  constexpr int kVec = (DIM / 4) * 4;
+  if constexpr (kVec == 0) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < DIM; ++i) {
+      const float d = __fsub_rn(a[i], b[i]);
+      const float sq = __fmul_rn(d, d);
+      s = (i == 0) ? sq : __fadd_rn(s, sq);
+    }
+    return s;
+  } else {
+    float lane[4];
+#pragma unroll
+    for (int l = 0; l < 4; ++l) {
+      const float d = __fsub_rn(a[l], b[l]);
+      lane[l] = __fmul_rn(d, d);
+    }
+#pragma unroll
+    for (int p = 4; p < kVec; p += 4) {
+#pragma unroll
+      for (int l = 0; l < 4; ++l) {
+        const float d = __fsub_rn(a[p + l], b[p + l]);
+        lane[l] = __fadd_rn(lane[l], __fmul_rn(d, d));
+      }
+    }
+    float res = __fadd_rn(__fadd_rn(lane[0], lane[1]), __fadd_rn(lane[2], lane[3]));
+    if constexpr (kVec < DIM) {
+      float rem = 0.f;
+#pragma unroll
+      for (int i = kVec; i < DIM; ++i) {
+        const float d = __fsub_rn(a[i], b[i]);
+        const float sq = __fmul_rn(d, d);
+        rem = (i == kVec) ? sq : __fadd_rn(rem, sq);
+      }
+      res = __fadd_rn(res, rem);
+    }
+    return res;
+  }
+}
+
+// One warp per query descriptor. The visited cells' lists are flattened into one entry range and
+// dealt to the lanes 32 at a time; inside a block of the list the layout is [dim+1][block size]
+// words, so the 32 lanes of a full block read 128 contiguous bytes per dimension.
+template <int DIM, int KT>
+__global__ void __launch_bounds__(256)
+imi_scan_kernel(const float* __restrict__ q, int64_t n_q, const int32_t* __restrict__ cells, int nw,
+                const uint2* __restrict__ cell_info, const uint32_t* __restrict__ lists, int k,
+                int32_t* __restrict__ out_idx, float* __restrict__ out_dist) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp_global = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 5;
+  const int64_t warp_stride = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+  for (int64_t qi = warp_global; qi < n_q; qi += warp_stride) {
+    float qv[DIM];
+#pragma unroll
+    for (int d = 0; d < DIM; ++d) qv[d] = __ldg(q + qi * DIM + d);
+    uint32_t start16 = 0, len = 0;
+    if (lane < nw) {
+      const int32_t c = __ldg(cells + qi * nw + lane);
+      if (c >= 0) {
+        const uint2 info = __ldg(cell_info + c);
+        start16 = info.x;
+        len = info.y;
+      }
+    }
+    // inclusive prefix sum of list lengths over the (<= 16) cell lanes
+    uint32_t incl = len;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += v;
+    }
+    const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+    const uint32_t excl = incl - len;
+
+    uint64_t best[KT];
+#pragma unroll
+    for (int i = 0; i < KT; ++i) best[i] = kEmptyKey;
+
+    for (uint32_t base = 0; base < total; base += 32) {
+      const uint32_t e = base + lane;
+      // cell of entry e: number of cells whose inclusive prefix is <= e
+      int cell_lane = 0;
+      uint32_t c_excl = 0, c_start = 0, c_len = 0;
+#pragma unroll
+      for (int j = 0; j < kMaxWords; ++j) {
+        if (j < nw) {
+          const uint32_t inc_j = __shfl_sync(0xffffffffu, incl, j);
+          if (inc_j <= e) cell_lane = j + 1;
+        }
+      }
+      cell_lane = min(cell_lane, nw - 1);
+      c_excl = __shfl_sync(0xffffffffu, excl, cell_lane);
+      c_start = __shfl_sync(0xffffffffu, start16, cell_lane);
+      c_len = __shfl_sync(0xffffffffu, len, cell_lane);
+      if (e < total) {
+        const uint32_t within = e - c_excl;         // entry number inside its cell
+        const uint32_t blk = within >> 5;           // block of 32 entries
+        const uint32_t bs = min(32u, c_len - (blk << 5));
+        const uint32_t* w = lists + (static_cast<size_t>(c_start) << 2) +
+                            static_cast<size_t>(blk) * ((DIM + 1) * 32) + (within & 31u);
+        float sv[DIM];
+#pragma unroll
+        for (int d = 0; d < DIM; ++d) sv[d] = __uint_as_float(__ldg(w + d * bs));
+        const uint32_t id = __ldg(w + DIM * bs);
+        const float dist = SquaredDistanceCanonical<DIM>(sv, qv);
+        uint64_t key = (static_cast<uint64_t>(__float_as_uint(dist)) << 32) | id;
+        if (key < best[KT - 1]) {
+#pragma unroll
+          for (int i = 0; i < KT; ++i) {
+            const uint64_t lo = key < best[i] ? key : best[i];
+            const uint64_t hi = key < best[i] ? best[i] : key;
+            best[i] = lo;
+            key = hi;
+          }
+        }
+      }
+    }
+    // k rounds of warp arg-min over the lanes' heads
+    for (int r = 0; r < k; ++r) {
+      const uint32_t hd = static_cast<uint32_t>(best[0] >> 32);
+      const uint32_t hi_min = __reduce_min_sync(0xffffffffu, hd);
+      const uint32_t lo_cand = (hd == hi_min) ? static_cast<uint32_t>(best[0]) : 0xFFFFFFFFu;
+      const uint32_t lo_min = __reduce_min_sync(0xffffffffu, lo_cand);
+      const bool winner = (hd == hi_min) && (static_cast<uint32_t>(best[0]) == lo_min);
+      if (lane == 0) {
+        const bool empty = (hi_min == 0x7f800000u && lo_min == 0xFFFFFFFFu);
+        out_idx[qi * k + r] = empty ? -1 : static_cast<int32_t>(lo_min);
+        out_dist[qi * k + r] = __uint_as_float(hi_min);
+      }
+      if (winner && !(hi_min == 0x7f800000u && lo_min == 0xFFFFFFFFu)) {
+#pragma unroll
+        for (int i = 0; i + 1 < KT; ++i) best[i] = best[i + 1];
+        best[KT - 1] = kEmptyKey;
+      }
+    }
+  }
+}
+
+template <int DIM>
+cudaError_t LaunchScanDim(const float* q, int64_t n_q, const int32_t* cells, int nw,
+                          const uint2* cell_info, const uint32_t* lists, int k, int32_t* out_idx,
+                          float* out_dist, int sm_count, cudaStream_t stream) {
+  const int threads = 256;
+  int64_t blocks = (n_q * 32 + threads - 1) / threads;
+  const int64_t cap = static_cast<int64_t>(sm_count) * 32;
+  if (blocks > cap) blocks = cap;
+  const unsigned g = static_cast<unsigned>(blocks);
+#define MLC_SCAN(KT)                                                                         \
+  imi_scan_kernel<DIM, KT><<<g, threads, 0, stream>>>(q, n_q, cells, nw, cell_info, lists, k, \
+                                                      out_idx, out_dist)
+  if (k <= 1) MLC_SCAN(1);
+  else if (k <= 2) MLC_SCAN(2);
+  else if (k <= 4) MLC_SCAN(4);
+  else if (k <= 6) MLC_SCAN(6);
+  else if (k <= 8) MLC_SCAN(8);
+  else if (k <= 10) MLC_SCAN(10);
+  else MLC_SCAN(16);
+#undef MLC_SCAN
+  CountLaunch();
+  return cudaGetLastError();
+}
+
+}  // namespace
+
+cudaError_t LaunchImiScan(int dim, const float* q, int64_t n_q, const int32_t* cells, int nw,
+                          const uint2* cell_info, const uint32_t* lists, int k, int32_t* out_idx,
+                          float* out_dist, int sm_count, cudaStream_t stream) {
+  if (n_q <= 0) return cudaSuccess;
+  if (k > 16 || nw > kMaxWords) return cudaErrorInvalidValue;
+  switch (dim) {
+    case 10:
+      return LaunchScanDim<10>(q, n_q, cells, nw, cell_info, lists, k, out_idx, out_dist, sm_count,
+                               stream);
+    case 6:
+      return LaunchScanDim<6>(q, n_q, cells, nw, cell_info, lists, k, out_idx, out_dist, sm_count,
+                              stream);
+    case 4:
+      return LaunchScanDim<4>(q, n_q, cells, nw, cell_info, lists, k, out_idx, out_dist, sm_count,
+                              stream);
+    default:
+      return cudaErrorInvalidValue;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// scan statistics: algorithmic entries visited = sum over (query, cell) of the list length
+// ---------------------------------------------------------------------------------------------
+namespace {
+__global__ void scan_entries_kernel(const int32_t* __restrict__ cells, int64_t n_visits,
+                                    const uint2* __restrict__ cell_info,
+                                    unsigned long long* __restrict__ total) {
+  unsigned long long local = 0;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n_visits;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int32_t c = cells[i];
+    if (c >= 0) local += cell_info[c].y;
+  }
+  typedef cub::BlockReduce<unsigned long long, 256> Reduce;
+  __shared__ typename Reduce::TempStorage tmp;
+  const unsigned long long sum = Reduce(tmp).Sum(local);
+  if (threadIdx.x == 0 && sum) atomicAdd(total, sum);  // one per block; statistics only
+}
+}  // namespace
+
+cudaError_t LaunchScanEntries(const int32_t* cells, int64_t n_visits, const uint2* cell_info,
+                              unsigned long long* d_total, cudaStream_t stream) {
+  if (n_visits <= 0) return cudaSuccess;
+  int64_t blocks = (n_visits + 255) / 256;
+  if (blocks > 1184) blocks = 1184;
+  scan_entries_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(cells, n_visits, cell_info,
+                                                                         d_total);
+  CountLaunch();
+  return cudaGetLastError();
+}
+
+// =============================================================================================
+// cross-shard top-k merge (consumer of the all-gather)
+// =============================================================================================
+namespace {
+__global__ void merge_topk_kernel(const int32_t* __restrict__ idx_lists,
+                                  const float* __restrict__ dist_lists, int num_lists, int64_t n_q,
+                                  int k, int32_t* __restrict__ out_idx,
+                                  float* __restrict__ out_dist) {
+  const int64_t qi = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (qi >= n_q) return;
+  int head[16];
+  for (int l = 0; l < num_lists; ++l) head[l] = 0;
+  for (int r = 0; r < k; ++r) {
+    uint64_t best = kEmptyKey;
+    int best_l = -1;
+    for (int l = 0; l < num_lists; ++l) {
+      if (head[l] >= k) continue;
+      const size_t at = (static_cast<size_t>(l) * n_q + qi) * k + head[l];
+      const int32_t id = idx_lists[at];
+      if (id < 0) continue;  // missing neighbours are trailing
+      const uint64_t key =
+          (static_cast<uint64_t>(__float_as_uint(dist_lists[at])) << 32) | static_cast<uint32_t>(id);
+      if (key < best) {
+        best = key;
+        best_l = l;
+      }
+    }
+    if (best_l < 0) {
+      out_idx[qi * k + r] = -1;
+      out_dist[qi * k + r] = __int_as_float(0x7f800000);
+    } else {
+      out_idx[qi * k + r] = static_cast<int32_t>(best & 0xFFFFFFFFu);
+      out_dist[qi * k + r] = __uint_as_float(static_cast<uint32_t>(best >> 32));
+      ++head[best_l];
+    }
+  }
+}
+}  // namespace
+
+cudaError_t LaunchMergeTopk(const int32_t* idx_lists, const float* dist_lists, int num_lists,
+                            int64_t n_q, int k, int32_t* out_idx, float* out_dist,
+                            cudaStream_t stream) {
+  if (n_q <= 0) return cudaSuccess;
+  if (num_lists > 16) return cudaErrorInvalidValue;
+  const int threads = 128;
+  merge_topk_kernel<<<static_cast<unsigned>((n_q + threads - 1) / threads), threads, 0, stream>>>(
+      idx_lists, dist_lists, num_lists, n_q, k, out_idx, out_dist);
+  CountLaunch();
+  return cudaGetLastError();
+}
+
+// =============================================================================================
+// index build
+// =============================================================================================
+namespace {
+
+// cells of this shard's descriptors -> sort keys; descriptors of other shards get the key
+// `num_cells` (sorted to the end and ignored).
+__global__ void shard_keys_kernel(const int32_t* __restrict__ cells, int64_t n, int shard_rank,
+                                  int shard_count, uint32_t num_cells,
+                                  uint32_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+  const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (i >= n) return;
+  const int32_t c = cells[i];
+  const bool mine = (i % shard_count) == shard_rank && c >= 0;
+  keys[i] = mine ? static_cast<uint32_t>(c) : num_cells;
+  vals[i] = static_cast<uint32_t>(i);
+}
+
+// first/last position of every cell in the sorted key array (no atomics).
+__global__ void cell_bounds_kernel(const uint32_t* __restrict__ keys, int64_t n, uint32_t num_cells,
+                                   uint32_t* __restrict__ first, uint32_t* __restrict__ len) {
+  const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t c = keys[i];
+  if (c >= num_cells) return;
+  if (i == 0 || keys[i - 1] != c) first[c] = static_cast<uint32_t>(i);
+  if (i == n - 1 || keys[i + 1] != c) len[c] = static_cast<uint32_t>(i);  // last, fixed up below
+}
+__global__ void cell_sizes_kernel(uint32_t num_cells, const uint32_t* __restrict__ first,
+                                  uint32_t* __restrict__ len, int words_per_entry,
+                                  uint32_t* __restrict__ size16) {
+  const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= num_cells) return;
+  uint32_t l = 0;
+  if (first[c] != 0xFFFFFFFFu) l = len[c] - first[c] + 1;
+  len[c] = l;
+  size16[c] = (l * static_cast<uint32_t>(words_per_entry) * 4u + 15u) >> 4;
+}
+__global__ void cell_info_kernel(uint32_t num_cells, const uint32_t* __restrict__ start16,
+                                 const uint32_t* __restrict__ len, uint2* __restrict__ info) {
+  const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= num_cells) return;
+  info[c] = make_uint2(start16[c], len[c]);
+}
+// Scatter descriptor i into block-SoA position of its cell.
+__global__ void fill_lists_kernel(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals,
+                                  int64_t n, uint32_t num_cells, const uint32_t* __restrict__ first,
+                                  const uint2* __restrict__ info, const float* __restrict__ desc,
+                                  int dim, uint32_t* __restrict__ lists) {
+  const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t c = keys[i];
+  if (c >= num_cells) return;
+  const uint32_t within = static_cast<uint32_t>(i) - first[c];
+  const uint2 ci = info[c];
+  const uint32_t blk = within >> 5;
+  const uint32_t bs = min(32u, ci.y - (blk << 5));
+  uint32_t* w = lists + (static_cast<size_t>(ci.x) << 2) + static_cast<size_t>(blk) * ((dim + 1) * 32) +
+                (within & 31u);
+  const uint32_t id = vals[i];
+  const float* src = desc + static_cast<size_t>(id) * dim;
+  for (int d = 0; d < dim; ++d) w[d * bs] = __float_as_uint(src[d]);
+  w[dim * bs] = id;
+}
+
+}  // namespace
+
+#define MLC_CUDA_TRY(x)                \
+  do {                                 \
+    cudaError_t e__ = (x);             \
+    if (e__ != cudaSuccess) return e__; \
+  } while (0)
+
+cudaError_t BuildImiLists(const int32_t* d_cells, const float* d_desc, int64_t n, int dim,
+                          uint32_t num_cells, int shard_rank, int shard_count, DeviceLists* out,
+                          cudaStream_t stream) {
+  out->Free();
+  out->num_cells = num_cells;
+  out->dim = dim;
+  MLC_CUDA_TRY(cudaMalloc(&out->cell_info, sizeof(uint2) * static_cast<size_t>(num_cells)));
+  if (n == 0) {
+    MLC_CUDA_TRY(cudaMemsetAsync(out->cell_info, 0, sizeof(uint2) * static_cast<size_t>(num_cells),
+                                 stream));
+    MLC_CUDA_TRY(cudaMalloc(&out->lists, 16));
+    out->list_bytes = 0;
+    return cudaStreamSynchronize(stream);
+  }
+  uint32_t *keys = nullptr, *vals = nullptr, *keys_s = nullptr, *vals_s = nullptr;
+  uint32_t *first = nullptr, *len = nullptr, *size16 = nullptr, *start16 = nullptr;
+  void* tmp = nullptr;
+  size_t tmp_bytes = 0, tmp_scan = 0;
+  cudaError_t err = cudaSuccess;
+  auto cleanup = [&]() {
+    cudaFree(keys);
+    cudaFree(vals);
+    cudaFree(keys_s);
+    cudaFree(vals_s);
+    cudaFree(first);
+    cudaFree(len);
+    cudaFree(size16);
+    cudaFree(start16);
+    cudaFree(tmp);
+  };
+#define MLC_TRY_C(x)          \
+  do {                        \
+    err = (x);                \
+    if (err != cudaSuccess) { \
+      cleanup();              \
+      return err;             \
+    }                         \
+  } while (0)
+  MLC_TRY_C(cudaMalloc(&keys, 4 * n));
+  MLC_TRY_C(cudaMalloc(&vals, 4 * n));
+  MLC_TRY_C(cudaMalloc(&keys_s, 4 * n));
+  MLC_TRY_C(cudaMalloc(&vals_s, 4 * n));
+  MLC_TRY_C(cudaMalloc(&first, 4 * static_cast<size_t>(num_cells)));
+  MLC_TRY_C(cudaMalloc(&len, 4 * static_cast<size_t>(num_cells)));
+  MLC_TRY_C(cudaMalloc(&size16, 4 * static_cast<size_t>(num_cells)));
+  MLC_TRY_C(cudaMalloc(&start16, 4 * static_cast<size_t>(num_cells)));
+  const unsigned nb = static_cast<unsigned>((n + 255) / 256);
+  const unsigned cb = (num_cells + 255) / 256;
+  shard_keys_kernel<<<nb, 256, 0, stream>>>(d_cells, n, shard_rank, shard_count, num_cells, keys,
+                                            vals);
+  CountLaunch();
+  int end_bit = 1;
+  while ((1ull << end_bit) <= num_cells) ++end_bit;
+  MLC_TRY_C(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys, keys_s, vals, vals_s,
+                                            static_cast<int>(n), 0, end_bit, stream));
+  MLC_TRY_C(cub::DeviceScan::ExclusiveSum(nullptr, tmp_scan, size16, start16,
+                                          static_cast<int>(num_cells), stream));
+  if (tmp_scan > tmp_bytes) tmp_bytes = tmp_scan;
+  MLC_TRY_C(cudaMalloc(&tmp, tmp_bytes));
+  MLC_TRY_C(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, keys, keys_s, vals, vals_s,
+                                            static_cast<int>(n), 0, end_bit, stream));
+  CountLaunch();
+  MLC_TRY_C(cudaMemsetAsync(first, 0xFF, 4 * static_cast<size_t>(num_cells), stream));
+  MLC_TRY_C(cudaMemsetAsync(len, 0, 4 * static_cast<size_t>(num_cells), stream));
+  cell_bounds_kernel<<<nb, 256, 0, stream>>>(keys_s, n, num_cells, first, len);
+  CountLaunch();
+  cell_sizes_kernel<<<cb, 256, 0, stream>>>(num_cells, first, len, dim + 1, size16);
+  CountLaunch();
+  MLC_TRY_C(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, size16, start16,
+                                          static_cast<int>(num_cells), stream));
+  CountLaunch();
+  cell_info_kernel<<<cb, 256, 0, stream>>>(num_cells, start16, len, out->cell_info);
+  CountLaunch();
+  uint32_t last_start = 0, last_size = 0;
+  MLC_TRY_C(cudaMemcpyAsync(&last_start, start16 + (num_cells - 1), 4, cudaMemcpyDeviceToHost,
+                            stream));
+  MLC_TRY_C(cudaMemcpyAsync(&last_size, size16 + (num_cells - 1), 4, cudaMemcpyDeviceToHost, stream));
+  MLC_TRY_C(cudaStreamSynchronize(stream));
+  out->list_bytes = (static_cast<size_t>(last_start) + last_size) * 16;
+  MLC_TRY_C(cudaMalloc(&out->lists, out->list_bytes + 16));
+  fill_lists_kernel<<<nb, 256, 0, stream>>>(keys_s, vals_s, n, num_cells, first, out->cell_info,
+                                            d_desc, dim, out->lists);
+  CountLaunch();
+  MLC_TRY_C(cudaGetLastError());
+  MLC_TRY_C(cudaStreamSynchronize(stream));
+  cleanup();
+#undef MLC_TRY_C
+  return cudaSuccess;
+}
+
+}  // namespace mlc
