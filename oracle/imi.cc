@@ -131,6 +131,9 @@ int InvertedMultiIndex::CellOfDescriptor(const float* desc) const {
   std::vector<std::pair<int, int>> cw;
   FindClosestWords(desc, sub_dim_, 1, t1_, t2_, sp_, &cw);
   assert(!cw.empty());
+  // Quirk 1: no word inside lc_knn_max_radius in one of the halves. The reference
+  // would compute an aliased / negative cell id; the canonical definition is "not indexed".
+  if (cw[0].first < 0 || cw[0].second < 0) return -1;
   return cw[0].first * w2_ + cw[0].second;
 }
 
@@ -140,6 +143,10 @@ void InvertedMultiIndex::AddDescriptors(const float* desc, int n) {
   for (int i = 0; i < n; ++i) {
     const float* d = desc + static_cast<size_t>(i) * dim;
     const int word_index = CellOfDescriptor(d);
+    if (word_index < 0) {  // quirk 1: unreachable descriptor keeps its index but is not stored
+      ++max_db_descriptor_index_;
+      continue;
+    }
     auto it = word_index_map_.find(word_index);
     if (it == word_index_map_.end()) {
       word_index_map_.emplace(word_index, static_cast<int>(inverted_files_.size()));
@@ -290,6 +297,10 @@ void InvertedMultiPQIndex::AddDescriptors(const float* desc, int n) {
     const float* d = desc + static_cast<size_t>(i) * dim;
     FindClosestWords(d, sub_dim_, 1, t1_, t2_, sp_, &cw);
     const int word1 = cw[0].first, word2 = cw[0].second;
+    if (word1 < 0 || word2 < 0) {  // quirk 1, as in InvertedMultiIndex::AddDescriptors
+      ++max_db_descriptor_index_;
+      continue;
+    }
     const int word_index = word1 * w2_ + word2;
     for (int j = 0; j < sub_dim_; ++j) res[j] = d[j] - words1_.at(j, word1);
     q1_[word1].Quantize(res.data(), codes.data());
