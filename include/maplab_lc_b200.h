@@ -177,6 +177,13 @@ int mlc_find_batch_bits(mlc_detector* d, const mlc_frame* frames, int64_t num_fr
                         int64_t capacity, int64_t* match_offsets, int64_t* num_vertices,
                         int64_t* num_matches);
 
+/* Kernel 3 only, on kNN lists that already live on the device (n_q x k for the concatenated
+ * descriptors of `frames`; e.g. the merged result of the cross-shard all-gather). */
+int mlc_find_from_knn_device(mlc_detector* d, const mlc_frame* frames, int64_t num_frames,
+                             const int32_t* d_idx, const float* d_dist, int k, mlc_match* matches,
+                             int64_t capacity, int64_t* match_offsets, int64_t* num_vertices,
+                             int64_t* num_matches);
+
 /* Batched geometric verification: LoopClosureHandler::handleLoopClosure gates +
  * PnpPoseEstimator::absoluteMultiPoseRansacPinholeCam (LCH/src/loop-closure-handler.cc:235-480,
  * aslam_cv2/aslam_cv_geometric_vision/src/pnp-pose-estimator.cc:75-132, :193-280).

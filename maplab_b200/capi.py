@@ -18,7 +18,7 @@ EXPORTS = [
     "mlc_num_descriptors", "mlc_num_neighbors", "mlc_target_dim", "mlc_project",
     "mlc_project_device", "mlc_insert", "mlc_insert_batch", "mlc_initialize", "mlc_knn",
     "mlc_knn_device", "mlc_coarse_cells", "mlc_merge_topk_device", "mlc_last_scan_stats",
-    "mlc_find_batch", "mlc_find_batch_bits", "mlc_pnp_ransac_batch",
+    "mlc_find_batch", "mlc_find_batch_bits", "mlc_find_from_knn_device", "mlc_pnp_ransac_batch",
 ]
 
 
@@ -250,6 +250,19 @@ class Detector:
                                         C.byref(nm)))
         if nm.value > cap:
             raise MlcError(f"match capacity {cap} too small for {nm.value} matches")
+        return matches[:nm.value], offsets[:nv.value + 1]
+
+    def find_from_knn_device(self, frames, idx_ptr, dist_ptr, k, capacity=None):
+        frames = np.ascontiguousarray(frames, FRAME_DTYPE)
+        nf = len(frames)
+        total = int(frames["num_descriptors"].sum())
+        cap = capacity if capacity is not None else total * k + 16
+        matches = np.zeros(cap, MATCH_DTYPE)
+        offsets = np.zeros(nf + 1, np.int64)
+        nv, nm = C.c_int64(), C.c_int64()
+        _check(lib().mlc_find_from_knn_device(self._h, _ptr(frames), C.c_int64(nf), C.c_void_p(idx_ptr),
+                                              C.c_void_p(dist_ptr), k, _ptr(matches), C.c_int64(cap),
+                                              _ptr(offsets), C.byref(nv), C.byref(nm)))
         return matches[:nm.value], offsets[:nv.value + 1]
 
     def pnp_ransac_batch(self, cams, offsets, keypoints, camera_index, keypoint_index, landmarks,

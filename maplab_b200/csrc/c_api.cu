@@ -169,6 +169,20 @@ int mlc_find_batch_bits(mlc_detector* d, const mlc_frame* frames, int64_t num_fr
              : Fail(err);
 }
 
+int mlc_find_from_knn_device(mlc_detector* d, const mlc_frame* frames, int64_t num_frames,
+                             const int32_t* d_idx, const float* d_dist, int k, mlc_match* matches,
+                             int64_t capacity, int64_t* match_offsets, int64_t* num_vertices,
+                             int64_t* num_matches) {
+  MLC_REQUIRE(d && num_vertices && num_matches && (num_frames == 0 || (frames && match_offsets)),
+              "mlc_find_from_knn_device: null argument");
+  MLC_REQUIRE(k > 0 && k <= 16, "k must be in 1..16");
+  std::string err;
+  return d->impl.FindFromKnn(frames, num_frames, d_idx, d_dist, k, matches, capacity, match_offsets,
+                             num_vertices, num_matches, &err)
+             ? 0
+             : Fail(err);
+}
+
 int mlc_pnp_ransac_batch(mlc_detector* d, const mlc_ransac_settings* rs, const mlc_camera* cams,
                          int num_cams, int64_t num_problems, const int64_t* offsets,
                          const double* keypoints, const int32_t* camera_index,

@@ -1,0 +1,417 @@
+// Kernel 3 of the loop-closure path: match gathering with the time/mission filter, per-keyframe
+// vote counting, top-fraction selection and landmark-covisibility clustering — one CTA per query
+// frame (pass 1) or per multi-camera query vertex (pass 2). Everything is sort / scan / segmented
+// reduction in shared memory; no atomics.
+//
+// Reference: matching-based-loopclosure/src/matching-based-engine.cc:101-123 (neighbour walk with
+// `break`), :170-215 (getMatchForDescriptorIndex), :147-165 (vertex pass);
+// include/matching-based-loopclosure/matching-based-engine-inl.h:45-183 (doCovisibilityFiltering),
+// :219-254 (computeRelevantIdsForFiltering); scoring.h:38-59 (accumulation score).
+// Canonical orders where the reference depends on hash-map iteration (oracle/engine.cc):
+// top-fraction ties by keyframe number, component ties by smallest member, duplicates keep the
+// smallest database descriptor, output sorted by (query frame, keypoint, database descriptor).
+#include <cub/cub.cuh>
+
+#include "covis.h"
+
+namespace mlc {
+namespace {
+
+constexpr uint16_t kNone16 = 0xFFFFu;
+
+template <int MAXM>
+struct CovisSmem {
+  unsigned long long keys[MAXM];
+  uint16_t a1[MAXM + 2], a2[MAXM + 2], a3[MAXM + 2], a4[MAXM + 2];
+  uint16_t a5[MAXM + 2], a6[MAXM + 2], a7[MAXM + 2], a8[MAXM + 2];
+  uint8_t f1[MAXM], f2[MAXM];
+  int bcast[4];
+};
+
+template <int THREADS>
+__device__ __forceinline__ void BitonicSort(unsigned long long* keys, int p2) {
+  for (int k2 = 2; k2 <= p2; k2 <<= 1) {
+    for (int j = k2 >> 1; j > 0; j >>= 1) {
+      for (int i = threadIdx.x; i < p2; i += THREADS) {
+        const int ixj = i ^ j;
+        if (ixj > i) {
+          const bool asc = (i & k2) == 0;
+          const unsigned long long a = keys[i], b = keys[ixj];
+          if ((a > b) == asc) {
+            keys[i] = b;
+            keys[ixj] = a;
+          }
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+__device__ __forceinline__ int NextPow2(int n) {
+  int p = 2;
+  while (p < n) p <<= 1;
+  return p;
+}
+
+// Order-preserving exclusive scan of 0/1 flags over [0, n): thread t owns the contiguous chunk
+// [t*IPT, (t+1)*IPT). pos[i] = number of set flags before i. Returns the total.
+template <int THREADS, int IPT, typename FlagFn, typename OutFn>
+__device__ __forceinline__ int FlagScan(int n, FlagFn flag, OutFn out,
+                                        typename cub::BlockScan<int, THREADS>::TempStorage& tmp) {
+  const int begin = threadIdx.x * IPT;
+  int local = 0;
+#pragma unroll
+  for (int i = 0; i < IPT; ++i) {
+    const int at = begin + i;
+    if (at < n && flag(at)) ++local;
+  }
+  int offset = 0, total = 0;
+  cub::BlockScan<int, THREADS>(tmp).ExclusiveSum(local, offset, total);
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < IPT; ++i) {
+    const int at = begin + i;
+    if (at < n) {
+      const bool f = flag(at);
+      out(at, offset, f);
+      if (f) ++offset;
+    }
+  }
+  __syncthreads();
+  return total;
+}
+
+template <int MAXM, int THREADS>
+__global__ void __launch_bounds__(THREADS) covis_kernel(CovisArgs a) {
+  constexpr int IPT = MAXM / THREADS;
+  constexpr int SLOT_BITS = (MAXM == 8192) ? 13 : 12;
+  constexpr unsigned long long SLOT_MASK = (1ull << SLOT_BITS) - 1;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  CovisSmem<MAXM>& s = *reinterpret_cast<CovisSmem<MAXM>*>(smem_raw);
+  __shared__ typename cub::BlockScan<int, THREADS>::TempStorage scan_tmp;
+  typedef cub::BlockReduce<unsigned long long, THREADS> BlockMax;
+  __shared__ typename BlockMax::TempStorage red_tmp;
+  mlc_match* rec = a.scratch + static_cast<size_t>(blockIdx.x) * MAXM;
+  const int tid = threadIdx.x;
+
+  for (int w = blockIdx.x; w < a.num_items; w += gridDim.x) {
+    const CovisItem item = a.items[w];
+    // ------------------------------------------------------------------ load + compact (P5)
+    int R = 0;
+    if (!a.by_vertex) {
+      // pass 1: neighbour slots of one query frame, scan order = (keypoint, neighbour rank)
+      const int n_slots = item.count * a.k;
+      const int32_t* idx = a.knn_idx + static_cast<size_t>(item.first) * a.k;
+      const float* dst = a.knn_dist + static_cast<size_t>(item.first) * a.k;
+      auto valid = [&](int slot) -> bool {
+        const int32_t id = idx[slot];
+        if (id < 0 || dst[slot] == __int_as_float(0x7f800000)) return false;  // trailing (-1, inf)
+        const KeyframeMeta& kf = a.kf_meta[a.desc_kf[id]];
+        long long dt = item.ts - kf.ts;
+        if (dt < 0) dt = -dt;
+        // skip iff |dt| < min_seconds * 1e9 AND same mission (matching-based-engine.cc:192-198)
+        return !(static_cast<double>(dt) < a.min_time_ns && item.mission == kf.mission);
+      };
+      R = FlagScan<THREADS, IPT>(
+          n_slots, valid,
+          [&](int slot, int pos, bool f) {
+            if (!f) return;
+            const int32_t id = idx[slot];
+            const int32_t kfn = a.desc_kf[id];
+            mlc_match m;
+            m.query_frame = item.frame;
+            m.query_keypoint = slot / a.k;
+            m.db_descriptor = id;
+            m.db_keyframe = kfn;
+            m.db_vertex = a.kf_meta[kfn].vertex;
+            m.landmark = a.desc_lm[id];
+            rec[pos] = m;
+          },
+          scan_tmp);
+    } else {
+      // pass 2: concatenation of the pass-1 outputs of the vertex' frames
+      for (int f = 0; f < item.count; ++f) {
+        const int fi = item.first + f;
+        const int cnt = a.in_counts[fi];
+        const mlc_match* src = a.in_matches + a.in_offsets[fi];
+        for (int i = tid; i < cnt; i += THREADS)
+          if (R + i < MAXM) rec[R + i] = src[i];
+        R += cnt;
+      }
+    }
+    __syncthreads();
+    int out_count = 0;
+    mlc_match* out = a.out_matches + item.out_offset;
+    if (R > MAXM) {
+      out_count = -1;  // more surviving matches than the kernel can cluster: reported to the host
+    } else if (R > 0) {
+      // ---------------------------------------------------------------- A: sort by group, votes
+      const int p2 = NextPow2(R);
+      for (int i = tid; i < p2; i += THREADS) {
+        unsigned long long key = ~0ull;
+        if (i < R) {
+          const long long g = a.by_vertex ? rec[i].db_vertex : static_cast<long long>(rec[i].db_keyframe);
+          key = (static_cast<unsigned long long>(g) << SLOT_BITS) | static_cast<unsigned>(i);
+        }
+        s.keys[i] = key;
+      }
+      __syncthreads();
+      BitonicSort<THREADS>(s.keys, p2);
+      // candidate rank b of every match (a1), first sorted position of every candidate (a2)
+      const int Cn = FlagScan<THREADS, IPT>(
+          R, [&](int i) { return i == 0 || (s.keys[i] >> SLOT_BITS) != (s.keys[i - 1] >> SLOT_BITS); },
+          [&](int i, int pos, bool f) {
+            const int b = f ? pos : pos - 1;
+            s.a1[s.keys[i] & SLOT_MASK] = static_cast<uint16_t>(b);
+            if (f) s.a2[b] = static_cast<uint16_t>(i);
+          },
+          scan_tmp);
+      if (tid == 0) s.a2[Cn] = static_cast<uint16_t>(R);
+      __syncthreads();
+      // ---------------------------------------------------------------- B: scores, top fraction
+      int n_eval = Cn;
+      if (!a.by_vertex) {
+        // computeRelevantIdsForFiltering: max(floor(float(size) * fraction), 4), capped by size
+        int want = static_cast<int>(__fmul_rn(static_cast<float>(Cn), a.fraction_best_scores));
+        if (want < 4) want = 4;
+        n_eval = want < Cn ? want : Cn;
+        const int pc = NextPow2(Cn);
+        for (int b = tid; b < pc; b += THREADS) {
+          unsigned long long key = ~0ull;
+          if (b < Cn) {
+            const float score = static_cast<float>(s.a2[b + 1] - s.a2[b]);  // accumulation score
+            const unsigned ord = __float_as_uint(score);                    // scores are >= 0
+            key = (static_cast<unsigned long long>(0xFFFFFFFFu - ord) << SLOT_BITS) | static_cast<unsigned>(b);
+          }
+          s.keys[b] = key;
+        }
+        __syncthreads();
+        BitonicSort<THREADS>(s.keys, pc);
+        for (int b = tid; b < Cn; b += THREADS) s.f1[b] = 0;
+        __syncthreads();
+        for (int r = tid; r < n_eval; r += THREADS) s.f1[s.keys[r] & SLOT_MASK] = 1;
+        __syncthreads();
+      } else {
+        for (int b = tid; b < Cn; b += THREADS) s.f1[b] = 1;
+        __syncthreads();
+      }
+      // dense id of the selected candidates (a3), ascending group id
+      FlagScan<THREADS, IPT>(
+          Cn, [&](int b) { return s.f1[b] != 0; },
+          [&](int b, int pos, bool f) { s.a3[b] = f ? static_cast<uint16_t>(pos) : kNone16; }, scan_tmp);
+      // a1[match] := selected dense group id or none
+      for (int i = tid; i < R; i += THREADS) s.a1[i] = s.a3[s.a1[i]];
+      __syncthreads();
+      // ---------------------------------------------------------------- C: landmark ids, both orders
+      for (int i = tid; i < p2; i += THREADS) {
+        unsigned long long key = ~0ull;
+        if (i < R && s.a1[i] != kNone16)
+          key = (static_cast<unsigned long long>(rec[i].landmark + 1) << SLOT_BITS) | static_cast<unsigned>(i);
+        s.keys[i] = key;
+      }
+      __syncthreads();
+      BitonicSort<THREADS>(s.keys, p2);
+      // S = number of selected matches = number of keys != ~0
+      const int S = FlagScan<THREADS, IPT>(
+          R, [&](int i) { return s.keys[i] != ~0ull; }, [&](int, int, bool) {}, scan_tmp);
+      // landmark dense id a4[match]; offA (a5), listA (a6) = group of the match at sorted position
+      const int nL = FlagScan<THREADS, IPT>(
+          S, [&](int i) { return i == 0 || (s.keys[i] >> SLOT_BITS) != (s.keys[i - 1] >> SLOT_BITS); },
+          [&](int i, int pos, bool f) {
+            const int la = f ? pos : pos - 1;
+            const int slot = static_cast<int>(s.keys[i] & SLOT_MASK);
+            s.a4[slot] = static_cast<uint16_t>(la);
+            s.a6[i] = s.a1[slot];
+            if (f) s.a5[la] = static_cast<uint16_t>(i);
+          },
+          scan_tmp);
+      if (tid == 0) s.a5[nL] = static_cast<uint16_t>(S);
+      __syncthreads();
+      // order B: selected matches sorted by dense group id; offB (a7), listB (a8) = landmark id
+      for (int i = tid; i < p2; i += THREADS) {
+        unsigned long long key = ~0ull;
+        if (i < R && s.a1[i] != kNone16)
+          key = (static_cast<unsigned long long>(s.a1[i]) << SLOT_BITS) | static_cast<unsigned>(i);
+        s.keys[i] = key;
+      }
+      __syncthreads();
+      BitonicSort<THREADS>(s.keys, p2);
+      FlagScan<THREADS, IPT>(
+          S, [&](int i) { return i == 0 || (s.keys[i] >> SLOT_BITS) != (s.keys[i - 1] >> SLOT_BITS); },
+          [&](int i, int pos, bool f) {
+            const int slot = static_cast<int>(s.keys[i] & SLOT_MASK);
+            s.a8[i] = s.a4[slot];
+            if (f) s.a7[s.keys[i] >> SLOT_BITS] = static_cast<uint16_t>(i);
+          },
+          scan_tmp);
+      if (tid == 0) s.a7[n_eval] = static_cast<uint16_t>(S);
+      __syncthreads();
+      // ---------------------------------------------------------------- D: components (min label)
+      uint16_t* K = s.a2;  // label per selected group
+      uint16_t* L = s.a3;  // label per landmark
+      for (int b = tid; b < n_eval; b += THREADS) K[b] = static_cast<uint16_t>(b);
+      __syncthreads();
+      for (;;) {
+        for (int la = tid; la < nL; la += THREADS) {
+          uint16_t mn = kNone16;
+          for (int i = s.a5[la]; i < s.a5[la + 1]; ++i) mn = min(mn, K[s.a6[i]]);
+          L[la] = mn;
+        }
+        __syncthreads();
+        int changed = 0;
+        for (int b = tid; b < n_eval; b += THREADS) {
+          uint16_t mn = K[b];
+          for (int i = s.a7[b]; i < s.a7[b + 1]; ++i) mn = min(mn, L[s.a8[i]]);
+          if (mn != K[b]) {
+            K[b] = mn;
+            changed = 1;
+          }
+        }
+        if (!__syncthreads_or(changed)) break;
+      }
+      // ---------------------------------------------------------------- E: distinct matches, sizes
+      // Duplicates (same query keypoint, keyframe and landmark, different database descriptor)
+      // can only sit among the <= k neighbours of one keypoint, which are adjacent in `rec`.
+      for (int i = tid; i < R; i += THREADS) {
+        uint8_t distinct = 0;
+        if (s.a1[i] != kNone16) {
+          distinct = 1;
+          const mlc_match me = rec[i];
+          for (int d = -(a.k - 1); d <= a.k - 1; ++d) {
+            const int j = i + d;
+            if (d == 0 || j < 0 || j >= R || s.a1[j] == kNone16) continue;
+            const mlc_match o = rec[j];
+            if (o.query_frame == me.query_frame && o.query_keypoint == me.query_keypoint &&
+                o.db_keyframe == me.db_keyframe && o.landmark == me.landmark &&
+                o.db_descriptor < me.db_descriptor)
+              distinct = 0;
+          }
+        }
+        s.f2[i] = distinct;
+      }
+      __syncthreads();
+      uint16_t* cnt = s.a3;  // distinct matches per selected group (L no longer needed)
+      for (int b = tid; b < n_eval; b += THREADS) {
+        int c = 0;
+        for (int i = s.a7[b]; i < s.a7[b + 1]; ++i) c += s.f2[s.keys[i] & SLOT_MASK];
+        cnt[b] = static_cast<uint16_t>(c);
+      }
+      __syncthreads();
+      unsigned long long best = 0;
+      for (int r = tid; r < n_eval; r += THREADS) {
+        if (K[r] != r) continue;  // not a root
+        unsigned size = 0;
+        for (int b = r; b < n_eval; ++b)
+          if (K[b] == r) size += cnt[b];
+        // larger size wins; ties -> smaller root
+        const unsigned long long cand = (static_cast<unsigned long long>(size) << 16) | (0xFFFFu - r);
+        if (cand > best) best = cand;
+      }
+      best = BlockMax(red_tmp).Reduce(best, cub::Max());
+      if (tid == 0) {
+        s.bcast[0] = static_cast<int>(best >> 16);
+        s.bcast[1] = 0xFFFF - static_cast<int>(best & 0xFFFFu);
+      }
+      __syncthreads();
+      const int best_size = s.bcast[0], best_root = s.bcast[1];
+      if (static_cast<unsigned long long>(best_size) > a.min_verify_matches_num) {
+        // -------------------------------------------------------------- F: winners, uniqueness, order
+        for (int i = tid; i < R; i += THREADS)
+          s.f1[i] = (s.f2[i] && K[s.a1[i]] == best_root) ? 1 : 0;
+        __syncthreads();
+        const bool unique = a.by_vertex ? true : (item.make_unique != 0);
+        for (int i = tid; i < p2; i += THREADS) {
+          unsigned long long key = ~0ull;
+          if (i < R && s.f1[i]) {
+            bool keep = true;
+            const mlc_match me = rec[i];
+            if (unique) {
+              // (query keypoint, landmark) unique: the smallest database descriptor survives
+              for (int d = -(a.k - 1); d <= a.k - 1; ++d) {
+                const int j = i + d;
+                if (d == 0 || j < 0 || j >= R || !s.f1[j]) continue;
+                const mlc_match o = rec[j];
+                if (o.query_frame == me.query_frame && o.query_keypoint == me.query_keypoint &&
+                    o.landmark == me.landmark && o.db_descriptor < me.db_descriptor)
+                  keep = false;
+              }
+            }
+            if (keep) {
+              // canonical order (query frame, keypoint, database descriptor); query_frame is the
+              // batch frame number, monotone within a vertex
+              key = (static_cast<unsigned long long>(me.query_frame - item.frame) << 59) |
+                    (static_cast<unsigned long long>(me.query_keypoint) << 44) |
+                    (static_cast<unsigned long long>(static_cast<unsigned>(me.db_descriptor)) << SLOT_BITS) |
+                    static_cast<unsigned>(i);
+            }
+          }
+          s.keys[i] = key;
+        }
+        __syncthreads();
+        BitonicSort<THREADS>(s.keys, p2);
+        out_count = FlagScan<THREADS, IPT>(
+            R, [&](int i) { return s.keys[i] != ~0ull; },
+            [&](int i, int pos, bool f) {
+              if (f) out[pos] = rec[s.keys[i] & SLOT_MASK];
+            },
+            scan_tmp);
+      }
+    }
+    if (tid == 0) a.out_counts[w] = out_count;
+    __syncthreads();
+  }
+}
+
+__global__ void compact_matches_kernel(const mlc_match* __restrict__ in, const CovisItem* items,
+                                       const int* __restrict__ counts,
+                                       const long long* __restrict__ dst_offsets, int num_items,
+                                       mlc_match* __restrict__ out) {
+  for (int w = blockIdx.x; w < num_items; w += gridDim.x) {
+    const mlc_match* src = in + items[w].out_offset;
+    mlc_match* dst = out + dst_offsets[w];
+    const int n = counts[w];
+    const uint4* s4 = reinterpret_cast<const uint4*>(src);
+    uint4* d4 = reinterpret_cast<uint4*>(dst);
+    for (int i = threadIdx.x; i < n * 2; i += blockDim.x) d4[i] = s4[i];
+  }
+}
+
+}  // namespace
+
+size_t CovisScratchMatches(int max_matches, int grid) {
+  return static_cast<size_t>(max_matches > 4096 ? 8192 : 4096) * grid;
+}
+
+cudaError_t LaunchCovis(const CovisArgs& a, int max_matches, int grid, cudaStream_t stream) {
+  if (a.num_items <= 0) return cudaSuccess;
+  if (max_matches > 8192 || a.k > 16) return cudaErrorInvalidValue;
+  cudaError_t e;
+  if (max_matches <= 4096) {
+    auto fn = covis_kernel<4096, 512>;
+    e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             static_cast<int>(sizeof(CovisSmem<4096>)));
+    if (e != cudaSuccess) return e;
+    fn<<<grid, 512, sizeof(CovisSmem<4096>), stream>>>(a);
+  } else {
+    auto fn = covis_kernel<8192, 1024>;
+    e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             static_cast<int>(sizeof(CovisSmem<8192>)));
+    if (e != cudaSuccess) return e;
+    fn<<<grid, 1024, sizeof(CovisSmem<8192>), stream>>>(a);
+  }
+  CountLaunch();
+  return cudaGetLastError();
+}
+
+cudaError_t LaunchCompactMatches(const mlc_match* in, const CovisItem* items, const int* counts,
+                                 const long long* dst_offsets, int num_items, mlc_match* out,
+                                 cudaStream_t stream) {
+  if (num_items <= 0) return cudaSuccess;
+  const int grid = num_items < 1184 ? num_items : 1184;
+  compact_matches_kernel<<<grid, 128, 0, stream>>>(in, items, counts, dst_offsets, num_items, out);
+  CountLaunch();
+  return cudaGetLastError();
+}
+
+}  // namespace mlc

@@ -75,6 +75,11 @@ class Detector {
                  const uint8_t* bits, int bytes_per_desc, mlc_match* matches, int64_t capacity,
                  int64_t* match_offsets, int64_t* num_vertices, int64_t* num_matches,
                  std::string* err);
+  // Kernel 3 on kNN results that already live on the device (after the cross-shard merge).
+  bool FindFromKnn(const mlc_frame* frames, int64_t num_frames, const int32_t* d_idx,
+                   const float* d_dist, int k, mlc_match* matches, int64_t capacity,
+                   int64_t* match_offsets, int64_t* num_vertices, int64_t* num_matches,
+                   std::string* err);
   bool PnpRansacBatch(const mlc_ransac_settings& rs, const mlc_camera* cams, int num_cams,
                       int64_t num_problems, const int64_t* offsets, const double* keypoints,
                       const int32_t* camera_index, const int32_t* keypoint_index,
