@@ -26,6 +26,7 @@ Detector::~Detector() {
                     &d_idx_,      &d_dist_,    &d_bits_,    &d_stats_};
   for (DevBuf* b : bufs) b->Free();
   for (DevBuf& b : d_covis_) b.Free();
+  for (DevBuf& b : d_ransac_) b.Free();
   if (ev0_) cudaEventDestroy(ev0_);
   if (ev1_) cudaEventDestroy(ev1_);
   if (stream_) cudaStreamDestroy(stream_);

@@ -121,6 +121,7 @@ class Detector {
   // per-call scratch
   DevBuf d_q_, d_cells_, d_idx_, d_dist_, d_bits_, d_stats_;
   DevBuf d_covis_[8];
+  DevBuf d_ransac_[4];
   int64_t last_nq_ = 0;
   int last_nw_ = 0;
   bool last_valid_ = false;

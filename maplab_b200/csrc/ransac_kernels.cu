@@ -1,0 +1,842 @@
+// Kernel 4 of the loop-closure path: batched geometric verification, one warp per query vertex.
+//   LoopClosureHandler::handleLoopClosure gates      loop-closure-handler/src/loop-closure-handler.cc:235-480
+//   PnpPoseEstimator::absoluteMultiPoseRansacPinholeCam  aslam_cv_geometric_vision/src/pnp-pose-estimator.cc:75-132, :193-280
+//   opengv Ransac / sampler                          opengv/include/opengv/sac/implementation/Ransac.hpp:44-143,
+//                                                    SampleConsensusProblem.hpp:62-82, :165-205
+//   GP3P model + disambiguation + scoring            opengv/src/sac_problems/absolute_pose/AbsolutePoseSacProblem.cpp:111-199,
+//                                                    opengv/src/absolute_pose/modules/main.cpp:375-436
+//   getBestStructureMatchForEveryKeypoint            loop-closure-handler/src/inlier-index-with-reprojection-error.cc:7-51
+//
+// The sample sequence of opengv's RANSAC does not depend on the data (persistent partial
+// Fisher-Yates over an explicit int stream), so the warp draws 32 samples ahead, every lane solves
+// one GP3P hypothesis (Groebner elimination as the table-driven micro-op program shared with the
+// oracle, 8x8 eigen-solve, Cayley back-substitution) and scores it against all correspondences;
+// the sequential bookkeeping (skips, best-so-far with strict >, adaptive k) is then replayed in
+// sample order. fp64 throughout; this file is compiled with -fmad=false so every expression
+// rounds exactly like the SSE2 build of the reference/oracle.
+#include <climits>
+#include <cmath>
+#include <vector>
+
+#include "detector.h"
+
+namespace mlc {
+namespace {
+#include "gp3p_program.inc"
+
+enum {
+  MOP_DIVSUB = 0,
+  MOP_DIV,
+  MOP_NEGDIV,
+  MOP_FACTOR_DIV,
+  MOP_ZERO,
+  MOP_SUBMUL,
+  MOP_FACTOR_LOAD,
+  MOP_FACTOR_INV,
+  MOP_SCALE
+};
+
+constexpr int N8 = 8;
+constexpr int kWarpsPerBlock = 4;
+
+struct RansacArgs {
+  int64_t num_problems;
+  const int64_t* offsets;
+  const double* keypoints;      // 2 per correspondence
+  const int32_t* camera_index;
+  const int32_t* keypoint_index;
+  const double* landmarks;      // 3 per correspondence
+  const mlc_camera* cams;
+  int num_cams;
+  double threshold;             // 1 - cos(atan(sigma / mean focal)), computed on the host
+  double log_one_minus_p;       // log(1 - 0.99)
+  int min_inlier_count, max_iterations;
+  double min_inlier_ratio;
+  const int32_t* rnd_stream;    // uniform_int_distribution<int>(0, INT_MAX) draws, host generated
+  int rnd_len;
+  const int4* mops;             // packed micro-ops {op | a<<16, b | c<<16, d | e<<16, 0}
+  const short* init_table;      // GP3P_INIT
+  const short* action;          // GP3P_ACTION
+  double* slots;                // per warp: GP3P_NUM_SLOTS x 32 doubles
+  double* bearings;             // 3 per correspondence
+  int32_t* shuffled;            // per correspondence
+  mlc_pose_result* results;
+  uint8_t* inlier_flags;        // may be null
+};
+
+// ---------------------------------------------------------------- GP3P elimination (per lane)
+// S(slot) of this lane lives at slots[slot * 32 + lane]: the 32 lanes of a warp execute the same
+// micro-op on 32 hypotheses with fully coalesced accesses.
+__device__ void Gp3pEliminate(const RansacArgs& a, const double* f, const double* v, const double* p,
+                              double* S) {
+  for (int s = 0; s < GP3P_NUM_SLOTS; ++s) S[s * 32] = 0.0;
+  for (int e = 0; e < GP3P_NUM_INIT; ++e) {
+    const short* in = a.init_table + e * 18;
+    double acc = 0.0;
+    const int nt = in[1];
+    for (int t = 0; t < nt; ++t) {
+      const short* tm = in + 2 + 4 * t;
+      const double* src = tm[1] == 0 ? f : (tm[1] == 1 ? v : p);
+      const double term = static_cast<double>(tm[0]) * src[tm[3] * 3 + tm[2]];
+      acc = (t == 0) ? term : acc + term;
+    }
+    S[in[0] * 32] = acc;
+  }
+  double factor = 0.0;
+  for (int i = 0; i < GP3P_NUM_MOPS; ++i) {
+    const int4 m = __ldg(a.mops + i);
+    const int op = m.x & 0xFFFF, m1 = m.x >> 16, m2 = m.y & 0xFFFF, m3 = m.y >> 16, m4 = m.z & 0xFFFF,
+              m5 = m.z >> 16;
+    switch (op) {
+      case MOP_DIVSUB:
+        S[m1 * 32] = S[m2 * 32] / S[m3 * 32] - S[m4 * 32] / S[m5 * 32];
+        break;
+      case MOP_DIV:
+        S[m1 * 32] = S[m2 * 32] / S[m3 * 32];
+        break;
+      case MOP_NEGDIV:
+        S[m1 * 32] = -S[m2 * 32] / S[m3 * 32];
+        break;
+      case MOP_FACTOR_DIV:
+        factor = S[m1 * 32] / S[m2 * 32];
+        break;
+      case MOP_ZERO:
+        S[m1 * 32] = 0.0;
+        break;
+      case MOP_SUBMUL:
+        S[m1 * 32] = S[m1 * 32] - factor * S[m2 * 32];
+        break;
+      case MOP_FACTOR_LOAD:
+        factor = S[m1 * 32];
+        break;
+      case MOP_FACTOR_INV:
+        factor = 1.0 / S[m1 * 32];
+        break;
+      case MOP_SCALE:
+        S[m1 * 32] = factor * S[m1 * 32];
+        break;
+    }
+  }
+}
+
+// ---------------------------------------------------------------- 8x8 real eigen-solver
+// Householder Hessenberg reduction + Francis shifted QR (EISPACK orthes / hqr scheme), exactly
+// the operation sequence of the oracle (oracle/pnp.cc).
+__device__ void Hessenberg(double H[N8][N8]) {
+  double ort[N8];
+  const int high = N8 - 1;
+  for (int m = 1; m <= high - 1; ++m) {
+    double scale = 0.0;
+    for (int i = m; i <= high; ++i) scale += fabs(H[i][m - 1]);
+    if (scale != 0.0) {
+      double h = 0.0;
+      for (int i = high; i >= m; --i) {
+        ort[i] = H[i][m - 1] / scale;
+        h += ort[i] * ort[i];
+      }
+      double g = sqrt(h);
+      if (ort[m] > 0) g = -g;
+      h -= ort[m] * g;
+      ort[m] -= g;
+      for (int j = m; j < N8; ++j) {
+        double fsum = 0.0;
+        for (int i = high; i >= m; --i) fsum += ort[i] * H[i][j];
+        fsum /= h;
+        for (int i = m; i <= high; ++i) H[i][j] -= fsum * ort[i];
+      }
+      for (int i = 0; i <= high; ++i) {
+        double fsum = 0.0;
+        for (int j = high; j >= m; --j) fsum += ort[j] * H[i][j];
+        fsum /= h;
+        for (int j = m; j <= high; ++j) H[i][j] -= fsum * ort[j];
+      }
+      ort[m] = scale * ort[m];
+      H[m][m - 1] = scale * g;
+    }
+  }
+  for (int i = 2; i < N8; ++i)
+    for (int j = 0; j < i - 1; ++j) H[i][j] = 0.0;
+}
+
+__device__ __forceinline__ double SignOf(double a, double b) { return b >= 0.0 ? fabs(a) : -fabs(a); }
+
+__device__ bool HqrEigenvalues(double a[N8][N8], double wr[N8], double wi[N8]) {
+  int nn, m, l, k, j, its, i, mmin;
+  double z, y, x, w, v, u, t, s, r = 0, q = 0, p = 0, anorm = 0.0;
+  for (i = 0; i < N8; i++)
+    for (j = (i - 1 > 0 ? i - 1 : 0); j < N8; j++) anorm += fabs(a[i][j]);
+  nn = N8 - 1;
+  t = 0.0;
+  while (nn >= 0) {
+    its = 0;
+    do {
+      for (l = nn; l >= 1; l--) {
+        s = fabs(a[l - 1][l - 1]) + fabs(a[l][l]);
+        if (s == 0.0) s = anorm;
+        if (fabs(a[l][l - 1]) + s == s) {
+          a[l][l - 1] = 0.0;
+          break;
+        }
+      }
+      x = a[nn][nn];
+      if (l == nn) {
+        wr[nn] = x + t;
+        wi[nn--] = 0.0;
+      } else {
+        y = a[nn - 1][nn - 1];
+        w = a[nn][nn - 1] * a[nn - 1][nn];
+        if (l == (nn - 1)) {
+          p = 0.5 * (y - x);
+          q = p * p + w;
+          z = sqrt(fabs(q));
+          x += t;
+          if (q >= 0.0) {
+            z = p + SignOf(z, p);
+            wr[nn - 1] = wr[nn] = x + z;
+            if (z != 0.0) wr[nn] = x - w / z;
+            wi[nn - 1] = wi[nn] = 0.0;
+          } else {
+            wr[nn - 1] = wr[nn] = x + p;
+            wi[nn - 1] = -(wi[nn] = z);
+          }
+          nn -= 2;
+        } else {
+          if (its == 60) return false;
+          if (its == 10 || its == 20) {
+            t += x;
+            for (i = 0; i <= nn; i++) a[i][i] -= x;
+            s = fabs(a[nn][nn - 1]) + fabs(a[nn - 1][nn - 2]);
+            y = x = 0.75 * s;
+            w = -0.4375 * s * s;
+          }
+          ++its;
+          for (m = (nn - 2); m >= l; m--) {
+            z = a[m][m];
+            r = x - z;
+            s = y - z;
+            p = (r * s - w) / a[m + 1][m] + a[m][m + 1];
+            q = a[m + 1][m + 1] - z - r - s;
+            r = a[m + 2][m + 1];
+            s = fabs(p) + fabs(q) + fabs(r);
+            p /= s;
+            q /= s;
+            r /= s;
+            if (m == l) break;
+            u = fabs(a[m][m - 1]) * (fabs(q) + fabs(r));
+            v = fabs(p) * (fabs(a[m - 1][m - 1]) + fabs(z) + fabs(a[m + 1][m + 1]));
+            if (u + v == v) break;
+          }
+          for (i = m + 2; i <= nn; i++) {
+            a[i][i - 2] = 0.0;
+            if (i != (m + 2)) a[i][i - 3] = 0.0;
+          }
+          for (k = m; k <= nn - 1; k++) {
+            if (k != m) {
+              p = a[k][k - 1];
+              q = a[k + 1][k - 1];
+              r = 0.0;
+              if (k != (nn - 1)) r = a[k + 2][k - 1];
+              if ((x = fabs(p) + fabs(q) + fabs(r)) != 0.0) {
+                p /= x;
+                q /= x;
+                r /= x;
+              }
+            }
+            if ((s = SignOf(sqrt(p * p + q * q + r * r), p)) != 0.0) {
+              if (k == m) {
+                if (l != m) a[k][k - 1] = -a[k][k - 1];
+              } else {
+                a[k][k - 1] = -s * x;
+              }
+              p += s;
+              x = p / s;
+              y = q / s;
+              z = r / s;
+              q /= p;
+              r /= p;
+              for (j = k; j <= nn; j++) {
+                p = a[k][j] + q * a[k + 1][j];
+                if (k != (nn - 1)) {
+                  p += r * a[k + 2][j];
+                  a[k + 2][j] -= p * z;
+                }
+                a[k + 1][j] -= p * y;
+                a[k][j] -= p * x;
+              }
+              mmin = nn < k + 3 ? nn : k + 3;
+              for (i = l; i <= mmin; i++) {
+                p = x * a[i][k] + y * a[i][k + 1];
+                if (k != (nn - 1)) {
+                  p += z * a[i][k + 2];
+                  a[i][k + 2] -= p * r;
+                }
+                a[i][k + 1] -= p * q;
+                a[i][k] -= p;
+              }
+            }
+          }
+        }
+      }
+    } while (l < nn - 1);
+  }
+  return true;
+}
+
+struct Cx {
+  double re, im;
+};
+__device__ __forceinline__ Cx CxMul(Cx a, Cx b) {
+  return Cx{a.re * b.re - a.im * b.im, a.re * b.im + a.im * b.re};
+}
+__device__ __forceinline__ Cx CxSub(Cx a, Cx b) { return Cx{a.re - b.re, a.im - b.im}; }
+__device__ __forceinline__ Cx CxDiv(Cx a, Cx b) {
+  const double den = b.re * b.re + b.im * b.im;
+  return Cx{(a.re * b.re + a.im * b.im) / den, (a.im * b.re - a.re * b.im) / den};
+}
+__device__ __forceinline__ double CxAbs2(Cx a) { return a.re * a.re + a.im * a.im; }
+
+// Eigenvector by inverse iteration (complex LU with partial pivoting); only component ratios are
+// consumed downstream.
+__device__ void InverseIteration(const double M[N8][N8], Cx lambda, Cx vec[N8]) {
+  Cx A[N8][N8];
+  double norm = 0.0;
+  for (int i = 0; i < N8; ++i)
+    for (int j = 0; j < N8; ++j) {
+      A[i][j] = Cx{M[i][j], 0.0};
+      norm = fmax(norm, fabs(M[i][j]));
+    }
+  if (norm == 0.0) norm = 1.0;
+  for (int i = 0; i < N8; ++i) A[i][i] = CxSub(A[i][i], lambda);
+  const double tiny = norm * 2.220446049250313e-16;
+  const double tiny2 = tiny * tiny;
+  int perm[N8];
+  for (int i = 0; i < N8; ++i) perm[i] = i;
+  for (int c = 0; c < N8; ++c) {
+    int piv = c;
+    double best = CxAbs2(A[c][c]);
+    for (int r = c + 1; r < N8; ++r) {
+      const double ab = CxAbs2(A[r][c]);
+      if (ab > best) {
+        best = ab;
+        piv = r;
+      }
+    }
+    if (piv != c) {
+      for (int j = 0; j < N8; ++j) {
+        const Cx tmp = A[c][j];
+        A[c][j] = A[piv][j];
+        A[piv][j] = tmp;
+      }
+      const int tp = perm[c];
+      perm[c] = perm[piv];
+      perm[piv] = tp;
+    }
+    if (CxAbs2(A[c][c]) < tiny2) A[c][c] = Cx{tiny, 0.0};
+    for (int r = c + 1; r < N8; ++r) {
+      const Cx mlt = CxDiv(A[r][c], A[c][c]);
+      A[r][c] = mlt;
+      for (int j = c + 1; j < N8; ++j) A[r][j] = CxSub(A[r][j], CxMul(mlt, A[c][j]));
+    }
+  }
+  Cx x[N8];
+  for (int i = 0; i < N8; ++i) x[i] = Cx{1.0, 0.0};
+  for (int iter = 0; iter < 3; ++iter) {
+    Cx b[N8];
+    if (iter == 0) {
+      for (int i = 0; i < N8; ++i) b[i] = x[i];
+    } else {
+      for (int i = 0; i < N8; ++i) b[i] = x[perm[i]];
+      for (int i = 0; i < N8; ++i)
+        for (int j = 0; j < i; ++j) b[i] = CxSub(b[i], CxMul(A[i][j], b[j]));
+    }
+    for (int i = N8 - 1; i >= 0; --i) {
+      Cx s = b[i];
+      for (int j = i + 1; j < N8; ++j) s = CxSub(s, CxMul(A[i][j], x[j]));
+      x[i] = CxDiv(s, A[i][i]);
+    }
+    double mx = 0.0;
+    for (int i = 0; i < N8; ++i) mx = fmax(mx, fmax(fabs(x[i].re), fabs(x[i].im)));
+    if (mx == 0.0 || !isfinite(mx)) break;
+    for (int i = 0; i < N8; ++i) {
+      x[i].re = x[i].re / mx;
+      x[i].im = x[i].im / mx;
+    }
+  }
+  for (int i = 0; i < N8; ++i) vec[i] = x[i];
+}
+
+// opengv::math::cayley2rot, row-major.
+__device__ void Cayley2Rot(const double c[3], double R[9]) {
+  const double c0 = c[0] * c[0], c1 = c[1] * c[1], c2 = c[2] * c[2];
+  const double scale = 1 + c0 + c1 + c2;
+  R[0] = 1 + c0 - c1 - c2;
+  R[1] = 2 * (c[0] * c[1] - c[2]);
+  R[2] = 2 * (c[0] * c[2] + c[1]);
+  R[3] = 2 * (c[0] * c[1] + c[2]);
+  R[4] = 1 - c0 + c1 - c2;
+  R[5] = 2 * (c[1] * c[2] - c[0]);
+  R[6] = 2 * (c[0] * c[2] - c[1]);
+  R[7] = 2 * (c[1] * c[2] + c[0]);
+  R[8] = 1 - c0 - c1 + c2;
+  const double inv = 1 / scale;
+  for (int i = 0; i < 9; ++i) R[i] = inv * R[i];
+}
+
+struct Problem {
+  const double* bearings;  // 3 x n
+  const int32_t* cam_idx;
+  const double* points;    // 3 x n
+  const mlc_camera* cams;
+  int n;
+};
+
+// 1 - cos(angle) reprojection score (AbsolutePoseSacProblem.cpp:165-199).
+__device__ double Distance(const Problem& pb, const double T[12], int i) {
+  double tinv[3];
+  for (int a = 0; a < 3; ++a) tinv[a] = -(T[0 * 4 + a] * T[3] + T[1 * 4 + a] * T[7] + T[2 * 4 + a] * T[11]);
+  const double* P = pb.points + 3 * i;
+  double body[3];
+  for (int a = 0; a < 3; ++a)
+    body[a] = T[0 * 4 + a] * P[0] + T[1 * 4 + a] * P[1] + T[2 * 4 + a] * P[2] + tinv[a] * 1.0;
+  const mlc_camera& c = pb.cams[pb.cam_idx[i]];
+  const double d[3] = {body[0] - c.t_B_C[0], body[1] - c.t_B_C[1], body[2] - c.t_B_C[2]};
+  double r[3];
+  for (int a = 0; a < 3; ++a)
+    r[a] = c.R_B_C[0 * 3 + a] * d[0] + c.R_B_C[1 * 3 + a] * d[1] + c.R_B_C[2 * 3 + a] * d[2];
+  const double nrm = sqrt(r[0] * r[0] + r[1] * r[1] + r[2] * r[2]);
+  r[0] /= nrm;
+  r[1] /= nrm;
+  r[2] /= nrm;
+  const double* b = pb.bearings + 3 * i;
+  return 1.0 - (r[0] * b[0] + r[1] * b[1] + r[2] * b[2]);
+}
+
+// gp3p_main + the GP3P branch of computeModelCoefficients. All 32 lanes must call this together
+// (the elimination is executed in lock-step); `active` lanes produce a model.
+__device__ bool ComputeModel(const RansacArgs& a, const Problem& pb, const int sel[4], double* S,
+                             double model[12]) {
+  double f[9], v[9], p[9];
+  for (int i = 0; i < 3; ++i) {
+    const mlc_camera& c = pb.cams[pb.cam_idx[sel[i]]];
+    const double* b = pb.bearings + 3 * sel[i];
+    for (int k = 0; k < 3; ++k) {
+      f[i * 3 + k] = c.R_B_C[k * 3 + 0] * b[0] + c.R_B_C[k * 3 + 1] * b[1] + c.R_B_C[k * 3 + 2] * b[2];
+      v[i * 3 + k] = c.t_B_C[k];
+      p[i * 3 + k] = pb.points[3 * sel[i] + k];
+    }
+  }
+  Gp3pEliminate(a, f, v, p, S);
+  double M[N8][N8];
+  for (int r = 0; r < N8; ++r)
+    for (int c = 0; c < N8; ++c) M[r][c] = 0.0;
+  for (int r = 0; r < 6; ++r)
+    for (int c = 0; c < 8; ++c) {
+      const int slot = a.action[r * 8 + c];
+      M[r][c] = (slot >= 0) ? -S[slot * 32] : -0.0;
+    }
+  M[6][0] = 1.0;
+  M[7][6] = 1.0;
+  for (int r = 0; r < N8; ++r)
+    for (int c = 0; c < N8; ++c)
+      if (!isfinite(M[r][c])) return false;
+  double H[N8][N8];
+  for (int r = 0; r < N8; ++r)
+    for (int c = 0; c < N8; ++c) H[r][c] = M[r][c];
+  Hessenberg(H);
+  double wr[N8], wi[N8];
+  if (!HqrEigenvalues(H, wr, wi)) return false;
+  int num = 0;
+  double min_score = 1000000.0;
+  int min_index = -1;
+  double first[12];
+  for (int c = 0; c < N8; ++c) {
+    if (!(wi[c] < 0.0001)) continue;
+    Cx V[N8];
+    InverseIteration(M, Cx{wr[c], wi[c]}, V);
+    double cay[3], n[3];
+    for (int i = 0; i < 3; ++i) {
+      cay[2 - i] = CxDiv(V[i + 4], V[7]).re;
+      n[2 - i] = CxDiv(V[i + 1], V[7]).re;
+    }
+    double Rt[9];
+    Cayley2Rot(cay, Rt);
+    double R[9];
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 3; ++j) R[i * 3 + j] = Rt[j * 3 + i];
+    double center_cam[3] = {0, 0, 0}, center_world[3] = {0, 0, 0};
+    for (int i = 0; i < 3; ++i) {
+      double tmp[3], w[3];
+      for (int k = 0; k < 3; ++k) w[k] = n[i] * f[i * 3 + k] + v[i * 3 + k];
+      for (int k = 0; k < 3; ++k) tmp[k] = R[k * 3 + 0] * w[0] + R[k * 3 + 1] * w[1] + R[k * 3 + 2] * w[2];
+      for (int k = 0; k < 3; ++k) {
+        center_cam[k] = center_cam[k] + tmp[k];
+        center_world[k] = center_world[k] + p[i * 3 + k];
+      }
+    }
+    double sol[12];
+    for (int k = 0; k < 3; ++k) {
+      sol[k * 4 + 0] = R[k * 3 + 0];
+      sol[k * 4 + 1] = R[k * 3 + 1];
+      sol[k * 4 + 2] = R[k * 3 + 2];
+      sol[k * 4 + 3] = center_world[k] / 3 - center_cam[k] / 3;
+    }
+    if (num == 0)
+      for (int k = 0; k < 12; ++k) first[k] = sol[k];
+    ++num;
+    // disambiguation with the 4th sample point: smallest score, first wins on ties
+    const double score = Distance(pb, sol, sel[3]);
+    if (score < min_score) {
+      min_score = score;
+      min_index = c;
+      for (int k = 0; k < 12; ++k) model[k] = sol[k];
+    }
+  }
+  if (num == 1) {  // a single solution is accepted without the check
+    for (int k = 0; k < 12; ++k) model[k] = first[k];
+    return true;
+  }
+  return min_index != -1;
+}
+
+// PinholeCamera::backProject3 + bearing normalisation (camera-pinhole.cc:47-63,
+// distortion-fisheye.cc:119-143).
+__device__ void BackProject3(const mlc_camera& c, const double* kp, double* b) {
+  double x = (kp[0] - c.cu) / c.fu;
+  double y = (kp[1] - c.cv) / c.fv;
+  if (c.distortion == 1) {
+    const double w = c.dist[0];
+    const double mul2tanwby2 = tan(w / 2.0) * 2.0;
+    const double r_d = sqrt(x * x + y * y);
+    if (!(mul2tanwby2 == 0 || r_d == 0)) {
+      if (fabs(r_d * w) <= (89.0 * 3.14159265358979323846 / 180.0)) {
+        const double r_u = tan(r_d * w) / (r_d * mul2tanwby2);
+        x *= r_u;
+        y *= r_u;
+      }
+    }
+  }
+  const double nrm = sqrt(x * x + y * y + 1.0);
+  b[0] = x / nrm;
+  b[1] = y / nrm;
+  b[2] = 1.0 / nrm;
+}
+
+__device__ __forceinline__ double ShflD(double v, int src) {
+  return __shfl_sync(0xffffffffu, v, src);
+}
+
+__global__ void __launch_bounds__(kWarpsPerBlock * 32) ransac_kernel(RansacArgs a) {
+  __shared__ int s_sel[kWarpsPerBlock][32][4];
+  const int lane = threadIdx.x & 31;
+  const int wib = threadIdx.x >> 5;
+  const int64_t warp = static_cast<int64_t>(blockIdx.x) * kWarpsPerBlock + wib;
+  const int64_t num_warps = static_cast<int64_t>(gridDim.x) * kWarpsPerBlock;
+  double* S = a.slots + static_cast<size_t>(warp) * GP3P_NUM_SLOTS * 32 + lane;
+
+  for (int64_t pi = warp; pi < a.num_problems; pi += num_warps) {
+    const int64_t off = a.offsets[pi];
+    const int n = static_cast<int>(a.offsets[pi + 1] - off);
+    mlc_pose_result res;
+    res.accepted = 0;
+    res.ransac_success = 0;
+    res.num_inliers = 0;
+    res.num_ransac_inliers = 0;
+    res.iterations = 0;
+    for (int i = 0; i < 4; ++i) res.model_indices[i] = -1;
+    res.pad_ = 0;
+    res.inlier_ratio = 0.0;
+    for (int i = 0; i < 12; ++i) res.T_G_I[i] = 0.0;
+    if (a.inlier_flags)
+      for (int i = lane; i < n; i += 32) a.inlier_flags[off + i] = 0;
+    if (n < a.min_inlier_count) {  // handleLoopClosure bails before RANSAC (loop-closure-handler.cc:262-270)
+      if (lane == 0) a.results[pi] = res;
+      continue;
+    }
+    Problem pb;
+    pb.bearings = a.bearings + 3 * off;
+    pb.cam_idx = a.camera_index + off;
+    pb.points = a.landmarks + 3 * off;
+    pb.cams = a.cams;
+    pb.n = n;
+    for (int i = lane; i < n; i += 32) {
+      BackProject3(a.cams[a.camera_index[off + i]], a.keypoints + 2 * (off + i), a.bearings + 3 * (off + i));
+      a.shuffled[off + i] = i;
+    }
+    __syncwarp();
+    int32_t* shuf = a.shuffled + off;
+    int iterations = 0, best = -INT_MAX, skipped = 0, stream_pos = 0;
+    const int max_skip = a.max_iterations * 10;
+    double k = 1.0;
+    bool have_model = false, done = false;
+    double best_model[12];
+    int best_sel[4] = {-1, -1, -1, -1};
+    if (n < 4) {  // getSamples cannot draw 4 unique indices
+      iterations = INT_MAX;
+      done = true;
+    }
+    while (!done) {
+      if (!(static_cast<double>(iterations) < k && skipped < max_skip)) break;
+      if (stream_pos + 128 > a.rnd_len) break;  // cannot happen: stream sized for the worst case
+      if (lane == 0) {
+        for (int t = 0; t < 32; ++t) {
+          for (int i = 0; i < 4; ++i) {
+            const int j = i + a.rnd_stream[stream_pos + 4 * t + i] % (n - i);
+            const int32_t tmp = shuf[i];
+            shuf[i] = shuf[j];
+            shuf[j] = tmp;
+          }
+          for (int i = 0; i < 4; ++i) s_sel[wib][t][i] = shuf[i];
+        }
+      }
+      stream_pos += 128;
+      __syncwarp();
+      int sel[4];
+      for (int i = 0; i < 4; ++i) sel[i] = s_sel[wib][lane][i];
+      double model[12];
+      const bool ok = ComputeModel(a, pb, sel, S, model);
+      int count = 0;
+      if (ok)
+        for (int i = 0; i < n; ++i)
+          if (Distance(pb, model, i) < a.threshold) ++count;
+      __syncwarp();
+      // replay the sequential bookkeeping of Ransac::computeModel in sample order
+      for (int t = 0; t < 32; ++t) {
+        if (!(static_cast<double>(iterations) < k && skipped < max_skip)) {
+          done = true;
+          break;
+        }
+        const int ok_t = __shfl_sync(0xffffffffu, ok ? 1 : 0, t);
+        if (!ok_t) {
+          ++skipped;
+          continue;
+        }
+        const int c_t = __shfl_sync(0xffffffffu, count, t);
+        if (c_t > best) {
+          best = c_t;
+          have_model = true;
+          for (int i = 0; i < 12; ++i) best_model[i] = ShflD(model[i], t);
+          for (int i = 0; i < 4; ++i) best_sel[i] = s_sel[wib][t][i];
+          const double w = static_cast<double>(best) / static_cast<double>(n);
+          double p_no_outliers = 1.0 - pow(w, 4.0);
+          p_no_outliers = fmax(2.220446049250313e-16, p_no_outliers);
+          p_no_outliers = fmin(1.0 - 2.220446049250313e-16, p_no_outliers);
+          k = a.log_one_minus_p / log(p_no_outliers);
+        }
+        ++iterations;
+        if (iterations > a.max_iterations) {
+          done = true;
+          break;
+        }
+      }
+      __syncwarp();
+    }
+    res.iterations = iterations;
+    if (have_model) {
+      res.ransac_success = 1;
+      for (int i = 0; i < 12; ++i) res.T_G_I[i] = best_model[i];
+      for (int i = 0; i < 4; ++i) res.model_indices[i] = best_sel[i];
+      // selectWithinDistance on the best model; distances parked in the bearing scratch is not
+      // possible (still needed), so they are recomputed where compared.
+      int my_inliers = 0;
+      for (int i = lane; i < n; i += 32)
+        if (Distance(pb, best_model, i) < a.threshold) ++my_inliers;
+      int total = my_inliers;
+      for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
+      res.num_ransac_inliers = total;
+      // best inlier per (camera, keypoint): smallest score, first index wins on ties
+      int my_best = 0;
+      for (int i = lane; i < n; i += 32) {
+        const double di = Distance(pb, best_model, i);
+        if (!(di < a.threshold)) continue;
+        bool is_best = true;
+        const int cam = a.camera_index[off + i], kp = a.keypoint_index[off + i];
+        for (int j = 0; j < n && is_best; ++j) {
+          if (j == i || a.camera_index[off + j] != cam || a.keypoint_index[off + j] != kp) continue;
+          const double dj = Distance(pb, best_model, j);
+          if (!(dj < a.threshold)) continue;
+          if (dj < di || (dj == di && j < i)) is_best = false;
+        }
+        if (is_best) ++my_best;
+        if (a.inlier_flags) a.inlier_flags[off + i] = is_best ? 3 : 1;
+      }
+      for (int o = 16; o > 0; o >>= 1) my_best += __shfl_xor_sync(0xffffffffu, my_best, o);
+      res.num_inliers = my_best;
+    }
+    if (res.num_inliers >= a.min_inlier_count) {
+      res.inlier_ratio = static_cast<double>(res.num_inliers) / static_cast<double>(n);
+      if (!(res.inlier_ratio < a.min_inlier_ratio)) res.accepted = 1;
+    }
+    if (lane == 0) a.results[pi] = res;
+    __syncwarp();
+  }
+}
+
+// std::mt19937 + libstdc++ uniform_int_distribution<int>(0, INT_MAX).
+class HostRng {
+ public:
+  HostRng(uint32_t seed, int mapping) : idx_(624), mapping_(mapping) {
+    mt_[0] = seed;
+    for (int i = 1; i < 624; ++i) mt_[i] = 1812433253u * (mt_[i - 1] ^ (mt_[i - 1] >> 30)) + i;
+  }
+  int Next() {
+    if (mapping_ == 1) return static_cast<int>(U32() >> 1);  // libstdc++ >= 11: one draw, x >> 1
+    uint32_t x;
+    do {
+      x = U32();
+    } while (x >= 0x80000000u);  // libstdc++ <= 10: rejection, scaling 1
+    return static_cast<int>(x);
+  }
+
+ private:
+  uint32_t U32() {
+    if (idx_ >= 624) {
+      for (int i = 0; i < 624; ++i) {
+        const uint32_t y = (mt_[i] & 0x80000000u) | (mt_[(i + 1) % 624] & 0x7fffffffu);
+        mt_[i] = mt_[(i + 397) % 624] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+      }
+      idx_ = 0;
+    }
+    uint32_t y = mt_[idx_++];
+    y ^= (y >> 11);
+    y ^= (y << 7) & 0x9d2c5680u;
+    y ^= (y << 15) & 0xefc60000u;
+    y ^= (y >> 18);
+    return y;
+  }
+  uint32_t mt_[624];
+  int idx_, mapping_;
+};
+
+struct ProgramDevice {
+  int4* mops = nullptr;
+  short* init_table = nullptr;
+  short* action = nullptr;
+};
+ProgramDevice g_program;  // per process (one GPU per process)
+
+cudaError_t EnsureProgram() {
+  if (g_program.mops) return cudaSuccess;
+  std::vector<int4> packed(GP3P_NUM_MOPS);
+  for (int i = 0; i < GP3P_NUM_MOPS; ++i) {
+    const short* m = GP3P_MOPS[i];
+    auto u = [](short s) { return static_cast<int>(static_cast<unsigned short>(s)); };
+    packed[i] = make_int4(u(m[0]) | (u(m[1]) << 16), u(m[2]) | (u(m[3]) << 16), u(m[4]) | (u(m[5]) << 16), 0);
+  }
+  cudaError_t e;
+  if ((e = cudaMalloc(&g_program.mops, sizeof(int4) * GP3P_NUM_MOPS)) != cudaSuccess) return e;
+  if ((e = cudaMalloc(&g_program.init_table, sizeof(GP3P_INIT))) != cudaSuccess) return e;
+  if ((e = cudaMalloc(&g_program.action, sizeof(GP3P_ACTION))) != cudaSuccess) return e;
+  if ((e = cudaMemcpy(g_program.mops, packed.data(), sizeof(int4) * GP3P_NUM_MOPS, cudaMemcpyHostToDevice)) != cudaSuccess) return e;
+  if ((e = cudaMemcpy(g_program.init_table, GP3P_INIT, sizeof(GP3P_INIT), cudaMemcpyHostToDevice)) != cudaSuccess) return e;
+  return cudaMemcpy(g_program.action, GP3P_ACTION, sizeof(GP3P_ACTION), cudaMemcpyHostToDevice);
+}
+
+}  // namespace
+
+bool Detector::PnpRansacBatch(const mlc_ransac_settings& rs, const mlc_camera* cams, int num_cams,
+                              int64_t num_problems, const int64_t* offsets, const double* keypoints,
+                              const int32_t* camera_index, const int32_t* keypoint_index,
+                              const double* landmarks, mlc_pose_result* results,
+                              uint8_t* inlier_flags, std::string* err) {
+  std::lock_guard<std::recursive_mutex> lock(mu_);
+  if (num_problems == 0) return true;
+  if (rs.num_ransac_iters < 0 || rs.num_ransac_iters > 100000) {
+    *err = "bad RANSAC iteration count";
+    return false;
+  }
+  const int64_t total = offsets[num_problems];
+  for (int64_t p = 0; p < num_problems; ++p) {
+    if (offsets[p + 1] < offsets[p]) {
+      *err = "offsets must be non-decreasing";
+      return false;
+    }
+  }
+  for (int64_t i = 0; i < total; ++i) {
+    if (camera_index[i] < 0 || camera_index[i] >= num_cams) {
+      *err = "camera index out of range";
+      return false;
+    }
+  }
+  if (!Cuda(EnsureProgram(), "upload GP3P program", err)) return false;
+  // absoluteMultiPoseRansacPinholeCam: threshold from the mean focal length (pnp-pose-estimator.cc:75-132)
+  double focal = 0;
+  for (int i = 0; i < num_cams; ++i) focal += (cams[i].fu + cams[i].fv);
+  focal /= (2.0 * static_cast<double>(num_cams));
+  const double threshold = 1.0 - std::cos(std::atan(rs.ransac_pixel_sigma / focal));
+  // draws: 4 per attempted sample; attempts <= max_iterations + 1 counted + 10 * max_iterations skipped
+  const int rnd_len = 4 * (11 * rs.num_ransac_iters + 2 + 64);
+  std::vector<int32_t> stream(rnd_len);
+  HostRng rng(rs.seed, rs.rng_mapping);
+  for (int i = 0; i < rnd_len; ++i) stream[i] = rng.Next();
+
+  const int blocks = static_cast<int>(std::min<int64_t>((num_problems + kWarpsPerBlock - 1) / kWarpsPerBlock,
+                                                        static_cast<int64_t>(sm_count_) * 2));
+  const size_t warps = static_cast<size_t>(blocks) * kWarpsPerBlock;
+  DevBuf &b_in = d_ransac_[0], &b_scr = d_ransac_[1], &b_slots = d_ransac_[2], &b_out = d_ransac_[3];
+  // input blob layout
+  size_t o = 0;
+  auto place = [&](size_t bytes) {
+    const size_t at = o;
+    o = (o + bytes + 255) & ~static_cast<size_t>(255);
+    return at;
+  };
+  const size_t o_off = place(sizeof(int64_t) * (num_problems + 1));
+  const size_t o_kp = place(sizeof(double) * 2 * total);
+  const size_t o_ci = place(sizeof(int32_t) * total);
+  const size_t o_ki = place(sizeof(int32_t) * total);
+  const size_t o_lm = place(sizeof(double) * 3 * total);
+  const size_t o_cam = place(sizeof(mlc_camera) * num_cams);
+  const size_t o_rnd = place(sizeof(int32_t) * rnd_len);
+  const size_t in_bytes = o;
+  if (!Cuda(b_in.Reserve(in_bytes), "alloc", err) ||
+      !Cuda(b_scr.Reserve(sizeof(double) * 3 * total + sizeof(int32_t) * total + 512), "alloc", err) ||
+      !Cuda(b_slots.Reserve(sizeof(double) * GP3P_NUM_SLOTS * 32 * warps), "alloc", err) ||
+      !Cuda(b_out.Reserve(sizeof(mlc_pose_result) * num_problems + total + 512), "alloc", err))
+    return false;
+  unsigned char* din = b_in.as<unsigned char>();
+  auto up = [&](size_t at, const void* src, size_t bytes) {
+    return bytes == 0 ||
+           Cuda(cudaMemcpyAsync(din + at, src, bytes, cudaMemcpyHostToDevice, stream_), "H2D", err);
+  };
+  if (!up(o_off, offsets, sizeof(int64_t) * (num_problems + 1)) || !up(o_kp, keypoints, sizeof(double) * 2 * total) ||
+      !up(o_ci, camera_index, sizeof(int32_t) * total) || !up(o_ki, keypoint_index, sizeof(int32_t) * total) ||
+      !up(o_lm, landmarks, sizeof(double) * 3 * total) || !up(o_cam, cams, sizeof(mlc_camera) * num_cams) ||
+      !up(o_rnd, stream.data(), sizeof(int32_t) * rnd_len))
+    return false;
+  RansacArgs a;
+  a.num_problems = num_problems;
+  a.offsets = reinterpret_cast<const int64_t*>(din + o_off);
+  a.keypoints = reinterpret_cast<const double*>(din + o_kp);
+  a.camera_index = reinterpret_cast<const int32_t*>(din + o_ci);
+  a.keypoint_index = reinterpret_cast<const int32_t*>(din + o_ki);
+  a.landmarks = reinterpret_cast<const double*>(din + o_lm);
+  a.cams = reinterpret_cast<const mlc_camera*>(din + o_cam);
+  a.num_cams = num_cams;
+  a.threshold = threshold;
+  a.log_one_minus_p = std::log(1.0 - 0.99);
+  a.min_inlier_count = rs.min_inlier_count;
+  a.max_iterations = rs.num_ransac_iters;
+  a.min_inlier_ratio = rs.min_inlier_ratio;
+  a.rnd_stream = reinterpret_cast<const int32_t*>(din + o_rnd);
+  a.rnd_len = rnd_len;
+  a.mops = g_program.mops;
+  a.init_table = g_program.init_table;
+  a.action = g_program.action;
+  a.slots = b_slots.as<double>();
+  a.bearings = b_scr.as<double>();
+  a.shuffled = reinterpret_cast<int32_t*>(b_scr.as<unsigned char>() + ((sizeof(double) * 3 * total + 255) & ~static_cast<size_t>(255)));
+  a.results = b_out.as<mlc_pose_result>();
+  a.inlier_flags = inlier_flags ? b_out.as<uint8_t>() + sizeof(mlc_pose_result) * num_problems : nullptr;
+  ransac_kernel<<<blocks, kWarpsPerBlock * 32, 0, stream_>>>(a);
+  CountLaunch();
+  if (!Cuda(cudaGetLastError(), "ransac kernel", err)) return false;
+  if (!Cuda(cudaMemcpyAsync(results, a.results, sizeof(mlc_pose_result) * num_problems, cudaMemcpyDeviceToHost, stream_),
+            "D2H results", err))
+    return false;
+  if (inlier_flags && total > 0 &&
+      !Cuda(cudaMemcpyAsync(inlier_flags, a.inlier_flags, total, cudaMemcpyDeviceToHost, stream_), "D2H flags", err))
+    return false;
+  return Cuda(cudaStreamSynchronize(stream_), "pnp ransac", err);
+}
+
+}  // namespace mlc
