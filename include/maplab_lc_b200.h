@@ -197,6 +197,37 @@ int mlc_pnp_ransac_batch(mlc_detector* d, const mlc_ransac_settings* rs, const m
                          const int32_t* keypoint_index, const double* landmarks,
                          mlc_pose_result* results, uint8_t* inlier_flags);
 
+/* Landmark positions in the global frame by dense landmark id (what handleLoopClosure reads
+ * through vi_map::VIMap::getLandmark_G_p, LCH/src/loop-closure-handler.cc:272-366). xyz: n x 3. */
+int mlc_set_landmark_positions(mlc_detector* d, const double* xyz, int64_t n);
+
+/* Fused batched query = LoopDetectorNode::queryVertexInDatabase for a batch of vertices
+ * (LCH/src/loop-detector-node.cc:668-766, :819-873): project -> kNN -> Find -> correspondence
+ * assembly -> handleLoopClosure verdict + T_G_I, all on the device. keypoints: 2 doubles per
+ * query descriptor (same order as bits); frame_index of each frame = its camera in `cams`.
+ * results: one per query vertex (in order of first appearance). matches / match_offsets /
+ * num_matches / inlier_flags may be NULL. */
+int mlc_query_batch(mlc_detector* d, const mlc_frame* frames, int64_t num_frames, const uint8_t* bits,
+                    int bytes_per_desc, const double* keypoints, const mlc_camera* cams, int num_cams,
+                    const mlc_ransac_settings* rs, mlc_pose_result* results, int64_t* num_vertices,
+                    mlc_match* matches, int64_t capacity, int64_t* match_offsets,
+                    int64_t* num_matches, uint8_t* inlier_flags);
+/* Same with `d_bits` / `d_keypoints` already resident on the device. */
+int mlc_query_batch_device(mlc_detector* d, const mlc_frame* frames, int64_t num_frames,
+                           const uint8_t* d_bits, int bytes_per_desc, const double* d_keypoints,
+                           const mlc_camera* cams, int num_cams, const mlc_ransac_settings* rs,
+                           mlc_pose_result* results, int64_t* num_vertices, mlc_match* matches,
+                           int64_t capacity, int64_t* match_offsets, int64_t* num_matches,
+                           uint8_t* inlier_flags);
+/* Kernels 3 + 4 on (merged) kNN lists that live on the device: the per-rank tail of the sharded
+ * path after the NCCL all-gather. d_keypoints: 2 per query descriptor. */
+int mlc_query_from_knn_device(mlc_detector* d, const mlc_frame* frames, int64_t num_frames,
+                              const int32_t* d_idx, const float* d_dist, int k,
+                              const double* d_keypoints, const mlc_camera* cams, int num_cams,
+                              const mlc_ransac_settings* rs, mlc_pose_result* results,
+                              int64_t* num_vertices, mlc_match* matches, int64_t capacity,
+                              int64_t* match_offsets, int64_t* num_matches, uint8_t* inlier_flags);
+
 #ifdef __cplusplus
 }
 #endif

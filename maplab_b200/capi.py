@@ -19,6 +19,7 @@ EXPORTS = [
     "mlc_project_device", "mlc_insert", "mlc_insert_batch", "mlc_initialize", "mlc_knn",
     "mlc_knn_device", "mlc_coarse_cells", "mlc_merge_topk_device", "mlc_last_scan_stats",
     "mlc_find_batch", "mlc_find_batch_bits", "mlc_find_from_knn_device", "mlc_pnp_ransac_batch",
+    "mlc_set_landmark_positions", "mlc_query_batch", "mlc_query_batch_device", "mlc_query_from_knn_device",
 ]
 
 
@@ -264,6 +265,53 @@ class Detector:
                                               C.c_void_p(dist_ptr), k, _ptr(matches), C.c_int64(cap),
                                               _ptr(offsets), C.byref(nv), C.byref(nm)))
         return matches[:nm.value], offsets[:nv.value + 1]
+
+    def set_landmark_positions(self, xyz):
+        xyz = np.ascontiguousarray(xyz, np.float64).reshape(-1, 3)
+        _check(lib().mlc_set_landmark_positions(self._h, _ptr(xyz), C.c_int64(len(xyz))))
+
+    def _query(self, fn, frames, a0, a1, a2, cams, rs, want_matches, want_flags, extra=()):
+        frames = np.ascontiguousarray(frames, FRAME_DTYPE)
+        cams = np.ascontiguousarray(cams, CAMERA_DTYPE)
+        rs = rs or default_ransac_settings()
+        nf = len(frames)
+        total = int(frames["num_descriptors"].sum())
+        k = max(self.num_neighbors(), 1)
+        res = np.zeros(max(nf, 1), POSE_DTYPE)
+        nv, nm = C.c_int64(), C.c_int64()
+        cap = total * k + 16 if want_matches else 0
+        matches = np.zeros(cap, MATCH_DTYPE) if want_matches else None
+        offsets = np.zeros(nf + 1, np.int64)
+        flags = np.zeros(total * k + 16, np.uint8) if want_flags else None
+        _check(fn(self._h, _ptr(frames), C.c_int64(nf), a0, a1, a2, *extra, _ptr(cams), len(cams),
+                  C.byref(rs), _ptr(res), C.byref(nv),
+                  _ptr(matches) if matches is not None else C.c_void_p(0), C.c_int64(cap),
+                  _ptr(offsets), C.byref(nm), _ptr(flags) if flags is not None else C.c_void_p(0)))
+        out = dict(results=res[:nv.value], offsets=offsets[:nv.value + 1], num_matches=nm.value)
+        if want_matches:
+            out["matches"] = matches[:nm.value]
+        if want_flags:
+            out["inlier_flags"] = flags[:nm.value]
+        return out
+
+    def query_batch(self, frames, bits, keypoints, cams, rs=None, want_matches=False, want_flags=False):
+        """Fused host-buffer query (the e2e call): returns dict(results, offsets, num_matches, ...)."""
+        bits = np.ascontiguousarray(bits, np.uint8)
+        kp = np.ascontiguousarray(keypoints, np.float64).reshape(-1, 2)
+        assert len(bits) == len(kp)
+        return self._query(lib().mlc_query_batch, frames, _ptr(bits), bits.shape[1], _ptr(kp), cams, rs,
+                           want_matches, want_flags)
+
+    def query_batch_device(self, frames, bits_ptr, bytes_per_desc, keypoints_ptr, cams, rs=None,
+                           want_matches=False, want_flags=False):
+        return self._query(lib().mlc_query_batch_device, frames, C.c_void_p(bits_ptr), bytes_per_desc,
+                           C.c_void_p(keypoints_ptr), cams, rs, want_matches, want_flags)
+
+    def query_from_knn_device(self, frames, idx_ptr, dist_ptr, k, keypoints_ptr, cams, rs=None,
+                              want_matches=False, want_flags=False):
+        return self._query(lib().mlc_query_from_knn_device, frames, C.c_void_p(idx_ptr),
+                           C.c_void_p(dist_ptr), k, cams, rs, want_matches, want_flags,
+                           extra=(C.c_void_p(keypoints_ptr),))
 
     def pnp_ransac_batch(self, cams, offsets, keypoints, camera_index, keypoint_index, landmarks,
                          rs=None, want_flags=True):

@@ -198,4 +198,61 @@ int mlc_pnp_ransac_batch(mlc_detector* d, const mlc_ransac_settings* rs, const m
              : Fail(err);
 }
 
+int mlc_set_landmark_positions(mlc_detector* d, const double* xyz, int64_t n) {
+  MLC_REQUIRE(d, "null detector");
+  std::string err;
+  return d->impl.SetLandmarkPositions(xyz, n, &err) ? 0 : Fail(err);
+}
+
+static int QueryImpl(mlc_detector* d, const mlc_frame* frames, int64_t num_frames, const uint8_t* bits,
+                     int bytes_per_desc, const double* keypoints, bool on_device,
+                     const mlc_camera* cams, int num_cams, const mlc_ransac_settings* rs,
+                     mlc_pose_result* results, int64_t* num_vertices, mlc_match* matches,
+                     int64_t capacity, int64_t* match_offsets, int64_t* num_matches,
+                     uint8_t* inlier_flags) {
+  MLC_REQUIRE(d && rs && cams && num_cams > 0 && num_vertices, "mlc_query_batch: null argument");
+  MLC_REQUIRE(num_frames == 0 || (frames && bits && keypoints && results), "mlc_query_batch: null argument");
+  MLC_REQUIRE(bytes_per_desc > 0 && bytes_per_desc % 16 == 0, "bytes per descriptor must be a multiple of 16");
+  std::string err;
+  return d->impl.QueryBatch(frames, num_frames, bits, bytes_per_desc, keypoints, on_device, cams,
+                            num_cams, *rs, results, num_vertices, matches, capacity, match_offsets,
+                            num_matches, inlier_flags, &err)
+             ? 0
+             : Fail(err);
+}
+int mlc_query_batch(mlc_detector* d, const mlc_frame* frames, int64_t num_frames, const uint8_t* bits,
+                    int bytes_per_desc, const double* keypoints, const mlc_camera* cams, int num_cams,
+                    const mlc_ransac_settings* rs, mlc_pose_result* results, int64_t* num_vertices,
+                    mlc_match* matches, int64_t capacity, int64_t* match_offsets,
+                    int64_t* num_matches, uint8_t* inlier_flags) {
+  return QueryImpl(d, frames, num_frames, bits, bytes_per_desc, keypoints, false, cams, num_cams, rs,
+                   results, num_vertices, matches, capacity, match_offsets, num_matches, inlier_flags);
+}
+int mlc_query_batch_device(mlc_detector* d, const mlc_frame* frames, int64_t num_frames,
+                           const uint8_t* d_bits, int bytes_per_desc, const double* d_keypoints,
+                           const mlc_camera* cams, int num_cams, const mlc_ransac_settings* rs,
+                           mlc_pose_result* results, int64_t* num_vertices, mlc_match* matches,
+                           int64_t capacity, int64_t* match_offsets, int64_t* num_matches,
+                           uint8_t* inlier_flags) {
+  return QueryImpl(d, frames, num_frames, d_bits, bytes_per_desc, d_keypoints, true, cams, num_cams, rs,
+                   results, num_vertices, matches, capacity, match_offsets, num_matches, inlier_flags);
+}
+int mlc_query_from_knn_device(mlc_detector* d, const mlc_frame* frames, int64_t num_frames,
+                              const int32_t* d_idx, const float* d_dist, int k,
+                              const double* d_keypoints, const mlc_camera* cams, int num_cams,
+                              const mlc_ransac_settings* rs, mlc_pose_result* results,
+                              int64_t* num_vertices, mlc_match* matches, int64_t capacity,
+                              int64_t* match_offsets, int64_t* num_matches, uint8_t* inlier_flags) {
+  MLC_REQUIRE(d && rs && cams && num_cams > 0 && num_vertices, "mlc_query_from_knn_device: null argument");
+  MLC_REQUIRE(num_frames == 0 || (frames && d_idx && d_dist && d_keypoints && results),
+              "mlc_query_from_knn_device: null argument");
+  MLC_REQUIRE(k > 0 && k <= 16, "k must be in 1..16");
+  std::string err;
+  return d->impl.QueryFromKnn(frames, num_frames, d_idx, d_dist, k, d_keypoints, cams, num_cams, *rs,
+                              results, num_vertices, matches, capacity, match_offsets, num_matches,
+                              inlier_flags, &err)
+             ? 0
+             : Fail(err);
+}
+
 }  // extern "C"

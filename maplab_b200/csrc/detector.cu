@@ -27,6 +27,8 @@ Detector::~Detector() {
   for (DevBuf* b : bufs) b->Free();
   for (DevBuf& b : d_covis_) b.Free();
   for (DevBuf& b : d_ransac_) b.Free();
+  for (DevBuf& b : d_query_) b.Free();
+  d_landmark_xyz_.Free();
   if (ev0_) cudaEventDestroy(ev0_);
   if (ev1_) cudaEventDestroy(ev1_);
   if (stream_) cudaStreamDestroy(stream_);

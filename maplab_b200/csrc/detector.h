@@ -80,6 +80,28 @@ class Detector {
                    const float* d_dist, int k, mlc_match* matches, int64_t capacity,
                    int64_t* match_offsets, int64_t* num_vertices, int64_t* num_matches,
                    std::string* err);
+  bool FindOnDevice(const mlc_frame* frames, int64_t num_frames, const int32_t* d_idx,
+                    const float* d_dist, int k, std::vector<long long>* fin_off, std::string* err);
+  bool RansacOnDevice(const mlc_ransac_settings& rs, const mlc_camera* cams, int num_cams,
+                      int64_t num_problems, int64_t total, const int64_t* d_offsets,
+                      const double* d_keypoints, const int32_t* d_camera_index,
+                      const int32_t* d_keypoint_index, const double* d_landmarks,
+                      mlc_pose_result* results, uint8_t* inlier_flags, std::string* err);
+  // Landmark positions in the global frame by dense landmark id (vi_map::Landmark::get_p_G of
+  // the landmark store, read by loop-closure-handler.cc:272-366); replicated on every shard.
+  bool SetLandmarkPositions(const double* xyz, int64_t n, std::string* err);
+  // Fused query: project -> kNN -> kernel 3 -> correspondence gather -> kernel 4.
+  bool QueryBatch(const mlc_frame* frames, int64_t num_frames, const uint8_t* bits, int bytes_per_desc,
+                  const double* keypoints, bool inputs_on_device, const mlc_camera* cams, int num_cams,
+                  const mlc_ransac_settings& rs, mlc_pose_result* results, int64_t* num_vertices,
+                  mlc_match* matches, int64_t capacity, int64_t* match_offsets, int64_t* num_matches,
+                  uint8_t* inlier_flags, std::string* err);
+  bool QueryFromKnn(const mlc_frame* frames, int64_t num_frames, const int32_t* d_idx,
+                    const float* d_dist, int k, const double* d_keypoints, const mlc_camera* cams,
+                    int num_cams, const mlc_ransac_settings& rs, mlc_pose_result* results,
+                    int64_t* num_vertices, mlc_match* matches, int64_t capacity,
+                    int64_t* match_offsets, int64_t* num_matches, uint8_t* inlier_flags,
+                    std::string* err);
   bool PnpRansacBatch(const mlc_ransac_settings& rs, const mlc_camera* cams, int num_cams,
                       int64_t num_problems, const int64_t* offsets, const double* keypoints,
                       const int32_t* camera_index, const int32_t* keypoint_index,
@@ -122,6 +144,12 @@ class Detector {
   DevBuf d_q_, d_cells_, d_idx_, d_dist_, d_bits_, d_stats_;
   DevBuf d_covis_[8];
   DevBuf d_ransac_[4];
+  DevBuf d_query_[4];
+  DevBuf d_landmark_xyz_;
+  int64_t num_landmark_xyz_ = 0;
+  std::vector<int32_t> rnd_host_;
+  uint32_t rnd_seed_ = 0;
+  int rnd_mapping_ = -1;
   int64_t last_nq_ = 0;
   int last_nw_ = 0;
   bool last_valid_ = false;

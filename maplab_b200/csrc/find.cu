@@ -66,6 +66,25 @@ bool Detector::FindFromKnn(const mlc_frame* frames, int64_t num_frames, const in
   *num_vertices = 0;
   *num_matches = 0;
   if (num_frames == 0) return true;
+  std::vector<long long> fin_off;
+  if (!FindOnDevice(frames, num_frames, d_idx, d_dist, k, &fin_off, err)) return false;
+  const int64_t nvx = static_cast<int64_t>(fin_off.size()) - 1;
+  for (int64_t v = 0; v <= nvx; ++v) match_offsets[v] = fin_off[v];
+  *num_vertices = nvx;
+  *num_matches = fin_off[nvx];
+  if (fin_off[nvx] > capacity || fin_off[nvx] == 0) return true;  // caller retries with more room
+  if (!Cuda(cudaMemcpyAsync(matches, d_covis_[5].p, sizeof(mlc_match) * fin_off[nvx],
+                            cudaMemcpyDeviceToHost, stream_), "D2H matches", err))
+    return false;
+  return Cuda(cudaStreamSynchronize(stream_), "find", err);
+}
+
+// Kernel 3 for a batch; leaves the accepted matches of all query vertices compacted in
+// d_covis_[5] (canonical order) and returns their per-vertex offsets.
+bool Detector::FindOnDevice(const mlc_frame* frames, int64_t num_frames, const int32_t* d_idx,
+                            const float* d_dist, int k, std::vector<long long>* fin_off_out,
+                            std::string* err) {
+  fin_off_out->assign(1, 0);
   if (s_.scoring != 0) {
     *err = "scoring function not built: only 'accumulation' (0) is available on the device";
     return false;
@@ -193,19 +212,15 @@ bool Detector::FindFromKnn(const mlc_frame* frames, int64_t num_frames, const in
   const int nvx = static_cast<int>(vertices.size());
   std::vector<CovisItem> fin(nvx);
   std::vector<int> fin_counts(nvx);
-  std::vector<long long> fin_off(nvx + 1, 0);
+  std::vector<long long>& fin_off = *fin_off_out;
+  fin_off.assign(nvx + 1, 0);
   int multi = 0;
   for (int vi = 0; vi < nvx; ++vi) {
     const Vertex& v = vertices[vi];
     fin[vi] = items[v.first_frame];
     fin_counts[vi] = v.num_frames < 2 ? counts[v.first_frame] : counts[nf + multi++];
     fin_off[vi + 1] = fin_off[vi] + fin_counts[vi];
-    match_offsets[vi] = fin_off[vi];
   }
-  match_offsets[nvx] = fin_off[nvx];
-  *num_vertices = nvx;
-  *num_matches = fin_off[nvx];
-  if (fin_off[nvx] > capacity) return true;  // caller sees num_matches > capacity and retries
   if (fin_off[nvx] == 0) return true;
   const size_t aux_bytes = sizeof(CovisItem) * nvx + sizeof(int) * nvx + sizeof(long long) * (nvx + 1) + 64;
   if (!Cuda(b_aux.Reserve(aux_bytes), "alloc", err) ||
@@ -219,13 +234,160 @@ bool Detector::FindFromKnn(const mlc_frame* frames, int64_t num_frames, const in
       !Cuda(cudaMemcpyAsync(d_fin_off, fin_off.data(), sizeof(long long) * (nvx + 1), cudaMemcpyHostToDevice, stream_), "H2D", err) ||
       !Cuda(cudaMemcpyAsync(d_fin_cnt, fin_counts.data(), sizeof(int) * nvx, cudaMemcpyHostToDevice, stream_), "H2D", err))
     return false;
-  if (!Cuda(LaunchCompactMatches(b_out.as<mlc_match>(), d_fin, d_fin_cnt, d_fin_off, nvx,
-                                 b_final.as<mlc_match>(), stream_), "compact matches", err))
+  return Cuda(LaunchCompactMatches(b_out.as<mlc_match>(), d_fin, d_fin_cnt, d_fin_off, nvx,
+                                   b_final.as<mlc_match>(), stream_), "compact matches", err);
+}
+
+}  // namespace mlc
+
+namespace mlc {
+namespace {
+// Correspondence assembly of handleLoopClosure (loop-closure-handler.cc:272-366): query keypoint
+// measurement, camera (frame) index, keypoint index and G_landmark position of every match.
+__global__ void gather_correspondences_kernel(const mlc_match* __restrict__ m, int64_t total,
+                                              const int64_t* __restrict__ frame_desc_offset,
+                                              const int32_t* __restrict__ frame_index,
+                                              const double* __restrict__ keypoints,
+                                              const double* __restrict__ lm_xyz, int64_t num_lm,
+                                              double* __restrict__ out_kp, int32_t* __restrict__ out_ci,
+                                              int32_t* __restrict__ out_ki, double* __restrict__ out_lm) {
+  const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (i >= total) return;
+  const mlc_match r = m[i];
+  const int64_t qd = frame_desc_offset[r.query_frame] + r.query_keypoint;
+  out_kp[2 * i] = keypoints[2 * qd];
+  out_kp[2 * i + 1] = keypoints[2 * qd + 1];
+  out_ci[i] = frame_index[r.query_frame];
+  out_ki[i] = r.query_keypoint;
+  const bool known = r.landmark >= 0 && r.landmark < num_lm;
+  const double nan = __longlong_as_double(0x7ff8000000000000LL);
+  for (int c = 0; c < 3; ++c) out_lm[3 * i + c] = known ? lm_xyz[3 * r.landmark + c] : nan;
+}
+}  // namespace
+
+bool Detector::SetLandmarkPositions(const double* xyz, int64_t n, std::string* err) {
+  std::lock_guard<std::recursive_mutex> lock(mu_);
+  if (n < 0 || (n > 0 && !xyz)) {
+    *err = "bad landmark table";
     return false;
-  if (!Cuda(cudaMemcpyAsync(matches, b_final.p, sizeof(mlc_match) * fin_off[nvx], cudaMemcpyDeviceToHost, stream_),
-            "D2H matches", err))
+  }
+  if (!Cuda(d_landmark_xyz_.Reserve(sizeof(double) * 3 * n + 16), "alloc landmarks", err)) return false;
+  if (n > 0 && !Cuda(cudaMemcpyAsync(d_landmark_xyz_.p, xyz, sizeof(double) * 3 * n, cudaMemcpyHostToDevice, stream_),
+                     "H2D landmarks", err))
     return false;
-  return Cuda(cudaStreamSynchronize(stream_), "find", err);
+  num_landmark_xyz_ = n;
+  return Cuda(cudaStreamSynchronize(stream_), "landmark upload", err);
+}
+
+bool Detector::QueryBatch(const mlc_frame* frames, int64_t num_frames, const uint8_t* bits,
+                          int bytes_per_desc, const double* keypoints, bool inputs_on_device,
+                          const mlc_camera* cams, int num_cams, const mlc_ransac_settings& rs,
+                          mlc_pose_result* results, int64_t* num_vertices, mlc_match* matches,
+                          int64_t capacity, int64_t* match_offsets, int64_t* num_matches,
+                          uint8_t* inlier_flags, std::string* err) {
+  std::lock_guard<std::recursive_mutex> lock(mu_);
+  *num_vertices = 0;
+  if (num_matches) *num_matches = 0;
+  if (num_frames == 0) return true;
+  if (s_.shard_count > 1) {
+    *err = "sharded detector: merge the per-shard kNN lists first and call mlc_query_from_knn_device";
+    return false;
+  }
+  if (!EnsureIndex(err)) return false;
+  int64_t n = 0;
+  for (int64_t f = 0; f < num_frames; ++f) n += frames[f].num_descriptors;
+  const int k = NumNeighbors();
+  const size_t qb = static_cast<size_t>(n) * dim() * 4, rb = static_cast<size_t>(n) * k * 4;
+  if (!Cuda(d_q_.Reserve(qb + 16), "alloc", err) || !Cuda(d_idx_.Reserve(rb + 16), "alloc", err) ||
+      !Cuda(d_dist_.Reserve(rb + 16), "alloc", err))
+    return false;
+  const uint8_t* d_bits = bits;
+  const double* d_kp = keypoints;
+  if (!inputs_on_device && n > 0) {
+    const size_t bb = static_cast<size_t>(n) * bytes_per_desc;
+    if (!Cuda(d_bits_.Reserve(bb), "alloc", err) || !Cuda(d_query_[0].Reserve(sizeof(double) * 2 * n), "alloc", err))
+      return false;
+    if (!Cuda(cudaMemcpyAsync(d_bits_.p, bits, bb, cudaMemcpyHostToDevice, stream_), "H2D bits", err) ||
+        !Cuda(cudaMemcpyAsync(d_query_[0].p, keypoints, sizeof(double) * 2 * n, cudaMemcpyHostToDevice, stream_),
+              "H2D keypoints", err))
+      return false;
+    d_bits = d_bits_.as<uint8_t>();
+    d_kp = d_query_[0].as<double>();
+  }
+  if (n > 0) {
+    if (!ProjectDevice(d_bits, bytes_per_desc, n, d_q_.as<float>(), stream_, err)) return false;
+    if (!KnnDevice(d_q_.as<float>(), n, k, d_idx_.as<int32_t>(), d_dist_.as<float>(), stream_, err))
+      return false;
+  }
+  return QueryFromKnn(frames, num_frames, d_idx_.as<int32_t>(), d_dist_.as<float>(), k, d_kp, cams,
+                      num_cams, rs, results, num_vertices, matches, capacity, match_offsets,
+                      num_matches, inlier_flags, err);
+}
+
+bool Detector::QueryFromKnn(const mlc_frame* frames, int64_t num_frames, const int32_t* d_idx,
+                            const float* d_dist, int k, const double* d_keypoints,
+                            const mlc_camera* cams, int num_cams, const mlc_ransac_settings& rs,
+                            mlc_pose_result* results, int64_t* num_vertices, mlc_match* matches,
+                            int64_t capacity, int64_t* match_offsets, int64_t* num_matches,
+                            uint8_t* inlier_flags, std::string* err) {
+  std::lock_guard<std::recursive_mutex> lock(mu_);
+  *num_vertices = 0;
+  if (num_matches) *num_matches = 0;
+  if (num_frames == 0) return true;
+  std::vector<long long> fin_off;
+  if (!FindOnDevice(frames, num_frames, d_idx, d_dist, k, &fin_off, err)) return false;
+  const int64_t nvx = static_cast<int64_t>(fin_off.size()) - 1;
+  const int64_t total = fin_off[nvx];
+  *num_vertices = nvx;
+  if (num_matches) *num_matches = total;
+  if (match_offsets)
+    for (int64_t v = 0; v <= nvx; ++v) match_offsets[v] = fin_off[v];
+  for (int64_t f = 0; f < num_frames; ++f) {
+    if (frames[f].frame_index < 0 || frames[f].frame_index >= num_cams) {
+      *err = "frame_index is the camera index of the query rig: out of range";
+      return false;
+    }
+  }
+  // per-frame tables + problem offsets
+  std::vector<int64_t> desc_off(num_frames), prob_off(fin_off.begin(), fin_off.end());
+  std::vector<int32_t> fidx(num_frames);
+  int64_t at = 0;
+  for (int64_t f = 0; f < num_frames; ++f) {
+    desc_off[f] = at;
+    fidx[f] = frames[f].frame_index;
+    at += frames[f].num_descriptors;
+  }
+  DevBuf &b_tab = d_query_[1], &b_corr = d_query_[2];
+  const size_t t_doff = 0, t_fidx = sizeof(int64_t) * num_frames,
+               t_poff = (t_fidx + sizeof(int32_t) * num_frames + 15) & ~static_cast<size_t>(15);
+  if (!Cuda(b_tab.Reserve(t_poff + sizeof(int64_t) * (nvx + 1) + 16), "alloc", err)) return false;
+  unsigned char* tab = b_tab.as<unsigned char>();
+  if (!Cuda(cudaMemcpyAsync(tab + t_doff, desc_off.data(), sizeof(int64_t) * num_frames, cudaMemcpyHostToDevice, stream_), "H2D", err) ||
+      !Cuda(cudaMemcpyAsync(tab + t_fidx, fidx.data(), sizeof(int32_t) * num_frames, cudaMemcpyHostToDevice, stream_), "H2D", err) ||
+      !Cuda(cudaMemcpyAsync(tab + t_poff, prob_off.data(), sizeof(int64_t) * (nvx + 1), cudaMemcpyHostToDevice, stream_), "H2D", err))
+    return false;
+  const size_t c_kp = 0, c_lm = (sizeof(double) * 2 * total + 255) & ~static_cast<size_t>(255),
+               c_ci = (c_lm + sizeof(double) * 3 * total + 255) & ~static_cast<size_t>(255),
+               c_ki = (c_ci + sizeof(int32_t) * total + 255) & ~static_cast<size_t>(255);
+  if (!Cuda(b_corr.Reserve(c_ki + sizeof(int32_t) * total + 256), "alloc", err)) return false;
+  unsigned char* corr = b_corr.as<unsigned char>();
+  if (total > 0) {
+    gather_correspondences_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream_>>>(
+        d_covis_[5].as<mlc_match>(), total, reinterpret_cast<const int64_t*>(tab + t_doff),
+        reinterpret_cast<const int32_t*>(tab + t_fidx), d_keypoints, d_landmark_xyz_.as<double>(),
+        num_landmark_xyz_, reinterpret_cast<double*>(corr + c_kp), reinterpret_cast<int32_t*>(corr + c_ci),
+        reinterpret_cast<int32_t*>(corr + c_ki), reinterpret_cast<double*>(corr + c_lm));
+    CountLaunch();
+    if (!Cuda(cudaGetLastError(), "gather correspondences", err)) return false;
+    if (matches && total <= capacity &&
+        !Cuda(cudaMemcpyAsync(matches, d_covis_[5].p, sizeof(mlc_match) * total, cudaMemcpyDeviceToHost, stream_),
+              "D2H matches", err))
+      return false;
+  }
+  return RansacOnDevice(rs, cams, num_cams, nvx, total, reinterpret_cast<const int64_t*>(tab + t_poff),
+                        reinterpret_cast<const double*>(corr + c_kp), reinterpret_cast<const int32_t*>(corr + c_ci),
+                        reinterpret_cast<const int32_t*>(corr + c_ki), reinterpret_cast<const double*>(corr + c_lm),
+                        results, inlier_flags, err);
 }
 
 }  // namespace mlc

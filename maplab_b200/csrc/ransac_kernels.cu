@@ -740,10 +740,6 @@ bool Detector::PnpRansacBatch(const mlc_ransac_settings& rs, const mlc_camera* c
                               uint8_t* inlier_flags, std::string* err) {
   std::lock_guard<std::recursive_mutex> lock(mu_);
   if (num_problems == 0) return true;
-  if (rs.num_ransac_iters < 0 || rs.num_ransac_iters > 100000) {
-    *err = "bad RANSAC iteration count";
-    return false;
-  }
   const int64_t total = offsets[num_problems];
   for (int64_t p = 0; p < num_problems; ++p) {
     if (offsets[p + 1] < offsets[p]) {
@@ -757,23 +753,7 @@ bool Detector::PnpRansacBatch(const mlc_ransac_settings& rs, const mlc_camera* c
       return false;
     }
   }
-  if (!Cuda(EnsureProgram(), "upload GP3P program", err)) return false;
-  // absoluteMultiPoseRansacPinholeCam: threshold from the mean focal length (pnp-pose-estimator.cc:75-132)
-  double focal = 0;
-  for (int i = 0; i < num_cams; ++i) focal += (cams[i].fu + cams[i].fv);
-  focal /= (2.0 * static_cast<double>(num_cams));
-  const double threshold = 1.0 - std::cos(std::atan(rs.ransac_pixel_sigma / focal));
-  // draws: 4 per attempted sample; attempts <= max_iterations + 1 counted + 10 * max_iterations skipped
-  const int rnd_len = 4 * (11 * rs.num_ransac_iters + 2 + 64);
-  std::vector<int32_t> stream(rnd_len);
-  HostRng rng(rs.seed, rs.rng_mapping);
-  for (int i = 0; i < rnd_len; ++i) stream[i] = rng.Next();
-
-  const int blocks = static_cast<int>(std::min<int64_t>((num_problems + kWarpsPerBlock - 1) / kWarpsPerBlock,
-                                                        static_cast<int64_t>(sm_count_) * 2));
-  const size_t warps = static_cast<size_t>(blocks) * kWarpsPerBlock;
-  DevBuf &b_in = d_ransac_[0], &b_scr = d_ransac_[1], &b_slots = d_ransac_[2], &b_out = d_ransac_[3];
-  // input blob layout
+  DevBuf& b_in = d_ransac_[0];
   size_t o = 0;
   auto place = [&](size_t bytes) {
     const size_t at = o;
@@ -785,14 +765,7 @@ bool Detector::PnpRansacBatch(const mlc_ransac_settings& rs, const mlc_camera* c
   const size_t o_ci = place(sizeof(int32_t) * total);
   const size_t o_ki = place(sizeof(int32_t) * total);
   const size_t o_lm = place(sizeof(double) * 3 * total);
-  const size_t o_cam = place(sizeof(mlc_camera) * num_cams);
-  const size_t o_rnd = place(sizeof(int32_t) * rnd_len);
-  const size_t in_bytes = o;
-  if (!Cuda(b_in.Reserve(in_bytes), "alloc", err) ||
-      !Cuda(b_scr.Reserve(sizeof(double) * 3 * total + sizeof(int32_t) * total + 512), "alloc", err) ||
-      !Cuda(b_slots.Reserve(sizeof(double) * GP3P_NUM_SLOTS * 32 * warps), "alloc", err) ||
-      !Cuda(b_out.Reserve(sizeof(mlc_pose_result) * num_problems + total + 512), "alloc", err))
-    return false;
+  if (!Cuda(b_in.Reserve(o), "alloc", err)) return false;
   unsigned char* din = b_in.as<unsigned char>();
   auto up = [&](size_t at, const void* src, size_t bytes) {
     return bytes == 0 ||
@@ -800,31 +773,81 @@ bool Detector::PnpRansacBatch(const mlc_ransac_settings& rs, const mlc_camera* c
   };
   if (!up(o_off, offsets, sizeof(int64_t) * (num_problems + 1)) || !up(o_kp, keypoints, sizeof(double) * 2 * total) ||
       !up(o_ci, camera_index, sizeof(int32_t) * total) || !up(o_ki, keypoint_index, sizeof(int32_t) * total) ||
-      !up(o_lm, landmarks, sizeof(double) * 3 * total) || !up(o_cam, cams, sizeof(mlc_camera) * num_cams) ||
-      !up(o_rnd, stream.data(), sizeof(int32_t) * rnd_len))
+      !up(o_lm, landmarks, sizeof(double) * 3 * total))
+    return false;
+  return RansacOnDevice(rs, cams, num_cams, num_problems, total,
+                        reinterpret_cast<const int64_t*>(din + o_off),
+                        reinterpret_cast<const double*>(din + o_kp),
+                        reinterpret_cast<const int32_t*>(din + o_ci),
+                        reinterpret_cast<const int32_t*>(din + o_ki),
+                        reinterpret_cast<const double*>(din + o_lm), results, inlier_flags, err);
+}
+
+// Kernel 4 on correspondences that already live on the device; results (and flags) come back to
+// the host and the stream is synchronised.
+bool Detector::RansacOnDevice(const mlc_ransac_settings& rs, const mlc_camera* cams, int num_cams,
+                              int64_t num_problems, int64_t total, const int64_t* d_offsets,
+                              const double* d_keypoints, const int32_t* d_camera_index,
+                              const int32_t* d_keypoint_index, const double* d_landmarks,
+                              mlc_pose_result* results, uint8_t* inlier_flags, std::string* err) {
+  if (num_problems == 0) return true;
+  if (rs.num_ransac_iters < 0 || rs.num_ransac_iters > 100000 || num_cams <= 0) {
+    *err = "bad RANSAC settings";
+    return false;
+  }
+  if (!Cuda(EnsureProgram(), "upload GP3P program", err)) return false;
+  // absoluteMultiPoseRansacPinholeCam: threshold from the mean focal length (pnp-pose-estimator.cc:75-132)
+  double focal = 0;
+  for (int i = 0; i < num_cams; ++i) focal += (cams[i].fu + cams[i].fv);
+  focal /= (2.0 * static_cast<double>(num_cams));
+  const double threshold = 1.0 - std::cos(std::atan(rs.ransac_pixel_sigma / focal));
+  // draws: 4 per attempted sample; attempts <= max_iterations + 1 counted + 10 * max_iterations skipped
+  const int rnd_len = 4 * (11 * rs.num_ransac_iters + 2 + 64);
+  if (rnd_seed_ != rs.seed || rnd_mapping_ != rs.rng_mapping || static_cast<int>(rnd_host_.size()) != rnd_len) {
+    rnd_host_.resize(rnd_len);
+    HostRng rng(rs.seed, rs.rng_mapping);
+    for (int i = 0; i < rnd_len; ++i) rnd_host_[i] = rng.Next();
+    rnd_seed_ = rs.seed;
+    rnd_mapping_ = rs.rng_mapping;
+  }
+  const int blocks = static_cast<int>(std::min<int64_t>((num_problems + kWarpsPerBlock - 1) / kWarpsPerBlock,
+                                                        static_cast<int64_t>(sm_count_) * 2));
+  const size_t warps = static_cast<size_t>(blocks) * kWarpsPerBlock;
+  DevBuf &b_scr = d_ransac_[1], &b_slots = d_ransac_[2], &b_out = d_ransac_[3];
+  const size_t o_cam = 0;
+  const size_t o_rnd = (sizeof(mlc_camera) * num_cams + 255) & ~static_cast<size_t>(255);
+  const size_t o_bear = (o_rnd + sizeof(int32_t) * rnd_len + 255) & ~static_cast<size_t>(255);
+  const size_t o_shuf = (o_bear + sizeof(double) * 3 * total + 255) & ~static_cast<size_t>(255);
+  if (!Cuda(b_scr.Reserve(o_shuf + sizeof(int32_t) * total + 256), "alloc", err) ||
+      !Cuda(b_slots.Reserve(sizeof(double) * GP3P_NUM_SLOTS * 32 * warps), "alloc", err) ||
+      !Cuda(b_out.Reserve(sizeof(mlc_pose_result) * num_problems + total + 512), "alloc", err))
+    return false;
+  unsigned char* scr = b_scr.as<unsigned char>();
+  if (!Cuda(cudaMemcpyAsync(scr + o_cam, cams, sizeof(mlc_camera) * num_cams, cudaMemcpyHostToDevice, stream_), "H2D", err) ||
+      !Cuda(cudaMemcpyAsync(scr + o_rnd, rnd_host_.data(), sizeof(int32_t) * rnd_len, cudaMemcpyHostToDevice, stream_), "H2D", err))
     return false;
   RansacArgs a;
   a.num_problems = num_problems;
-  a.offsets = reinterpret_cast<const int64_t*>(din + o_off);
-  a.keypoints = reinterpret_cast<const double*>(din + o_kp);
-  a.camera_index = reinterpret_cast<const int32_t*>(din + o_ci);
-  a.keypoint_index = reinterpret_cast<const int32_t*>(din + o_ki);
-  a.landmarks = reinterpret_cast<const double*>(din + o_lm);
-  a.cams = reinterpret_cast<const mlc_camera*>(din + o_cam);
+  a.offsets = d_offsets;
+  a.keypoints = d_keypoints;
+  a.camera_index = d_camera_index;
+  a.keypoint_index = d_keypoint_index;
+  a.landmarks = d_landmarks;
+  a.cams = reinterpret_cast<const mlc_camera*>(scr + o_cam);
   a.num_cams = num_cams;
   a.threshold = threshold;
   a.log_one_minus_p = std::log(1.0 - 0.99);
   a.min_inlier_count = rs.min_inlier_count;
   a.max_iterations = rs.num_ransac_iters;
   a.min_inlier_ratio = rs.min_inlier_ratio;
-  a.rnd_stream = reinterpret_cast<const int32_t*>(din + o_rnd);
+  a.rnd_stream = reinterpret_cast<const int32_t*>(scr + o_rnd);
   a.rnd_len = rnd_len;
   a.mops = g_program.mops;
   a.init_table = g_program.init_table;
   a.action = g_program.action;
   a.slots = b_slots.as<double>();
-  a.bearings = b_scr.as<double>();
-  a.shuffled = reinterpret_cast<int32_t*>(b_scr.as<unsigned char>() + ((sizeof(double) * 3 * total + 255) & ~static_cast<size_t>(255)));
+  a.bearings = reinterpret_cast<double*>(scr + o_bear);
+  a.shuffled = reinterpret_cast<int32_t*>(scr + o_shuf);
   a.results = b_out.as<mlc_pose_result>();
   a.inlier_flags = inlier_flags ? b_out.as<uint8_t>() + sizeof(mlc_pose_result) * num_problems : nullptr;
   ransac_kernel<<<blocks, kWarpsPerBlock * 32, 0, stream_>>>(a);

@@ -1,6 +1,8 @@
 // ORACLE (test infrastructure): flat C entry points for ctypes (tests/, smoke(),
 // bench.py cpu_baseline / --impl reference only).
+#include <algorithm>
 #include <chrono>
+#include <limits>
 #include <cstring>
 #include <thread>
 
@@ -468,6 +470,120 @@ void lco_handle_loop_closure(int n, const double* keypoints, const int* frame_in
   }
   for (size_t i = 0; i < r.best_inlier_per_keypoint.size(); ++i)
     out_best_per_keypoint[i] = r.best_inlier_per_keypoint[i];
+}
+
+// ---- whole query path for a batch of vertices, threaded like common::ParallelProcess ----
+// (contiguous blocks of query vertices over num_threads std::threads:
+//  common/maplab-common/include/maplab-common/parallel-process.h:49-92, driven from
+//  loop-closure-handler/src/loop-detector-node.cc:867-873). Per vertex: ProjectDescriptors ->
+// Find -> correspondence assembly -> HandleLoopClosure (queryVertexInDatabase, :668-766).
+// out_scalars: per vertex {accepted, num_inliers, iterations, num_matches, ransac_success};
+// stage_seconds: summed over threads {project, find, verify}.
+int lco_query_batch(void* h, int num_frames, const int64_t* ts, const int64_t* vertex,
+                    const int64_t* mission, const int* frame_index, const int* n_desc,
+                    const uint8_t* bits, int bytes_per_desc, const double* keypoints,
+                    const double* landmark_xyz, int64_t num_landmarks, const lco_camera* cams,
+                    int n_cams, int min_inlier_count, double min_inlier_ratio, double pixel_sigma,
+                    int num_iters, uint32_t seed, int rng_mapping, int num_threads,
+                    int* out_scalars, double* out_T, double* stage_seconds) {
+  LoopDetector* ld = static_cast<LoopDetector*>(h);
+  const std::vector<Camera> cam_vec = ToCams(cams, n_cams);
+  struct V {
+    int first, count;
+  };
+  std::vector<V> verts;
+  std::vector<int64_t> desc_off(num_frames + 1, 0);
+  for (int f = 0; f < num_frames; ++f) {
+    desc_off[f + 1] = desc_off[f] + n_desc[f];
+    if (f > 0 && vertex[f] == vertex[f - 1])
+      ++verts.back().count;
+    else
+      verts.push_back(V{f, 1});
+  }
+  const int nv = static_cast<int>(verts.size());
+  HandlerSettings hs;
+  hs.min_inlier_count = min_inlier_count;
+  hs.min_inlier_ratio = min_inlier_ratio;
+  hs.ransac_pixel_sigma = pixel_sigma;
+  hs.num_ransac_iters = num_iters;
+  hs.seed = seed;
+  hs.rng_mapping = rng_mapping;
+  const int dim = ld->fixed_projection().target_dim;
+  std::vector<double> t_stage(3 * std::max(num_threads, 1), 0.0);
+  auto work = [&](int tid, int v0, int v1) {
+    using clk = std::chrono::steady_clock;
+    for (int v = v0; v < v1; ++v) {
+      const V& vx = verts[v];
+      std::vector<ProjectedImage> ims(vx.count);
+      std::vector<const ProjectedImage*> ptrs;
+      auto t0 = clk::now();
+      for (int c = 0; c < vx.count; ++c) {
+        const int f = vx.first + c;
+        ims[c].timestamp_ns = ts[f];
+        ims[c].vertex_id = vertex[f];
+        ims[c].frame_index = frame_index[f];
+        ims[c].mission_id = mission[f];
+        ims[c].dim = dim;
+        ims[c].projected_descriptors.resize(static_cast<size_t>(n_desc[f]) * dim);
+        ld->ProjectDescriptors(bits + desc_off[f] * bytes_per_desc, bytes_per_desc, n_desc[f],
+                               ims[c].projected_descriptors.data());
+        ptrs.push_back(&ims[c]);
+      }
+      auto t1 = clk::now();
+      std::vector<Match> matches;
+      ld->Find(ptrs, &matches);
+      auto t2 = clk::now();
+      VerifyInput in;
+      in.n = static_cast<int>(matches.size());
+      for (const Match& m : matches) {
+        int f = vx.first;
+        for (int c = 0; c < vx.count; ++c)
+          if (frame_index[vx.first + c] == m.query_frame_index) f = vx.first + c;
+        const int64_t qd = desc_off[f] + m.query_keypoint;
+        in.keypoints.push_back(keypoints[2 * qd]);
+        in.keypoints.push_back(keypoints[2 * qd + 1]);
+        in.frame_index.push_back(m.query_frame_index);
+        in.keypoint_index.push_back(m.query_keypoint);
+        for (int a = 0; a < 3; ++a) {
+          const bool known = m.landmark >= 0 && m.landmark < num_landmarks;
+          in.landmarks.push_back(known ? landmark_xyz[3 * m.landmark + a]
+                                       : std::numeric_limits<double>::quiet_NaN());
+        }
+      }
+      VerifyResult r;
+      HandleLoopClosure(in, cam_vec, hs, &r);
+      auto t3 = clk::now();
+      int* sc = out_scalars + 5 * static_cast<size_t>(v);
+      sc[0] = r.accepted;
+      sc[1] = r.num_inliers;
+      sc[2] = r.ransac.iterations;
+      sc[3] = in.n;
+      sc[4] = r.ransac.success;
+      if (r.ransac.success)
+        std::memcpy(out_T + 12 * static_cast<size_t>(v), r.ransac.T, sizeof(double) * 12);
+      else
+        std::memset(out_T + 12 * static_cast<size_t>(v), 0, sizeof(double) * 12);
+      t_stage[3 * tid + 0] += std::chrono::duration<double>(t1 - t0).count();
+      t_stage[3 * tid + 1] += std::chrono::duration<double>(t2 - t1).count();
+      t_stage[3 * tid + 2] += std::chrono::duration<double>(t3 - t2).count();
+    }
+  };
+  if (num_threads <= 1) {
+    work(0, 0, nv);
+  } else {
+    std::vector<std::thread> pool;
+    const int per = (nv + num_threads - 1) / num_threads;
+    for (int t = 0; t < num_threads; ++t) {
+      const int v0 = std::min(nv, t * per), v1 = std::min(nv, (t + 1) * per);
+      pool.emplace_back(work, t, v0, v1);
+    }
+    for (auto& th : pool) th.join();
+  }
+  for (int s2 = 0; s2 < 3; ++s2) {
+    stage_seconds[s2] = 0;
+    for (int t = 0; t < std::max(num_threads, 1); ++t) stage_seconds[s2] += t_stage[3 * t + s2];
+  }
+  return nv;
 }
 
 }  // extern "C"

@@ -384,6 +384,35 @@ class Engine:
             self.h = None
 
 
+def query_batch(engine, frames, bits, keypoints, landmark_xyz, cams, min_inlier_count=10,
+                min_inlier_ratio=0.0, pixel_sigma=2.0, num_iters=100, seed=12345, rng_mapping=1,
+                num_threads=1):
+    """Whole query path on the CPU for a batch (frames: dict/structured array with timestamp_ns,
+    vertex_id, mission_id, frame_index, num_descriptors). Returns dict of per-vertex arrays."""
+    ts = np.ascontiguousarray(frames["timestamp_ns"], np.int64)
+    vx = np.ascontiguousarray(frames["vertex_id"], np.int64)
+    ms = np.ascontiguousarray(frames["mission_id"], np.int64)
+    fi = np.ascontiguousarray(frames["frame_index"], np.int32)
+    nd = np.ascontiguousarray(frames["num_descriptors"], np.int32)
+    bits = np.ascontiguousarray(bits, np.uint8)
+    kp = _f64(keypoints)
+    xyz = _f64(landmark_xyz)
+    arr = (Camera * len(cams))(*cams)
+    nf = len(ts)
+    sc = np.zeros((nf, 5), np.int32)
+    T = np.zeros((nf, 3, 4), np.float64)
+    st = np.zeros(3, np.float64)
+    nv = lib().lco_query_batch(engine.h, nf, _p(ts, c_i64_p), _p(vx, c_i64_p), _p(ms, c_i64_p),
+                               _p(fi, c_int_p), _p(nd, c_int_p), _p(bits, c_u8_p), bits.shape[1],
+                               _p(kp, c_double_p), _p(xyz, c_double_p), C.c_int64(len(xyz)), arr,
+                               len(cams), min_inlier_count, C.c_double(min_inlier_ratio),
+                               C.c_double(pixel_sigma), num_iters, C.c_uint32(seed), rng_mapping,
+                               num_threads, _p(sc, c_int_p), _p(T, c_double_p), _p(st, c_double_p))
+    sc, T = sc[:nv], T[:nv]
+    return dict(accepted=sc[:, 0], num_inliers=sc[:, 1], iterations=sc[:, 2], num_matches=sc[:, 3],
+                ransac_success=sc[:, 4], T=T, stage_seconds=dict(project=st[0], find=st[1], verify=st[2]))
+
+
 # ------------------------------------------------------------------ geometry
 class Camera(C.Structure):
     _fields_ = [("fu", C.c_double), ("fv", C.c_double), ("cu", C.c_double), ("cv", C.c_double),

@@ -1,0 +1,102 @@
+"""End-to-end parity of the fused device path (mlc_query_batch: project -> kNN -> vote/cluster ->
+correspondence gather -> GP3P-RANSAC) with the oracle's queryVertexInDatabase restatement:
+accepted loop closures, inlier counts, RANSAC iterations and match counts bit-exact; recovered
+transforms within 1e-6 m / 1e-6 rad (identical in practice)."""
+import numpy as np
+import pytest
+
+from maplab_b200 import capi, synthetic
+from oracle import pyoracle as po
+from helpers import fill_oracle, frames_of, small_world
+
+pytestmark = pytest.mark.gpu
+
+
+def _setup(num_queries=16, **kw):
+    m, blob, _, q = small_world(num_queries=num_queries)
+    det = capi.Detector(blob, capi.default_settings(**kw))
+    ora = po.Engine(blob, po.default_settings(**kw))
+    proj = det.project(m["bits"])
+    frames = frames_of(m["frames"])
+    det.insert_batch(frames, proj, m["landmarks"])
+    det.set_landmark_positions(m["landmark_xyz"])
+    fill_oracle(ora, frames, proj, m["landmarks"])
+    return m, q, det, ora
+
+
+def _compare(out, exp, qframes):
+    res = out["results"]
+    assert len(res) == len(exp["accepted"])
+    assert np.array_equal(res["accepted"], exp["accepted"])
+    assert np.array_equal(res["num_inliers"], exp["num_inliers"])
+    assert np.array_equal(res["iterations"], exp["iterations"])
+    assert np.array_equal(res["ransac_success"], exp["ransac_success"])
+    assert np.array_equal(np.diff(out["offsets"]), exp["num_matches"])
+    T = res["T_G_I"].reshape(-1, 3, 4)
+    ok = exp["ransac_success"].astype(bool)
+    assert np.abs(T[ok][:, :, 3] - exp["T"][ok][:, :, 3]).max(initial=0) <= 1e-6
+    for a, b in zip(T[ok], exp["T"][ok]):
+        dR = a[:, :3] @ b[:, :3].T
+        assert np.arccos(np.clip((np.trace(dR) - 1) / 2, -1, 1)) <= 1e-6
+    assert np.array_equal(T[ok], exp["T"][ok])
+
+
+def test_fused_query_matches_oracle_and_recovers_pose():
+    m, q, det, ora = _setup(num_nearest_neighbors=6)
+    cam = synthetic.camera_dict()
+    qframes = frames_of(q["frames"])
+    out = det.query_batch(qframes, q["bits"], q["keypoints"], capi.make_cameras([cam]),
+                          want_matches=True, want_flags=True)
+    exp = po.query_batch(ora, qframes, q["bits"], q["keypoints"], m["landmark_xyz"],
+                         [po.make_camera(cam["fu"], cam["fv"], cam["cu"], cam["cv"])])
+    _compare(out, exp, qframes)
+    acc = out["results"]["accepted"].astype(bool)
+    assert acc.sum() >= len(acc) // 2, "synthetic revisits should close loops"
+    # accepted closures recover the ground-truth pose of the query keyframe
+    T = out["results"]["T_G_I"].reshape(-1, 3, 4)[acc]
+    Tgt = q["T_G_I"][acc]
+    assert np.abs(T[:, :, 3] - Tgt[:, :, 3]).max() < 0.2
+    # inlier flags are consistent with the verdicts
+    off = out["offsets"]
+    for v in range(len(acc)):
+        f = out["inlier_flags"][off[v]:off[v + 1]]
+        assert (f == 3).sum() == out["results"]["num_inliers"][v]
+
+
+def test_fused_query_multi_camera_and_device_inputs():
+    import torch
+    m, q, det, ora = _setup(num_nearest_neighbors=4, min_verify_matches_num=5)
+    rng = np.random.default_rng(3)
+    c0 = synthetic.camera_dict()
+    c1 = dict(c0, R_B_C=np.array([[0.96, 0, 0.28], [0, 1, 0], [-0.28, 0, 0.96]]), t_B_C=np.array([0.1, 0, 0]))
+    qframes = frames_of(q["frames"])
+    qframes["vertex_id"] = 7000 + np.arange(len(qframes)) // 2
+    qframes["frame_index"] = np.arange(len(qframes)) % 2
+    cams = capi.make_cameras([c0, c1])
+    ocams = [po.make_camera(c["fu"], c["fv"], c["cu"], c["cv"], c["R_B_C"], c["t_B_C"]) for c in (c0, c1)]
+    exp = po.query_batch(ora, qframes, q["bits"], q["keypoints"], m["landmark_xyz"], ocams, num_threads=3)
+    out = det.query_batch(qframes, q["bits"], q["keypoints"], cams)
+    _compare(out, exp, qframes)
+    bits_d = torch.from_numpy(q["bits"]).cuda()
+    kp_d = torch.from_numpy(np.ascontiguousarray(q["keypoints"], np.float64)).cuda()
+    out2 = det.query_batch_device(qframes, bits_d.data_ptr(), 64, kp_d.data_ptr(), cams)
+    _compare(out2, exp, qframes)
+
+
+def test_fused_query_empty_and_no_closure():
+    m, q, det, ora = _setup()
+    cams = capi.make_cameras([synthetic.camera_dict()])
+    out = det.query_batch(frames_of(q["frames"])[:0], q["bits"][:0], q["keypoints"][:0], cams)
+    assert len(out["results"]) == 0
+    # random descriptors: whatever survives covisibility filtering is rejected geometrically
+    rng = np.random.default_rng(1)
+    fr = capi.make_frames([5, 6], [123, 124], [9, 9], [0, 0], [400, 3])
+    bits = rng.integers(0, 256, (403, 64), dtype=np.uint8)
+    kp = rng.uniform(0, 400, (403, 2))
+    out = det.query_batch(fr, bits, kp, cams)
+    cam = synthetic.camera_dict()
+    exp = po.query_batch(ora, fr, bits, kp, m["landmark_xyz"],
+                         [po.make_camera(cam["fu"], cam["fv"], cam["cu"], cam["cv"])])
+    _compare(out, exp, fr)
+    assert out["results"]["accepted"].tolist() == [0, 0]
+    assert out["results"]["iterations"][1] == 0  # 3 descriptors: below lc_min_inlier_count, no RANSAC
