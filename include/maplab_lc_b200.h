@@ -153,6 +153,12 @@ int mlc_knn_device(mlc_detector* d, const float* d_q, int64_t n_q, int k, int32_
 /* Parity checkpoints P2/P3: cell of each descriptor at insert (nw = 1) / visited cells per query
  * (nw = settings.num_closest_words; -1 for pairs with a missing word). cells: n x nw (host). */
 int mlc_coarse_cells(mlc_detector* d, const float* q, int64_t n, int nw, int32_t* cells);
+/* Kernel 2a and kernel 2b separately, device buffers (sharded path: visit lists are computed once
+ * per query slice, exchanged, then every shard scans its own inverted lists for all queries).
+ * d_cells: n x nw int32 (nw = settings.num_closest_words for the scan). */
+int mlc_coarse_device(mlc_detector* d, const float* d_q, int64_t n, int nw, int32_t* d_cells, void* stream);
+int mlc_scan_device(mlc_detector* d, const float* d_q, const int32_t* d_cells, int64_t n_q, int k,
+                    int32_t* d_idx, float* d_dist, void* stream);
 /* Merge `num_lists` per-shard top-k lists (each n_q x k, concatenated list-major, device) into
  * the k smallest by (distance, index) — the consumer of the NCCL all-gather. */
 int mlc_merge_topk_device(mlc_detector* d, const int32_t* d_idx_lists, const float* d_dist_lists,
@@ -196,6 +202,10 @@ int mlc_pnp_ransac_batch(mlc_detector* d, const mlc_ransac_settings* rs, const m
                          const double* keypoints, const int32_t* camera_index,
                          const int32_t* keypoint_index, const double* landmarks,
                          mlc_pose_result* results, uint8_t* inlier_flags);
+
+/* CUDA-event times (ms) of the stages of the last mlc_query_batch* call:
+ * {project, coarse word search, list scan, vote/cluster, gather + RANSAC}. */
+int mlc_last_stage_ms(mlc_detector* d, double* ms5);
 
 /* Landmark positions in the global frame by dense landmark id (what handleLoopClosure reads
  * through vi_map::VIMap::getLandmark_G_p, LCH/src/loop-closure-handler.cc:272-366). xyz: n x 3. */

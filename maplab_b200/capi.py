@@ -19,7 +19,7 @@ EXPORTS = [
     "mlc_project_device", "mlc_insert", "mlc_insert_batch", "mlc_initialize", "mlc_knn",
     "mlc_knn_device", "mlc_coarse_cells", "mlc_merge_topk_device", "mlc_last_scan_stats",
     "mlc_find_batch", "mlc_find_batch_bits", "mlc_find_from_knn_device", "mlc_pnp_ransac_batch",
-    "mlc_set_landmark_positions", "mlc_query_batch", "mlc_query_batch_device", "mlc_query_from_knn_device",
+    "mlc_coarse_device", "mlc_scan_device", "mlc_last_stage_ms", "mlc_set_landmark_positions", "mlc_query_batch", "mlc_query_batch_device", "mlc_query_from_knn_device",
 ]
 
 
@@ -219,6 +219,19 @@ class Detector:
     def knn_device(self, q_ptr, n, k, idx_ptr, dist_ptr, stream=0):
         _check(lib().mlc_knn_device(self._h, C.c_void_p(q_ptr), C.c_int64(n), k, C.c_void_p(idx_ptr),
                                     C.c_void_p(dist_ptr), C.c_void_p(stream)))
+
+    def coarse_device(self, q_ptr, n, nw, cells_ptr, stream=0):
+        _check(lib().mlc_coarse_device(self._h, C.c_void_p(q_ptr), C.c_int64(n), nw, C.c_void_p(cells_ptr),
+                                       C.c_void_p(stream)))
+
+    def scan_device(self, q_ptr, cells_ptr, n, k, idx_ptr, dist_ptr, stream=0):
+        _check(lib().mlc_scan_device(self._h, C.c_void_p(q_ptr), C.c_void_p(cells_ptr), C.c_int64(n), k,
+                                     C.c_void_p(idx_ptr), C.c_void_p(dist_ptr), C.c_void_p(stream)))
+
+    def last_stage_ms(self):
+        ms = (C.c_double * 5)()
+        _check(lib().mlc_last_stage_ms(self._h, ms))
+        return dict(zip(("project", "coarse", "scan", "vote_cluster", "ransac"), [float(x) for x in ms]))
 
     def merge_topk_device(self, idx_lists_ptr, dist_lists_ptr, num_lists, n, k, idx_ptr, dist_ptr,
                           stream=0):

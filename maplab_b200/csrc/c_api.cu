@@ -127,6 +127,24 @@ int mlc_coarse_cells(mlc_detector* d, const float* q, int64_t n, int nw, int32_t
   std::string err;
   return d->impl.CoarseCells(q, n, nw, cells, &err) ? 0 : Fail(err);
 }
+int mlc_coarse_device(mlc_detector* d, const float* d_q, int64_t n, int nw, int32_t* d_cells, void* stream) {
+  MLC_REQUIRE(d && (n == 0 || (d_q && d_cells)), "mlc_coarse_device: null argument");
+  std::string err;
+  return d->impl.CoarseDevice(d_q, n, nw, d_cells, static_cast<cudaStream_t>(stream), &err) ? 0 : Fail(err);
+}
+int mlc_scan_device(mlc_detector* d, const float* d_q, const int32_t* d_cells, int64_t n_q, int k,
+                    int32_t* d_idx, float* d_dist, void* stream) {
+  MLC_REQUIRE(d && (n_q == 0 || (d_q && d_cells && d_idx && d_dist)), "mlc_scan_device: null argument");
+  std::string err;
+  return d->impl.ScanDevice(d_q, d_cells, n_q, k, d_idx, d_dist, static_cast<cudaStream_t>(stream), &err)
+             ? 0
+             : Fail(err);
+}
+int mlc_last_stage_ms(mlc_detector* d, double* ms5) {
+  MLC_REQUIRE(d && ms5, "null argument");
+  std::string err;
+  return d->impl.LastStageMs(ms5, &err) ? 0 : Fail(err);
+}
 int mlc_merge_topk_device(mlc_detector* d, const int32_t* d_idx_lists, const float* d_dist_lists,
                           int num_lists, int64_t n_q, int k, int32_t* d_idx, float* d_dist,
                           void* stream) {

@@ -31,6 +31,8 @@ Detector::~Detector() {
   d_landmark_xyz_.Free();
   if (ev0_) cudaEventDestroy(ev0_);
   if (ev1_) cudaEventDestroy(ev1_);
+  for (cudaEvent_t e : ev_stage_)
+    if (e) cudaEventDestroy(e);
   if (stream_) cudaStreamDestroy(stream_);
 }
 
@@ -75,6 +77,8 @@ bool Detector::Create(const mlc_settings& s, const void* blob, size_t size, std:
     return false;
   if (!Cuda(cudaEventCreate(&ev0_), "cudaEventCreate", err)) return false;
   if (!Cuda(cudaEventCreate(&ev1_), "cudaEventCreate", err)) return false;
+  for (cudaEvent_t& e : ev_stage_)
+    if (!Cuda(cudaEventCreate(&e), "cudaEventCreate", err)) return false;
 
   fp_.Build(vocab_.projection, vocab_.target_dim);
   if (fp_.kp <= 512 && fp_.dim <= 12) {
@@ -350,6 +354,58 @@ bool Detector::CoarseCells(const float* q, int64_t n, int nw, int32_t* cells, st
   if (!Cuda(cudaMemcpyAsync(cells, d_cells_.p, cb, cudaMemcpyDeviceToHost, stream_), "D2H", err)) return false;
   last_valid_ = false;
   return Cuda(cudaStreamSynchronize(stream_), "coarse cells", err);
+}
+
+bool Detector::CoarseDevice(const float* d_q, int64_t n, int nw, int32_t* d_cells, cudaStream_t stream,
+                            std::string* err) {
+  std::lock_guard<std::recursive_mutex> lock(mu_);
+  if (nw <= 0 || nw > 16) {
+    *err = "nw must be in 1..16";
+    return false;
+  }
+  return Cuda(LaunchCoarseWords(coarse_, d_q, n, nw, d_cells, sm_count_, stream), "coarse word search", err);
+}
+
+bool Detector::ScanDevice(const float* d_q, const int32_t* d_cells, int64_t n_q, int k, int32_t* d_idx,
+                          float* d_dist, cudaStream_t stream, std::string* err) {
+  std::lock_guard<std::recursive_mutex> lock(mu_);
+  if (k <= 0 || k > 16) {
+    *err = "k must be in 1..16";
+    return false;
+  }
+  if (!EnsureIndex(err)) return false;
+  if (n_q == 0) return true;
+  const int nw = s_.num_closest_words;
+  // keep a copy of the visit list for mlc_last_scan_stats
+  if (!Cuda(d_cells_.Reserve(static_cast<size_t>(n_q) * nw * 4), "alloc visit list", err)) return false;
+  if (d_cells != d_cells_.as<int32_t>() &&
+      !Cuda(cudaMemcpyAsync(d_cells_.p, d_cells, static_cast<size_t>(n_q) * nw * 4, cudaMemcpyDeviceToDevice, stream),
+            "copy visit list", err))
+    return false;
+  cudaEventRecord(ev0_, stream);
+  if (!Cuda(LaunchImiScan(dim(), d_q, n_q, d_cells, nw, lists_.cell_info, lists_.lists, k, d_idx, d_dist,
+                          sm_count_, stream), "list scan", err))
+    return false;
+  cudaEventRecord(ev1_, stream);
+  last_nq_ = n_q;
+  last_nw_ = nw;
+  last_valid_ = true;
+  return true;
+}
+
+bool Detector::LastStageMs(double* ms5, std::string* err) {
+  std::lock_guard<std::recursive_mutex> lock(mu_);
+  if (!stage_valid_) {
+    *err = "no fused query to report on";
+    return false;
+  }
+  cudaEventSynchronize(ev_stage_[5]);
+  for (int i = 0; i < 5; ++i) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, ev_stage_[i], ev_stage_[i + 1]) != cudaSuccess) ms = 0.f;
+    ms5[i] = ms;
+  }
+  return true;
 }
 
 bool Detector::MergeTopkDevice(const int32_t* d_idx_lists, const float* d_dist_lists, int num_lists,

@@ -66,6 +66,14 @@ class Detector {
   bool Knn(const float* q, int64_t n_q, int k, int32_t* idx, float* dist, std::string* err);
   bool KnnDevice(const float* d_q, int64_t n_q, int k, int32_t* d_idx, float* d_dist,
                  cudaStream_t stream, std::string* err);
+  // Kernel 2a / 2b separately on device buffers (sharded path: cells are computed once per query
+  // slice, all-gathered, then every shard scans its lists for all queries).
+  bool CoarseDevice(const float* d_q, int64_t n, int nw, int32_t* d_cells, cudaStream_t stream,
+                    std::string* err);
+  bool ScanDevice(const float* d_q, const int32_t* d_cells, int64_t n_q, int k, int32_t* d_idx,
+                  float* d_dist, cudaStream_t stream, std::string* err);
+  // CUDA-event stage times of the last fused query: project, coarse, scan, vote_cluster, ransac.
+  bool LastStageMs(double* ms5, std::string* err);
   bool CoarseCells(const float* q, int64_t n, int nw, int32_t* cells, std::string* err);
   bool MergeTopkDevice(const int32_t* d_idx_lists, const float* d_dist_lists, int num_lists,
                        int64_t n_q, int k, int32_t* d_idx, float* d_dist, cudaStream_t stream,
@@ -120,6 +128,8 @@ class Detector {
   int device_ = 0, sm_count_ = 148;
   cudaStream_t stream_ = nullptr;
   cudaEvent_t ev0_ = nullptr, ev1_ = nullptr;
+  cudaEvent_t ev_stage_[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  bool stage_valid_ = false;
   std::recursive_mutex mu_;  // queries are serialised on the detector's stream (SURVEY §8b Threading)
 
   ProjectionDevice proj_;

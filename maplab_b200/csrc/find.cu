@@ -314,14 +314,28 @@ bool Detector::QueryBatch(const mlc_frame* frames, int64_t num_frames, const uin
     d_bits = d_bits_.as<uint8_t>();
     d_kp = d_query_[0].as<double>();
   }
+  stage_valid_ = false;
+  cudaEventRecord(ev_stage_[0], stream_);
   if (n > 0) {
+    const int nw = s_.num_closest_words;
     if (!ProjectDevice(d_bits, bytes_per_desc, n, d_q_.as<float>(), stream_, err)) return false;
-    if (!KnnDevice(d_q_.as<float>(), n, k, d_idx_.as<int32_t>(), d_dist_.as<float>(), stream_, err))
+    cudaEventRecord(ev_stage_[1], stream_);
+    if (!Cuda(d_cells_.Reserve(static_cast<size_t>(n) * nw * 4), "alloc visit list", err)) return false;
+    if (!CoarseDevice(d_q_.as<float>(), n, nw, d_cells_.as<int32_t>(), stream_, err)) return false;
+    cudaEventRecord(ev_stage_[2], stream_);
+    if (!ScanDevice(d_q_.as<float>(), d_cells_.as<int32_t>(), n, k, d_idx_.as<int32_t>(),
+                    d_dist_.as<float>(), stream_, err))
       return false;
+  } else {
+    cudaEventRecord(ev_stage_[1], stream_);
+    cudaEventRecord(ev_stage_[2], stream_);
   }
-  return QueryFromKnn(frames, num_frames, d_idx_.as<int32_t>(), d_dist_.as<float>(), k, d_kp, cams,
-                      num_cams, rs, results, num_vertices, matches, capacity, match_offsets,
-                      num_matches, inlier_flags, err);
+  cudaEventRecord(ev_stage_[3], stream_);
+  const bool ok = QueryFromKnn(frames, num_frames, d_idx_.as<int32_t>(), d_dist_.as<float>(), k, d_kp,
+                               cams, num_cams, rs, results, num_vertices, matches, capacity,
+                               match_offsets, num_matches, inlier_flags, err);
+  stage_valid_ = ok;
+  return ok;
 }
 
 bool Detector::QueryFromKnn(const mlc_frame* frames, int64_t num_frames, const int32_t* d_idx,
@@ -336,6 +350,7 @@ bool Detector::QueryFromKnn(const mlc_frame* frames, int64_t num_frames, const i
   if (num_frames == 0) return true;
   std::vector<long long> fin_off;
   if (!FindOnDevice(frames, num_frames, d_idx, d_dist, k, &fin_off, err)) return false;
+  cudaEventRecord(ev_stage_[4], stream_);
   const int64_t nvx = static_cast<int64_t>(fin_off.size()) - 1;
   const int64_t total = fin_off[nvx];
   *num_vertices = nvx;

@@ -852,6 +852,7 @@ bool Detector::RansacOnDevice(const mlc_ransac_settings& rs, const mlc_camera* c
   a.inlier_flags = inlier_flags ? b_out.as<uint8_t>() + sizeof(mlc_pose_result) * num_problems : nullptr;
   ransac_kernel<<<blocks, kWarpsPerBlock * 32, 0, stream_>>>(a);
   CountLaunch();
+  cudaEventRecord(ev_stage_[5], stream_);
   if (!Cuda(cudaGetLastError(), "ransac kernel", err)) return false;
   if (!Cuda(cudaMemcpyAsync(results, a.results, sizeof(mlc_pose_result) * num_problems, cudaMemcpyDeviceToHost, stream_),
             "D2H results", err))
