@@ -1,0 +1,144 @@
+// maplab_lc_b200_shim.h — header-only C++ shim over the C-ABI with the method names, argument meaning
+// and error behaviour of matching_based_loopclosure::LoopDetector
+// (algorithms/loopclosure/matching-based-loopclosure/include/matching-based-loopclosure/matching-based-engine.h:18-52)
+// and loop_closure::IndexInterface (…/index-interface.h:9-36). Eigen-free (POD views) so that it
+// compiles anywhere; the Eigen-typed adapter a maplab maintainer adds on top is in INTEGRATION.md.
+// A violated precondition / device error throws std::runtime_error (the reference CHECK-aborts);
+// define MAPLAB_LC_B200_ABORT to abort instead.
+#ifndef MAPLAB_LC_B200_SHIM_H_
+#define MAPLAB_LC_B200_SHIM_H_
+
+#include <cstdint>
+#include <cstdlib>
+#include <stdexcept>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "maplab_lc_b200.h"
+
+namespace maplab_lc_b200 {
+
+inline void Check(int rc) {
+  if (rc == 0) return;
+#ifdef MAPLAB_LC_B200_ABORT
+  std::abort();
+#else
+  throw std::runtime_error(mlc_last_error());
+#endif
+}
+
+// Dense numbering of 128-bit maplab ids (aslam::HashId: two uint64 words).
+struct Id128 {
+  uint64_t hi, lo;
+  bool operator==(const Id128& o) const { return hi == o.hi && lo == o.lo; }
+};
+struct Id128Hash {
+  size_t operator()(const Id128& id) const { return static_cast<size_t>(id.hi ^ id.lo); }
+};
+class IdTable {
+ public:
+  int64_t Number(const Id128& id) {
+    auto it = map_.find(id);
+    if (it != map_.end()) return it->second;
+    const int64_t n = static_cast<int64_t>(ids_.size());
+    map_.emplace(id, n);
+    ids_.push_back(id);
+    return n;
+  }
+  const Id128& Id(int64_t number) const { return ids_.at(static_cast<size_t>(number)); }
+  size_t size() const { return ids_.size(); }
+
+ private:
+  std::unordered_map<Id128, int64_t, Id128Hash> map_;
+  std::vector<Id128> ids_;
+};
+
+// loop_closure::ProjectedImage (descriptor-projection.h:23-31) with dense ids and POD storage.
+struct ProjectedImage {
+  int64_t timestamp_nanoseconds = 0;
+  int64_t vertex_id = 0;  // dense number of keyframe_id.vertex_id
+  int32_t frame_index = 0;
+  int64_t mission_id = 0;
+  std::vector<float> projected_descriptors;  // dim x n column-major == n rows of dim floats
+  std::vector<int64_t> landmarks;            // dense landmark numbers (database images)
+};
+
+class LoopDetector {
+ public:
+  LoopDetector(const mlc_settings& settings, const void* quantizer_blob, size_t size) {
+    Check(mlc_create(&settings, quantizer_blob, size, &d_));
+    dim_ = mlc_target_dim(d_);
+  }
+  ~LoopDetector() { mlc_destroy(d_); }
+  LoopDetector(const LoopDetector&) = delete;
+  LoopDetector& operator=(const LoopDetector&) = delete;
+
+  void Initialize() { Check(mlc_initialize(d_)); }
+  void Clear() { Check(mlc_clear(d_)); }
+  size_t NumEntries() const { return static_cast<size_t>(mlc_num_entries(d_)); }
+  int NumDescriptors() const { return static_cast<int>(mlc_num_descriptors(d_)); }
+  int dim() const { return dim_; }
+  mlc_detector* handle() { return d_; }
+
+  // descriptors: (bytes x n) column-major uchar == n rows of `bytes`; out: dim x n column-major.
+  void ProjectDescriptors(const uint8_t* descriptors, int bytes_per_descriptor, int64_t n,
+                          float* projected) const {
+    Check(mlc_project(d_, descriptors, bytes_per_descriptor, n, projected));
+  }
+
+  void Insert(const ProjectedImage& image) {
+    const int64_t n = dim_ ? static_cast<int64_t>(image.projected_descriptors.size()) / dim_ : 0;
+    if (!image.landmarks.empty() && static_cast<int64_t>(image.landmarks.size()) != n)
+      Check(Fail("Insert: projected_descriptors.cols() != landmarks.size()"));
+    mlc_frame f{image.timestamp_nanoseconds, image.vertex_id, image.mission_id, image.frame_index,
+                static_cast<int32_t>(n)};
+    Check(mlc_insert(d_, &f, image.projected_descriptors.data(),
+                     image.landmarks.empty() ? nullptr : image.landmarks.data()));
+  }
+
+  // All images belong to one vertex (CHECK at matching-based-engine.cc:57). `parallelize_if_possible`
+  // is accepted for signature parity; the device path is batched either way.
+  void Find(const std::vector<const ProjectedImage*>& images, bool /*parallelize_if_possible*/,
+            std::vector<mlc_match>* matches) const {
+    matches->clear();
+    if (images.empty()) return;
+    std::vector<mlc_frame> frames;
+    std::vector<float> proj;
+    for (const ProjectedImage* im : images) {
+      if (im->vertex_id != images[0]->vertex_id) Check(Fail("Find: images of different vertices"));
+      const int64_t n = static_cast<int64_t>(im->projected_descriptors.size()) / dim_;
+      frames.push_back(mlc_frame{im->timestamp_nanoseconds, im->vertex_id, im->mission_id,
+                                 im->frame_index, static_cast<int32_t>(n)});
+      proj.insert(proj.end(), im->projected_descriptors.begin(), im->projected_descriptors.end());
+    }
+    const int64_t cap = static_cast<int64_t>(proj.size() / dim_) * 16 + 16;
+    matches->resize(static_cast<size_t>(cap));
+    std::vector<int64_t> offsets(frames.size() + 1);
+    int64_t nv = 0, nm = 0;
+    Check(mlc_find_batch(d_, frames.data(), static_cast<int64_t>(frames.size()), proj.data(),
+                         matches->data(), cap, offsets.data(), &nv, &nm));
+    matches->resize(static_cast<size_t>(nm));
+  }
+
+  // loop_closure::IndexInterface::GetNNearestNeighborsForFeatures (index-interface.h:27-35).
+  void GetNNearestNeighborsForFeatures(const float* query_features, int64_t n, int num_neighbors,
+                                       int32_t* indices, float* distances) const {
+    Check(mlc_knn(d_, query_features, n, num_neighbors, indices, distances));
+  }
+
+ private:
+  static int Fail(const char* msg) {
+    last_shim_error() = msg;
+    throw std::runtime_error(msg);
+  }
+  static std::string& last_shim_error() {
+    static thread_local std::string e;
+    return e;
+  }
+  mlc_detector* d_ = nullptr;
+  int dim_ = 0;
+};
+
+}  // namespace maplab_lc_b200
+#endif  // MAPLAB_LC_B200_SHIM_H_
