@@ -1,0 +1,316 @@
+// Kernel 2a of the loop-closure path: coarse word search = common::FindClosestWords
+// (imilib/inverted-multi-index-common.h:148-188): two ε-approximate libnabo kd-tree searches
+// (nabo/kdtree_cpu.cpp:368-447 recurseKnn, allowSelfMatch, sorted results; heap:
+// nabo/index_heap.h:263-363) followed by common::MultiSequenceAlgorithm (:84-134).
+//
+// The kd-tree search is emulated bit-for-bit (same traversal order, same fp32 operations without
+// contraction, same pruning tests), because the reference's coarse search is NOT an exact top-k
+// (SURVEY F3). Work item = (query descriptor, half). To keep the warps converged the depth-first
+// search runs as a per-lane state machine whose every iteration performs ONE micro-step — descend
+// one inner node, score one bucket point, or pop one frame — and lanes that finish pull the next
+// work item of their warp's range (persistent lanes). Blocks with even/odd index own half 0 / 1
+// and stage only that half's tree in shared memory; the per-lane result heaps live in shared
+// memory too ([entry][thread], conflict free).
+#include "device_index.h"
+#include "ptx.cuh"
+
+namespace mlc {
+namespace {
+
+constexpr int kMaxWords = 16;     // nw <= 16
+constexpr int kMaxStack = 48;     // >= tree depth (checked on the host)
+constexpr int kThreads = 256;
+
+enum LaneState : int { kIdle = 0, kDescend = 1, kLeaf = 2, kPop = 3, kDone = 4 };
+constexpr uint32_t kRestoreTag = 0x80000000u;
+
+template <int D>
+__device__ __forceinline__ float Pick(const float (&v)[D], uint32_t d) {
+  float r = v[0];
+#pragma unroll
+  for (int i = 1; i < D; ++i) r = (d == static_cast<uint32_t>(i)) ? v[i] : r;
+  return r;
+}
+template <int D>
+__device__ __forceinline__ void Put(float (&v)[D], uint32_t d, float x) {
+#pragma unroll
+  for (int i = 0; i < D; ++i) v[i] = (d == static_cast<uint32_t>(i)) ? x : v[i];
+}
+
+template <int D>
+__global__ void __launch_bounds__(kThreads)
+kd_search_kernel(CoarseParams p, const float* __restrict__ q, int64_t n, int kk1, int kk2, int kk_max,
+                 int32_t* __restrict__ out_idx, float* __restrict__ out_val) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int half = blockIdx.x & 1;
+  const int kk = half ? kk2 : kk1;
+  const KdNodeDev* nodes = half ? p.nodes2 : p.nodes1;
+  const int32_t* buckets = half ? p.buckets2 : p.buckets1;
+  const float* cloud = half ? p.cloud2 : p.cloud1;
+  // shared memory: [heap values kk x T][heap indices kk x T][tree blob of this half]
+  float* hv = reinterpret_cast<float*>(smem_raw);
+  int32_t* hi = reinterpret_cast<int32_t*>(smem_raw + sizeof(float) * kk_max * kThreads);
+  const size_t half_base = half ? static_cast<size_t>(n) * kk1 : 0;  // [half 0: n x kk1][half 1: n x kk2]
+  if (p.stage_in_smem) {
+    unsigned char* dst = smem_raw + 2 * sizeof(float) * kk_max * kThreads;
+    const uint32_t begin = half ? p.off_nodes2 : p.off_nodes1;
+    const uint32_t end = half ? p.packed_bytes : p.off_nodes2;
+    const unsigned char* src = reinterpret_cast<const unsigned char*>(p.packed) + begin;
+    for (uint32_t i = threadIdx.x * 16; i < end - begin; i += kThreads * 16)
+      *reinterpret_cast<uint4*>(dst + i) = *reinterpret_cast<const uint4*>(src + i);
+    __syncthreads();
+    nodes = reinterpret_cast<const KdNodeDev*>(dst + ((half ? p.off_nodes2 : p.off_nodes1) - begin));
+    buckets = reinterpret_cast<const int32_t*>(dst + ((half ? p.off_buckets2 : p.off_buckets1) - begin));
+    cloud = reinterpret_cast<const float*>(dst + ((half ? p.off_cloud2 : p.off_cloud1) - begin));
+  }
+  const int tid = threadIdx.x;
+  const int lane = tid & 31;
+  const uint32_t lanemask_lt = (1u << lane) - 1u;
+  // contiguous range of queries for this warp
+  const int64_t warps_total = static_cast<int64_t>(gridDim.x >> 1) * (kThreads / 32);
+  const int64_t warp_id = static_cast<int64_t>(blockIdx.x >> 1) * (kThreads / 32) + (tid >> 5);
+  const int64_t per_warp = (n + warps_total - 1) / warps_total;
+  int64_t warp_next = warp_id * per_warp;
+  const int64_t warp_end = min(n, warp_next + per_warp);
+
+  const float inf = __int_as_float(0x7f800000);
+  float qv[D], off[D];
+  uint32_t st_tag[kMaxStack];
+  float st_val[kMaxStack];
+  int state = kIdle, sp = 0;
+  uint32_t node = 0, pos = 0, end = 0;
+  float rd = 0.f, head = inf;
+  int64_t item = 0;
+
+  for (;;) {
+    // ---- refill idle lanes from the warp's range ----
+    const uint32_t idle = __ballot_sync(0xffffffffu, state == kIdle);
+    if (idle) {
+      if (state == kIdle) {
+        item = warp_next + __popc(idle & lanemask_lt);
+        if (item < warp_end) {
+          const float* src = q + item * (2 * D) + half * D;
+#pragma unroll
+          for (int d = 0; d < D; ++d) {
+            qv[d] = __ldg(src + d);
+            off[d] = 0.f;
+          }
+          for (int j = 0; j < kk; ++j) {
+            hv[j * kThreads + tid] = inf;
+            hi[j * kThreads + tid] = -1;
+          }
+          head = inf;
+          node = 0;
+          rd = 0.f;
+          sp = 0;
+          state = kDescend;
+        } else {
+          state = kDone;
+        }
+      }
+      warp_next += __popc(idle);
+    }
+    if (__all_sync(0xffffffffu, state == kDone)) break;
+
+    if (state == kDescend) {
+      const KdNodeDev nd = nodes[node];
+      if (nd.dim == static_cast<uint32_t>(D)) {  // leaf
+        pos = nd.cut_or_bucket;
+        end = pos + nd.child_or_size;
+        state = (nd.child_or_size > 0) ? kLeaf : kPop;
+      } else {
+        const uint32_t cd = nd.dim;
+        const float old_off = Pick<D>(off, cd);
+        const float new_off = __fsub_rn(Pick<D>(qv, cd), __uint_as_float(nd.cut_or_bucket));
+        // rd += -old_off * old_off + new_off * new_off   (for the far child)
+        st_val[sp] = __fadd_rn(rd, __fadd_rn(__fmul_rn(-old_off, old_off), __fmul_rn(new_off, new_off)));
+        st_tag[sp] = node;  // far child and offsets are re-derived from the parent when popped
+        ++sp;
+        node = (new_off > 0.f) ? nd.child_or_size : node + 1;  // near child first
+      }
+    } else if (state == kLeaf) {
+      const int pidx = buckets[pos];
+      const float* pt = cloud + static_cast<size_t>(pidx) * D;
+      float dist = 0.f;
+#pragma unroll
+      for (int j = 0; j < D; ++j) {
+        const float diff = __fsub_rn(qv[j], pt[j]);
+        dist = __fadd_rn(dist, __fmul_rn(diff, diff));
+      }
+      if ((dist <= p.max_radius2) && (dist < head)) {
+        // IndexHeapBruteForceVector::replaceHead: shift while the predecessor is strictly larger
+        int i = kk - 1;
+        for (; i > 0; --i) {
+          const float pv = hv[(i - 1) * kThreads + tid];
+          if (pv > dist) {
+            hv[i * kThreads + tid] = pv;
+            hi[i * kThreads + tid] = hi[(i - 1) * kThreads + tid];
+          } else {
+            break;
+          }
+        }
+        hv[i * kThreads + tid] = dist;
+        hi[i * kThreads + tid] = pidx;
+        head = hv[(kk - 1) * kThreads + tid];
+      }
+      if (++pos == end) state = kPop;
+    } else if (state == kPop) {
+      if (sp == 0) {
+        // search finished: emit the sorted heap
+        int32_t* oi = out_idx + half_base + static_cast<size_t>(item) * kk;
+        float* ov = out_val + half_base + static_cast<size_t>(item) * kk;
+        for (int j = 0; j < kk; ++j) {
+          oi[j] = hi[j * kThreads + tid];
+          ov[j] = hv[j * kThreads + tid];
+        }
+        state = kIdle;
+      } else {
+        --sp;
+        const uint32_t tag = st_tag[sp];
+        if (tag & kRestoreTag) {
+          Put<D>(off, tag & 0xFFu, st_val[sp]);  // leave the far subtree: restore the offset
+        } else {
+          const float frd = st_val[sp];
+          if ((frd <= p.max_radius2) && (__fmul_rn(frd, p.max_error2) < head)) {
+            const KdNodeDev nd = nodes[tag];
+            const uint32_t cd = nd.dim;
+            const float new_off = __fsub_rn(Pick<D>(qv, cd), __uint_as_float(nd.cut_or_bucket));
+            st_tag[sp] = kRestoreTag | cd;
+            st_val[sp] = Pick<D>(off, cd);  // old offset (the near subtree restored it)
+            ++sp;
+            Put<D>(off, cd, new_off);
+            node = (new_off > 0.f) ? tag + 1 : nd.child_or_size;  // far child
+            rd = frd;
+            state = kDescend;
+          }
+        }
+      }
+    }
+  }
+}
+
+// MultiSequenceAlgorithm: pop the pairs (i1, i2) in ascending (d1[i1] + d2[i2], i1, i2).
+__global__ void __launch_bounds__(128)
+multi_sequence_kernel(const int32_t* __restrict__ h_idx, const float* __restrict__ h_val, int64_t n,
+                      int n1, int n2, int num_words, int w2, int32_t* __restrict__ cells) {
+  const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (i >= n) return;
+  int32_t idx1[kMaxWords], idx2[kMaxWords];
+  float d1[kMaxWords], d2[kMaxWords];
+  for (int j = 0; j < n1; ++j) {
+    idx1[j] = h_idx[i * n1 + j];
+    d1[j] = h_val[i * n1 + j];
+  }
+  const size_t base2 = static_cast<size_t>(n) * n1;
+  for (int j = 0; j < n2; ++j) {
+    idx2[j] = h_idx[base2 + i * n2 + j];
+    d2[j] = h_val[base2 + i * n2 + j];
+  }
+  uint32_t used[(kMaxWords * kMaxWords) / 32];
+#pragma unroll
+  for (int j = 0; j < (kMaxWords * kMaxWords) / 32; ++j) used[j] = 0;
+  float pq_sum[kMaxWords + 4];
+  int pq_i1[kMaxWords + 4], pq_i2[kMaxWords + 4];
+  pq_sum[0] = __fadd_rn(d1[0], d2[0]);
+  pq_i1[0] = 0;
+  pq_i2[0] = 0;
+  int pq_n = 1, emitted = 0;
+  int32_t* dst = cells + i * num_words;
+  while (pq_n > 0 && emitted < num_words) {
+    int best = 0;
+    for (int j = 1; j < pq_n; ++j) {
+      const bool less = (pq_sum[j] < pq_sum[best]) ||
+                        (!(pq_sum[best] < pq_sum[j]) &&
+                         ((pq_i1[j] < pq_i1[best]) || (pq_i1[j] == pq_i1[best] && pq_i2[j] < pq_i2[best])));
+      if (less) best = j;
+    }
+    const int i1 = pq_i1[best], i2 = pq_i2[best];
+    --pq_n;
+    pq_sum[best] = pq_sum[pq_n];
+    pq_i1[best] = pq_i1[pq_n];
+    pq_i2[best] = pq_i2[pq_n];
+    const int word_index = i1 * n2 + i2;
+    used[word_index >> 5] |= 1u << (word_index & 31);
+    const int a = idx1[i1], b = idx2[i2];
+    // A pair with a missing word (fewer than nw words inside the radius) is skipped (-1).
+    dst[emitted++] = (a < 0 || b < 0) ? -1 : a * w2 + b;
+    if (i1 + 1 < n1) {
+      const int nb = word_index + n2 - 1;
+      if (i2 == 0 || ((used[nb >> 5] >> (nb & 31)) & 1u)) {
+        pq_sum[pq_n] = __fadd_rn(d1[i1 + 1], d2[i2]);
+        pq_i1[pq_n] = i1 + 1;
+        pq_i2[pq_n] = i2;
+        ++pq_n;
+      }
+    }
+    if (i2 + 1 < n2) {
+      const int nb = word_index - n2 + 1;
+      if (i1 == 0 || ((used[nb >> 5] >> (nb & 31)) & 1u)) {
+        pq_sum[pq_n] = __fadd_rn(d1[i1], d2[i2 + 1]);
+        pq_i1[pq_n] = i1;
+        pq_i2[pq_n] = i2 + 1;
+        ++pq_n;
+      }
+    }
+  }
+  for (int j = emitted; j < num_words; ++j) dst[j] = -1;
+}
+
+template <int D>
+cudaError_t LaunchSearch(const CoarseParams& p, const float* d_q, int64_t n, int kk1, int kk2,
+                         int32_t* h_idx, float* h_val, int sm_count, cudaStream_t stream) {
+  const uint32_t tree_bytes =
+      p.stage_in_smem ? max(p.off_nodes2, p.packed_bytes - p.off_nodes2) : 0u;
+  const int kk_max = max(kk1, kk2);
+  const size_t smem = 2 * sizeof(float) * kk_max * kThreads + tree_bytes;
+  cudaError_t e = cudaFuncSetAttribute(kd_search_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       static_cast<int>(smem));
+  if (e != cudaSuccess) return e;
+  int per_sm = 1;
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kd_search_kernel<D>, kThreads, smem);
+  if (e != cudaSuccess) return e;
+  if (per_sm < 1) per_sm = 1;
+  int64_t blocks_per_half = (static_cast<int64_t>(sm_count) * per_sm) / 2;
+  const int64_t needed = (n + kThreads - 1) / kThreads;  // at least one query per lane to start with
+  if (blocks_per_half > needed) blocks_per_half = needed;
+  if (blocks_per_half < 1) blocks_per_half = 1;
+  kd_search_kernel<D><<<static_cast<unsigned>(2 * blocks_per_half), kThreads, smem, stream>>>(
+      p, d_q, n, kk1, kk2, kk_max, h_idx, h_val);
+  CountLaunch();
+  return cudaGetLastError();
+}
+
+}  // namespace
+
+size_t CoarseScratchBytes(const CoarseParams& p, int64_t n, int num_words) {
+  const int kk1 = min(p.num_words1, num_words), kk2 = min(p.num_words2, num_words);
+  return static_cast<size_t>(n) * (kk1 + kk2) * 8 + 256;
+}
+
+cudaError_t LaunchCoarseWords(const CoarseParams& p, const float* d_q, int64_t n, int num_words,
+                              int32_t* d_cells, void* scratch, int sm_count, cudaStream_t stream) {
+  if (n <= 0) return cudaSuccess;
+  if (num_words <= 0 || num_words > kMaxWords) return cudaErrorInvalidValue;
+  const int kk1 = min(p.num_words1, num_words), kk2 = min(p.num_words2, num_words);
+  int32_t* h_idx = static_cast<int32_t*>(scratch);
+  float* h_val = reinterpret_cast<float*>(static_cast<unsigned char*>(scratch) +
+                                          ((static_cast<size_t>(n) * (kk1 + kk2) * 4 + 127) & ~static_cast<size_t>(127)));
+  cudaError_t e;
+  switch (p.sub_dim) {
+#define MLC_CASE(D)                                                                     \
+  case D:                                                                               \
+    e = LaunchSearch<D>(p, d_q, n, kk1, kk2, h_idx, h_val, sm_count, stream);           \
+    break;
+    MLC_CASE(1) MLC_CASE(2) MLC_CASE(3) MLC_CASE(4) MLC_CASE(5) MLC_CASE(6) MLC_CASE(7) MLC_CASE(8)
+#undef MLC_CASE
+    default:
+      return cudaErrorInvalidValue;
+  }
+  if (e != cudaSuccess) return e;
+  multi_sequence_kernel<<<static_cast<unsigned>((n + 127) / 128), 128, 0, stream>>>(
+      h_idx, h_val, n, kk1, kk2, num_words, p.num_words2, d_cells);
+  CountLaunch();
+  return cudaGetLastError();
+}
+
+}  // namespace mlc

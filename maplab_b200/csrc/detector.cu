@@ -29,6 +29,7 @@ Detector::~Detector() {
   for (DevBuf& b : d_ransac_) b.Free();
   for (DevBuf& b : d_query_) b.Free();
   d_landmark_xyz_.Free();
+  d_coarse_scratch_.Free();
   if (ev0_) cudaEventDestroy(ev0_);
   if (ev1_) cudaEventDestroy(ev1_);
   for (cudaEvent_t e : ev_stage_)
@@ -266,9 +267,7 @@ bool Detector::EnsureIndex(std::string* err) {
               "H2D db descriptors", err))
       return false;
     if (!Cuda(d_db_cells_.Reserve(static_cast<size_t>(n) * 4), "alloc cells", err)) return false;
-    if (!Cuda(LaunchCoarseWords(coarse_, d_desc, n, 1, d_db_cells_.as<int32_t>(), sm_count_, stream_),
-              "cell assignment", err))
-      return false;
+    if (!CoarseChunks(d_desc, n, 1, d_db_cells_.as<int32_t>(), stream_, err)) return false;
   }
   bool ok = Cuda(BuildImiLists(d_db_cells_.as<int32_t>(), d_desc, n, d, static_cast<uint32_t>(cells64),
                                s_.shard_rank, s_.shard_count, &lists_, stream_),
@@ -303,9 +302,7 @@ bool Detector::KnnDevice(const float* d_q, int64_t n_q, int k, int32_t* d_idx, f
   if (n_q == 0) return true;
   const int nw = s_.num_closest_words;
   if (!Cuda(d_cells_.Reserve(static_cast<size_t>(n_q) * nw * 4), "alloc visit list", err)) return false;
-  if (!Cuda(LaunchCoarseWords(coarse_, d_q, n_q, nw, d_cells_.as<int32_t>(), sm_count_, stream),
-            "coarse word search", err))
-    return false;
+  if (!CoarseChunks(d_q, n_q, nw, d_cells_.as<int32_t>(), stream, err)) return false;
   cudaEventRecord(ev0_, stream);
   if (!Cuda(LaunchImiScan(dim(), d_q, n_q, d_cells_.as<int32_t>(), nw, lists_.cell_info, lists_.lists,
                           k, d_idx, d_dist, sm_count_, stream),
@@ -348,9 +345,7 @@ bool Detector::CoarseCells(const float* q, int64_t n, int nw, int32_t* cells, st
   const size_t qb = static_cast<size_t>(n) * dim() * 4, cb = static_cast<size_t>(n) * nw * 4;
   if (!Cuda(d_q_.Reserve(qb), "alloc", err) || !Cuda(d_cells_.Reserve(cb), "alloc", err)) return false;
   if (!Cuda(cudaMemcpyAsync(d_q_.p, q, qb, cudaMemcpyHostToDevice, stream_), "H2D", err)) return false;
-  if (!Cuda(LaunchCoarseWords(coarse_, d_q_.as<float>(), n, nw, d_cells_.as<int32_t>(), sm_count_, stream_),
-            "coarse word search", err))
-    return false;
+  if (!CoarseChunks(d_q_.as<float>(), n, nw, d_cells_.as<int32_t>(), stream_, err)) return false;
   if (!Cuda(cudaMemcpyAsync(cells, d_cells_.p, cb, cudaMemcpyDeviceToHost, stream_), "D2H", err)) return false;
   last_valid_ = false;
   return Cuda(cudaStreamSynchronize(stream_), "coarse cells", err);
@@ -363,7 +358,23 @@ bool Detector::CoarseDevice(const float* d_q, int64_t n, int nw, int32_t* d_cell
     *err = "nw must be in 1..16";
     return false;
   }
-  return Cuda(LaunchCoarseWords(coarse_, d_q, n, nw, d_cells, sm_count_, stream), "coarse word search", err);
+  return CoarseChunks(d_q, n, nw, d_cells, stream, err);
+}
+
+// Kernel 2a in chunks of <= 4 M descriptors so that the per-half word-list scratch stays bounded.
+bool Detector::CoarseChunks(const float* d_q, int64_t n, int nw, int32_t* d_cells, cudaStream_t stream,
+                            std::string* err) {
+  const int64_t kChunk = 4 << 20;
+  const int64_t first = std::min<int64_t>(n, kChunk);
+  if (!Cuda(d_coarse_scratch_.Reserve(CoarseScratchBytes(coarse_, first, nw)), "alloc coarse scratch", err))
+    return false;
+  for (int64_t s = 0; s < n; s += kChunk) {
+    const int64_t c = std::min<int64_t>(kChunk, n - s);
+    if (!Cuda(LaunchCoarseWords(coarse_, d_q + s * dim(), c, nw, d_cells + s * nw, d_coarse_scratch_.p,
+                                sm_count_, stream), "coarse word search", err))
+      return false;
+  }
+  return true;
 }
 
 bool Detector::ScanDevice(const float* d_q, const int32_t* d_cells, int64_t n_q, int k, int32_t* d_idx,

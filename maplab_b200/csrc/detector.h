@@ -154,6 +154,8 @@ class Detector {
   DevBuf d_q_, d_cells_, d_idx_, d_dist_, d_bits_, d_stats_;
   DevBuf d_covis_[8];
   DevBuf d_ransac_[4];
+  DevBuf d_coarse_scratch_;
+  bool CoarseChunks(const float* d_q, int64_t n, int nw, int32_t* d_cells, cudaStream_t stream, std::string* err);
   DevBuf d_query_[4];
   DevBuf d_landmark_xyz_;
   int64_t num_landmark_xyz_ = 0;

@@ -27,8 +27,10 @@ struct CoarseParams {
   float max_radius2, max_error2;
   int stage_in_smem;
 };
+// scratch: CoarseScratchBytes(p, n, num_words) bytes for the per-half sorted word lists.
+size_t CoarseScratchBytes(const CoarseParams& p, int64_t n, int num_words);
 cudaError_t LaunchCoarseWords(const CoarseParams& p, const float* d_q, int64_t n, int num_words,
-                              int32_t* d_cells, int sm_count, cudaStream_t stream);
+                              int32_t* d_cells, void* scratch, int sm_count, cudaStream_t stream);
 
 // ---- kernel 2b -------------------------------------------------------------------------------
 // Inverted lists in HBM. Cell c owns `len` entries starting at byte 16 * start16 of `lists`:

@@ -1,8 +1,5 @@
 // Kernel 2 of the loop-closure path: inverted-multi-index kNN.
-//   2a  coarse_words_kernel   — FindClosestWords: two ε-approximate kd-tree searches (libnabo
-//                               traversal order, fp32, no FMA contraction) + multi-sequence
-//                               (imilib/inverted-multi-index-common.h:84-134, :148-188;
-//                               nabo/kdtree_cpu.cpp:368-447, nabo/index_heap.h:263-363)
+//   2a  (coarse_kernels.cu)   — FindClosestWords: kd-tree searches + multi-sequence
 //   2b  imi_scan_kernel       — InvertedMultiIndex::GetNNearestNeighbors: stream the visited
 //                               cells' inverted lists, squared L2 in the canonical fp32 order,
 //                               top-k by (distance, index) (imilib/inverted-multi-index.h:100-161,
@@ -17,254 +14,11 @@
 namespace mlc {
 
 // =============================================================================================
-// 2a: coarse word search
-// =============================================================================================
-namespace {
-
-constexpr int kMaxSubDim = 8;
-constexpr int kMaxWords = 16;   // nw <= 16
-constexpr int kMaxStack = 96;   // 2 * max tree depth
-
-struct TreeView {
-  const KdNodeDev* nodes;
-  const int32_t* buckets;
-  const float* cloud;  // dim x n column-major
-};
-
-// libnabo IndexHeapBruteForceVector: ascending array, head = last element.
-struct LinearHeap {
-  int k;
-  int32_t idx[kMaxWords];
-  float val[kMaxWords];
-  __device__ void Reset() {
-    for (int i = 0; i < k; ++i) {
-      idx[i] = -1;
-      val[i] = __int_as_float(0x7f800000);
-    }
-  }
-  __device__ float Head() const { return val[k - 1]; }
-  __device__ void ReplaceHead(int index, float value) {
-    int i = k - 1;
-    for (; i > 0; --i) {
-      if (val[i - 1] > value) {
-        val[i] = val[i - 1];
-        idx[i] = idx[i - 1];
-      } else {
-        break;
-      }
-    }
-    val[i] = value;
-    idx[i] = index;
-  }
-};
-
-// Frame kinds of the explicit DFS stack.
-constexpr uint32_t kFrameFar = 1u << 30;      // deferred far-child test
-constexpr uint32_t kFrameRestore = 2u << 30;  // restore off[cd] after the far subtree
-
-// recurseKnn (allowSelfMatch, no statistics) as an explicit-stack DFS. The pruning test of a far
-// child is evaluated when its frame is popped, i.e. after the near subtree has been searched —
-// exactly when the recursive reference evaluates it.
-__device__ void KdKnn(const TreeView& t, int dim, const float* q, float max_radius2,
-                      float max_error2, LinearHeap* heap) {
-  heap->Reset();
-  float off[kMaxSubDim];
-#pragma unroll
-  for (int d = 0; d < kMaxSubDim; ++d) off[d] = 0.f;
-  uint32_t st_node[kMaxStack];
-  float st_rd[kMaxStack], st_new[kMaxStack], st_old[kMaxStack];
-  int sp = 0;
-  uint32_t n = 0;
-  float rd = 0.f;
-  bool descend = true;
-  for (;;) {
-    if (!descend) {
-      if (sp == 0) break;
-      --sp;
-      const uint32_t tag = st_node[sp];
-      const uint32_t cd = (tag >> 20) & 0xFu;
-      if (tag & kFrameRestore) {
-        off[cd] = st_old[sp];
-        continue;
-      }
-      // far child
-      const float frd = st_rd[sp];
-      if (!((frd <= max_radius2) && (__fmul_rn(frd, max_error2) < heap->Head()))) continue;
-      off[cd] = st_new[sp];
-      st_node[sp] = kFrameRestore | (cd << 20);  // st_old[sp] already holds the old offset
-      ++sp;
-      n = tag & 0xFFFFFu;
-      rd = frd;
-    }
-    descend = false;
-    // walk down to a leaf, deferring the far children
-    for (;;) {
-      const KdNodeDev node = t.nodes[n];
-      if (node.dim == static_cast<uint32_t>(dim)) {
-        const uint32_t bs = node.child_or_size;
-        for (uint32_t i = 0; i < bs; ++i) {
-          const int pidx = t.buckets[node.cut_or_bucket + i];
-          const float* p = t.cloud + static_cast<size_t>(pidx) * dim;
-          float dist = 0.f;
-          for (int j = 0; j < dim; ++j) {
-            const float diff = __fsub_rn(q[j], p[j]);
-            dist = __fadd_rn(dist, __fmul_rn(diff, diff));
-          }
-          if ((dist <= max_radius2) && (dist < heap->Head())) heap->ReplaceHead(pidx, dist);
-        }
-        break;
-      }
-      const uint32_t cd = node.dim;
-      const float old_off = off[cd];
-      const float new_off = __fsub_rn(q[cd], __uint_as_float(node.cut_or_bucket));
-      // rd += -old_off * old_off + new_off * new_off;
-      const float frd = __fadd_rn(
-          rd, __fadd_rn(__fmul_rn(-old_off, old_off), __fmul_rn(new_off, new_off)));
-      const uint32_t right = node.child_or_size;
-      uint32_t near_child, far_child;
-      if (new_off > 0.f) {
-        near_child = right;
-        far_child = n + 1;
-      } else {
-        near_child = n + 1;
-        far_child = right;
-      }
-      st_node[sp] = kFrameFar | (cd << 20) | far_child;
-      st_rd[sp] = frd;
-      st_new[sp] = new_off;
-      st_old[sp] = old_off;
-      ++sp;
-      n = near_child;
-    }
-  }
-}
-
-// MultiSequenceAlgorithm: pop the pairs (i1, i2) in ascending (d1[i1] + d2[i2], i1, i2).
-__device__ int MultiSequence(const LinearHeap& h1, const LinearHeap& h2, int num_words, int w2,
-                             int32_t* cells_out) {
-  const int n1 = h1.k, n2 = h2.k;
-  uint32_t used[(kMaxWords * kMaxWords) / 32];
-#pragma unroll
-  for (int i = 0; i < (kMaxWords * kMaxWords) / 32; ++i) used[i] = 0;
-  float pq_sum[kMaxWords + 4];
-  int pq_i1[kMaxWords + 4], pq_i2[kMaxWords + 4];
-  int pq_n = 0;
-  pq_sum[0] = __fadd_rn(h1.val[0], h2.val[0]);
-  pq_i1[0] = 0;
-  pq_i2[0] = 0;
-  pq_n = 1;
-  int emitted = 0;
-  while (pq_n > 0 && emitted < num_words) {
-    int best = 0;
-    for (int i = 1; i < pq_n; ++i) {
-      const bool less = (pq_sum[i] < pq_sum[best]) ||
-                        (!(pq_sum[best] < pq_sum[i]) &&
-                         ((pq_i1[i] < pq_i1[best]) ||
-                          (pq_i1[i] == pq_i1[best] && pq_i2[i] < pq_i2[best])));
-      if (less) best = i;
-    }
-    const int i1 = pq_i1[best], i2 = pq_i2[best];
-    --pq_n;
-    pq_sum[best] = pq_sum[pq_n];
-    pq_i1[best] = pq_i1[pq_n];
-    pq_i2[best] = pq_i2[pq_n];
-    const int word_index = i1 * n2 + i2;
-    used[word_index >> 5] |= 1u << (word_index & 31);
-    const int a = h1.idx[i1], b = h2.idx[i2];
-    // A pair with a missing word (fewer than nw words inside the radius) is skipped (-1).
-    cells_out[emitted++] = (a < 0 || b < 0) ? -1 : a * w2 + b;
-    if (i1 + 1 < n1) {
-      const int nb = word_index + n2 - 1;
-      if (i2 == 0 || ((used[nb >> 5] >> (nb & 31)) & 1u)) {
-        pq_sum[pq_n] = __fadd_rn(h1.val[i1 + 1], h2.val[i2]);
-        pq_i1[pq_n] = i1 + 1;
-        pq_i2[pq_n] = i2;
-        ++pq_n;
-      }
-    }
-    if (i2 + 1 < n2) {
-      const int nb = word_index - n2 + 1;
-      if (i1 == 0 || ((used[nb >> 5] >> (nb & 31)) & 1u)) {
-        pq_sum[pq_n] = __fadd_rn(h1.val[i1], h2.val[i2 + 1]);
-        pq_i1[pq_n] = i1;
-        pq_i2[pq_n] = i2 + 1;
-        ++pq_n;
-      }
-    }
-  }
-  return emitted;
-}
-
-__global__ void __launch_bounds__(128)
-coarse_words_kernel(CoarseParams p, const float* __restrict__ q, int64_t n, int num_words,
-                    int32_t* __restrict__ cells) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  TreeView t1{p.nodes1, p.buckets1, p.cloud1};
-  TreeView t2{p.nodes2, p.buckets2, p.cloud2};
-  if (p.stage_in_smem) {
-    // Stage both trees (nodes, buckets, word coordinates) in shared memory.
-    unsigned char* dst = smem_raw;
-    const unsigned char* src = reinterpret_cast<const unsigned char*>(p.packed);
-    for (uint32_t i = threadIdx.x * 16; i < p.packed_bytes; i += blockDim.x * 16)
-      *reinterpret_cast<uint4*>(dst + i) = *reinterpret_cast<const uint4*>(src + i);
-    __syncthreads();
-    t1.nodes = reinterpret_cast<const KdNodeDev*>(dst + p.off_nodes1);
-    t1.buckets = reinterpret_cast<const int32_t*>(dst + p.off_buckets1);
-    t1.cloud = reinterpret_cast<const float*>(dst + p.off_cloud1);
-    t2.nodes = reinterpret_cast<const KdNodeDev*>(dst + p.off_nodes2);
-    t2.buckets = reinterpret_cast<const int32_t*>(dst + p.off_buckets2);
-    t2.cloud = reinterpret_cast<const float*>(dst + p.off_cloud2);
-  }
-  const int dim = p.sub_dim;
-  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n;
-       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    float qa[kMaxSubDim], qb[kMaxSubDim];
-    const float* qp = q + i * (2 * dim);
-#pragma unroll
-    for (int d = 0; d < kMaxSubDim; ++d) {
-      qa[d] = d < dim ? qp[d] : 0.f;
-      qb[d] = d < dim ? qp[dim + d] : 0.f;
-    }
-    LinearHeap h1, h2;
-    h1.k = min(p.num_words1, num_words);
-    h2.k = min(p.num_words2, num_words);
-    KdKnn(t1, dim, qa, p.max_radius2, p.max_error2, &h1);
-    KdKnn(t2, dim, qb, p.max_radius2, p.max_error2, &h2);
-    int32_t out[kMaxWords];
-    const int got = MultiSequence(h1, h2, num_words, p.num_words2, out);
-    int32_t* dst = cells + i * num_words;
-    for (int j = 0; j < num_words; ++j) dst[j] = j < got ? out[j] : -1;
-  }
-}
-
-}  // namespace
-
-cudaError_t LaunchCoarseWords(const CoarseParams& p, const float* d_q, int64_t n, int num_words,
-                              int32_t* d_cells, int sm_count, cudaStream_t stream) {
-  if (n <= 0) return cudaSuccess;
-  const int threads = 128;
-  const size_t smem = p.stage_in_smem ? p.packed_bytes : 0;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(coarse_words_kernel,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    if (e != cudaSuccess) return e;
-    attr_set = true;
-  }
-  int64_t blocks = (n + threads - 1) / threads;
-  const int64_t cap = static_cast<int64_t>(sm_count) * 8;
-  if (blocks > cap) blocks = cap;
-  coarse_words_kernel<<<static_cast<unsigned>(blocks), threads, smem, stream>>>(p, d_q, n, num_words,
-                                                                                d_cells);
-  CountLaunch();
-  return cudaGetLastError();
-}
-
-// =============================================================================================
 // 2b: inverted-list scan
 // =============================================================================================
 namespace {
 
+constexpr int kMaxWords = 16;   // nw <= 16
 constexpr uint64_t kEmptyKey = 0x7f800000FFFFFFFFull;  // (+inf, idx -1): sorts after every entry
 
 // (stored - query).squaredNorm() in the canonical fp32 order of the oracle (packets of four
