@@ -8,12 +8,19 @@
 //   getBestStructureMatchForEveryKeypoint            loop-closure-handler/src/inlier-index-with-reprojection-error.cc:7-51
 //
 // The sample sequence of opengv's RANSAC does not depend on the data (persistent partial
-// Fisher-Yates over an explicit int stream), so the warp draws 32 samples ahead, every lane solves
-// one GP3P hypothesis (Groebner elimination as the table-driven micro-op program shared with the
-// oracle, 8x8 eigen-solve, Cayley back-substitution) and scores it against all correspondences;
-// the sequential bookkeeping (skips, best-so-far with strict >, adaptive k) is then replayed in
-// sample order. fp64 throughout; this file is compiled with -fmad=false so every expression
-// rounds exactly like the SSE2 build of the reference/oracle.
+// Fisher-Yates over an explicit int stream), so the warp draws kHyp samples ahead and evaluates
+// them speculatively; the sequential bookkeeping (skips, best-so-far with strict >, adaptive k) is
+// then replayed in sample order. Per hypothesis:
+//   * Groebner elimination: the micro-op program the oracle executes sequentially
+//     (gp3p_program.inc) re-scheduled offline into waves of independent three-address ops
+//     (gp3p_schedule.inc, gen_gp3p_schedule.py; dead ops removed, bit-identical results). The 32
+//     lanes execute one wave chunk per step on a slot array in shared memory: 253 steps instead
+//     of 12 253 dependent operations;
+//   * 8x8 eigenvalues (Hessenberg + Francis QR) by one lane per hypothesis, then one lane per
+//     (hypothesis, eigenvalue) for inverse iteration, Cayley back-substitution and the
+//     disambiguation score; inlier counting with the lanes striding over the correspondences.
+// fp64 throughout; this file is compiled with -fmad=false so every expression rounds exactly
+// like the SSE2 build of the reference/oracle.
 #include <climits>
 #include <cmath>
 #include <vector>
@@ -23,6 +30,7 @@
 namespace mlc {
 namespace {
 #include "gp3p_program.inc"
+#include "gp3p_schedule.inc"
 
 enum {
   MOP_DIVSUB = 0,
@@ -38,6 +46,7 @@ enum {
 
 constexpr int N8 = 8;
 constexpr int kWarpsPerBlock = 4;
+constexpr int kHyp = 8;  // hypotheses evaluated speculatively per round
 
 struct RansacArgs {
   int64_t num_problems;
@@ -54,69 +63,67 @@ struct RansacArgs {
   double min_inlier_ratio;
   const int32_t* rnd_stream;    // uniform_int_distribution<int>(0, INT_MAX) draws, host generated
   int rnd_len;
-  const int4* mops;             // packed micro-ops {op | a<<16, b | c<<16, d | e<<16, 0}
+  const uint4* wops;            // wave-scheduled ops {op | d<<16, a | b<<16, c | e<<16, 0}
+  const unsigned short* wave_offsets;
   const short* init_table;      // GP3P_INIT
   const short* action;          // GP3P_ACTION
-  double* slots;                // per warp: GP3P_NUM_SLOTS x 32 doubles
   double* bearings;             // 3 per correspondence
   int32_t* shuffled;            // per correspondence
   mlc_pose_result* results;
   uint8_t* inlier_flags;        // may be null
 };
 
-// ---------------------------------------------------------------- GP3P elimination (per lane)
-// S(slot) of this lane lives at slots[slot * 32 + lane]: the 32 lanes of a warp execute the same
-// micro-op on 32 hypotheses with fully coalesced accesses.
-__device__ void Gp3pEliminate(const RansacArgs& a, const double* f, const double* v, const double* p,
-                              double* S) {
-  for (int s = 0; s < GP3P_NUM_SLOTS; ++s) S[s * 32] = 0.0;
-  for (int e = 0; e < GP3P_NUM_INIT; ++e) {
+// ---------------------------------------------------------------- GP3P elimination (per warp)
+// One hypothesis, all 32 lanes. S = slot array of this warp in shared memory. fvp = {f, v, p}
+// (3 x 9 doubles, column per point). Leaves the 6x8 action-matrix rows in M (row-major 8x8).
+__device__ void Gp3pEliminateWarp(const RansacArgs& a, const double* fvp, double* S, double* M, int lane) {
+  for (int s = lane; s < GP3P_W_NUM_SLOTS; s += 32) S[s] = 0.0;
+  __syncwarp();
+  for (int e = lane; e < GP3P_NUM_INIT; e += 32) {
     const short* in = a.init_table + e * 18;
     double acc = 0.0;
     const int nt = in[1];
     for (int t = 0; t < nt; ++t) {
       const short* tm = in + 2 + 4 * t;
-      const double* src = tm[1] == 0 ? f : (tm[1] == 1 ? v : p);
-      const double term = static_cast<double>(tm[0]) * src[tm[3] * 3 + tm[2]];
+      const double term = static_cast<double>(tm[0]) * fvp[tm[1] * 9 + tm[3] * 3 + tm[2]];
       acc = (t == 0) ? term : acc + term;
     }
-    S[in[0] * 32] = acc;
+    S[in[0]] = acc;
   }
-  double factor = 0.0;
-  for (int i = 0; i < GP3P_NUM_MOPS; ++i) {
-    const int4 m = __ldg(a.mops + i);
-    const int op = m.x & 0xFFFF, m1 = m.x >> 16, m2 = m.y & 0xFFFF, m3 = m.y >> 16, m4 = m.z & 0xFFFF,
-              m5 = m.z >> 16;
-    switch (op) {
-      case MOP_DIVSUB:
-        S[m1 * 32] = S[m2 * 32] / S[m3 * 32] - S[m4 * 32] / S[m5 * 32];
-        break;
-      case MOP_DIV:
-        S[m1 * 32] = S[m2 * 32] / S[m3 * 32];
-        break;
-      case MOP_NEGDIV:
-        S[m1 * 32] = -S[m2 * 32] / S[m3 * 32];
-        break;
-      case MOP_FACTOR_DIV:
-        factor = S[m1 * 32] / S[m2 * 32];
-        break;
-      case MOP_ZERO:
-        S[m1 * 32] = 0.0;
-        break;
-      case MOP_SUBMUL:
-        S[m1 * 32] = S[m1 * 32] - factor * S[m2 * 32];
-        break;
-      case MOP_FACTOR_LOAD:
-        factor = S[m1 * 32];
-        break;
-      case MOP_FACTOR_INV:
-        factor = 1.0 / S[m1 * 32];
-        break;
-      case MOP_SCALE:
-        S[m1 * 32] = factor * S[m1 * 32];
-        break;
+  __syncwarp();
+  for (int w = 0; w < GP3P_W_NUM_WAVES; ++w) {
+    const int begin = a.wave_offsets[w], end = a.wave_offsets[w + 1];
+    for (int i = begin + lane; i < end; i += 32) {
+      const uint4 m = __ldg(a.wops + i);
+      const unsigned op = m.x & 0xFFFFu, d = m.x >> 16, x = m.y & 0xFFFFu, y = m.y >> 16,
+                     c = m.z & 0xFFFFu, e = m.z >> 16;
+      double val;
+      switch (op) {
+        case 0: val = S[x] / S[y] - S[c] / S[e]; break;
+        case 1: val = S[x] / S[y]; break;
+        case 2: val = -S[x] / S[y]; break;
+        case 3: val = 0.0; break;
+        case 4: val = S[d] - S[x] * S[y]; break;
+        case 5: val = S[x] * S[d]; break;
+        case 6: val = S[x]; break;
+        default: val = 1.0 / S[x]; break;
+      }
+      S[d] = val;  // ops of one wave are independent (RAW/WAR/WAW): no barrier inside a wave
     }
+    __syncwarp();
   }
+  for (int i = lane; i < 64; i += 32) {
+    const int r = i >> 3, c = i & 7;
+    double v = 0.0;
+    if (r < 6) {
+      const int slot = a.action[i];
+      v = (slot >= 0) ? -S[slot] : -0.0;
+    } else if ((r == 6 && c == 0) || (r == 7 && c == 6)) {
+      v = 1.0;
+    }
+    M[i] = v;
+  }
+  __syncwarp();
 }
 
 // ---------------------------------------------------------------- 8x8 real eigen-solver
@@ -411,91 +418,45 @@ __device__ double Distance(const Problem& pb, const double T[12], int i) {
   return 1.0 - (r[0] * b[0] + r[1] * b[1] + r[2] * b[2]);
 }
 
-// gp3p_main + the GP3P branch of computeModelCoefficients. All 32 lanes must call this together
-// (the elimination is executed in lock-step); `active` lanes produce a model.
-__device__ bool ComputeModel(const RansacArgs& a, const Problem& pb, const int sel[4], double* S,
-                             double model[12]) {
-  double f[9], v[9], p[9];
-  for (int i = 0; i < 3; ++i) {
-    const mlc_camera& c = pb.cams[pb.cam_idx[sel[i]]];
-    const double* b = pb.bearings + 3 * sel[i];
-    for (int k = 0; k < 3; ++k) {
-      f[i * 3 + k] = c.R_B_C[k * 3 + 0] * b[0] + c.R_B_C[k * 3 + 1] * b[1] + c.R_B_C[k * 3 + 2] * b[2];
-      v[i * 3 + k] = c.t_B_C[k];
-      p[i * 3 + k] = pb.points[3 * sel[i] + k];
-    }
-  }
-  Gp3pEliminate(a, f, v, p, S);
+// One real-ish eigenvalue of the action matrix -> candidate pose (gp3p_main, main.cpp:396-433)
+// and its disambiguation score on the 4th sample point.
+__device__ void SolutionForEigenvalue(const Problem& pb, const double* Ms, double wr, double wi,
+                                      const double* fvp, int fourth, double sol[12], double* score) {
   double M[N8][N8];
   for (int r = 0; r < N8; ++r)
-    for (int c = 0; c < N8; ++c) M[r][c] = 0.0;
-  for (int r = 0; r < 6; ++r)
-    for (int c = 0; c < 8; ++c) {
-      const int slot = a.action[r * 8 + c];
-      M[r][c] = (slot >= 0) ? -S[slot * 32] : -0.0;
-    }
-  M[6][0] = 1.0;
-  M[7][6] = 1.0;
-  for (int r = 0; r < N8; ++r)
-    for (int c = 0; c < N8; ++c)
-      if (!isfinite(M[r][c])) return false;
-  double H[N8][N8];
-  for (int r = 0; r < N8; ++r)
-    for (int c = 0; c < N8; ++c) H[r][c] = M[r][c];
-  Hessenberg(H);
-  double wr[N8], wi[N8];
-  if (!HqrEigenvalues(H, wr, wi)) return false;
-  int num = 0;
-  double min_score = 1000000.0;
-  int min_index = -1;
-  double first[12];
-  for (int c = 0; c < N8; ++c) {
-    if (!(wi[c] < 0.0001)) continue;
-    Cx V[N8];
-    InverseIteration(M, Cx{wr[c], wi[c]}, V);
-    double cay[3], n[3];
-    for (int i = 0; i < 3; ++i) {
-      cay[2 - i] = CxDiv(V[i + 4], V[7]).re;
-      n[2 - i] = CxDiv(V[i + 1], V[7]).re;
-    }
-    double Rt[9];
-    Cayley2Rot(cay, Rt);
-    double R[9];
-    for (int i = 0; i < 3; ++i)
-      for (int j = 0; j < 3; ++j) R[i * 3 + j] = Rt[j * 3 + i];
-    double center_cam[3] = {0, 0, 0}, center_world[3] = {0, 0, 0};
-    for (int i = 0; i < 3; ++i) {
-      double tmp[3], w[3];
-      for (int k = 0; k < 3; ++k) w[k] = n[i] * f[i * 3 + k] + v[i * 3 + k];
-      for (int k = 0; k < 3; ++k) tmp[k] = R[k * 3 + 0] * w[0] + R[k * 3 + 1] * w[1] + R[k * 3 + 2] * w[2];
-      for (int k = 0; k < 3; ++k) {
-        center_cam[k] = center_cam[k] + tmp[k];
-        center_world[k] = center_world[k] + p[i * 3 + k];
-      }
-    }
-    double sol[12];
+    for (int c = 0; c < N8; ++c) M[r][c] = Ms[r * 8 + c];
+  const double* f = fvp;
+  const double* v = fvp + 9;
+  const double* p = fvp + 18;
+  Cx V[N8];
+  InverseIteration(M, Cx{wr, wi}, V);
+  double cay[3], n[3];
+  for (int i = 0; i < 3; ++i) {
+    cay[2 - i] = CxDiv(V[i + 4], V[7]).re;
+    n[2 - i] = CxDiv(V[i + 1], V[7]).re;
+  }
+  double Rt[9];
+  Cayley2Rot(cay, Rt);
+  double R[9];
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) R[i * 3 + j] = Rt[j * 3 + i];
+  double center_cam[3] = {0, 0, 0}, center_world[3] = {0, 0, 0};
+  for (int i = 0; i < 3; ++i) {
+    double tmp[3], w[3];
+    for (int k = 0; k < 3; ++k) w[k] = n[i] * f[i * 3 + k] + v[i * 3 + k];
+    for (int k = 0; k < 3; ++k) tmp[k] = R[k * 3 + 0] * w[0] + R[k * 3 + 1] * w[1] + R[k * 3 + 2] * w[2];
     for (int k = 0; k < 3; ++k) {
-      sol[k * 4 + 0] = R[k * 3 + 0];
-      sol[k * 4 + 1] = R[k * 3 + 1];
-      sol[k * 4 + 2] = R[k * 3 + 2];
-      sol[k * 4 + 3] = center_world[k] / 3 - center_cam[k] / 3;
-    }
-    if (num == 0)
-      for (int k = 0; k < 12; ++k) first[k] = sol[k];
-    ++num;
-    // disambiguation with the 4th sample point: smallest score, first wins on ties
-    const double score = Distance(pb, sol, sel[3]);
-    if (score < min_score) {
-      min_score = score;
-      min_index = c;
-      for (int k = 0; k < 12; ++k) model[k] = sol[k];
+      center_cam[k] = center_cam[k] + tmp[k];
+      center_world[k] = center_world[k] + p[i * 3 + k];
     }
   }
-  if (num == 1) {  // a single solution is accepted without the check
-    for (int k = 0; k < 12; ++k) model[k] = first[k];
-    return true;
+  for (int k = 0; k < 3; ++k) {
+    sol[k * 4 + 0] = R[k * 3 + 0];
+    sol[k * 4 + 1] = R[k * 3 + 1];
+    sol[k * 4 + 2] = R[k * 3 + 2];
+    sol[k * 4 + 3] = center_world[k] / 3 - center_cam[k] / 3;
   }
-  return min_index != -1;
+  *score = Distance(pb, sol, fourth);
 }
 
 // PinholeCamera::backProject3 + bearing normalisation (camera-pinhole.cc:47-63,
@@ -525,13 +486,31 @@ __device__ __forceinline__ double ShflD(double v, int src) {
   return __shfl_sync(0xffffffffu, v, src);
 }
 
+struct Candidate {  // one GP3P solution of one hypothesis
+  double T[12];
+  double score;
+  int valid, pad;
+};
+struct WarpScratch {
+  union {
+    double S[GP3P_W_NUM_SLOTS];       // elimination slots ...
+    Candidate cand[kHyp][N8];         // ... reused for the candidate poses afterwards
+  };
+  double M[kHyp][64];
+  double wr[kHyp][N8], wi[kHyp][N8];
+  double fvp[kHyp][27];
+  double model[kHyp][12];
+  int sel[kHyp][4];
+  int eig_ok[kHyp], model_ok[kHyp];
+};
+
 __global__ void __launch_bounds__(kWarpsPerBlock * 32) ransac_kernel(RansacArgs a) {
-  __shared__ int s_sel[kWarpsPerBlock][32][4];
+  extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31;
   const int wib = threadIdx.x >> 5;
+  WarpScratch& ws = reinterpret_cast<WarpScratch*>(smem_raw)[wib];
   const int64_t warp = static_cast<int64_t>(blockIdx.x) * kWarpsPerBlock + wib;
   const int64_t num_warps = static_cast<int64_t>(gridDim.x) * kWarpsPerBlock;
-  double* S = a.slots + static_cast<size_t>(warp) * GP3P_NUM_SLOTS * 32 + lane;
 
   for (int64_t pi = warp; pi < a.num_problems; pi += num_warps) {
     const int64_t off = a.offsets[pi];
@@ -576,46 +555,127 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) ransac_kernel(RansacArgs 
     }
     while (!done) {
       if (!(static_cast<double>(iterations) < k && skipped < max_skip)) break;
-      if (stream_pos + 128 > a.rnd_len) break;  // cannot happen: stream sized for the worst case
+      if (stream_pos + 4 * kHyp > a.rnd_len) break;  // cannot happen: stream sized for the worst case
+      // ---- draw the next kHyp samples (persistent partial Fisher-Yates) ----
       if (lane == 0) {
-        for (int t = 0; t < 32; ++t) {
+        for (int t = 0; t < kHyp; ++t) {
           for (int i = 0; i < 4; ++i) {
             const int j = i + a.rnd_stream[stream_pos + 4 * t + i] % (n - i);
             const int32_t tmp = shuf[i];
             shuf[i] = shuf[j];
             shuf[j] = tmp;
           }
-          for (int i = 0; i < 4; ++i) s_sel[wib][t][i] = shuf[i];
+          for (int i = 0; i < 4; ++i) ws.sel[t][i] = shuf[i];
         }
       }
-      stream_pos += 128;
+      stream_pos += 4 * kHyp;
       __syncwarp();
-      int sel[4];
-      for (int i = 0; i < 4; ++i) sel[i] = s_sel[wib][lane][i];
-      double model[12];
-      const bool ok = ComputeModel(a, pb, sel, S, model);
-      int count = 0;
-      if (ok)
-        for (int i = 0; i < n; ++i)
-          if (Distance(pb, model, i) < a.threshold) ++count;
+      // ---- f (bearing in the body frame), v (camera offset), p (world point) per hypothesis ----
+      for (int e = lane; e < kHyp * 27; e += 32) {
+        const int h = e / 27, r = e % 27, which = r / 9, i = (r % 9) / 3, kk = r % 3;
+        const int ci = ws.sel[h][i];
+        const mlc_camera& c = pb.cams[pb.cam_idx[ci]];
+        double val;
+        if (which == 0) {
+          const double* b = pb.bearings + 3 * ci;
+          val = c.R_B_C[kk * 3 + 0] * b[0] + c.R_B_C[kk * 3 + 1] * b[1] + c.R_B_C[kk * 3 + 2] * b[2];
+        } else if (which == 1) {
+          val = c.t_B_C[kk];
+        } else {
+          val = pb.points[3 * ci + kk];
+        }
+        ws.fvp[h][r] = val;
+      }
       __syncwarp();
-      // replay the sequential bookkeeping of Ransac::computeModel in sample order
-      for (int t = 0; t < 32; ++t) {
+      // ---- Groebner elimination, one hypothesis at a time, wave-parallel over the lanes ----
+      for (int h = 0; h < kHyp; ++h) Gp3pEliminateWarp(a, ws.fvp[h], ws.S, ws.M[h], lane);
+      // ---- eigenvalues: one lane per hypothesis ----
+      if (lane < kHyp) {
+        double H[N8][N8];
+        bool finite = true;
+        for (int r = 0; r < N8; ++r)
+          for (int c = 0; c < N8; ++c) {
+            H[r][c] = ws.M[lane][r * 8 + c];
+            if (!isfinite(H[r][c])) finite = false;
+          }
+        bool ok = finite;
+        if (ok) {
+          Hessenberg(H);
+          double wr[N8], wi[N8];
+          ok = HqrEigenvalues(H, wr, wi);
+          for (int c = 0; c < N8; ++c) {
+            ws.wr[lane][c] = wr[c];
+            ws.wi[lane][c] = wi[c];
+          }
+        }
+        ws.eig_ok[lane] = ok ? 1 : 0;
+      }
+      __syncwarp();
+      // ---- candidate poses: one lane per (hypothesis, eigenvalue) ----
+      for (int task = lane; task < kHyp * N8; task += 32) {
+        const int h = task >> 3, c = task & 7;
+        Candidate& cd = ws.cand[h][c];
+        cd.valid = 0;
+        if (ws.eig_ok[h] && (ws.wi[h][c] < 0.0001)) {  // main.cpp:400 (no fabs)
+          double sol[12], score;
+          SolutionForEigenvalue(pb, ws.M[h], ws.wr[h][c], ws.wi[h][c], ws.fvp[h], ws.sel[h][3], sol, &score);
+          for (int i = 0; i < 12; ++i) cd.T[i] = sol[i];
+          cd.score = score;
+          cd.valid = 1;
+        }
+      }
+      __syncwarp();
+      // ---- disambiguation (AbsolutePoseSacProblem.cpp:133-163): single solution accepted as is,
+      //      otherwise the smallest score on the 4th point, first wins ----
+      if (lane < kHyp) {
+        int num = 0, first = -1, min_index = -1;
+        double min_score = 1000000.0;
+        for (int c = 0; c < N8; ++c) {
+          if (!ws.cand[lane][c].valid) continue;
+          if (num == 0) first = c;
+          ++num;
+          if (ws.cand[lane][c].score < min_score) {
+            min_score = ws.cand[lane][c].score;
+            min_index = c;
+          }
+        }
+        const int pick = (num == 1) ? first : min_index;
+        ws.model_ok[lane] = (pick >= 0) ? 1 : 0;
+        if (pick >= 0)
+          for (int i = 0; i < 12; ++i) ws.model[lane][i] = ws.cand[lane][pick].T[i];
+      }
+      __syncwarp();
+      // ---- countWithinDistance per hypothesis, lanes over the correspondences ----
+      int counts[kHyp];
+#pragma unroll
+      for (int h = 0; h < kHyp; ++h) {
+        int c = 0;
+        if (ws.model_ok[h]) {
+          double T[12];
+          for (int i = 0; i < 12; ++i) T[i] = ws.model[h][i];
+          for (int i = lane; i < n; i += 32)
+            if (Distance(pb, T, i) < a.threshold) ++c;
+          for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+        }
+        counts[h] = c;
+      }
+      // ---- replay the sequential bookkeeping of Ransac::computeModel in sample order ----
+#pragma unroll
+      for (int t = 0; t < kHyp; ++t) {
+        if (done) break;
         if (!(static_cast<double>(iterations) < k && skipped < max_skip)) {
           done = true;
           break;
         }
-        const int ok_t = __shfl_sync(0xffffffffu, ok ? 1 : 0, t);
-        if (!ok_t) {
+        if (!ws.model_ok[t]) {
           ++skipped;
           continue;
         }
-        const int c_t = __shfl_sync(0xffffffffu, count, t);
-        if (c_t > best) {
-          best = c_t;
+        if (counts[t] > best) {
+          best = counts[t];
           have_model = true;
-          for (int i = 0; i < 12; ++i) best_model[i] = ShflD(model[i], t);
-          for (int i = 0; i < 4; ++i) best_sel[i] = s_sel[wib][t][i];
+          for (int i = 0; i < 12; ++i) best_model[i] = ws.model[t][i];
+          for (int i = 0; i < 4; ++i) best_sel[i] = ws.sel[t][i];
           const double w = static_cast<double>(best) / static_cast<double>(n);
           double p_no_outliers = 1.0 - pow(w, 4.0);
           p_no_outliers = fmax(2.220446049250313e-16, p_no_outliers);
@@ -623,10 +683,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) ransac_kernel(RansacArgs 
           k = a.log_one_minus_p / log(p_no_outliers);
         }
         ++iterations;
-        if (iterations > a.max_iterations) {
-          done = true;
-          break;
-        }
+        if (iterations > a.max_iterations) done = true;
       }
       __syncwarp();
     }
@@ -635,8 +692,6 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) ransac_kernel(RansacArgs 
       res.ransac_success = 1;
       for (int i = 0; i < 12; ++i) res.T_G_I[i] = best_model[i];
       for (int i = 0; i < 4; ++i) res.model_indices[i] = best_sel[i];
-      // selectWithinDistance on the best model; distances parked in the bearing scratch is not
-      // possible (still needed), so they are recomputed where compared.
       int my_inliers = 0;
       for (int i = lane; i < n; i += 32)
         if (Distance(pb, best_model, i) < a.threshold) ++my_inliers;
@@ -708,25 +763,28 @@ class HostRng {
 };
 
 struct ProgramDevice {
-  int4* mops = nullptr;
+  uint4* wops = nullptr;
+  unsigned short* wave_offsets = nullptr;
   short* init_table = nullptr;
   short* action = nullptr;
 };
 ProgramDevice g_program;  // per process (one GPU per process)
 
 cudaError_t EnsureProgram() {
-  if (g_program.mops) return cudaSuccess;
-  std::vector<int4> packed(GP3P_NUM_MOPS);
-  for (int i = 0; i < GP3P_NUM_MOPS; ++i) {
-    const short* m = GP3P_MOPS[i];
-    auto u = [](short s) { return static_cast<int>(static_cast<unsigned short>(s)); };
-    packed[i] = make_int4(u(m[0]) | (u(m[1]) << 16), u(m[2]) | (u(m[3]) << 16), u(m[4]) | (u(m[5]) << 16), 0);
+  if (g_program.wops) return cudaSuccess;
+  std::vector<uint4> packed(GP3P_W_NUM_OPS);
+  for (int i = 0; i < GP3P_W_NUM_OPS; ++i) {
+    const unsigned short* m = GP3P_W_OPS[i];
+    packed[i] = make_uint4(m[0] | (static_cast<unsigned>(m[1]) << 16), m[2] | (static_cast<unsigned>(m[3]) << 16),
+                           m[4] | (static_cast<unsigned>(m[5]) << 16), 0u);
   }
   cudaError_t e;
-  if ((e = cudaMalloc(&g_program.mops, sizeof(int4) * GP3P_NUM_MOPS)) != cudaSuccess) return e;
+  if ((e = cudaMalloc(&g_program.wops, sizeof(uint4) * GP3P_W_NUM_OPS)) != cudaSuccess) return e;
+  if ((e = cudaMalloc(&g_program.wave_offsets, sizeof(GP3P_W_WAVE_OFFSETS))) != cudaSuccess) return e;
   if ((e = cudaMalloc(&g_program.init_table, sizeof(GP3P_INIT))) != cudaSuccess) return e;
   if ((e = cudaMalloc(&g_program.action, sizeof(GP3P_ACTION))) != cudaSuccess) return e;
-  if ((e = cudaMemcpy(g_program.mops, packed.data(), sizeof(int4) * GP3P_NUM_MOPS, cudaMemcpyHostToDevice)) != cudaSuccess) return e;
+  if ((e = cudaMemcpy(g_program.wops, packed.data(), sizeof(uint4) * GP3P_W_NUM_OPS, cudaMemcpyHostToDevice)) != cudaSuccess) return e;
+  if ((e = cudaMemcpy(g_program.wave_offsets, GP3P_W_WAVE_OFFSETS, sizeof(GP3P_W_WAVE_OFFSETS), cudaMemcpyHostToDevice)) != cudaSuccess) return e;
   if ((e = cudaMemcpy(g_program.init_table, GP3P_INIT, sizeof(GP3P_INIT), cudaMemcpyHostToDevice)) != cudaSuccess) return e;
   return cudaMemcpy(g_program.action, GP3P_ACTION, sizeof(GP3P_ACTION), cudaMemcpyHostToDevice);
 }
@@ -802,7 +860,7 @@ bool Detector::RansacOnDevice(const mlc_ransac_settings& rs, const mlc_camera* c
   focal /= (2.0 * static_cast<double>(num_cams));
   const double threshold = 1.0 - std::cos(std::atan(rs.ransac_pixel_sigma / focal));
   // draws: 4 per attempted sample; attempts <= max_iterations + 1 counted + 10 * max_iterations skipped
-  const int rnd_len = 4 * (11 * rs.num_ransac_iters + 2 + 64);
+  const int rnd_len = 4 * (11 * rs.num_ransac_iters + 2 + 2 * kHyp);
   if (rnd_seed_ != rs.seed || rnd_mapping_ != rs.rng_mapping || static_cast<int>(rnd_host_.size()) != rnd_len) {
     rnd_host_.resize(rnd_len);
     HostRng rng(rs.seed, rs.rng_mapping);
@@ -812,14 +870,12 @@ bool Detector::RansacOnDevice(const mlc_ransac_settings& rs, const mlc_camera* c
   }
   const int blocks = static_cast<int>(std::min<int64_t>((num_problems + kWarpsPerBlock - 1) / kWarpsPerBlock,
                                                         static_cast<int64_t>(sm_count_) * 2));
-  const size_t warps = static_cast<size_t>(blocks) * kWarpsPerBlock;
-  DevBuf &b_scr = d_ransac_[1], &b_slots = d_ransac_[2], &b_out = d_ransac_[3];
+  DevBuf &b_scr = d_ransac_[1], &b_out = d_ransac_[3];
   const size_t o_cam = 0;
   const size_t o_rnd = (sizeof(mlc_camera) * num_cams + 255) & ~static_cast<size_t>(255);
   const size_t o_bear = (o_rnd + sizeof(int32_t) * rnd_len + 255) & ~static_cast<size_t>(255);
   const size_t o_shuf = (o_bear + sizeof(double) * 3 * total + 255) & ~static_cast<size_t>(255);
   if (!Cuda(b_scr.Reserve(o_shuf + sizeof(int32_t) * total + 256), "alloc", err) ||
-      !Cuda(b_slots.Reserve(sizeof(double) * GP3P_NUM_SLOTS * 32 * warps), "alloc", err) ||
       !Cuda(b_out.Reserve(sizeof(mlc_pose_result) * num_problems + total + 512), "alloc", err))
     return false;
   unsigned char* scr = b_scr.as<unsigned char>();
@@ -842,15 +898,19 @@ bool Detector::RansacOnDevice(const mlc_ransac_settings& rs, const mlc_camera* c
   a.min_inlier_ratio = rs.min_inlier_ratio;
   a.rnd_stream = reinterpret_cast<const int32_t*>(scr + o_rnd);
   a.rnd_len = rnd_len;
-  a.mops = g_program.mops;
+  a.wops = g_program.wops;
+  a.wave_offsets = g_program.wave_offsets;
   a.init_table = g_program.init_table;
   a.action = g_program.action;
-  a.slots = b_slots.as<double>();
   a.bearings = reinterpret_cast<double*>(scr + o_bear);
   a.shuffled = reinterpret_cast<int32_t*>(scr + o_shuf);
   a.results = b_out.as<mlc_pose_result>();
   a.inlier_flags = inlier_flags ? b_out.as<uint8_t>() + sizeof(mlc_pose_result) * num_problems : nullptr;
-  ransac_kernel<<<blocks, kWarpsPerBlock * 32, 0, stream_>>>(a);
+  const size_t smem = sizeof(WarpScratch) * kWarpsPerBlock;
+  if (!Cuda(cudaFuncSetAttribute(ransac_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)),
+            "ransac smem", err))
+    return false;
+  ransac_kernel<<<blocks, kWarpsPerBlock * 32, smem, stream_>>>(a);
   CountLaunch();
   cudaEventRecord(ev_stage_[5], stream_);
   if (!Cuda(cudaGetLastError(), "ransac kernel", err)) return false;
