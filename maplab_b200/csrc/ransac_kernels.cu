@@ -482,248 +482,326 @@ __device__ void BackProject3(const mlc_camera& c, const double* kp, double* b) {
   b[2] = 1.0 / nrm;
 }
 
-__device__ __forceinline__ double ShflD(double v, int src) {
-  return __shfl_sync(0xffffffffu, v, src);
+// ---------------------------------------------------------------- hypothesis-parallel RANSAC
+// Per round every still-running problem speculates kHyp hypotheses. The stages are separate
+// kernels so that each one exposes its natural parallelism across ALL problems of the batch:
+//   sample (thread / problem) -> eliminate (warp / hypothesis) -> eigenvalues (thread / hypothesis)
+//   -> candidate poses (thread / (hypothesis, eigenvalue)) -> select + count inliers
+//   (warp / hypothesis) -> bookkeeping replay (thread / problem).
+struct ProblemState {  // sequential state of opengv::sac::Ransac::computeModel for one problem
+  int iterations, best, skipped, stream_pos;
+  int have_model, done, pad0, pad1;
+  double k;
+  double best_model[12];
+  int best_sel[4];
+};
+struct Hypothesis {
+  double fvp[27];
+  double M[64];
+  double wr[N8], wi[N8];
+  double cand_T[N8][12];
+  double cand_score[N8];
+  double model[12];
+  int cand_valid[N8];
+  int sel[4];
+  int active, eig_ok, model_ok, count;
+};
+
+__device__ __forceinline__ Problem MakeProblem(const RansacArgs& a, int64_t pi) {
+  const int64_t off = a.offsets[pi];
+  Problem pb;
+  pb.bearings = a.bearings + 3 * off;
+  pb.cam_idx = a.camera_index + off;
+  pb.points = a.landmarks + 3 * off;
+  pb.cams = a.cams;
+  pb.n = static_cast<int>(a.offsets[pi + 1] - off);
+  return pb;
 }
 
-struct Candidate {  // one GP3P solution of one hypothesis
-  double T[12];
-  double score;
-  int valid, pad;
-};
-struct WarpScratch {
-  union {
-    double S[GP3P_W_NUM_SLOTS];       // elimination slots ...
-    Candidate cand[kHyp][N8];         // ... reused for the candidate poses afterwards
-  };
-  double M[kHyp][64];
-  double wr[kHyp][N8], wi[kHyp][N8];
-  double fvp[kHyp][27];
-  double model[kHyp][12];
-  int sel[kHyp][4];
-  int eig_ok[kHyp], model_ok[kHyp];
-};
-
-__global__ void __launch_bounds__(kWarpsPerBlock * 32) ransac_kernel(RansacArgs a) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+// bearings, identity shuffle, initial state. One warp per problem.
+__global__ void __launch_bounds__(128) ransac_init_kernel(RansacArgs a, ProblemState* st) {
   const int lane = threadIdx.x & 31;
-  const int wib = threadIdx.x >> 5;
-  WarpScratch& ws = reinterpret_cast<WarpScratch*>(smem_raw)[wib];
-  const int64_t warp = static_cast<int64_t>(blockIdx.x) * kWarpsPerBlock + wib;
-  const int64_t num_warps = static_cast<int64_t>(gridDim.x) * kWarpsPerBlock;
-
-  for (int64_t pi = warp; pi < a.num_problems; pi += num_warps) {
-    const int64_t off = a.offsets[pi];
-    const int n = static_cast<int>(a.offsets[pi + 1] - off);
-    mlc_pose_result res;
-    res.accepted = 0;
-    res.ransac_success = 0;
-    res.num_inliers = 0;
-    res.num_ransac_inliers = 0;
-    res.iterations = 0;
-    for (int i = 0; i < 4; ++i) res.model_indices[i] = -1;
-    res.pad_ = 0;
-    res.inlier_ratio = 0.0;
-    for (int i = 0; i < 12; ++i) res.T_G_I[i] = 0.0;
-    if (a.inlier_flags)
-      for (int i = lane; i < n; i += 32) a.inlier_flags[off + i] = 0;
-    if (n < a.min_inlier_count) {  // handleLoopClosure bails before RANSAC (loop-closure-handler.cc:262-270)
-      if (lane == 0) a.results[pi] = res;
-      continue;
-    }
-    Problem pb;
-    pb.bearings = a.bearings + 3 * off;
-    pb.cam_idx = a.camera_index + off;
-    pb.points = a.landmarks + 3 * off;
-    pb.cams = a.cams;
-    pb.n = n;
-    for (int i = lane; i < n; i += 32) {
+  const int64_t pi = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 5;
+  if (pi >= a.num_problems) return;
+  const int64_t off = a.offsets[pi];
+  const int n = static_cast<int>(a.offsets[pi + 1] - off);
+  for (int i = lane; i < n; i += 32) {
+    if (a.inlier_flags) a.inlier_flags[off + i] = 0;
+    if (n >= a.min_inlier_count) {
       BackProject3(a.cams[a.camera_index[off + i]], a.keypoints + 2 * (off + i), a.bearings + 3 * (off + i));
       a.shuffled[off + i] = i;
     }
-    __syncwarp();
-    int32_t* shuf = a.shuffled + off;
-    int iterations = 0, best = -INT_MAX, skipped = 0, stream_pos = 0;
-    const int max_skip = a.max_iterations * 10;
-    double k = 1.0;
-    bool have_model = false, done = false;
-    double best_model[12];
-    int best_sel[4] = {-1, -1, -1, -1};
-    if (n < 4) {  // getSamples cannot draw 4 unique indices
-      iterations = INT_MAX;
-      done = true;
+  }
+  if (lane == 0) {
+    ProblemState s;
+    s.iterations = 0;
+    s.best = -INT_MAX;
+    s.skipped = 0;
+    s.stream_pos = 0;
+    s.have_model = 0;
+    s.done = 0;
+    s.pad0 = s.pad1 = 0;
+    s.k = 1.0;
+    for (int i = 0; i < 12; ++i) s.best_model[i] = 0.0;
+    for (int i = 0; i < 4; ++i) s.best_sel[i] = -1;
+    if (n < a.min_inlier_count) s.done = 1;  // handleLoopClosure bails before RANSAC
+    if (!s.done && n < 4) {                  // getSamples cannot draw 4 unique indices
+      s.iterations = INT_MAX;
+      s.done = 1;
     }
-    while (!done) {
-      if (!(static_cast<double>(iterations) < k && skipped < max_skip)) break;
-      if (stream_pos + 4 * kHyp > a.rnd_len) break;  // cannot happen: stream sized for the worst case
-      // ---- draw the next kHyp samples (persistent partial Fisher-Yates) ----
-      if (lane == 0) {
-        for (int t = 0; t < kHyp; ++t) {
-          for (int i = 0; i < 4; ++i) {
-            const int j = i + a.rnd_stream[stream_pos + 4 * t + i] % (n - i);
-            const int32_t tmp = shuf[i];
-            shuf[i] = shuf[j];
-            shuf[j] = tmp;
-          }
-          for (int i = 0; i < 4; ++i) ws.sel[t][i] = shuf[i];
-        }
+    st[pi] = s;
+  }
+}
+
+// Draw the next kHyp samples of every running problem (persistent partial Fisher-Yates).
+__global__ void __launch_bounds__(128) ransac_sample_kernel(RansacArgs a, ProblemState* st, Hypothesis* hyp) {
+  const int64_t pi = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (pi >= a.num_problems) return;
+  ProblemState& s = st[pi];
+  Hypothesis* h = hyp + pi * kHyp;
+  const int max_skip = a.max_iterations * 10;
+  bool run = !s.done && (static_cast<double>(s.iterations) < s.k && s.skipped < max_skip) &&
+             (s.stream_pos + 4 * kHyp <= a.rnd_len);
+  if (!run) {
+    s.done = 1;
+    for (int t = 0; t < kHyp; ++t) h[t].active = 0;
+    return;
+  }
+  const int64_t off = a.offsets[pi];
+  const int n = static_cast<int>(a.offsets[pi + 1] - off);
+  int32_t* shuf = a.shuffled + off;
+  for (int t = 0; t < kHyp; ++t) {
+    for (int i = 0; i < 4; ++i) {
+      const int j = i + a.rnd_stream[s.stream_pos + 4 * t + i] % (n - i);
+      const int32_t tmp = shuf[i];
+      shuf[i] = shuf[j];
+      shuf[j] = tmp;
+    }
+    for (int i = 0; i < 4; ++i) h[t].sel[i] = shuf[i];
+    h[t].active = 1;
+  }
+  s.stream_pos += 4 * kHyp;
+}
+
+// Groebner elimination: one warp per hypothesis, slot array in shared memory.
+__global__ void __launch_bounds__(kWarpsPerBlock * 32) gp3p_eliminate_kernel(RansacArgs a, Hypothesis* hyp, int64_t num_hyp) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31;
+  const int wib = threadIdx.x >> 5;
+  double* S = reinterpret_cast<double*>(smem_raw) + static_cast<size_t>(wib) * (GP3P_W_NUM_SLOTS + 27 + 64);
+  double* fvp = S + GP3P_W_NUM_SLOTS;
+  double* M = fvp + 27;
+  const int64_t warps = static_cast<int64_t>(gridDim.x) * kWarpsPerBlock;
+  for (int64_t hi = static_cast<int64_t>(blockIdx.x) * kWarpsPerBlock + wib; hi < num_hyp; hi += warps) {
+    Hypothesis& h = hyp[hi];
+    if (!h.active) continue;
+    const Problem pb = MakeProblem(a, hi / kHyp);
+    // f (bearing rotated into the body frame), v (camera offset), p (world point) of the 3 points
+    if (lane < 27) {
+      const int which = lane / 9, i = (lane % 9) / 3, kk = lane % 3;
+      const int ci = h.sel[i];
+      const mlc_camera& c = pb.cams[pb.cam_idx[ci]];
+      double val;
+      if (which == 0) {
+        const double* b = pb.bearings + 3 * ci;
+        val = c.R_B_C[kk * 3 + 0] * b[0] + c.R_B_C[kk * 3 + 1] * b[1] + c.R_B_C[kk * 3 + 2] * b[2];
+      } else if (which == 1) {
+        val = c.t_B_C[kk];
+      } else {
+        val = pb.points[3 * ci + kk];
       }
-      stream_pos += 4 * kHyp;
-      __syncwarp();
-      // ---- f (bearing in the body frame), v (camera offset), p (world point) per hypothesis ----
-      for (int e = lane; e < kHyp * 27; e += 32) {
-        const int h = e / 27, r = e % 27, which = r / 9, i = (r % 9) / 3, kk = r % 3;
-        const int ci = ws.sel[h][i];
-        const mlc_camera& c = pb.cams[pb.cam_idx[ci]];
-        double val;
-        if (which == 0) {
-          const double* b = pb.bearings + 3 * ci;
-          val = c.R_B_C[kk * 3 + 0] * b[0] + c.R_B_C[kk * 3 + 1] * b[1] + c.R_B_C[kk * 3 + 2] * b[2];
-        } else if (which == 1) {
-          val = c.t_B_C[kk];
-        } else {
-          val = pb.points[3 * ci + kk];
-        }
-        ws.fvp[h][r] = val;
-      }
-      __syncwarp();
-      // ---- Groebner elimination, one hypothesis at a time, wave-parallel over the lanes ----
-      for (int h = 0; h < kHyp; ++h) Gp3pEliminateWarp(a, ws.fvp[h], ws.S, ws.M[h], lane);
-      // ---- eigenvalues: one lane per hypothesis ----
-      if (lane < kHyp) {
-        double H[N8][N8];
-        bool finite = true;
-        for (int r = 0; r < N8; ++r)
-          for (int c = 0; c < N8; ++c) {
-            H[r][c] = ws.M[lane][r * 8 + c];
-            if (!isfinite(H[r][c])) finite = false;
-          }
-        bool ok = finite;
-        if (ok) {
-          Hessenberg(H);
-          double wr[N8], wi[N8];
-          ok = HqrEigenvalues(H, wr, wi);
-          for (int c = 0; c < N8; ++c) {
-            ws.wr[lane][c] = wr[c];
-            ws.wi[lane][c] = wi[c];
-          }
-        }
-        ws.eig_ok[lane] = ok ? 1 : 0;
-      }
-      __syncwarp();
-      // ---- candidate poses: one lane per (hypothesis, eigenvalue) ----
-      for (int task = lane; task < kHyp * N8; task += 32) {
-        const int h = task >> 3, c = task & 7;
-        Candidate& cd = ws.cand[h][c];
-        cd.valid = 0;
-        if (ws.eig_ok[h] && (ws.wi[h][c] < 0.0001)) {  // main.cpp:400 (no fabs)
-          double sol[12], score;
-          SolutionForEigenvalue(pb, ws.M[h], ws.wr[h][c], ws.wi[h][c], ws.fvp[h], ws.sel[h][3], sol, &score);
-          for (int i = 0; i < 12; ++i) cd.T[i] = sol[i];
-          cd.score = score;
-          cd.valid = 1;
-        }
-      }
-      __syncwarp();
-      // ---- disambiguation (AbsolutePoseSacProblem.cpp:133-163): single solution accepted as is,
-      //      otherwise the smallest score on the 4th point, first wins ----
-      if (lane < kHyp) {
-        int num = 0, first = -1, min_index = -1;
-        double min_score = 1000000.0;
-        for (int c = 0; c < N8; ++c) {
-          if (!ws.cand[lane][c].valid) continue;
-          if (num == 0) first = c;
-          ++num;
-          if (ws.cand[lane][c].score < min_score) {
-            min_score = ws.cand[lane][c].score;
-            min_index = c;
-          }
-        }
-        const int pick = (num == 1) ? first : min_index;
-        ws.model_ok[lane] = (pick >= 0) ? 1 : 0;
-        if (pick >= 0)
-          for (int i = 0; i < 12; ++i) ws.model[lane][i] = ws.cand[lane][pick].T[i];
-      }
-      __syncwarp();
-      // ---- countWithinDistance per hypothesis, lanes over the correspondences ----
-      int counts[kHyp];
-#pragma unroll
-      for (int h = 0; h < kHyp; ++h) {
-        int c = 0;
-        if (ws.model_ok[h]) {
-          double T[12];
-          for (int i = 0; i < 12; ++i) T[i] = ws.model[h][i];
-          for (int i = lane; i < n; i += 32)
-            if (Distance(pb, T, i) < a.threshold) ++c;
-          for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
-        }
-        counts[h] = c;
-      }
-      // ---- replay the sequential bookkeeping of Ransac::computeModel in sample order ----
-#pragma unroll
+      fvp[lane] = val;
+      h.fvp[lane] = val;
+    }
+    __syncwarp();
+    Gp3pEliminateWarp(a, fvp, S, M, lane);
+    for (int i = lane; i < 64; i += 32) h.M[i] = M[i];
+    __syncwarp();
+  }
+}
+
+// Eigenvalues of the 8x8 action matrix: one thread per hypothesis.
+__global__ void __launch_bounds__(64) gp3p_eigen_kernel(Hypothesis* hyp, int64_t num_hyp) {
+  const int64_t hi = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (hi >= num_hyp) return;
+  Hypothesis& h = hyp[hi];
+  if (!h.active) return;
+  double H[N8][N8];
+  bool finite = true;
+  for (int r = 0; r < N8; ++r)
+    for (int c = 0; c < N8; ++c) {
+      H[r][c] = h.M[r * 8 + c];
+      if (!isfinite(H[r][c])) finite = false;
+    }
+  bool ok = finite;
+  if (ok) {
+    Hessenberg(H);
+    double wr[N8], wi[N8];
+    ok = HqrEigenvalues(H, wr, wi);
+    for (int c = 0; c < N8; ++c) {
+      h.wr[c] = wr[c];
+      h.wi[c] = wi[c];
+    }
+  }
+  h.eig_ok = ok ? 1 : 0;
+}
+
+// Candidate pose + disambiguation score: one thread per (hypothesis, eigenvalue).
+__global__ void __launch_bounds__(64) gp3p_candidate_kernel(RansacArgs a, Hypothesis* hyp, int64_t num_hyp) {
+  const int64_t task = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  const int64_t hi = task >> 3;
+  const int c = static_cast<int>(task & 7);
+  if (hi >= num_hyp) return;
+  Hypothesis& h = hyp[hi];
+  if (!h.active) return;
+  int valid = 0;
+  if (h.eig_ok && (h.wi[c] < 0.0001)) {  // main.cpp:400 (no fabs: negative imaginary parts pass)
+    const Problem pb = MakeProblem(a, hi / kHyp);
+    double sol[12], score;
+    SolutionForEigenvalue(pb, h.M, h.wr[c], h.wi[c], h.fvp, h.sel[3], sol, &score);
+    for (int i = 0; i < 12; ++i) h.cand_T[c][i] = sol[i];
+    h.cand_score[c] = score;
+    valid = 1;
+  }
+  h.cand_valid[c] = valid;
+}
+
+// Disambiguation (AbsolutePoseSacProblem.cpp:133-163) + countWithinDistance: one warp per hypothesis.
+__global__ void __launch_bounds__(128) ransac_score_kernel(RansacArgs a, Hypothesis* hyp, int64_t num_hyp) {
+  const int lane = threadIdx.x & 31;
+  const int64_t hi = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 5;
+  if (hi >= num_hyp) return;
+  Hypothesis& h = hyp[hi];
+  if (!h.active) return;
+  // every lane evaluates the (cheap) selection redundantly
+  int num = 0, first = -1, min_index = -1;
+  double min_score = 1000000.0;
+  for (int c = 0; c < N8; ++c) {
+    if (!h.cand_valid[c]) continue;
+    if (num == 0) first = c;
+    ++num;
+    if (h.cand_score[c] < min_score) {  // smallest score on the 4th point, first wins
+      min_score = h.cand_score[c];
+      min_index = c;
+    }
+  }
+  const int pick = (num == 1) ? first : min_index;  // a single solution is accepted as is
+  int count = 0;
+  if (pick >= 0) {
+    const Problem pb = MakeProblem(a, hi / kHyp);
+    double T[12];
+    for (int i = 0; i < 12; ++i) T[i] = h.cand_T[pick][i];
+    for (int i = lane; i < pb.n; i += 32)
+      if (Distance(pb, T, i) < a.threshold) ++count;
+    for (int o = 16; o > 0; o >>= 1) count += __shfl_xor_sync(0xffffffffu, count, o);
+    if (lane < 12) h.model[lane] = T[lane];
+  }
+  if (lane == 0) {
+    h.model_ok = pick >= 0 ? 1 : 0;
+    h.count = count;
+  }
+}
+
+// Replay of the sequential bookkeeping of Ransac::computeModel (Ransac.hpp:64-128) in sample
+// order; counts the problems that need another round.
+__global__ void __launch_bounds__(128) ransac_update_kernel(RansacArgs a, ProblemState* st, const Hypothesis* hyp,
+                                                            int* remaining) {
+  const int64_t pi = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  int still = 0;
+  if (pi < a.num_problems) {
+    ProblemState& s = st[pi];
+    if (!s.done) {
+      const Hypothesis* h = hyp + pi * kHyp;
+      const int n = static_cast<int>(a.offsets[pi + 1] - a.offsets[pi]);
+      const int max_skip = a.max_iterations * 10;
       for (int t = 0; t < kHyp; ++t) {
-        if (done) break;
-        if (!(static_cast<double>(iterations) < k && skipped < max_skip)) {
-          done = true;
+        if (!(static_cast<double>(s.iterations) < s.k && s.skipped < max_skip)) {
+          s.done = 1;
           break;
         }
-        if (!ws.model_ok[t]) {
-          ++skipped;
+        if (!h[t].model_ok) {
+          ++s.skipped;
           continue;
         }
-        if (counts[t] > best) {
-          best = counts[t];
-          have_model = true;
-          for (int i = 0; i < 12; ++i) best_model[i] = ws.model[t][i];
-          for (int i = 0; i < 4; ++i) best_sel[i] = ws.sel[t][i];
-          const double w = static_cast<double>(best) / static_cast<double>(n);
+        if (h[t].count > s.best) {
+          s.best = h[t].count;
+          s.have_model = 1;
+          for (int i = 0; i < 12; ++i) s.best_model[i] = h[t].model[i];
+          for (int i = 0; i < 4; ++i) s.best_sel[i] = h[t].sel[i];
+          const double w = static_cast<double>(s.best) / static_cast<double>(n);
           double p_no_outliers = 1.0 - pow(w, 4.0);
           p_no_outliers = fmax(2.220446049250313e-16, p_no_outliers);
           p_no_outliers = fmin(1.0 - 2.220446049250313e-16, p_no_outliers);
-          k = a.log_one_minus_p / log(p_no_outliers);
+          s.k = a.log_one_minus_p / log(p_no_outliers);
         }
-        ++iterations;
-        if (iterations > a.max_iterations) done = true;
-      }
-      __syncwarp();
-    }
-    res.iterations = iterations;
-    if (have_model) {
-      res.ransac_success = 1;
-      for (int i = 0; i < 12; ++i) res.T_G_I[i] = best_model[i];
-      for (int i = 0; i < 4; ++i) res.model_indices[i] = best_sel[i];
-      int my_inliers = 0;
-      for (int i = lane; i < n; i += 32)
-        if (Distance(pb, best_model, i) < a.threshold) ++my_inliers;
-      int total = my_inliers;
-      for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
-      res.num_ransac_inliers = total;
-      // best inlier per (camera, keypoint): smallest score, first index wins on ties
-      int my_best = 0;
-      for (int i = lane; i < n; i += 32) {
-        const double di = Distance(pb, best_model, i);
-        if (!(di < a.threshold)) continue;
-        bool is_best = true;
-        const int cam = a.camera_index[off + i], kp = a.keypoint_index[off + i];
-        for (int j = 0; j < n && is_best; ++j) {
-          if (j == i || a.camera_index[off + j] != cam || a.keypoint_index[off + j] != kp) continue;
-          const double dj = Distance(pb, best_model, j);
-          if (!(dj < a.threshold)) continue;
-          if (dj < di || (dj == di && j < i)) is_best = false;
+        ++s.iterations;
+        if (s.iterations > a.max_iterations) {
+          s.done = 1;
+          break;
         }
-        if (is_best) ++my_best;
-        if (a.inlier_flags) a.inlier_flags[off + i] = is_best ? 3 : 1;
       }
-      for (int o = 16; o > 0; o >>= 1) my_best += __shfl_xor_sync(0xffffffffu, my_best, o);
-      res.num_inliers = my_best;
+      if (!s.done && !(static_cast<double>(s.iterations) < s.k && s.skipped < max_skip)) s.done = 1;
+      still = s.done ? 0 : 1;
     }
-    if (res.num_inliers >= a.min_inlier_count) {
-      res.inlier_ratio = static_cast<double>(res.num_inliers) / static_cast<double>(n);
-      if (!(res.inlier_ratio < a.min_inlier_ratio)) res.accepted = 1;
-    }
-    if (lane == 0) a.results[pi] = res;
-    __syncwarp();
   }
+  const int any = __syncthreads_count(still);
+  if (threadIdx.x == 0 && any) atomicAdd(remaining, any);  // one per block; round control only
+}
+
+// selectWithinDistance on the best model, best inlier per keypoint, handleLoopClosure gates.
+__global__ void __launch_bounds__(128) ransac_finalize_kernel(RansacArgs a, const ProblemState* st) {
+  const int lane = threadIdx.x & 31;
+  const int64_t pi = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 5;
+  if (pi >= a.num_problems) return;
+  const ProblemState& s = st[pi];
+  const int64_t off = a.offsets[pi];
+  const Problem pb = MakeProblem(a, pi);
+  const int n = pb.n;
+  mlc_pose_result res;
+  res.accepted = 0;
+  res.ransac_success = 0;
+  res.num_inliers = 0;
+  res.num_ransac_inliers = 0;
+  res.iterations = s.iterations;
+  for (int i = 0; i < 4; ++i) res.model_indices[i] = -1;
+  res.pad_ = 0;
+  res.inlier_ratio = 0.0;
+  for (int i = 0; i < 12; ++i) res.T_G_I[i] = 0.0;
+  if (s.have_model) {
+    double best_model[12];
+    for (int i = 0; i < 12; ++i) best_model[i] = s.best_model[i];
+    res.ransac_success = 1;
+    for (int i = 0; i < 12; ++i) res.T_G_I[i] = best_model[i];
+    for (int i = 0; i < 4; ++i) res.model_indices[i] = s.best_sel[i];
+    int total = 0, my_best = 0;
+    for (int i = lane; i < n; i += 32) {
+      const double di = Distance(pb, best_model, i);
+      if (!(di < a.threshold)) continue;
+      ++total;
+      // best inlier per (camera, keypoint): smallest score, first index wins on ties
+      bool is_best = true;
+      const int cam = a.camera_index[off + i], kp = a.keypoint_index[off + i];
+      for (int j = 0; j < n && is_best; ++j) {
+        if (j == i || a.keypoint_index[off + j] != kp || a.camera_index[off + j] != cam) continue;
+        const double dj = Distance(pb, best_model, j);
+        if (!(dj < a.threshold)) continue;
+        if (dj < di || (dj == di && j < i)) is_best = false;
+      }
+      if (is_best) ++my_best;
+      if (a.inlier_flags) a.inlier_flags[off + i] = is_best ? 3 : 1;
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+      total += __shfl_xor_sync(0xffffffffu, total, o);
+      my_best += __shfl_xor_sync(0xffffffffu, my_best, o);
+    }
+    res.num_ransac_inliers = total;
+    res.num_inliers = my_best;
+  }
+  if (res.num_inliers >= a.min_inlier_count) {
+    res.inlier_ratio = static_cast<double>(res.num_inliers) / static_cast<double>(n);
+    if (!(res.inlier_ratio < a.min_inlier_ratio)) res.accepted = 1;
+  }
+  if (lane == 0) a.results[pi] = res;
 }
 
 // std::mt19937 + libstdc++ uniform_int_distribution<int>(0, INT_MAX).
@@ -868,17 +946,20 @@ bool Detector::RansacOnDevice(const mlc_ransac_settings& rs, const mlc_camera* c
     rnd_seed_ = rs.seed;
     rnd_mapping_ = rs.rng_mapping;
   }
-  const int blocks = static_cast<int>(std::min<int64_t>((num_problems + kWarpsPerBlock - 1) / kWarpsPerBlock,
-                                                        static_cast<int64_t>(sm_count_) * 2));
-  DevBuf &b_scr = d_ransac_[1], &b_out = d_ransac_[3];
+  DevBuf &b_scr = d_ransac_[1], &b_hyp = d_ransac_[2], &b_out = d_ransac_[3];
+  const int64_t num_hyp = num_problems * kHyp;
   const size_t o_cam = 0;
   const size_t o_rnd = (sizeof(mlc_camera) * num_cams + 255) & ~static_cast<size_t>(255);
   const size_t o_bear = (o_rnd + sizeof(int32_t) * rnd_len + 255) & ~static_cast<size_t>(255);
   const size_t o_shuf = (o_bear + sizeof(double) * 3 * total + 255) & ~static_cast<size_t>(255);
   if (!Cuda(b_scr.Reserve(o_shuf + sizeof(int32_t) * total + 256), "alloc", err) ||
+      !Cuda(b_hyp.Reserve(sizeof(Hypothesis) * num_hyp + sizeof(ProblemState) * num_problems + 256), "alloc", err) ||
       !Cuda(b_out.Reserve(sizeof(mlc_pose_result) * num_problems + total + 512), "alloc", err))
     return false;
   unsigned char* scr = b_scr.as<unsigned char>();
+  Hypothesis* d_hyp = b_hyp.as<Hypothesis>();
+  ProblemState* d_state = reinterpret_cast<ProblemState*>(b_hyp.as<unsigned char>() + sizeof(Hypothesis) * num_hyp);
+  int* d_remaining = reinterpret_cast<int*>(reinterpret_cast<unsigned char*>(d_state) + sizeof(ProblemState) * num_problems);
   if (!Cuda(cudaMemcpyAsync(scr + o_cam, cams, sizeof(mlc_camera) * num_cams, cudaMemcpyHostToDevice, stream_), "H2D", err) ||
       !Cuda(cudaMemcpyAsync(scr + o_rnd, rnd_host_.data(), sizeof(int32_t) * rnd_len, cudaMemcpyHostToDevice, stream_), "H2D", err))
     return false;
@@ -906,14 +987,36 @@ bool Detector::RansacOnDevice(const mlc_ransac_settings& rs, const mlc_camera* c
   a.shuffled = reinterpret_cast<int32_t*>(scr + o_shuf);
   a.results = b_out.as<mlc_pose_result>();
   a.inlier_flags = inlier_flags ? b_out.as<uint8_t>() + sizeof(mlc_pose_result) * num_problems : nullptr;
-  const size_t smem = sizeof(WarpScratch) * kWarpsPerBlock;
-  if (!Cuda(cudaFuncSetAttribute(ransac_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)),
-            "ransac smem", err))
+  const size_t smem = sizeof(double) * (GP3P_W_NUM_SLOTS + 27 + 64) * kWarpsPerBlock;
+  if (!Cuda(cudaFuncSetAttribute(gp3p_eliminate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 static_cast<int>(smem)), "ransac smem", err))
     return false;
-  ransac_kernel<<<blocks, kWarpsPerBlock * 32, smem, stream_>>>(a);
+  const unsigned warp_blocks = static_cast<unsigned>((num_problems * 32 + 127) / 128);
+  const unsigned thread_blocks = static_cast<unsigned>((num_problems + 127) / 128);
+  ransac_init_kernel<<<warp_blocks, 128, 0, stream_>>>(a, d_state);
+  CountLaunch();
+  const int max_rounds = (11 * rs.num_ransac_iters + 2 + kHyp - 1) / kHyp + 1;
+  const unsigned elim_blocks = static_cast<unsigned>(
+      std::min<int64_t>((num_hyp + kWarpsPerBlock - 1) / kWarpsPerBlock, static_cast<int64_t>(sm_count_) * 4));
+  for (int round = 0; round < max_rounds; ++round) {
+    if (!Cuda(cudaMemsetAsync(d_remaining, 0, sizeof(int), stream_), "memset", err)) return false;
+    ransac_sample_kernel<<<thread_blocks, 128, 0, stream_>>>(a, d_state, d_hyp);
+    gp3p_eliminate_kernel<<<elim_blocks, kWarpsPerBlock * 32, smem, stream_>>>(a, d_hyp, num_hyp);
+    gp3p_eigen_kernel<<<static_cast<unsigned>((num_hyp + 63) / 64), 64, 0, stream_>>>(d_hyp, num_hyp);
+    gp3p_candidate_kernel<<<static_cast<unsigned>((num_hyp * 8 + 63) / 64), 64, 0, stream_>>>(a, d_hyp, num_hyp);
+    ransac_score_kernel<<<static_cast<unsigned>((num_hyp * 32 + 127) / 128), 128, 0, stream_>>>(a, d_hyp, num_hyp);
+    ransac_update_kernel<<<thread_blocks, 128, 0, stream_>>>(a, d_state, d_hyp, d_remaining);
+    for (int i = 0; i < 6; ++i) CountLaunch();
+    int remaining = 0;
+    if (!Cuda(cudaMemcpyAsync(&remaining, d_remaining, sizeof(int), cudaMemcpyDeviceToHost, stream_), "D2H", err) ||
+        !Cuda(cudaStreamSynchronize(stream_), "ransac round", err))
+      return false;
+    if (remaining == 0) break;
+  }
+  ransac_finalize_kernel<<<warp_blocks, 128, 0, stream_>>>(a, d_state);
   CountLaunch();
   cudaEventRecord(ev_stage_[5], stream_);
-  if (!Cuda(cudaGetLastError(), "ransac kernel", err)) return false;
+  if (!Cuda(cudaGetLastError(), "ransac kernels", err)) return false;
   if (!Cuda(cudaMemcpyAsync(results, a.results, sizeof(mlc_pose_result) * num_problems, cudaMemcpyDeviceToHost, stream_),
             "D2H results", err))
     return false;
