@@ -32,15 +32,14 @@ template <int THREADS>
 __device__ __forceinline__ void BitonicSort(unsigned long long* keys, int p2) {
   for (int k2 = 2; k2 <= p2; k2 <<= 1) {
     for (int j = k2 >> 1; j > 0; j >>= 1) {
-      for (int i = threadIdx.x; i < p2; i += THREADS) {
-        const int ixj = i ^ j;
-        if (ixj > i) {
-          const bool asc = (i & k2) == 0;
-          const unsigned long long a = keys[i], b = keys[ixj];
-          if ((a > b) == asc) {
-            keys[i] = b;
-            keys[ixj] = a;
-          }
+      for (int t = threadIdx.x; t < (p2 >> 1); t += THREADS) {  // one compare-exchange per pair
+        const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+        const int ixj = i | j;
+        const bool asc = (i & k2) == 0;
+        const unsigned long long a = keys[i], b = keys[ixj];
+        if ((a > b) == asc) {
+          keys[i] = b;
+          keys[ixj] = a;
         }
       }
       __syncthreads();
@@ -204,17 +203,25 @@ __global__ void __launch_bounds__(THREADS) covis_kernel(CovisArgs a) {
       for (int i = tid; i < R; i += THREADS) s.a1[i] = s.a3[s.a1[i]];
       __syncthreads();
       // ---------------------------------------------------------------- C: landmark ids, both orders
-      for (int i = tid; i < p2; i += THREADS) {
+      // compact list of the selected matches (a8, rewritten later as listB) so that the remaining
+      // sorts run over next_pow2(S) instead of next_pow2(R) keys
+      const int S = FlagScan<THREADS, IPT>(
+          R, [&](int i) { return s.a1[i] != kNone16; },
+          [&](int i, int pos, bool f) {
+            if (f) s.a8[pos] = static_cast<uint16_t>(i);
+          },
+          scan_tmp);
+      const int ps = NextPow2(S);
+      for (int j = tid; j < ps; j += THREADS) {
         unsigned long long key = ~0ull;
-        if (i < R && s.a1[i] != kNone16)
-          key = (static_cast<unsigned long long>(rec[i].landmark + 1) << SLOT_BITS) | static_cast<unsigned>(i);
-        s.keys[i] = key;
+        if (j < S) {
+          const unsigned i = s.a8[j];
+          key = (static_cast<unsigned long long>(rec[i].landmark + 1) << SLOT_BITS) | i;
+        }
+        s.keys[j] = key;
       }
       __syncthreads();
-      BitonicSort<THREADS>(s.keys, p2);
-      // S = number of selected matches = number of keys != ~0
-      const int S = FlagScan<THREADS, IPT>(
-          R, [&](int i) { return s.keys[i] != ~0ull; }, [&](int, int, bool) {}, scan_tmp);
+      BitonicSort<THREADS>(s.keys, ps);
       // landmark dense id a4[match]; offA (a5), listA (a6) = group of the match at sorted position
       const int nL = FlagScan<THREADS, IPT>(
           S, [&](int i) { return i == 0 || (s.keys[i] >> SLOT_BITS) != (s.keys[i - 1] >> SLOT_BITS); },
@@ -229,14 +236,16 @@ __global__ void __launch_bounds__(THREADS) covis_kernel(CovisArgs a) {
       if (tid == 0) s.a5[nL] = static_cast<uint16_t>(S);
       __syncthreads();
       // order B: selected matches sorted by dense group id; offB (a7), listB (a8) = landmark id
-      for (int i = tid; i < p2; i += THREADS) {
+      for (int j = tid; j < ps; j += THREADS) {
         unsigned long long key = ~0ull;
-        if (i < R && s.a1[i] != kNone16)
-          key = (static_cast<unsigned long long>(s.a1[i]) << SLOT_BITS) | static_cast<unsigned>(i);
-        s.keys[i] = key;
+        if (j < S) {
+          const unsigned i = s.a8[j];
+          key = (static_cast<unsigned long long>(s.a1[i]) << SLOT_BITS) | i;
+        }
+        s.keys[j] = key;
       }
       __syncthreads();
-      BitonicSort<THREADS>(s.keys, p2);
+      BitonicSort<THREADS>(s.keys, ps);
       FlagScan<THREADS, IPT>(
           S, [&](int i) { return i == 0 || (s.keys[i] >> SLOT_BITS) != (s.keys[i - 1] >> SLOT_BITS); },
           [&](int i, int pos, bool f) {
@@ -321,17 +330,20 @@ __global__ void __launch_bounds__(THREADS) covis_kernel(CovisArgs a) {
           s.f1[i] = (s.f2[i] && K[s.a1[i]] == best_root) ? 1 : 0;
         __syncthreads();
         const bool unique = a.by_vertex ? true : (item.make_unique != 0);
-        for (int i = tid; i < p2; i += THREADS) {
+        // winners are a subset of the selected matches: walk the order-B positions (each thread
+        // rewrites exactly the key slots it read)
+        for (int j = tid; j < ps; j += THREADS) {
           unsigned long long key = ~0ull;
-          if (i < R && s.f1[i]) {
+          const int i = j < S ? static_cast<int>(s.keys[j] & SLOT_MASK) : -1;
+          if (i >= 0 && s.f1[i]) {
             bool keep = true;
             const mlc_match me = rec[i];
             if (unique) {
               // (query keypoint, landmark) unique: the smallest database descriptor survives
               for (int d = -(a.k - 1); d <= a.k - 1; ++d) {
-                const int j = i + d;
-                if (d == 0 || j < 0 || j >= R || !s.f1[j]) continue;
-                const mlc_match o = rec[j];
+                const int o_i = i + d;
+                if (d == 0 || o_i < 0 || o_i >= R || !s.f1[o_i]) continue;
+                const mlc_match o = rec[o_i];
                 if (o.query_frame == me.query_frame && o.query_keypoint == me.query_keypoint &&
                     o.landmark == me.landmark && o.db_descriptor < me.db_descriptor)
                   keep = false;
@@ -346,12 +358,12 @@ __global__ void __launch_bounds__(THREADS) covis_kernel(CovisArgs a) {
                     static_cast<unsigned>(i);
             }
           }
-          s.keys[i] = key;
+          s.keys[j] = key;
         }
         __syncthreads();
-        BitonicSort<THREADS>(s.keys, p2);
+        BitonicSort<THREADS>(s.keys, ps);
         out_count = FlagScan<THREADS, IPT>(
-            R, [&](int i) { return s.keys[i] != ~0ull; },
+            S, [&](int i) { return s.keys[i] != ~0ull; },
             [&](int i, int pos, bool f) {
               if (f) out[pos] = rec[s.keys[i] & SLOT_MASK];
             },
