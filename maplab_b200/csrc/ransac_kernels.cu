@@ -46,7 +46,8 @@ enum {
 
 constexpr int N8 = 8;
 constexpr int kWarpsPerBlock = 4;
-constexpr int kHyp = 8;  // hypotheses evaluated speculatively per round
+constexpr int kHyp = 16;      // hypothesis slots per problem
+constexpr int kHypFirst = 8;  // speculated in the first round (k is still unknown)
 
 struct RansacArgs {
   int64_t num_problems;
@@ -129,165 +130,7 @@ __device__ void Gp3pEliminateWarp(const RansacArgs& a, const double* fvp, double
 // ---------------------------------------------------------------- 8x8 real eigen-solver
 // Householder Hessenberg reduction + Francis shifted QR (EISPACK orthes / hqr scheme), exactly
 // the operation sequence of the oracle (oracle/pnp.cc).
-__device__ void Hessenberg(double H[N8][N8]) {
-  double ort[N8];
-  const int high = N8 - 1;
-  for (int m = 1; m <= high - 1; ++m) {
-    double scale = 0.0;
-    for (int i = m; i <= high; ++i) scale += fabs(H[i][m - 1]);
-    if (scale != 0.0) {
-      double h = 0.0;
-      for (int i = high; i >= m; --i) {
-        ort[i] = H[i][m - 1] / scale;
-        h += ort[i] * ort[i];
-      }
-      double g = sqrt(h);
-      if (ort[m] > 0) g = -g;
-      h -= ort[m] * g;
-      ort[m] -= g;
-      for (int j = m; j < N8; ++j) {
-        double fsum = 0.0;
-        for (int i = high; i >= m; --i) fsum += ort[i] * H[i][j];
-        fsum /= h;
-        for (int i = m; i <= high; ++i) H[i][j] -= fsum * ort[i];
-      }
-      for (int i = 0; i <= high; ++i) {
-        double fsum = 0.0;
-        for (int j = high; j >= m; --j) fsum += ort[j] * H[i][j];
-        fsum /= h;
-        for (int j = m; j <= high; ++j) H[i][j] -= fsum * ort[j];
-      }
-      ort[m] = scale * ort[m];
-      H[m][m - 1] = scale * g;
-    }
-  }
-  for (int i = 2; i < N8; ++i)
-    for (int j = 0; j < i - 1; ++j) H[i][j] = 0.0;
-}
-
 __device__ __forceinline__ double SignOf(double a, double b) { return b >= 0.0 ? fabs(a) : -fabs(a); }
-
-__device__ bool HqrEigenvalues(double a[N8][N8], double wr[N8], double wi[N8]) {
-  int nn, m, l, k, j, its, i, mmin;
-  double z, y, x, w, v, u, t, s, r = 0, q = 0, p = 0, anorm = 0.0;
-  for (i = 0; i < N8; i++)
-    for (j = (i - 1 > 0 ? i - 1 : 0); j < N8; j++) anorm += fabs(a[i][j]);
-  nn = N8 - 1;
-  t = 0.0;
-  while (nn >= 0) {
-    its = 0;
-    do {
-      for (l = nn; l >= 1; l--) {
-        s = fabs(a[l - 1][l - 1]) + fabs(a[l][l]);
-        if (s == 0.0) s = anorm;
-        if (fabs(a[l][l - 1]) + s == s) {
-          a[l][l - 1] = 0.0;
-          break;
-        }
-      }
-      x = a[nn][nn];
-      if (l == nn) {
-        wr[nn] = x + t;
-        wi[nn--] = 0.0;
-      } else {
-        y = a[nn - 1][nn - 1];
-        w = a[nn][nn - 1] * a[nn - 1][nn];
-        if (l == (nn - 1)) {
-          p = 0.5 * (y - x);
-          q = p * p + w;
-          z = sqrt(fabs(q));
-          x += t;
-          if (q >= 0.0) {
-            z = p + SignOf(z, p);
-            wr[nn - 1] = wr[nn] = x + z;
-            if (z != 0.0) wr[nn] = x - w / z;
-            wi[nn - 1] = wi[nn] = 0.0;
-          } else {
-            wr[nn - 1] = wr[nn] = x + p;
-            wi[nn - 1] = -(wi[nn] = z);
-          }
-          nn -= 2;
-        } else {
-          if (its == 60) return false;
-          if (its == 10 || its == 20) {
-            t += x;
-            for (i = 0; i <= nn; i++) a[i][i] -= x;
-            s = fabs(a[nn][nn - 1]) + fabs(a[nn - 1][nn - 2]);
-            y = x = 0.75 * s;
-            w = -0.4375 * s * s;
-          }
-          ++its;
-          for (m = (nn - 2); m >= l; m--) {
-            z = a[m][m];
-            r = x - z;
-            s = y - z;
-            p = (r * s - w) / a[m + 1][m] + a[m][m + 1];
-            q = a[m + 1][m + 1] - z - r - s;
-            r = a[m + 2][m + 1];
-            s = fabs(p) + fabs(q) + fabs(r);
-            p /= s;
-            q /= s;
-            r /= s;
-            if (m == l) break;
-            u = fabs(a[m][m - 1]) * (fabs(q) + fabs(r));
-            v = fabs(p) * (fabs(a[m - 1][m - 1]) + fabs(z) + fabs(a[m + 1][m + 1]));
-            if (u + v == v) break;
-          }
-          for (i = m + 2; i <= nn; i++) {
-            a[i][i - 2] = 0.0;
-            if (i != (m + 2)) a[i][i - 3] = 0.0;
-          }
-          for (k = m; k <= nn - 1; k++) {
-            if (k != m) {
-              p = a[k][k - 1];
-              q = a[k + 1][k - 1];
-              r = 0.0;
-              if (k != (nn - 1)) r = a[k + 2][k - 1];
-              if ((x = fabs(p) + fabs(q) + fabs(r)) != 0.0) {
-                p /= x;
-                q /= x;
-                r /= x;
-              }
-            }
-            if ((s = SignOf(sqrt(p * p + q * q + r * r), p)) != 0.0) {
-              if (k == m) {
-                if (l != m) a[k][k - 1] = -a[k][k - 1];
-              } else {
-                a[k][k - 1] = -s * x;
-              }
-              p += s;
-              x = p / s;
-              y = q / s;
-              z = r / s;
-              q /= p;
-              r /= p;
-              for (j = k; j <= nn; j++) {
-                p = a[k][j] + q * a[k + 1][j];
-                if (k != (nn - 1)) {
-                  p += r * a[k + 2][j];
-                  a[k + 2][j] -= p * z;
-                }
-                a[k + 1][j] -= p * y;
-                a[k][j] -= p * x;
-              }
-              mmin = nn < k + 3 ? nn : k + 3;
-              for (i = l; i <= mmin; i++) {
-                p = x * a[i][k] + y * a[i][k + 1];
-                if (k != (nn - 1)) {
-                  p += z * a[i][k + 2];
-                  a[i][k + 2] -= p * r;
-                }
-                a[i][k + 1] -= p * q;
-                a[i][k] -= p;
-              }
-            }
-          }
-        }
-      }
-    } while (l < nn - 1);
-  }
-  return true;
-}
 
 struct Cx {
   double re, im;
@@ -553,15 +396,23 @@ __global__ void __launch_bounds__(128) ransac_init_kernel(RansacArgs a, ProblemS
   }
 }
 
-// Draw the next kHyp samples of every running problem (persistent partial Fisher-Yates).
+// Draw the next samples of every running problem (persistent partial Fisher-Yates). First round:
+// kHypFirst samples; later rounds: as many as the adaptive bound k still asks for (<= kHyp).
 __global__ void __launch_bounds__(128) ransac_sample_kernel(RansacArgs a, ProblemState* st, Hypothesis* hyp) {
   const int64_t pi = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
   if (pi >= a.num_problems) return;
   ProblemState& s = st[pi];
   Hypothesis* h = hyp + pi * kHyp;
   const int max_skip = a.max_iterations * 10;
-  bool run = !s.done && (static_cast<double>(s.iterations) < s.k && s.skipped < max_skip) &&
-             (s.stream_pos + 4 * kHyp <= a.rnd_len);
+  int want = kHypFirst;
+  if (s.stream_pos > 0) {
+    const double need = ceil(s.k - static_cast<double>(s.iterations));
+    want = need >= static_cast<double>(kHyp) ? kHyp : (need <= 1.0 ? 1 : static_cast<int>(need));
+    const int room = a.max_iterations + 1 - s.iterations;  // iterations_ > max_iterations_ stops the loop
+    if (want > room) want = room > 1 ? room : 1;
+  }
+  const bool run = !s.done && (static_cast<double>(s.iterations) < s.k && s.skipped < max_skip) &&
+                   (s.stream_pos + 4 * want <= a.rnd_len);
   if (!run) {
     s.done = 1;
     for (int t = 0; t < kHyp; ++t) h[t].active = 0;
@@ -570,7 +421,7 @@ __global__ void __launch_bounds__(128) ransac_sample_kernel(RansacArgs a, Proble
   const int64_t off = a.offsets[pi];
   const int n = static_cast<int>(a.offsets[pi + 1] - off);
   int32_t* shuf = a.shuffled + off;
-  for (int t = 0; t < kHyp; ++t) {
+  for (int t = 0; t < want; ++t) {
     for (int i = 0; i < 4; ++i) {
       const int j = i + a.rnd_stream[s.stream_pos + 4 * t + i] % (n - i);
       const int32_t tmp = shuf[i];
@@ -580,7 +431,8 @@ __global__ void __launch_bounds__(128) ransac_sample_kernel(RansacArgs a, Proble
     for (int i = 0; i < 4; ++i) h[t].sel[i] = shuf[i];
     h[t].active = 1;
   }
-  s.stream_pos += 4 * kHyp;
+  for (int t = want; t < kHyp; ++t) h[t].active = 0;
+  s.stream_pos += 4 * want;
 }
 
 // Groebner elimination: one warp per hypothesis, slot array in shared memory.
@@ -620,30 +472,225 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) gp3p_eliminate_kernel(Ran
   }
 }
 
-// Eigenvalues of the 8x8 action matrix: one thread per hypothesis.
-__global__ void __launch_bounds__(64) gp3p_eigen_kernel(Hypothesis* hyp, int64_t num_hyp) {
-  const int64_t hi = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
-  if (hi >= num_hyp) return;
-  Hypothesis& h = hyp[hi];
-  if (!h.active) return;
-  double H[N8][N8];
-  bool finite = true;
-  for (int r = 0; r < N8; ++r)
-    for (int c = 0; c < N8; ++c) {
-      H[r][c] = h.M[r * 8 + c];
-      if (!isfinite(H[r][c])) finite = false;
-    }
-  bool ok = finite;
-  if (ok) {
-    Hessenberg(H);
-    double wr[N8], wi[N8];
-    ok = HqrEigenvalues(H, wr, wi);
-    for (int c = 0; c < N8; ++c) {
-      h.wr[c] = wr[c];
-      h.wi[c] = wi[c];
+// Eigenvalues of the 8x8 action matrix: EIGHT lanes per hypothesis. The matrix lives in shared
+// memory; every scalar quantity of orthes/hqr is evaluated redundantly by the 8 lanes (same
+// operations, same order), the row/column update loops — whose iterations are independent — are
+// dealt one row or column per lane. Bit-identical to the sequential Hessenberg()/HqrEigenvalues().
+#define A_(i, j) a[(i) * 8 + (j)]
+__device__ void HessenbergGroup(double* a, int L, unsigned gm) {
+  double ort[N8];
+  const int high = N8 - 1;
+  for (int m = 1; m <= high - 1; ++m) {
+    double scale = 0.0;
+    for (int i = m; i <= high; ++i) scale += fabs(A_(i, m - 1));
+    if (scale != 0.0) {
+      double h = 0.0;
+      for (int i = high; i >= m; --i) {
+        ort[i] = A_(i, m - 1) / scale;
+        h += ort[i] * ort[i];
+      }
+      double g = sqrt(h);
+      if (ort[m] > 0) g = -g;
+      h -= ort[m] * g;
+      ort[m] -= g;
+      __syncwarp(gm);  // everyone has read column m-1
+      if (L >= m) {    // column L
+        const int j = L;
+        double fsum = 0.0;
+        for (int i = high; i >= m; --i) fsum += ort[i] * A_(i, j);
+        fsum /= h;
+        for (int i = m; i <= high; ++i) A_(i, j) -= fsum * ort[i];
+      }
+      __syncwarp(gm);
+      {  // row L
+        const int i = L;
+        double fsum = 0.0;
+        for (int j = high; j >= m; --j) fsum += ort[j] * A_(i, j);
+        fsum /= h;
+        for (int j = m; j <= high; ++j) A_(i, j) -= fsum * ort[j];
+      }
+      __syncwarp(gm);
+      if (L == 0) A_(m, m - 1) = scale * g;
+      __syncwarp(gm);
     }
   }
-  h.eig_ok = ok ? 1 : 0;
+  if (L >= 2)
+    for (int j = 0; j < L - 1; ++j) A_(L, j) = 0.0;
+  __syncwarp(gm);
+}
+
+__device__ bool HqrGroup(double* a, double* wr, double* wi, int L, unsigned gm) {
+  int nn, m, l, k, j, its, i, mmin;
+  double z, y, x, w, v, u, t, s, r = 0, q = 0, p = 0, anorm = 0.0;
+  for (i = 0; i < N8; i++)
+    for (j = (i - 1 > 0 ? i - 1 : 0); j < N8; j++) anorm += fabs(A_(i, j));
+  nn = N8 - 1;
+  t = 0.0;
+  while (nn >= 0) {
+    its = 0;
+    do {
+      for (l = nn; l >= 1; l--) {
+        s = fabs(A_(l - 1, l - 1)) + fabs(A_(l, l));
+        if (s == 0.0) s = anorm;
+        if (fabs(A_(l, l - 1)) + s == s) {
+          __syncwarp(gm);
+          if (L == 0) A_(l, l - 1) = 0.0;
+          __syncwarp(gm);
+          break;
+        }
+      }
+      x = A_(nn, nn);
+      if (l == nn) {
+        if (L == 0) {
+          wr[nn] = x + t;
+          wi[nn] = 0.0;
+        }
+        nn--;
+      } else {
+        y = A_(nn - 1, nn - 1);
+        w = A_(nn, nn - 1) * A_(nn - 1, nn);
+        if (l == (nn - 1)) {
+          p = 0.5 * (y - x);
+          q = p * p + w;
+          z = sqrt(fabs(q));
+          x += t;
+          if (L == 0) {
+            if (q >= 0.0) {
+              z = p + SignOf(z, p);
+              wr[nn - 1] = wr[nn] = x + z;
+              if (z != 0.0) wr[nn] = x - w / z;
+              wi[nn - 1] = wi[nn] = 0.0;
+            } else {
+              wr[nn - 1] = wr[nn] = x + p;
+              wi[nn - 1] = -(wi[nn] = z);
+            }
+          }
+          nn -= 2;
+        } else {
+          if (its == 60) return false;
+          if (its == 10 || its == 20) {
+            t += x;
+            __syncwarp(gm);
+            if (L <= nn) A_(L, L) -= x;
+            __syncwarp(gm);
+            s = fabs(A_(nn, nn - 1)) + fabs(A_(nn - 1, nn - 2));
+            y = x = 0.75 * s;
+            w = -0.4375 * s * s;
+          }
+          ++its;
+          for (m = (nn - 2); m >= l; m--) {
+            z = A_(m, m);
+            r = x - z;
+            s = y - z;
+            p = (r * s - w) / A_(m + 1, m) + A_(m, m + 1);
+            q = A_(m + 1, m + 1) - z - r - s;
+            r = A_(m + 2, m + 1);
+            s = fabs(p) + fabs(q) + fabs(r);
+            p /= s;
+            q /= s;
+            r /= s;
+            if (m == l) break;
+            u = fabs(A_(m, m - 1)) * (fabs(q) + fabs(r));
+            v = fabs(p) * (fabs(A_(m - 1, m - 1)) + fabs(z) + fabs(A_(m + 1, m + 1)));
+            if (u + v == v) break;
+          }
+          __syncwarp(gm);
+          if (L >= m + 2 && L <= nn) {
+            A_(L, L - 2) = 0.0;
+            if (L != (m + 2)) A_(L, L - 3) = 0.0;
+          }
+          __syncwarp(gm);
+          for (k = m; k <= nn - 1; k++) {
+            if (k != m) {
+              p = A_(k, k - 1);
+              q = A_(k + 1, k - 1);
+              r = 0.0;
+              if (k != (nn - 1)) r = A_(k + 2, k - 1);
+              if ((x = fabs(p) + fabs(q) + fabs(r)) != 0.0) {
+                p /= x;
+                q /= x;
+                r /= x;
+              }
+            }
+            if ((s = SignOf(sqrt(p * p + q * q + r * r), p)) != 0.0) {
+              __syncwarp(gm);  // all lanes have read column k-1
+              if (L == 0) {
+                if (k == m) {
+                  if (l != m) A_(k, k - 1) = -A_(k, k - 1);
+                } else {
+                  A_(k, k - 1) = -s * x;
+                }
+              }
+              p += s;
+              x = p / s;
+              y = q / s;
+              z = r / s;
+              q /= p;
+              r /= p;
+              __syncwarp(gm);
+              if (L >= k && L <= nn) {  // row modification, column L
+                j = L;
+                double pp = A_(k, j) + q * A_(k + 1, j);
+                if (k != (nn - 1)) {
+                  pp += r * A_(k + 2, j);
+                  A_(k + 2, j) -= pp * z;
+                }
+                A_(k + 1, j) -= pp * y;
+                A_(k, j) -= pp * x;
+              }
+              __syncwarp(gm);
+              mmin = nn < k + 3 ? nn : k + 3;
+              if (L >= l && L <= mmin) {  // column modification, row L
+                i = L;
+                double pp = x * A_(i, k) + y * A_(i, k + 1);
+                if (k != (nn - 1)) {
+                  pp += z * A_(i, k + 2);
+                  A_(i, k + 2) -= pp * r;
+                }
+                A_(i, k + 1) -= pp * q;
+                A_(i, k) -= pp;
+              }
+              __syncwarp(gm);
+            }
+          }
+        }
+      }
+    } while (l < nn - 1);
+  }
+  return true;
+}
+#undef A_
+
+__global__ void __launch_bounds__(128) gp3p_eigen_kernel(Hypothesis* hyp, int64_t num_hyp) {
+  __shared__ double s_a[16][64];
+  __shared__ double s_w[16][16];
+  const int lane = threadIdx.x & 31;
+  const int L = lane & 7;
+  const int g = threadIdx.x >> 3;  // group within the block
+  const unsigned gm = 0xFFu << (lane & 24);
+  const int64_t hi = static_cast<int64_t>(blockIdx.x) * 16 + g;
+  if (hi >= num_hyp) return;   // whole group leaves together
+  Hypothesis& h = hyp[hi];
+  if (!h.active) return;
+  double* a = s_a[g];
+  bool finite = true;
+  for (int c = 0; c < N8; ++c) {
+    const double v = h.M[L * 8 + c];
+    a[L * 8 + c] = v;
+    if (!isfinite(v)) finite = false;
+  }
+  const bool ok_in = __all_sync(gm, finite);
+  bool ok = ok_in;
+  if (ok) {
+    HessenbergGroup(a, L, gm);
+    ok = HqrGroup(a, s_w[g], s_w[g] + 8, L, gm);
+    __syncwarp(gm);
+    if (ok) {
+      h.wr[L] = s_w[g][L];
+      h.wi[L] = s_w[g][8 + L];
+    }
+  }
+  if (L == 0) h.eig_ok = ok ? 1 : 0;
 }
 
 // Candidate pose + disambiguation score: one thread per (hypothesis, eigenvalue).
@@ -714,7 +761,7 @@ __global__ void __launch_bounds__(128) ransac_update_kernel(RansacArgs a, Proble
       const Hypothesis* h = hyp + pi * kHyp;
       const int n = static_cast<int>(a.offsets[pi + 1] - a.offsets[pi]);
       const int max_skip = a.max_iterations * 10;
-      for (int t = 0; t < kHyp; ++t) {
+      for (int t = 0; t < kHyp && h[t].active; ++t) {
         if (!(static_cast<double>(s.iterations) < s.k && s.skipped < max_skip)) {
           s.done = 1;
           break;
@@ -938,7 +985,7 @@ bool Detector::RansacOnDevice(const mlc_ransac_settings& rs, const mlc_camera* c
   focal /= (2.0 * static_cast<double>(num_cams));
   const double threshold = 1.0 - std::cos(std::atan(rs.ransac_pixel_sigma / focal));
   // draws: 4 per attempted sample; attempts <= max_iterations + 1 counted + 10 * max_iterations skipped
-  const int rnd_len = 4 * (11 * rs.num_ransac_iters + 2 + 2 * kHyp);
+  const int rnd_len = 4 * (11 * rs.num_ransac_iters + 2 + 2 * kHyp);  // worst case + speculation slack
   if (rnd_seed_ != rs.seed || rnd_mapping_ != rs.rng_mapping || static_cast<int>(rnd_host_.size()) != rnd_len) {
     rnd_host_.resize(rnd_len);
     HostRng rng(rs.seed, rs.rng_mapping);
@@ -995,14 +1042,14 @@ bool Detector::RansacOnDevice(const mlc_ransac_settings& rs, const mlc_camera* c
   const unsigned thread_blocks = static_cast<unsigned>((num_problems + 127) / 128);
   ransac_init_kernel<<<warp_blocks, 128, 0, stream_>>>(a, d_state);
   CountLaunch();
-  const int max_rounds = (11 * rs.num_ransac_iters + 2 + kHyp - 1) / kHyp + 1;
+  const int max_rounds = 11 * rs.num_ransac_iters + 4;  // >= one consumed sample per round
   const unsigned elim_blocks = static_cast<unsigned>(
       std::min<int64_t>((num_hyp + kWarpsPerBlock - 1) / kWarpsPerBlock, static_cast<int64_t>(sm_count_) * 4));
   for (int round = 0; round < max_rounds; ++round) {
     if (!Cuda(cudaMemsetAsync(d_remaining, 0, sizeof(int), stream_), "memset", err)) return false;
     ransac_sample_kernel<<<thread_blocks, 128, 0, stream_>>>(a, d_state, d_hyp);
     gp3p_eliminate_kernel<<<elim_blocks, kWarpsPerBlock * 32, smem, stream_>>>(a, d_hyp, num_hyp);
-    gp3p_eigen_kernel<<<static_cast<unsigned>((num_hyp + 63) / 64), 64, 0, stream_>>>(d_hyp, num_hyp);
+    gp3p_eigen_kernel<<<static_cast<unsigned>((num_hyp + 15) / 16), 128, 0, stream_>>>(d_hyp, num_hyp);
     gp3p_candidate_kernel<<<static_cast<unsigned>((num_hyp * 8 + 63) / 64), 64, 0, stream_>>>(a, d_hyp, num_hyp);
     ransac_score_kernel<<<static_cast<unsigned>((num_hyp * 32 + 127) / 128), 128, 0, stream_>>>(a, d_hyp, num_hyp);
     ransac_update_kernel<<<thread_blocks, 128, 0, stream_>>>(a, d_state, d_hyp, d_remaining);
