@@ -66,101 +66,175 @@ __device__ __forceinline__ float SquaredDistanceCanonical(const float (&a)[DIM],
   }
 }
 
-// One warp per query descriptor. The visited cells' lists are flattened into one entry range and
-// dealt to the lanes 32 at a time; inside a block of the list the layout is [dim+1][block size]
-// words, so the 32 lanes of a full block read 128 contiguous bytes per dimension.
+// One warp per query descriptor, persistent warps. The (<= 16) visited cells' lists are flattened
+// into one entry range and dealt to the lanes 64 at a time (two independent 32-entry windows per
+// trip, so 2 x (DIM + 1) loads per lane are in flight); inside a block of a list the layout is
+// [dim+1][block size] words, so the 32 lanes of a full block read 128 contiguous bytes per
+// dimension. Query metadata is software-pipelined two deep: while query i is scanned, the cell
+// table entries of query i+1 and the visit list of query i+2 are already in flight, which hides
+// the dependent chain visit list -> cell table -> list entries.
+constexpr int kScanThreads = 256;
+constexpr int kScanCtasPerSm = 3;
+constexpr uint32_t kFull = 0xffffffffu;
+
+struct ScanEntry {
+  uint64_t key;
+};
+
+template <int DIM>
+__device__ __forceinline__ void LoadWindow(const uint32_t* __restrict__ lists, const uint4* seg,
+                                           uint32_t base, uint32_t total, uint32_t len,
+                                           uint32_t excl, int lane, uint32_t lanemask_le,
+                                           float (&sv)[DIM], uint32_t* id, bool* valid) {
+  // non-empty cells whose first entry falls into this window set bit (first entry - base)
+  const uint32_t rel = excl - base;
+  const uint32_t heads = __reduce_or_sync(kFull, (len > 0 && rel < 32u) ? (1u << rel) : 0u);
+  const uint32_t before = __popc(__ballot_sync(kFull, len > 0 && excl < base));
+  const uint32_t e = base + lane;
+  *valid = e < total;
+  if (*valid) {
+    const uint4 s = seg[before + __popc(heads & lanemask_le) - 1];  // {excl, start16, len}
+    const uint32_t within = e - s.x;            // entry number inside its cell
+    const uint32_t blk = within >> 5;           // block of 32 entries
+    const uint32_t bs = min(32u, s.z - (blk << 5));
+    const uint32_t* w = lists + (static_cast<size_t>(s.y) << 2) +
+                        static_cast<size_t>(blk) * ((DIM + 1) * 32) + (within & 31u);
+#pragma unroll
+    for (int d = 0; d < DIM; ++d) sv[d] = __uint_as_float(__ldg(w + d * bs));
+    *id = __ldg(w + DIM * bs);
+  }
+}
+
+template <int KT>
+__device__ __forceinline__ void InsertKey(uint64_t (&best)[KT], uint64_t key) {
+  if (key < best[KT - 1]) {
+#pragma unroll
+    for (int i = 0; i < KT; ++i) {
+      const bool lt = key < best[i];
+      const uint64_t lo = lt ? key : best[i];
+      const uint64_t hi = lt ? best[i] : key;
+      best[i] = lo;
+      key = hi;
+    }
+  }
+}
+
 template <int DIM, int KT>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(kScanThreads, kScanCtasPerSm)
 imi_scan_kernel(const float* __restrict__ q, int64_t n_q, const int32_t* __restrict__ cells, int nw,
                 const uint2* __restrict__ cell_info, const uint32_t* __restrict__ lists, int k,
                 int32_t* __restrict__ out_idx, float* __restrict__ out_dist) {
+  __shared__ uint4 seg_s[kScanThreads / 32][kMaxWords];
   const int lane = threadIdx.x & 31;
-  const int64_t warp_global = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 5;
+  uint4* seg = seg_s[threadIdx.x >> 5];
+  const uint32_t lanemask_lt = (1u << lane) - 1u;
+  const uint32_t lanemask_le = lanemask_lt | (1u << lane);
   const int64_t warp_stride = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
-  for (int64_t qi = warp_global; qi < n_q; qi += warp_stride) {
-    float qv[DIM];
-#pragma unroll
-    for (int d = 0; d < DIM; ++d) qv[d] = __ldg(q + qi * DIM + d);
-    uint32_t start16 = 0, len = 0;
+  int64_t qi = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 5;
+  if (qi >= n_q) return;
+
+  // pipeline prologue: visit list of queries 0 and 1, cell table entries + descriptor of query 0
+  int32_t c_next = -1;
+  uint2 info = make_uint2(0u, 0u);
+  float q_l = 0.f;
+  {
+    int32_t c = -1;
     if (lane < nw) {
-      const int32_t c = __ldg(cells + qi * nw + lane);
-      if (c >= 0) {
-        const uint2 info = __ldg(cell_info + c);
-        start16 = info.x;
-        len = info.y;
-      }
+      c = __ldg(cells + qi * nw + lane);
+      if (qi + warp_stride < n_q) c_next = __ldg(cells + (qi + warp_stride) * nw + lane);
     }
-    // inclusive prefix sum of list lengths over the (<= 16) cell lanes
-    uint32_t incl = len;
+    if (lane < DIM) q_l = __ldg(q + qi * DIM + lane);
+    if (c >= 0) info = __ldg(cell_info + c);
+  }
+
+  for (; qi < n_q; qi += warp_stride) {
+    // ---- prefetch: cell table of query i+1, visit list of query i+2, descriptor of query i+1
+    uint2 info_next = make_uint2(0u, 0u);
+    int32_t c_next2 = -1;
+    float q_next_l = 0.f;
+    if (c_next >= 0) info_next = __ldg(cell_info + c_next);
+    if (qi + warp_stride < n_q) {
+      if (lane < DIM) q_next_l = __ldg(q + (qi + warp_stride) * DIM + lane);
+      if (lane < nw && qi + 2 * warp_stride < n_q)
+        c_next2 = __ldg(cells + (qi + 2 * warp_stride) * nw + lane);
+    }
+
+    // ---- this query
+    const uint32_t start16 = info.x, len = info.y;
+    uint32_t incl = len;  // inclusive prefix sum over the (<= 16) cell lanes
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+    for (int o = 1; o < kMaxWords; o <<= 1) {
+      const uint32_t v = __shfl_up_sync(kFull, incl, o);
       if (lane >= o) incl += v;
     }
-    const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+    const uint32_t total = __shfl_sync(kFull, incl, kMaxWords - 1);
     const uint32_t excl = incl - len;
+    const uint32_t nonempty = __ballot_sync(kFull, len > 0);
+    if (len > 0) seg[__popc(nonempty & lanemask_lt)] = make_uint4(excl, start16, len, 0u);
+    float qv[DIM];
+#pragma unroll
+    for (int d = 0; d < DIM; ++d) qv[d] = __shfl_sync(kFull, q_l, d);
+    __syncwarp();
 
     uint64_t best[KT];
 #pragma unroll
     for (int i = 0; i < KT; ++i) best[i] = kEmptyKey;
 
-    for (uint32_t base = 0; base < total; base += 32) {
-      const uint32_t e = base + lane;
-      // cell of entry e: number of cells whose inclusive prefix is <= e
-      int cell_lane = 0;
-      uint32_t c_excl = 0, c_start = 0, c_len = 0;
-#pragma unroll
-      for (int j = 0; j < kMaxWords; ++j) {
-        if (j < nw) {
-          const uint32_t inc_j = __shfl_sync(0xffffffffu, incl, j);
-          if (inc_j <= e) cell_lane = j + 1;
+    for (uint32_t base = 0; base < total; base += 64) {
+      float sa[DIM], sb[DIM];
+      uint32_t ida = 0xFFFFFFFFu, idb = 0xFFFFFFFFu;
+      bool va = false, vb = false;
+      LoadWindow<DIM>(lists, seg, base, total, len, excl, lane, lanemask_le, sa, &ida, &va);
+      const bool second = base + 32 < total;  // warp-uniform
+      if (second)
+        LoadWindow<DIM>(lists, seg, base + 32, total, len, excl, lane, lanemask_le, sb, &idb, &vb);
+      uint64_t ka = kEmptyKey, kb = kEmptyKey;
+      if (va)
+        ka = (static_cast<uint64_t>(__float_as_uint(SquaredDistanceCanonical<DIM>(sa, qv))) << 32) | ida;
+      if (vb)
+        kb = (static_cast<uint64_t>(__float_as_uint(SquaredDistanceCanonical<DIM>(sb, qv))) << 32) | idb;
+      if (base == 0) {
+        // first trip: the per-lane list is empty, so the two keys only need ordering
+        if constexpr (KT >= 2) {
+          best[0] = ka < kb ? ka : kb;
+          best[1] = ka < kb ? kb : ka;
+        } else {
+          best[0] = ka < kb ? ka : kb;
         }
-      }
-      cell_lane = min(cell_lane, nw - 1);
-      c_excl = __shfl_sync(0xffffffffu, excl, cell_lane);
-      c_start = __shfl_sync(0xffffffffu, start16, cell_lane);
-      c_len = __shfl_sync(0xffffffffu, len, cell_lane);
-      if (e < total) {
-        const uint32_t within = e - c_excl;         // entry number inside its cell
-        const uint32_t blk = within >> 5;           // block of 32 entries
-        const uint32_t bs = min(32u, c_len - (blk << 5));
-        const uint32_t* w = lists + (static_cast<size_t>(c_start) << 2) +
-                            static_cast<size_t>(blk) * ((DIM + 1) * 32) + (within & 31u);
-        float sv[DIM];
-#pragma unroll
-        for (int d = 0; d < DIM; ++d) sv[d] = __uint_as_float(__ldg(w + d * bs));
-        const uint32_t id = __ldg(w + DIM * bs);
-        const float dist = SquaredDistanceCanonical<DIM>(sv, qv);
-        uint64_t key = (static_cast<uint64_t>(__float_as_uint(dist)) << 32) | id;
-        if (key < best[KT - 1]) {
-#pragma unroll
-          for (int i = 0; i < KT; ++i) {
-            const uint64_t lo = key < best[i] ? key : best[i];
-            const uint64_t hi = key < best[i] ? best[i] : key;
-            best[i] = lo;
-            key = hi;
-          }
-        }
+      } else {
+        InsertKey<KT>(best, ka);
+        if (second) InsertKey<KT>(best, kb);
       }
     }
-    // k rounds of warp arg-min over the lanes' heads
+    __syncwarp();  // every lane is done with seg before the next query overwrites it
+
+    // ---- k rounds of warp arg-min over the lanes' heads; lane r keeps the r-th result
+    uint32_t res_d = 0x7f800000u, res_i = 0xFFFFFFFFu;
     for (int r = 0; r < k; ++r) {
       const uint32_t hd = static_cast<uint32_t>(best[0] >> 32);
-      const uint32_t hi_min = __reduce_min_sync(0xffffffffu, hd);
-      const uint32_t lo_cand = (hd == hi_min) ? static_cast<uint32_t>(best[0]) : 0xFFFFFFFFu;
-      const uint32_t lo_min = __reduce_min_sync(0xffffffffu, lo_cand);
-      const bool winner = (hd == hi_min) && (static_cast<uint32_t>(best[0]) == lo_min);
-      if (lane == 0) {
-        const bool empty = (hi_min == 0x7f800000u && lo_min == 0xFFFFFFFFu);
-        out_idx[qi * k + r] = empty ? -1 : static_cast<int32_t>(lo_min);
-        out_dist[qi * k + r] = __uint_as_float(hi_min);
+      const uint32_t id = static_cast<uint32_t>(best[0]);
+      const uint32_t hi_min = __reduce_min_sync(kFull, hd);
+      const uint32_t lo_min = __reduce_min_sync(kFull, (hd == hi_min) ? id : 0xFFFFFFFFu);
+      if (lane == r) {
+        res_d = hi_min;
+        res_i = lo_min;
       }
-      if (winner && !(hi_min == 0x7f800000u && lo_min == 0xFFFFFFFFu)) {
+      if (hi_min == 0x7f800000u && lo_min == 0xFFFFFFFFu) break;  // nothing left (warp-uniform)
+      if (hd == hi_min && id == lo_min) {
 #pragma unroll
         for (int i = 0; i + 1 < KT; ++i) best[i] = best[i + 1];
         best[KT - 1] = kEmptyKey;
       }
     }
+    if (lane < k) {  // missing neighbours: (+inf, -1), trailing
+      out_idx[qi * k + lane] = static_cast<int32_t>(res_i);
+      out_dist[qi * k + lane] = __uint_as_float(res_d);
+    }
+
+    // ---- rotate the pipeline
+    info = info_next;
+    c_next = c_next2;
+    q_l = q_next_l;
   }
 }
 
@@ -168,9 +242,9 @@ template <int DIM>
 cudaError_t LaunchScanDim(const float* q, int64_t n_q, const int32_t* cells, int nw,
                           const uint2* cell_info, const uint32_t* lists, int k, int32_t* out_idx,
                           float* out_dist, int sm_count, cudaStream_t stream) {
-  const int threads = 256;
+  const int threads = kScanThreads;
   int64_t blocks = (n_q * 32 + threads - 1) / threads;
-  const int64_t cap = static_cast<int64_t>(sm_count) * 32;
+  const int64_t cap = static_cast<int64_t>(sm_count) * kScanCtasPerSm;  // persistent: every CTA resident
   if (blocks > cap) blocks = cap;
   const unsigned g = static_cast<unsigned>(blocks);
 #define MLC_SCAN(KT)                                                                         \
