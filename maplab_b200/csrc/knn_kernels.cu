@@ -4,8 +4,8 @@
 //                               cells' inverted lists, squared L2 in the canonical fp32 order,
 //                               top-k by (distance, index) (imilib/inverted-multi-index.h:100-161,
 //                               inverted-multi-index-common.h:54-72)
-//   index build                — cell assignment (2a with one word), radix sort by cell, blocked
-//                               SoA inverted lists (imilib/inverted-multi-index.h:77-94)
+//   index build                — cell assignment (2a with one word), radix sort by cell, padded
+//                               16-byte aligned entries (imilib/inverted-multi-index.h:77-94)
 #include <cub/cub.cuh>
 
 #include "device_index.h"
@@ -66,63 +66,92 @@ __device__ __forceinline__ float SquaredDistanceCanonical(const float (&a)[DIM],
   }
 }
 
-// One warp per query descriptor, persistent warps. The (<= 16) visited cells' lists are flattened
-// into one entry range and dealt to the lanes 64 at a time (two independent 32-entry windows per
-// trip, so 2 x (DIM + 1) loads per lane are in flight); inside a block of a list the layout is
-// [dim+1][block size] words, so the 32 lanes of a full block read 128 contiguous bytes per
-// dimension. Query metadata is software-pipelined two deep: while query i is scanned, the cell
-// table entries of query i+1 and the visit list of query i+2 are already in flight, which hides
-// the dependent chain visit list -> cell table -> list entries.
-constexpr int kScanThreads = 256;
-constexpr int kScanCtasPerSm = 3;
-constexpr uint32_t kFull = 0xffffffffu;
-
-struct ScanEntry {
-  uint64_t key;
-};
-
+// Entry layout: one inverted-list entry is kWpe<DIM> 32-bit words, 16-byte aligned:
+// DIM fp32 coordinates, the global descriptor index, zero padding (12 words = 48 B at DIM 10; the
+// ALGORITHMIC size stays 4 * (DIM + 1) = 44 B). A lane fetches its entry with kWpe / 4 LDG.128.
 template <int DIM>
-__device__ __forceinline__ void LoadWindow(const uint32_t* __restrict__ lists, const uint4* seg,
+constexpr int kWpe = (DIM + 1 + 3) & ~3;
+
+// One warp per query descriptor, persistent warps. The (<= 16) visited cells' lists are flattened
+// into one entry range and dealt to the lanes 64 at a time (two 32-entry windows per trip, all
+// their loads issued before the first use). Top-k selection is warp-distributed: lane r holds the
+// r-th smallest (distance bits, index) key seen so far. The first trip fills it with k rounds of
+// warp arg-min over the (<= 64) fresh keys; later trips only touch it for keys below the current
+// k-th key (ballot), inserted one by one with a shift through the lanes. Query metadata is
+// software-pipelined two deep: while query i is scanned, the cell table entries of query i+1 and
+// the visit list of query i+2 are already in flight, which hides the dependent chain
+// visit list -> cell table -> list entries.
+constexpr int kScanThreads = 256;
+constexpr int kScanCtasPerSm = 4;
+constexpr uint32_t kFull = 0xffffffffu;
+constexpr uint32_t kInfBits = 0x7f800000u;
+constexpr uint32_t kNoIndex = 0xFFFFFFFFu;
+
+// Issue the loads of window [base, base + 32): lane l takes flattened entry base + l.
+template <int DIM>
+__device__ __forceinline__ bool LoadWindow(const uint4* __restrict__ lists, const uint4* seg,
                                            uint32_t base, uint32_t total, uint32_t len,
                                            uint32_t excl, int lane, uint32_t lanemask_le,
-                                           float (&sv)[DIM], uint32_t* id, bool* valid) {
+                                           uint4 (&v)[kWpe<DIM> / 4]) {
   // non-empty cells whose first entry falls into this window set bit (first entry - base)
   const uint32_t rel = excl - base;
   const uint32_t heads = __reduce_or_sync(kFull, (len > 0 && rel < 32u) ? (1u << rel) : 0u);
   const uint32_t before = __popc(__ballot_sync(kFull, len > 0 && excl < base));
   const uint32_t e = base + lane;
-  *valid = e < total;
-  if (*valid) {
+  const bool valid = e < total;
+  if (valid) {
     const uint4 s = seg[before + __popc(heads & lanemask_le) - 1];  // {excl, start16, len}
-    const uint32_t within = e - s.x;            // entry number inside its cell
-    const uint32_t blk = within >> 5;           // block of 32 entries
-    const uint32_t bs = min(32u, s.z - (blk << 5));
-    const uint32_t* w = lists + (static_cast<size_t>(s.y) << 2) +
-                        static_cast<size_t>(blk) * ((DIM + 1) * 32) + (within & 31u);
+    const uint4* p = lists + s.y + static_cast<size_t>(e - s.x) * (kWpe<DIM> / 4);
 #pragma unroll
-    for (int d = 0; d < DIM; ++d) sv[d] = __uint_as_float(__ldg(w + d * bs));
-    *id = __ldg(w + DIM * bs);
+    for (int j = 0; j < kWpe<DIM> / 4; ++j) v[j] = __ldg(p + j);
+  }
+  return valid;
+}
+
+// (distance bits << 32 | index) of a loaded entry; NaN distances never enter a result.
+template <int DIM>
+__device__ __forceinline__ uint64_t EntryKey(const uint4 (&v)[kWpe<DIM> / 4], const float (&qv)[DIM],
+                                             bool valid) {
+  uint32_t w[kWpe<DIM>];
+#pragma unroll
+  for (int j = 0; j < kWpe<DIM> / 4; ++j) {
+    w[4 * j + 0] = v[j].x;
+    w[4 * j + 1] = v[j].y;
+    w[4 * j + 2] = v[j].z;
+    w[4 * j + 3] = v[j].w;
+  }
+  float sv[DIM];
+#pragma unroll
+  for (int d = 0; d < DIM; ++d) sv[d] = __uint_as_float(w[d]);
+  const uint32_t bits = __float_as_uint(SquaredDistanceCanonical<DIM>(sv, qv));
+  if (!valid || bits > kInfBits) return kEmptyKey;
+  return (static_cast<uint64_t>(bits) << 32) | w[DIM];
+}
+
+__device__ __forceinline__ uint64_t ShflKey(uint64_t key, int src) {
+  const uint32_t hi = __shfl_sync(kFull, static_cast<uint32_t>(key >> 32), src);
+  const uint32_t lo = __shfl_sync(kFull, static_cast<uint32_t>(key), src);
+  return (static_cast<uint64_t>(hi) << 32) | lo;
+}
+
+// Insert the keys of the lanes named in `mask` (ascending lane order) into the warp-distributed
+// sorted list `held` (lane r = r-th smallest). Warp-uniform control flow.
+__device__ __forceinline__ void InsertCandidates(uint32_t mask, uint64_t key, uint64_t& held, int lane) {
+  while (mask) {
+    const int src = __ffs(mask) - 1;
+    mask &= mask - 1;
+    const uint64_t c = ShflKey(key, src);
+    const uint32_t p_hi = __shfl_up_sync(kFull, static_cast<uint32_t>(held >> 32), 1);
+    const uint32_t p_lo = __shfl_up_sync(kFull, static_cast<uint32_t>(held), 1);
+    const uint64_t prev = (static_cast<uint64_t>(p_hi) << 32) | p_lo;
+    if (c < held) held = (lane > 0 && c < prev) ? prev : c;
   }
 }
 
-template <int KT>
-__device__ __forceinline__ void InsertKey(uint64_t (&best)[KT], uint64_t key) {
-  if (key < best[KT - 1]) {
-#pragma unroll
-    for (int i = 0; i < KT; ++i) {
-      const bool lt = key < best[i];
-      const uint64_t lo = lt ? key : best[i];
-      const uint64_t hi = lt ? best[i] : key;
-      best[i] = lo;
-      key = hi;
-    }
-  }
-}
-
-template <int DIM, int KT>
+template <int DIM>
 __global__ void __launch_bounds__(kScanThreads, kScanCtasPerSm)
 imi_scan_kernel(const float* __restrict__ q, int64_t n_q, const int32_t* __restrict__ cells, int nw,
-                const uint2* __restrict__ cell_info, const uint32_t* __restrict__ lists, int k,
+                const uint2* __restrict__ cell_info, const uint4* __restrict__ lists, int k,
                 int32_t* __restrict__ out_idx, float* __restrict__ out_dist) {
   __shared__ uint4 seg_s[kScanThreads / 32][kMaxWords];
   const int lane = threadIdx.x & 31;
@@ -176,59 +205,42 @@ imi_scan_kernel(const float* __restrict__ q, int64_t n_q, const int32_t* __restr
     for (int d = 0; d < DIM; ++d) qv[d] = __shfl_sync(kFull, q_l, d);
     __syncwarp();
 
-    uint64_t best[KT];
-#pragma unroll
-    for (int i = 0; i < KT; ++i) best[i] = kEmptyKey;
-
+    uint64_t held = kEmptyKey;  // lane r: r-th smallest key so far
     for (uint32_t base = 0; base < total; base += 64) {
-      float sa[DIM], sb[DIM];
-      uint32_t ida = 0xFFFFFFFFu, idb = 0xFFFFFFFFu;
-      bool va = false, vb = false;
-      LoadWindow<DIM>(lists, seg, base, total, len, excl, lane, lanemask_le, sa, &ida, &va);
-      const bool second = base + 32 < total;  // warp-uniform
-      if (second)
-        LoadWindow<DIM>(lists, seg, base + 32, total, len, excl, lane, lanemask_le, sb, &idb, &vb);
-      uint64_t ka = kEmptyKey, kb = kEmptyKey;
-      if (va)
-        ka = (static_cast<uint64_t>(__float_as_uint(SquaredDistanceCanonical<DIM>(sa, qv))) << 32) | ida;
-      if (vb)
-        kb = (static_cast<uint64_t>(__float_as_uint(SquaredDistanceCanonical<DIM>(sb, qv))) << 32) | idb;
+      uint4 va[kWpe<DIM> / 4], vb[kWpe<DIM> / 4];
+      const bool in_a = LoadWindow<DIM>(lists, seg, base, total, len, excl, lane, lanemask_le, va);
+      bool in_b = false;
+      if (base + 32 < total)  // warp-uniform
+        in_b = LoadWindow<DIM>(lists, seg, base + 32, total, len, excl, lane, lanemask_le, vb);
+      uint64_t ka = EntryKey<DIM>(va, qv, in_a);
+      uint64_t kb = in_b ? EntryKey<DIM>(vb, qv, true) : kEmptyKey;
       if (base == 0) {
-        // first trip: the per-lane list is empty, so the two keys only need ordering
-        if constexpr (KT >= 2) {
-          best[0] = ka < kb ? ka : kb;
-          best[1] = ka < kb ? kb : ka;
-        } else {
-          best[0] = ka < kb ? ka : kb;
+        // k rounds of warp arg-min over the fresh keys; lane r keeps the r-th
+        for (int r = 0; r < k; ++r) {
+          const uint32_t a_hi = static_cast<uint32_t>(ka >> 32), a_lo = static_cast<uint32_t>(ka);
+          const uint32_t b_hi = static_cast<uint32_t>(kb >> 32), b_lo = static_cast<uint32_t>(kb);
+          const uint32_t m_hi = __reduce_min_sync(kFull, min(a_hi, b_hi));
+          const uint32_t ca = (a_hi == m_hi) ? a_lo : kNoIndex;
+          const uint32_t cb = (b_hi == m_hi) ? b_lo : kNoIndex;
+          const uint32_t m_lo = __reduce_min_sync(kFull, min(ca, cb));
+          if (m_lo == kNoIndex) break;  // nothing left (warp-uniform)
+          if (lane == r) held = (static_cast<uint64_t>(m_hi) << 32) | m_lo;
+          if (ca == m_lo) ka = kEmptyKey;
+          if (cb == m_lo) kb = kEmptyKey;
         }
       } else {
-        InsertKey<KT>(best, ka);
-        if (second) InsertKey<KT>(best, kb);
+        const uint64_t kth = ShflKey(held, k - 1);
+        const uint32_t ma = __ballot_sync(kFull, ka < kth);
+        const uint32_t mb = __ballot_sync(kFull, kb < kth);
+        InsertCandidates(ma, ka, held, lane);
+        InsertCandidates(mb, kb, held, lane);
       }
     }
     __syncwarp();  // every lane is done with seg before the next query overwrites it
 
-    // ---- k rounds of warp arg-min over the lanes' heads; lane r keeps the r-th result
-    uint32_t res_d = 0x7f800000u, res_i = 0xFFFFFFFFu;
-    for (int r = 0; r < k; ++r) {
-      const uint32_t hd = static_cast<uint32_t>(best[0] >> 32);
-      const uint32_t id = static_cast<uint32_t>(best[0]);
-      const uint32_t hi_min = __reduce_min_sync(kFull, hd);
-      const uint32_t lo_min = __reduce_min_sync(kFull, (hd == hi_min) ? id : 0xFFFFFFFFu);
-      if (lane == r) {
-        res_d = hi_min;
-        res_i = lo_min;
-      }
-      if (hi_min == 0x7f800000u && lo_min == 0xFFFFFFFFu) break;  // nothing left (warp-uniform)
-      if (hd == hi_min && id == lo_min) {
-#pragma unroll
-        for (int i = 0; i + 1 < KT; ++i) best[i] = best[i + 1];
-        best[KT - 1] = kEmptyKey;
-      }
-    }
     if (lane < k) {  // missing neighbours: (+inf, -1), trailing
-      out_idx[qi * k + lane] = static_cast<int32_t>(res_i);
-      out_dist[qi * k + lane] = __uint_as_float(res_d);
+      out_idx[qi * k + lane] = static_cast<int32_t>(static_cast<uint32_t>(held));
+      out_dist[qi * k + lane] = __uint_as_float(static_cast<uint32_t>(held >> 32));
     }
 
     // ---- rotate the pipeline
@@ -246,18 +258,8 @@ cudaError_t LaunchScanDim(const float* q, int64_t n_q, const int32_t* cells, int
   int64_t blocks = (n_q * 32 + threads - 1) / threads;
   const int64_t cap = static_cast<int64_t>(sm_count) * kScanCtasPerSm;  // persistent: every CTA resident
   if (blocks > cap) blocks = cap;
-  const unsigned g = static_cast<unsigned>(blocks);
-#define MLC_SCAN(KT)                                                                         \
-  imi_scan_kernel<DIM, KT><<<g, threads, 0, stream>>>(q, n_q, cells, nw, cell_info, lists, k, \
-                                                      out_idx, out_dist)
-  if (k <= 1) MLC_SCAN(1);
-  else if (k <= 2) MLC_SCAN(2);
-  else if (k <= 4) MLC_SCAN(4);
-  else if (k <= 6) MLC_SCAN(6);
-  else if (k <= 8) MLC_SCAN(8);
-  else if (k <= 10) MLC_SCAN(10);
-  else MLC_SCAN(16);
-#undef MLC_SCAN
+  imi_scan_kernel<DIM><<<static_cast<unsigned>(blocks), threads, 0, stream>>>(
+      q, n_q, cells, nw, cell_info, reinterpret_cast<const uint4*>(lists), k, out_idx, out_dist);
   CountLaunch();
   return cudaGetLastError();
 }
@@ -410,7 +412,7 @@ __global__ void cell_info_kernel(uint32_t num_cells, const uint32_t* __restrict_
   if (c >= num_cells) return;
   info[c] = make_uint2(start16[c], len[c]);
 }
-// Scatter descriptor i into block-SoA position of its cell.
+// Scatter descriptor i into its entry slot (16-byte aligned, padded) of its cell.
 __global__ void fill_lists_kernel(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals,
                                   int64_t n, uint32_t num_cells, const uint32_t* __restrict__ first,
                                   const uint2* __restrict__ info, const float* __restrict__ desc,
@@ -421,14 +423,13 @@ __global__ void fill_lists_kernel(const uint32_t* __restrict__ keys, const uint3
   if (c >= num_cells) return;
   const uint32_t within = static_cast<uint32_t>(i) - first[c];
   const uint2 ci = info[c];
-  const uint32_t blk = within >> 5;
-  const uint32_t bs = min(32u, ci.y - (blk << 5));
-  uint32_t* w = lists + (static_cast<size_t>(ci.x) << 2) + static_cast<size_t>(blk) * ((dim + 1) * 32) +
-                (within & 31u);
+  const int wpe = (dim + 1 + 3) & ~3;
+  uint32_t* w = lists + (static_cast<size_t>(ci.x) << 2) + static_cast<size_t>(within) * wpe;
   const uint32_t id = vals[i];
   const float* src = desc + static_cast<size_t>(id) * dim;
-  for (int d = 0; d < dim; ++d) w[d * bs] = __float_as_uint(src[d]);
-  w[dim * bs] = id;
+  for (int d = 0; d < dim; ++d) w[d] = __float_as_uint(src[d]);
+  w[dim] = id;
+  for (int d = dim + 1; d < wpe; ++d) w[d] = 0u;
 }
 
 }  // namespace
@@ -505,7 +506,7 @@ cudaError_t BuildImiLists(const int32_t* d_cells, const float* d_desc, int64_t n
   MLC_TRY_C(cudaMemsetAsync(len, 0, 4 * static_cast<size_t>(num_cells), stream));
   cell_bounds_kernel<<<nb, 256, 0, stream>>>(keys_s, n, num_cells, first, len);
   CountLaunch();
-  cell_sizes_kernel<<<cb, 256, 0, stream>>>(num_cells, first, len, dim + 1, size16);
+  cell_sizes_kernel<<<cb, 256, 0, stream>>>(num_cells, first, len, (dim + 1 + 3) & ~3, size16);
   CountLaunch();
   MLC_TRY_C(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, size16, start16,
                                           static_cast<int>(num_cells), stream));
