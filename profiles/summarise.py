@@ -56,14 +56,19 @@ def main():
     c_line, c_src = h.index("Line No"), h.index("Source")
     c_inst, c_smp = h.index("Instructions Executed"), h.index("# Samples")
     c_wf = h.index("L1 Tag Requests Global") if "L1 Tag Requests Global" in h else None
-    body = [r for r in tab[1:] if len(r) > c_inst and r[c_line] != "" and r[c_inst] not in ("", "0")]
-    tot_i = sum(int(r[c_inst]) for r in body) or 1
-    tot_s = sum(int(r[c_smp] or 0) for r in body) or 1
+    def num(x):
+        try:
+            return int(x)
+        except ValueError:
+            return 0
+    body = [r for r in tab[1:] if len(r) > c_inst and r[c_line] != "" and num(r[c_inst]) > 0]
+    tot_i = sum(num(r[c_inst]) for r in body) or 1
+    tot_s = sum(num(r[c_smp]) for r in body) or 1
     print(f"\n## per source line (first launch): instructions executed {tot_i}, stall samples {tot_s}")
     print(f"{'line':>5s} {'inst%':>6s} {'smp%':>6s} {'L1 tag req':>11s}  source")
-    body.sort(key=lambda r: -int(r[c_inst]))
+    body.sort(key=lambda r: -num(r[c_inst]))
     for r in body[:45]:
-        print(f"{r[c_line]:>5s} {100 * int(r[c_inst]) / tot_i:6.2f} {100 * int(r[c_smp] or 0) / tot_s:6.2f} "
+        print(f"{r[c_line]:>5s} {100 * num(r[c_inst]) / tot_i:6.2f} {100 * num(r[c_smp]) / tot_s:6.2f} "
               f"{(r[c_wf] if c_wf is not None else ''):>11s}  {r[c_src].strip()[:100]}")
 
 
