@@ -165,6 +165,14 @@ int mlc_merge_topk_device(mlc_detector* d, const int32_t* d_idx_lists, const flo
                           int num_lists, int64_t n_q, int k, int32_t* d_idx, float* d_dist,
                           void* stream);
 
+/* scoring::computeAccumulationScore / computeProbabilisticScore
+ * (MBL/include/matching-based-loopclosure/scoring.h:38-59, :92-187) over an explicit id list, on the
+ * device: scores[i] for an id with num_matches[i] votes that owns num_descriptors[i] of the
+ * num_db_descriptors database descriptors (scoring: 0 accumulation, 1 probabilistic; ids are scored
+ * in the order given, which matters for the reference's in-loop +inf patch). An empty database or
+ * id list yields no scores. mlc_find_batch applies the function selected in mlc_settings.scoring. */
+int mlc_score(mlc_detector* d, int scoring, const uint64_t* num_matches, const uint64_t* num_descriptors,
+              int n, int64_t num_db_descriptors, float* scores);
 /* Algorithmic bytes the last mlc_knn* call scanned: sum over (query, visited cell present in
  * this shard) of list_length * bytes_per_entry (44 imi / 9 imipq) — SURVEY.md §8d. */
 int mlc_last_scan_stats(mlc_detector* d, uint64_t* algorithmic_bytes, uint64_t* entries_scanned,

@@ -20,6 +20,7 @@ EXPORTS = [
     "mlc_knn_device", "mlc_coarse_cells", "mlc_merge_topk_device", "mlc_last_scan_stats",
     "mlc_find_batch", "mlc_find_batch_bits", "mlc_find_from_knn_device", "mlc_pnp_ransac_batch",
     "mlc_coarse_device", "mlc_scan_device", "mlc_last_stage_ms", "mlc_set_landmark_positions", "mlc_query_batch", "mlc_query_batch_device", "mlc_query_from_knn_device",
+    "mlc_score",
 ]
 
 
@@ -232,6 +233,16 @@ class Detector:
         ms = (C.c_double * 5)()
         _check(lib().mlc_last_stage_ms(self._h, ms))
         return dict(zip(("project", "coarse", "scan", "vote_cluster", "ransac"), [float(x) for x in ms]))
+
+    def score(self, num_matches, num_descriptors, num_db, probabilistic):
+        """scoring::compute*Score on the device (scoring.h:38-59, :92-187)."""
+        m = np.ascontiguousarray(num_matches, np.uint64)
+        d = np.ascontiguousarray(num_descriptors, np.uint64)
+        out = np.zeros(len(m), np.float32)
+        _check(lib().mlc_score(self._h, 1 if probabilistic else 0, m.ctypes.data_as(C.c_void_p),
+                               d.ctypes.data_as(C.c_void_p), len(m), C.c_int64(num_db),
+                               out.ctypes.data_as(C.c_void_p)))
+        return out if num_db > 0 else out[:0]
 
     def merge_topk_device(self, idx_lists_ptr, dist_lists_ptr, num_lists, n, k, idx_ptr, dist_ptr,
                           stream=0):

@@ -155,6 +155,12 @@ int mlc_merge_topk_device(mlc_detector* d, const int32_t* d_idx_lists, const flo
              ? 0
              : Fail(err);
 }
+int mlc_score(mlc_detector* d, int scoring, const uint64_t* num_matches, const uint64_t* num_descriptors,
+              int n, int64_t num_db_descriptors, float* scores) {
+  MLC_REQUIRE(d && (n == 0 || (num_matches && num_descriptors && scores)), "mlc_score: null argument");
+  std::string err;
+  return d->impl.Score(scoring, num_matches, num_descriptors, n, num_db_descriptors, scores, &err) ? 0 : Fail(err);
+}
 int mlc_last_scan_stats(mlc_detector* d, uint64_t* algorithmic_bytes, uint64_t* entries_scanned,
                         double* scan_kernel_ms) {
   MLC_REQUIRE(d && algorithmic_bytes && entries_scanned && scan_kernel_ms, "null argument");

@@ -35,6 +35,8 @@ struct CovisArgs {
   double min_time_ns;
   unsigned long long min_verify_matches_num;
   float fraction_best_scores;
+  int scoring;                   // 0 accumulation, 1 probabilistic (scoring.h)
+  long long num_db_descriptors;  // whole database (all shards)
   mlc_match* scratch;  // grid * (4096 | 8192) records
   mlc_match* out_matches;
   int* out_counts;
@@ -42,6 +44,8 @@ struct CovisArgs {
 
 size_t CovisScratchMatches(int max_matches, int grid);
 cudaError_t LaunchCovis(const CovisArgs& a, int max_matches, int grid, cudaStream_t stream);
+cudaError_t LaunchScore(const unsigned long long* votes, const unsigned long long* num_desc, int n,
+                        long long num_db, int scoring, float* out, cudaStream_t stream);
 cudaError_t LaunchCompactMatches(const mlc_match* in, const CovisItem* items, const int* counts,
                                  const long long* dst_offsets, int num_items, mlc_match* out,
                                  cudaStream_t stream);

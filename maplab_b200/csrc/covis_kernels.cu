@@ -6,7 +6,8 @@
 // Reference: matching-based-loopclosure/src/matching-based-engine.cc:101-123 (neighbour walk with
 // `break`), :170-215 (getMatchForDescriptorIndex), :147-165 (vertex pass);
 // include/matching-based-loopclosure/matching-based-engine-inl.h:45-183 (doCovisibilityFiltering),
-// :219-254 (computeRelevantIdsForFiltering); scoring.h:38-59 (accumulation score).
+// :219-254 (computeRelevantIdsForFiltering); scoring.h:38-59 (accumulation score), :92-187
+// (probabilistic score).
 // Canonical orders where the reference depends on hash-map iteration (oracle/engine.cc):
 // top-fraction ties by keyframe number, component ties by smallest member, duplicates keep the
 // smallest database descriptor, output sorted by (query frame, keypoint, database descriptor).
@@ -79,6 +80,33 @@ __device__ __forceinline__ int FlagScan(int n, FlagFn flag, OutFn out,
   }
   __syncthreads();
   return total;
+}
+
+// boost::math::pdf(binomial(n, p), k) = C(n,k) p^k (1-p)^(n-k) (special cases first), fp64.
+__device__ double BinomialPdf(double n, double p, double k) {
+  if (p == 0) return (k == 0) ? 1.0 : 0.0;
+  if (p == 1) return (k == n) ? 1.0 : 0.0;
+  if (n == 0) return 1.0;
+  if (k == 0) return pow(1 - p, n);
+  if (k == n) return pow(p, k);
+  const double lg = lgamma(n + 1) - lgamma(k + 1) - lgamma(n - k + 1) + k * log(p) + (n - k) * log1p(-p);
+  return exp(lg);
+}
+
+// Score of one candidate id (scoring.h:139-178): -log10 of the probability that `votes` of the
+// `total` votes fall on an id holding `num_desc` of the `num_db` database descriptors by chance;
+// 0 below the expected count; FLT_MAX (+ *underflow) when the pdf underflows to 0.
+__device__ float ProbabilisticScore(unsigned votes, unsigned total, unsigned num_desc, long long num_db,
+                                    bool* underflow) {
+  const double p = static_cast<double>(num_desc) / static_cast<double>(num_db);
+  const unsigned long long lower_median = static_cast<unsigned long long>(static_cast<double>(total) * p);
+  if (!(votes > lower_median)) return 0.f;
+  const double prob = BinomialPdf(static_cast<double>(total), p, static_cast<double>(votes));
+  if (prob == 0.0) {
+    *underflow = true;
+    return 3.402823466e+38f;
+  }
+  return static_cast<float>(-log10(prob));
 }
 
 template <int MAXM, int THREADS>
@@ -176,11 +204,47 @@ __global__ void __launch_bounds__(THREADS) covis_kernel(CovisArgs a) {
         if (want < 4) want = 4;
         n_eval = want < Cn ? want : Cn;
         const int pc = NextPow2(Cn);
+        unsigned* prob_score = reinterpret_cast<unsigned*>(s.a5);  // a5/a6 are free until stage C
+        if (a.scoring == 1) {
+          // computeProbabilisticScore (scoring.h:92-187), candidates in ascending keyframe number
+          // (the canonical replacement of the hash-map iteration order, oracle/engine.cc)
+          int underflow = 0;
+          for (int b = tid; b < Cn; b += THREADS) {
+            const int kfn = rec[s.keys[s.a2[b]] & SLOT_MASK].db_keyframe;
+            bool uf = false;
+            prob_score[b] = __float_as_uint(ProbabilisticScore(
+                static_cast<unsigned>(s.a2[b + 1] - s.a2[b]), static_cast<unsigned>(R),
+                static_cast<unsigned>(a.kf_meta[kfn].num_descriptors), a.num_db_descriptors, &uf));
+            s.f2[b] = uf ? 1 : 0;
+            underflow |= uf ? 1 : 0;
+          }
+          if (__syncthreads_or(underflow)) {
+            // quirk 7 (scoring.h:180-184): the +inf patch runs inside the per-id loop, so the id
+            // whose pdf underflowed with the most votes so far becomes +inf only if the NEXT id
+            // does not take that role over; the last id is never patched.
+            if (tid == 0) {
+              unsigned best = 0;
+              int holder = -1;
+              for (int b = 0; b < Cn; ++b) {
+                const unsigned m = static_cast<unsigned>(s.a2[b + 1] - s.a2[b]);
+                const bool takes_over = s.f2[b] && m > best;
+                if (takes_over) {
+                  best = m;
+                  holder = b;
+                } else if (holder >= 0) {
+                  prob_score[holder] = 0x7f800000u;
+                }
+              }
+            }
+            __syncthreads();
+          }
+        }
         for (int b = tid; b < pc; b += THREADS) {
           unsigned long long key = ~0ull;
           if (b < Cn) {
-            const float score = static_cast<float>(s.a2[b + 1] - s.a2[b]);  // accumulation score
-            const unsigned ord = __float_as_uint(score);                    // scores are >= 0
+            float score = static_cast<float>(s.a2[b + 1] - s.a2[b]);  // accumulation score
+            if (a.scoring == 1) score = __uint_as_float(prob_score[b]);
+            const unsigned ord = __float_as_uint(score);              // scores are >= 0
             key = (static_cast<unsigned long long>(0xFFFFFFFFu - ord) << SLOT_BITS) | static_cast<unsigned>(b);
           }
           s.keys[b] = key;
@@ -375,6 +439,44 @@ __global__ void __launch_bounds__(THREADS) covis_kernel(CovisArgs a) {
   }
 }
 
+// scoring::compute{Accumulation,Probabilistic}Score for an explicit id list (mlc_score): the same
+// device functions the covisibility kernel uses, ids in the order given.
+__global__ void score_kernel(const unsigned long long* __restrict__ votes,
+                             const unsigned long long* __restrict__ num_desc, int n, long long num_db,
+                             int scoring, float* __restrict__ out) {
+  __shared__ unsigned long long total_s;
+  if (threadIdx.x == 0) {
+    unsigned long long t = 0;
+    for (int i = 0; i < n; ++i) t += votes[i];
+    total_s = t;
+  }
+  __syncthreads();
+  const unsigned total = static_cast<unsigned>(total_s);
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    float score = static_cast<float>(votes[i]);
+    if (scoring == 1) {
+      bool uf = false;
+      score = ProbabilisticScore(static_cast<unsigned>(votes[i]), total, static_cast<unsigned>(num_desc[i]),
+                                 num_db, &uf);
+    }
+    out[i] = score;
+  }
+  __syncthreads();
+  if (scoring == 1 && threadIdx.x == 0) {
+    unsigned long long best = 0;
+    int holder = -1;
+    for (int i = 0; i < n; ++i) {
+      const bool takes_over = out[i] == 3.402823466e+38f && votes[i] > best;
+      if (takes_over) {
+        best = votes[i];
+        holder = i;
+      } else if (holder >= 0) {
+        out[holder] = __int_as_float(0x7f800000);
+      }
+    }
+  }
+}
+
 __global__ void compact_matches_kernel(const mlc_match* __restrict__ in, const CovisItem* items,
                                        const int* __restrict__ counts,
                                        const long long* __restrict__ dst_offsets, int num_items,
@@ -412,6 +514,14 @@ cudaError_t LaunchCovis(const CovisArgs& a, int max_matches, int grid, cudaStrea
     if (e != cudaSuccess) return e;
     fn<<<grid, 1024, sizeof(CovisSmem<8192>), stream>>>(a);
   }
+  CountLaunch();
+  return cudaGetLastError();
+}
+
+cudaError_t LaunchScore(const unsigned long long* votes, const unsigned long long* num_desc, int n,
+                        long long num_db, int scoring, float* out, cudaStream_t stream) {
+  if (n <= 0) return cudaSuccess;
+  score_kernel<<<1, 256, 0, stream>>>(votes, num_desc, n, num_db, scoring, out);
   CountLaunch();
   return cudaGetLastError();
 }

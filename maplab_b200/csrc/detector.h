@@ -79,6 +79,9 @@ class Detector {
                        int64_t n_q, int k, int32_t* d_idx, float* d_dist, cudaStream_t stream,
                        std::string* err);
   bool LastScanStats(uint64_t* bytes, uint64_t* entries, double* ms, std::string* err);
+  // scoring::compute*Score over an explicit id list, on the device (scoring.h:38-59, :92-187).
+  bool Score(int scoring, const uint64_t* votes, const uint64_t* num_desc, int n, int64_t num_db,
+             float* scores, std::string* err);
   bool FindBatch(const mlc_frame* frames, int64_t num_frames, const float* proj,
                  const uint8_t* bits, int bytes_per_desc, mlc_match* matches, int64_t capacity,
                  int64_t* match_offsets, int64_t* num_vertices, int64_t* num_matches,

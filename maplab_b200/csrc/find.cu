@@ -85,8 +85,8 @@ bool Detector::FindOnDevice(const mlc_frame* frames, int64_t num_frames, const i
                             const float* d_dist, int k, std::vector<long long>* fin_off_out,
                             std::string* err) {
   fin_off_out->assign(1, 0);
-  if (s_.scoring != 0) {
-    *err = "scoring function not built: only 'accumulation' (0) is available on the device";
+  if (s_.scoring != 0 && s_.scoring != 1) {
+    *err = "unknown scoring function (0 accumulation, 1 probabilistic)";
     return false;
   }
   if (!EnsureIndex(err)) return false;
@@ -174,6 +174,8 @@ bool Detector::FindOnDevice(const mlc_frame* frames, int64_t num_frames, const i
   a.min_time_ns = s_.min_image_time_seconds * 1e9;  // kSecondsToNanoSeconds
   a.min_verify_matches_num = s_.min_verify_matches_num;
   a.fraction_best_scores = s_.fraction_best_scores;
+  a.scoring = s_.scoring;
+  a.num_db_descriptors = NumDescriptors();
   a.scratch = b_scr.as<mlc_match>();
   a.out_matches = b_out.as<mlc_match>();
   a.out_counts = b_cnt.as<int>();
@@ -403,6 +405,31 @@ bool Detector::QueryFromKnn(const mlc_frame* frames, int64_t num_frames, const i
                         reinterpret_cast<const double*>(corr + c_kp), reinterpret_cast<const int32_t*>(corr + c_ci),
                         reinterpret_cast<const int32_t*>(corr + c_ki), reinterpret_cast<const double*>(corr + c_lm),
                         results, inlier_flags, err);
+}
+
+bool Detector::Score(int scoring, const uint64_t* votes, const uint64_t* num_desc, int n, int64_t num_db,
+                     float* scores, std::string* err) {
+  std::lock_guard<std::recursive_mutex> lock(mu_);
+  if (n <= 0 || num_db <= 0) return true;  // scoring.h:108-116: empty database / no ids -> no scores
+  if (scoring != 0 && scoring != 1) {
+    *err = "unknown scoring function (0 accumulation, 1 probabilistic)";
+    return false;
+  }
+  DevBuf &b_in = d_covis_[6], &b_out = d_covis_[7];
+  if (!Cuda(b_in.Reserve(sizeof(uint64_t) * 2 * n), "alloc", err) ||
+      !Cuda(b_out.Reserve(sizeof(float) * n), "alloc", err))
+    return false;
+  uint64_t* d_votes = b_in.as<uint64_t>();
+  if (!Cuda(cudaMemcpyAsync(d_votes, votes, sizeof(uint64_t) * n, cudaMemcpyHostToDevice, stream_), "H2D", err) ||
+      !Cuda(cudaMemcpyAsync(d_votes + n, num_desc, sizeof(uint64_t) * n, cudaMemcpyHostToDevice, stream_), "H2D", err))
+    return false;
+  if (!Cuda(LaunchScore(reinterpret_cast<const unsigned long long*>(d_votes),
+                        reinterpret_cast<const unsigned long long*>(d_votes + n), n, num_db, scoring,
+                        b_out.as<float>(), stream_), "score kernel", err))
+    return false;
+  if (!Cuda(cudaMemcpyAsync(scores, b_out.p, sizeof(float) * n, cudaMemcpyDeviceToHost, stream_), "D2H", err))
+    return false;
+  return Cuda(cudaStreamSynchronize(stream_), "score", err);
 }
 
 }  // namespace mlc

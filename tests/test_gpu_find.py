@@ -62,6 +62,9 @@ def _check_batch(det, ora, qframes, qproj):
     dict(num_nearest_neighbors=8, min_verify_matches_num=3, fraction_best_scores=0.5),
     dict(num_nearest_neighbors=4, min_verify_matches_num=40),
     dict(num_nearest_neighbors=10, fraction_best_scores=0.01),  # floor(size*fraction) < 4 -> 4
+    dict(scoring=1),                                       # probabilistic score (scoring.h:92-187)
+    dict(scoring=1, num_nearest_neighbors=8, fraction_best_scores=0.5, min_verify_matches_num=3),
+    dict(scoring=1, num_nearest_neighbors=10, fraction_best_scores=0.1),
 ])
 def test_find_matches_oracle_single_camera(kw):
     m, blob, _, q = small_world(num_queries=12)
@@ -132,3 +135,44 @@ def test_reference_api_mirror_and_preconditions():
         ld.Insert(ProjectedImage(0, 1, 0, 0, qp, np.arange(3)))
     ld.Clear()
     assert ld.NumEntries() == 0 and len(ld.Find([img])) == 0
+
+
+def _any_detector():
+    m, blob, _, _ = small_world(num_queries=12)
+    return capi.Detector(blob, capi.default_settings())
+
+
+def test_reference_golden_scoring_on_device():
+    # test_scoring.cc:94-140 through the device scoring functions (mlc_score)
+    import json
+    import os
+    t = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "reference_goldens.json")))["scoring"]
+    det = _any_detector()
+    acc = det.score(t["num_matches"], t["num_descriptors"], t["num_db"], False)
+    assert acc.tolist() == t["expected_accumulation"]
+    prob = det.score(t["num_matches"], t["num_descriptors"], t["num_db"], True)
+    assert np.allclose(prob, t["expected_probabilistic"], atol=t["tolerance"])
+    assert len(det.score([], [], 50, True)) == 0
+    assert len(det.score([1], [1], 0, True)) == 0  # empty database: no scores (scoring.h:108-112)
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2, 3])
+def test_probabilistic_score_matches_oracle(seed):
+    # random vote tables incl. pdf underflow (FLT_MAX / the in-loop +inf patch, quirk 7):
+    # zeros, FLT_MAX and +inf at identical positions, the rest within 1e-5 relative
+    rng = np.random.default_rng(seed)
+    n = int(rng.integers(1, 400))
+    votes = rng.integers(1, 60, n).astype(np.uint64)
+    num_desc = rng.integers(50, 600, n).astype(np.uint64)
+    for j in rng.integers(0, n, 6):  # underflowing ids with rising / falling / equal vote counts
+        votes[j] = int(rng.choice([900, 1200, 1200, 1500, 2500]))
+    num_db = int(num_desc.sum()) * [1, 3, 50, 2000][seed]
+    det = _any_detector()
+    got = det.score(votes, num_desc, num_db, True)
+    exp = po.score(votes.tolist(), num_desc.tolist(), num_db, True)
+    special = (exp == 0) | np.isinf(exp) | (exp == np.finfo(np.float32).max)
+    assert np.array_equal(got[special], exp[special])
+    assert np.array_equal(special, (got == 0) | np.isinf(got) | (got == np.finfo(np.float32).max))
+    assert np.allclose(got[~special], exp[~special], rtol=1e-5, atol=0)
+    if seed == 0:
+        assert np.isinf(exp).any() or (exp == np.finfo(np.float32).max).any(), "underflow branch not exercised"
