@@ -20,6 +20,7 @@ bool Detector::Cuda(cudaError_t e, const char* what, std::string* err) const {
 
 Detector::~Detector() {
   if (d_tree_blob_) cudaFree(d_tree_blob_);
+  if (d_pq_blob_) cudaFree(d_pq_blob_);
   if (proj_.b_image) cudaFree(proj_.b_image);
   lists_.Free();
   DevBuf* bufs[] = {&d_db_cells_, &d_desc_kf_, &d_desc_lm_, &d_kf_meta_, &d_q_,    &d_cells_,
@@ -48,8 +49,8 @@ bool Detector::Create(const mlc_settings& s, const void* blob, size_t size, std:
     *err = "num_closest_words must be in 1..16";
     return false;
   }
-  if (s_.engine != 0) {
-    *err = "detector engine not built: only 'imi' (0) is available in this build";
+  if (s_.engine != 0 && s_.engine != 1) {
+    *err = "unknown detector engine (0 imi, 1 imipq)";
     return false;
   }
   if (!vocab_.Parse(blob, size, s_.engine == 1, err)) return false;
@@ -91,7 +92,58 @@ bool Detector::Create(const mlc_settings& s, const void* blob, size_t size, std:
     *err = "vocabulary kd-tree deeper than the device traversal stack";
     return false;
   }
-  return UploadTrees(err);
+  if (!UploadTrees(err)) return false;
+  return s_.engine == 1 ? UploadPq(err) : true;
+}
+
+// imipq: coarse words + residual quantiser centres on the device
+// (InvertedMultiProductQuantizationIndex ctor, …-quantization-index.h:70-130).
+bool Detector::UploadPq(std::string* err) {
+  const VocabularyFile& v = vocab_;
+  const int half = v.pq_components / 2, sub = v.target_dim / 2;
+  if (!v.has_pq || v.pq_components <= 0 || (v.pq_components & 1) || v.pq_components > 12 ||
+      v.pq_centers <= 0 || v.pq_centers > 256 || v.pq_dim_per_comp <= 0 || half * v.pq_dim_per_comp != sub) {
+    *err = "imipq: unsupported product quantiser shape (components even and <= 12, centres <= 256, "
+           "components/2 * dims_per_component == target_dim/2)";
+    return false;
+  }
+  const size_t per_word = static_cast<size_t>(half) * v.pq_centers * v.pq_dim_per_comp;
+  if (v.pq_centers1.v.size() != per_word * v.words1.cols || v.pq_centers2.v.size() != per_word * v.words2.cols) {
+    *err = "imipq: quantiser centre matrices do not match the vocabulary";
+    return false;
+  }
+  const size_t n_w1 = v.words1.v.size(), n_w2 = v.words2.v.size();
+  const size_t n_c1 = v.pq_centers1.v.size(), n_c2 = v.pq_centers2.v.size();
+  std::vector<float> blob;
+  blob.reserve(n_w1 + n_w2 + n_c1 + n_c2);
+  blob.insert(blob.end(), v.words1.v.begin(), v.words1.v.end());
+  blob.insert(blob.end(), v.words2.v.begin(), v.words2.v.end());
+  blob.insert(blob.end(), v.pq_centers1.v.begin(), v.pq_centers1.v.end());
+  blob.insert(blob.end(), v.pq_centers2.v.begin(), v.pq_centers2.v.end());
+  if (!Cuda(cudaMalloc(&d_pq_blob_, blob.size() * 4), "cudaMalloc(pq)", err)) return false;
+  if (!Cuda(cudaMemcpy(d_pq_blob_, blob.data(), blob.size() * 4, cudaMemcpyHostToDevice), "upload pq", err))
+    return false;
+  const float* base = static_cast<const float*>(d_pq_blob_);
+  pq_.words1 = base;
+  pq_.words2 = base + n_w1;
+  pq_.centers1 = base + n_w1 + n_w2;
+  pq_.centers2 = base + n_w1 + n_w2 + n_c1;
+  pq_.sub_dim = sub;
+  pq_.half_ncomp = half;
+  pq_.dim_per_comp = v.pq_dim_per_comp;
+  pq_.num_centers = v.pq_centers;
+  pq_.num_words1 = v.words1.cols;
+  pq_.num_words2 = v.words2.cols;
+  return true;
+}
+
+cudaError_t Detector::LaunchScan(const float* d_q, int64_t n_q, const int32_t* d_cells, int nw, int k,
+                                 int32_t* d_idx, float* d_dist, cudaStream_t stream) {
+  if (s_.engine == 1)
+    return LaunchImipqScan(pq_, d_q, n_q, d_cells, nw, lists_.cell_info, lists_.lists, k, d_idx, d_dist,
+                           sm_count_, stream);
+  return LaunchImiScan(dim(), d_q, n_q, d_cells, nw, lists_.cell_info, lists_.lists, k, d_idx, d_dist,
+                       sm_count_, stream);
 }
 
 bool Detector::UploadTrees(std::string* err) {
@@ -269,9 +321,24 @@ bool Detector::EnsureIndex(std::string* err) {
     if (!Cuda(d_db_cells_.Reserve(static_cast<size_t>(n) * 4), "alloc cells", err)) return false;
     if (!CoarseChunks(d_desc, n, 1, d_db_cells_.as<int32_t>(), stream_, err)) return false;
   }
-  bool ok = Cuda(BuildImiLists(d_db_cells_.as<int32_t>(), d_desc, n, d, static_cast<uint32_t>(cells64),
-                               s_.shard_rank, s_.shard_count, &lists_, stream_),
-                 "build inverted lists", err);
+  bool ok = true;
+  if (s_.engine == 1) {
+    // imipq: entries carry the quantised residual (12 code bytes) instead of the coordinates
+    uint32_t* d_codes = nullptr;
+    if (n > 0) {
+      ok = Cuda(cudaMalloc(&d_codes, static_cast<size_t>(n) * 12), "alloc pq codes", err) &&
+           Cuda(LaunchPqEncode(pq_, d_desc, d_db_cells_.as<int32_t>(), n, d_codes, stream_), "pq encode", err);
+    }
+    ok = ok && Cuda(BuildImiLists(d_db_cells_.as<int32_t>(), reinterpret_cast<const float*>(d_codes), n, 3,
+                                  static_cast<uint32_t>(cells64), s_.shard_rank, s_.shard_count, &lists_,
+                                  stream_),
+                    "build inverted lists", err);
+    if (d_codes) cudaFree(d_codes);
+  } else {
+    ok = Cuda(BuildImiLists(d_db_cells_.as<int32_t>(), d_desc, n, d, static_cast<uint32_t>(cells64),
+                            s_.shard_rank, s_.shard_count, &lists_, stream_),
+              "build inverted lists", err);
+  }
   if (d_desc) cudaFree(d_desc);
   if (!ok) return false;
   // metadata replicas for voting / clustering (kernel 3)
@@ -304,9 +371,7 @@ bool Detector::KnnDevice(const float* d_q, int64_t n_q, int k, int32_t* d_idx, f
   if (!Cuda(d_cells_.Reserve(static_cast<size_t>(n_q) * nw * 4), "alloc visit list", err)) return false;
   if (!CoarseChunks(d_q, n_q, nw, d_cells_.as<int32_t>(), stream, err)) return false;
   cudaEventRecord(ev0_, stream);
-  if (!Cuda(LaunchImiScan(dim(), d_q, n_q, d_cells_.as<int32_t>(), nw, lists_.cell_info, lists_.lists,
-                          k, d_idx, d_dist, sm_count_, stream),
-            "list scan", err))
+  if (!Cuda(LaunchScan(d_q, n_q, d_cells_.as<int32_t>(), nw, k, d_idx, d_dist, stream), "list scan", err))
     return false;
   cudaEventRecord(ev1_, stream);
   last_nq_ = n_q;
@@ -394,8 +459,7 @@ bool Detector::ScanDevice(const float* d_q, const int32_t* d_cells, int64_t n_q,
             "copy visit list", err))
     return false;
   cudaEventRecord(ev0_, stream);
-  if (!Cuda(LaunchImiScan(dim(), d_q, n_q, d_cells, nw, lists_.cell_info, lists_.lists, k, d_idx, d_dist,
-                          sm_count_, stream), "list scan", err))
+  if (!Cuda(LaunchScan(d_q, n_q, d_cells, nw, k, d_idx, d_dist, stream), "list scan", err))
     return false;
   cudaEventRecord(ev1_, stream);
   last_nq_ = n_q;
@@ -445,7 +509,14 @@ bool Detector::LastScanStats(uint64_t* bytes, uint64_t* entries, double* ms, std
   cudaEventSynchronize(ev1_);
   if (cudaEventElapsedTime(&msf, ev0_, ev1_) != cudaSuccess) msf = 0.f;
   *entries = total;
-  *bytes = total * static_cast<uint64_t>(4 * (dim() + 1));
+  if (s_.engine == 1) {
+    // algorithmic entry = index + packed codes (9 B at 10 components x 16 centres)
+    int bits = 1;
+    while ((1 << bits) < pq_.num_centers) ++bits;
+    *bytes = total * static_cast<uint64_t>(4 + (2 * pq_.half_ncomp * bits + 7) / 8);
+  } else {
+    *bytes = total * static_cast<uint64_t>(4 * (dim() + 1));
+  }
   *ms = msf;
   return true;
 }

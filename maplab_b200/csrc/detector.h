@@ -138,6 +138,12 @@ class Detector {
   ProjectionDevice proj_;
   void* d_tree_blob_ = nullptr;
   CoarseParams coarse_{};
+  PqParams pq_{};            // engine 1 (imipq)
+  void* d_pq_blob_ = nullptr;
+  bool UploadPq(std::string* err);
+  // engine dispatch of the inverted-list scan (kernel 2b)
+  cudaError_t LaunchScan(const float* d_q, int64_t n_q, const int32_t* d_cells, int nw, int k,
+                         int32_t* d_idx, float* d_dist, cudaStream_t stream);
 
   // database (host mirror of what Insert keeps, matching-based-engine.cc:227-251)
   std::vector<KeyframeMeta> keyframes_;

@@ -33,10 +33,10 @@ cudaError_t LaunchCoarseWords(const CoarseParams& p, const float* d_q, int64_t n
                               int32_t* d_cells, void* scratch, int sm_count, cudaStream_t stream);
 
 // ---- kernel 2b -------------------------------------------------------------------------------
-// Inverted lists in HBM. Cell c owns `len` entries starting at byte 16 * start16 of `lists`:
-// consecutive blocks of 32 entries, each block stored as [dim + 1][block size] 32-bit words
-// (dim float rows, then the row of global descriptor indices); the last block of a cell holds
-// len % 32 entries. 4 * (dim + 1) bytes per entry (44 B at dim 10), cells padded to 16 B.
+// Inverted lists in HBM. Cell c owns `len` consecutive entries starting at byte 16 * start16 of
+// `lists`. One entry = `dim` payload words, the global descriptor index, zero padding up to a
+// multiple of 16 bytes: imi = 10 fp32 coordinates + index (48 B stored, 44 B algorithmic); imipq =
+// 12 code bytes + index (16 B stored; 9 B algorithmic at 10 components x 16 centres).
 struct DeviceLists {
   uint2* cell_info = nullptr;  // {start16, len} per cell
   uint32_t* lists = nullptr;
@@ -57,6 +57,18 @@ cudaError_t BuildImiLists(const int32_t* d_cells, const float* d_desc, int64_t n
 cudaError_t LaunchImiScan(int dim, const float* q, int64_t n_q, const int32_t* cells, int nw,
                           const uint2* cell_info, const uint32_t* lists, int k, int32_t* out_idx,
                           float* out_dist, int sm_count, cudaStream_t stream);
+// imipq engine (imilib/inverted-multi-product-quantization-index.h): device views of the coarse
+// words (column-major sub_dim x W) and of the per-word residual quantiser centres
+// ([word][component][centre][dim_per_comp], as serialised).
+struct PqParams {
+  const float *words1 = nullptr, *words2 = nullptr, *centers1 = nullptr, *centers2 = nullptr;
+  int sub_dim = 0, half_ncomp = 0, dim_per_comp = 0, num_centers = 0, num_words1 = 0, num_words2 = 0;
+};
+cudaError_t LaunchPqEncode(const PqParams& p, const float* desc, const int32_t* cells, int64_t n,
+                           uint32_t* codes, cudaStream_t stream);
+cudaError_t LaunchImipqScan(const PqParams& p, const float* q, int64_t n_q, const int32_t* cells, int nw,
+                            const uint2* cell_info, const uint32_t* lists, int k, int32_t* out_idx,
+                            float* out_dist, int sm_count, cudaStream_t stream);
 cudaError_t LaunchScanEntries(const int32_t* cells, int64_t n_visits, const uint2* cell_info,
                               unsigned long long* d_total, cudaStream_t stream);
 cudaError_t LaunchMergeTopk(const int32_t* idx_lists, const float* dist_lists, int num_lists,

@@ -286,6 +286,184 @@ cudaError_t LaunchImiScan(int dim, const float* q, int64_t n_q, const int32_t* c
   }
 }
 
+// =============================================================================================
+// imipq engine: product-quantised residuals (imilib/inverted-multi-product-quantization-index.h,
+// imilib/product-quantization.h)
+// =============================================================================================
+namespace {
+
+// SquaredDistance of two runtime-length vectors in the canonical fp32 order (see
+// SquaredDistanceCanonical), dim <= 8.
+__device__ __forceinline__ float SquaredDistanceRuntime(const float* a, const float* b, int dim) {
+  const int vec = (dim / 4) * 4;
+  if (vec == 0) {
+    float s = 0.f;
+    for (int i = 0; i < dim; ++i) {
+      const float d = __fsub_rn(a[i], b[i]);
+      const float sq = __fmul_rn(d, d);
+      s = (i == 0) ? sq : __fadd_rn(s, sq);
+    }
+    return s;
+  }
+  float lane[4];
+  for (int l = 0; l < 4; ++l) {
+    const float d = __fsub_rn(a[l], b[l]);
+    lane[l] = __fmul_rn(d, d);
+  }
+  for (int p = 4; p < vec; p += 4)
+    for (int l = 0; l < 4; ++l) {
+      const float d = __fsub_rn(a[p + l], b[p + l]);
+      lane[l] = __fadd_rn(lane[l], __fmul_rn(d, d));
+    }
+  float res = __fadd_rn(__fadd_rn(lane[0], lane[1]), __fadd_rn(lane[2], lane[3]));
+  if (vec < dim) {
+    float rem = 0.f;
+    for (int i = vec; i < dim; ++i) {
+      const float d = __fsub_rn(a[i], b[i]);
+      const float sq = __fmul_rn(d, d);
+      rem = (i == vec) ? sq : __fadd_rn(rem, sq);
+    }
+    res = __fadd_rn(res, rem);
+  }
+  return res;
+}
+
+// AddDescriptors of the PQ index (…-quantization-index.h:136-175): residual of each half against
+// its coarse word, per component the nearest of the word's centres (first minimum wins,
+// product-quantization.h:81-103). One thread per descriptor; code j lands in byte j of 12.
+__global__ void pq_encode_kernel(PqParams p, const float* __restrict__ desc, const int32_t* __restrict__ cells,
+                                 int64_t n, uint32_t* __restrict__ codes) {
+  const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (i >= n) return;
+  uint32_t out[3] = {0u, 0u, 0u};
+  const int32_t cell = cells[i];
+  if (cell >= 0) {
+    const int dim = 2 * p.sub_dim;
+    const int per_word = p.half_ncomp * p.num_centers * p.dim_per_comp;
+    for (int h = 0; h < 2; ++h) {
+      const int w = h ? cell % p.num_words2 : cell / p.num_words2;
+      const float* word = (h ? p.words2 : p.words1) + static_cast<size_t>(w) * p.sub_dim;
+      const float* ctrs = (h ? p.centers2 : p.centers1) + static_cast<size_t>(w) * per_word;
+      float res[8];
+      for (int j = 0; j < p.sub_dim; ++j) res[j] = __fsub_rn(desc[i * dim + h * p.sub_dim + j], word[j]);
+      for (int j = 0; j < p.half_ncomp; ++j) {
+        int best = 0;
+        float best_d = 0.f;
+        for (int c = 0; c < p.num_centers; ++c) {
+          const float d = SquaredDistanceRuntime(ctrs + static_cast<size_t>(j * p.num_centers + c) * p.dim_per_comp,
+                                                 res + j * p.dim_per_comp, p.dim_per_comp);
+          if (c == 0 || d < best_d) {
+            best_d = d;
+            best = c;
+          }
+        }
+        const int at = h * p.half_ncomp + j;
+        out[at >> 2] |= static_cast<uint32_t>(best) << (8 * (at & 3));
+      }
+    }
+  }
+  codes[i * 3 + 0] = out[0];
+  codes[i * 3 + 1] = out[1];
+  codes[i * 3 + 2] = out[2];
+}
+
+// GetNNearestNeighbors of the PQ index (…-quantization-index.h:181-288): one warp per query
+// descriptor. Per visited, non-empty cell (w1, w2) the lanes fill the two look-up tables
+// LUT_h[component][centre] = (centre - residual_h)^2 in shared memory (FillLUT,
+// product-quantization.h:107-125), then stream the cell's 16-byte entries {12 code bytes, index}:
+// distance = (sequential sum over the first-half components from 0.0f) + (the same over the
+// second half) (ComputeDistance, :144-152). Top-k as in imi_scan_kernel.
+__global__ void __launch_bounds__(256)
+imipq_scan_kernel(PqParams p, const float* __restrict__ q, int64_t n_q, const int32_t* __restrict__ cells,
+                  int nw, const uint2* __restrict__ cell_info, const uint4* __restrict__ lists, int k,
+                  int32_t* __restrict__ out_idx, float* __restrict__ out_dist) {
+  extern __shared__ float lut_s[];
+  const int lane = threadIdx.x & 31;
+  const int lut_size = 2 * p.half_ncomp * p.num_centers;
+  float* lut = lut_s + static_cast<size_t>(threadIdx.x >> 5) * lut_size;
+  const int dim = 2 * p.sub_dim;
+  const int per_half = p.half_ncomp * p.num_centers;
+  const int per_word = per_half * p.dim_per_comp;
+  const int64_t warp_stride = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+  for (int64_t qi = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 5; qi < n_q;
+       qi += warp_stride) {
+    uint64_t held = kEmptyKey;
+    const float* qd = q + qi * dim;
+    for (int v = 0; v < nw; ++v) {
+      const int32_t cell = __ldg(cells + qi * nw + v);
+      if (cell < 0) continue;  // missing word
+      const uint2 info = __ldg(cell_info + cell);
+      if (info.y == 0) continue;  // cell not in word_index_map_
+      __syncwarp();
+      for (int t = lane; t < lut_size; t += 32) {
+        const int h = t / per_half, r = t - h * per_half;
+        const int comp = r / p.num_centers;
+        const int w = h ? cell % p.num_words2 : cell / p.num_words2;
+        const float* word = (h ? p.words2 : p.words1) + static_cast<size_t>(w) * p.sub_dim + comp * p.dim_per_comp;
+        const float* ctr = (h ? p.centers2 : p.centers1) + static_cast<size_t>(w) * per_word +
+                           static_cast<size_t>(r) * p.dim_per_comp;
+        float res[8];
+        for (int d = 0; d < p.dim_per_comp; ++d)
+          res[d] = __fsub_rn(__ldg(qd + h * p.sub_dim + comp * p.dim_per_comp + d), __ldg(word + d));
+        lut[t] = SquaredDistanceRuntime(ctr, res, p.dim_per_comp);
+      }
+      __syncwarp();
+      const uint4* entries = lists + info.x;
+      for (uint32_t base = 0; base < info.y; base += 32) {
+        const uint32_t e = base + lane;
+        uint64_t key = kEmptyKey;
+        if (e < info.y) {
+          const uint4 en = __ldg(entries + e);
+          const uint32_t cw[3] = {en.x, en.y, en.z};
+          float s1 = 0.0f, s2 = 0.0f;
+          for (int j = 0; j < p.half_ncomp; ++j) {
+            const int a1 = j, a2 = p.half_ncomp + j;
+            s1 = __fadd_rn(s1, lut[j * p.num_centers + ((cw[a1 >> 2] >> (8 * (a1 & 3))) & 0xFFu)]);
+            s2 = __fadd_rn(s2, lut[per_half + j * p.num_centers + ((cw[a2 >> 2] >> (8 * (a2 & 3))) & 0xFFu)]);
+          }
+          const uint32_t bits = __float_as_uint(__fadd_rn(s1, s2));
+          if (bits <= kInfBits) key = (static_cast<uint64_t>(bits) << 32) | en.w;
+        }
+        const uint64_t kth = ShflKey(held, k - 1);
+        InsertCandidates(__ballot_sync(kFull, key < kth), key, held, lane);
+      }
+    }
+    if (lane < k) {
+      out_idx[qi * k + lane] = static_cast<int32_t>(static_cast<uint32_t>(held));
+      out_dist[qi * k + lane] = __uint_as_float(static_cast<uint32_t>(held >> 32));
+    }
+  }
+}
+
+}  // namespace
+
+cudaError_t LaunchPqEncode(const PqParams& p, const float* desc, const int32_t* cells, int64_t n,
+                           uint32_t* codes, cudaStream_t stream) {
+  if (n <= 0) return cudaSuccess;
+  pq_encode_kernel<<<static_cast<unsigned>((n + 127) / 128), 128, 0, stream>>>(p, desc, cells, n, codes);
+  CountLaunch();
+  return cudaGetLastError();
+}
+
+cudaError_t LaunchImipqScan(const PqParams& p, const float* q, int64_t n_q, const int32_t* cells, int nw,
+                            const uint2* cell_info, const uint32_t* lists, int k, int32_t* out_idx,
+                            float* out_dist, int sm_count, cudaStream_t stream) {
+  if (n_q <= 0) return cudaSuccess;
+  if (k > 16 || nw > kMaxWords) return cudaErrorInvalidValue;
+  const size_t smem = static_cast<size_t>(256 / 32) * 2 * p.half_ncomp * p.num_centers * sizeof(float);
+  if (smem > 96 * 1024) return cudaErrorInvalidValue;
+  cudaError_t e = cudaFuncSetAttribute(imipq_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       static_cast<int>(smem));
+  if (e != cudaSuccess) return e;
+  int64_t blocks = (n_q * 32 + 255) / 256;
+  const int64_t cap = static_cast<int64_t>(sm_count) * 4;
+  if (blocks > cap) blocks = cap;
+  imipq_scan_kernel<<<static_cast<unsigned>(blocks), 256, smem, stream>>>(
+      p, q, n_q, cells, nw, cell_info, reinterpret_cast<const uint4*>(lists), k, out_idx, out_dist);
+  CountLaunch();
+  return cudaGetLastError();
+}
+
 // ---------------------------------------------------------------------------------------------
 // scan statistics: algorithmic entries visited = sum over (query, cell) of the list length
 // ---------------------------------------------------------------------------------------------

@@ -97,6 +97,21 @@ def make_vocabulary(train_desc, num_words=1000, target_dim=10, desc_bits=512, ro
     return blob, dict(P=P, W1=W1, W2=W2)
 
 
+def add_product_quantizer(voc, num_components=10, num_centers=16, spread=0.6, seed=13):
+    """Append a residual product quantiser (InvertedMultiIndexProductVocabulary,
+    inverted-multi-index-interface.h:59-88) to a vocabulary dict of make_vocabulary: per coarse word
+    and component `num_centers` seeded random centres (stand-in for TrainProjectedVocabulary's
+    residual k-means, an offline trainer out of scope). Returns the version-200 blob."""
+    rng = np.random.default_rng(seed)
+    P, W1, W2 = voc["P"], voc["W1"], voc["W2"]
+    half = num_components // 2
+    dpc = W1.shape[0] // half
+    assert half * dpc == W1.shape[0]
+    Q1 = (spread * rng.standard_normal((dpc, half * num_centers * W1.shape[1]))).astype(np.float32)
+    Q2 = (spread * rng.standard_normal((dpc, half * num_centers * W2.shape[1]))).astype(np.float32)
+    return serialize_vocabulary(P, W1, W2, 2 * W1.shape[0], pq=(num_components, num_centers, dpc, Q1, Q2))
+
+
 # ----------------------------------------------------------------------------- synthetic map
 def _flip_mask(rng, n, nbytes, log2_inv_p):
     """Random bit mask with P(bit) = 2^-log2_inv_p (AND of independent uniform words)."""

@@ -176,3 +176,14 @@ def test_probabilistic_score_matches_oracle(seed):
     assert np.allclose(got[~special], exp[~special], rtol=1e-5, atol=0)
     if seed == 0:
         assert np.isinf(exp).any() or (exp == np.finfo(np.float32).max).any(), "underflow branch not exercised"
+
+
+def test_find_matches_oracle_imipq_engine():
+    # --lc_detector_engine=imipq (+ probabilistic scoring): the whole Find on PQ distances
+    m, _, voc, q = small_world(num_queries=12)
+    blob = synthetic.add_product_quantizer(voc, 10, 16)
+    for kw in (dict(engine=1, num_nearest_neighbors=6), dict(engine=1, scoring=1, num_nearest_neighbors=8)):
+        det, ora = _pair(blob, m, **kw)
+        qframes = frames_of(q["frames"])
+        qproj = det.project(q["bits"])
+        assert _check_batch(det, ora, qframes, qproj) > 0

@@ -155,3 +155,45 @@ def test_sharded_lists_merge_to_the_single_index_result():
     torch.cuda.synchronize()
     assert np.array_equal(out_i.cpu().numpy(), ref_idx)
     assert np.array_equal(out_d.cpu().numpy(), ref_dist)
+
+
+def test_reference_golden_imipq_add_and_knn():
+    # test_inverted-multi-index-product-quantization.cc:68-146 (template <int, 4, 1, 2>) through the
+    # device PQ encode + scan kernels
+    t = G["imipq"]
+    W1 = np.asarray(t["words1"], np.float32)
+    W2 = np.asarray(t["words2"], np.float32)
+    Q1 = np.asarray(t["quantizer_centers_1"], np.float32)[None, :]
+    Q2 = np.asarray(t["quantizer_centers_2"], np.float32)[None, :]
+    blob = synthetic.serialize_vocabulary(np.zeros((4, 16), np.float32), W1, W2, pq=(4, 2, 1, Q1, Q2))
+    det = capi.Detector(blob, capi.default_settings(engine=1, knn_epsilon=t["epsilon"],
+                                                    num_closest_words=t["num_closest_words"]))
+    desc = np.asarray(t["descriptors"], np.float32).T
+    det.insert(0, 0, 0, 0, desc, np.arange(len(desc)))
+    idx, dist = det.knn(np.asarray([t["query"]], np.float32), t["num_neighbors"])
+    assert idx[0].tolist() == t["expected_indices"]
+    for got, exp in zip(dist[0], t["expected_distances"]):
+        assert (np.isinf(got) if exp == "inf" else got == np.float32(exp))
+
+
+@pytest.mark.parametrize("ncomp,ncent,k", [(10, 16, 6), (2, 256, 10), (10, 3, 1)])
+def test_imipq_knn_matches_oracle(ncomp, ncent, k):
+    # imipq engine: indices AND distances bit-identical to the oracle's
+    # InvertedMultiProductQuantizationIndex restatement on a seeded synthetic map
+    m, _, voc, q = small_world()
+    blob = synthetic.add_product_quantizer(voc, ncomp, ncent)
+    det = capi.Detector(blob, capi.default_settings(engine=1))
+    ora = po.Engine(blob, po.default_settings(engine=1))
+    proj = det.project(m["bits"])
+    frames = frames_of(m["frames"])
+    det.insert_batch(frames, proj, m["landmarks"])
+    fill_oracle(ora, frames, proj, m["landmarks"])
+    qp = det.project(q["bits"])
+    idx, dist = det.knn(qp, k)
+    oidx, odist = ora.knn(qp, k)
+    assert np.array_equal(idx, oidx)
+    assert np.array_equal(dist, odist)
+    assert (idx >= 0).any()
+    st = det.last_scan_stats()
+    bits = int(np.ceil(np.log2(ncent)))
+    assert st["algorithmic_bytes"] == st["entries"] * (4 + (ncomp * bits + 7) // 8)
