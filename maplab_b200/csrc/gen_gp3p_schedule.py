@@ -8,7 +8,9 @@ This script
   2. removes dead operations (results that never reach the 48 action-matrix entries),
   3. list-schedules the rest into WAVES of mutually independent operations (RAW, WAR and WAW all
      respected, so the operations of one wave may execute in any order / in parallel),
-  4. sorts every wave by opcode and emits gp3p_schedule.inc.
+  4. renames every value to a recycled physical slot (liveness over the wave schedule), which
+     shrinks the per-hypothesis slot array ~3x (more hypotheses resident per SM),
+  5. sorts every wave by opcode and emits gp3p_schedule.inc.
 Every operation still computes exactly the same IEEE-754 expression on exactly the same operand
 values, so the wave-parallel execution is bit-identical to the sequential program; the script
 checks that on random inputs before writing the file.
@@ -129,8 +131,123 @@ def main():
     offsets = np.cumsum([0] + [len(w) for w in waves]).tolist()
     chunks = sum((len(w) + 31) // 32 for w in waves)
 
-    # ---- 4. self-check against the sequential program ----
+    # ---- 4. slot compaction: rename every VALUE (definition) to a physical slot that is free ----
+    # A value lives from the wave that defines it (0 = initial state) to the last wave that reads it;
+    # SUBMUL / SCALE update their destination in place and keep its slot. A slot is recycled for a
+    # definition of wave w only if its previous value was last read in a wave < w, so the
+    # operations of one wave stay mutually independent. Slots that are only ever read as the
+    # implicit initial 0.0 (structural zeros of the elimination template) share slot 0.
+    W_RMW = (W_SUBMUL, W_SCALE)
+    cur, vals = {}, []            # logical slot -> value id; value = [def_wave, last_read, kind]
+    def new_value(wave, kind):
+        vals.append([wave, wave, kind])
+        return len(vals) - 1
+    init_value = {}
+    for e in init:
+        init_value[e[0]] = cur[e[0]] = new_value(0, "init")
+    op_vals = []                  # per op: (value ids of the reads, value id of the result)
+    for wi, w in enumerate(waves):
+        reads_of = []
+        for op in w:
+            r, d = reads_writes(op)
+            ids = []
+            for sl in r:
+                if sl not in cur:
+                    cur[sl] = new_value(0, "zero")
+                v = cur[sl]
+                vals[v][1] = max(vals[v][1], wi + 1)
+                ids.append(v)
+            reads_of.append(ids)
+        for op, ids in zip(w, reads_of):
+            d = op[1]
+            if op[0] in W_RMW:
+                v = cur[d]
+                if vals[v][2] == "zero":
+                    vals[v][2] = "zero_rmw"   # needs its own zero-filled slot
+            else:
+                cur[d] = v = new_value(wi + 1, "def")
+            op_vals.append((ids, v))
+    END = len(waves) + 1
+    for sl in action:
+        if sl >= 0:
+            vals[cur[sl]][1] = END
+    ZERO_SLOT = 0
+    phys = [None] * len(vals)
+    next_slot, free = 1, []
+    by_def = {}
+    for v, (dw, lr, kind) in enumerate(vals):
+        by_def.setdefault(dw, []).append(v)
+    expiring = {}
+    for wave in range(0, END + 1):
+        for v in by_def.get(wave, []):
+            dw, lr, kind = vals[v]
+            if kind == "zero":
+                phys[v] = ZERO_SLOT
+                continue
+            # initial values (wave 0) need fresh slots: they are written / zero-filled before wave 1
+            if wave > 0 and free:
+                phys[v] = free.pop()
+            else:
+                phys[v] = next_slot
+                next_slot += 1
+            expiring.setdefault(lr, []).append(phys[v])
+        # values last read in this wave free their slot for definitions of LATER waves
+        free.extend(expiring.pop(wave, []))
+    dummy_slot = next_slot        # init entries nobody reads land here
+    compact_slots = next_slot + 1
+    new_waves, at = [], 0
+    for w in waves:
+        nw_ = []
+        for op in w:
+            ids, v = op_vals[at]
+            at += 1
+            r, d = reads_writes(op)
+            m = {sl: phys[i] for sl, i in zip(r, ids)}
+            o, d0, a0, b0, c0, e0 = op
+            def mp(x, used):
+                return m[x] if used else 0
+            if o == W_DIVSUB:
+                nw_.append((o, phys[v], m[a0], m[b0], m[c0], m[e0]))
+            elif o in (W_DIV, W_NEGDIV):
+                nw_.append((o, phys[v], m[a0], m[b0], 0, 0))
+            elif o == W_ZERO:
+                nw_.append((o, phys[v], 0, 0, 0, 0))
+            elif o == W_SUBMUL:
+                assert phys[v] == m[d0]
+                nw_.append((o, phys[v], m[a0], m[b0], 0, 0))
+            elif o == W_SCALE:
+                assert phys[v] == m[d0]
+                nw_.append((o, phys[v], m[a0], 0, 0, 0))
+            else:
+                nw_.append((o, phys[v], m[a0], 0, 0, 0))
+        nw_.sort(key=lambda op: (op[0], op[1]))
+        new_waves.append(nw_)
+    new_init = []
+    for e in init:
+        v = init_value[e[0]]
+        dead = vals[v][1] == 0
+        new_init.append([dummy_slot if dead else phys[v]] + list(e[1:]))
+    new_action = [(-1 if sl < 0 else phys[cur[sl]]) for sl in action]
+    old_total_slots, old_init, old_waves = total_slots, init, waves
+    total_slots, waves = compact_slots, new_waves
+    flat = [op for w in waves for op in w]
+
+    # ---- 5. self-check against the sequential program ----
     rng = np.random.default_rng(0)
+
+    def init_slots_seq(f, v, p):
+        S = np.zeros(old_total_slots)
+        src = (f, v, p)
+        for e in old_init:
+            acc = 0.0
+            for t in range(e[1]):
+                coef, kind, i, j = e[2 + 4 * t: 6 + 4 * t]
+                term = float(coef) * src[kind][j * 3 + i]
+                acc = term if t == 0 else acc + term
+            S[e[0]] = acc
+        return S
+
+    init = new_init
 
     def init_slots(f, v, p):
         S = np.zeros(total_slots)
@@ -196,11 +313,12 @@ def main():
     with np.errstate(all="ignore"):
         for trial in range(5):
             f, v, p = rng.normal(size=9), rng.normal(size=9) * 0.1, rng.normal(size=9) * 3
-            a = run_seq(init_slots(f, v, p))
+            a = run_seq(init_slots_seq(f, v, p))
             b = run_waves(init_slots(f, v, p))
-            for s in action:
+            assert b[ZERO_SLOT] == 0.0
+            for s, ns in zip(action, new_action):
                 if s >= 0:
-                    assert a[s].tobytes() == b[s].tobytes(), (trial, s, a[s], b[s])
+                    assert a[s].tobytes() == b[ns].tobytes(), (trial, s, a[s], b[ns])
 
     with open(OUT, "w") as fo:
         fo.write("// GENERATED by maplab_b200/csrc/gen_gp3p_schedule.py from gp3p_program.inc. Do not edit.\n")
@@ -214,8 +332,14 @@ def main():
             fo.write("  {" + ",".join(str(x) for x in op) + "},\n")
         fo.write("};\nstatic const unsigned short GP3P_W_WAVE_OFFSETS[GP3P_W_NUM_WAVES + 1] = {")
         fo.write(",".join(str(x) for x in offsets) + "};\n")
+        fo.write("// GP3P_INIT / GP3P_ACTION of gp3p_program.inc with the compacted slot numbers\n")
+        fo.write(f"static const short GP3P_W_INIT[{len(new_init)}][{len(new_init[0])}] = {{\n")
+        for e in new_init:
+            fo.write("  {" + ",".join(str(x) for x in e) + "},\n")
+        fo.write("};\n")
+        fo.write(f"static const short GP3P_W_ACTION[{len(new_action)}] = {{" + ",".join(str(x) for x in new_action) + "};\n")
     print(f"ops {len(mops)} -> {len(flat)} after DCE; waves {num_waves}; 32-wide chunks {chunks}; "
-          f"slots {total_slots}; widest wave {max(len(w) for w in waves)}")
+          f"slots {old_total_slots} -> {total_slots} after compaction; widest wave {max(len(w) for w in waves)}")
 
 
 if __name__ == "__main__":

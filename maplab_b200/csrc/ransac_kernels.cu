@@ -66,8 +66,8 @@ struct RansacArgs {
   int rnd_len;
   const uint4* wops;            // wave-scheduled ops {op | d<<16, a | b<<16, c | e<<16, 0}
   const unsigned short* wave_offsets;
-  const short* init_table;      // GP3P_INIT
-  const short* action;          // GP3P_ACTION
+  const short* init_table;      // GP3P_W_INIT (compacted slots)
+  const short* action;          // GP3P_W_ACTION
   double* bearings;             // 3 per correspondence
   int32_t* shuffled;            // per correspondence
   mlc_pose_result* results;
@@ -906,12 +906,12 @@ cudaError_t EnsureProgram() {
   cudaError_t e;
   if ((e = cudaMalloc(&g_program.wops, sizeof(uint4) * GP3P_W_NUM_OPS)) != cudaSuccess) return e;
   if ((e = cudaMalloc(&g_program.wave_offsets, sizeof(GP3P_W_WAVE_OFFSETS))) != cudaSuccess) return e;
-  if ((e = cudaMalloc(&g_program.init_table, sizeof(GP3P_INIT))) != cudaSuccess) return e;
-  if ((e = cudaMalloc(&g_program.action, sizeof(GP3P_ACTION))) != cudaSuccess) return e;
+  if ((e = cudaMalloc(&g_program.init_table, sizeof(GP3P_W_INIT))) != cudaSuccess) return e;
+  if ((e = cudaMalloc(&g_program.action, sizeof(GP3P_W_ACTION))) != cudaSuccess) return e;
   if ((e = cudaMemcpy(g_program.wops, packed.data(), sizeof(uint4) * GP3P_W_NUM_OPS, cudaMemcpyHostToDevice)) != cudaSuccess) return e;
   if ((e = cudaMemcpy(g_program.wave_offsets, GP3P_W_WAVE_OFFSETS, sizeof(GP3P_W_WAVE_OFFSETS), cudaMemcpyHostToDevice)) != cudaSuccess) return e;
-  if ((e = cudaMemcpy(g_program.init_table, GP3P_INIT, sizeof(GP3P_INIT), cudaMemcpyHostToDevice)) != cudaSuccess) return e;
-  return cudaMemcpy(g_program.action, GP3P_ACTION, sizeof(GP3P_ACTION), cudaMemcpyHostToDevice);
+  if ((e = cudaMemcpy(g_program.init_table, GP3P_W_INIT, sizeof(GP3P_W_INIT), cudaMemcpyHostToDevice)) != cudaSuccess) return e;
+  return cudaMemcpy(g_program.action, GP3P_W_ACTION, sizeof(GP3P_W_ACTION), cudaMemcpyHostToDevice);
 }
 
 }  // namespace
@@ -1043,8 +1043,13 @@ bool Detector::RansacOnDevice(const mlc_ransac_settings& rs, const mlc_camera* c
   ransac_init_kernel<<<warp_blocks, 128, 0, stream_>>>(a, d_state);
   CountLaunch();
   const int max_rounds = 11 * rs.num_ransac_iters + 4;  // >= one consumed sample per round
-  const unsigned elim_blocks = static_cast<unsigned>(
-      std::min<int64_t>((num_hyp + kWarpsPerBlock - 1) / kWarpsPerBlock, static_cast<int64_t>(sm_count_) * 4));
+  int elim_per_sm = 4;  // resident CTAs per SM: bounded by the slot arrays in shared memory
+  if (!Cuda(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&elim_per_sm, gp3p_eliminate_kernel,
+                                                          kWarpsPerBlock * 32, smem), "ransac occupancy", err))
+    return false;
+  if (elim_per_sm < 1) elim_per_sm = 1;
+  const unsigned elim_blocks = static_cast<unsigned>(std::min<int64_t>(
+      (num_hyp + kWarpsPerBlock - 1) / kWarpsPerBlock, static_cast<int64_t>(sm_count_) * elim_per_sm));
   for (int round = 0; round < max_rounds; ++round) {
     if (!Cuda(cudaMemsetAsync(d_remaining, 0, sizeof(int), stream_), "memset", err)) return false;
     ransac_sample_kernel<<<thread_blocks, 128, 0, stream_>>>(a, d_state, d_hyp);
