@@ -6,11 +6,12 @@
 // The kd-tree search is emulated bit-for-bit (same traversal order, same fp32 operations without
 // contraction, same pruning tests), because the reference's coarse search is NOT an exact top-k
 // (SURVEY F3). Work item = (query descriptor, half). To keep the warps converged the depth-first
-// search runs as a per-lane state machine whose every iteration performs ONE micro-step — descend
-// one inner node, score one bucket point, or pop one frame — and lanes that finish pull the next
-// work item of their warp's range (persistent lanes). Blocks with even/odd index own half 0 / 1
-// and stage only that half's tree in shared memory; the per-lane result heaps live in shared
-// memory too ([entry][thread], conflict free).
+// search runs as a per-lane state machine (descend one inner node / score one bucket point / pop
+// one frame) driven in three warp-wide phases — all descending lanes walk to their leaves, all
+// lanes at a leaf score their buckets, all unwinding lanes pop — so that the lanes of a warp
+// execute the same code most of the time; lanes that finish pull the next work item of their
+// warp's range (persistent lanes). Blocks with even/odd index own half 0 / 1 and stage only that
+// half's tree in shared memory; the per-lane result heaps live in registers.
 #include "device_index.h"
 #include "ptx.cuh"
 
@@ -37,9 +38,12 @@ __device__ __forceinline__ void Put(float (&v)[D], uint32_t d, float x) {
   for (int i = 0; i < D; ++i) v[i] = (d == static_cast<uint32_t>(i)) ? x : v[i];
 }
 
-template <int D>
+// KK >= kk: capacity of the per-lane result heap, which lives in REGISTERS, right-aligned
+// (entries [KK - kk, KK) are real, the ones before are -inf sentinels that never move), so that the
+// k-th best ("head") is always hv[KK - 1] and an insertion is one branch-free pass.
+template <int D, int KK>
 __global__ void __launch_bounds__(kThreads)
-kd_search_kernel(CoarseParams p, const float* __restrict__ q, int64_t n, int kk1, int kk2, int kk_max,
+kd_search_kernel(CoarseParams p, const float* __restrict__ q, int64_t n, int kk1, int kk2,
                  int32_t* __restrict__ out_idx, float* __restrict__ out_val) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int half = blockIdx.x & 1;
@@ -47,12 +51,9 @@ kd_search_kernel(CoarseParams p, const float* __restrict__ q, int64_t n, int kk1
   const KdNodeDev* nodes = half ? p.nodes2 : p.nodes1;
   const int32_t* buckets = half ? p.buckets2 : p.buckets1;
   const float* cloud = half ? p.cloud2 : p.cloud1;
-  // shared memory: [heap values kk x T][heap indices kk x T][tree blob of this half]
-  float* hv = reinterpret_cast<float*>(smem_raw);
-  int32_t* hi = reinterpret_cast<int32_t*>(smem_raw + sizeof(float) * kk_max * kThreads);
   const size_t half_base = half ? static_cast<size_t>(n) * kk1 : 0;  // [half 0: n x kk1][half 1: n x kk2]
   if (p.stage_in_smem) {
-    unsigned char* dst = smem_raw + 2 * sizeof(float) * kk_max * kThreads;
+    unsigned char* dst = smem_raw;
     const uint32_t begin = half ? p.off_nodes2 : p.off_nodes1;
     const uint32_t end = half ? p.packed_bytes : p.off_nodes2;
     const unsigned char* src = reinterpret_cast<const unsigned char*>(p.packed) + begin;
@@ -66,6 +67,7 @@ kd_search_kernel(CoarseParams p, const float* __restrict__ q, int64_t n, int kk1
   const int tid = threadIdx.x;
   const int lane = tid & 31;
   const uint32_t lanemask_lt = (1u << lane) - 1u;
+  constexpr uint32_t kAll = 0xffffffffu;
   // contiguous range of queries for this warp
   const int64_t warps_total = static_cast<int64_t>(gridDim.x >> 1) * (kThreads / 32);
   const int64_t warp_id = static_cast<int64_t>(blockIdx.x >> 1) * (kThreads / 32) + (tid >> 5);
@@ -75,16 +77,18 @@ kd_search_kernel(CoarseParams p, const float* __restrict__ q, int64_t n, int kk1
 
   const float inf = __int_as_float(0x7f800000);
   float qv[D], off[D];
+  float hv[KK];
+  int32_t hx[KK];
   uint32_t st_tag[kMaxStack];
   float st_val[kMaxStack];
   int state = kIdle, sp = 0;
   uint32_t node = 0, pos = 0, end = 0;
-  float rd = 0.f, head = inf;
+  float rd = 0.f;
   int64_t item = 0;
 
   for (;;) {
     // ---- refill idle lanes from the warp's range ----
-    const uint32_t idle = __ballot_sync(0xffffffffu, state == kIdle);
+    const uint32_t idle = __ballot_sync(kAll, state == kIdle);
     if (idle) {
       if (state == kIdle) {
         item = warp_next + __popc(idle & lanemask_lt);
@@ -95,11 +99,11 @@ kd_search_kernel(CoarseParams p, const float* __restrict__ q, int64_t n, int kk1
             qv[d] = __ldg(src + d);
             off[d] = 0.f;
           }
-          for (int j = 0; j < kk; ++j) {
-            hv[j * kThreads + tid] = inf;
-            hi[j * kThreads + tid] = -1;
+#pragma unroll
+          for (int j = 0; j < KK; ++j) {
+            hv[j] = (j >= KK - kk) ? inf : -inf;
+            hx[j] = -1;
           }
-          head = inf;
           node = 0;
           rd = 0.f;
           sp = 0;
@@ -110,78 +114,96 @@ kd_search_kernel(CoarseParams p, const float* __restrict__ q, int64_t n, int kk1
       }
       warp_next += __popc(idle);
     }
-    if (__all_sync(0xffffffffu, state == kDone)) break;
+    if (__all_sync(kAll, state == kDone)) break;
 
-    if (state == kDescend) {
-      const KdNodeDev nd = nodes[node];
-      if (nd.dim == static_cast<uint32_t>(D)) {  // leaf
-        pos = nd.cut_or_bucket;
-        end = pos + nd.child_or_size;
-        state = (nd.child_or_size > 0) ? kLeaf : kPop;
-      } else {
-        const uint32_t cd = nd.dim;
-        const float old_off = Pick<D>(off, cd);
-        const float new_off = __fsub_rn(Pick<D>(qv, cd), __uint_as_float(nd.cut_or_bucket));
-        // rd += -old_off * old_off + new_off * new_off   (for the far child)
-        st_val[sp] = __fadd_rn(rd, __fadd_rn(__fmul_rn(-old_off, old_off), __fmul_rn(new_off, new_off)));
-        st_tag[sp] = node;  // far child and offsets are re-derived from the parent when popped
-        ++sp;
-        node = (new_off > 0.f) ? nd.child_or_size : node + 1;  // near child first
+    // ---- phase 1: every descending lane walks down to its leaf ----
+    while (__any_sync(kAll, state == kDescend)) {
+      if (state == kDescend) {
+        const KdNodeDev nd = nodes[node];
+        if (nd.dim == static_cast<uint32_t>(D)) {  // leaf
+          pos = nd.cut_or_bucket;
+          end = pos + nd.child_or_size;
+          state = (nd.child_or_size > 0) ? kLeaf : kPop;
+        } else {
+          const uint32_t cd = nd.dim;
+          const float old_off = Pick<D>(off, cd);
+          const float new_off = __fsub_rn(Pick<D>(qv, cd), __uint_as_float(nd.cut_or_bucket));
+          // rd += -old_off * old_off + new_off * new_off   (for the far child)
+          st_val[sp] = __fadd_rn(rd, __fadd_rn(__fmul_rn(-old_off, old_off), __fmul_rn(new_off, new_off)));
+          st_tag[sp] = node;  // far child and offsets are re-derived from the parent when popped
+          ++sp;
+          node = (new_off > 0.f) ? nd.child_or_size : node + 1;  // near child first
+        }
       }
-    } else if (state == kLeaf) {
-      const int pidx = buckets[pos];
-      const float* pt = cloud + static_cast<size_t>(pidx) * D;
-      float dist = 0.f;
+    }
+
+    // ---- phase 2: every lane at a leaf scores its bucket, point by point ----
+    while (__any_sync(kAll, state == kLeaf)) {
+      if (state == kLeaf) {
+        const int pidx = buckets[pos];
+        const float* pt = cloud + static_cast<size_t>(pidx) * D;
+        float dist = 0.f;
 #pragma unroll
-      for (int j = 0; j < D; ++j) {
-        const float diff = __fsub_rn(qv[j], pt[j]);
-        dist = __fadd_rn(dist, __fmul_rn(diff, diff));
-      }
-      if ((dist <= p.max_radius2) && (dist < head)) {
-        // IndexHeapBruteForceVector::replaceHead: shift while the predecessor is strictly larger
-        int i = kk - 1;
-        for (; i > 0; --i) {
-          const float pv = hv[(i - 1) * kThreads + tid];
-          if (pv > dist) {
-            hv[i * kThreads + tid] = pv;
-            hi[i * kThreads + tid] = hi[(i - 1) * kThreads + tid];
-          } else {
-            break;
+        for (int j = 0; j < D; ++j) {
+          const float diff = __fsub_rn(qv[j], pt[j]);
+          dist = __fadd_rn(dist, __fmul_rn(diff, diff));
+        }
+        if ((dist <= p.max_radius2) && (dist < hv[KK - 1])) {
+          // IndexHeapBruteForceVector::replaceHead: the new entry goes behind every entry that is
+          // not strictly larger; the largest one drops out
+          bool prev_gt = false;  // hv[i - 1] > dist
+          float prev_v = 0.f;
+          int32_t prev_x = 0;
+#pragma unroll
+          for (int i = 0; i < KK; ++i) {
+            const float v = hv[i];
+            const int32_t x = hx[i];
+            const bool gt = v > dist;
+            hv[i] = prev_gt ? prev_v : (gt ? dist : v);
+            hx[i] = prev_gt ? prev_x : (gt ? pidx : x);
+            prev_gt = gt;
+            prev_v = v;
+            prev_x = x;
           }
         }
-        hv[i * kThreads + tid] = dist;
-        hi[i * kThreads + tid] = pidx;
-        head = hv[(kk - 1) * kThreads + tid];
+        if (++pos == end) state = kPop;
       }
-      if (++pos == end) state = kPop;
-    } else if (state == kPop) {
-      if (sp == 0) {
-        // search finished: emit the sorted heap
-        int32_t* oi = out_idx + half_base + static_cast<size_t>(item) * kk;
-        float* ov = out_val + half_base + static_cast<size_t>(item) * kk;
-        for (int j = 0; j < kk; ++j) {
-          oi[j] = hi[j * kThreads + tid];
-          ov[j] = hv[j * kThreads + tid];
-        }
-        state = kIdle;
-      } else {
-        --sp;
-        const uint32_t tag = st_tag[sp];
-        if (tag & kRestoreTag) {
-          Put<D>(off, tag & 0xFFu, st_val[sp]);  // leave the far subtree: restore the offset
+    }
+
+    // ---- phase 3: unwind until a far subtree must be visited (or the search ends) ----
+    while (__any_sync(kAll, state == kPop)) {
+      if (state == kPop) {
+        if (sp == 0) {
+          // search finished: emit the sorted heap
+          int32_t* oi = out_idx + half_base + static_cast<size_t>(item) * kk;
+          float* ov = out_val + half_base + static_cast<size_t>(item) * kk;
+#pragma unroll
+          for (int j = 0; j < KK; ++j) {
+            if (j >= KK - kk) {
+              oi[j - (KK - kk)] = hx[j];
+              ov[j - (KK - kk)] = hv[j];
+            }
+          }
+          state = kIdle;
         } else {
-          const float frd = st_val[sp];
-          if ((frd <= p.max_radius2) && (__fmul_rn(frd, p.max_error2) < head)) {
-            const KdNodeDev nd = nodes[tag];
-            const uint32_t cd = nd.dim;
-            const float new_off = __fsub_rn(Pick<D>(qv, cd), __uint_as_float(nd.cut_or_bucket));
-            st_tag[sp] = kRestoreTag | cd;
-            st_val[sp] = Pick<D>(off, cd);  // old offset (the near subtree restored it)
-            ++sp;
-            Put<D>(off, cd, new_off);
-            node = (new_off > 0.f) ? tag + 1 : nd.child_or_size;  // far child
-            rd = frd;
-            state = kDescend;
+          --sp;
+          const uint32_t tag = st_tag[sp];
+          if (tag & kRestoreTag) {
+            Put<D>(off, tag & 0xFFu, st_val[sp]);  // leave the far subtree: restore the offset
+          } else {
+            const float frd = st_val[sp];
+            if ((frd <= p.max_radius2) && (__fmul_rn(frd, p.max_error2) < hv[KK - 1])) {
+              const KdNodeDev nd = nodes[tag];
+              const uint32_t cd = nd.dim;
+              const float new_off = __fsub_rn(Pick<D>(qv, cd), __uint_as_float(nd.cut_or_bucket));
+              st_tag[sp] = kRestoreTag | cd;
+              st_val[sp] = Pick<D>(off, cd);  // old offset (the near subtree restored it)
+              ++sp;
+              Put<D>(off, cd, new_off);
+              node = (new_off > 0.f) ? tag + 1 : nd.child_or_size;  // far child
+              rd = frd;
+              state = kDescend;
+            }
           }
         }
       }
@@ -256,28 +278,36 @@ multi_sequence_kernel(const int32_t* __restrict__ h_idx, const float* __restrict
   for (int j = emitted; j < num_words; ++j) dst[j] = -1;
 }
 
-template <int D>
-cudaError_t LaunchSearch(const CoarseParams& p, const float* d_q, int64_t n, int kk1, int kk2,
-                         int32_t* h_idx, float* h_val, int sm_count, cudaStream_t stream) {
+template <int D, int KK>
+cudaError_t LaunchSearchK(const CoarseParams& p, const float* d_q, int64_t n, int kk1, int kk2,
+                          int32_t* h_idx, float* h_val, int sm_count, cudaStream_t stream) {
   const uint32_t tree_bytes =
       p.stage_in_smem ? max(p.off_nodes2, p.packed_bytes - p.off_nodes2) : 0u;
-  const int kk_max = max(kk1, kk2);
-  const size_t smem = 2 * sizeof(float) * kk_max * kThreads + tree_bytes;
-  cudaError_t e = cudaFuncSetAttribute(kd_search_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  const size_t smem = tree_bytes;
+  cudaError_t e = cudaFuncSetAttribute(kd_search_kernel<D, KK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        static_cast<int>(smem));
   if (e != cudaSuccess) return e;
   int per_sm = 1;
-  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kd_search_kernel<D>, kThreads, smem);
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kd_search_kernel<D, KK>, kThreads, smem);
   if (e != cudaSuccess) return e;
   if (per_sm < 1) per_sm = 1;
   int64_t blocks_per_half = (static_cast<int64_t>(sm_count) * per_sm) / 2;
   const int64_t needed = (n + kThreads - 1) / kThreads;  // at least one query per lane to start with
   if (blocks_per_half > needed) blocks_per_half = needed;
   if (blocks_per_half < 1) blocks_per_half = 1;
-  kd_search_kernel<D><<<static_cast<unsigned>(2 * blocks_per_half), kThreads, smem, stream>>>(
-      p, d_q, n, kk1, kk2, kk_max, h_idx, h_val);
+  kd_search_kernel<D, KK><<<static_cast<unsigned>(2 * blocks_per_half), kThreads, smem, stream>>>(
+      p, d_q, n, kk1, kk2, h_idx, h_val);
   CountLaunch();
   return cudaGetLastError();
+}
+
+template <int D>
+cudaError_t LaunchSearch(const CoarseParams& p, const float* d_q, int64_t n, int kk1, int kk2,
+                         int32_t* h_idx, float* h_val, int sm_count, cudaStream_t stream) {
+  const int kk_max = max(kk1, kk2);
+  if (kk_max <= 1) return LaunchSearchK<D, 1>(p, d_q, n, kk1, kk2, h_idx, h_val, sm_count, stream);
+  if (kk_max <= 10) return LaunchSearchK<D, 10>(p, d_q, n, kk1, kk2, h_idx, h_val, sm_count, stream);
+  return LaunchSearchK<D, 16>(p, d_q, n, kk1, kk2, h_idx, h_val, sm_count, stream);
 }
 
 }  // namespace
