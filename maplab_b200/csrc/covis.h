@@ -35,6 +35,7 @@ struct CovisArgs {
   double min_time_ns;
   unsigned long long min_verify_matches_num;
   float fraction_best_scores;
+  int group_bits;                // 2^group_bits > number of database keyframes
   int scoring;                   // 0 accumulation, 1 probabilistic (scoring.h)
   long long num_db_descriptors;  // whole database (all shards)
   mlc_match* scratch;  // grid * (4096 | 8192) records

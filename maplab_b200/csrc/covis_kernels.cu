@@ -110,7 +110,7 @@ __device__ float ProbabilisticScore(unsigned votes, unsigned total, unsigned num
 }
 
 template <int MAXM, int THREADS>
-__global__ void __launch_bounds__(THREADS) covis_kernel(CovisArgs a) {
+__global__ void __launch_bounds__(THREADS, (THREADS <= 512 ? 2 : 1)) covis_kernel(CovisArgs a) {
   constexpr int IPT = MAXM / THREADS;
   constexpr int SLOT_BITS = (MAXM == 8192) ? 13 : 12;
   constexpr unsigned long long SLOT_MASK = (1ull << SLOT_BITS) - 1;
@@ -175,7 +175,8 @@ __global__ void __launch_bounds__(THREADS) covis_kernel(CovisArgs a) {
     } else if (R > 0) {
       // ---------------------------------------------------------------- A: sort by group, votes
       const int p2 = NextPow2(R);
-      for (int i = tid; i < p2; i += THREADS) {
+      const int fill = (!a.by_vertex && p2 > 1024) ? MAXM : p2;
+      for (int i = tid; i < fill; i += THREADS) {
         unsigned long long key = ~0ull;
         if (i < R) {
           const long long g = a.by_vertex ? rec[i].db_vertex : static_cast<long long>(rec[i].db_keyframe);
@@ -184,7 +185,26 @@ __global__ void __launch_bounds__(THREADS) covis_kernel(CovisArgs a) {
         s.keys[i] = key;
       }
       __syncthreads();
-      BitonicSort<THREADS>(s.keys, p2);
+      if (!a.by_vertex && p2 > 1024) {
+        // large frame: stable LSD radix sort over the keyframe-number bits only (the slot bits are
+        // already ascending in the blocked arrangement), ~5x fewer shared-memory passes than the
+        // bitonic network; its scratch aliases a3..a8, which are dead until stage B
+        typedef cub::BlockRadixSort<unsigned long long, THREADS, IPT> RadixSort;
+        static_assert(sizeof(typename RadixSort::TempStorage) + 16 <= 6 * sizeof(s.a3), "radix scratch");
+        typename RadixSort::TempStorage& radix_tmp = *reinterpret_cast<typename RadixSort::TempStorage*>(
+            (reinterpret_cast<uintptr_t>(s.a3) + 15) & ~static_cast<uintptr_t>(15));
+        unsigned long long kreg[IPT];
+#pragma unroll
+        for (int i = 0; i < IPT; ++i) kreg[i] = s.keys[tid * IPT + i];  // MAXM >= p2; pad = ~0
+        __syncthreads();
+        RadixSort(radix_tmp).Sort(kreg, SLOT_BITS, SLOT_BITS + a.group_bits);
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < IPT; ++i) s.keys[tid * IPT + i] = kreg[i];
+        __syncthreads();
+      } else {
+        BitonicSort<THREADS>(s.keys, p2);
+      }
       // candidate rank b of every match (a1), first sorted position of every candidate (a2)
       const int Cn = FlagScan<THREADS, IPT>(
           R, [&](int i) { return i == 0 || (s.keys[i] >> SLOT_BITS) != (s.keys[i - 1] >> SLOT_BITS); },

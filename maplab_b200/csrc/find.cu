@@ -175,6 +175,8 @@ bool Detector::FindOnDevice(const mlc_frame* frames, int64_t num_frames, const i
   a.min_verify_matches_num = s_.min_verify_matches_num;
   a.fraction_best_scores = s_.fraction_best_scores;
   a.scoring = s_.scoring;
+  a.group_bits = 1;
+  while ((1ull << a.group_bits) <= keyframes_.size()) ++a.group_bits;
   a.num_db_descriptors = NumDescriptors();
   a.scratch = b_scr.as<mlc_match>();
   a.out_matches = b_out.as<mlc_match>();
