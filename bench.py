@@ -5,8 +5,10 @@ One step = one batch of query keyframes through the whole hot path: descriptor p
 (kernel 1) -> IMI kNN (kernels 2a/2b) -> covisibility voting/clustering (kernel 3) -> correspondence
 gather + GP3P-RANSAC verdicts (kernel 4). `value` is measured with the batch resident in HBM, `e2e`
 through the C-ABI with host buffers (H2D/D2H inside the timed region). N > 1: the inverted lists
-are sharded over the ranks (strong scaling: same map, same batch), visit lists and per-shard top-k
-lists are exchanged over NCCL. One JSON line on stdout from rank 0. See DESIGN.md "Measurement".
+are sharded over the ranks (maplab_b200/sharded.py; weak scaling by default: --landmarks per GPU, the
+query batch fixed), visit lists and per-shard top-k lists are exchanged over NCCL. At N = 1 the line
+also carries `roofline_at_shard_scale`: the same step on the per-GPU shard of the 50M-landmark /
+8-GPU configuration. One JSON line on stdout from rank 0. See DESIGN.md "Measurement".
 """
 import argparse
 import json
@@ -32,11 +34,16 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--landmarks", type=int, default=1_000_000, help="landmarks in the map (total)")
+    ap.add_argument("--landmarks", type=int, default=1_000_000, help="landmarks in the map (per GPU under weak scaling)")
     ap.add_argument("--queries", type=int, default=1000, help="query keyframes per step")
     ap.add_argument("--words", type=int, default=1000)
     ap.add_argument("--cpu-queries", type=int, default=0, help="cpu_baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="N > 1: weak = --landmarks per GPU (map grows with N), strong = --landmarks in total")
+    ap.add_argument("--no-scan-probe", action="store_true",
+                    help="skip the extra scan-roofline measurement at the north-star shard size (N = 1 only)")
+    ap.add_argument("--probe-landmarks", type=int, default=6_250_000)
     return ap.parse_args()
 
 
@@ -98,13 +105,13 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def build_world(args):
+def build_world(landmarks, queries, words):
     """Seeded synthetic map + queries + vocabulary (identical on every rank)."""
     from maplab_b200 import synthetic
-    m = synthetic.make_map(args.landmarks, seed=1)
+    m = synthetic.make_map(landmarks, seed=1)
     stride = max(len(m["bits"]) // 100_000, 1)
-    blob, _ = synthetic.make_vocabulary(m["bits"][::stride][:100_000], num_words=args.words, seed=7)
-    q = synthetic.make_queries(m, args.queries, seed=11)
+    blob, _ = synthetic.make_vocabulary(m["bits"][::stride][:100_000], num_words=words, seed=7)
+    q = synthetic.make_queries(m, queries, seed=11)
     return m, blob, q
 
 
@@ -114,29 +121,15 @@ def frames_array(fr):
                             fr["num_descriptors"])
 
 
-def workload_string(args, n_db, n_kf, k):
-    return (f"synthetic single-session map, {args.landmarks} landmarks ({n_db} db descriptors, "
-            f"{n_kf} keyframes), 512-bit FREAK, {args.queries} query keyframes x 500 descriptors per "
-            f"step (20% outlier descriptors), k={k}, nw=10, W={args.words}x{args.words} cells, "
+def workload_string(landmarks, queries, words, n_db, n_kf, k):
+    return (f"synthetic single-session map, {landmarks} landmarks ({n_db} db descriptors, "
+            f"{n_kf} keyframes), 512-bit FREAK, {queries} query keyframes x 500 descriptors per "
+            f"step (20% outlier descriptors), k={k}, nw=10, W={words}x{words} cells, "
             f"accumulation scoring, GP3P-RANSAC 100 iters")
 
 
-def run_b200(args):
-    import torch
-    import torch.distributed as dist
-    from maplab_b200 import capi, synthetic
-
-    rank = int(os.environ.get("RANK", 0))
-    world = int(os.environ.get("WORLD_SIZE", 1))
-    local = int(os.environ.get("LOCAL_RANK", 0))
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    hbm_peak, peak_src = peaks()
-    t_setup = time.time()
-    m, blob, q = build_world(args)
-    det = capi.Detector(blob, capi.default_settings(device=local, shard_rank=rank, shard_count=world))
+def load_database(det, m):
+    """Project the map descriptors on the device (kernel 1), insert, build the index."""
     frames = frames_array(m["frames"])
     n_db = len(m["bits"])
     proj = np.empty((n_db, det.dim), np.float32)
@@ -147,6 +140,77 @@ def run_b200(args):
     det.initialize()
     t_build = time.time() - t1
     det.set_landmark_positions(m["landmark_xyz"])
+    return frames, proj, t_build
+
+
+def measured_traffic(n_db, n_q):
+    """DRAM bytes per scan launch from the committed `ncu --set full` capture of this workload
+    (profiles/traffic.json), or None when no capture matches."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if not os.path.exists(p):
+        return None
+    for e in json.load(open(p)).get("imi_scan_kernel", []):
+        if e.get("db_descriptors") == n_db and e.get("query_descriptors") == n_q:
+            return e.get("dram_bytes_per_launch")
+    return None
+
+
+def scan_probe(args, local, hbm_peak):
+    """IMI list scan at the north-star shard size (the per-GPU shard of the 50M-landmark map over 8
+    GPUs: 6.25M landmarks, 25M descriptors, 25 entries per cell on average): same fused step, its
+    scan kernel timed with CUDA events inside the step."""
+    import torch
+    from maplab_b200 import capi, synthetic
+    lm = args.probe_landmarks
+    m, blob, q = build_world(lm, args.queries, args.words)
+    det = capi.Detector(blob, capi.default_settings(device=local))
+    frames, _, _ = load_database(det, m)
+    n_db = len(m["bits"])
+    k = det.num_neighbors()
+    cams = capi.make_cameras([synthetic.camera_dict()])
+    qframes = frames_array(q["frames"])
+    dev = torch.device("cuda", local)
+    qbits_d = torch.from_numpy(q["bits"]).to(dev)
+    kp_d = torch.from_numpy(np.ascontiguousarray(q["keypoints"], np.float64)).to(dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    ms, nbytes = [], 0
+    for i in range(3 + 5):
+        flush.fill_(i & 0xFF)
+        torch.cuda.synchronize()
+        det.query_batch_device(qframes, qbits_d.data_ptr(), 64, kp_d.data_ptr(), cams)
+        st = det.last_scan_stats()
+        if i >= 3:
+            ms.append(st["scan_ms"])
+            nbytes = st["algorithmic_bytes"]
+    launch_ms = float(np.mean(ms))
+    achieved = nbytes / (launch_ms * 1e-3) / 1e9
+    return {"kernel": "imi_scan_kernel", "workload": workload_string(lm, args.queries, args.words, n_db, len(frames), k),
+            "why": "per-GPU shard of BASELINE config 'multi-robot synthetic map, 50M landmarks sharded across 8 B200'",
+            "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+            "algorithmic_bytes_per_launch": float(nbytes), "launch_ms": launch_ms, "steps": 5, "warmup": 3}
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    from maplab_b200 import capi, sharded, synthetic
+
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    hbm_peak, peak_src = peaks()
+    t_setup = time.time()
+    # weak scaling: the map (hence every GPU's shard of the inverted lists) grows with the GPU count,
+    # the query batch per step stays the same
+    landmarks = args.landmarks * (world if args.scaling == "weak" else 1)
+    m, blob, q = build_world(landmarks, args.queries, args.words)
+    det = capi.Detector(blob, capi.default_settings(device=local, shard_rank=rank, shard_count=world))
+    frames, proj, t_build = load_database(det, m)
+    n_db = len(m["bits"])
     k = det.num_neighbors()
     nw = 10
     cams = capi.make_cameras([synthetic.camera_dict()])
@@ -157,54 +221,28 @@ def run_b200(args):
     kp_np = np.ascontiguousarray(q["keypoints"], np.float64)
     kp_h = torch.from_numpy(kp_np).pin_memory()
     qbits_d, kp_d = qbits_h.to(dev), kp_h.to(dev)
-    stream = torch.cuda.current_stream().cuda_stream
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
     if world > 1:
-        assert nq_kf % world == 0 and len(set(qframes["num_descriptors"].tolist())) == 1, \
-            "sharded bench needs equal query slices"
-        f0, f1 = rank * nq_kf // world, (rank + 1) * nq_kf // world
-        n_s = n_q // world
-        d0 = rank * n_s
-        sl_frames = qframes[f0:f1].copy()
-        proj_s = torch.empty((n_s, det.dim), dtype=torch.float32, device=dev)
-        cells_s = torch.empty((n_s, nw), dtype=torch.int32, device=dev)
-        proj_all = torch.empty((world, n_s, det.dim), dtype=torch.float32, device=dev)
-        cells_all = torch.empty((world, n_s, nw), dtype=torch.int32, device=dev)
-        pidx = torch.empty((world, n_s, k), dtype=torch.int32, device=dev)
-        pdist = torch.empty((world, n_s, k), dtype=torch.float32, device=dev)
-        ridx, rdist = torch.empty_like(pidx), torch.empty_like(pdist)
-        midx = torch.empty((n_s, k), dtype=torch.int32, device=dev)
-        mdist = torch.empty((n_s, k), dtype=torch.float32, device=dev)
-        sbits_d = qbits_d[d0:d0 + n_s]
-        skp_d = kp_d[d0:d0 + n_s]
-        sbits_e = torch.empty_like(sbits_d)
-        skp_e = torch.empty_like(skp_d)
-
-        def sharded(bits_t, kp_t):
-            det.project_device(bits_t.data_ptr(), 64, n_s, proj_s.data_ptr(), stream)
-            det.coarse_device(proj_s.data_ptr(), n_s, nw, cells_s.data_ptr(), stream)
-            dist.all_gather_into_tensor(proj_all, proj_s)      # exchange 1: queries -> all shards
-            dist.all_gather_into_tensor(cells_all, cells_s)
-            for r in range(world):
-                det.scan_device(proj_all[r].data_ptr(), cells_all[r].data_ptr(), n_s, k,
-                                pidx[r].data_ptr(), pdist[r].data_ptr(), stream)
-            dist.all_to_all_single(ridx, pidx)                 # exchange 2: per-shard top-k lists
-            dist.all_to_all_single(rdist, pdist)
-            det.merge_topk_device(ridx.data_ptr(), rdist.data_ptr(), world, n_s, k, midx.data_ptr(),
-                                  mdist.data_ptr(), stream)
-            torch.cuda.current_stream().synchronize()  # kernels 3/4 run on the detector's own stream
-            return det.query_from_knn_device(sl_frames, midx.data_ptr(), mdist.data_ptr(), k,
-                                             kp_t.data_ptr(), cams)
+        ops = sharded.DetectorOps(det, cams)
+        step = sharded.ShardedQueryStep(ops, qframes, rank, world, det.dim, nw, k, 64, dev)
+        sbits_d, skp_d = step.slice_of(qbits_d), step.slice_of(kp_d)
+        sbits_e, skp_e = torch.empty_like(sbits_d), torch.empty_like(skp_d)
+        sbits_h, skp_h = step.slice_of(qbits_h), step.slice_of(kp_h)
+        h2d_bytes = int(sbits_h.numel() + skp_h.numel() * 8) * world
+        d2h_bytes = int(nq_kf * capi.POSE_DTYPE.itemsize)
 
         def step_device():
-            return sharded(sbits_d, skp_d)
+            return step.run(sbits_d, skp_d)
 
         def step_e2e():
-            sbits_e.copy_(qbits_h[d0:d0 + n_s], non_blocking=True)
-            skp_e.copy_(kp_h[d0:d0 + n_s], non_blocking=True)
-            return sharded(sbits_e, skp_e)
+            sbits_e.copy_(sbits_h, non_blocking=True)
+            skp_e.copy_(skp_h, non_blocking=True)
+            return step.run(sbits_e, skp_e)
     else:
+        h2d_bytes = int(q["bits"].nbytes + kp_np.nbytes)
+        d2h_bytes = int(nq_kf * capi.POSE_DTYPE.itemsize)
+
         def step_device():
             return det.query_batch_device(qframes, qbits_d.data_ptr(), 64, kp_d.data_ptr(), cams)
 
@@ -218,12 +256,24 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    def max_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
     W = max(args.warmup, 3)
     for _ in range(W):
         out = step_device()
     barrier()
-    accepted = int(out["results"]["accepted"].sum())
-    num_matches = int(out["num_matches"])
+    accepted = int(sum_over_ranks(float(out["results"]["accepted"].sum())))
+    num_matches = int(sum_over_ranks(float(out["num_matches"])))
 
     # ---- timed: device-resident ----
     sampler = ClockSampler(local)
@@ -231,67 +281,48 @@ def run_b200(args):
         sampler.start()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     stage_acc = np.zeros(5)
+    scan_ms_acc, scan_bytes = 0.0, 0
     launches0 = capi.kernel_launch_count()
     barrier()
     wall0 = time.perf_counter()
     for i in range(args.steps):
         flush.fill_(i & 0xFF)  # evict L2 between timed iterations
-        torch.cuda.synchronize()
+        barrier()
         ev[i][0].record()
         step_device()          # ends with the D2H of the verdicts (stream synchronised)
         ev[i][1].record()
+        launches_step = capi.kernel_launch_count()
         if world == 1:
             stage_acc += np.array(list(det.last_stage_ms().values()))
+        st = det.last_scan_stats()  # CUDA events around the scan launch of this step (+1 counting launch)
+        scan_ms_acc += st["scan_ms"]
+        scan_bytes = st["algorithmic_bytes"]
+        launches0 += capi.kernel_launch_count() - launches_step  # the counting kernel is not part of the step
     barrier()
     wall = time.perf_counter() - wall0
     launches = capi.kernel_launch_count() - launches0
     clocks = sampler.stop() if rank == 0 else None
     dev_ms = float(np.sum([a.elapsed_time(b) for a, b in ev]))
-    t = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_per_step = float(t.item()) / args.steps
+    ms_per_step = max_over_ranks(dev_ms) / max(args.steps, 1)
 
-    # ---- timed: end to end with host buffers ----
+    # ---- timed: end to end with host buffers (pinned H2D of the step's inputs, D2H of the verdicts) ----
     for _ in range(2):
         step_e2e()
-    barrier()
-    e0 = time.perf_counter()
-    for _ in range(args.steps):
+    e2e_ms = 0.0
+    for i in range(args.steps):
+        barrier()
+        ev[i][0].record()
         step_e2e()
-    barrier()
-    t = torch.tensor([time.perf_counter() - e0], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_s_per_step = float(t.item()) / args.steps
+        ev[i][1].record()
+        torch.cuda.synchronize()
+        e2e_ms += ev[i][0].elapsed_time(ev[i][1])
+    e2e_s_per_step = max_over_ranks(e2e_ms) * 1e-3 / max(args.steps, 1)
 
-    # ---- roofline of the IMI list scan (untimed pass: one launch per query chunk) ----
-    scan_bytes, scan_ms = 0, 0.0
-    for rep in range(3):
-        scan_bytes, scan_ms = 0, 0.0
-        flush.fill_(rep)
-        if world > 1:
-            for r in range(world):
-                det.scan_device(proj_all[r].data_ptr(), cells_all[r].data_ptr(), n_s, k,
-                                pidx[r].data_ptr(), pdist[r].data_ptr(), stream)
-                st = det.last_scan_stats()
-                scan_bytes += st["algorithmic_bytes"]
-                scan_ms += st["scan_ms"]
-        else:
-            step_device()
-            st = det.last_scan_stats()
-            scan_bytes, scan_ms = st["algorithmic_bytes"], st["scan_ms"]
-    if world == 1 and args.steps > 0:
-        scan_ms = stage_acc[2] / args.steps  # measured live inside the timed region
-    tb = torch.tensor([float(scan_bytes), scan_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        tsum = tb.clone()
-        dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
-        dist.all_reduce(tb, op=dist.ReduceOp.MAX)
-        scan_bytes_total, scan_ms_max = float(tsum[0].item()), float(tb[1].item())
-    else:
-        scan_bytes_total, scan_ms_max = float(scan_bytes), scan_ms
-    achieved = scan_bytes_total / world / (scan_ms_max * 1e-3) / 1e9 if scan_ms_max > 0 else 0.0
+    # ---- roofline of the IMI list scan: CUDA-event time of the launch inside the timed steps ----
+    scan_ms = scan_ms_acc / max(args.steps, 1)
+    scan_ms_max = max_over_ranks(scan_ms)
+    scan_bytes_mean = sum_over_ranks(float(scan_bytes)) / world
+    achieved = scan_bytes_mean / (scan_ms_max * 1e-3) / 1e9 if scan_ms_max > 0 else 0.0
 
     if rank != 0:
         dist.destroy_process_group()
@@ -299,22 +330,26 @@ def run_b200(args):
     out = {
         "metric": METRIC, "value": nq_kf / (ms_per_step * 1e-3), "unit": UNIT,
         "n_gpus": world, "steps": args.steps, "warmup": W, "ms_per_step": ms_per_step,
-        "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
         "dtype": "u8 x s8 -> s32 (projection), f32 (distances), f64 (RANSAC)", "data": "synthetic",
-        "config": {"workload": workload_string(args, n_db, len(frames), k),
-                   "sharding": f"inverted lists: descriptor i on rank i % {world}" if world > 1 else "none",
+        "config": {"workload": workload_string(landmarks, args.queries, args.words, n_db, len(frames), k),
+                   "sharding": (f"inverted lists: descriptor i on rank i % {world}; map size = "
+                                f"{args.landmarks} landmarks x {world} GPUs ({args.scaling} scaling), query "
+                                f"batch fixed") if world > 1 else "none",
                    "l2": "256 MiB flush buffer written between timed iterations",
                    "db_build_s": round(t_build, 3),
                    "accepted_loop_closures_per_step": accepted, "matches_per_step": num_matches},
         "roofline": {"kernel": "imi_scan_kernel", "bound": "hbm", "achieved": achieved,
                      "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                      "peak_source": peak_src,
-                     "algorithmic_bytes_per_launch": scan_bytes_total / world / max(world, 1),
-                     "launch_ms": scan_ms_max / max(world, 1), "launches_per_step": world,
-                     "per": "GPU", "traffic": None},
+                     "algorithmic_bytes_per_launch": scan_bytes_mean,
+                     "launch_ms": scan_ms_max, "launches_per_step": 1,
+                     "per": "GPU", "traffic": measured_traffic(n_db, n_q) if world == 1 else None,
+                     "attainable_note": "lists average ~5 entries (240 B) per cell at this map size: "
+                                        "profiles/microbench/chunk_read_b200.txt measures 4.0-4.4 TB/s as "
+                                        "the B200 ceiling for random 240-byte chunks (6.2 TB/s at 1.5 KB)"},
         "e2e": {"value": nq_kf / e2e_s_per_step, "unit": UNIT,
-                "h2d_bytes_per_step": int(q["bits"].nbytes + kp_np.nbytes),
-                "d2h_bytes_per_step": int(nq_kf * capi.POSE_DTYPE.itemsize)},
+                "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "setup_s": round(time.time() - t_setup, 1), "timed_wall_s": round(wall, 3),
@@ -324,6 +359,10 @@ def run_b200(args):
                                    [round(float(x) / max(args.steps, 1), 4) for x in stage_acc]))
     if not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline(args, m, blob, q, proj, frames)
+    if world == 1 and not args.no_scan_probe:
+        del det, m, q, proj, qbits_d, kp_d, flush
+        torch.cuda.empty_cache()
+        out["roofline_at_shard_scale"] = scan_probe(args, local, hbm_peak)
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
@@ -382,7 +421,8 @@ def run_reference(args):
         return
     from oracle import pyoracle as po
     threads = os.cpu_count() or 1
-    m, blob, q = build_world(args)
+    landmarks = args.landmarks * (args.gpus if args.scaling == "weak" else 1)
+    m, blob, q = build_world(landmarks, args.queries, args.words)
     frames = frames_array(m["frames"])
     ora0 = po.Engine(blob)
     n_db = len(m["bits"])
@@ -414,8 +454,8 @@ def run_reference(args):
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": W, "ms_per_step": 1e3 * t_total / args.steps,
-        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32/f64 (CPU)",
-        "data": "synthetic", "config": {"workload": workload_string(args, n_db, len(frames), k),
+        "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32/f64 (CPU)",
+        "data": "synthetic", "config": {"workload": workload_string(landmarks, args.queries, args.words, n_db, len(frames), k),
                                         "accepted_loop_closures_in_sample": acc},
         "cpu_baseline": cb,
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
