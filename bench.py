@@ -363,7 +363,7 @@ def run_b200(args):
         del det, m, q, proj, qbits_d, kp_d, flush
         torch.cuda.empty_cache()
         out["roofline_at_shard_scale"] = scan_probe(args, local, hbm_peak)
-    print(json.dumps(out))
+    print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
@@ -462,6 +462,11 @@ def run_reference(args):
 
 
 if __name__ == "__main__":
+    # the contract is ONE JSON line on stdout: libraries (NCCL prints its version banner there) get
+    # stderr instead, the result line goes to the real stdout
+    _real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    sys.stdout = _real_stdout
     a = parse_args()
     if a.impl == "reference":
         run_reference(a)

@@ -47,9 +47,10 @@ enum {
 constexpr int N8 = 8;
 constexpr int kWarpsPerBlock = 4;
 constexpr int kHyp = 16;      // hypothesis slots per problem
-constexpr int kHypFirst = 8;  // speculated in the first round (k is still unknown)
+constexpr int kHypFirst = 12; // speculated in the first round (k is still unknown) when the batch fills the GPU
 
 struct RansacArgs {
+  int first_hyp;                // hypotheses speculated per problem in the first round
   int64_t num_problems;
   const int64_t* offsets;
   const double* keypoints;      // 2 per correspondence
@@ -397,14 +398,14 @@ __global__ void __launch_bounds__(128) ransac_init_kernel(RansacArgs a, ProblemS
 }
 
 // Draw the next samples of every running problem (persistent partial Fisher-Yates). First round:
-// kHypFirst samples; later rounds: as many as the adaptive bound k still asks for (<= kHyp).
+// a.first_hyp samples; later rounds: as many as the adaptive bound k still asks for (<= kHyp).
 __global__ void __launch_bounds__(128) ransac_sample_kernel(RansacArgs a, ProblemState* st, Hypothesis* hyp) {
   const int64_t pi = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
   if (pi >= a.num_problems) return;
   ProblemState& s = st[pi];
   Hypothesis* h = hyp + pi * kHyp;
   const int max_skip = a.max_iterations * 10;
-  int want = kHypFirst;
+  int want = a.first_hyp;
   if (s.stream_pos > 0) {
     const double need = ceil(s.k - static_cast<double>(s.iterations));
     want = need >= static_cast<double>(kHyp) ? kHyp : (need <= 1.0 ? 1 : static_cast<int>(need));
@@ -1038,16 +1039,25 @@ bool Detector::RansacOnDevice(const mlc_ransac_settings& rs, const mlc_camera* c
   if (!Cuda(cudaFuncSetAttribute(gp3p_eliminate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  static_cast<int>(smem)), "ransac smem", err))
     return false;
-  const unsigned warp_blocks = static_cast<unsigned>((num_problems * 32 + 127) / 128);
-  const unsigned thread_blocks = static_cast<unsigned>((num_problems + 127) / 128);
-  ransac_init_kernel<<<warp_blocks, 128, 0, stream_>>>(a, d_state);
-  CountLaunch();
-  const int max_rounds = 11 * rs.num_ransac_iters + 4;  // >= one consumed sample per round
   int elim_per_sm = 4;  // resident CTAs per SM: bounded by the slot arrays in shared memory
   if (!Cuda(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&elim_per_sm, gp3p_eliminate_kernel,
                                                           kWarpsPerBlock * 32, smem), "ransac occupancy", err))
     return false;
   if (elim_per_sm < 1) elim_per_sm = 1;
+  // First round: k is unknown, so speculation depth trades wasted hypotheses against one more
+  // latency-bound round. A batch that does not fill the resident hypothesis slots of the
+  // elimination kernel speculates the full kHyp for free.
+  const int64_t resident = static_cast<int64_t>(sm_count_) * elim_per_sm * kWarpsPerBlock;
+  a.first_hyp = (num_problems * kHyp <= resident + resident / 2) ? kHyp : kHypFirst;
+  if (const char* env = getenv("MLC_RANSAC_FIRST_HYP")) {
+    const int v = atoi(env);
+    if (v >= 1 && v <= kHyp) a.first_hyp = v;
+  }
+  const unsigned warp_blocks = static_cast<unsigned>((num_problems * 32 + 127) / 128);
+  const unsigned thread_blocks = static_cast<unsigned>((num_problems + 127) / 128);
+  ransac_init_kernel<<<warp_blocks, 128, 0, stream_>>>(a, d_state);
+  CountLaunch();
+  const int max_rounds = 11 * rs.num_ransac_iters + 4;  // >= one consumed sample per round
   const unsigned elim_blocks = static_cast<unsigned>(std::min<int64_t>(
       (num_hyp + kWarpsPerBlock - 1) / kWarpsPerBlock, static_cast<int64_t>(sm_count_) * elim_per_sm));
   for (int round = 0; round < max_rounds; ++round) {
