@@ -35,6 +35,9 @@ Detector::~Detector() {
   if (ev1_) cudaEventDestroy(ev1_);
   for (cudaEvent_t e : ev_stage_)
     if (e) cudaEventDestroy(e);
+  for (cudaEvent_t e : ev_copy_)
+    if (e) cudaEventDestroy(e);
+  if (copy_stream_) cudaStreamDestroy(copy_stream_);
   if (stream_) cudaStreamDestroy(stream_);
 }
 
@@ -77,6 +80,10 @@ bool Detector::Create(const mlc_settings& s, const void* blob, size_t size, std:
   sm_count_ = prop.multiProcessorCount;
   if (!Cuda(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking), "cudaStreamCreate", err))
     return false;
+  if (!Cuda(cudaStreamCreateWithFlags(&copy_stream_, cudaStreamNonBlocking), "cudaStreamCreate", err))
+    return false;
+  for (cudaEvent_t& e : ev_copy_)
+    if (!Cuda(cudaEventCreateWithFlags(&e, cudaEventDisableTiming), "cudaEventCreate", err)) return false;
   if (!Cuda(cudaEventCreate(&ev0_), "cudaEventCreate", err)) return false;
   if (!Cuda(cudaEventCreate(&ev1_), "cudaEventCreate", err)) return false;
   for (cudaEvent_t& e : ev_stage_)

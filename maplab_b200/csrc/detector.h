@@ -130,6 +130,11 @@ class Detector {
   KdTreeHost tree1_, tree2_;
   int device_ = 0, sm_count_ = 148;
   cudaStream_t stream_ = nullptr;
+  // host-buffer queries: the H2D copies run on their own stream in chunks, so that projection and
+  // coarse search of chunk i overlap the copy of chunk i+1
+  cudaStream_t copy_stream_ = nullptr;
+  static constexpr int kCopyChunks = 4;
+  cudaEvent_t ev_copy_[kCopyChunks + 1] = {nullptr, nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t ev0_ = nullptr, ev1_ = nullptr;
   cudaEvent_t ev_stage_[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   bool stage_valid_ = false;

@@ -307,13 +307,32 @@ bool Detector::QueryBatch(const mlc_frame* frames, int64_t num_frames, const uin
     return false;
   const uint8_t* d_bits = bits;
   const double* d_kp = keypoints;
+  // Host buffers: copy in chunks on copy_stream_ (bits first, keypoints — needed only by kernel 4 —
+  // last); stream_ waits for chunk i right before it projects / coarse-searches it, so the PCIe
+  // transfer of the later chunks hides behind kernels 1 and 2a of the earlier ones.
+  const int chunks = (!inputs_on_device && n >= 65536) ? kCopyChunks : 1;
+  const int64_t per_chunk = (n + chunks - 1) / chunks;
   if (!inputs_on_device && n > 0) {
     const size_t bb = static_cast<size_t>(n) * bytes_per_desc;
     if (!Cuda(d_bits_.Reserve(bb), "alloc", err) || !Cuda(d_query_[0].Reserve(sizeof(double) * 2 * n), "alloc", err))
       return false;
-    if (!Cuda(cudaMemcpyAsync(d_bits_.p, bits, bb, cudaMemcpyHostToDevice, stream_), "H2D bits", err) ||
-        !Cuda(cudaMemcpyAsync(d_query_[0].p, keypoints, sizeof(double) * 2 * n, cudaMemcpyHostToDevice, stream_),
-              "H2D keypoints", err))
+    // buffers of the previous call may still be in use on stream_ (never across a completed call,
+    // every call ends synchronised) — the copy stream starts after everything enqueued so far
+    if (!Cuda(cudaEventRecord(ev_copy_[kCopyChunks], stream_), "event", err) ||
+        !Cuda(cudaStreamWaitEvent(copy_stream_, ev_copy_[kCopyChunks], 0), "wait", err))
+      return false;
+    for (int c = 0; c < chunks; ++c) {
+      const int64_t s0 = c * per_chunk, cnt = std::min<int64_t>(per_chunk, n - s0);
+      if (cnt <= 0) break;
+      if (!Cuda(cudaMemcpyAsync(d_bits_.as<uint8_t>() + s0 * bytes_per_desc, bits + s0 * bytes_per_desc,
+                                static_cast<size_t>(cnt) * bytes_per_desc, cudaMemcpyHostToDevice, copy_stream_),
+                "H2D bits", err) ||
+          !Cuda(cudaEventRecord(ev_copy_[c], copy_stream_), "event", err))
+        return false;
+    }
+    if (!Cuda(cudaMemcpyAsync(d_query_[0].p, keypoints, sizeof(double) * 2 * n, cudaMemcpyHostToDevice, copy_stream_),
+              "H2D keypoints", err) ||
+        !Cuda(cudaEventRecord(ev_copy_[kCopyChunks], copy_stream_), "event", err))
       return false;
     d_bits = d_bits_.as<uint8_t>();
     d_kp = d_query_[0].as<double>();
@@ -322,13 +341,22 @@ bool Detector::QueryBatch(const mlc_frame* frames, int64_t num_frames, const uin
   cudaEventRecord(ev_stage_[0], stream_);
   if (n > 0) {
     const int nw = s_.num_closest_words;
-    if (!ProjectDevice(d_bits, bytes_per_desc, n, d_q_.as<float>(), stream_, err)) return false;
-    cudaEventRecord(ev_stage_[1], stream_);
     if (!Cuda(d_cells_.Reserve(static_cast<size_t>(n) * nw * 4), "alloc visit list", err)) return false;
-    if (!CoarseDevice(d_q_.as<float>(), n, nw, d_cells_.as<int32_t>(), stream_, err)) return false;
+    for (int c = 0; c < chunks; ++c) {
+      const int64_t s0 = c * per_chunk, cnt = std::min<int64_t>(per_chunk, n - s0);
+      if (cnt <= 0) break;
+      if (!inputs_on_device && !Cuda(cudaStreamWaitEvent(stream_, ev_copy_[c], 0), "wait", err)) return false;
+      if (!ProjectDevice(d_bits + s0 * bytes_per_desc, bytes_per_desc, cnt, d_q_.as<float>() + s0 * dim(), stream_, err))
+        return false;
+      if (c == chunks - 1) cudaEventRecord(ev_stage_[1], stream_);
+      if (!CoarseDevice(d_q_.as<float>() + s0 * dim(), cnt, nw, d_cells_.as<int32_t>() + s0 * nw, stream_, err))
+        return false;
+    }
     cudaEventRecord(ev_stage_[2], stream_);
     if (!ScanDevice(d_q_.as<float>(), d_cells_.as<int32_t>(), n, k, d_idx_.as<int32_t>(),
                     d_dist_.as<float>(), stream_, err))
+      return false;
+    if (!inputs_on_device && !Cuda(cudaStreamWaitEvent(stream_, ev_copy_[kCopyChunks], 0), "wait", err))
       return false;
   } else {
     cudaEventRecord(ev_stage_[1], stream_);

@@ -100,3 +100,23 @@ def test_fused_query_empty_and_no_closure():
     _compare(out, exp, fr)
     assert out["results"]["accepted"].tolist() == [0, 0]
     assert out["results"]["iterations"][1] == 0  # 3 descriptors: below lc_min_inlier_count, no RANSAC
+
+
+def test_large_host_batch_chunked_copies_equal_device_path():
+    # >= 65536 query descriptors: mlc_query_batch copies the host buffers in chunks on a second
+    # stream, overlapped with kernels 1 / 2a; results must equal the device-resident path
+    import torch
+    m, q, det, _ = _setup(num_queries=136, num_nearest_neighbors=6)
+    cams = capi.make_cameras([synthetic.camera_dict()])
+    qframes = frames_of(q["frames"])
+    assert int(qframes["num_descriptors"].sum()) >= 65536
+    kp = np.ascontiguousarray(q["keypoints"], np.float64)
+    host = det.query_batch(qframes, q["bits"], kp, cams, want_matches=True)
+    bits_d = torch.from_numpy(q["bits"]).cuda()
+    kp_d = torch.from_numpy(kp).cuda()
+    devr = det.query_batch_device(qframes, bits_d.data_ptr(), q["bits"].shape[1], kp_d.data_ptr(), cams,
+                                  want_matches=True)
+    assert host["results"].tobytes() == devr["results"].tobytes()
+    assert np.array_equal(host["offsets"], devr["offsets"])
+    assert host["matches"].tobytes() == devr["matches"].tobytes()
+    assert host["results"]["accepted"].sum() > 60
