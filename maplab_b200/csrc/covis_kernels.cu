@@ -210,7 +210,9 @@ __global__ void __launch_bounds__(THREADS, (THREADS <= 512 ? 2 : 1)) covis_kerne
           R, [&](int i) { return i == 0 || (s.keys[i] >> SLOT_BITS) != (s.keys[i - 1] >> SLOT_BITS); },
           [&](int i, int pos, bool f) {
             const int b = f ? pos : pos - 1;
-            s.a1[s.keys[i] & SLOT_MASK] = static_cast<uint16_t>(b);
+            const unsigned slot = static_cast<unsigned>(s.keys[i] & SLOT_MASK);
+            s.a1[slot] = static_cast<uint16_t>(b);
+            s.a8[i] = static_cast<uint16_t>(slot);  // sorted position -> match, kept until stage C
             if (f) s.a2[b] = static_cast<uint16_t>(i);
           },
           scan_tmp);
@@ -287,23 +289,16 @@ __global__ void __launch_bounds__(THREADS, (THREADS <= 512 ? 2 : 1)) covis_kerne
       for (int i = tid; i < R; i += THREADS) s.a1[i] = s.a3[s.a1[i]];
       __syncthreads();
       // ---------------------------------------------------------------- C: landmark ids, both orders
-      // compact list of the selected matches (a8, rewritten later as listB) so that the remaining
-      // sorts run over next_pow2(S) instead of next_pow2(R) keys
+      // keys of the selected matches only (compacted in slot order), so that the remaining sorts
+      // run over next_pow2(S) instead of next_pow2(R) keys
       const int S = FlagScan<THREADS, IPT>(
           R, [&](int i) { return s.a1[i] != kNone16; },
           [&](int i, int pos, bool f) {
-            if (f) s.a8[pos] = static_cast<uint16_t>(i);
+            if (f) s.keys[pos] = (static_cast<unsigned long long>(rec[i].landmark + 1) << SLOT_BITS) | static_cast<unsigned>(i);
           },
           scan_tmp);
       const int ps = NextPow2(S);
-      for (int j = tid; j < ps; j += THREADS) {
-        unsigned long long key = ~0ull;
-        if (j < S) {
-          const unsigned i = s.a8[j];
-          key = (static_cast<unsigned long long>(rec[i].landmark + 1) << SLOT_BITS) | i;
-        }
-        s.keys[j] = key;
-      }
+      for (int j = S + tid; j < ps; j += THREADS) s.keys[j] = ~0ull;
       __syncthreads();
       BitonicSort<THREADS>(s.keys, ps);
       // landmark dense id a4[match]; offA (a5), listA (a6) = group of the match at sorted position
@@ -319,26 +314,21 @@ __global__ void __launch_bounds__(THREADS, (THREADS <= 512 ? 2 : 1)) covis_kerne
           scan_tmp);
       if (tid == 0) s.a5[nL] = static_cast<uint16_t>(S);
       __syncthreads();
-      // order B: selected matches sorted by dense group id; offB (a7), listB (a8) = landmark id
-      for (int j = tid; j < ps; j += THREADS) {
-        unsigned long long key = ~0ull;
-        if (j < S) {
-          const unsigned i = s.a8[j];
-          key = (static_cast<unsigned long long>(s.a1[i]) << SLOT_BITS) | i;
-        }
-        s.keys[j] = key;
-      }
-      __syncthreads();
-      BitonicSort<THREADS>(s.keys, ps);
+      // order B: selected matches by (dense group id, slot) = the stage-A order (a8) restricted to
+      // the selected matches, because dense ids ascend with the group id — no sort; offB (a7)
       FlagScan<THREADS, IPT>(
-          S, [&](int i) { return i == 0 || (s.keys[i] >> SLOT_BITS) != (s.keys[i - 1] >> SLOT_BITS); },
-          [&](int i, int pos, bool f) {
-            const int slot = static_cast<int>(s.keys[i] & SLOT_MASK);
-            s.a8[i] = s.a4[slot];
-            if (f) s.a7[s.keys[i] >> SLOT_BITS] = static_cast<uint16_t>(i);
+          R, [&](int pp) { return s.a1[s.a8[pp]] != kNone16; },
+          [&](int pp, int pos, bool f) {
+            if (!f) return;
+            const unsigned slot = s.a8[pp];
+            const uint16_t g = s.a1[slot];
+            s.keys[pos] = (static_cast<unsigned long long>(g) << SLOT_BITS) | slot;
+            if (pp == 0 || s.a1[s.a8[pp - 1]] != g) s.a7[g] = static_cast<uint16_t>(pos);
           },
           scan_tmp);
       if (tid == 0) s.a7[n_eval] = static_cast<uint16_t>(S);
+      // listB (a8, overwriting the stage-A order it no longer needs) = landmark id at order-B position
+      for (int j = tid; j < S; j += THREADS) s.a8[j] = s.a4[s.keys[j] & SLOT_MASK];
       __syncthreads();
       // ---------------------------------------------------------------- D: components (min label)
       uint16_t* K = s.a2;  // label per selected group
