@@ -6,11 +6,13 @@ Groebner template by oracle/gen_gp3p_program.py) has a critical path of only a f
 This script
   1. makes the implicit `factor` register explicit (three-address form with factor slots),
   2. removes dead operations (results that never reach the 48 action-matrix entries),
-  3. list-schedules the rest into WAVES of mutually independent operations (RAW, WAR and WAW all
-     respected, so the operations of one wave may execute in any order / in parallel),
-  4. renames every value to a recycled physical slot (liveness over the wave schedule), which
-     shrinks the per-hypothesis slot array ~3x (more hypotheses resident per SM),
-  5. sorts every wave by opcode and emits gp3p_schedule.inc.
+  3. builds the true (read-after-write) dependency graph of the remaining operations,
+  4. list-schedules them (longest-path priority) into STEPS of at most 32 mutually independent
+     operations — one step = one warp-wide instruction group,
+  5. allocates a physical slot per value by liveness over the steps (in-place updates where
+     possible), which removes the WAR/WAW hazards of the original slot names and shrinks the
+     per-hypothesis slot array ~3x (more hypotheses resident per SM),
+  6. sorts every step by opcode, pads it to 32 operations and emits gp3p_schedule.inc.
 Every operation still computes exactly the same IEEE-754 expression on exactly the same operand
 values, so the wave-parallel execution is bit-identical to the sequential program; the script
 checks that on random inputs before writing the file.
@@ -104,135 +106,144 @@ def main():
             live.update(r)
     ops = [op for op, k in zip(ops, keep) if k]
 
-    # ---- 3. wave scheduling ----
-    last_write = {}   # slot -> level of its last writer
-    last_read = {}    # slot -> max level of readers since the last write
-    level = []
-    for op in ops:
-        r, w = reads_writes(op)
-        lv = 0
-        for s in r:
-            lv = max(lv, last_write.get(s, 0) + 1)          # RAW
-        lv = max(lv, last_write.get(w, 0) + 1)              # WAW
-        lv = max(lv, last_read.get(w, 0) + 1)               # WAR
-        lv = max(lv, 1)
-        level.append(lv)
-        for s in r:
-            last_read[s] = max(last_read.get(s, 0), lv)
-        last_write[w] = lv
-        last_read[w] = 0 if w not in r else lv
-    num_waves = max(level)
-    waves = [[] for _ in range(num_waves)]
-    for op, lv in zip(ops, level):
-        waves[lv - 1].append(op)
-    for w in waves:
-        w.sort(key=lambda op: (op[0], op[1]))
-    flat = [op for w in waves for op in w]
-    offsets = np.cumsum([0] + [len(w) for w in waves]).tolist()
-    chunks = sum((len(w) + 31) // 32 for w in waves)
-
-    # ---- 4. slot compaction: rename every VALUE (definition) to a physical slot that is free ----
-    # A value lives from the wave that defines it (0 = initial state) to the last wave that reads it;
-    # SUBMUL / SCALE update their destination in place and keep its slot. A slot is recycled for a
-    # definition of wave w only if its previous value was last read in a wave < w, so the
-    # operations of one wave stay mutually independent. Slots that are only ever read as the
-    # implicit initial 0.0 (structural zeros of the elimination template) share slot 0.
+    # ---- 3. values (SSA over the program order) and true dependencies ----
     W_RMW = (W_SUBMUL, W_SCALE)
-    cur, vals = {}, []            # logical slot -> value id; value = [def_wave, last_read, kind]
-    def new_value(wave, kind):
-        vals.append([wave, wave, kind])
+    cur, vals = {}, []            # logical slot -> value id; value = [kind, producer op, in-place input]
+    def new_value(kind, prod, inplace=None):
+        vals.append([kind, prod, inplace])
         return len(vals) - 1
     init_value = {}
     for e in init:
-        init_value[e[0]] = cur[e[0]] = new_value(0, "init")
-    op_vals = []                  # per op: (value ids of the reads, value id of the result)
-    for wi, w in enumerate(waves):
-        reads_of = []
-        for op in w:
-            r, d = reads_writes(op)
-            ids = []
-            for sl in r:
-                if sl not in cur:
-                    cur[sl] = new_value(0, "zero")
-                v = cur[sl]
-                vals[v][1] = max(vals[v][1], wi + 1)
-                ids.append(v)
-            reads_of.append(ids)
-        for op, ids in zip(w, reads_of):
-            d = op[1]
-            if op[0] in W_RMW:
-                v = cur[d]
-                if vals[v][2] == "zero":
-                    vals[v][2] = "zero_rmw"   # needs its own zero-filled slot
-            else:
-                cur[d] = v = new_value(wi + 1, "def")
-            op_vals.append((ids, v))
-    END = len(waves) + 1
-    for sl in action:
-        if sl >= 0:
-            vals[cur[sl]][1] = END
+        init_value[e[0]] = cur[e[0]] = new_value("init", None)
+    op_reads, op_write = [], []
+    for i, op in enumerate(ops):
+        r, d = reads_writes(op)
+        ids = []
+        for sl in r:
+            if sl not in cur:
+                cur[sl] = new_value("zero", None)   # implicit initial 0.0 (structural zero)
+            ids.append(cur[sl])
+        op_reads.append(ids)
+        cur[d] = v = new_value("def", i, ids[0] if op[0] in W_RMW else None)
+        op_write.append(v)
+    out_value = {sl: cur[sl] for sl in action if sl >= 0}
+    n = len(ops)
+    succs, npred = [[] for _ in range(n)], [0] * n
+    for i in range(n):
+        preds = set(vals[v][1] for v in op_reads[i] if vals[v][1] is not None)
+        npred[i] = len(preds)
+        for q in preds:
+            succs[q].append(i)
+    height = [1] * n              # longest dependency chain from the op to a sink (priority)
+    for i in range(n - 1, -1, -1):
+        for q in succs[i]:
+            height[i] = max(height[i], height[q] + 1)
+
+    # ---- 4. list scheduling into STEPS of at most 32 mutually independent operations ----
+    # (one step = one warp-wide instruction group; only true dependencies constrain the order,
+    # the slot allocator below removes the WAR/WAW hazards of the original slot names)
+    import heapq
+    LANES = 32
+    ready = [(-height[i], i) for i in range(n) if npred[i] == 0]
+    heapq.heapify(ready)
+    steps, step_of, left = [], [0] * n, n
+    while left:
+        take = []
+        while ready and len(take) < LANES:
+            take.append(heapq.heappop(ready)[1])
+        assert take
+        for i in take:
+            step_of[i] = len(steps) + 1          # steps are numbered from 1; 0 = initial state
+        steps.append(take)
+        left -= len(take)
+        for i in take:
+            for q in succs[i]:
+                npred[q] -= 1
+                if npred[q] == 0:
+                    heapq.heappush(ready, (-height[q], q))
+    num_waves = len(steps)
+    critical_path = max(height)
+
+    # ---- 5. slot allocation by liveness over the steps ----
+    # A value lives from the step that defines it to the last step that reads it. Its slot is
+    # recycled for definitions of strictly later steps; SUBMUL / SCALE overwrite their first
+    # operand in place when they are its only remaining reader. Values that are only ever the
+    # implicit initial 0.0 share slot 0.
+    END = num_waves + 1
+    def_step = [0] * len(vals)
+    last_read = [0] * len(vals)
+    readers_in_step = {}
+    for i in range(n):
+        def_step[op_write[i]] = step_of[i]
+        last_read[op_write[i]] = max(last_read[op_write[i]], step_of[i])
+        for v in set(op_reads[i]):
+            last_read[v] = max(last_read[v], step_of[i])
+            readers_in_step[(v, step_of[i])] = readers_in_step.get((v, step_of[i]), 0) + 1
+    for v in out_value.values():
+        last_read[v] = END
     ZERO_SLOT = 0
     phys = [None] * len(vals)
-    next_slot, free = 1, []
-    by_def = {}
-    for v, (dw, lr, kind) in enumerate(vals):
-        by_def.setdefault(dw, []).append(v)
-    expiring = {}
-    for wave in range(0, END + 1):
-        for v in by_def.get(wave, []):
-            dw, lr, kind = vals[v]
-            if kind == "zero":
-                phys[v] = ZERO_SLOT
-                continue
-            # initial values (wave 0) need fresh slots: they are written / zero-filled before wave 1
-            if wave > 0 and free:
+    next_slot, free, expiring, taken_over = 1, [], {}, set()
+    for v, (kind, prod, inplace) in enumerate(vals):
+        if kind == "zero":
+            phys[v] = ZERO_SLOT
+        elif kind == "init":
+            phys[v] = next_slot
+            next_slot += 1
+            expiring.setdefault(last_read[v], []).append(v)
+    free.extend(phys[v] for v in expiring.pop(0, []))   # init values nobody reads
+    for t in range(1, END):
+        for i in steps[t - 1]:
+            v = op_write[i]
+            src = vals[v][2]
+            if (src is not None and vals[src][0] != "zero" and last_read[src] == t
+                    and readers_in_step[(src, t)] == 1):
+                phys[v] = phys[src]                   # in place
+                taken_over.add(src)
+            elif free:
                 phys[v] = free.pop()
             else:
                 phys[v] = next_slot
                 next_slot += 1
-            expiring.setdefault(lr, []).append(phys[v])
-        # values last read in this wave free their slot for definitions of LATER waves
-        free.extend(expiring.pop(wave, []))
-    dummy_slot = next_slot        # init entries nobody reads land here
+            expiring.setdefault(last_read[v], []).append(v)
+        free.extend(phys[v] for v in expiring.pop(t, []) if v not in taken_over)
+    dummy_slot = next_slot        # padding operations and dead init entries land here
     compact_slots = next_slot + 1
-    new_waves, at = [], 0
-    for w in waves:
-        nw_ = []
-        for op in w:
-            ids, v = op_vals[at]
-            at += 1
-            r, d = reads_writes(op)
-            m = {sl: phys[i] for sl, i in zip(r, ids)}
-            o, d0, a0, b0, c0, e0 = op
-            def mp(x, used):
-                return m[x] if used else 0
+    new_waves = []
+    for take in steps:
+        row = []
+        for i in take:
+            o = ops[i][0]
+            rd = [phys[v] for v in op_reads[i]]
+            d = phys[op_write[i]]
             if o == W_DIVSUB:
-                nw_.append((o, phys[v], m[a0], m[b0], m[c0], m[e0]))
+                row.append((o, d, rd[0], rd[1], rd[2], rd[3]))
             elif o in (W_DIV, W_NEGDIV):
-                nw_.append((o, phys[v], m[a0], m[b0], 0, 0))
+                row.append((o, d, rd[0], rd[1], 0, 0))
             elif o == W_ZERO:
-                nw_.append((o, phys[v], 0, 0, 0, 0))
-            elif o == W_SUBMUL:
-                assert phys[v] == m[d0]
-                nw_.append((o, phys[v], m[a0], m[b0], 0, 0))
-            elif o == W_SCALE:
-                assert phys[v] == m[d0]
-                nw_.append((o, phys[v], m[a0], 0, 0, 0))
+                row.append((o, d, 0, 0, 0, 0))
+            elif o == W_SUBMUL:                       # d = x - a * b with x the first operand
+                row.append((o, d, rd[1], rd[2], rd[0], 0))
+            elif o == W_SCALE:                        # d = a * x
+                row.append((o, d, rd[1], rd[0], 0, 0))
             else:
-                nw_.append((o, phys[v], m[a0], 0, 0, 0))
-        nw_.sort(key=lambda op: (op[0], op[1]))
-        new_waves.append(nw_)
+                row.append((o, d, rd[0], 0, 0, 0))
+        row.sort(key=lambda op: (op[0], op[1]))
+        row += [(W_COPY, dummy_slot, dummy_slot, 0, 0, 0)] * (LANES - len(row))   # padding: no-ops
+        new_waves.append(row)
     new_init = []
     for e in init:
         v = init_value[e[0]]
-        dead = vals[v][1] == 0
+        dead = last_read[v] == 0
         new_init.append([dummy_slot if dead else phys[v]] + list(e[1:]))
-    new_action = [(-1 if sl < 0 else phys[cur[sl]]) for sl in action]
-    old_total_slots, old_init, old_waves = total_slots, init, waves
+    new_action = [(-1 if sl < 0 else phys[out_value[sl]]) for sl in action]
+    old_total_slots, old_init = total_slots, init
     total_slots, waves = compact_slots, new_waves
     flat = [op for w in waves for op in w]
+    offsets = [LANES * i for i in range(num_waves + 1)]
+    chunks = num_waves
 
-    # ---- 5. self-check against the sequential program ----
+    # ---- 6. self-check against the sequential program ----
     rng = np.random.default_rng(0)
 
     def init_slots_seq(f, v, p):
@@ -298,9 +309,9 @@ def main():
                 elif o == W_ZERO:
                     val = 0.0
                 elif o == W_SUBMUL:
-                    val = S[d] - S[a] * S[b]
+                    val = S[c] - S[a] * S[b]
                 elif o == W_SCALE:
-                    val = S[a] * S[d]
+                    val = S[a] * S[b]
                 elif o == W_COPY:
                     val = S[a]
                 elif o == W_INV:
@@ -326,7 +337,8 @@ def main():
         fo.write("// mutually independent (RAW/WAR/WAW respected), results are bit-identical to the sequential program.\n")
         fo.write(f"#define GP3P_W_NUM_SLOTS {total_slots}\n#define GP3P_W_NUM_OPS {len(flat)}\n")
         fo.write(f"#define GP3P_W_NUM_WAVES {num_waves}\n#define GP3P_W_NUM_CHUNKS {chunks}\n")
-        fo.write("// op: 0 DIVSUB d=a/b-c/e, 1 DIV d=a/b, 2 NEGDIV d=-a/b, 3 ZERO, 4 SUBMUL d=d-a*b, 5 SCALE d=a*d, 6 COPY d=a, 7 INV d=1/a\n")
+        fo.write("// op: 0 DIVSUB d=a/b-c/e, 1 DIV d=a/b, 2 NEGDIV d=-a/b, 3 ZERO, 4 SUBMUL d=c-a*b, 5 SCALE d=a*b, 6 COPY d=a, 7 INV d=1/a\n")
+        fo.write("// every step holds exactly 32 operations (padded with COPY dummy<-dummy): step s = ops [32 s, 32 s + 32)\n")
         fo.write("static const unsigned short GP3P_W_OPS[GP3P_W_NUM_OPS][6] = {\n")
         for op in flat:
             fo.write("  {" + ",".join(str(x) for x in op) + "},\n")
@@ -338,8 +350,8 @@ def main():
             fo.write("  {" + ",".join(str(x) for x in e) + "},\n")
         fo.write("};\n")
         fo.write(f"static const short GP3P_W_ACTION[{len(new_action)}] = {{" + ",".join(str(x) for x in new_action) + "};\n")
-    print(f"ops {len(mops)} -> {len(flat)} after DCE; waves {num_waves}; 32-wide chunks {chunks}; "
-          f"slots {old_total_slots} -> {total_slots} after compaction; widest wave {max(len(w) for w in waves)}")
+    print(f"ops {len(mops)} -> {n} after DCE; critical path {critical_path}; {num_waves} steps of 32 lanes "
+          f"({100.0 * n / (32 * num_waves):.0f}% filled); slots {old_total_slots} -> {total_slots}")
 
 
 if __name__ == "__main__":

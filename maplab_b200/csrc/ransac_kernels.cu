@@ -14,8 +14,8 @@
 //   * Groebner elimination: the micro-op program the oracle executes sequentially
 //     (gp3p_program.inc) re-scheduled offline into waves of independent three-address ops
 //     (gp3p_schedule.inc, gen_gp3p_schedule.py; dead ops removed, bit-identical results). The 32
-//     lanes execute one wave chunk per step on a slot array in shared memory: 253 steps instead
-//     of 12 253 dependent operations;
+//     lanes execute one 32-operation step at a time on a slot array in shared memory: 188 steps
+//     instead of 12 253 dependent operations;
 //   * 8x8 eigenvalues (Hessenberg + Francis QR) by one lane per hypothesis, then one lane per
 //     (hypothesis, eigenvalue) for inverse iteration, Cayley back-substitution and the
 //     disambiguation score; inlier counting with the lanes striding over the correspondences.
@@ -93,25 +93,28 @@ __device__ void Gp3pEliminateWarp(const RansacArgs& a, const double* fvp, double
     S[in[0]] = acc;
   }
   __syncwarp();
+  // one step = 32 mutually independent operations (padded), one per lane; the next step's
+  // operation word is fetched while the current one executes
+  uint4 next = __ldg(a.wops + lane);
   for (int w = 0; w < GP3P_W_NUM_WAVES; ++w) {
-    const int begin = a.wave_offsets[w], end = a.wave_offsets[w + 1];
-    for (int i = begin + lane; i < end; i += 32) {
-      const uint4 m = __ldg(a.wops + i);
-      const unsigned op = m.x & 0xFFFFu, d = m.x >> 16, x = m.y & 0xFFFFu, y = m.y >> 16,
-                     c = m.z & 0xFFFFu, e = m.z >> 16;
-      double val;
-      switch (op) {
-        case 0: val = S[x] / S[y] - S[c] / S[e]; break;
-        case 1: val = S[x] / S[y]; break;
-        case 2: val = -S[x] / S[y]; break;
-        case 3: val = 0.0; break;
-        case 4: val = S[d] - S[x] * S[y]; break;
-        case 5: val = S[x] * S[d]; break;
-        case 6: val = S[x]; break;
-        default: val = 1.0 / S[x]; break;
-      }
-      S[d] = val;  // ops of one wave are independent (RAW/WAR/WAW): no barrier inside a wave
+    const uint4 m = next;
+    if (w + 1 < GP3P_W_NUM_WAVES) next = __ldg(a.wops + (w + 1) * 32 + lane);
+    const unsigned op = m.x & 0xFFFFu, d = m.x >> 16, x = m.y & 0xFFFFu, y = m.y >> 16,
+                   c = m.z & 0xFFFFu, e = m.z >> 16;
+    double val;
+    switch (op) {
+      case 0: val = S[x] / S[y] - S[c] / S[e]; break;
+      case 1: val = S[x] / S[y]; break;
+      case 2: val = -S[x] / S[y]; break;
+      case 3: val = 0.0; break;
+      case 4: val = S[c] - S[x] * S[y]; break;
+      case 5: val = S[x] * S[y]; break;
+      case 6: val = S[x]; break;
+      default: val = 1.0 / S[x]; break;
     }
+    // destinations are slots that were free before this step (or the lane's own first operand,
+    // updated in place), so no barrier is needed between the reads and the writes of one step
+    S[d] = val;
     __syncwarp();
   }
   for (int i = lane; i < 64; i += 32) {
