@@ -37,6 +37,11 @@ Detector::~Detector() {
     if (e) cudaEventDestroy(e);
   for (cudaEvent_t e : ev_copy_)
     if (e) cudaEventDestroy(e);
+  if (h_remaining_) cudaFreeHost(h_remaining_);
+  for (cudaEvent_t e : ev_ransac_)
+    if (e) cudaEventDestroy(e);
+  for (cudaStream_t st : ransac_stream_)
+    if (st) cudaStreamDestroy(st);
   if (copy_stream_) cudaStreamDestroy(copy_stream_);
   if (stream_) cudaStreamDestroy(stream_);
 }
@@ -84,6 +89,10 @@ bool Detector::Create(const mlc_settings& s, const void* blob, size_t size, std:
     return false;
   for (cudaEvent_t& e : ev_copy_)
     if (!Cuda(cudaEventCreateWithFlags(&e, cudaEventDisableTiming), "cudaEventCreate", err)) return false;
+  for (cudaEvent_t& e : ev_ransac_)
+    if (!Cuda(cudaEventCreateWithFlags(&e, cudaEventDisableTiming), "cudaEventCreate", err)) return false;
+  for (cudaStream_t& st : ransac_stream_)
+    if (!Cuda(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking), "cudaStreamCreate", err)) return false;
   if (!Cuda(cudaEventCreate(&ev0_), "cudaEventCreate", err)) return false;
   if (!Cuda(cudaEventCreate(&ev1_), "cudaEventCreate", err)) return false;
   for (cudaEvent_t& e : ev_stage_)

@@ -133,6 +133,9 @@ class Detector {
   // host-buffer queries: the H2D copies run on their own stream in chunks, so that projection and
   // coarse search of chunk i overlap the copy of chunk i+1
   cudaStream_t copy_stream_ = nullptr;
+  cudaStream_t ransac_stream_[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // extra streams of the RANSAC problem groups
+  cudaEvent_t ev_ransac_[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  int* h_remaining_ = nullptr;  // pinned round counters
   static constexpr int kCopyChunks = 4;
   cudaEvent_t ev_copy_[kCopyChunks + 1] = {nullptr, nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t ev0_ = nullptr, ev1_ = nullptr;

@@ -47,6 +47,7 @@ enum {
 constexpr int N8 = 8;
 constexpr int kWarpsPerBlock = 4;
 constexpr int kHyp = 16;      // hypothesis slots per problem
+constexpr int kRansacGroups = 6;  // problem groups pipelined on separate streams
 constexpr int kHypFirst = 12; // speculated in the first round (k is still unknown) when the batch fills the GPU
 
 struct RansacArgs {
@@ -1004,7 +1005,7 @@ bool Detector::RansacOnDevice(const mlc_ransac_settings& rs, const mlc_camera* c
   const size_t o_bear = (o_rnd + sizeof(int32_t) * rnd_len + 255) & ~static_cast<size_t>(255);
   const size_t o_shuf = (o_bear + sizeof(double) * 3 * total + 255) & ~static_cast<size_t>(255);
   if (!Cuda(b_scr.Reserve(o_shuf + sizeof(int32_t) * total + 256), "alloc", err) ||
-      !Cuda(b_hyp.Reserve(sizeof(Hypothesis) * num_hyp + sizeof(ProblemState) * num_problems + 256), "alloc", err) ||
+      !Cuda(b_hyp.Reserve(sizeof(Hypothesis) * num_hyp + sizeof(ProblemState) * num_problems + 256)  /* + group counters */, "alloc", err) ||
       !Cuda(b_out.Reserve(sizeof(mlc_pose_result) * num_problems + total + 512), "alloc", err))
     return false;
   unsigned char* scr = b_scr.as<unsigned char>();
@@ -1056,30 +1057,87 @@ bool Detector::RansacOnDevice(const mlc_ransac_settings& rs, const mlc_camera* c
     const int v = atoi(env);
     if (v >= 1 && v <= kHyp) a.first_hyp = v;
   }
-  const unsigned warp_blocks = static_cast<unsigned>((num_problems * 32 + 127) / 128);
-  const unsigned thread_blocks = static_cast<unsigned>((num_problems + 127) / 128);
-  ransac_init_kernel<<<warp_blocks, 128, 0, stream_>>>(a, d_state);
-  CountLaunch();
-  const int max_rounds = 11 * rs.num_ransac_iters + 4;  // >= one consumed sample per round
-  const unsigned elim_blocks = static_cast<unsigned>(std::min<int64_t>(
-      (num_hyp + kWarpsPerBlock - 1) / kWarpsPerBlock, static_cast<int64_t>(sm_count_) * elim_per_sm));
-  for (int round = 0; round < max_rounds; ++round) {
-    if (!Cuda(cudaMemsetAsync(d_remaining, 0, sizeof(int), stream_), "memset", err)) return false;
-    ransac_sample_kernel<<<thread_blocks, 128, 0, stream_>>>(a, d_state, d_hyp);
-    gp3p_eliminate_kernel<<<elim_blocks, kWarpsPerBlock * 32, smem, stream_>>>(a, d_hyp, num_hyp);
-    gp3p_eigen_kernel<<<static_cast<unsigned>((num_hyp + 15) / 16), 128, 0, stream_>>>(d_hyp, num_hyp);
-    gp3p_candidate_kernel<<<static_cast<unsigned>((num_hyp * 8 + 63) / 64), 64, 0, stream_>>>(a, d_hyp, num_hyp);
-    ransac_score_kernel<<<static_cast<unsigned>((num_hyp * 32 + 127) / 128), 128, 0, stream_>>>(a, d_hyp, num_hyp);
-    ransac_update_kernel<<<thread_blocks, 128, 0, stream_>>>(a, d_state, d_hyp, d_remaining);
-    for (int i = 0; i < 6; ++i) CountLaunch();
-    int remaining = 0;
-    if (!Cuda(cudaMemcpyAsync(&remaining, d_remaining, sizeof(int), cudaMemcpyDeviceToHost, stream_), "D2H", err) ||
-        !Cuda(cudaStreamSynchronize(stream_), "ransac round", err))
-      return false;
-    if (remaining == 0) break;
+  // The problems are dealt into groups that run the round pipeline on their own streams: the
+  // stages are latency-bound kernels with long tails, and with staggered groups the tail of one
+  // group's stage overlaps the next stage of another group.
+  int groups = num_problems >= 384 ? 3 : (num_problems >= 96 ? 2 : 1);  // tuned on B200, 1000 problems
+  if (const char* env = getenv("MLC_RANSAC_GROUPS")) {
+    const int v = atoi(env);
+    if (v >= 1 && v <= kRansacGroups) groups = v;
   }
-  ransac_finalize_kernel<<<warp_blocks, 128, 0, stream_>>>(a, d_state);
-  CountLaunch();
+  if (groups > num_problems) groups = static_cast<int>(num_problems);
+  int* d_remaining_all = d_remaining;  // one counter per group (room reserved below)
+  // pinned, so that the per-round read-back does not block the host while it enqueues the other groups
+  if (!h_remaining_ && !Cuda(cudaHostAlloc(&h_remaining_, sizeof(int) * 8, cudaHostAllocDefault), "pinned alloc", err))
+    return false;
+  int* remaining_h = h_remaining_;
+  bool active[kRansacGroups] = {};
+  RansacArgs ga[kRansacGroups];
+  ProblemState* g_state[kRansacGroups];
+  Hypothesis* g_hyp[kRansacGroups];
+  cudaStream_t g_stream[kRansacGroups];
+  if (!Cuda(cudaEventRecord(ev_ransac_[kRansacGroups], stream_), "event", err)) return false;
+  for (int g = 0; g < groups; ++g) {
+    const int64_t p0 = num_problems * g / groups, p1 = num_problems * (g + 1) / groups;
+    ga[g] = a;
+    ga[g].num_problems = p1 - p0;
+    ga[g].offsets = a.offsets + p0;     // correspondence arrays stay absolute
+    ga[g].results = a.results + p0;
+    g_state[g] = d_state + p0;
+    g_hyp[g] = d_hyp + p0 * kHyp;
+    g_stream[g] = g == 0 ? stream_ : ransac_stream_[g - 1];
+    active[g] = p1 > p0;
+    if (g > 0 && !Cuda(cudaStreamWaitEvent(g_stream[g], ev_ransac_[kRansacGroups], 0), "wait", err)) return false;
+  }
+  auto blocks_of = [](int64_t items, int per_block) { return static_cast<unsigned>((items + per_block - 1) / per_block); };
+  for (int g = 0; g < groups; ++g) {
+    if (!active[g]) continue;
+    ransac_init_kernel<<<blocks_of(ga[g].num_problems * 32, 128), 128, 0, g_stream[g]>>>(ga[g], g_state[g]);
+    CountLaunch();
+  }
+  const int max_rounds = 11 * rs.num_ransac_iters + 4;  // >= one consumed sample per round
+  for (int round = 0; round < max_rounds; ++round) {
+    bool any = false;
+    for (int g = 0; g < groups; ++g) {
+      if (!active[g]) continue;
+      any = true;
+      const int64_t np = ga[g].num_problems, nh = np * kHyp;
+      cudaStream_t st = g_stream[g];
+      const unsigned elim_blocks = static_cast<unsigned>(std::min<int64_t>(
+          (nh + kWarpsPerBlock - 1) / kWarpsPerBlock, static_cast<int64_t>(sm_count_) * elim_per_sm));
+      if (!Cuda(cudaMemsetAsync(d_remaining_all + g, 0, sizeof(int), st), "memset", err)) return false;
+      ransac_sample_kernel<<<blocks_of(np, 128), 128, 0, st>>>(ga[g], g_state[g], g_hyp[g]);
+      gp3p_eliminate_kernel<<<elim_blocks, kWarpsPerBlock * 32, smem, st>>>(ga[g], g_hyp[g], nh);
+      gp3p_eigen_kernel<<<blocks_of(nh, 16), 128, 0, st>>>(g_hyp[g], nh);
+      gp3p_candidate_kernel<<<blocks_of(nh * 8, 64), 64, 0, st>>>(ga[g], g_hyp[g], nh);
+      ransac_score_kernel<<<blocks_of(nh * 32, 128), 128, 0, st>>>(ga[g], g_hyp[g], nh);
+      ransac_update_kernel<<<blocks_of(np, 128), 128, 0, st>>>(ga[g], g_state[g], g_hyp[g], d_remaining_all + g);
+      for (int i = 0; i < 6; ++i) CountLaunch();
+      if (!Cuda(cudaMemcpyAsync(&remaining_h[g], d_remaining_all + g, sizeof(int), cudaMemcpyDeviceToHost, st), "D2H", err))
+        return false;
+    }
+    if (!any) break;
+    for (int g = 0; g < groups; ++g) {
+      if (!active[g]) continue;
+      if (!Cuda(cudaStreamSynchronize(g_stream[g]), "ransac round", err)) return false;
+      if (remaining_h[g] == 0) {
+        active[g] = false;  // this group is done: finalize it right away on its stream
+        ransac_finalize_kernel<<<blocks_of(ga[g].num_problems * 32, 128), 128, 0, g_stream[g]>>>(ga[g], g_state[g]);
+        CountLaunch();
+        if (g > 0) {
+          if (!Cuda(cudaEventRecord(ev_ransac_[g - 1], g_stream[g]), "event", err) ||
+              !Cuda(cudaStreamWaitEvent(stream_, ev_ransac_[g - 1], 0), "wait", err))
+            return false;
+        }
+      }
+    }
+  }
+  for (int g = 0; g < groups; ++g) {
+    if (active[g]) {  // round limit reached (cannot happen: every round consumes a sample)
+      *err = "RANSAC round limit reached";
+      return false;
+    }
+  }
   cudaEventRecord(ev_stage_[5], stream_);
   if (!Cuda(cudaGetLastError(), "ransac kernels", err)) return false;
   if (!Cuda(cudaMemcpyAsync(results, a.results, sizeof(mlc_pose_result) * num_problems, cudaMemcpyDeviceToHost, stream_),
