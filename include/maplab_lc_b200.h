@@ -219,6 +219,16 @@ int mlc_last_stage_ms(mlc_detector* d, double* ms5);
  * through vi_map::VIMap::getLandmark_G_p, LCH/src/loop-closure-handler.cc:272-366). xyz: n x 3. */
 int mlc_set_landmark_positions(mlc_detector* d, const double* xyz, int64_t n);
 
+/* Database persistence (no reference counterpart: maplab rebuilds the loop-closure database for
+ * every `lc` / `aam` / `relax` invocation and per mission, LCH/src/loop-detector-node.cc:273-339,
+ * vi-map-merger.cc:71-78). mlc_save_index writes the built index — keyframe headers, projected
+ * descriptors, landmark numbers, inverted lists, cell table, landmark positions — to one file;
+ * mlc_load_index replaces the detector's database with it (the detector must have been created with
+ * the same vocabulary, engine and sharding: checked, non-zero otherwise). Queries on a loaded
+ * index return exactly what they returned on the index that was saved. */
+int mlc_save_index(mlc_detector* d, const char* path);
+int mlc_load_index(mlc_detector* d, const char* path);
+
 /* Fused batched query = LoopDetectorNode::queryVertexInDatabase for a batch of vertices
  * (LCH/src/loop-detector-node.cc:668-766, :819-873): project -> kNN -> Find -> correspondence
  * assembly -> handleLoopClosure verdict + T_G_I, all on the device. keypoints: 2 doubles per

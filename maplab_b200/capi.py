@@ -20,7 +20,7 @@ EXPORTS = [
     "mlc_knn_device", "mlc_coarse_cells", "mlc_merge_topk_device", "mlc_last_scan_stats",
     "mlc_find_batch", "mlc_find_batch_bits", "mlc_find_from_knn_device", "mlc_pnp_ransac_batch",
     "mlc_coarse_device", "mlc_scan_device", "mlc_last_stage_ms", "mlc_set_landmark_positions", "mlc_query_batch", "mlc_query_batch_device", "mlc_query_from_knn_device",
-    "mlc_score",
+    "mlc_score", "mlc_save_index", "mlc_load_index",
 ]
 
 
@@ -233,6 +233,12 @@ class Detector:
         ms = (C.c_double * 5)()
         _check(lib().mlc_last_stage_ms(self._h, ms))
         return dict(zip(("project", "coarse", "scan", "vote_cluster", "ransac"), [float(x) for x in ms]))
+
+    def save_index(self, path):
+        _check(lib().mlc_save_index(self._h, str(path).encode()))
+
+    def load_index(self, path):
+        _check(lib().mlc_load_index(self._h, str(path).encode()))
 
     def score(self, num_matches, num_descriptors, num_db, probabilistic):
         """scoring::compute*Score on the device (scoring.h:38-59, :92-187)."""

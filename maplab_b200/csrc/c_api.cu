@@ -228,6 +228,17 @@ int mlc_set_landmark_positions(mlc_detector* d, const double* xyz, int64_t n) {
   return d->impl.SetLandmarkPositions(xyz, n, &err) ? 0 : Fail(err);
 }
 
+int mlc_save_index(mlc_detector* d, const char* path) {
+  MLC_REQUIRE(d && path, "mlc_save_index: null argument");
+  std::string err;
+  return d->impl.SaveIndex(path, &err) ? 0 : Fail(err);
+}
+int mlc_load_index(mlc_detector* d, const char* path) {
+  MLC_REQUIRE(d && path, "mlc_load_index: null argument");
+  std::string err;
+  return d->impl.LoadIndex(path, &err) ? 0 : Fail(err);
+}
+
 static int QueryImpl(mlc_detector* d, const mlc_frame* frames, int64_t num_frames, const uint8_t* bits,
                      int bytes_per_desc, const double* keypoints, bool on_device,
                      const mlc_camera* cams, int num_cams, const mlc_ransac_settings* rs,

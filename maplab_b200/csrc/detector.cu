@@ -2,6 +2,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
 #include <cstring>
 
 namespace mlc {
@@ -62,6 +63,9 @@ bool Detector::Create(const mlc_settings& s, const void* blob, size_t size, std:
     return false;
   }
   if (!vocab_.Parse(blob, size, s_.engine == 1, err)) return false;
+  vocab_hash_ = 1469598103934665603ull;
+  for (size_t i = 0; i < size; ++i)
+    vocab_hash_ = (vocab_hash_ ^ static_cast<const unsigned char*>(blob)[i]) * 1099511628211ull;
   if (vocab_.target_dim / 2 > 8) {
     *err = "target dimensionality > 16 is not supported";
     return false;
@@ -534,6 +538,154 @@ bool Detector::LastScanStats(uint64_t* bytes, uint64_t* entries, double* ms, std
     *bytes = total * static_cast<uint64_t>(4 * (dim() + 1));
   }
   *ms = msf;
+  return true;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Database persistence. The reference rebuilds its database for every `lc` / `aam` / `relax`
+// invocation (loop-detector-node.cc:273-339, vi-map-merger.cc:71-78); here the built index is one
+// little-endian file: header, keyframes, projected descriptors, landmark numbers, descriptor ->
+// keyframe, cell per descriptor, cell table, inverted lists, landmark positions.
+// ---------------------------------------------------------------------------------------------
+namespace {
+struct IndexFileHeader {
+  char magic[8];  // "MLCIDX01"
+  uint64_t vocab_hash;
+  int32_t engine, dim, shard_rank, shard_count;
+  uint32_t num_cells;
+  int32_t list_dim;
+  int64_t num_descriptors, num_keyframes, num_landmark_xyz;
+  uint64_t list_bytes;
+};
+bool WriteAll(FILE* f, const void* p, size_t bytes) { return bytes == 0 || fwrite(p, 1, bytes, f) == bytes; }
+bool ReadAll(FILE* f, void* p, size_t bytes) { return bytes == 0 || fread(p, 1, bytes, f) == bytes; }
+}  // namespace
+
+bool Detector::SaveIndex(const char* path, std::string* err) {
+  std::lock_guard<std::recursive_mutex> lock(mu_);
+  if (!EnsureIndex(err)) return false;
+  FILE* f = fopen(path, "wb");
+  if (!f) {
+    *err = std::string("cannot open ") + path + " for writing";
+    return false;
+  }
+  IndexFileHeader h{};
+  std::memcpy(h.magic, "MLCIDX01", 8);
+  h.vocab_hash = vocab_hash_;
+  h.engine = s_.engine;
+  h.dim = dim();
+  h.shard_rank = s_.shard_rank;
+  h.shard_count = s_.shard_count;
+  h.num_cells = lists_.num_cells;
+  h.list_dim = lists_.dim;
+  h.num_descriptors = NumDescriptors();
+  h.num_keyframes = static_cast<int64_t>(keyframes_.size());
+  h.num_landmark_xyz = num_landmark_xyz_;
+  h.list_bytes = lists_.list_bytes;
+  const size_t n = static_cast<size_t>(h.num_descriptors);
+  bool ok = WriteAll(f, &h, sizeof(h)) && WriteAll(f, keyframes_.data(), keyframes_.size() * sizeof(KeyframeMeta)) &&
+            WriteAll(f, desc_.data(), desc_.size() * 4) && WriteAll(f, landmarks_.data(), landmarks_.size() * 8) &&
+            WriteAll(f, desc_kf_.data(), desc_kf_.size() * 4);
+  // device-resident parts through a bounded staging buffer
+  std::vector<unsigned char> stage(size_t{64} << 20);
+  auto dump = [&](const void* dptr, size_t bytes) {
+    for (size_t at = 0; ok && at < bytes; at += stage.size()) {
+      const size_t c = std::min(stage.size(), bytes - at);
+      ok = Cuda(cudaMemcpy(stage.data(), static_cast<const unsigned char*>(dptr) + at, c, cudaMemcpyDeviceToHost),
+                "D2H index", err) && WriteAll(f, stage.data(), c);
+    }
+  };
+  if (ok) dump(d_db_cells_.p, n * 4);
+  if (ok) dump(lists_.cell_info, static_cast<size_t>(lists_.num_cells) * sizeof(uint2));
+  if (ok) dump(lists_.lists, lists_.list_bytes);
+  if (ok) dump(d_landmark_xyz_.p, static_cast<size_t>(num_landmark_xyz_) * 24);
+  ok = (fclose(f) == 0) && ok;
+  if (!ok && err->empty()) *err = std::string("short write to ") + path;
+  return ok;
+}
+
+bool Detector::LoadIndex(const char* path, std::string* err) {
+  std::lock_guard<std::recursive_mutex> lock(mu_);
+  FILE* f = fopen(path, "rb");
+  if (!f) {
+    *err = std::string("cannot open ") + path;
+    return false;
+  }
+  IndexFileHeader h{};
+  bool ok = ReadAll(f, &h, sizeof(h));
+  if (!ok || std::memcmp(h.magic, "MLCIDX01", 8) != 0) {
+    fclose(f);
+    *err = "not an index file of this library";
+    return false;
+  }
+  const uint64_t cells64 = static_cast<uint64_t>(vocab_.words1.cols) * vocab_.words2.cols;
+  if (h.vocab_hash != vocab_hash_ || h.engine != s_.engine || h.dim != dim() || h.num_cells != cells64 ||
+      h.shard_rank != s_.shard_rank || h.shard_count != s_.shard_count || h.num_descriptors < 0 ||
+      h.num_keyframes < 0 || h.num_landmark_xyz < 0) {
+    fclose(f);
+    *err = "index file was built with another vocabulary / engine / sharding";
+    return false;
+  }
+  const size_t n = static_cast<size_t>(h.num_descriptors);
+  std::vector<KeyframeMeta> kfs(static_cast<size_t>(h.num_keyframes));
+  std::vector<float> desc(n * h.dim);
+  std::vector<int64_t> lms(n);
+  std::vector<int32_t> dkf(n);
+  ok = ReadAll(f, kfs.data(), kfs.size() * sizeof(KeyframeMeta)) && ReadAll(f, desc.data(), desc.size() * 4) &&
+       ReadAll(f, lms.data(), lms.size() * 8) && ReadAll(f, dkf.data(), dkf.size() * 4);
+  DeviceLists lists;
+  lists.num_cells = h.num_cells;
+  lists.dim = h.list_dim;
+  lists.list_bytes = h.list_bytes;
+  DevBuf cells, xyz;
+  std::vector<unsigned char> stage(size_t{64} << 20);
+  auto fill = [&](void* dptr, size_t bytes) {
+    for (size_t at = 0; ok && at < bytes; at += stage.size()) {
+      const size_t c = std::min(stage.size(), bytes - at);
+      ok = ReadAll(f, stage.data(), c) &&
+           Cuda(cudaMemcpy(static_cast<unsigned char*>(dptr) + at, stage.data(), c, cudaMemcpyHostToDevice),
+                "H2D index", err);
+    }
+  };
+  ok = ok && Cuda(cells.Reserve(n * 4 + 16), "alloc", err) &&
+       Cuda(cudaMalloc(&lists.cell_info, sizeof(uint2) * static_cast<size_t>(h.num_cells)), "alloc", err) &&
+       Cuda(cudaMalloc(&lists.lists, h.list_bytes + 16), "alloc", err) &&
+       Cuda(xyz.Reserve(static_cast<size_t>(h.num_landmark_xyz) * 24 + 16), "alloc", err);
+  if (ok) fill(cells.p, n * 4);
+  if (ok) fill(lists.cell_info, static_cast<size_t>(h.num_cells) * sizeof(uint2));
+  if (ok) fill(lists.lists, h.list_bytes);
+  if (ok) fill(xyz.p, static_cast<size_t>(h.num_landmark_xyz) * 24);
+  fclose(f);
+  if (!ok) {
+    lists.Free();
+    cells.Free();
+    xyz.Free();
+    if (err->empty()) *err = std::string("truncated index file ") + path;
+    return false;
+  }
+  // commit: replace the current database
+  keyframes_.swap(kfs);
+  desc_.swap(desc);
+  landmarks_.swap(lms);
+  desc_kf_.swap(dkf);
+  lists_.Free();
+  lists_ = lists;
+  d_db_cells_.Free();
+  d_db_cells_ = cells;
+  d_landmark_xyz_.Free();
+  d_landmark_xyz_ = xyz;
+  num_landmark_xyz_ = h.num_landmark_xyz;
+  last_valid_ = false;
+  if (n > 0) {
+    if (!Cuda(d_desc_kf_.Reserve(n * 4), "alloc", err) || !Cuda(d_desc_lm_.Reserve(n * 8), "alloc", err) ||
+        !Cuda(d_kf_meta_.Reserve(keyframes_.size() * sizeof(KeyframeMeta)), "alloc", err) ||
+        !Cuda(cudaMemcpy(d_desc_kf_.p, desc_kf_.data(), n * 4, cudaMemcpyHostToDevice), "H2D", err) ||
+        !Cuda(cudaMemcpy(d_desc_lm_.p, landmarks_.data(), n * 8, cudaMemcpyHostToDevice), "H2D", err) ||
+        !Cuda(cudaMemcpy(d_kf_meta_.p, keyframes_.data(), keyframes_.size() * sizeof(KeyframeMeta),
+                         cudaMemcpyHostToDevice), "H2D", err))
+      return false;
+  }
+  index_dirty_ = false;
   return true;
 }
 

@@ -101,6 +101,10 @@ class Detector {
   // Landmark positions in the global frame by dense landmark id (vi_map::Landmark::get_p_G of
   // the landmark store, read by loop-closure-handler.cc:272-366); replicated on every shard.
   bool SetLandmarkPositions(const double* xyz, int64_t n, std::string* err);
+  // Database persistence: the built index (inverted lists, cell table, metadata,
+  // landmark positions) as one file, so that later runs skip projection + cell assignment + sort.
+  bool SaveIndex(const char* path, std::string* err);
+  bool LoadIndex(const char* path, std::string* err);
   // Fused query: project -> kNN -> kernel 3 -> correspondence gather -> kernel 4.
   bool QueryBatch(const mlc_frame* frames, int64_t num_frames, const uint8_t* bits, int bytes_per_desc,
                   const double* keypoints, bool inputs_on_device, const mlc_camera* cams, int num_cams,
@@ -126,6 +130,7 @@ class Detector {
 
   mlc_settings s_{};
   VocabularyFile vocab_;
+  uint64_t vocab_hash_ = 0;  // FNV-1a of the vocabulary blob (index files are tied to it)
   FixedProjection fp_;
   KdTreeHost tree1_, tree2_;
   int device_ = 0, sm_count_ = 148;
