@@ -404,42 +404,43 @@ __global__ void __launch_bounds__(THREADS, (THREADS <= 512 ? 2 : 1)) covis_kerne
           s.f1[i] = (s.f2[i] && K[s.a1[i]] == best_root) ? 1 : 0;
         __syncthreads();
         const bool unique = a.by_vertex ? true : (item.make_unique != 0);
-        // winners are a subset of the selected matches: walk the order-B positions (each thread
-        // rewrites exactly the key slots it read)
-        for (int j = tid; j < ps; j += THREADS) {
-          unsigned long long key = ~0ull;
-          const int i = j < S ? static_cast<int>(s.keys[j] & SLOT_MASK) : -1;
-          if (i >= 0 && s.f1[i]) {
-            bool keep = true;
+        // f2[i] := match i is emitted (winner, and the smallest database descriptor of its
+        // (query keypoint, landmark) when uniqueness is enforced)
+        for (int i = tid; i < R; i += THREADS) {
+          uint8_t keep = s.f1[i];
+          if (keep && unique) {
             const mlc_match me = rec[i];
-            if (unique) {
-              // (query keypoint, landmark) unique: the smallest database descriptor survives
-              for (int d = -(a.k - 1); d <= a.k - 1; ++d) {
-                const int o_i = i + d;
-                if (d == 0 || o_i < 0 || o_i >= R || !s.f1[o_i]) continue;
-                const mlc_match o = rec[o_i];
-                if (o.query_frame == me.query_frame && o.query_keypoint == me.query_keypoint &&
-                    o.landmark == me.landmark && o.db_descriptor < me.db_descriptor)
-                  keep = false;
-              }
-            }
-            if (keep) {
-              // canonical order (query frame, keypoint, database descriptor); query_frame is the
-              // batch frame number, monotone within a vertex
-              key = (static_cast<unsigned long long>(me.query_frame - item.frame) << 59) |
-                    (static_cast<unsigned long long>(me.query_keypoint) << 44) |
-                    (static_cast<unsigned long long>(static_cast<unsigned>(me.db_descriptor)) << SLOT_BITS) |
-                    static_cast<unsigned>(i);
+            for (int d = -(a.k - 1); d <= a.k - 1; ++d) {
+              const int o_i = i + d;
+              if (d == 0 || o_i < 0 || o_i >= R || !s.f1[o_i]) continue;
+              const mlc_match o = rec[o_i];
+              if (o.query_frame == me.query_frame && o.query_keypoint == me.query_keypoint &&
+                  o.landmark == me.landmark && o.db_descriptor < me.db_descriptor)
+                keep = 0;
             }
           }
-          s.keys[j] = key;
+          s.f2[i] = keep;
         }
         __syncthreads();
-        BitonicSort<THREADS>(s.keys, ps);
+        // canonical order (query frame, keypoint, database descriptor): `rec` is already ordered by
+        // (query frame, keypoint) with the <= k entries of one keypoint adjacent, so the output
+        // position is the compaction rank corrected by the entry's rank among its keypoint's
+        // emitted entries — no sort
         out_count = FlagScan<THREADS, IPT>(
-            S, [&](int i) { return s.keys[i] != ~0ull; },
+            R, [&](int i) { return s.f2[i] != 0; },
             [&](int i, int pos, bool f) {
-              if (f) out[pos] = rec[s.keys[i] & SLOT_MASK];
+              if (!f) return;
+              const mlc_match me = rec[i];
+              int before = 0, smaller = 0;
+              for (int d = -(a.k - 1); d <= a.k - 1; ++d) {
+                const int o_i = i + d;
+                if (d == 0 || o_i < 0 || o_i >= R || !s.f2[o_i]) continue;
+                const mlc_match o = rec[o_i];
+                if (o.query_frame != me.query_frame || o.query_keypoint != me.query_keypoint) continue;
+                if (d < 0) ++before;
+                if (o.db_descriptor < me.db_descriptor) ++smaller;
+              }
+              out[pos - before + smaller] = me;
             },
             scan_tmp);
       }
