@@ -140,8 +140,11 @@ __global__ void __launch_bounds__(THREADS, (THREADS <= 512 ? 2 : 1)) covis_kerne
         // skip iff |dt| < min_seconds * 1e9 AND same mission (matching-based-engine.cc:192-198)
         return !(static_cast<double>(dt) < a.min_time_ns && item.mission == kf.mission);
       };
+      // evaluate the filter once per slot (two dependent random gathers), then compact
+      for (int slot = tid; slot < n_slots; slot += THREADS) s.f1[slot] = valid(slot) ? 1 : 0;
+      __syncthreads();
       R = FlagScan<THREADS, IPT>(
-          n_slots, valid,
+          n_slots, [&](int slot) { return s.f1[slot] != 0; },
           [&](int slot, int pos, bool f) {
             if (!f) return;
             const int32_t id = idx[slot];
