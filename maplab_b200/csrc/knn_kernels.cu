@@ -148,7 +148,7 @@ __device__ __forceinline__ void InsertCandidates(uint32_t mask, uint64_t key, ui
   }
 }
 
-template <int DIM>
+template <int DIM, int KT>  // KT >= k: unroll bound of the selection rounds
 __global__ void __launch_bounds__(kScanThreads, kScanCtasPerSm)
 imi_scan_kernel(const float* __restrict__ q, int64_t n_q, const int32_t* __restrict__ cells, int nw,
                 const uint2* __restrict__ cell_info, const uint4* __restrict__ lists, int k,
@@ -215,18 +215,27 @@ imi_scan_kernel(const float* __restrict__ q, int64_t n_q, const int32_t* __restr
       uint64_t ka = EntryKey<DIM>(va, qv, in_a);
       uint64_t kb = in_b ? EntryKey<DIM>(vb, qv, true) : kEmptyKey;
       if (base == 0) {
-        // k rounds of warp arg-min over the fresh keys; lane r keeps the r-th
-        for (int r = 0; r < k; ++r) {
+        // k rounds of warp arg-min over the fresh keys; lane r keeps the r-th. Each lane orders
+        // its two keys once, so a round only looks at the lanes' smaller keys and the winner
+        // promotes its second key.
+        if (kb < ka) {
+          const uint64_t t = ka;
+          ka = kb;
+          kb = t;
+        }
+#pragma unroll
+        for (int r = 0; r < KT; ++r) {
+          if (r >= k) break;
           const uint32_t a_hi = static_cast<uint32_t>(ka >> 32), a_lo = static_cast<uint32_t>(ka);
-          const uint32_t b_hi = static_cast<uint32_t>(kb >> 32), b_lo = static_cast<uint32_t>(kb);
-          const uint32_t m_hi = __reduce_min_sync(kFull, min(a_hi, b_hi));
-          const uint32_t ca = (a_hi == m_hi) ? a_lo : kNoIndex;
-          const uint32_t cb = (b_hi == m_hi) ? b_lo : kNoIndex;
-          const uint32_t m_lo = __reduce_min_sync(kFull, min(ca, cb));
+          const uint32_t m_hi = __reduce_min_sync(kFull, a_hi);
+          const uint32_t c = (a_hi == m_hi) ? a_lo : kNoIndex;
+          const uint32_t m_lo = __reduce_min_sync(kFull, c);
           if (m_lo == kNoIndex) break;  // nothing left (warp-uniform)
           if (lane == r) held = (static_cast<uint64_t>(m_hi) << 32) | m_lo;
-          if (ca == m_lo) ka = kEmptyKey;
-          if (cb == m_lo) kb = kEmptyKey;
+          if (c == m_lo) {
+            ka = kb;
+            kb = kEmptyKey;
+          }
         }
       } else {
         const uint64_t kth = ShflKey(held, k - 1);
@@ -258,8 +267,19 @@ cudaError_t LaunchScanDim(const float* q, int64_t n_q, const int32_t* cells, int
   int64_t blocks = (n_q * 32 + threads - 1) / threads;
   const int64_t cap = static_cast<int64_t>(sm_count) * kScanCtasPerSm;  // persistent: every CTA resident
   if (blocks > cap) blocks = cap;
-  imi_scan_kernel<DIM><<<static_cast<unsigned>(blocks), threads, 0, stream>>>(
-      q, n_q, cells, nw, cell_info, reinterpret_cast<const uint4*>(lists), k, out_idx, out_dist);
+  const unsigned g = static_cast<unsigned>(blocks);
+#define MLC_SCAN(KT)                                                                             \
+  imi_scan_kernel<DIM, KT><<<g, threads, 0, stream>>>(q, n_q, cells, nw, cell_info,              \
+                                                      reinterpret_cast<const uint4*>(lists), k,  \
+                                                      out_idx, out_dist)
+  if (k <= 1) MLC_SCAN(1);
+  else if (k <= 2) MLC_SCAN(2);
+  else if (k <= 4) MLC_SCAN(4);
+  else if (k <= 6) MLC_SCAN(6);
+  else if (k <= 8) MLC_SCAN(8);
+  else if (k <= 10) MLC_SCAN(10);
+  else MLC_SCAN(16);
+#undef MLC_SCAN
   CountLaunch();
   return cudaGetLastError();
 }
