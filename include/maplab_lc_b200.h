@@ -83,6 +83,11 @@ typedef struct mlc_ransac_settings {
   double ransac_pixel_sigma; /* --lc_ransac_pixel_sigma (2.0) */
   uint32_t seed;             /* opengv seed when --lc_use_random_pnp_seed=false: 12345 */
   int32_t rng_mapping;       /* libstdc++ uniform_int_distribution mapping: 1 = GCC>=11, 0 = GCC<=10 */
+  /* Topological gate, LCH/src/loop-closure-handler.cc:18-24, :424-455 (negative = off, the default):
+   * a closure whose T_G_I differs from the query vertex' current pose (mlc_set_query_priors) by more
+   * than this is rejected. */
+  double max_delta_position_m;   /* --lc_max_delta_position_m (-1) */
+  double max_delta_rotation_deg; /* --lc_max_delta_rotation_deg (-1) */
 } mlc_ransac_settings;
 
 /* Per-query result of geometric verification (LCH/src/loop-closure-handler.cc:235-550). */
@@ -218,6 +223,13 @@ int mlc_last_stage_ms(mlc_detector* d, double* ms5);
 /* Landmark positions in the global frame by dense landmark id (what handleLoopClosure reads
  * through vi_map::VIMap::getLandmark_G_p, LCH/src/loop-closure-handler.cc:272-366). xyz: n x 3. */
 int mlc_set_landmark_positions(mlc_detector* d, const double* xyz, int64_t n);
+
+/* Current poses T_G_I (3x4 row-major [R|t], map_->getVertex_T_G_I(query_vertex_id),
+ * LCH/src/loop-closure-handler.cc:436-437) of the query vertices of the NEXT mlc_query_* /
+ * mlc_pnp_ransac_batch call, one per query vertex / problem in batch order; copied, consumed by that
+ * call. Only read when a max_delta_* limit is >= 0; with a limit set and no (or a wrong number of)
+ * priors the call fails, like the reference's CHECK(query_vertex_id.isValid()). */
+int mlc_set_query_priors(mlc_detector* d, const double* T_G_I, int64_t num_vertices);
 
 /* Database persistence (no reference counterpart: maplab rebuilds the loop-closure database for
  * every `lc` / `aam` / `relax` invocation and per mission, LCH/src/loop-detector-node.cc:273-339,

@@ -20,7 +20,7 @@ EXPORTS = [
     "mlc_knn_device", "mlc_coarse_cells", "mlc_merge_topk_device", "mlc_last_scan_stats",
     "mlc_find_batch", "mlc_find_batch_bits", "mlc_find_from_knn_device", "mlc_pnp_ransac_batch",
     "mlc_coarse_device", "mlc_scan_device", "mlc_last_stage_ms", "mlc_set_landmark_positions", "mlc_query_batch", "mlc_query_batch_device", "mlc_query_from_knn_device",
-    "mlc_score", "mlc_save_index", "mlc_load_index",
+    "mlc_score", "mlc_save_index", "mlc_load_index", "mlc_set_query_priors",
 ]
 
 
@@ -54,7 +54,8 @@ POSE_DTYPE = np.dtype([("accepted", "<i4"), ("ransac_success", "<i4"), ("num_inl
 class RansacSettings(C.Structure):
     _fields_ = [("min_inlier_count", C.c_int32), ("num_ransac_iters", C.c_int32),
                 ("min_inlier_ratio", C.c_double), ("ransac_pixel_sigma", C.c_double),
-                ("seed", C.c_uint32), ("rng_mapping", C.c_int32)]
+                ("seed", C.c_uint32), ("rng_mapping", C.c_int32),
+                ("max_delta_position_m", C.c_double), ("max_delta_rotation_deg", C.c_double)]
 
 
 class MlcError(RuntimeError):
@@ -233,6 +234,11 @@ class Detector:
         ms = (C.c_double * 5)()
         _check(lib().mlc_last_stage_ms(self._h, ms))
         return dict(zip(("project", "coarse", "scan", "vote_cluster", "ransac"), [float(x) for x in ms]))
+
+    def set_query_priors(self, T_G_I):
+        """Current poses of the query vertices of the next query call (delta-pose gate)."""
+        t = np.ascontiguousarray(T_G_I, np.float64).reshape(-1, 12)
+        _check(lib().mlc_set_query_priors(self._h, t.ctypes.data_as(C.c_void_p), C.c_int64(len(t))))
 
     def save_index(self, path):
         _check(lib().mlc_save_index(self._h, str(path).encode()))

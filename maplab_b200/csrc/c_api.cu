@@ -50,6 +50,8 @@ void mlc_default_ransac_settings(mlc_ransac_settings* s) {
   s->ransac_pixel_sigma = 2.0;
   s->seed = 12345u;
   s->rng_mapping = 1;
+  s->max_delta_position_m = -1.0;
+  s->max_delta_rotation_deg = -1.0;
 }
 
 int mlc_create(const mlc_settings* settings, const void* vocab_blob, size_t vocab_size,
@@ -228,6 +230,11 @@ int mlc_set_landmark_positions(mlc_detector* d, const double* xyz, int64_t n) {
   return d->impl.SetLandmarkPositions(xyz, n, &err) ? 0 : Fail(err);
 }
 
+int mlc_set_query_priors(mlc_detector* d, const double* T_G_I, int64_t num_vertices) {
+  MLC_REQUIRE(d && (num_vertices == 0 || T_G_I) && num_vertices >= 0, "mlc_set_query_priors: bad argument");
+  d->impl.SetQueryPriors(T_G_I, num_vertices);
+  return 0;
+}
 int mlc_save_index(mlc_detector* d, const char* path) {
   MLC_REQUIRE(d && path, "mlc_save_index: null argument");
   std::string err;

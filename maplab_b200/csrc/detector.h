@@ -103,6 +103,11 @@ class Detector {
   bool SetLandmarkPositions(const double* xyz, int64_t n, std::string* err);
   // Database persistence: the built index (inverted lists, cell table, metadata,
   // landmark positions) as one file, so that later runs skip projection + cell assignment + sort.
+  void SetQueryPriors(const double* T_G_I, int64_t n) {
+    std::lock_guard<std::recursive_mutex> lock(mu_);
+    priors_.assign(T_G_I, T_G_I + 12 * n);
+    have_priors_ = true;
+  }
   bool SaveIndex(const char* path, std::string* err);
   bool LoadIndex(const char* path, std::string* err);
   // Fused query: project -> kNN -> kernel 3 -> correspondence gather -> kernel 4.
@@ -141,6 +146,8 @@ class Detector {
   cudaStream_t ransac_stream_[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // extra streams of the RANSAC problem groups
   cudaEvent_t ev_ransac_[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   int* h_remaining_ = nullptr;  // pinned round counters
+  std::vector<double> priors_;  // T_G_I of the query vertices of the next call (delta-pose gate)
+  bool have_priors_ = false;
   static constexpr int kCopyChunks = 4;
   cudaEvent_t ev_copy_[kCopyChunks + 1] = {nullptr, nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t ev0_ = nullptr, ev1_ = nullptr;

@@ -921,6 +921,47 @@ cudaError_t EnsureProgram() {
 
 }  // namespace
 
+namespace {
+// T_I_I_ransac = T_G_I(map)^-1 * T_G_I_ransac; position norm and Eigen's AngleAxis(quaternion)
+// angle, 2 * atan2(|q.vec|, |q.w|), of the relative rotation (matrix -> quaternion as Eigen does).
+bool DeltaPoseGate(const double* A, const double* B, double max_pos_m, double max_rot_deg) {
+  double R[9], d[3], p[3];
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) {
+      double s = 0.0;
+      for (int k = 0; k < 3; ++k) s += A[k * 4 + i] * B[k * 4 + j];
+      R[i * 3 + j] = s;
+    }
+  for (int k = 0; k < 3; ++k) d[k] = B[k * 4 + 3] - A[k * 4 + 3];
+  for (int i = 0; i < 3; ++i) p[i] = A[0 * 4 + i] * d[0] + A[1 * 4 + i] * d[1] + A[2 * 4 + i] * d[2];
+  const double dp = std::sqrt(p[0] * p[0] + p[1] * p[1] + p[2] * p[2]);
+  double w, v[3];
+  const double t = R[0] + R[4] + R[8];
+  if (t > 0.0) {
+    double r = std::sqrt(t + 1.0);
+    w = 0.5 * r;
+    r = 0.5 / r;
+    v[0] = (R[7] - R[5]) * r;
+    v[1] = (R[2] - R[6]) * r;
+    v[2] = (R[3] - R[1]) * r;
+  } else {
+    int i = 0;
+    if (R[4] > R[0]) i = 1;
+    if (R[8] > R[i * 3 + i]) i = 2;
+    const int j = (i + 1) % 3, k = (j + 1) % 3;
+    double r = std::sqrt(R[i * 3 + i] - R[j * 3 + j] - R[k * 3 + k] + 1.0);
+    v[i] = 0.5 * r;
+    r = 0.5 / r;
+    w = (R[k * 3 + j] - R[j * 3 + k]) * r;
+    v[j] = (R[j * 3 + i] + R[i * 3 + j]) * r;
+    v[k] = (R[k * 3 + i] + R[i * 3 + k]) * r;
+  }
+  const double n = std::sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+  const double deg = (n != 0.0 ? 2.0 * std::atan2(n, std::fabs(w)) : 0.0) * (180.0 / 3.14159265358979323846);
+  return (max_pos_m < 0.0 || dp <= max_pos_m) && (max_rot_deg < 0.0 || deg <= max_rot_deg);
+}
+}  // namespace
+
 bool Detector::PnpRansacBatch(const mlc_ransac_settings& rs, const mlc_camera* cams, int num_cams,
                               int64_t num_problems, const int64_t* offsets, const double* keypoints,
                               const int32_t* camera_index, const int32_t* keypoint_index,
@@ -1146,7 +1187,23 @@ bool Detector::RansacOnDevice(const mlc_ransac_settings& rs, const mlc_camera* c
   if (inlier_flags && total > 0 &&
       !Cuda(cudaMemcpyAsync(inlier_flags, a.inlier_flags, total, cudaMemcpyDeviceToHost, stream_), "D2H flags", err))
     return false;
-  return Cuda(cudaStreamSynchronize(stream_), "pnp ransac", err);
+  if (!Cuda(cudaStreamSynchronize(stream_), "pnp ransac", err)) return false;
+  // Topological gate of handleLoopClosure (loop-closure-handler.cc:424-455): a host-side verdict on
+  // the recovered pose against the vertex' current pose; off unless a limit is >= 0.
+  const bool gate = rs.max_delta_position_m >= 0.0 || rs.max_delta_rotation_deg >= 0.0;
+  const bool have = have_priors_;
+  have_priors_ = false;  // consumed by this call
+  if (gate) {
+    if (!have || static_cast<int64_t>(priors_.size()) != 12 * num_problems) {
+      *err = "max_delta_* limits need mlc_set_query_priors with one pose per query vertex";
+      return false;
+    }
+    for (int64_t p = 0; p < num_problems; ++p)
+      if (results[p].accepted &&
+          !DeltaPoseGate(&priors_[12 * p], results[p].T_G_I, rs.max_delta_position_m, rs.max_delta_rotation_deg))
+        results[p].accepted = 0;
+  }
+  return true;
 }
 
 }  // namespace mlc

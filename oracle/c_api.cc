@@ -586,4 +586,9 @@ int lco_query_batch(void* h, int num_frames, const int64_t* ts, const int64_t* v
   return nv;
 }
 
+int lco_delta_pose_gate(const double* T_map, const double* T_ransac, double max_pos_m, double max_rot_deg,
+                        double* delta) {
+  DeltaPose(T_map, T_ransac, &delta[0], &delta[1]);
+  return DeltaPoseGate(T_map, T_ransac, max_pos_m, max_rot_deg) ? 1 : 0;
+}
 }  // extern "C"

@@ -353,5 +353,12 @@ struct HandlerSettings {
 };
 void HandleLoopClosure(const VerifyInput& in, const std::vector<Camera>& cams,
                        const HandlerSettings& hs, VerifyResult* out);
+// Topological gate of handleLoopClosure (loop-closure-handler.cc:424-455): T_I_I_ransac =
+// T_G_I(map)^-1 * T_G_I_ransac; reject when its position norm / AngleAxis angle exceed the limits
+// (negative limit = check off). Transforms are 3x4 row-major [R|t].
+void DeltaPose(const double* T_G_I_map, const double* T_G_I_ransac, double* delta_position_m,
+               double* delta_rotation_deg);
+bool DeltaPoseGate(const double* T_G_I_map, const double* T_G_I_ransac, double max_delta_position_m,
+                   double max_delta_rotation_deg);
 
 }  // namespace lc_oracle

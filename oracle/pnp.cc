@@ -628,4 +628,58 @@ void HandleLoopClosure(const VerifyInput& in, const std::vector<Camera>& cams,
   out->accepted = true;
 }
 
+// loop-closure-handler.cc:436-442. The rotation angle is Eigen's AngleAxis(quaternion):
+// 2 * atan2(|q.vec|, |q.w|), with the quaternion of R_map^T R_ransac from Eigen's matrix ->
+// quaternion conversion (Shepperd's method, Eigen/src/Geometry/Quaternion.h).
+void DeltaPose(const double* A, const double* B, double* delta_position_m, double* delta_rotation_deg) {
+  double R[9], d[3], p[3];
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) {
+      double s = 0.0;
+      for (int k = 0; k < 3; ++k) s += A[k * 4 + i] * B[k * 4 + j];  // R_map^T * R_ransac
+      R[i * 3 + j] = s;
+    }
+  for (int k = 0; k < 3; ++k) d[k] = B[k * 4 + 3] - A[k * 4 + 3];
+  for (int i = 0; i < 3; ++i) p[i] = A[0 * 4 + i] * d[0] + A[1 * 4 + i] * d[1] + A[2 * 4 + i] * d[2];
+  *delta_position_m = std::sqrt(p[0] * p[0] + p[1] * p[1] + p[2] * p[2]);
+  double w, x, y, z;
+  const double t = R[0] + R[4] + R[8];
+  if (t > 0.0) {
+    double r = std::sqrt(t + 1.0);
+    w = 0.5 * r;
+    r = 0.5 / r;
+    x = (R[7] - R[5]) * r;
+    y = (R[2] - R[6]) * r;
+    z = (R[3] - R[1]) * r;
+  } else {
+    int i = 0;
+    if (R[4] > R[0]) i = 1;
+    if (R[8] > R[i * 3 + i]) i = 2;
+    const int j = (i + 1) % 3, k = (j + 1) % 3;
+    double r = std::sqrt(R[i * 3 + i] - R[j * 3 + j] - R[k * 3 + k] + 1.0);
+    double v[3];
+    v[i] = 0.5 * r;
+    r = 0.5 / r;
+    w = (R[k * 3 + j] - R[j * 3 + k]) * r;
+    v[j] = (R[j * 3 + i] + R[i * 3 + j]) * r;
+    v[k] = (R[k * 3 + i] + R[i * 3 + k]) * r;
+    x = v[0];
+    y = v[1];
+    z = v[2];
+  }
+  const double n = std::sqrt(x * x + y * y + z * z);
+  const double angle = n != 0.0 ? 2.0 * std::atan2(n, std::fabs(w)) : 0.0;
+  *delta_rotation_deg = angle * (180.0 / M_PI);
+}
+
+bool DeltaPoseGate(const double* T_G_I_map, const double* T_G_I_ransac, double max_delta_position_m,
+                   double max_delta_rotation_deg) {
+  if (!(max_delta_position_m >= 0.0 || max_delta_rotation_deg >= 0.0)) return true;
+  double dp, dr;
+  DeltaPose(T_G_I_map, T_G_I_ransac, &dp, &dr);
+  const bool is_distance_ok = max_delta_position_m < 0.0 || dp <= max_delta_position_m;
+  const bool is_rotation_ok = max_delta_rotation_deg < 0.0 || dr <= max_delta_rotation_deg;
+  return is_distance_ok && is_rotation_ok;
+}
+
 }  // namespace lc_oracle

@@ -486,3 +486,14 @@ def handle_loop_closure(keypoints, frame_index, keypoint_index, landmarks, cams,
                 iterations=int(sc[3]), inliers=inl[:sc[4]].copy(), inlier_distances=inl_d[:sc[4]].copy(),
                 model_indices=sc[5:9].copy(), best_per_keypoint=best[:sc[9]].copy(),
                 inlier_ratio=ratio.value, T=T)
+
+
+def delta_pose_gate(T_map, T_ransac, max_pos_m, max_rot_deg):
+    """handleLoopClosure's topological gate (loop-closure-handler.cc:424-455).
+    Returns (passes, delta_position_m, delta_rotation_deg)."""
+    a, b = _f64(np.asarray(T_map).reshape(12)), _f64(np.asarray(T_ransac).reshape(12))
+    d = np.zeros(2, np.float64)
+    lib().lco_delta_pose_gate.restype = C.c_int
+    ok = lib().lco_delta_pose_gate(_p(a, c_double_p), _p(b, c_double_p), C.c_double(max_pos_m),
+                                   C.c_double(max_rot_deg), _p(d, c_double_p))
+    return bool(ok), float(d[0]), float(d[1])

@@ -35,7 +35,7 @@ def test_struct_layouts_match_header():
     assert capi.MATCH_DTYPE.itemsize == 32
     assert capi.CAMERA_DTYPE.itemsize == 8 * 4 + 8 + 8 * 4 + 8 * 9 + 8 * 3
     assert capi.POSE_DTYPE.itemsize == 4 * 10 + 8 + 96
-    assert ctypes.sizeof(capi.RansacSettings) == 32
+    assert ctypes.sizeof(capi.RansacSettings) == 48
 
 
 def test_default_settings_are_the_reference_flags():

@@ -4,7 +4,7 @@ verdicts bit-exact; transforms within 1e-6 m / 1e-6 rad (north_star) — in prac
 import numpy as np
 import pytest
 
-from maplab_b200 import capi
+from maplab_b200 import capi, synthetic
 from oracle import pyoracle as po
 from helpers import small_world
 
@@ -142,3 +142,42 @@ def test_ransac_fisheye_camera():
     rng = np.random.default_rng(9)
     cams = _cams(rng, 2, fisheye=True)
     _check(cams, [_problem(rng, cams, 150, 0.3)[:4], _problem(rng, cams, 70, 0.5)[:4]])
+
+
+def test_delta_pose_gate_matches_oracle():
+    # handleLoopClosure's topological gate (loop-closure-handler.cc:424-455): off by default, needs
+    # the query vertices' current poses, rejects closures that move the vertex too far
+    from helpers import frames_of, small_world
+    m, blob, _, q = small_world(num_queries=12)
+    det = capi.Detector(blob, capi.default_settings(num_nearest_neighbors=6))
+    det.insert_batch(frames_of(m["frames"]), det.project(m["bits"]), m["landmarks"])
+    det.set_landmark_positions(m["landmark_xyz"])
+    cams = capi.make_cameras([synthetic.camera_dict()])
+    qframes = frames_of(q["frames"])
+    base = det.query_batch(qframes, q["bits"], q["keypoints"], cams)["results"]
+    assert base["accepted"].sum() >= 6
+    # priors = ground truth poses perturbed by growing offsets / yaw angles
+    rng = np.random.default_rng(3)
+    priors = q["T_G_I"].copy()
+    for i in range(len(priors)):
+        priors[i, :, 3] += rng.normal(size=3) * 0.08 * i
+        a = 0.01 * i
+        Ry = np.array([[np.cos(a), 0, np.sin(a)], [0, 1, 0], [-np.sin(a), 0, np.cos(a)]])
+        priors[i, :, :3] = priors[i, :, :3] @ Ry
+    for max_pos, max_rot in [(0.5, -1.0), (-1.0, 3.0), (0.6, 4.0), (1e9, 1e9)]:
+        rs = capi.default_ransac_settings(max_delta_position_m=max_pos, max_delta_rotation_deg=max_rot)
+        det.set_query_priors(priors)
+        got = det.query_batch(qframes, q["bits"], q["keypoints"], cams, rs=rs)["results"]
+        exp = base["accepted"].copy()
+        for i in range(len(exp)):
+            if exp[i]:
+                ok, _, _ = po.delta_pose_gate(priors[i], base["T_G_I"][i], max_pos, max_rot)
+                exp[i] = 1 if ok else 0
+        assert np.array_equal(got["accepted"], exp)
+        assert got["T_G_I"].tobytes() == base["T_G_I"].tobytes()     # the gate only changes the verdict
+    assert 0 < exp.sum()                                              # (1e9, 1e9): nothing rejected
+    rs = capi.default_ransac_settings(max_delta_position_m=0.5)
+    det.set_query_priors(priors)
+    assert det.query_batch(qframes, q["bits"], q["keypoints"], cams, rs=rs)["results"]["accepted"].sum() < base["accepted"].sum()
+    with pytest.raises(capi.MlcError):                                # priors were consumed by the last call
+        det.query_batch(qframes, q["bits"], q["keypoints"], cams, rs=rs)
