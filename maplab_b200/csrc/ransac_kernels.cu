@@ -426,15 +426,49 @@ __global__ void __launch_bounds__(128) ransac_sample_kernel(RansacArgs a, Proble
   const int64_t off = a.offsets[pi];
   const int n = static_cast<int>(a.offsets[pi + 1] - off);
   int32_t* shuf = a.shuffled + off;
-  for (int t = 0; t < want; ++t) {
-    for (int i = 0; i < 4; ++i) {
-      const int j = i + a.rnd_stream[s.stream_pos + 4 * t + i] % (n - i);
-      const int32_t tmp = shuf[i];
-      shuf[i] = shuf[j];
-      shuf[j] = tmp;
+  if (n >= 4) {
+    // The partial Fisher-Yates only ever moves entries through positions 0..3: keep those four in
+    // registers, so that one sample costs one round of independent loads instead of a chain of
+    // dependent global read-modify-writes.
+    int32_t s4[4] = {shuf[0], shuf[1], shuf[2], shuf[3]};
+    for (int t = 0; t < want; ++t) {
+      int r4[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) r4[i] = __ldg(a.rnd_stream + s.stream_pos + 4 * t + i);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int j = i + r4[i] % (n - i);
+        if (j < 4) {
+          const int32_t vi = s4[i];
+          int32_t vj = s4[0];
+#pragma unroll
+          for (int q = 1; q < 4; ++q) vj = (j == q) ? s4[q] : vj;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) s4[q] = (q == j) ? vi : s4[q];
+          s4[i] = vj;  // after the write of position j: i == j leaves the entry unchanged
+        } else {
+          const int32_t tmp = shuf[j];
+          shuf[j] = s4[i];
+          s4[i] = tmp;
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) h[t].sel[i] = s4[i];
+      h[t].active = 1;
     }
-    for (int i = 0; i < 4; ++i) h[t].sel[i] = shuf[i];
-    h[t].active = 1;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) shuf[i] = s4[i];
+  } else {
+    for (int t = 0; t < want; ++t) {
+      for (int i = 0; i < 4; ++i) {
+        const int j = i + a.rnd_stream[s.stream_pos + 4 * t + i] % (n - i);
+        const int32_t tmp = shuf[i];
+        shuf[i] = shuf[j];
+        shuf[j] = tmp;
+      }
+      for (int i = 0; i < 4; ++i) h[t].sel[i] = shuf[i];
+      h[t].active = 1;
+    }
   }
   for (int t = want; t < kHyp; ++t) h[t].active = 0;
   s.stream_pos += 4 * want;
@@ -766,20 +800,31 @@ __global__ void __launch_bounds__(128) ransac_update_kernel(RansacArgs a, Proble
       const Hypothesis* h = hyp + pi * kHyp;
       const int n = static_cast<int>(a.offsets[pi + 1] - a.offsets[pi]);
       const int max_skip = a.max_iterations * 10;
-      for (int t = 0; t < kHyp && h[t].active; ++t) {
+      // verdicts of all speculated hypotheses first (independent loads), then the sequential replay
+      // on registers; the winning model is copied once at the end
+      int h_active[kHyp], h_ok[kHyp], h_count[kHyp];
+#pragma unroll
+      for (int t = 0; t < kHyp; ++t) {
+        h_active[t] = h[t].active;
+        h_ok[t] = h[t].model_ok;
+        h_count[t] = h[t].count;
+      }
+      int best_t = -1;
+#pragma unroll
+      for (int t = 0; t < kHyp; ++t) {
+        if (!h_active[t]) break;
         if (!(static_cast<double>(s.iterations) < s.k && s.skipped < max_skip)) {
           s.done = 1;
           break;
         }
-        if (!h[t].model_ok) {
+        if (!h_ok[t]) {
           ++s.skipped;
           continue;
         }
-        if (h[t].count > s.best) {
-          s.best = h[t].count;
+        if (h_count[t] > s.best) {
+          s.best = h_count[t];
           s.have_model = 1;
-          for (int i = 0; i < 12; ++i) s.best_model[i] = h[t].model[i];
-          for (int i = 0; i < 4; ++i) s.best_sel[i] = h[t].sel[i];
+          best_t = t;
           const double w = static_cast<double>(s.best) / static_cast<double>(n);
           double p_no_outliers = 1.0 - pow(w, 4.0);
           p_no_outliers = fmax(2.220446049250313e-16, p_no_outliers);
@@ -791,6 +836,10 @@ __global__ void __launch_bounds__(128) ransac_update_kernel(RansacArgs a, Proble
           s.done = 1;
           break;
         }
+      }
+      if (best_t >= 0) {
+        for (int i = 0; i < 12; ++i) s.best_model[i] = h[best_t].model[i];
+        for (int i = 0; i < 4; ++i) s.best_sel[i] = h[best_t].sel[i];
       }
       if (!s.done && !(static_cast<double>(s.iterations) < s.k && s.skipped < max_skip)) s.done = 1;
       still = s.done ? 0 : 1;
