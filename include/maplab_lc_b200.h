@@ -231,6 +231,28 @@ int mlc_set_landmark_positions(mlc_detector* d, const double* xyz, int64_t n);
  * priors the call fails, like the reference's CHECK(query_vertex_id.isValid()). */
 int mlc_set_query_priors(mlc_detector* d, const double* T_G_I, int64_t num_vertices);
 
+/* Mission-level alignment after the queries.
+ * common::transformationRansac (common/maplab-common/include/maplab-common/geometry-inl.h:113-182),
+ * called by LoopDetectorNode::detectLoopClosuresMissionToDatabase
+ * (LCH/src/loop-detector-node.cc:923-933) on the per-vertex T_G_M samples: every draw picks one
+ * sample as hypothesis, inliers are the samples within both thresholds of it, the first hypothesis
+ * whose inlier count beats the best so far (initially {0}) wins; the result is the least-squares
+ * quaternion average (geometry.cc:9-31; the sign of the quaternion is not defined) and the mean
+ * position of the winner's inliers. Quaternions are Eigen coeffs() order (x, y, z, w). */
+typedef struct mlc_alignment_settings {
+  int32_t num_iterations;           /* --anchor_transform_ransac_num_interations (2000) */
+  int32_t rng_mapping;              /* libstdc++ uniform_int_distribution: 1 = GCC>=11, 0 = GCC<=10 */
+  double max_orientation_error_rad; /* --anchor_transform_ransac_max_orientation_error_rad (0.174) */
+  double max_position_error_m;      /* --anchor_transform_ransac_max_position_error_m (2.0) */
+  uint32_t seed;                    /* the reference seeds from std::random_device */
+  uint32_t pad_;
+} mlc_alignment_settings;
+void mlc_default_alignment_settings(mlc_alignment_settings* s);
+/* inlier_indices: room for n entries (ascending), may be NULL. */
+int mlc_transformation_ransac(mlc_detector* d, const double* quats_xyzw, const double* positions, int64_t n,
+                              const mlc_alignment_settings* settings, double* out_quat_xyzw, double* out_position,
+                              int32_t* inlier_indices, int32_t* num_inliers);
+
 /* Database persistence (no reference counterpart: maplab rebuilds the loop-closure database for
  * every `lc` / `aam` / `relax` invocation and per mission, LCH/src/loop-detector-node.cc:273-339,
  * vi-map-merger.cc:71-78). mlc_save_index writes the built index — keyframe headers, projected

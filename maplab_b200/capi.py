@@ -21,6 +21,7 @@ EXPORTS = [
     "mlc_find_batch", "mlc_find_batch_bits", "mlc_find_from_knn_device", "mlc_pnp_ransac_batch",
     "mlc_coarse_device", "mlc_scan_device", "mlc_last_stage_ms", "mlc_set_landmark_positions", "mlc_query_batch", "mlc_query_batch_device", "mlc_query_from_knn_device",
     "mlc_score", "mlc_save_index", "mlc_load_index", "mlc_set_query_priors",
+    "mlc_default_alignment_settings", "mlc_transformation_ransac",
 ]
 
 
@@ -56,6 +57,12 @@ class RansacSettings(C.Structure):
                 ("min_inlier_ratio", C.c_double), ("ransac_pixel_sigma", C.c_double),
                 ("seed", C.c_uint32), ("rng_mapping", C.c_int32),
                 ("max_delta_position_m", C.c_double), ("max_delta_rotation_deg", C.c_double)]
+
+
+class AlignmentSettings(C.Structure):
+    _fields_ = [("num_iterations", C.c_int32), ("rng_mapping", C.c_int32),
+                ("max_orientation_error_rad", C.c_double), ("max_position_error_m", C.c_double),
+                ("seed", C.c_uint32), ("pad_", C.c_uint32)]
 
 
 class MlcError(RuntimeError):
@@ -239,6 +246,26 @@ class Detector:
         """Current poses of the query vertices of the next query call (delta-pose gate)."""
         t = np.ascontiguousarray(T_G_I, np.float64).reshape(-1, 12)
         _check(lib().mlc_set_query_priors(self._h, t.ctypes.data_as(C.c_void_p), C.c_int64(len(t))))
+
+    def transformation_ransac(self, quats_xyzw, positions, **kw):
+        """common::transformationRansac (geometry-inl.h:113-182) on the device.
+        Returns (quaternion xyzw, position, ascending inlier indices)."""
+        s = AlignmentSettings()
+        lib().mlc_default_alignment_settings(C.byref(s))
+        for k, v in kw.items():
+            if not hasattr(s, k):
+                raise AttributeError(k)
+            setattr(s, k, v)
+        q = np.ascontiguousarray(quats_xyzw, np.float64).reshape(-1, 4)
+        p = np.ascontiguousarray(positions, np.float64).reshape(-1, 3)
+        oq, op = np.zeros(4, np.float64), np.zeros(3, np.float64)
+        inl = np.zeros(max(len(q), 1), np.int32)
+        cnt = C.c_int32(0)
+        _check(lib().mlc_transformation_ransac(self._h, q.ctypes.data_as(C.c_void_p), p.ctypes.data_as(C.c_void_p),
+                                               C.c_int64(len(q)), C.byref(s), oq.ctypes.data_as(C.c_void_p),
+                                               op.ctypes.data_as(C.c_void_p), inl.ctypes.data_as(C.c_void_p),
+                                               C.byref(cnt)))
+        return oq, op, inl[:cnt.value].copy()
 
     def save_index(self, path):
         _check(lib().mlc_save_index(self._h, str(path).encode()))

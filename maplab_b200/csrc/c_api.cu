@@ -235,6 +235,25 @@ int mlc_set_query_priors(mlc_detector* d, const double* T_G_I, int64_t num_verti
   d->impl.SetQueryPriors(T_G_I, num_vertices);
   return 0;
 }
+void mlc_default_alignment_settings(mlc_alignment_settings* s) {
+  s->num_iterations = 2000;
+  s->rng_mapping = 1;
+  s->max_orientation_error_rad = 0.174;
+  s->max_position_error_m = 2.0;
+  s->seed = 0u;
+  s->pad_ = 0u;
+}
+int mlc_transformation_ransac(mlc_detector* d, const double* quats_xyzw, const double* positions, int64_t n,
+                              const mlc_alignment_settings* settings, double* out_quat_xyzw, double* out_position,
+                              int32_t* inlier_indices, int32_t* num_inliers) {
+  MLC_REQUIRE(d && quats_xyzw && positions && settings && out_quat_xyzw && out_position && num_inliers,
+              "mlc_transformation_ransac: null argument");
+  std::string err;
+  return d->impl.TransformationRansac(quats_xyzw, positions, n, *settings, out_quat_xyzw, out_position,
+                                      inlier_indices, num_inliers, &err)
+             ? 0
+             : Fail(err);
+}
 int mlc_save_index(mlc_detector* d, const char* path) {
   MLC_REQUIRE(d && path, "mlc_save_index: null argument");
   std::string err;

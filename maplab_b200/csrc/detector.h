@@ -108,6 +108,9 @@ class Detector {
     priors_.assign(T_G_I, T_G_I + 12 * n);
     have_priors_ = true;
   }
+  bool TransformationRansac(const double* quats, const double* positions, int64_t n,
+                            const mlc_alignment_settings& as, double* out_quat, double* out_pos,
+                            int32_t* inlier_indices, int32_t* num_inliers, std::string* err);
   bool SaveIndex(const char* path, std::string* err);
   bool LoadIndex(const char* path, std::string* err);
   // Fused query: project -> kNN -> kernel 3 -> correspondence gather -> kernel 4.

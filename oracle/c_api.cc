@@ -591,4 +591,15 @@ int lco_delta_pose_gate(const double* T_map, const double* T_ransac, double max_
   DeltaPose(T_map, T_ransac, &delta[0], &delta[1]);
   return DeltaPoseGate(T_map, T_ransac, max_pos_m, max_rot_deg) ? 1 : 0;
 }
+int lco_transformation_ransac(const double* quats, const double* positions, int n, int num_iterations,
+                              double thr_rad, double thr_m, uint32_t seed, int rng_mapping, double* out_quat,
+                              double* out_pos, int* inlier_indices) {
+  return TransformationRansac(quats, positions, n, num_iterations, thr_rad, thr_m, seed, rng_mapping,
+                              out_quat, out_pos, inlier_indices);
+}
+void lco_uniform_indices(uint32_t seed, int mapping, uint32_t n, int count, int* out) {
+  RansacRng rng(seed, mapping);
+  for (int i = 0; i < count; ++i) out[i] = UniformIndex(&rng, n, mapping);
+}
+void lco_yaw_only(const double* q, double* out) { YawOnly(q, out); }
 }  // extern "C"

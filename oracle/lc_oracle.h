@@ -361,4 +361,18 @@ void DeltaPose(const double* T_G_I_map, const double* T_G_I_ransac, double* delt
 bool DeltaPoseGate(const double* T_G_I_map, const double* T_G_I_ransac, double max_delta_position_m,
                    double max_delta_rotation_deg);
 
+// ---------------------------------------------------------------------------
+// mission-level alignment (oracle/alignment.cc)
+// ---------------------------------------------------------------------------
+int UniformIndex(RansacRng* rng, uint32_t n, int mapping);
+double AngularDistance(const double* qa_xyzw, const double* qb_xyzw);
+bool PoseIsInlier(const double* qa, const double* pa, const double* qb, const double* pb, double thr_rad,
+                  double thr_m);
+void LsAverageQuaternion(const double* quats, const int* members, int n, double out[4]);
+// returns num_inliers; inlier_indices has room for n entries
+int TransformationRansac(const double* quats, const double* positions, int n, int num_iterations,
+                         double thr_rad, double thr_m, uint32_t seed, int rng_mapping, double out_quat[4],
+                         double out_pos[3], int* inlier_indices);
+void YawOnly(const double q[4], double out[4]);
+
 }  // namespace lc_oracle

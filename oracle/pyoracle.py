@@ -497,3 +497,31 @@ def delta_pose_gate(T_map, T_ransac, max_pos_m, max_rot_deg):
     ok = lib().lco_delta_pose_gate(_p(a, c_double_p), _p(b, c_double_p), C.c_double(max_pos_m),
                                    C.c_double(max_rot_deg), _p(d, c_double_p))
     return bool(ok), float(d[0]), float(d[1])
+
+
+def transformation_ransac(quats_xyzw, positions, num_iterations, thr_rad, thr_m, seed, rng_mapping=1):
+    """common::transformationRansac (geometry-inl.h:113-182). Returns (quat xyzw, position, inlier indices)."""
+    q = _f64(np.asarray(quats_xyzw).reshape(-1, 4))
+    p = _f64(np.asarray(positions).reshape(-1, 3))
+    n = len(q)
+    oq, op = np.zeros(4, np.float64), np.zeros(3, np.float64)
+    inl = np.zeros(n, np.int32)
+    lib().lco_transformation_ransac.restype = C.c_int
+    k = lib().lco_transformation_ransac(_p(q, c_double_p), _p(p, c_double_p), n, num_iterations,
+                                        C.c_double(thr_rad), C.c_double(thr_m), C.c_uint32(seed), rng_mapping,
+                                        _p(oq, c_double_p), _p(op, c_double_p), _p(inl, c_int_p))
+    return oq, op, inl[:k].copy()
+
+
+def uniform_indices(seed, mapping, n, count):
+    """libstdc++ uniform_int_distribution<int>(0, n-1) over mt19937(seed): first `count` draws."""
+    out = np.zeros(count, np.int32)
+    lib().lco_uniform_indices(C.c_uint32(seed), mapping, C.c_uint32(n), count, _p(out, c_int_p))
+    return out
+
+
+def yaw_only(q_xyzw):
+    q = _f64(np.asarray(q_xyzw).reshape(4))
+    out = np.zeros(4, np.float64)
+    lib().lco_yaw_only(_p(q, c_double_p), _p(out, c_double_p))
+    return out

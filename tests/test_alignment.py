@@ -1,0 +1,93 @@
+"""Mission-level alignment: common::transformationRansac + LS quaternion average.
+CPU: the oracle's restatement of libstdc++'s uniform_int_distribution<int>(0, n-1) is pinned against
+the real std::uniform_int_distribution of this image's g++ (a tiny program compiled on the fly), and the
+oracle RANSAC recovers a planted alignment. GPU: mlc_transformation_ransac == oracle (inlier set and
+count exact, pose to 1e-9; the quaternion sign is not defined by the reference)."""
+import os
+import shutil
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle import pyoracle as po
+
+
+def _rot(rv):
+    rv = np.asarray(rv, np.float64)
+    a = np.linalg.norm(rv)
+    if a == 0:
+        return np.array([0, 0, 0, 1.0])
+    return np.concatenate([np.sin(a / 2) * rv / a, [np.cos(a / 2)]])
+
+
+def _qmul(a, b):  # Hamilton, (x, y, z, w)
+    ax, ay, az, aw = a
+    bx, by, bz, bw = b
+    return np.array([aw * bx + ax * bw + ay * bz - az * by, aw * by - ax * bz + ay * bw + az * bx,
+                     aw * bz + ax * by - ay * bx + az * bw, aw * bw - ax * bx - ay * by - az * bz])
+
+
+def _samples(n, seed, outlier_every=3):
+    rng = np.random.default_rng(seed)
+    q_true, p_true = _rot([0.02, -0.01, 0.7]), np.array([3.0, -2.0, 0.5])
+    qs, ps = [], []
+    for i in range(n):
+        if i % outlier_every == 0:
+            qs.append(_rot(rng.normal(size=3)))
+            ps.append(rng.normal(size=3) * 5)
+        else:
+            qs.append(_qmul(q_true, _rot(rng.normal(size=3) * 0.01)))
+            ps.append(p_true + rng.normal(size=3) * 0.05)
+    return np.array(qs), np.array(ps), q_true, p_true
+
+
+def _angle(qa, qb):
+    return 2 * np.arctan2(np.linalg.norm(_qmul(qa, qb * [-1, -1, -1, 1])[:3]), abs(_qmul(qa, qb * [-1, -1, -1, 1])[3]))
+
+
+@pytest.mark.skipif(shutil.which("g++") is None, reason="needs g++")
+def test_uniform_index_matches_this_libstdcxx(tmp_path):
+    src = tmp_path / "u.cc"
+    src.write_text('#include <random>\n#include <cstdio>\nint main(int c, char** v){ unsigned seed = atoi(v[1]); int n = atoi(v[2]);'
+                   ' std::mt19937 g(seed); std::uniform_int_distribution<> d(0, n - 1);'
+                   ' for (int i = 0; i < 64; ++i) printf("%d ", d(g)); return 0; }\n')
+    exe = tmp_path / "u"
+    subprocess.check_call(["g++", "-O1", "-include", "cstdlib", "-o", str(exe), str(src)])
+    major = int(subprocess.check_output(["g++", "-dumpversion"]).decode().split(".")[0])
+    mapping = 1 if major >= 11 else 0
+    for seed, n in [(12345, 7), (1, 1000), (99, 3), (2024, 1 << 20), (5, 3000000000 % (1 << 31))]:
+        ref = [int(x) for x in subprocess.check_output([str(exe), str(seed), str(n)]).decode().split()]
+        assert po.uniform_indices(seed, mapping, n, 64).tolist() == ref
+
+
+def test_oracle_transformation_ransac_recovers_planted_alignment():
+    q, p, q_true, p_true = _samples(90, 0)
+    oq, op, inl = po.transformation_ransac(q, p, 2000, 0.174, 2.0, 42)
+    assert len(inl) == 60 and all(i % 3 != 0 for i in inl)
+    assert np.abs(op - p_true).max() < 0.05 and _angle(oq, q_true) < 0.01
+    # one sample: returned as is (geometry-inl.h:128-132); no iterations: {0} wins
+    oq, op, inl = po.transformation_ransac(q[:1], p[:1], 2000, 0.174, 2.0, 42)
+    assert np.array_equal(oq, q[0]) and np.array_equal(op, p[0]) and inl.tolist() == [0]
+    oq, op, inl = po.transformation_ransac(q, p, 0, 0.174, 2.0, 42)
+    assert inl.tolist() == [0] and np.array_equal(op, p[0])
+    yaw = po.yaw_only(oq)
+    assert yaw[0] == 0 and yaw[1] == 0 and abs(np.linalg.norm(yaw) - 1) < 1e-12
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,seed,mapping,iters", [(90, 42, 1, 2000), (1500, 7, 1, 2000), (300, 3, 0, 50),
+                                                  (2, 1, 1, 10), (1, 1, 1, 10), (64, 5, 1, 0)])
+def test_device_transformation_ransac_matches_oracle(n, seed, mapping, iters):
+    from maplab_b200 import capi
+    from helpers import small_world
+    _, blob, _, _ = small_world()
+    det = capi.Detector(blob)
+    q, p, _, _ = _samples(n, seed)
+    eq, ep, einl = po.transformation_ransac(q, p, iters, 0.174, 2.0, seed, mapping)
+    gq, gp, ginl = det.transformation_ransac(q, p, num_iterations=iters, seed=seed, rng_mapping=mapping)
+    assert ginl.tolist() == einl.tolist()
+    assert np.abs(gp - ep).max() <= 1e-9
+    assert min(np.abs(gq - eq).max(), np.abs(gq + eq).max()) <= 1e-9
+    with pytest.raises(capi.MlcError):
+        det.transformation_ransac(q[:0], p[:0])
