@@ -91,3 +91,21 @@ def test_device_transformation_ransac_matches_oracle(n, seed, mapping, iters):
     assert min(np.abs(gq - eq).max(), np.abs(gq + eq).max()) <= 1e-9
     with pytest.raises(capi.MlcError):
         det.transformation_ransac(q[:0], p[:0])
+
+
+@pytest.mark.skipif(shutil.which("g++") is None, reason="needs g++")
+def test_opengv_random_stream_matches_this_libstdcxx(tmp_path):
+    # opengv's SampleConsensusProblem::rnd(): uniform_int_distribution<int>(0, INT_MAX) over mt19937
+    # (SampleConsensusProblem.hpp:34-46, :157-161) — the oracle's stream, which the device
+    # RANSAC consumes, against the real distribution of this image's libstdc++
+    src = tmp_path / "r.cc"
+    src.write_text('#include <random>\n#include <climits>\n#include <cstdio>\n#include <cstdlib>\n'
+                   'int main(int c, char** v){ std::mt19937 g(atoi(v[1])); std::uniform_int_distribution<int> d(0, INT_MAX);'
+                   ' for (int i = 0; i < 256; ++i) printf("%d ", d(g)); return 0; }\n')
+    exe = tmp_path / "r"
+    subprocess.check_call(["g++", "-O1", "-o", str(exe), str(src)])
+    major = int(subprocess.check_output(["g++", "-dumpversion"]).decode().split(".")[0])
+    mapping = 1 if major >= 11 else 0
+    for seed in (12345, 1, 987654321):
+        ref = [int(x) for x in subprocess.check_output([str(exe), str(seed)]).decode().split()]
+        assert po.rng_stream(seed, mapping, 256).tolist() == ref
