@@ -151,6 +151,7 @@ class Detector {
   int* h_remaining_ = nullptr;  // pinned round counters
   std::vector<double> priors_;  // T_G_I of the query vertices of the next call (delta-pose gate)
   bool have_priors_ = false;
+  bool corr_grouped_ = false;  // next RansacOnDevice call: correspondences grouped by (camera, keypoint)
   static constexpr int kCopyChunks = 8;  // upper bound; 2 are used (tuned on B200, PCIe gen5)
   cudaEvent_t ev_copy_[kCopyChunks + 1] = {};
   cudaEvent_t ev0_ = nullptr, ev1_ = nullptr;

@@ -436,6 +436,7 @@ bool Detector::QueryFromKnn(const mlc_frame* frames, int64_t num_frames, const i
               "D2H matches", err))
       return false;
   }
+  corr_grouped_ = true;  // canonical order: (query frame, keypoint, database descriptor)
   return RansacOnDevice(rs, cams, num_cams, nvx, total, reinterpret_cast<const int64_t*>(tab + t_poff),
                         reinterpret_cast<const double*>(corr + c_kp), reinterpret_cast<const int32_t*>(corr + c_ci),
                         reinterpret_cast<const int32_t*>(corr + c_ki), reinterpret_cast<const double*>(corr + c_lm),

@@ -52,6 +52,7 @@ constexpr int kHypFirst = 12; // speculated in the first round (k is still unkno
 
 struct RansacArgs {
   int first_hyp;                // hypotheses speculated per problem in the first round
+  int grouped_by_keypoint;      // correspondences of one (camera, keypoint) are contiguous
   int64_t num_problems;
   const int64_t* offsets;
   const double* keypoints;      // 2 per correspondence
@@ -882,11 +883,24 @@ __global__ void __launch_bounds__(128) ransac_finalize_kernel(RansacArgs a, cons
       // best inlier per (camera, keypoint): smallest score, first index wins on ties
       bool is_best = true;
       const int cam = a.camera_index[off + i], kp = a.keypoint_index[off + i];
-      for (int j = 0; j < n && is_best; ++j) {
-        if (j == i || a.keypoint_index[off + j] != kp || a.camera_index[off + j] != cam) continue;
-        const double dj = Distance(pb, best_model, j);
-        if (!(dj < a.threshold)) continue;
-        if (dj < di || (dj == di && j < i)) is_best = false;
+      if (a.grouped_by_keypoint) {
+        // correspondences of one (camera, keypoint) are adjacent (the fused path emits them in
+        // canonical order): only the run around i has to be looked at
+        for (int dir = -1; dir <= 1 && is_best; dir += 2) {
+          for (int j = i + dir; j >= 0 && j < n && is_best; j += dir) {
+            if (a.keypoint_index[off + j] != kp || a.camera_index[off + j] != cam) break;
+            const double dj = Distance(pb, best_model, j);
+            if (!(dj < a.threshold)) continue;
+            if (dj < di || (dj == di && j < i)) is_best = false;
+          }
+        }
+      } else {
+        for (int j = 0; j < n && is_best; ++j) {
+          if (j == i || a.keypoint_index[off + j] != kp || a.camera_index[off + j] != cam) continue;
+          const double dj = Distance(pb, best_model, j);
+          if (!(dj < a.threshold)) continue;
+          if (dj < di || (dj == di && j < i)) is_best = false;
+        }
       }
       if (is_best) ++my_best;
       if (a.inlier_flags) a.inlier_flags[off + i] = is_best ? 3 : 1;
@@ -1106,6 +1120,8 @@ bool Detector::RansacOnDevice(const mlc_ransac_settings& rs, const mlc_camera* c
       !Cuda(cudaMemcpyAsync(scr + o_rnd, rnd_host_.data(), sizeof(int32_t) * rnd_len, cudaMemcpyHostToDevice, stream_), "H2D", err))
     return false;
   RansacArgs a;
+  a.grouped_by_keypoint = corr_grouped_ ? 1 : 0;
+  corr_grouped_ = false;  // one-shot, set by the fused path
   a.num_problems = num_problems;
   a.offsets = d_offsets;
   a.keypoints = d_keypoints;
