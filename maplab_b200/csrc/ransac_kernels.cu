@@ -46,13 +46,15 @@ enum {
 
 constexpr int N8 = 8;
 constexpr int kWarpsPerBlock = 4;
-constexpr int kHyp = 16;      // hypothesis slots per problem
+constexpr int kHyp = 16;      // hypothesis slots per problem (default)
+constexpr int kHypMax = 32;   // ... when the batch is small enough to speculate deeper for free
 constexpr int kRansacGroups = 6;  // problem groups pipelined on separate streams
 constexpr int kHypFirst = 12; // speculated in the first round (k is still unknown) when the batch fills the GPU
 
 struct RansacArgs {
   int first_hyp;                // hypotheses speculated per problem in the first round
   int grouped_by_keypoint;      // correspondences of one (camera, keypoint) are contiguous
+  int hyp_slots;                // hypothesis slots per problem (kHyp or kHypMax)
   int64_t num_problems;
   const int64_t* offsets;
   const double* keypoints;      // 2 per correspondence
@@ -408,12 +410,12 @@ __global__ void __launch_bounds__(128) ransac_sample_kernel(RansacArgs a, Proble
   const int64_t pi = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
   if (pi >= a.num_problems) return;
   ProblemState& s = st[pi];
-  Hypothesis* h = hyp + pi * kHyp;
+  Hypothesis* h = hyp + pi * a.hyp_slots;
   const int max_skip = a.max_iterations * 10;
   int want = a.first_hyp;
   if (s.stream_pos > 0) {
     const double need = ceil(s.k - static_cast<double>(s.iterations));
-    want = need >= static_cast<double>(kHyp) ? kHyp : (need <= 1.0 ? 1 : static_cast<int>(need));
+    want = need >= static_cast<double>(a.hyp_slots) ? a.hyp_slots : (need <= 1.0 ? 1 : static_cast<int>(need));
     const int room = a.max_iterations + 1 - s.iterations;  // iterations_ > max_iterations_ stops the loop
     if (want > room) want = room > 1 ? room : 1;
   }
@@ -421,7 +423,7 @@ __global__ void __launch_bounds__(128) ransac_sample_kernel(RansacArgs a, Proble
                    (s.stream_pos + 4 * want <= a.rnd_len);
   if (!run) {
     s.done = 1;
-    for (int t = 0; t < kHyp; ++t) h[t].active = 0;
+    for (int t = 0; t < a.hyp_slots; ++t) h[t].active = 0;
     return;
   }
   const int64_t off = a.offsets[pi];
@@ -471,7 +473,7 @@ __global__ void __launch_bounds__(128) ransac_sample_kernel(RansacArgs a, Proble
       h[t].active = 1;
     }
   }
-  for (int t = want; t < kHyp; ++t) h[t].active = 0;
+  for (int t = want; t < a.hyp_slots; ++t) h[t].active = 0;
   s.stream_pos += 4 * want;
 }
 
@@ -487,7 +489,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) gp3p_eliminate_kernel(Ran
   for (int64_t hi = static_cast<int64_t>(blockIdx.x) * kWarpsPerBlock + wib; hi < num_hyp; hi += warps) {
     Hypothesis& h = hyp[hi];
     if (!h.active) continue;
-    const Problem pb = MakeProblem(a, hi / kHyp);
+    const Problem pb = MakeProblem(a, hi / a.hyp_slots);
     // f (bearing rotated into the body frame), v (camera offset), p (world point) of the 3 points
     if (lane < 27) {
       const int which = lane / 9, i = (lane % 9) / 3, kk = lane % 3;
@@ -743,7 +745,7 @@ __global__ void __launch_bounds__(64) gp3p_candidate_kernel(RansacArgs a, Hypoth
   if (!h.active) return;
   int valid = 0;
   if (h.eig_ok && (h.wi[c] < 0.0001)) {  // main.cpp:400 (no fabs: negative imaginary parts pass)
-    const Problem pb = MakeProblem(a, hi / kHyp);
+    const Problem pb = MakeProblem(a, hi / a.hyp_slots);
     double sol[12], score;
     SolutionForEigenvalue(pb, h.M, h.wr[c], h.wi[c], h.fvp, h.sel[3], sol, &score);
     for (int i = 0; i < 12; ++i) h.cand_T[c][i] = sol[i];
@@ -775,7 +777,7 @@ __global__ void __launch_bounds__(128) ransac_score_kernel(RansacArgs a, Hypothe
   const int pick = (num == 1) ? first : min_index;  // a single solution is accepted as is
   int count = 0;
   if (pick >= 0) {
-    const Problem pb = MakeProblem(a, hi / kHyp);
+    const Problem pb = MakeProblem(a, hi / a.hyp_slots);
     double T[12];
     for (int i = 0; i < 12; ++i) T[i] = h.cand_T[pick][i];
     for (int i = lane; i < pb.n; i += 32)
@@ -798,44 +800,53 @@ __global__ void __launch_bounds__(128) ransac_update_kernel(RansacArgs a, Proble
   if (pi < a.num_problems) {
     ProblemState& s = st[pi];
     if (!s.done) {
-      const Hypothesis* h = hyp + pi * kHyp;
+      const Hypothesis* h = hyp + pi * a.hyp_slots;
       const int n = static_cast<int>(a.offsets[pi + 1] - a.offsets[pi]);
       const int max_skip = a.max_iterations * 10;
       // verdicts of all speculated hypotheses first (independent loads), then the sequential replay
       // on registers; the winning model is copied once at the end
-      int h_active[kHyp], h_ok[kHyp], h_count[kHyp];
-#pragma unroll
-      for (int t = 0; t < kHyp; ++t) {
-        h_active[t] = h[t].active;
-        h_ok[t] = h[t].model_ok;
-        h_count[t] = h[t].count;
-      }
       int best_t = -1;
+      bool stop = false;
+      for (int t0 = 0; t0 < a.hyp_slots && !stop; t0 += 8) {
+        int h_active[8], h_ok[8], h_count[8];
 #pragma unroll
-      for (int t = 0; t < kHyp; ++t) {
-        if (!h_active[t]) break;
-        if (!(static_cast<double>(s.iterations) < s.k && s.skipped < max_skip)) {
-          s.done = 1;
-          break;
+        for (int u = 0; u < 8; ++u) {
+          h_active[u] = h[t0 + u].active;
+          h_ok[u] = h[t0 + u].model_ok;
+          h_count[u] = h[t0 + u].count;
         }
-        if (!h_ok[t]) {
-          ++s.skipped;
-          continue;
-        }
-        if (h_count[t] > s.best) {
-          s.best = h_count[t];
-          s.have_model = 1;
-          best_t = t;
-          const double w = static_cast<double>(s.best) / static_cast<double>(n);
-          double p_no_outliers = 1.0 - pow(w, 4.0);
-          p_no_outliers = fmax(2.220446049250313e-16, p_no_outliers);
-          p_no_outliers = fmin(1.0 - 2.220446049250313e-16, p_no_outliers);
-          s.k = a.log_one_minus_p / log(p_no_outliers);
-        }
-        ++s.iterations;
-        if (s.iterations > a.max_iterations) {
-          s.done = 1;
-          break;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          if (stop) break;
+          if (!h_active[u]) {
+            stop = true;
+            break;
+          }
+          if (!(static_cast<double>(s.iterations) < s.k && s.skipped < max_skip)) {
+            s.done = 1;
+            stop = true;
+            break;
+          }
+          if (!h_ok[u]) {
+            ++s.skipped;
+            continue;
+          }
+          if (h_count[u] > s.best) {
+            s.best = h_count[u];
+            s.have_model = 1;
+            best_t = t0 + u;
+            const double w = static_cast<double>(s.best) / static_cast<double>(n);
+            double p_no_outliers = 1.0 - pow(w, 4.0);
+            p_no_outliers = fmax(2.220446049250313e-16, p_no_outliers);
+            p_no_outliers = fmin(1.0 - 2.220446049250313e-16, p_no_outliers);
+            s.k = a.log_one_minus_p / log(p_no_outliers);
+          }
+          ++s.iterations;
+          if (s.iterations > a.max_iterations) {
+            s.done = 1;
+            stop = true;
+            break;
+          }
         }
       }
       if (best_t >= 0) {
@@ -1094,7 +1105,7 @@ bool Detector::RansacOnDevice(const mlc_ransac_settings& rs, const mlc_camera* c
   focal /= (2.0 * static_cast<double>(num_cams));
   const double threshold = 1.0 - std::cos(std::atan(rs.ransac_pixel_sigma / focal));
   // draws: 4 per attempted sample; attempts <= max_iterations + 1 counted + 10 * max_iterations skipped
-  const int rnd_len = 4 * (11 * rs.num_ransac_iters + 2 + 2 * kHyp);  // worst case + speculation slack
+  const int rnd_len = 4 * (11 * rs.num_ransac_iters + 2 + 2 * kHypMax);  // worst case + speculation slack
   if (rnd_seed_ != rs.seed || rnd_mapping_ != rs.rng_mapping || static_cast<int>(rnd_host_.size()) != rnd_len) {
     rnd_host_.resize(rnd_len);
     HostRng rng(rs.seed, rs.rng_mapping);
@@ -1103,7 +1114,14 @@ bool Detector::RansacOnDevice(const mlc_ransac_settings& rs, const mlc_camera* c
     rnd_mapping_ = rs.rng_mapping;
   }
   DevBuf &b_scr = d_ransac_[1], &b_hyp = d_ransac_[2], &b_out = d_ransac_[3];
-  const int64_t num_hyp = num_problems * kHyp;
+  // small batches leave the GPU idle between the latency-bound rounds: deeper speculation
+  // (32 instead of 16 slots per problem) then saves whole rounds
+  int hyp_slots = (num_problems * kHypMax <= static_cast<int64_t>(sm_count_) * 60) ? kHypMax : kHyp;
+  if (const char* env = getenv("MLC_RANSAC_SLOTS")) {
+    const int v = atoi(env);
+    if (v == kHyp || v == kHypMax) hyp_slots = v;
+  }
+  const int64_t num_hyp = num_problems * hyp_slots;
   const size_t o_cam = 0;
   const size_t o_rnd = (sizeof(mlc_camera) * num_cams + 255) & ~static_cast<size_t>(255);
   const size_t o_bear = (o_rnd + sizeof(int32_t) * rnd_len + 255) & ~static_cast<size_t>(255);
@@ -1158,10 +1176,11 @@ bool Detector::RansacOnDevice(const mlc_ransac_settings& rs, const mlc_camera* c
   // latency-bound round. A batch that does not fill the resident hypothesis slots of the
   // elimination kernel speculates the full kHyp for free.
   const int64_t resident = static_cast<int64_t>(sm_count_) * elim_per_sm * kWarpsPerBlock;
-  a.first_hyp = (num_problems * kHyp <= resident + resident / 2) ? kHyp : kHypFirst;
+  a.hyp_slots = hyp_slots;
+  a.first_hyp = (num_problems * hyp_slots <= resident + resident / 2) ? hyp_slots : kHypFirst;
   if (const char* env = getenv("MLC_RANSAC_FIRST_HYP")) {
     const int v = atoi(env);
-    if (v >= 1 && v <= kHyp) a.first_hyp = v;
+    if (v >= 1 && v <= hyp_slots) a.first_hyp = v;
   }
   // The problems are dealt into groups that run the round pipeline on their own streams: the
   // stages are latency-bound kernels with long tails, and with staggered groups the tail of one
@@ -1190,7 +1209,7 @@ bool Detector::RansacOnDevice(const mlc_ransac_settings& rs, const mlc_camera* c
     ga[g].offsets = a.offsets + p0;     // correspondence arrays stay absolute
     ga[g].results = a.results + p0;
     g_state[g] = d_state + p0;
-    g_hyp[g] = d_hyp + p0 * kHyp;
+    g_hyp[g] = d_hyp + p0 * hyp_slots;
     g_stream[g] = g == 0 ? stream_ : ransac_stream_[g - 1];
     active[g] = p1 > p0;
     if (g > 0 && !Cuda(cudaStreamWaitEvent(g_stream[g], ev_ransac_[kRansacGroups], 0), "wait", err)) return false;
@@ -1207,7 +1226,7 @@ bool Detector::RansacOnDevice(const mlc_ransac_settings& rs, const mlc_camera* c
     for (int g = 0; g < groups; ++g) {
       if (!active[g]) continue;
       any = true;
-      const int64_t np = ga[g].num_problems, nh = np * kHyp;
+      const int64_t np = ga[g].num_problems, nh = np * hyp_slots;
       cudaStream_t st = g_stream[g];
       const unsigned elim_blocks = static_cast<unsigned>(std::min<int64_t>(
           (nh + kWarpsPerBlock - 1) / kWarpsPerBlock, static_cast<int64_t>(sm_count_) * elim_per_sm));
