@@ -703,14 +703,19 @@ __device__ bool HqrGroup(double* a, double* wr, double* wi, int L, unsigned gm) 
 }
 #undef A_
 
+// GPW = hypotheses (8-lane groups) per warp. The QR iteration is data dependent, so the groups of
+// one warp serialise each other's control flow; the kernel is latency bound with idle issue slots,
+// hence fewer groups per warp (idle lanes) finish sooner.
+template <int GPW>
 __global__ void __launch_bounds__(128) gp3p_eigen_kernel(Hypothesis* hyp, int64_t num_hyp) {
-  __shared__ double s_a[16][64];
-  __shared__ double s_w[16][16];
+  __shared__ double s_a[4 * GPW][64];
+  __shared__ double s_w[4 * GPW][16];
   const int lane = threadIdx.x & 31;
+  if (lane >= 8 * GPW) return;
   const int L = lane & 7;
-  const int g = threadIdx.x >> 3;  // group within the block
+  const int g = (threadIdx.x >> 5) * GPW + (lane >> 3);  // group within the block
   const unsigned gm = 0xFFu << (lane & 24);
-  const int64_t hi = static_cast<int64_t>(blockIdx.x) * 16 + g;
+  const int64_t hi = static_cast<int64_t>(blockIdx.x) * (4 * GPW) + g;
   if (hi >= num_hyp) return;   // whole group leaves together
   Hypothesis& h = hyp[hi];
   if (!h.active) return;
@@ -1220,6 +1225,11 @@ bool Detector::RansacOnDevice(const mlc_ransac_settings& rs, const mlc_camera* c
     ransac_init_kernel<<<blocks_of(ga[g].num_problems * 32, 128), 128, 0, g_stream[g]>>>(ga[g], g_state[g]);
     CountLaunch();
   }
+  int eigen_gpw = 4;  // 1 / 2 / 4 groups per warp measured: 1.54 / 1.47 / 1.47 ms RANSAC at 1000 problems
+  if (const char* env = getenv("MLC_EIGEN_GPW")) {
+    const int v = atoi(env);
+    if (v == 1 || v == 2 || v == 4) eigen_gpw = v;
+  }
   const int max_rounds = 11 * rs.num_ransac_iters + 4;  // >= one consumed sample per round
   for (int round = 0; round < max_rounds; ++round) {
     bool any = false;
@@ -1233,7 +1243,9 @@ bool Detector::RansacOnDevice(const mlc_ransac_settings& rs, const mlc_camera* c
       if (!Cuda(cudaMemsetAsync(d_remaining_all + g, 0, sizeof(int), st), "memset", err)) return false;
       ransac_sample_kernel<<<blocks_of(np, 128), 128, 0, st>>>(ga[g], g_state[g], g_hyp[g]);
       gp3p_eliminate_kernel<<<elim_blocks, kWarpsPerBlock * 32, smem, st>>>(ga[g], g_hyp[g], nh);
-      gp3p_eigen_kernel<<<blocks_of(nh, 16), 128, 0, st>>>(g_hyp[g], nh);
+      if (eigen_gpw == 1) gp3p_eigen_kernel<1><<<blocks_of(nh, 4), 128, 0, st>>>(g_hyp[g], nh);
+      else if (eigen_gpw == 2) gp3p_eigen_kernel<2><<<blocks_of(nh, 8), 128, 0, st>>>(g_hyp[g], nh);
+      else gp3p_eigen_kernel<4><<<blocks_of(nh, 16), 128, 0, st>>>(g_hyp[g], nh);
       gp3p_candidate_kernel<<<blocks_of(nh * 8, 64), 64, 0, st>>>(ga[g], g_hyp[g], nh);
       ransac_score_kernel<<<blocks_of(nh * 32, 128), 128, 0, st>>>(ga[g], g_hyp[g], nh);
       ransac_update_kernel<<<blocks_of(np, 128), 128, 0, st>>>(ga[g], g_state[g], g_hyp[g], d_remaining_all + g);
