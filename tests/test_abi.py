@@ -46,6 +46,12 @@ def test_default_settings_are_the_reference_flags():
     r = capi.default_ransac_settings()
     assert (r.min_inlier_count, r.num_ransac_iters, r.seed) == (10, 100, 12345)
     assert r.ransac_pixel_sigma == 2.0 and r.min_inlier_ratio == 0.0
+    assert r.max_delta_position_m == -1.0 and r.max_delta_rotation_deg == -1.0   # gates off
+    a = capi.AlignmentSettings()
+    capi.lib().mlc_default_alignment_settings(ctypes.byref(a))
+    assert (a.num_iterations, a.rng_mapping) == (2000, 1)                         # anchor_transform_* flags
+    assert a.max_orientation_error_rad == 0.174 and a.max_position_error_m == 2.0
+    assert ctypes.sizeof(capi.AlignmentSettings) == 32
 
 
 def test_vocabulary_roundtrip_and_errors():
