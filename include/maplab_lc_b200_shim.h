@@ -121,6 +121,56 @@ class LoopDetector {
     matches->resize(static_cast<size_t>(nm));
   }
 
+  // LoopDetectorNode::queryVertexInDatabase for a batch of vertices (loop-detector-node.cc:668-766,
+  // :819-873): frames of one vertex adjacent and in ascending camera index; one verdict per vertex.
+  // `inlier_matches` (optional) receives, per accepted vertex, the best-per-keypoint inlier matches
+  // (the reference's inlier_structure_matches).
+  void QueryBatch(const std::vector<mlc_frame>& frames, const uint8_t* descriptors, int bytes_per_descriptor,
+                  const double* keypoints_uv, const std::vector<mlc_camera>& cameras,
+                  const mlc_ransac_settings& ransac, std::vector<mlc_pose_result>* verdicts,
+                  std::vector<std::vector<mlc_match>>* inlier_matches = nullptr) const {
+    int64_t n = 0;
+    for (const mlc_frame& f : frames) n += f.num_descriptors;
+    verdicts->assign(frames.size(), mlc_pose_result{});
+    const int64_t cap = n * 16 + 16;
+    std::vector<mlc_match> matches(inlier_matches ? static_cast<size_t>(cap) : 0);
+    std::vector<uint8_t> flags(inlier_matches ? static_cast<size_t>(cap) : 0);
+    std::vector<int64_t> offsets(frames.size() + 1, 0);
+    int64_t nv = 0, nm = 0;
+    Check(mlc_query_batch(d_, frames.data(), static_cast<int64_t>(frames.size()), descriptors,
+                          bytes_per_descriptor, keypoints_uv, cameras.data(), static_cast<int>(cameras.size()),
+                          &ransac, verdicts->data(), &nv, inlier_matches ? matches.data() : nullptr, cap,
+                          offsets.data(), &nm, inlier_matches ? flags.data() : nullptr));
+    verdicts->resize(static_cast<size_t>(nv));
+    if (inlier_matches) {
+      inlier_matches->assign(static_cast<size_t>(nv), {});
+      for (int64_t v = 0; v < nv; ++v) {
+        if (!(*verdicts)[static_cast<size_t>(v)].accepted) continue;
+        for (int64_t i = offsets[v]; i < offsets[v + 1]; ++i)
+          if (flags[static_cast<size_t>(i)] == 3) (*inlier_matches)[static_cast<size_t>(v)].push_back(matches[static_cast<size_t>(i)]);
+      }
+    }
+  }
+  // map_->getVertex_T_G_I of the query vertices of the next QueryBatch (loop-closure-handler.cc:436-437);
+  // needed only with --lc_max_delta_position_m / --lc_max_delta_rotation_deg.
+  void SetQueryPriors(const double* T_G_I_3x4_rowmajor, int64_t num_vertices) {
+    Check(mlc_set_query_priors(d_, T_G_I_3x4_rowmajor, num_vertices));
+  }
+  void SetLandmarkPositions(const double* xyz, int64_t n) { Check(mlc_set_landmark_positions(d_, xyz, n)); }
+  void SaveIndex(const std::string& path) { Check(mlc_save_index(d_, path.c_str())); }
+  void LoadIndex(const std::string& path) { Check(mlc_load_index(d_, path.c_str())); }
+  // common::transformationRansac (geometry-inl.h:113-182); returns the number of inliers.
+  int TransformationRansac(const double* quats_xyzw, const double* positions, int64_t n,
+                           const mlc_alignment_settings& settings, double out_quat_xyzw[4], double out_position[3],
+                           std::vector<int32_t>* inlier_indices = nullptr) const {
+    std::vector<int32_t> tmp(static_cast<size_t>(n > 0 ? n : 1));
+    int32_t num = 0;
+    Check(mlc_transformation_ransac(d_, quats_xyzw, positions, n, &settings, out_quat_xyzw, out_position,
+                                    tmp.data(), &num));
+    if (inlier_indices) inlier_indices->assign(tmp.begin(), tmp.begin() + num);
+    return num;
+  }
+
   // loop_closure::IndexInterface::GetNNearestNeighborsForFeatures (index-interface.h:27-35).
   void GetNNearestNeighborsForFeatures(const float* query_features, int64_t n, int num_neighbors,
                                        int32_t* indices, float* distances) const {
