@@ -44,6 +44,8 @@ def parse_args():
     ap.add_argument("--no-scan-probe", action="store_true",
                     help="skip the extra scan-roofline measurement at the north-star shard size (N = 1 only)")
     ap.add_argument("--probe-landmarks", type=int, default=6_250_000)
+    ap.add_argument("--engine", default="imi", choices=["imi", "imipq"],
+                    help="--lc_detector_engine: imipq = product-quantised residuals (10 components x 16 centres)")
     return ap.parse_args()
 
 
@@ -105,12 +107,14 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def build_world(landmarks, queries, words):
+def build_world(landmarks, queries, words, engine="imi"):
     """Seeded synthetic map + queries + vocabulary (identical on every rank)."""
     from maplab_b200 import synthetic
     m = synthetic.make_map(landmarks, seed=1)
     stride = max(len(m["bits"]) // 100_000, 1)
-    blob, _ = synthetic.make_vocabulary(m["bits"][::stride][:100_000], num_words=words, seed=7)
+    blob, voc = synthetic.make_vocabulary(m["bits"][::stride][:100_000], num_words=words, seed=7)
+    if engine == "imipq":
+        blob = synthetic.add_product_quantizer(voc, 10, 16)
     q = synthetic.make_queries(m, queries, seed=11)
     return m, blob, q
 
@@ -239,8 +243,9 @@ def run_b200(args):
     # weak scaling: the map (hence every GPU's shard of the inverted lists) grows with the GPU count,
     # the query batch per step stays the same
     landmarks = args.landmarks * (world if args.scaling == "weak" else 1)
-    m, blob, q = build_world(landmarks, args.queries, args.words)
-    det = capi.Detector(blob, capi.default_settings(device=local, shard_rank=rank, shard_count=world))
+    m, blob, q = build_world(landmarks, args.queries, args.words, args.engine)
+    det = capi.Detector(blob, capi.default_settings(device=local, shard_rank=rank, shard_count=world,
+                                                    engine=1 if args.engine == "imipq" else 0))
     frames, proj, t_build = load_database(det, m)
     n_db = len(m["bits"])
     k = det.num_neighbors()
@@ -371,7 +376,7 @@ def run_b200(args):
                    "l2": "256 MiB flush buffer written between timed iterations",
                    "db_build_s": round(t_build, 3),
                    "accepted_loop_closures_per_step": accepted, "matches_per_step": num_matches},
-        "roofline": {"kernel": "imi_scan_kernel", "bound": "hbm", "achieved": achieved,
+        "roofline": {"kernel": "imi_scan_kernel" if args.engine == "imi" else "imipq_scan_kernel", "bound": "hbm", "achieved": achieved,
                      "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                      "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": scan_bytes_mean,
@@ -391,7 +396,9 @@ def run_b200(args):
                                    [round(float(x) / max(args.steps, 1), 4) for x in stage_acc]))
     if not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline(args, m, blob, q, proj, frames)
-    if world == 1 and not args.no_scan_probe:
+    if args.engine != "imi":
+        out["config"]["engine"] = args.engine
+    if world == 1 and not args.no_scan_probe and args.engine == "imi":
         out["projection"] = projection_probe(det, m, dev, hbm_peak)
         del det, m, q, proj, qbits_d, kp_d, flush
         torch.cuda.empty_cache()
@@ -401,9 +408,9 @@ def run_b200(args):
         dist.destroy_process_group()
 
 
-def oracle_with_db(m, blob, proj, frames):
+def oracle_with_db(m, blob, proj, frames, engine="imi"):
     from oracle import pyoracle as po
-    ora = po.Engine(blob)
+    ora = po.Engine(blob, po.default_settings(engine=1 if engine == "imipq" else 0))
     at = 0
     lm = m["landmarks"]
     nd = frames["num_descriptors"]
@@ -431,7 +438,7 @@ def cpu_query(ora, m, q, nq, threads):
 def cpu_baseline(args, m, blob, q, proj, frames):
     threads = os.cpu_count() or 1
     t0 = time.time()
-    ora = oracle_with_db(m, blob, proj, frames)
+    ora = oracle_with_db(m, blob, proj, frames, args.engine)
     t_build = time.time() - t0
     nq = args.cpu_queries or min(args.queries, max(8 * threads, 64))
     dt, r = cpu_query(ora, m, q, nq, threads)
@@ -455,7 +462,7 @@ def run_reference(args):
     from oracle import pyoracle as po
     threads = os.cpu_count() or 1
     landmarks = args.landmarks * (args.gpus if args.scaling == "weak" else 1)
-    m, blob, q = build_world(landmarks, args.queries, args.words)
+    m, blob, q = build_world(landmarks, args.queries, args.words, args.engine)
     frames = frames_array(m["frames"])
     ora0 = po.Engine(blob)
     n_db = len(m["bits"])
@@ -469,7 +476,7 @@ def run_reference(args):
     ts = [threading.Thread(target=work, args=(t,)) for t in range(threads)]
     [t.start() for t in ts]
     [t.join() for t in ts]
-    ora = oracle_with_db(m, blob, proj, frames)
+    ora = oracle_with_db(m, blob, proj, frames, args.engine)
     nq = args.cpu_queries or min(args.queries, max(4 * threads, 32))
     W = max(args.warmup, 1)
     for _ in range(W):

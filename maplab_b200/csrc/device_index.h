@@ -63,6 +63,8 @@ cudaError_t LaunchImiScan(int dim, const float* q, int64_t n_q, const int32_t* c
 struct PqParams {
   const float *words1 = nullptr, *words2 = nullptr, *centers1 = nullptr, *centers2 = nullptr;
   int sub_dim = 0, half_ncomp = 0, dim_per_comp = 0, num_centers = 0, num_words1 = 0, num_words2 = 0;
+  uint32_t magic_per_half = 0, magic_centers = 0;  // ceil(2^32 / d): t / d == __umulhi(t, magic) for small t
+  int vector_lut = 0;  // LUT fill with float4 centre loads (dim_per_comp == 1, aligned, centres % 4 == 0)
 };
 cudaError_t LaunchPqEncode(const PqParams& p, const float* desc, const int32_t* cells, int64_t n,
                            uint32_t* codes, cudaStream_t stream);

@@ -387,6 +387,7 @@ __global__ void pq_encode_kernel(PqParams p, const float* __restrict__ desc, con
   codes[i * 3 + 2] = out[2];
 }
 
+// Fallback for product quantisers whose look-up tables do not fit the fast kernel below.
 // GetNNearestNeighbors of the PQ index (…-quantization-index.h:181-288): one warp per query
 // descriptor. Per visited, non-empty cell (w1, w2) the lanes fill the two look-up tables
 // LUT_h[component][centre] = (centre - residual_h)^2 in shared memory (FillLUT,
@@ -394,7 +395,7 @@ __global__ void pq_encode_kernel(PqParams p, const float* __restrict__ desc, con
 // distance = (sequential sum over the first-half components from 0.0f) + (the same over the
 // second half) (ComputeDistance, :144-152). Top-k as in imi_scan_kernel.
 __global__ void __launch_bounds__(256)
-imipq_scan_kernel(PqParams p, const float* __restrict__ q, int64_t n_q, const int32_t* __restrict__ cells,
+imipq_scan_percell_kernel(PqParams p, const float* __restrict__ q, int64_t n_q, const int32_t* __restrict__ cells,
                   int nw, const uint2* __restrict__ cell_info, const uint4* __restrict__ lists, int k,
                   int32_t* __restrict__ out_idx, float* __restrict__ out_dist) {
   extern __shared__ float lut_s[];
@@ -455,6 +456,181 @@ imipq_scan_kernel(PqParams p, const float* __restrict__ q, int64_t n_q, const in
   }
 }
 
+// Fast path. One warp per query descriptor, persistent warps:
+//   1. the (<= 16) visited cells are split into their word halves; the DISTINCT words of each half
+//      get one look-up table (the reference caches LUTs per word the same way,
+//      …-quantization-index.h:226-262): slot numbers by __match_any_sync, tables
+//      LUT[slot][component][centre] = (centre - residual)^2 filled by all lanes together;
+//   2. the lists of the visited cells are flattened into one entry range and dealt to the lanes 64
+//      at a time (two windows, one LDG.128 per entry), distance = (sequential sum over the
+//      first-half components from 0.0f) + (same for the second half) — the reference's order;
+//   3. warp-distributed top-k as in imi_scan_kernel.
+
+__device__ __forceinline__ float PqDistance(const PqParams& p, const float* lut1, const float* lut2, uint4 en) {
+  const uint32_t cw[3] = {en.x, en.y, en.z};
+  float s1 = 0.0f, s2 = 0.0f;
+  for (int j = 0; j < p.half_ncomp; ++j) {
+    const int a1 = j, a2 = p.half_ncomp + j;
+    s1 = __fadd_rn(s1, lut1[j * p.num_centers + ((cw[a1 >> 2] >> (8 * (a1 & 3))) & 0xFFu)]);
+    s2 = __fadd_rn(s2, lut2[j * p.num_centers + ((cw[a2 >> 2] >> (8 * (a2 & 3))) & 0xFFu)]);
+  }
+  return __fadd_rn(s1, s2);
+}
+
+__device__ __forceinline__ uint64_t PqWindowKey(const PqParams& p, const uint4* __restrict__ lists,
+                                                const uint4* seg, const float* lut, int per_half, uint32_t base,
+                                                uint32_t total, uint32_t len, uint32_t excl, int lane,
+                                                uint32_t lanemask_le) {
+  const uint32_t rel = excl - base;
+  const uint32_t heads = __reduce_or_sync(kFull, (len > 0 && rel < 32u) ? (1u << rel) : 0u);
+  const uint32_t before = __popc(__ballot_sync(kFull, len > 0 && excl < base));
+  const uint32_t e = base + lane;
+  if (e >= total) return kEmptyKey;
+  const uint4 s = seg[before + __popc(heads & lanemask_le) - 1];  // {excl, start16, len, slot1 | slot2 << 8}
+  const uint4 en = __ldg(lists + s.y + (e - s.x));
+  const float* lut1 = lut + (s.w & 0xFFu) * per_half;
+  const float* lut2 = lut + (s.w >> 8) * per_half;
+  const uint32_t bits = __float_as_uint(PqDistance(p, lut1, lut2, en));
+  if (bits > kInfBits) return kEmptyKey;
+  return (static_cast<uint64_t>(bits) << 32) | en.w;
+}
+
+template <int KT>
+__global__ void __launch_bounds__(256)
+imipq_scan_kernel(PqParams p, const float* __restrict__ q, int64_t n_q, const int32_t* __restrict__ cells,
+                  int nw, const uint2* __restrict__ cell_info, const uint4* __restrict__ lists, int k,
+                  int32_t* __restrict__ out_idx, float* __restrict__ out_dist) {
+  extern __shared__ __align__(16) unsigned char pq_smem[];
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int per_half = p.half_ncomp * p.num_centers;
+  const int dim = 2 * p.sub_dim;
+  // per warp: seg[16] uint4 | slot words[32] int | query[16] float | lut[2 nw * per_half] float
+  const size_t per_warp = 16 * sizeof(uint4) + 32 * 4 + 16 * 4 + static_cast<size_t>(2 * nw) * per_half * 4;
+  unsigned char* mine = pq_smem + warp * per_warp;
+  uint4* seg = reinterpret_cast<uint4*>(mine);
+  int* slot_word = reinterpret_cast<int*>(mine + 16 * sizeof(uint4));
+  float* qs = reinterpret_cast<float*>(mine + 16 * sizeof(uint4) + 32 * 4);
+  float* lut = qs + 16;
+  const uint32_t lanemask_lt = (1u << lane) - 1u;
+  const uint32_t lanemask_le = lanemask_lt | (1u << lane);
+  const int64_t warp_stride = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+  for (int64_t qi = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 5; qi < n_q;
+       qi += warp_stride) {
+    // ---- visited cells of this query, one per lane
+    int32_t c = -1;
+    if (lane < nw) c = __ldg(cells + qi * nw + lane);
+    uint2 info = make_uint2(0u, 0u);
+    if (c >= 0) info = __ldg(cell_info + c);
+    const uint32_t len = info.y;
+    const bool used = len > 0;  // cell present in word_index_map_
+    const int w1 = used ? c / p.num_words2 : -1 - lane;
+    const int w2 = used ? c - w1 * p.num_words2 : -1 - lane;
+    // ---- one LUT slot per distinct word of each half
+    const uint32_t same1 = __match_any_sync(kFull, w1), same2 = __match_any_sync(kFull, w2);
+    const int lead1 = __ffs(same1) - 1, lead2 = __ffs(same2) - 1;
+    const uint32_t leaders1 = __ballot_sync(kFull, used && lead1 == lane);
+    const uint32_t leaders2 = __ballot_sync(kFull, used && lead2 == lane);
+    const int n1 = __popc(leaders1), n2 = __popc(leaders2);
+    const int slot1 = __popc(leaders1 & ((1u << lead1) - 1u));
+    const int slot2 = n1 + __popc(leaders2 & ((1u << lead2) - 1u));
+    __syncwarp();  // the previous query's tables / segments are no longer read
+    if (used && lead1 == lane) slot_word[slot1] = w1;
+    if (used && lead2 == lane) slot_word[slot2] = w2;
+    if (lane < dim) qs[lane] = __ldg(q + qi * dim + lane);
+    // ---- flattened entry range
+    uint32_t incl = len;
+#pragma unroll
+    for (int o = 1; o < kMaxWords; o <<= 1) {
+      const uint32_t v = __shfl_up_sync(kFull, incl, o);
+      if (lane >= o) incl += v;
+    }
+    const uint32_t total = __shfl_sync(kFull, incl, kMaxWords - 1);
+    const uint32_t excl = incl - len;
+    const uint32_t nonempty = __ballot_sync(kFull, used);
+    if (used)
+      seg[__popc(nonempty & lanemask_lt)] =
+          make_uint4(excl, info.x, len, static_cast<uint32_t>(slot1) | (static_cast<uint32_t>(slot2) << 8));
+    __syncwarp();
+    // ---- look-up tables: entry t = (slot, component, centre)
+    const int entries = (n1 + n2) * per_half;
+    if (p.vector_lut) {
+      // one scalar per component (dim_per_comp == 1), centres 16-byte aligned and a multiple of four
+      // per component: a lane fills four consecutive centres of one (slot, component) per step
+      for (int t4 = lane * 4; t4 < entries; t4 += 128) {
+        const int slot = __umulhi(static_cast<uint32_t>(t4), p.magic_per_half);
+        const int r = t4 - slot * per_half;
+        const int comp = __umulhi(static_cast<uint32_t>(r), p.magic_centers);
+        const int h = slot >= n1 ? 1 : 0;
+        const int w = slot_word[slot];
+        const float res = __fsub_rn(qs[h * p.sub_dim + comp], __ldg((h ? p.words2 : p.words1) + static_cast<size_t>(w) * p.sub_dim + comp));
+        const float4 c4 = __ldg(reinterpret_cast<const float4*>((h ? p.centers2 : p.centers1) + static_cast<size_t>(w) * per_half + r));
+        float4 o;
+        float d;
+        d = __fsub_rn(c4.x, res); o.x = __fmul_rn(d, d);
+        d = __fsub_rn(c4.y, res); o.y = __fmul_rn(d, d);
+        d = __fsub_rn(c4.z, res); o.z = __fmul_rn(d, d);
+        d = __fsub_rn(c4.w, res); o.w = __fmul_rn(d, d);
+        *reinterpret_cast<float4*>(lut + t4) = o;
+      }
+    } else {
+      for (int t = lane; t < entries; t += 32) {
+        const int slot = __umulhi(static_cast<uint32_t>(t), p.magic_per_half);
+        const int r = t - slot * per_half;
+        const int comp = __umulhi(static_cast<uint32_t>(r), p.magic_centers);
+        const int h = slot >= n1 ? 1 : 0;
+        const int w = slot_word[slot];
+        const float* word = (h ? p.words2 : p.words1) + static_cast<size_t>(w) * p.sub_dim + comp * p.dim_per_comp;
+        const float* ctr = (h ? p.centers2 : p.centers1) + (static_cast<size_t>(w) * per_half + r) * p.dim_per_comp;
+        float res[8];
+        for (int d = 0; d < p.dim_per_comp; ++d)
+          res[d] = __fsub_rn(qs[h * p.sub_dim + comp * p.dim_per_comp + d], __ldg(word + d));
+        lut[t] = SquaredDistanceRuntime(ctr, res, p.dim_per_comp);
+      }
+    }
+    __syncwarp();
+    // ---- scan
+    uint64_t held = kEmptyKey;
+    for (uint32_t base = 0; base < total; base += 64) {
+      uint64_t ka = PqWindowKey(p, lists, seg, lut, per_half, base, total, len, excl, lane, lanemask_le);
+      uint64_t kb = kEmptyKey;
+      if (base + 32 < total)
+        kb = PqWindowKey(p, lists, seg, lut, per_half, base + 32, total, len, excl, lane, lanemask_le);
+      if (base == 0) {
+        if (kb < ka) {
+          const uint64_t t = ka;
+          ka = kb;
+          kb = t;
+        }
+#pragma unroll
+        for (int r = 0; r < KT; ++r) {
+          if (r >= k) break;
+          const uint32_t a_hi = static_cast<uint32_t>(ka >> 32), a_lo = static_cast<uint32_t>(ka);
+          const uint32_t m_hi = __reduce_min_sync(kFull, a_hi);
+          const uint32_t cc = (a_hi == m_hi) ? a_lo : kNoIndex;
+          const uint32_t m_lo = __reduce_min_sync(kFull, cc);
+          if (m_lo == kNoIndex) break;
+          if (lane == r) held = (static_cast<uint64_t>(m_hi) << 32) | m_lo;
+          if (cc == m_lo) {
+            ka = kb;
+            kb = kEmptyKey;
+          }
+        }
+      } else {
+        const uint64_t kth = ShflKey(held, k - 1);
+        const uint32_t ma = __ballot_sync(kFull, ka < kth);
+        const uint32_t mb = __ballot_sync(kFull, kb < kth);
+        InsertCandidates(ma, ka, held, lane);
+        InsertCandidates(mb, kb, held, lane);
+      }
+    }
+    if (lane < k) {
+      out_idx[qi * k + lane] = static_cast<int32_t>(static_cast<uint32_t>(held));
+      out_dist[qi * k + lane] = __uint_as_float(static_cast<uint32_t>(held >> 32));
+    }
+  }
+}
+
 }  // namespace
 
 cudaError_t LaunchPqEncode(const PqParams& p, const float* desc, const int32_t* cells, int64_t n,
@@ -465,21 +641,57 @@ cudaError_t LaunchPqEncode(const PqParams& p, const float* desc, const int32_t* 
   return cudaGetLastError();
 }
 
-cudaError_t LaunchImipqScan(const PqParams& p, const float* q, int64_t n_q, const int32_t* cells, int nw,
+cudaError_t LaunchImipqScan(const PqParams& p_in, const float* q, int64_t n_q, const int32_t* cells, int nw,
                             const uint2* cell_info, const uint32_t* lists, int k, int32_t* out_idx,
                             float* out_dist, int sm_count, cudaStream_t stream) {
   if (n_q <= 0) return cudaSuccess;
   if (k > 16 || nw > kMaxWords) return cudaErrorInvalidValue;
-  const size_t smem = static_cast<size_t>(256 / 32) * 2 * p.half_ncomp * p.num_centers * sizeof(float);
+  PqParams p = p_in;
+  const int per_half = p.half_ncomp * p.num_centers;
+  p.magic_per_half = static_cast<uint32_t>((0x100000000ull + per_half - 1) / per_half);  // t / per_half, t < 2^16
+  p.magic_centers = static_cast<uint32_t>((0x100000000ull + p.num_centers - 1) / p.num_centers);
+  p.vector_lut = (p.dim_per_comp == 1 && p.num_centers % 4 == 0 &&
+                  reinterpret_cast<uintptr_t>(p.centers1) % 16 == 0 && reinterpret_cast<uintptr_t>(p.centers2) % 16 == 0)
+                     ? 1
+                     : 0;
+  int64_t blocks = (n_q * 32 + 255) / 256;
+  const uint4* lists4 = reinterpret_cast<const uint4*>(lists);
+  const size_t fast_smem = static_cast<size_t>(256 / 32) *
+                           (16 * sizeof(uint4) + 32 * 4 + 16 * 4 + static_cast<size_t>(2 * nw) * per_half * 4);
+  if (fast_smem <= 100 * 1024 && 2 * p.sub_dim <= 16) {
+    const int per_sm = fast_smem <= 56 * 1024 ? 4 : 2;
+    const int64_t cap = static_cast<int64_t>(sm_count) * per_sm;
+    if (blocks > cap) blocks = cap;
+    const unsigned g = static_cast<unsigned>(blocks);
+#define MLC_PQ_SCAN(KT)                                                                                   \
+  do {                                                                                                    \
+    cudaError_t e = cudaFuncSetAttribute(imipq_scan_kernel<KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                         static_cast<int>(fast_smem));                                    \
+    if (e != cudaSuccess) return e;                                                                       \
+    imipq_scan_kernel<KT><<<g, 256, fast_smem, stream>>>(p, q, n_q, cells, nw, cell_info, lists4, k,      \
+                                                         out_idx, out_dist);                              \
+  } while (0)
+    if (k <= 1) MLC_PQ_SCAN(1);
+    else if (k <= 2) MLC_PQ_SCAN(2);
+    else if (k <= 4) MLC_PQ_SCAN(4);
+    else if (k <= 6) MLC_PQ_SCAN(6);
+    else if (k <= 8) MLC_PQ_SCAN(8);
+    else if (k <= 10) MLC_PQ_SCAN(10);
+    else MLC_PQ_SCAN(16);
+#undef MLC_PQ_SCAN
+    CountLaunch();
+    return cudaGetLastError();
+  }
+  // large quantisers: one cell at a time with a single pair of tables
+  const size_t smem = static_cast<size_t>(256 / 32) * 2 * per_half * sizeof(float);
   if (smem > 96 * 1024) return cudaErrorInvalidValue;
-  cudaError_t e = cudaFuncSetAttribute(imipq_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  cudaError_t e = cudaFuncSetAttribute(imipq_scan_percell_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        static_cast<int>(smem));
   if (e != cudaSuccess) return e;
-  int64_t blocks = (n_q * 32 + 255) / 256;
   const int64_t cap = static_cast<int64_t>(sm_count) * 4;
   if (blocks > cap) blocks = cap;
-  imipq_scan_kernel<<<static_cast<unsigned>(blocks), 256, smem, stream>>>(
-      p, q, n_q, cells, nw, cell_info, reinterpret_cast<const uint4*>(lists), k, out_idx, out_dist);
+  imipq_scan_percell_kernel<<<static_cast<unsigned>(blocks), 256, smem, stream>>>(
+      p, q, n_q, cells, nw, cell_info, lists4, k, out_idx, out_dist);
   CountLaunch();
   return cudaGetLastError();
 }
