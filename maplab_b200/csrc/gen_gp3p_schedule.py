@@ -31,7 +31,7 @@ OUT = os.path.join(HERE, "gp3p_schedule.inc")
 (MOP_DIVSUB, MOP_DIV, MOP_NEGDIV, MOP_FACTOR_DIV, MOP_ZERO, MOP_SUBMUL, MOP_FACTOR_LOAD,
  MOP_FACTOR_INV, MOP_SCALE) = range(9)
 # three-address opcodes
-(W_DIVSUB, W_DIV, W_NEGDIV, W_ZERO, W_SUBMUL, W_SCALE, W_COPY, W_INV) = range(8)
+(W_DIVSUB, W_DIV, W_NEGDIV, W_ZERO, W_SUBMUL, W_SCALE, W_COPY, W_INV, W_NOP) = range(9)
 FACTOR_POOL = 96
 
 
@@ -207,8 +207,7 @@ def main():
                 next_slot += 1
             expiring.setdefault(last_read[v], []).append(v)
         free.extend(phys[v] for v in expiring.pop(t, []) if v not in taken_over)
-    dummy_slot = next_slot        # padding operations and dead init entries land here
-    compact_slots = next_slot + 1
+    compact_slots = next_slot
     new_waves = []
     for take in steps:
         row = []
@@ -229,13 +228,13 @@ def main():
             else:
                 row.append((o, d, rd[0], 0, 0, 0))
         row.sort(key=lambda op: (op[0], op[1]))
-        row += [(W_COPY, dummy_slot, dummy_slot, 0, 0, 0)] * (LANES - len(row))   # padding: no-ops
+        row += [(W_NOP, 0, 0, 0, 0, 0)] * (LANES - len(row))   # padding: no memory access at all
         new_waves.append(row)
     new_init = []
     for e in init:
         v = init_value[e[0]]
         dead = last_read[v] == 0
-        new_init.append([dummy_slot if dead else phys[v]] + list(e[1:]))
+        new_init.append([-1 if dead else phys[v]] + list(e[1:]))   # -1: nobody reads it, not stored
     new_action = [(-1 if sl < 0 else phys[out_value[sl]]) for sl in action]
     old_total_slots, old_init = total_slots, init
     total_slots, waves = compact_slots, new_waves
@@ -269,7 +268,8 @@ def main():
                 coef, kind, i, j = e[2 + 4 * t: 6 + 4 * t]
                 term = float(coef) * src[kind][j * 3 + i]
                 acc = term if t == 0 else acc + term
-            S[e[0]] = acc
+            if e[0] >= 0:
+                S[e[0]] = acc
         return S
 
     def run_seq(S):
@@ -300,6 +300,8 @@ def main():
         for w in waves:
             res = []
             for (o, d, a, b, c, e) in reversed(w):  # any order inside a wave; reads before writes
+                if o == W_NOP:
+                    continue
                 if o == W_DIVSUB:
                     val = S[a] / S[b] - S[c] / S[e]
                 elif o == W_DIV:
@@ -337,8 +339,8 @@ def main():
         fo.write("// mutually independent (RAW/WAR/WAW respected), results are bit-identical to the sequential program.\n")
         fo.write(f"#define GP3P_W_NUM_SLOTS {total_slots}\n#define GP3P_W_NUM_OPS {len(flat)}\n")
         fo.write(f"#define GP3P_W_NUM_WAVES {num_waves}\n#define GP3P_W_NUM_CHUNKS {chunks}\n")
-        fo.write("// op: 0 DIVSUB d=a/b-c/e, 1 DIV d=a/b, 2 NEGDIV d=-a/b, 3 ZERO, 4 SUBMUL d=c-a*b, 5 SCALE d=a*b, 6 COPY d=a, 7 INV d=1/a\n")
-        fo.write("// every step holds exactly 32 operations (padded with COPY dummy<-dummy): step s = ops [32 s, 32 s + 32)\n")
+        fo.write("// op: 0 DIVSUB d=a/b-c/e, 1 DIV d=a/b, 2 NEGDIV d=-a/b, 3 ZERO, 4 SUBMUL d=c-a*b, 5 SCALE d=a*b, 6 COPY d=a, 7 INV d=1/a, 8 NOP\n")
+        fo.write("// every step holds exactly 32 operations (padded with NOP): step s = ops [32 s, 32 s + 32); init slot -1 = dead\n")
         fo.write("static const unsigned short GP3P_W_OPS[GP3P_W_NUM_OPS][6] = {\n")
         for op in flat:
             fo.write("  {" + ",".join(str(x) for x in op) + "},\n")

@@ -94,7 +94,7 @@ __device__ void Gp3pEliminateWarp(const RansacArgs& a, const double* fvp, double
       const double term = static_cast<double>(tm[0]) * fvp[tm[1] * 9 + tm[3] * 3 + tm[2]];
       acc = (t == 0) ? term : acc + term;
     }
-    S[in[0]] = acc;
+    if (in[0] >= 0) S[in[0]] = acc;  // -1: value nobody reads
   }
   __syncwarp();
   // one step = 32 mutually independent operations (padded), one per lane; the next step's
@@ -114,11 +114,12 @@ __device__ void Gp3pEliminateWarp(const RansacArgs& a, const double* fvp, double
       case 4: val = S[c] - S[x] * S[y]; break;
       case 5: val = S[x] * S[y]; break;
       case 6: val = S[x]; break;
-      default: val = 1.0 / S[x]; break;
+      case 7: val = 1.0 / S[x]; break;
+      default: val = 0.0; break;  // 8: padding, nothing is stored
     }
     // destinations are slots that were free before this step (or the lane's own first operand,
     // updated in place), so no barrier is needed between the reads and the writes of one step
-    S[d] = val;
+    if (op != 8u) S[d] = val;
     __syncwarp();
   }
   for (int i = lane; i < 64; i += 32) {
