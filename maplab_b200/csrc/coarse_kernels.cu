@@ -76,7 +76,11 @@ kd_search_kernel(CoarseParams p, const float* __restrict__ q, int64_t n, int kk1
   const int64_t warp_end = min(n, warp_next + per_warp);
 
   const float inf = __int_as_float(0x7f800000);
-  float qv[D], off[D];
+  // query coordinates and the per-dimension offsets of the traversal are indexed by the cut
+  // dimension of the node: [dimension][thread] in shared memory (one LDS / STS instead of a select
+  // chain over registers)
+  __shared__ float qv_s[D][kThreads], off_s[D][kThreads];
+  float qv[D];
   float hv[KK];
   int32_t hx[KK];
   uint32_t st_tag[kMaxStack];
@@ -97,7 +101,8 @@ kd_search_kernel(CoarseParams p, const float* __restrict__ q, int64_t n, int kk1
 #pragma unroll
           for (int d = 0; d < D; ++d) {
             qv[d] = __ldg(src + d);
-            off[d] = 0.f;
+            qv_s[d][tid] = qv[d];
+            off_s[d][tid] = 0.f;
           }
 #pragma unroll
           for (int j = 0; j < KK; ++j) {
@@ -126,8 +131,8 @@ kd_search_kernel(CoarseParams p, const float* __restrict__ q, int64_t n, int kk1
           state = (nd.child_or_size > 0) ? kLeaf : kPop;
         } else {
           const uint32_t cd = nd.dim;
-          const float old_off = Pick<D>(off, cd);
-          const float new_off = __fsub_rn(Pick<D>(qv, cd), __uint_as_float(nd.cut_or_bucket));
+          const float old_off = off_s[cd][tid];
+          const float new_off = __fsub_rn(qv_s[cd][tid], __uint_as_float(nd.cut_or_bucket));
           // rd += -old_off * old_off + new_off * new_off   (for the far child)
           st_val[sp] = __fadd_rn(rd, __fadd_rn(__fmul_rn(-old_off, old_off), __fmul_rn(new_off, new_off)));
           st_tag[sp] = node;  // far child and offsets are re-derived from the parent when popped
@@ -189,17 +194,17 @@ kd_search_kernel(CoarseParams p, const float* __restrict__ q, int64_t n, int kk1
           --sp;
           const uint32_t tag = st_tag[sp];
           if (tag & kRestoreTag) {
-            Put<D>(off, tag & 0xFFu, st_val[sp]);  // leave the far subtree: restore the offset
+            off_s[tag & 0xFFu][tid] = st_val[sp];  // leave the far subtree: restore the offset
           } else {
             const float frd = st_val[sp];
             if ((frd <= p.max_radius2) && (__fmul_rn(frd, p.max_error2) < hv[KK - 1])) {
               const KdNodeDev nd = nodes[tag];
               const uint32_t cd = nd.dim;
-              const float new_off = __fsub_rn(Pick<D>(qv, cd), __uint_as_float(nd.cut_or_bucket));
+              const float new_off = __fsub_rn(qv_s[cd][tid], __uint_as_float(nd.cut_or_bucket));
               st_tag[sp] = kRestoreTag | cd;
-              st_val[sp] = Pick<D>(off, cd);  // old offset (the near subtree restored it)
+              st_val[sp] = off_s[cd][tid];  // old offset (the near subtree restored it)
               ++sp;
-              Put<D>(off, cd, new_off);
+              off_s[cd][tid] = new_off;
               node = (new_off > 0.f) ? tag + 1 : nd.child_or_size;  // far child
               rd = frd;
               state = kDescend;
