@@ -290,6 +290,45 @@ int mlc_query_from_knn_device(mlc_detector* d, const mlc_frame* frames, int64_t 
                               int64_t* num_vertices, mlc_match* matches, int64_t capacity,
                               int64_t* match_offsets, int64_t* num_matches, uint8_t* inlier_flags);
 
+/* Localization summary maps.
+ * File format: proto2 summary_map.proto.LocalizationSummaryMap (map-structure/localization-summary-map/
+ * proto/localization-summary-map/localization-summary-map.proto:4-14, common.proto.MatrixXf of
+ * common/maplab-common/proto/maplab-common/eigen.proto:8-12), the file "localization_summary_map"
+ * written by LocalizationSummaryMap::saveToFolder (src/localization-summary-map.cc:33-52, :121-140).
+ * The wire format is decoded here (no libprotobuf); matrices are column-major as in eigen_proto. */
+typedef struct mlc_summary_map_sizes {
+  int64_t num_landmarks;    /* G_landmark_position.cols() */
+  int64_t num_observers;    /* G_observer_position.cols() */
+  int64_t num_observations; /* observer_indices.rows() */
+  int64_t descriptor_rows;  /* projected_descriptors.rows() */
+  int64_t descriptor_cols;  /* projected_descriptors.cols() */
+} mlc_summary_map_sizes;
+/* LocalizationSummaryMap::deserialize (src/localization-summary-map.cc:53-93), host only (no device
+ * needed). Every output array may be NULL; call once with NULL arrays for the sizes. Arrays:
+ * G_landmark_position 3 x L, G_observer_position 3 x O, descriptors rows x cols (all column-major
+ * float), observer_indices / observation_to_landmark_index one uint32 per observation. */
+int mlc_summary_map_parse(const void* blob, size_t size, mlc_summary_map_sizes* sizes,
+                          float* G_landmark_position, float* G_observer_position, float* descriptors,
+                          uint32_t* observer_indices, uint32_t* observation_to_landmark_index);
+/* LocalizationSummaryMap::serialize (src/localization-summary-map.cc:33-52), host only: writes the
+ * bytes libprotobuf writes for these arrays. Returns the size needed through *out_size; fills `out`
+ * when capacity suffices (non-zero return otherwise, *out_size still set). */
+int mlc_summary_map_serialize(const mlc_summary_map_sizes* sizes, const float* G_landmark_position,
+                              const float* G_observer_position, const float* descriptors,
+                              const uint32_t* observer_indices,
+                              const uint32_t* observation_to_landmark_index, void* out,
+                              size_t capacity, size_t* out_size);
+/* LoopDetectorNode::addLocalizationSummaryMapToDatabase (LCH/src/loop-detector-node.cc:341-432):
+ * one database image per observer (timestamp 0, frame index 0, mission `mission_id` — the reference
+ * draws a random mission id per summary map; the caller hands out a dense one that no other mission
+ * uses), vertex id of observer o = first_vertex_id + o, landmark id of landmark l =
+ * first_landmark_id + l; the landmark positions (float, cast to double like
+ * LocalizationSummaryMap::getGLandmarkPosition) are written into the landmark table at those ids;
+ * ends with LoopDetector::Initialize. `sizes` may be NULL. */
+int mlc_add_summary_map(mlc_detector* d, const void* blob, size_t size, int64_t mission_id,
+                        int64_t first_vertex_id, int64_t first_landmark_id,
+                        mlc_summary_map_sizes* sizes);
+
 #ifdef __cplusplus
 }
 #endif

@@ -157,6 +157,14 @@ class LoopDetector {
     Check(mlc_set_query_priors(d_, T_G_I_3x4_rowmajor, num_vertices));
   }
   void SetLandmarkPositions(const double* xyz, int64_t n) { Check(mlc_set_landmark_positions(d_, xyz, n)); }
+  // LoopDetectorNode::addLocalizationSummaryMapToDatabase (LCH/src/loop-detector-node.cc:341-432) on
+  // the bytes of the `localization_summary_map` file; dense ids as in mlc_add_summary_map.
+  mlc_summary_map_sizes AddLocalizationSummaryMapToDatabase(const void* file_bytes, size_t size, int64_t mission_id,
+                                                            int64_t first_vertex_id, int64_t first_landmark_id) {
+    mlc_summary_map_sizes sizes{};
+    Check(mlc_add_summary_map(d_, file_bytes, size, mission_id, first_vertex_id, first_landmark_id, &sizes));
+    return sizes;
+  }
   void SaveIndex(const std::string& path) { Check(mlc_save_index(d_, path.c_str())); }
   void LoadIndex(const std::string& path) { Check(mlc_load_index(d_, path.c_str())); }
   // common::transformationRansac (geometry-inl.h:113-182); returns the number of inliers.

@@ -22,6 +22,7 @@ EXPORTS = [
     "mlc_coarse_device", "mlc_scan_device", "mlc_last_stage_ms", "mlc_set_landmark_positions", "mlc_query_batch", "mlc_query_batch_device", "mlc_query_from_knn_device",
     "mlc_score", "mlc_save_index", "mlc_load_index", "mlc_set_query_priors",
     "mlc_default_alignment_settings", "mlc_transformation_ransac",
+    "mlc_summary_map_parse", "mlc_summary_map_serialize", "mlc_add_summary_map",
 ]
 
 
@@ -63,6 +64,11 @@ class AlignmentSettings(C.Structure):
     _fields_ = [("num_iterations", C.c_int32), ("rng_mapping", C.c_int32),
                 ("max_orientation_error_rad", C.c_double), ("max_position_error_m", C.c_double),
                 ("seed", C.c_uint32), ("pad_", C.c_uint32)]
+
+
+class SummaryMapSizes(C.Structure):
+    _fields_ = [("num_landmarks", C.c_int64), ("num_observers", C.c_int64), ("num_observations", C.c_int64),
+                ("descriptor_rows", C.c_int64), ("descriptor_cols", C.c_int64)]
 
 
 class MlcError(RuntimeError):
@@ -114,6 +120,45 @@ def default_ransac_settings(**kw):
             raise AttributeError(k)
         setattr(s, k, v)
     return s
+
+
+def summary_map_parse(blob):
+    """LocalizationSummaryMap::deserialize on the serialized proto (host only, no device needed).
+    Matrices come back in Eigen's shape: G_landmark_position 3 x L, descriptors rows x cols."""
+    blob = bytes(blob)
+    sz = SummaryMapSizes()
+    null = C.c_void_p(0)
+    _check(lib().mlc_summary_map_parse(blob, C.c_size_t(len(blob)), C.byref(sz), null, null, null, null, null))
+    lm = np.zeros((sz.num_landmarks, 3), np.float32)
+    ob = np.zeros((sz.num_observers, 3), np.float32)
+    desc = np.zeros((sz.descriptor_cols, sz.descriptor_rows), np.float32)
+    oi = np.zeros(sz.num_observations, np.uint32)
+    ol = np.zeros(sz.num_observations, np.uint32)
+    _check(lib().mlc_summary_map_parse(blob, C.c_size_t(len(blob)), C.byref(sz), _ptr(lm), _ptr(ob), _ptr(desc),
+                                       _ptr(oi), _ptr(ol)))
+    return {"G_landmark_position": lm.T, "G_observer_position": ob.T, "descriptors": desc.T,
+            "observer_indices": oi, "observation_to_landmark_index": ol}
+
+
+def summary_map_serialize(G_landmark_position, G_observer_position, descriptors, observer_indices,
+                          observation_to_landmark_index):
+    """LocalizationSummaryMap::serialize: the bytes of the `localization_summary_map` file.
+    G_landmark_position 3 x L, G_observer_position 3 x O, descriptors dim x N (Eigen shapes)."""
+    lm = np.ascontiguousarray(np.asarray(G_landmark_position, np.float32).reshape(3, -1).T)
+    ob = np.ascontiguousarray(np.asarray(G_observer_position, np.float32).reshape(3, -1).T)
+    d = np.asarray(descriptors, np.float32)
+    desc = np.ascontiguousarray(d.T)
+    oi = np.ascontiguousarray(observer_indices, np.uint32)
+    ol = np.ascontiguousarray(observation_to_landmark_index, np.uint32)
+    assert len(oi) == len(ol)
+    sz = SummaryMapSizes(len(lm), len(ob), len(oi), d.shape[0], d.shape[1])
+    need = C.c_size_t(0)
+    lib().mlc_summary_map_serialize(C.byref(sz), _ptr(lm), _ptr(ob), _ptr(desc), _ptr(oi), _ptr(ol),
+                                    C.c_void_p(0), C.c_size_t(0), C.byref(need))
+    out = np.zeros(max(need.value, 1), np.uint8)
+    _check(lib().mlc_summary_map_serialize(C.byref(sz), _ptr(lm), _ptr(ob), _ptr(desc), _ptr(oi), _ptr(ol),
+                                           _ptr(out), C.c_size_t(need.value), C.byref(need)))
+    return out[:need.value].tobytes()
 
 
 def kernel_launch_count():
@@ -328,6 +373,14 @@ class Detector:
                                               C.c_void_p(dist_ptr), k, _ptr(matches), C.c_int64(cap),
                                               _ptr(offsets), C.byref(nv), C.byref(nm)))
         return matches[:nm.value], offsets[:nv.value + 1]
+
+    def add_summary_map(self, blob, mission_id, first_vertex_id, first_landmark_id):
+        """LoopDetectorNode::addLocalizationSummaryMapToDatabase on the serialized proto."""
+        blob = bytes(blob)
+        sz = SummaryMapSizes()
+        _check(lib().mlc_add_summary_map(self._h, blob, C.c_size_t(len(blob)), C.c_int64(mission_id),
+                                         C.c_int64(first_vertex_id), C.c_int64(first_landmark_id), C.byref(sz)))
+        return {k: int(getattr(sz, k)) for k, _ in SummaryMapSizes._fields_}
 
     def set_landmark_positions(self, xyz):
         xyz = np.ascontiguousarray(xyz, np.float64).reshape(-1, 3)

@@ -2,9 +2,11 @@
 #include <cstring>
 #include <new>
 #include <string>
+#include <vector>
 
 #include "../../include/maplab_lc_b200.h"
 #include "detector.h"
+#include "summary_map.h"
 
 struct mlc_detector {
   mlc::Detector impl;
@@ -253,6 +255,81 @@ int mlc_transformation_ransac(mlc_detector* d, const double* quats_xyzw, const d
                                       inlier_indices, num_inliers, &err)
              ? 0
              : Fail(err);
+}
+int mlc_summary_map_parse(const void* blob, size_t size, mlc_summary_map_sizes* sizes,
+                          float* G_landmark_position, float* G_observer_position, float* descriptors,
+                          uint32_t* observer_indices, uint32_t* observation_to_landmark_index) {
+  MLC_REQUIRE(sizes, "mlc_summary_map_parse: null sizes");
+  mlc::SummaryMap m;
+  std::string err;
+  if (!m.Parse(blob, size, &err)) return Fail(err);
+  sizes->num_landmarks = m.num_landmarks();
+  sizes->num_observers = m.num_observers();
+  sizes->num_observations = m.num_observations();
+  sizes->descriptor_rows = m.descriptor_rows;
+  sizes->descriptor_cols = m.descriptor_cols;
+  auto copy = [](auto* dst, const auto& v) {
+    if (dst && !v.empty()) std::memcpy(dst, v.data(), v.size() * sizeof(v[0]));
+  };
+  copy(G_landmark_position, m.G_landmark_position);
+  copy(G_observer_position, m.G_observer_position);
+  copy(descriptors, m.descriptors);
+  copy(observer_indices, m.observer_indices);
+  // observation_to_landmark_index is a separate repeated field: it has its own length
+  if (observation_to_landmark_index &&
+      m.observation_to_landmark_index.size() != m.observer_indices.size())
+    return Fail("summary map: observer_indices and observation_to_landmark_index differ in length");
+  copy(observation_to_landmark_index, m.observation_to_landmark_index);
+  return 0;
+}
+int mlc_summary_map_serialize(const mlc_summary_map_sizes* sizes, const float* G_landmark_position,
+                              const float* G_observer_position, const float* descriptors,
+                              const uint32_t* observer_indices,
+                              const uint32_t* observation_to_landmark_index, void* out,
+                              size_t capacity, size_t* out_size) {
+  MLC_REQUIRE(sizes && out_size, "mlc_summary_map_serialize: null argument");
+  MLC_REQUIRE(sizes->num_landmarks >= 0 && sizes->num_observers >= 0 && sizes->num_observations >= 0 &&
+                  sizes->descriptor_rows >= 0 && sizes->descriptor_cols >= 0 &&
+                  sizes->descriptor_rows <= 0xFFFFFFFFLL && sizes->descriptor_cols <= 0xFFFFFFFFLL,
+              "mlc_summary_map_serialize: bad sizes");
+  const size_t nd = static_cast<size_t>(sizes->descriptor_rows) * static_cast<size_t>(sizes->descriptor_cols);
+  MLC_REQUIRE((sizes->num_landmarks == 0 || G_landmark_position) &&
+                  (sizes->num_observers == 0 || G_observer_position) && (nd == 0 || descriptors) &&
+                  (sizes->num_observations == 0 || (observer_indices && observation_to_landmark_index)),
+              "mlc_summary_map_serialize: null array");
+  mlc::SummaryMap m;
+  m.has_uncompressed_map = true;
+  m.G_landmark_position.assign(G_landmark_position, G_landmark_position + 3 * sizes->num_landmarks);
+  m.G_observer_position.assign(G_observer_position, G_observer_position + 3 * sizes->num_observers);
+  m.descriptor_rows = static_cast<uint32_t>(sizes->descriptor_rows);
+  m.descriptor_cols = static_cast<uint32_t>(sizes->descriptor_cols);
+  m.descriptors.assign(descriptors, descriptors + nd);
+  m.observer_indices.assign(observer_indices, observer_indices + sizes->num_observations);
+  m.observation_to_landmark_index.assign(observation_to_landmark_index,
+                                         observation_to_landmark_index + sizes->num_observations);
+  std::vector<uint8_t> bytes;
+  m.Serialize(&bytes);
+  *out_size = bytes.size();
+  if (!out || capacity < bytes.size()) return Fail("mlc_summary_map_serialize: output buffer too small");
+  if (!bytes.empty()) std::memcpy(out, bytes.data(), bytes.size());
+  return 0;
+}
+int mlc_add_summary_map(mlc_detector* d, const void* blob, size_t size, int64_t mission_id,
+                        int64_t first_vertex_id, int64_t first_landmark_id,
+                        mlc_summary_map_sizes* sizes) {
+  MLC_REQUIRE(d && (blob || size == 0), "mlc_add_summary_map: null argument");
+  std::string err;
+  int64_t s4[5] = {0, 0, 0, 0, 0};
+  if (!d->impl.AddSummaryMap(blob, size, mission_id, first_vertex_id, first_landmark_id, s4, &err))
+    return Fail(err);
+  if (sizes) {
+    sizes->num_landmarks = s4[0];
+    sizes->num_observers = s4[1];
+    sizes->num_observations = s4[2];
+    sizes->descriptor_rows = s4[3];
+    sizes->descriptor_cols = s4[4];
+  }
+  return 0;
 }
 int mlc_save_index(mlc_detector* d, const char* path) {
   MLC_REQUIRE(d && path, "mlc_save_index: null argument");

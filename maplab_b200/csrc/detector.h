@@ -101,6 +101,14 @@ class Detector {
   // Landmark positions in the global frame by dense landmark id (vi_map::Landmark::get_p_G of
   // the landmark store, read by loop-closure-handler.cc:272-366); replicated on every shard.
   bool SetLandmarkPositions(const double* xyz, int64_t n, std::string* err);
+  // LoopDetectorNode::addLocalizationSummaryMapToDatabase (LCH/src/loop-detector-node.cc:341-432):
+  // one database image per observer of a serialized LocalizationSummaryMap (timestamp 0, one
+  // mission id for the whole map, frame index 0, pre-projected descriptors), then Initialize().
+  // Observer o gets vertex id first_vertex_id + o, landmark l gets id first_landmark_id + l and its
+  // position (LocalizationSummaryMap::getGLandmarkPosition: float -> double) is written into the
+  // landmark table at that id. sizes5 = {landmarks, observers, observations, descriptor rows, descriptor cols}.
+  bool AddSummaryMap(const void* blob, size_t size, int64_t mission_id, int64_t first_vertex_id,
+                     int64_t first_landmark_id, int64_t* sizes5, std::string* err);
   // Database persistence: the built index (inverted lists, cell table, metadata,
   // landmark positions) as one file, so that later runs skip projection + cell assignment + sort.
   void SetQueryPriors(const double* T_G_I, int64_t n) {

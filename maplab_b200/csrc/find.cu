@@ -3,10 +3,12 @@
 // the vertex-level second pass (:147-165).
 #include <cstdlib>
 #include <algorithm>
+#include <limits>
 #include <unordered_set>
 
 #include "covis.h"
 #include "detector.h"
+#include "summary_map.h"
 
 namespace mlc {
 
@@ -282,6 +284,54 @@ bool Detector::SetLandmarkPositions(const double* xyz, int64_t n, std::string* e
     return false;
   num_landmark_xyz_ = n;
   return Cuda(cudaStreamSynchronize(stream_), "landmark upload", err);
+}
+
+bool Detector::AddSummaryMap(const void* blob, size_t size, int64_t mission_id, int64_t first_vertex_id,
+                             int64_t first_landmark_id, int64_t* sizes5, std::string* err) {
+  std::lock_guard<std::recursive_mutex> lock(mu_);
+  SummaryMap map;
+  SummaryMapImages images;
+  if (!map.Parse(blob, size, err) || !GroupSummaryMapByObserver(map, &images, err)) return false;
+  if (map.num_observations() > 0 && static_cast<int>(map.descriptor_rows) != dim()) {
+    *err = "summary map: descriptor dimensionality differs from the vocabulary's target dimensionality";
+    return false;
+  }
+  if (first_landmark_id < 0) {
+    *err = "summary map: negative landmark id";
+    return false;
+  }
+  const int64_t observers = map.num_observers(), landmarks = map.num_landmarks();
+  // landmark table: keep what is there, unknown ids in a gap stay NaN (= "no position")
+  const int64_t old_n = num_landmark_xyz_, new_n = std::max(old_n, first_landmark_id + landmarks);
+  std::vector<double> xyz(static_cast<size_t>(new_n) * 3, std::numeric_limits<double>::quiet_NaN());
+  if (old_n > 0) {
+    if (!Cuda(cudaMemcpyAsync(xyz.data(), d_landmark_xyz_.p, sizeof(double) * 3 * old_n, cudaMemcpyDeviceToHost,
+                              stream_),
+              "D2H landmarks", err) ||
+        !Cuda(cudaStreamSynchronize(stream_), "landmark download", err))
+      return false;
+  }
+  for (int64_t i = 0; i < 3 * landmarks; ++i)
+    xyz[static_cast<size_t>(3 * first_landmark_id + i)] = static_cast<double>(map.G_landmark_position[i]);
+  std::vector<mlc_frame> frames(static_cast<size_t>(observers));
+  for (int64_t o = 0; o < observers; ++o) {
+    frames[o].timestamp_ns = 0;  // "not relevant": the map has its own mission id
+    frames[o].vertex_id = first_vertex_id + o;
+    frames[o].mission_id = mission_id;
+    frames[o].frame_index = 0;  // kFrameIndex
+    frames[o].num_descriptors = images.num_descriptors[o];
+  }
+  for (int64_t& l : images.landmark_index) l += first_landmark_id;
+  if (!InsertBatch(frames.data(), observers, images.proj.data(), images.landmark_index.data(), err)) return false;
+  if (!SetLandmarkPositions(xyz.data(), new_n, err)) return false;
+  if (sizes5) {
+    sizes5[0] = landmarks;
+    sizes5[1] = observers;
+    sizes5[2] = map.num_observations();
+    sizes5[3] = map.descriptor_rows;
+    sizes5[4] = map.descriptor_cols;
+  }
+  return EnsureIndex(err);
 }
 
 bool Detector::QueryBatch(const mlc_frame* frames, int64_t num_frames, const uint8_t* bits,

@@ -52,6 +52,11 @@ class LoopDetector:
         self._d.insert(image.timestamp_nanoseconds, image.vertex_id, image.frame_index,
                        image.mission_id, image.projected_descriptors, image.landmarks)
 
+    def AddLocalizationSummaryMapToDatabase(self, file_bytes, mission_id, first_vertex_id, first_landmark_id):
+        """LoopDetectorNode::addLocalizationSummaryMapToDatabase (LCH/src/loop-detector-node.cc:341-432)
+        on the bytes of a `localization_summary_map` file."""
+        return self._d.add_summary_map(file_bytes, mission_id, first_vertex_id, first_landmark_id)
+
     def Find(self, images, parallelize_if_possible=False):
         """images: ProjectedImage list of ONE vertex. Returns matches (capi.MATCH_DTYPE) in
         canonical order (query frame index, keypoint, db descriptor)."""

@@ -324,6 +324,20 @@ class Engine:
                                 C.c_int64(mission), self.dim, _p(proj, c_float_p), len(lm),
                                 _p(lm, c_i64_p))
 
+    def add_summary_map(self, arrays, mission_id, first_vertex_id, first_landmark_id):
+        """addLocalizationSummaryMapToDatabase on deserialized arrays (Eigen shapes: descriptors
+        dim x N, G_*_position 3 x n). Returns 0, or the number of the CHECK that would abort."""
+        d = np.asarray(arrays["descriptors"], np.float32)
+        desc = np.ascontiguousarray(d.T)
+        oi = np.ascontiguousarray(arrays["observer_indices"], np.uint32)
+        ol = np.ascontiguousarray(arrays["observation_to_landmark_index"], np.uint32)
+        u32p = C.POINTER(C.c_uint32)
+        return lib().lco_engine_add_summary_map(
+            self.h, d.shape[0], C.c_int64(np.asarray(arrays["G_observer_position"]).shape[1]),
+            C.c_int64(np.asarray(arrays["G_landmark_position"]).shape[1]), C.c_int64(len(oi)),
+            C.c_int64(d.shape[1]), _p(desc, c_float_p), _p(oi, u32p), _p(ol, u32p), C.c_int64(len(ol)),
+            C.c_int64(mission_id), C.c_int64(first_vertex_id), C.c_int64(first_landmark_id))
+
     def num_descriptors(self):
         return lib().lco_engine_num_descriptors(self.h)
 
