@@ -5,8 +5,8 @@ One step = one batch of query keyframes through the whole hot path: descriptor p
 (kernel 1) -> IMI kNN (kernels 2a/2b) -> covisibility voting/clustering (kernel 3) -> correspondence
 gather + GP3P-RANSAC verdicts (kernel 4). `value` is measured with the batch resident in HBM, `e2e`
 through the C-ABI with host buffers (H2D/D2H inside the timed region). N > 1: the inverted lists
-are sharded over the ranks (maplab_b200/sharded.py; weak scaling by default: --landmarks per GPU, the
-query batch fixed), visit lists and per-shard top-k lists are exchanged over NCCL. At N = 1 the line
+are sharded over the ranks (maplab_b200/sharded.py; weak scaling by default: --landmarks AND --queries
+are per GPU, so the map and the query batch of a step both grow with N), visit lists and per-shard top-k lists are exchanged over NCCL. At N = 1 the line
 also carries `roofline_at_shard_scale`: the same step on the per-GPU shard of the 50M-landmark /
 8-GPU configuration. One JSON line on stdout from rank 0. See DESIGN.md "Measurement".
 """
@@ -35,12 +35,13 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--landmarks", type=int, default=1_000_000, help="landmarks in the map (per GPU under weak scaling)")
-    ap.add_argument("--queries", type=int, default=1000, help="query keyframes per step")
+    ap.add_argument("--queries", type=int, default=1000, help="query keyframes per step (per GPU under weak scaling)")
     ap.add_argument("--words", type=int, default=1000)
     ap.add_argument("--cpu-queries", type=int, default=0, help="cpu_baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
-                    help="N > 1: weak = --landmarks per GPU (map grows with N), strong = --landmarks in total")
+                    help="N > 1: weak = --landmarks and --queries per GPU (map and query batch grow with N), "
+                         "strong = both in total")
     ap.add_argument("--no-scan-probe", action="store_true",
                     help="skip the extra scan-roofline measurement at the north-star shard size (N = 1 only)")
     ap.add_argument("--probe-landmarks", type=int, default=6_250_000)
@@ -240,10 +241,11 @@ def run_b200(args):
         dist.init_process_group("nccl", device_id=dev)
     hbm_peak, peak_src = peaks()
     t_setup = time.time()
-    # weak scaling: the map (hence every GPU's shard of the inverted lists) grows with the GPU count,
-    # the query batch per step stays the same
+    # weak scaling: per-GPU work is fixed — the map (hence every GPU's shard of the inverted lists) and
+    # the query batch of a step both grow with the GPU count (every rank owns --queries keyframes)
     landmarks = args.landmarks * (world if args.scaling == "weak" else 1)
-    m, blob, q = build_world(landmarks, args.queries, args.words, args.engine)
+    queries = args.queries * (world if args.scaling == "weak" else 1)
+    m, blob, q = build_world(landmarks, queries, args.words, args.engine)
     det = capi.Detector(blob, capi.default_settings(device=local, shard_rank=rank, shard_count=world,
                                                     engine=1 if args.engine == "imipq" else 0))
     frames, proj, t_build = load_database(det, m)
@@ -369,10 +371,11 @@ def run_b200(args):
         "n_gpus": world, "steps": args.steps, "warmup": W, "ms_per_step": ms_per_step,
         "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
         "dtype": "u8 x s8 -> s32 (projection), f32 (distances), f64 (RANSAC)", "data": "synthetic",
-        "config": {"workload": workload_string(landmarks, args.queries, args.words, n_db, len(frames), k),
-                   "sharding": (f"inverted lists: descriptor i on rank i % {world}; map size = "
-                                f"{args.landmarks} landmarks x {world} GPUs ({args.scaling} scaling), query "
-                                f"batch fixed") if world > 1 else "none",
+        "config": {"workload": workload_string(landmarks, queries, args.words, n_db, len(frames), k),
+                   "sharding": (f"inverted lists: descriptor i on rank i % {world}; {args.scaling} scaling: map = "
+                                f"{landmarks} landmarks, query batch = {queries} keyframes per step ("
+                                + (f"{args.landmarks} landmarks and {args.queries} query keyframes per GPU"
+                                   if args.scaling == "weak" else "totals fixed") + ")") if world > 1 else "none",
                    "l2": "256 MiB flush buffer written between timed iterations",
                    "db_build_s": round(t_build, 3),
                    "accepted_loop_closures_per_step": accepted, "matches_per_step": num_matches},
@@ -394,7 +397,7 @@ def run_b200(args):
     if world == 1:
         out["stage_ms"] = dict(zip(("project", "coarse", "scan", "vote_cluster", "ransac"),
                                    [round(float(x) / max(args.steps, 1), 4) for x in stage_acc]))
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:  # the CPU path is timed beside the N = 1 run only
         out["cpu_baseline"] = cpu_baseline(args, m, blob, q, proj, frames)
     if args.engine != "imi":
         out["config"]["engine"] = args.engine
@@ -462,7 +465,8 @@ def run_reference(args):
     from oracle import pyoracle as po
     threads = os.cpu_count() or 1
     landmarks = args.landmarks * (args.gpus if args.scaling == "weak" else 1)
-    m, blob, q = build_world(landmarks, args.queries, args.words, args.engine)
+    queries = args.queries * (args.gpus if args.scaling == "weak" else 1)
+    m, blob, q = build_world(landmarks, queries, args.words, args.engine)
     frames = frames_array(m["frames"])
     ora0 = po.Engine(blob)
     n_db = len(m["bits"])
@@ -477,7 +481,7 @@ def run_reference(args):
     [t.start() for t in ts]
     [t.join() for t in ts]
     ora = oracle_with_db(m, blob, proj, frames, args.engine)
-    nq = args.cpu_queries or min(args.queries, max(4 * threads, 32))
+    nq = args.cpu_queries or min(queries, max(4 * threads, 32))
     W = max(args.warmup, 1)
     for _ in range(W):
         cpu_query(ora, m, q, nq, threads)
@@ -489,13 +493,13 @@ def run_reference(args):
     value = nq * args.steps / t_total
     k = ora.num_neighbors()
     cb = {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
-          "sample": f"each step = first {nq} of {args.queries} query keyframes, full database, "
+          "sample": f"each step = first {nq} of {queries} query keyframes, full database, "
                     f"{threads} std::threads; oracle = CPU restatement of maplab"}
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": W, "ms_per_step": 1e3 * t_total / args.steps,
         "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32/f64 (CPU)",
-        "data": "synthetic", "config": {"workload": workload_string(landmarks, args.queries, args.words, n_db, len(frames), k),
+        "data": "synthetic", "config": {"workload": workload_string(landmarks, queries, args.words, n_db, len(frames), k),
                                         "accepted_loop_closures_in_sample": acc},
         "cpu_baseline": cb,
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
