@@ -69,7 +69,8 @@ typedef struct mlc_match {
 /* Pinhole camera of the query n-camera rig (aslam::PinholeCamera + T_B_C). */
 typedef struct mlc_camera {
   double fu, fv, cu, cv;
-  int32_t distortion; /* 0 none, 1 fisheye(FOV) */
+  int32_t distortion; /* aslam::Distortion of the camera: 0 none, 1 fisheye (FOV, dist[0] = w),
+                         2 radtan (k1, k2, p1, p2), 3 equidistant (k1..k4) */
   int32_t pad_;
   double dist[4];
   double R_B_C[9]; /* row-major */

@@ -311,8 +311,77 @@ __device__ void SolutionForEigenvalue(const Problem& pb, const double* Ms, doubl
   *score = Distance(pb, sol, fourth);
 }
 
-// PinholeCamera::backProject3 + bearing normalisation (camera-pinhole.cc:47-63,
-// distortion-fisheye.cc:119-143).
+// Forward models + Jacobians of the two iteratively inverted distortions.
+// RadTanDistortion::distortUsingExternalCoefficients (distortion-radtan.cc:14-62)
+__device__ void DistortRadTan(const double* k, double* px, double* py, double F[4]) {
+  const double x = *px, y = *py;
+  const double k1 = k[0], k2 = k[1], p1 = k[2], p2 = k[3];
+  const double mx2 = x * x, my2 = y * y, mxy = x * y, rho2 = mx2 + my2;
+  const double rad = k1 * rho2 + k2 * rho2 * rho2;
+  F[0] = 1.0 + rad + 2.0 * k1 * mx2 + 4.0 * k2 * rho2 * mx2 + 2.0 * p1 * y + 6.0 * p2 * x;
+  F[1] = 2.0 * k1 * mxy + 4.0 * k2 * rho2 * mxy + 2.0 * p1 * x + 2.0 * p2 * y;
+  F[2] = F[1];
+  F[3] = 1.0 + rad + 2.0 * k1 * my2 + 4.0 * k2 * rho2 * my2 + 2.0 * p2 * x + 6.0 * p1 * y;
+  *px = x + (x * rad + 2.0 * p1 * mxy + p2 * (rho2 + 2.0 * mx2));
+  *py = y + (y * rad + 2.0 * p2 * mxy + p1 * (rho2 + 2.0 * my2));
+}
+// EquidistantDistortion::distortUsingExternalCoefficients (distortion-equidistant.cc:14-103)
+__device__ void DistortEquidistant(const double* k, double* px, double* py, double F[4]) {
+  const double x = *px, y = *py;
+  const double k1 = k[0], k2 = k[1], k3 = k[2], k4 = k[3];
+  const double x2 = x * x, y2 = y * y, r = sqrt(x2 + y2);
+  if (r < 1e-10) {
+    F[0] = F[1] = F[2] = F[3] = 0.0;
+    return;
+  }
+  const double theta = atan(r), theta2 = theta * theta, theta4 = theta2 * theta2, theta6 = theta2 * theta4,
+               theta8 = theta4 * theta4;
+  const double poly = k1 * theta2 + k2 * theta4 + k3 * theta6 + k4 * theta8 + 1.0;
+  const double thetad = theta * (1 + k1 * theta2 + k2 * theta4 + k3 * theta6 + k4 * theta8);
+  const double theta3 = theta2 * theta, theta5 = theta4 * theta, theta7 = theta6 * theta;
+  const double s = x2 + y2, s1 = x2 + y2 + 1.0, r3 = pow(x2 + y2, 3.0 / 2.0);
+  // the reference's MATLAB-generated Jacobian, same grouping: c = x for d/du, y for d/dv
+  auto dpoly = [&](double c) {
+    return (k2 * c * theta3 / r * 4.0) / s1 + (k3 * c * theta5 / r * 6.0) / s1 + (k4 * c * theta7 / r * 8.0) / s1 +
+           (k1 * c * theta / r * 2.0) / s1;
+  };
+  F[0] = theta / r * poly + x * theta / r * dpoly(x) + (x2 * poly) / (s * s1) - x2 * theta / r3 * poly;
+  F[1] = x * theta / r * dpoly(y) + (x * y * poly) / (s * s1) - x * y * theta / r3 * poly;
+  F[2] = y * theta / r * dpoly(x) + (x * y * poly) / (s * s1) - x * y * theta / r3 * poly;
+  F[3] = theta / r * poly + y * theta / r * dpoly(y) + (y2 * poly) / (s * s1) - y2 * theta / r3 * poly;
+  const double scaling = (r > 1e-8) ? thetad / r : 1.0;
+  *px = x * scaling;
+  *py = y * scaling;
+}
+// {RadTan,Equidistant}Distortion::undistortUsingExternalCoefficients (distortion-radtan.cc:96-118,
+// distortion-equidistant.cc:144-173): Gauss-Newton on the forward model, du = (F^T F)^-1 F^T e, at most 30
+// iterations, stop once e.e <= --acv_inv_distortion_tolerance (1e-8) AFTER applying the step.
+__device__ void UndistortIterative(int model, const double* k, double* px, double* py) {
+  const double yx = *px, yy = *py;
+  if (model == 3 && yx * yx + yy * yy < 1e-6) return;  // equidistant: unchanged around the image centre
+  double bx = yx, by = yy;
+  for (int i = 0; i < 30; ++i) {
+    double tx = bx, ty = by, F[4];
+    if (model == 2) DistortRadTan(k, &tx, &ty, F);
+    else DistortEquidistant(k, &tx, &ty, F);
+    const double ex = yx - tx, ey = yy - ty;
+    // F^T F (2 x 2 coefficient-wise product), its closed-form inverse, times F^T, times e
+    const double a = F[0] * F[0] + F[2] * F[2], b = F[0] * F[1] + F[2] * F[3], c = F[1] * F[0] + F[3] * F[2],
+                 d = F[1] * F[1] + F[3] * F[3];
+    const double invdet = 1.0 / (a * d - b * c);
+    const double i00 = d * invdet, i01 = -b * invdet, i10 = -c * invdet, i11 = a * invdet;
+    const double m00 = i00 * F[0] + i01 * F[1], m01 = i00 * F[2] + i01 * F[3], m10 = i10 * F[0] + i11 * F[1],
+                 m11 = i10 * F[2] + i11 * F[3];
+    bx += m00 * ex + m01 * ey;
+    by += m10 * ex + m11 * ey;
+    if (ex * ex + ey * ey <= 1e-8) break;
+  }
+  *px = bx;
+  *py = by;
+}
+
+// PinholeCamera::backProject3 + bearing normalisation (camera-pinhole.cc:47-63; undistort of
+// distortion-fisheye.cc:119-143, distortion-radtan.cc:96-118, distortion-equidistant.cc:144-173).
 __device__ void BackProject3(const mlc_camera& c, const double* kp, double* b) {
   double x = (kp[0] - c.cu) / c.fu;
   double y = (kp[1] - c.cv) / c.fv;
@@ -327,6 +396,8 @@ __device__ void BackProject3(const mlc_camera& c, const double* kp, double* b) {
         y *= r_u;
       }
     }
+  } else if (c.distortion == 2 || c.distortion == 3) {
+    UndistortIterative(c.distortion, c.dist, &x, &y);
   }
   const double nrm = sqrt(x * x + y * y + 1.0);
   b[0] = x / nrm;

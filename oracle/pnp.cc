@@ -440,6 +440,115 @@ int RansacRng::Next() {
 }
 
 // ------------------------------ camera -------------------------------------
+namespace {
+struct Mat2 {
+  double a, b, c, d;  // [a b; c d]
+};
+inline Mat2 Mul(const Mat2& l, const Mat2& r) {  // Eigen fixed-size product: sum over k ascending
+  return Mat2{l.a * r.a + l.b * r.c, l.a * r.b + l.b * r.d, l.c * r.a + l.d * r.c, l.c * r.b + l.d * r.d};
+}
+inline Mat2 Transpose(const Mat2& m) { return Mat2{m.a, m.c, m.b, m.d}; }
+inline Mat2 Inverse(const Mat2& m) {  // Eigen compute_inverse_size2_helper: invdet = 1 / det
+  const double invdet = 1.0 / (m.a * m.d - m.b * m.c);
+  return Mat2{m.d * invdet, -m.b * invdet, -m.c * invdet, m.a * invdet};
+}
+
+// aslam_cv2/aslam_cv_cameras/src/distortion-radtan.cc:14-62
+void RadTanDistort(const double* coeffs, double* point, Mat2* jac) {
+  double& x = point[0];
+  double& y = point[1];
+  const double k1 = coeffs[0], k2 = coeffs[1], p1 = coeffs[2], p2 = coeffs[3];
+  double mx2_u = x * x;
+  double my2_u = y * y;
+  double mxy_u = x * y;
+  double rho2_u = mx2_u + my2_u;
+  double rad_dist_u = k1 * rho2_u + k2 * rho2_u * rho2_u;
+  const double duf_du = 1.0 + rad_dist_u + 2.0 * k1 * mx2_u + 4.0 * k2 * rho2_u * mx2_u + 2.0 * p1 * y + 6.0 * p2 * x;
+  const double duf_dv = 2.0 * k1 * mxy_u + 4.0 * k2 * rho2_u * mxy_u + 2.0 * p1 * x + 2.0 * p2 * y;
+  const double dvf_du = duf_dv;
+  const double dvf_dv = 1.0 + rad_dist_u + 2.0 * k1 * my2_u + 4.0 * k2 * rho2_u * my2_u + 2.0 * p2 * x + 6.0 * p1 * y;
+  *jac = Mat2{duf_du, duf_dv, dvf_du, dvf_dv};
+  x += x * rad_dist_u + 2.0 * p1 * mxy_u + p2 * (rho2_u + 2.0 * mx2_u);
+  y += y * rad_dist_u + 2.0 * p2 * mxy_u + p1 * (rho2_u + 2.0 * my2_u);
+}
+
+// aslam_cv2/aslam_cv_cameras/src/distortion-equidistant.cc:14-103
+void EquidistantDistort(const double* coeffs, double* point, Mat2* jac) {
+  double& x = point[0];
+  double& y = point[1];
+  const double k1 = coeffs[0], k2 = coeffs[1], k3 = coeffs[2], k4 = coeffs[3];
+  double x2 = x * x;
+  double y2 = y * y;
+  double r = std::sqrt(x2 + y2);
+  if (r < 1e-10) {  // keypoint remains unchanged
+    *jac = Mat2{0, 0, 0, 0};
+    return;
+  }
+  double theta = std::atan(r);
+  double theta2 = theta * theta;
+  double theta4 = theta2 * theta2;
+  double theta6 = theta2 * theta4;
+  double theta8 = theta4 * theta4;
+  double thetad = theta * (1 + k1 * theta2 + k2 * theta4 + k3 * theta6 + k4 * theta8);
+  double theta3 = theta2 * theta;
+  double theta5 = theta4 * theta;
+  double theta7 = theta6 * theta;
+  const double duf_du =
+      theta * 1.0 / r * (k1 * theta2 + k2 * theta4 + k3 * theta6 + k4 * theta8 + 1.0) +
+      x * theta * 1.0 / r *
+          ((k2 * x * theta3 * 1.0 / r * 4.0) / (x2 + y2 + 1.0) + (k3 * x * theta5 * 1.0 / r * 6.0) / (x2 + y2 + 1.0) +
+           (k4 * x * theta7 * 1.0 / r * 8.0) / (x2 + y2 + 1.0) + (k1 * x * theta * 1.0 / r * 2.0) / (x2 + y2 + 1.0)) +
+      ((x2) * (k1 * theta2 + k2 * theta4 + k3 * theta6 + k4 * theta8 + 1.0)) / ((x2 + y2) * (x2 + y2 + 1.0)) -
+      (x2)*theta * 1.0 / std::pow(x2 + y2, 3.0 / 2.0) * (k1 * theta2 + k2 * theta4 + k3 * theta6 + k4 * theta8 + 1.0);
+  const double duf_dv =
+      x * theta * 1.0 / r *
+          ((k2 * y * theta3 * 1.0 / r * 4.0) / (x2 + y2 + 1.0) + (k3 * y * theta5 * 1.0 / r * 6.0) / (x2 + y2 + 1.0) +
+           (k4 * y * theta7 * 1.0 / r * 8.0) / (x2 + y2 + 1.0) + (k1 * y * theta * 1.0 / r * 2.0) / (x2 + y2 + 1.0)) +
+      (x * y * (k1 * theta2 + k2 * theta4 + k3 * theta6 + k4 * theta8 + 1.0)) / ((x2 + y2) * (x2 + y2 + 1.0)) -
+      x * y * theta * 1.0 / std::pow(x2 + y2, 3.0 / 2.0) * (k1 * theta2 + k2 * theta4 + k3 * theta6 + k4 * theta8 + 1.0);
+  const double dvf_du =
+      y * theta * 1.0 / r *
+          ((k2 * x * theta3 * 1.0 / r * 4.0) / (x2 + y2 + 1.0) + (k3 * x * theta5 * 1.0 / r * 6.0) / (x2 + y2 + 1.0) +
+           (k4 * x * theta7 * 1.0 / r * 8.0) / (x2 + y2 + 1.0) + (k1 * x * theta * 1.0 / r * 2.0) / (x2 + y2 + 1.0)) +
+      (x * y * (k1 * theta2 + k2 * theta4 + k3 * theta6 + k4 * theta8 + 1.0)) / ((x2 + y2) * (x2 + y2 + 1.0)) -
+      x * y * theta * 1.0 / std::pow(x2 + y2, 3.0 / 2.0) * (k1 * theta2 + k2 * theta4 + k3 * theta6 + k4 * theta8 + 1.0);
+  const double dvf_dv =
+      theta * 1.0 / r * (k1 * theta2 + k2 * theta4 + k3 * theta6 + k4 * theta8 + 1.0) +
+      y * theta * 1.0 / r *
+          ((k2 * y * theta3 * 1.0 / r * 4.0) / (x2 + y2 + 1.0) + (k3 * y * theta5 * 1.0 / r * 6.0) / (x2 + y2 + 1.0) +
+           (k4 * y * theta7 * 1.0 / r * 8.0) / (x2 + y2 + 1.0) + (k1 * y * theta * 1.0 / r * 2.0) / (x2 + y2 + 1.0)) +
+      ((y2) * (k1 * theta2 + k2 * theta4 + k3 * theta6 + k4 * theta8 + 1.0)) / ((x2 + y2) * (x2 + y2 + 1.0)) -
+      (y2)*theta * 1.0 / std::pow(x2 + y2, 3.0 / 2.0) * (k1 * theta2 + k2 * theta4 + k3 * theta6 + k4 * theta8 + 1.0);
+  *jac = Mat2{duf_du, duf_dv, dvf_du, dvf_dv};
+  double scaling = (r > 1e-8) ? thetad / r : 1.0;
+  x *= scaling;
+  y *= scaling;
+}
+
+// distortion-radtan.cc:96-118 / distortion-equidistant.cc:144-173 (--acv_inv_distortion_tolerance = 1e-8,
+// aslam_cv_cameras/src/distortion.cc:8)
+void UndistortIterative(bool equidistant, const double* coeffs, double* point) {
+  const int n = 30;
+  const double y[2] = {point[0], point[1]};
+  double ybar[2] = {y[0], y[1]};
+  if (equidistant && y[0] * y[0] + y[1] * y[1] < 1e-6) return;  // special case around the image centre
+  for (int i = 0; i < n; ++i) {
+    double y_tmp[2] = {ybar[0], ybar[1]};
+    Mat2 F;
+    if (equidistant) EquidistantDistort(coeffs, y_tmp, &F);
+    else RadTanDistort(coeffs, y_tmp, &F);
+    const double e[2] = {y[0] - y_tmp[0], y[1] - y_tmp[1]};
+    const Mat2 Ft = Transpose(F);
+    const Mat2 M = Mul(Inverse(Mul(Ft, F)), Ft);  // (F^T F)^-1 F^T
+    ybar[0] += M.a * e[0] + M.b * e[1];
+    ybar[1] += M.c * e[0] + M.d * e[1];
+    if (e[0] * e[0] + e[1] * e[1] <= 1e-8) break;
+  }
+  point[0] = ybar[0];
+  point[1] = ybar[1];
+}
+}  // namespace
+
 void BackProject3(const Camera& c, const double kp_in[2], double b[3]) {
   double x = (kp_in[0] - c.cu) / c.fu;
   double y = (kp_in[1] - c.cv) / c.fv;
@@ -454,6 +563,11 @@ void BackProject3(const Camera& c, const double kp_in[2], double b[3]) {
         y *= r_u;
       }
     }
+  } else if (c.distortion == 2 || c.distortion == 3) {  // RadTanDistortion / EquidistantDistortion
+    double pt[2] = {x, y};
+    UndistortIterative(c.distortion == 3, c.dist, pt);
+    x = pt[0];
+    y = pt[1];
   }
   const double nrm = std::sqrt(x * x + y * y + 1.0);  // bearing.normalize()
   b[0] = x / nrm;
