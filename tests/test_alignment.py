@@ -109,3 +109,71 @@ def test_opengv_random_stream_matches_this_libstdcxx(tmp_path):
     for seed in (12345, 1, 987654321):
         ref = [int(x) for x in subprocess.check_output([str(exe), str(seed)]).decode().split()]
         assert po.rng_stream(seed, mapping, 256).tolist() == ref
+
+
+# ---- the reference's own tests of common::transformationRansac, restated -------------------------------
+# common/maplab-common/test/test_geometry.cc:10-106 (GeometryTransformationRansac: OnlyInliers,
+# InliersAndOutliers, OnlyOutliers). The fixture draws its samples from std::mt19937(++seed_), seed_ = 20,
+# through std::uniform_real_distribution<double> — libstdc++'s generate_canonical takes two 32-bit draws,
+# (lo + hi * 2^32) / 2^64 — reproduced here on numpy's legacy MT19937 (same init_genrand seeding).
+class _GeometryFixture:
+    def __init__(self):
+        self.seed, self.q, self.p = 20, [], []
+
+    @staticmethod
+    def _uniform(rs, a, b):
+        lo, hi = (int(x) for x in rs.randint(0, 2 ** 32, size=2, dtype=np.uint64))
+        return a + (b - a) * ((lo + hi * 2.0 ** 32) / 2.0 ** 64)
+
+    def _add(self, rs, metres, rad):
+        pos = [self._uniform(rs, -metres, metres) for _ in range(3)]
+        angle = self._uniform(rs, -rad, rad)  # AngleAxisd(angle, UnitX)
+        self.q.append([np.sin(angle / 2), 0.0, 0.0, np.cos(angle / 2)])
+        self.p.append(pos)
+
+    def add_inliers(self, n):
+        self.seed += 1
+        rs = np.random.RandomState(self.seed)
+        for _ in range(n):
+            self._add(rs, 0.01, 0.01)
+
+    def add_outlier(self):
+        self.seed += 1
+        self._add(np.random.RandomState(self.seed), 5.0, 0.5)
+
+    def arrays(self):
+        return np.array(self.q), np.array(self.p)
+
+
+def _geometry_cases():
+    a = _GeometryFixture(); a.add_inliers(20)
+    b = _GeometryFixture(); b.add_inliers(20); [b.add_outlier() for _ in range(3)]
+    c = _GeometryFixture(); [c.add_outlier() for _ in range(20)]
+    return a, b, c
+
+
+def _expect_geometry(run):
+    """run(q, p) -> (quaternion, position, inliers) with the test's settings: 40 iterations, thresholds 0.1 rad /
+    0.1 m, seed 42."""
+    only_inliers, mixed, only_outliers = _geometry_cases()
+    for fx, expected in ((only_inliers, 20), (mixed, 20)):
+        q, p, inl = run(*fx.arrays())
+        assert len(inl) == expected                                  # EXPECT_EQ(kNumInliers, num_inliers)
+        assert np.abs(p).max() < 1e-1 and _angle(q, np.array([0, 0, 0, 1.0])) < 1e-1   # NEAR identity, 1e-1
+        assert all(i < 20 for i in inl)
+    q, p, inl = run(*only_outliers.arrays())
+    assert len(inl) <= 1                                             # EXPECT_GE(1, num_inliers)
+
+
+def test_oracle_passes_the_reference_transformation_ransac_tests():
+    _expect_geometry(lambda q, p: po.transformation_ransac(q, p, 40, 0.1, 0.1, 42))
+
+
+@pytest.mark.gpu
+def test_device_passes_the_reference_transformation_ransac_tests():
+    from maplab_b200 import capi
+    from helpers import small_world
+    _, blob, _, _ = small_world()
+    det = capi.Detector(blob)
+    _expect_geometry(lambda q, p: det.transformation_ransac(q, p, num_iterations=40, seed=42,
+                                                            max_orientation_error_rad=0.1, max_position_error_m=0.1))
