@@ -42,7 +42,7 @@ __device__ __forceinline__ void Put(float (&v)[D], uint32_t d, float x) {
 // (entries [KK - kk, KK) are real, the ones before are -inf sentinels that never move), so that the
 // k-th best ("head") is always hv[KK - 1] and an insertion is one branch-free pass.
 template <int D, int KK>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 4)
 kd_search_kernel(CoarseParams p, const float* __restrict__ q, int64_t n, int kk1, int kk2,
                  int32_t* __restrict__ out_idx, float* __restrict__ out_val) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -83,8 +83,12 @@ kd_search_kernel(CoarseParams p, const float* __restrict__ q, int64_t n, int kk1
   float qv[D];
   float hv[KK];
   int32_t hx[KK];
+  // explicit stack: the newest entry (index sp - 1) lives in registers, entries 0 .. sp - 2 in local
+  // memory — a pop hands out the register copy at once and reloads the next one in the background
   uint32_t st_tag[kMaxStack];
   float st_val[kMaxStack];
+  uint32_t top_tag = 0;
+  float top_val = 0.f;
   int state = kIdle, sp = 0;
   uint32_t node = 0, pos = 0, end = 0;
   float rd = 0.f;
@@ -134,8 +138,12 @@ kd_search_kernel(CoarseParams p, const float* __restrict__ q, int64_t n, int kk1
           const float old_off = off_s[cd][tid];
           const float new_off = __fsub_rn(qv_s[cd][tid], __uint_as_float(nd.cut_or_bucket));
           // rd += -old_off * old_off + new_off * new_off   (for the far child)
-          st_val[sp] = __fadd_rn(rd, __fadd_rn(__fmul_rn(-old_off, old_off), __fmul_rn(new_off, new_off)));
-          st_tag[sp] = node;  // far child and offsets are re-derived from the parent when popped
+          if (sp > 0) {
+            st_val[sp - 1] = top_val;
+            st_tag[sp - 1] = top_tag;
+          }
+          top_val = __fadd_rn(rd, __fadd_rn(__fmul_rn(-old_off, old_off), __fmul_rn(new_off, new_off)));
+          top_tag = node;  // far child and offsets are re-derived from the parent when popped
           ++sp;
           node = (new_off > 0.f) ? nd.child_or_size : node + 1;  // near child first
         }
@@ -191,23 +199,31 @@ kd_search_kernel(CoarseParams p, const float* __restrict__ q, int64_t n, int kk1
           }
           state = kIdle;
         } else {
-          --sp;
-          const uint32_t tag = st_tag[sp];
+          const uint32_t tag = top_tag;
+          const float val = top_val;
+          bool replaced = false;
           if (tag & kRestoreTag) {
-            off_s[tag & 0xFFu][tid] = st_val[sp];  // leave the far subtree: restore the offset
+            off_s[tag & 0xFFu][tid] = val;  // leave the far subtree: restore the offset
           } else {
-            const float frd = st_val[sp];
+            const float frd = val;
             if ((frd <= p.max_radius2) && (__fmul_rn(frd, p.max_error2) < hv[KK - 1])) {
               const KdNodeDev nd = nodes[tag];
               const uint32_t cd = nd.dim;
               const float new_off = __fsub_rn(qv_s[cd][tid], __uint_as_float(nd.cut_or_bucket));
-              st_tag[sp] = kRestoreTag | cd;
-              st_val[sp] = off_s[cd][tid];  // old offset (the near subtree restored it)
-              ++sp;
+              top_tag = kRestoreTag | cd;   // the popped entry is replaced by the restore entry
+              top_val = off_s[cd][tid];     // old offset (the near subtree restored it)
+              replaced = true;
               off_s[cd][tid] = new_off;
               node = (new_off > 0.f) ? tag + 1 : nd.child_or_size;  // far child
               rd = frd;
               state = kDescend;
+            }
+          }
+          if (!replaced) {
+            --sp;
+            if (sp > 0) {
+              top_tag = st_tag[sp - 1];
+              top_val = st_val[sp - 1];
             }
           }
         }
