@@ -319,6 +319,23 @@ int mlc_summary_map_serialize(const mlc_summary_map_sizes* sizes, const float* G
                               const uint32_t* observer_indices,
                               const uint32_t* observation_to_landmark_index, void* out,
                               size_t capacity, size_t* out_size);
+/* summary_map::createLocalizationSummaryMapFromLandmarkList (map-structure/localization-summary-map/src/
+ * localization-summary-map-creation.cc:63-204) + LocalizationSummaryMap::serialize: the observations of the
+ * chosen landmarks, landmark-major (all observations of landmark 0, then of landmark 1, ...), are projected on
+ * the device (kernel 1 = descriptor_projection::ProjectDescriptor with the detector's projection matrix and
+ * target dimensionality); observers are numbered in order of first appearance of `observer_key` (any number
+ * that identifies the observing visual frame, the reference keys on vi_map::VisualFrameIdentifier) and take the
+ * G_p_I of that first observation; positions are cast to float like setGLandmarkPosition / setGObserverPosition.
+ *   G_landmark_position: 3 doubles per landmark; observations_per_landmark: one count per landmark (sum =
+ *   num_observations); bits: num_observations x bytes_per_desc; observer_key / G_observer_position
+ *   (3 doubles): per observation.
+ * Writes the serialized proto into `out` (size needed through *out_size; non-zero return and nothing
+ * written when capacity is too small — the required size depends only on the counts and ids, so a first call
+ * with out = NULL costs no device work). */
+int mlc_create_summary_map(mlc_detector* d, int64_t num_landmarks, const double* G_landmark_position,
+                           const int64_t* observations_per_landmark, int64_t num_observations,
+                           const uint8_t* bits, int bytes_per_desc, const int64_t* observer_key,
+                           const double* G_observer_position, void* out, size_t capacity, size_t* out_size);
 /* LoopDetectorNode::addLocalizationSummaryMapToDatabase (LCH/src/loop-detector-node.cc:341-432):
  * one database image per observer (timestamp 0, frame index 0, mission `mission_id` — the reference
  * draws a random mission id per summary map; the caller hands out a dense one that no other mission

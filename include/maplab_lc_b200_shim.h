@@ -165,6 +165,21 @@ class LoopDetector {
     Check(mlc_add_summary_map(d_, file_bytes, size, mission_id, first_vertex_id, first_landmark_id, &sizes));
     return sizes;
   }
+  // summary_map::createLocalizationSummaryMapFromLandmarkList + serialize: bytes of the `localization_summary_map` file.
+  std::vector<uint8_t> CreateLocalizationSummaryMap(int64_t num_landmarks, const double* G_landmark_position,
+                                                    const int64_t* observations_per_landmark, int64_t num_observations,
+                                                    const uint8_t* descriptors, int bytes_per_descriptor,
+                                                    const int64_t* observer_key, const double* G_observer_position) {
+    size_t need = 0;
+    mlc_create_summary_map(d_, num_landmarks, G_landmark_position, observations_per_landmark, num_observations,
+                           descriptors, bytes_per_descriptor, observer_key, G_observer_position, nullptr, 0, &need);
+    if (need == 0) Check(1);
+    std::vector<uint8_t> bytes(need);
+    Check(mlc_create_summary_map(d_, num_landmarks, G_landmark_position, observations_per_landmark, num_observations,
+                                 descriptors, bytes_per_descriptor, observer_key, G_observer_position, bytes.data(),
+                                 bytes.size(), &need));
+    return bytes;
+  }
   void SaveIndex(const std::string& path) { Check(mlc_save_index(d_, path.c_str())); }
   void LoadIndex(const std::string& path) { Check(mlc_load_index(d_, path.c_str())); }
   // common::transformationRansac (geometry-inl.h:113-182); returns the number of inliers.

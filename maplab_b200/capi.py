@@ -22,7 +22,7 @@ EXPORTS = [
     "mlc_coarse_device", "mlc_scan_device", "mlc_last_stage_ms", "mlc_set_landmark_positions", "mlc_query_batch", "mlc_query_batch_device", "mlc_query_from_knn_device",
     "mlc_score", "mlc_save_index", "mlc_load_index", "mlc_set_query_priors",
     "mlc_default_alignment_settings", "mlc_transformation_ransac",
-    "mlc_summary_map_parse", "mlc_summary_map_serialize", "mlc_add_summary_map",
+    "mlc_summary_map_parse", "mlc_summary_map_serialize", "mlc_add_summary_map", "mlc_create_summary_map",
 ]
 
 
@@ -373,6 +373,27 @@ class Detector:
                                               C.c_void_p(dist_ptr), k, _ptr(matches), C.c_int64(cap),
                                               _ptr(offsets), C.byref(nv), C.byref(nm)))
         return matches[:nm.value], offsets[:nv.value + 1]
+
+    def create_summary_map(self, G_landmark_position, observations_per_landmark, bits, observer_key,
+                           G_observer_position):
+        """createLocalizationSummaryMapFromLandmarkList + serialize: the `localization_summary_map` file
+        bytes for landmark-major observations (G_landmark_position [L][3], bits [N][bytes],
+        observer_key [N], G_observer_position [N][3])."""
+        lm = np.ascontiguousarray(G_landmark_position, np.float64).reshape(-1, 3)
+        cnt = np.ascontiguousarray(observations_per_landmark, np.int64)
+        bits = np.ascontiguousarray(bits, np.uint8)
+        key = np.ascontiguousarray(observer_key, np.int64)
+        pos = np.ascontiguousarray(G_observer_position, np.float64).reshape(-1, 3)
+        assert len(cnt) == len(lm) and len(key) == len(bits) == len(pos)
+        need = C.c_size_t(0)
+        args = (self._h, C.c_int64(len(lm)), _ptr(lm), _ptr(cnt), C.c_int64(len(bits)), _ptr(bits),
+                C.c_int(bits.shape[1] if bits.ndim == 2 else 0), _ptr(key), _ptr(pos))
+        lib().mlc_create_summary_map(*args, C.c_void_p(0), C.c_size_t(0), C.byref(need))
+        if need.value == 0:
+            raise MlcError(lib().mlc_last_error().decode())
+        out = np.zeros(need.value, np.uint8)
+        _check(lib().mlc_create_summary_map(*args, _ptr(out), C.c_size_t(need.value), C.byref(need)))
+        return out.tobytes()
 
     def add_summary_map(self, blob, mission_id, first_vertex_id, first_landmark_id):
         """LoopDetectorNode::addLocalizationSummaryMapToDatabase on the serialized proto."""

@@ -2,6 +2,7 @@
 #include <cstring>
 #include <new>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "../../include/maplab_lc_b200.h"
@@ -312,6 +313,55 @@ int mlc_summary_map_serialize(const mlc_summary_map_sizes* sizes, const float* G
   *out_size = bytes.size();
   if (!out || capacity < bytes.size()) return Fail("mlc_summary_map_serialize: output buffer too small");
   if (!bytes.empty()) std::memcpy(out, bytes.data(), bytes.size());
+  return 0;
+}
+int mlc_create_summary_map(mlc_detector* d, int64_t num_landmarks, const double* G_landmark_position,
+                           const int64_t* observations_per_landmark, int64_t num_observations,
+                           const uint8_t* bits, int bytes_per_desc, const int64_t* observer_key,
+                           const double* G_observer_position, void* out, size_t capacity, size_t* out_size) {
+  MLC_REQUIRE(d && out_size && num_landmarks > 0 && G_landmark_position && observations_per_landmark,
+              "mlc_create_summary_map: null argument or no landmarks (CHECK(!landmark_ids.empty()))");
+  MLC_REQUIRE(num_observations > 0 && num_observations <= 0x7FFFFFFFLL && bits && observer_key && G_observer_position,
+              "mlc_create_summary_map: no landmark observations for summary map");
+  mlc::SummaryMap m;
+  m.has_uncompressed_map = true;
+  m.G_landmark_position.resize(static_cast<size_t>(num_landmarks) * 3);
+  for (size_t i = 0; i < m.G_landmark_position.size(); ++i)
+    m.G_landmark_position[i] = static_cast<float>(G_landmark_position[i]);
+  // observation -> landmark index: landmark-major runs
+  m.observation_to_landmark_index.reserve(static_cast<size_t>(num_observations));
+  for (int64_t l = 0; l < num_landmarks; ++l) {
+    MLC_REQUIRE(observations_per_landmark[l] >= 0, "mlc_create_summary_map: negative observation count");
+    MLC_REQUIRE(static_cast<int64_t>(m.observation_to_landmark_index.size()) + observations_per_landmark[l] <=
+                    num_observations,
+                "mlc_create_summary_map: observation counts exceed num_observations");
+    m.observation_to_landmark_index.insert(m.observation_to_landmark_index.end(),
+                                           static_cast<size_t>(observations_per_landmark[l]), static_cast<uint32_t>(l));
+  }
+  MLC_REQUIRE(static_cast<int64_t>(m.observation_to_landmark_index.size()) == num_observations,
+              "mlc_create_summary_map: observation counts do not add up to num_observations");
+  // observers in order of first appearance (frame_id_to_index of the reference)
+  std::unordered_map<int64_t, uint32_t> observer_of_key;
+  m.observer_indices.resize(static_cast<size_t>(num_observations));
+  for (int64_t i = 0; i < num_observations; ++i) {
+    auto it = observer_of_key.find(observer_key[i]);
+    if (it == observer_of_key.end()) {
+      it = observer_of_key.emplace(observer_key[i], static_cast<uint32_t>(observer_of_key.size())).first;
+      for (int c = 0; c < 3; ++c) m.G_observer_position.push_back(static_cast<float>(G_observer_position[3 * i + c]));
+    }
+    m.observer_indices[i] = it->second;
+  }
+  m.descriptor_rows = static_cast<uint32_t>(mlc_target_dim(d));
+  m.descriptor_cols = static_cast<uint32_t>(num_observations);
+  *out_size = m.SerializedSize();
+  if (!out || capacity < *out_size) return Fail("mlc_create_summary_map: output buffer too small");
+  m.descriptors.resize(static_cast<size_t>(num_observations) * m.descriptor_rows);
+  std::string err;
+  if (!d->impl.Project(bits, bytes_per_desc, num_observations, m.descriptors.data(), &err)) return Fail(err);
+  std::vector<uint8_t> bytes;
+  m.Serialize(&bytes);
+  if (bytes.size() != *out_size) return Fail("mlc_create_summary_map: internal size mismatch");
+  std::memcpy(out, bytes.data(), bytes.size());
   return 0;
 }
 int mlc_add_summary_map(mlc_detector* d, const void* blob, size_t size, int64_t mission_id,

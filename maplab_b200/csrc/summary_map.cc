@@ -245,6 +245,14 @@ bool SummaryMap::Parse(const void* blob, size_t size, std::string* err) {
   return true;
 }
 
+size_t SummaryMap::SerializedSize() const {
+  const size_t matrix_size = 1 + VarintSize(descriptor_rows) + 1 + VarintSize(descriptor_cols) +
+                             5 * (static_cast<size_t>(descriptor_rows) * descriptor_cols);
+  const size_t sub_size = 1 + VarintSize(matrix_size) + matrix_size + 5 * G_observer_position.size() +
+                          U32sSize(observer_indices) + U32sSize(observation_to_landmark_index);
+  return 5 * G_landmark_position.size() + 1 + VarintSize(sub_size) + sub_size;
+}
+
 void SummaryMap::Serialize(std::vector<uint8_t>* out) const {
   out->clear();
   PutFloats(1, G_landmark_position, out);

@@ -37,6 +37,7 @@ struct SummaryMap {
   // scalars unpacked (no [packed=true] in the .proto), optional rows / cols always set by
   // eigen_proto::serialize (eigen-proto-inl.h:99-111).
   void Serialize(std::vector<uint8_t>* out) const;
+  size_t SerializedSize() const;  // without building the bytes (descriptor VALUES do not change the size)
 };
 
 // addLocalizationSummaryMapToDatabase's regrouping (loop-detector-node.cc:368-424): observation i

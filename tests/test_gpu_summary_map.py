@@ -137,3 +137,27 @@ def test_summary_map_rejections():
         det.add_summary_map(b"\x0a\x05abc", 1, 0, 0)
     assert det.add_summary_map(smp.encode(**good), 1, 0, 0)["num_observers"] == 2
     assert det.num_entries() == 2 and det.num_descriptors() == 3
+
+
+def test_create_summary_map_equals_reference_construction():
+    # createLocalizationSummaryMapFromLandmarkList: observations landmark-major, projected on the device,
+    # observers numbered by first appearance, positions cast to float; the file bytes must be what
+    # libprotobuf writes for the arrays of the numpy restatement (summary_map_of)
+    m, blob, _, _ = small_world()
+    det = capi.Detector(blob, capi.default_settings())
+    proj = det.project(m["bits"])
+    arrays, order = summary_map_of(m, proj)
+    kf_of_desc = np.repeat(np.arange(len(m["frames"]["num_descriptors"])), m["frames"]["num_descriptors"])
+    counts = np.bincount(m["landmarks"], minlength=len(m["landmark_xyz"]))
+    file_bytes = det.create_summary_map(m["landmark_xyz"], counts, m["bits"][order], 1000 + 7 * kf_of_desc[order],
+                                        m["kf_pos"][kf_of_desc[order]])
+    assert file_bytes == smp.encode(**arrays)
+    got = capi.summary_map_parse(file_bytes)
+    assert np.array_equal(got["descriptors"], proj[order].T)
+    # and it feeds the database like any other summary map
+    det2 = capi.Detector(blob, capi.default_settings())
+    sizes = det2.add_summary_map(file_bytes, 5, 0, 0)
+    assert sizes["num_observations"] == len(order) and det2.num_descriptors() == len(order)
+    with pytest.raises(capi.MlcError, match="do not add up"):
+        det.create_summary_map(m["landmark_xyz"], counts[::-1] * 0 + 1, m["bits"][order], kf_of_desc[order],
+                               m["kf_pos"][kf_of_desc[order]])
