@@ -443,7 +443,7 @@ def cpu_baseline(args, m, blob, q, proj, frames):
     t0 = time.time()
     ora = oracle_with_db(m, blob, proj, frames, args.engine)
     t_build = time.time() - t0
-    nq = args.cpu_queries or min(args.queries, max(8 * threads, 64))
+    nq = args.cpu_queries or min(args.queries, 1000)  # the whole step at the default size: ~15 s of CPU work
     dt, r = cpu_query(ora, m, q, nq, threads)
     st = r["stage_seconds"]
     return {"value": nq / dt, "unit": UNIT, "cores": threads, "kind": "port",
@@ -481,7 +481,7 @@ def run_reference(args):
     [t.start() for t in ts]
     [t.join() for t in ts]
     ora = oracle_with_db(m, blob, proj, frames, args.engine)
-    nq = args.cpu_queries or min(queries, max(4 * threads, 32))
+    nq = args.cpu_queries or min(queries, 512)  # bounded sample per step: the run stays within a minute
     W = max(args.warmup, 1)
     for _ in range(W):
         cpu_query(ora, m, q, nq, threads)
