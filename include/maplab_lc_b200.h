@@ -294,9 +294,11 @@ int mlc_query_from_knn_device(mlc_detector* d, const mlc_frame* frames, int64_t 
 /* Localization summary maps.
  * File format: proto2 summary_map.proto.LocalizationSummaryMap (map-structure/localization-summary-map/
  * proto/localization-summary-map/localization-summary-map.proto:4-14, common.proto.MatrixXf of
- * common/maplab-common/proto/maplab-common/eigen.proto:8-12), the file "localization_summary_map"
- * written by LocalizationSummaryMap::saveToFolder (src/localization-summary-map.cc:33-52, :121-140).
- * The wire format is decoded here (no libprotobuf); matrices are column-major as in eigen_proto. */
+ * common/maplab-common/proto/maplab-common/eigen.proto:8-12), the message inside the file
+ * "localization_summary_map" written by LocalizationSummaryMap::saveToFolder (src/localization-summary-map.cc:33-52,
+ * :121-140). `blob` is the serialized message: with --proto_use_compression (the default) the file on disk is that
+ * message as a gzip stream (maplab-common/src/proto-serialization-helper.cc:63-76, :120-131), to be inflated by the
+ * caller. The wire format is decoded here (no libprotobuf); matrices are column-major as in eigen_proto. */
 typedef struct mlc_summary_map_sizes {
   int64_t num_landmarks;    /* G_landmark_position.cols() */
   int64_t num_observers;    /* G_observer_position.cols() */

@@ -107,12 +107,17 @@ def descriptors_of(frame):
     return np.frombuffer(blob, np.uint8, rows * cols, 24).reshape(cols, rows)
 
 
-def _read(path, cls):
+def read_proto_bytes(path):
+    """The serialized message of a file written by common::proto_serialization_helper::serializeProtoToFile
+    (maplab-common/src/proto-serialization-helper.cc:104-140): a gzip stream with --proto_use_compression (default),
+    the plain message otherwise."""
     raw = open(path, "rb").read()
-    if raw[:2] == b"\x1f\x8b":  # the map files are gzip streams
-        raw = gzip.decompress(raw)
+    return gzip.decompress(raw) if raw[:2] == b"\x1f\x8b" else raw
+
+
+def _read(path, cls):
     msg = cls()
-    msg.ParseFromString(raw)
+    msg.ParseFromString(read_proto_bytes(path))
     return msg
 
 

@@ -122,3 +122,17 @@ def test_malformed_inputs_are_rejected():
             capi.summary_map_parse(bad)
     with pytest.raises(capi.MlcError, match="Unsupported"):
         capi.summary_map_parse(b"")
+
+
+def test_file_as_written_with_proto_use_compression(tmp_path):
+    # serializeProtoToFile wraps the message into a GzipOutputStream by default: inflate, then parse
+    import gzip
+    from maplab_b200 import vi_map_io
+    m = random_map(11)
+    path = tmp_path / "localization_summary_map"
+    path.write_bytes(gzip.compress(smp.encode(**m)))
+    assert same(capi.summary_map_parse(vi_map_io.read_proto_bytes(str(path))), m)
+    path.write_bytes(smp.encode(**m))  # --proto_use_compression=false
+    assert same(capi.summary_map_parse(vi_map_io.read_proto_bytes(str(path))), m)
+    with pytest.raises(capi.MlcError):
+        capi.summary_map_parse(gzip.compress(smp.encode(**m)))  # the gzip stream itself is not a message
