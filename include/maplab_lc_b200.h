@@ -349,6 +349,37 @@ int mlc_add_summary_map(mlc_detector* d, const void* blob, size_t size, int64_t 
                         int64_t first_vertex_id, int64_t first_landmark_id,
                         mlc_summary_map_sizes* sizes);
 
+/* Saved vi_maps: one `vertices<N>` file = the message vi_map.proto.VIMap with its
+ * vertex_ids / vertices (map-structure/vi-map/proto/vi-map/vi_map.proto:27-43, :82-100, :161-176;
+ * aslam-serialization/visual-frame.proto:5-26), written by vi_map::serialization::serializeVertices
+ * (vi-map/src/vi-map-serialization.cc:27-43). `proto` is the serialized message — the file on disk is a gzip stream
+ * of it (proto-serialization-helper.cc:120-131), inflate it first. Host only; what the loop-closure path consumes
+ * (LoopDetectorNode::addVertexToDatabase / queryVertexInDatabase, LCH/src/loop-detector-node.cc:273-339, :668-766). */
+typedef struct mlc_vi_map_counts {
+  int64_t num_vertices, num_frames, num_keypoints, num_landmarks;
+  int32_t descriptor_bytes; /* 48 BRISK, 64 FREAK; 0 without keypoints */
+  int32_t pad_;
+} mlc_vi_map_counts;
+typedef struct mlc_vi_map_arrays { /* caller-allocated from mlc_vi_map_counts; any pointer may be NULL */
+  uint64_t* vertex_id;             /* 2 words per vertex (aslam::HashId) */
+  uint64_t* mission_id;            /* 2 per vertex */
+  double* T_M_I;                   /* 7 per vertex: quaternion x y z w, position (eigen-proto-inl.h:165-177) */
+  int32_t* vertex_num_frames;      /* per vertex */
+  int32_t* vertex_num_landmarks;   /* per vertex: size of its landmark store */
+  int64_t* frame_timestamp_ns;     /* per visual frame, vertex-major */
+  int32_t* frame_num_keypoints;
+  uint8_t* frame_is_valid;
+  double* keypoint_measurement;    /* 2 per keypoint, frame-major */
+  uint8_t* keypoint_descriptor;    /* descriptor_bytes per keypoint */
+  uint64_t* keypoint_landmark_id;  /* 2 per keypoint; (0, 0) = no landmark */
+  uint64_t* landmark_id;           /* 2 per stored landmark, vertex-major */
+  double* landmark_p_B;            /* 3 per landmark: position in the storing vertex' frame */
+  int32_t* landmark_quality;       /* vi_map::Landmark::Quality: 0 unknown, 1 bad, 2 good */
+} mlc_vi_map_arrays;
+int mlc_vi_map_count(const void* proto, size_t size, mlc_vi_map_counts* counts);
+/* `counts` must be what mlc_vi_map_count returned for the same bytes (checked). */
+int mlc_vi_map_read(const void* proto, size_t size, const mlc_vi_map_counts* counts, const mlc_vi_map_arrays* out);
+
 #ifdef __cplusplus
 }
 #endif

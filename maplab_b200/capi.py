@@ -23,6 +23,7 @@ EXPORTS = [
     "mlc_score", "mlc_save_index", "mlc_load_index", "mlc_set_query_priors",
     "mlc_default_alignment_settings", "mlc_transformation_ransac",
     "mlc_summary_map_parse", "mlc_summary_map_serialize", "mlc_add_summary_map", "mlc_create_summary_map",
+    "mlc_vi_map_count", "mlc_vi_map_read",
 ]
 
 
@@ -69,6 +70,18 @@ class AlignmentSettings(C.Structure):
 class SummaryMapSizes(C.Structure):
     _fields_ = [("num_landmarks", C.c_int64), ("num_observers", C.c_int64), ("num_observations", C.c_int64),
                 ("descriptor_rows", C.c_int64), ("descriptor_cols", C.c_int64)]
+
+
+class ViMapCounts(C.Structure):
+    _fields_ = [("num_vertices", C.c_int64), ("num_frames", C.c_int64), ("num_keypoints", C.c_int64),
+                ("num_landmarks", C.c_int64), ("descriptor_bytes", C.c_int32), ("pad_", C.c_int32)]
+
+
+class ViMapArrays(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in (
+        "vertex_id", "mission_id", "T_M_I", "vertex_num_frames", "vertex_num_landmarks", "frame_timestamp_ns",
+        "frame_num_keypoints", "frame_is_valid", "keypoint_measurement", "keypoint_descriptor",
+        "keypoint_landmark_id", "landmark_id", "landmark_p_B", "landmark_quality")]
 
 
 class MlcError(RuntimeError):
@@ -159,6 +172,25 @@ def summary_map_serialize(G_landmark_position, G_observer_position, descriptors,
     _check(lib().mlc_summary_map_serialize(C.byref(sz), _ptr(lm), _ptr(ob), _ptr(desc), _ptr(oi), _ptr(ol),
                                            _ptr(out), C.c_size_t(need.value), C.byref(need)))
     return out[:need.value].tobytes()
+
+
+def vi_map_read_vertices(proto_bytes):
+    """One `vertices<N>` message of a saved vi_map (already inflated, vi_map_io.read_proto_bytes) -> dict of
+    arrays (mlc_vi_map_arrays). Host only."""
+    blob = bytes(proto_bytes)
+    c = ViMapCounts()
+    _check(lib().mlc_vi_map_count(blob, C.c_size_t(len(blob)), C.byref(c)))
+    V, F, K, L, B = c.num_vertices, c.num_frames, c.num_keypoints, c.num_landmarks, c.descriptor_bytes
+    out = dict(vertex_id=np.zeros((V, 2), np.uint64), mission_id=np.zeros((V, 2), np.uint64),
+               T_M_I=np.zeros((V, 7), np.float64), vertex_num_frames=np.zeros(V, np.int32),
+               vertex_num_landmarks=np.zeros(V, np.int32), frame_timestamp_ns=np.zeros(F, np.int64),
+               frame_num_keypoints=np.zeros(F, np.int32), frame_is_valid=np.zeros(F, np.uint8),
+               keypoint_measurement=np.zeros((K, 2), np.float64), keypoint_descriptor=np.zeros((K, B), np.uint8),
+               keypoint_landmark_id=np.zeros((K, 2), np.uint64), landmark_id=np.zeros((L, 2), np.uint64),
+               landmark_p_B=np.zeros((L, 3), np.float64), landmark_quality=np.zeros(L, np.int32))
+    arrays = ViMapArrays(**{k: (v.ctypes.data if v.size else None) for k, v in out.items()})
+    _check(lib().mlc_vi_map_read(blob, C.c_size_t(len(blob)), C.byref(c), C.byref(arrays)))
+    return out
 
 
 def kernel_launch_count():

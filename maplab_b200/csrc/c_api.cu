@@ -8,6 +8,7 @@
 #include "../../include/maplab_lc_b200.h"
 #include "detector.h"
 #include "summary_map.h"
+#include "vi_map_reader.h"
 
 struct mlc_detector {
   mlc::Detector impl;
@@ -379,6 +380,51 @@ int mlc_add_summary_map(mlc_detector* d, const void* blob, size_t size, int64_t 
     sizes->descriptor_rows = s4[3];
     sizes->descriptor_cols = s4[4];
   }
+  return 0;
+}
+namespace {
+void Counts(const mlc::ViMapVertices& m, mlc_vi_map_counts* c) {
+  c->num_vertices = m.num_vertices();
+  c->num_frames = m.num_frames();
+  c->num_keypoints = m.num_keypoints();
+  c->num_landmarks = m.num_landmarks();
+  c->descriptor_bytes = m.descriptor_bytes;
+  c->pad_ = 0;
+}
+}  // namespace
+int mlc_vi_map_count(const void* proto, size_t size, mlc_vi_map_counts* counts) {
+  MLC_REQUIRE(counts, "mlc_vi_map_count: null counts");
+  mlc::ViMapVertices m;
+  std::string err;
+  if (!m.Parse(proto, size, &err)) return Fail(err);
+  Counts(m, counts);
+  return 0;
+}
+int mlc_vi_map_read(const void* proto, size_t size, const mlc_vi_map_counts* counts, const mlc_vi_map_arrays* out) {
+  MLC_REQUIRE(counts && out, "mlc_vi_map_read: null argument");
+  mlc::ViMapVertices m;
+  std::string err;
+  if (!m.Parse(proto, size, &err)) return Fail(err);
+  mlc_vi_map_counts now;
+  Counts(m, &now);
+  if (std::memcmp(&now, counts, sizeof(now)) != 0) return Fail("mlc_vi_map_read: counts do not belong to these bytes");
+  auto copy = [](auto* dst, const auto& v) {
+    if (dst && !v.empty()) std::memcpy(dst, v.data(), v.size() * sizeof(v[0]));
+  };
+  copy(out->vertex_id, m.vertex_id);
+  copy(out->mission_id, m.mission_id);
+  copy(out->T_M_I, m.T_M_I);
+  copy(out->vertex_num_frames, m.vertex_num_frames);
+  copy(out->vertex_num_landmarks, m.vertex_num_landmarks);
+  copy(out->frame_timestamp_ns, m.frame_timestamp_ns);
+  copy(out->frame_num_keypoints, m.frame_num_keypoints);
+  copy(out->frame_is_valid, m.frame_is_valid);
+  copy(out->keypoint_measurement, m.keypoint_measurement);
+  copy(out->keypoint_descriptor, m.keypoint_descriptor);
+  copy(out->keypoint_landmark_id, m.keypoint_landmark_id);
+  copy(out->landmark_id, m.landmark_id);
+  copy(out->landmark_p_B, m.landmark_p_B);
+  copy(out->landmark_quality, m.landmark_quality);
   return 0;
 }
 int mlc_save_index(mlc_detector* d, const char* path) {

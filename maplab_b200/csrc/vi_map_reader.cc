@@ -1,0 +1,244 @@
+// See vi_map_reader.h.
+#include "vi_map_reader.h"
+
+#include <cstring>
+
+#include "proto_wire.h"
+
+namespace mlc {
+namespace {
+using namespace wire;
+
+// aslam.proto.Id -> two 64-bit words (missing words read as 0 = the invalid id)
+bool ParseId(Reader r, uint64_t out[2]) {
+  std::vector<uint64_t> words;
+  uint32_t field;
+  int wt;
+  while (r.p != r.end) {
+    if (!Key(&r, &field, &wt)) return false;
+    bool handled = false;
+    if (field == 1 && !RepeatedU64(&r, wt, &words, &handled)) return false;
+    if (!handled && !r.Skip(field, wt)) return false;
+  }
+  out[0] = words.size() > 0 ? words[0] : 0;
+  out[1] = words.size() > 1 ? words[1] : 0;
+  return words.size() <= 2;
+}
+
+bool ParseFrame(Reader r, ViMapVertices* m, std::string* err) {
+  std::vector<double> measurements;
+  std::vector<uint64_t> landmark_ids;
+  const uint8_t* desc = nullptr;
+  size_t desc_size = 0;
+  int64_t timestamp = 0;
+  uint8_t is_valid = 0;
+  uint32_t field;
+  int wt;
+  while (r.p != r.end) {
+    if (!Key(&r, &field, &wt)) return false;
+    bool handled = false;
+    uint64_t v;
+    Reader sub;
+    if (field == 2 && wt == 0) {
+      if (!r.Varint(&v)) return false;
+      timestamp = static_cast<int64_t>(v);
+      handled = true;
+    } else if (field == 3) {
+      if (!RepeatedDouble(&r, wt, &measurements, &handled)) return false;
+    } else if (field == 5 && wt == 2) {
+      if (!r.Sub(&sub)) return false;
+      desc = sub.p;  // optional bytes: the last occurrence wins
+      desc_size = static_cast<size_t>(sub.end - sub.p);
+      handled = true;
+    } else if (field == 7 && wt == 2) {
+      uint64_t id[2];
+      if (!r.Sub(&sub) || !ParseId(sub, id)) return false;
+      landmark_ids.push_back(id[0]);
+      landmark_ids.push_back(id[1]);
+      handled = true;
+    } else if (field == 9 && wt == 0) {
+      if (!r.Varint(&v)) return false;
+      is_valid = v != 0;
+      handled = true;
+    }
+    if (!handled && !r.Skip(field, wt)) return false;
+  }
+  if (measurements.size() % 2 != 0) {
+    *err = "vi_map: odd number of keypoint measurement coordinates";
+    return false;
+  }
+  const size_t n = measurements.size() / 2;
+  if (landmark_ids.size() != 2 * n) {
+    *err = "vi_map: keypoints and observed landmark ids differ in number";
+    return false;
+  }
+  if (n > 0 || desc_size > 0) {
+    // aslam's descriptor matrix: 24-byte header with int32 rows at byte 8 and int32 cols at byte 12, then the
+    // column-major uchar data (one descriptor per column)
+    int32_t rows = 0, cols = 0;
+    if (desc_size >= 24) {
+      std::memcpy(&rows, desc + 8, 4);
+      std::memcpy(&cols, desc + 12, 4);
+    }
+    if (desc_size < 24 || rows <= 0 || cols < 0 || static_cast<size_t>(rows) * cols + 24 != desc_size ||
+        static_cast<size_t>(cols) != n) {
+      *err = "vi_map: descriptor matrix does not match the keypoints";
+      return false;
+    }
+    if (m->descriptor_bytes == 0) m->descriptor_bytes = rows;
+    if (m->descriptor_bytes != rows) {
+      *err = "vi_map: descriptors of different sizes in one file";
+      return false;
+    }
+    m->keypoint_descriptor.insert(m->keypoint_descriptor.end(), desc + 24, desc + desc_size);
+  }
+  m->keypoint_measurement.insert(m->keypoint_measurement.end(), measurements.begin(), measurements.end());
+  m->keypoint_landmark_id.insert(m->keypoint_landmark_id.end(), landmark_ids.begin(), landmark_ids.end());
+  m->frame_timestamp_ns.push_back(timestamp);
+  m->frame_num_keypoints.push_back(static_cast<int32_t>(n));
+  m->frame_is_valid.push_back(is_valid);
+  return true;
+}
+
+bool ParseNFrame(Reader r, ViMapVertices* m, int32_t* num_frames, std::string* err) {
+  uint32_t field;
+  int wt;
+  while (r.p != r.end) {
+    if (!Key(&r, &field, &wt)) return false;
+    if (field == 2 && wt == 2) {
+      Reader sub;
+      if (!r.Sub(&sub) || !ParseFrame(sub, m, err)) return false;
+      ++*num_frames;
+    } else if (!r.Skip(field, wt)) {
+      return false;
+    }
+  }
+  return true;
+}
+
+bool ParseLandmark(Reader r, ViMapVertices* m, std::string* err) {
+  uint64_t id[2] = {0, 0};
+  std::vector<double> position;
+  int32_t quality = 0;  // [default = kUnknown]
+  uint32_t field;
+  int wt;
+  while (r.p != r.end) {
+    if (!Key(&r, &field, &wt)) return false;
+    bool handled = false;
+    Reader sub;
+    uint64_t v;
+    if (field == 1 && wt == 2) {
+      if (!r.Sub(&sub) || !ParseId(sub, id)) return false;
+      handled = true;
+    } else if (field == 2) {
+      if (!RepeatedDouble(&r, wt, &position, &handled)) return false;
+    } else if (field == 7 && wt == 0) {
+      if (!r.Varint(&v)) return false;
+      quality = static_cast<int32_t>(v);
+      handled = true;
+    }
+    if (!handled && !r.Skip(field, wt)) return false;
+  }
+  if (position.size() != 3) {
+    *err = "vi_map: landmark position is not 3-dimensional";
+    return false;
+  }
+  m->landmark_id.push_back(id[0]);
+  m->landmark_id.push_back(id[1]);
+  m->landmark_p_B.insert(m->landmark_p_B.end(), position.begin(), position.end());
+  m->landmark_quality.push_back(quality);
+  return true;
+}
+
+bool ParseLandmarkStore(Reader r, ViMapVertices* m, int32_t* num_landmarks, std::string* err) {
+  uint32_t field;
+  int wt;
+  while (r.p != r.end) {
+    if (!Key(&r, &field, &wt)) return false;
+    if (field == 1 && wt == 2) {
+      Reader sub;
+      if (!r.Sub(&sub) || !ParseLandmark(sub, m, err)) return false;
+      ++*num_landmarks;
+    } else if (!r.Skip(field, wt)) {
+      return false;
+    }
+  }
+  return true;
+}
+
+bool ParseVertex(Reader r, ViMapVertices* m, std::string* err) {
+  std::vector<double> T_M_I;
+  uint64_t mission[2] = {0, 0};
+  int32_t num_frames = 0, num_landmarks = 0;
+  uint32_t field;
+  int wt;
+  while (r.p != r.end) {
+    if (!Key(&r, &field, &wt)) return false;
+    bool handled = false;
+    Reader sub;
+    if (field == 3) {
+      if (!RepeatedDouble(&r, wt, &T_M_I, &handled)) return false;
+    } else if (field == 7 && wt == 2) {
+      if (!r.Sub(&sub) || !ParseNFrame(sub, m, &num_frames, err)) return false;
+      handled = true;
+    } else if (field == 8 && wt == 2) {
+      if (!r.Sub(&sub) || !ParseLandmarkStore(sub, m, &num_landmarks, err)) return false;
+      handled = true;
+    } else if (field == 14 && wt == 2) {
+      if (!r.Sub(&sub) || !ParseId(sub, mission)) return false;
+      handled = true;
+    }
+    if (!handled && !r.Skip(field, wt)) return false;
+  }
+  if (T_M_I.size() != 7) {
+    *err = "vi_map: T_M_I is not a 7-vector (quaternion + position)";
+    return false;
+  }
+  m->T_M_I.insert(m->T_M_I.end(), T_M_I.begin(), T_M_I.end());
+  m->mission_id.push_back(mission[0]);
+  m->mission_id.push_back(mission[1]);
+  m->vertex_num_frames.push_back(num_frames);
+  m->vertex_num_landmarks.push_back(num_landmarks);
+  return true;
+}
+
+}  // namespace
+
+bool ViMapVertices::Parse(const void* proto, size_t size, std::string* err) {
+  *this = ViMapVertices();
+  if (size > 0 && !proto) {
+    *err = "vi_map: null buffer";
+    return false;
+  }
+  err->clear();
+  Reader r{static_cast<const uint8_t*>(proto), static_cast<const uint8_t*>(proto) + size};
+  uint32_t field;
+  int wt;
+  bool ok = true;
+  while (ok && r.p != r.end) {
+    ok = Key(&r, &field, &wt);
+    if (!ok) break;
+    Reader sub;
+    if (field == 1 && wt == 2) {
+      uint64_t id[2];
+      ok = r.Sub(&sub) && ParseId(sub, id);
+      vertex_id.push_back(id[0]);
+      vertex_id.push_back(id[1]);
+    } else if (field == 2 && wt == 2) {
+      ok = r.Sub(&sub) && ParseVertex(sub, this, err);
+    } else {
+      ok = r.Skip(field, wt);
+    }
+  }
+  if (!ok) {
+    if (err->empty()) *err = "vi_map: malformed protobuf wire data (is the file still gzip-compressed?)";
+    return false;
+  }
+  if (vertex_id.size() != 2 * static_cast<size_t>(num_vertices())) {
+    *err = "vi_map: vertex_ids and vertices differ in number (CHECK_EQ of deserializeVertices)";
+    return false;
+  }
+  return true;
+}
+
+}  // namespace mlc

@@ -15,6 +15,7 @@ the shipped projection / quantizer files can feed the B200 detector without the 
                                 (T_G_M * T_M_I(storing vertex) * p_B, vi_map::VIMap::getLandmark_G_p), vertex poses and
                                 the cameras (mlc_camera fields) of the n-camera rig.
 Host-side plumbing only; nothing here touches the device."""
+import functools
 import glob
 import gzip
 import os
@@ -31,6 +32,7 @@ def load_projection_matrix(path):
     return np.frombuffer(raw, np.float32, rows * cols, 8).reshape(cols, rows).T.copy()
 
 
+@functools.lru_cache(maxsize=1)
 def _vi_map_class():
     """The fields of the three .proto files that the loop-closure inputs need (others are skipped as unknown)."""
     from google.protobuf import descriptor_pb2, descriptor_pool, message_factory

@@ -65,3 +65,106 @@ def test_projection_matrix_reader_rejects_garbage(tmp_path):
         vi_map_io.load_projection_matrix(str(p))
     p.write_bytes(np.array([2, 3], np.int32).tobytes() + np.arange(6, dtype=np.float32).tobytes())
     assert vi_map_io.load_projection_matrix(str(p)).tolist() == [[0, 2, 4], [1, 3, 5]]
+
+
+# ---- the library's own reader of the vertices files (mlc_vi_map_count / mlc_vi_map_read, C++, no libprotobuf)
+# against the protobuf runtime
+def _compare_with_runtime(proto_bytes):
+    from maplab_b200 import capi
+    got = capi.vi_map_read_vertices(proto_bytes)
+    msg = vi_map_io._vi_map_class()()
+    msg.ParseFromString(proto_bytes)
+    V = len(msg.vertices)
+    assert got["vertex_id"].tolist() == [list(i.uint) for i in msg.vertex_ids]
+    assert got["mission_id"].tolist() == [list(v.mission_id.uint) for v in msg.vertices]
+    assert np.array_equal(got["T_M_I"], np.array([list(v.T_M_I) for v in msg.vertices]).reshape(V, 7))
+    frames = [f for v in msg.vertices for f in v.n_visual_frame.frames]
+    assert got["vertex_num_frames"].tolist() == [len(v.n_visual_frame.frames) for v in msg.vertices]
+    assert got["frame_timestamp_ns"].tolist() == [f.timestamp for f in frames]
+    assert got["frame_is_valid"].tolist() == [int(f.is_valid) for f in frames]
+    assert got["frame_num_keypoints"].tolist() == [len(f.keypoint_measurements) // 2 for f in frames]
+    kp = np.concatenate([np.zeros((0, 2))] + [np.array(f.keypoint_measurements).reshape(-1, 2) for f in frames])
+    assert np.array_equal(got["keypoint_measurement"], kp)
+    desc = [vi_map_io.descriptors_of(f) for f in frames]
+    width = got["keypoint_descriptor"].shape[1]
+    assert np.array_equal(got["keypoint_descriptor"],
+                          np.concatenate([np.zeros((0, width), np.uint8)] + [d for d in desc if d.size]))
+    ids = [list(l.uint) + [0] * (2 - len(l.uint)) for f in frames for l in f.landmark_ids]
+    assert got["keypoint_landmark_id"].tolist() == ids
+    lms = [l for v in msg.vertices for l in v.landmark_store.landmarks]
+    assert got["vertex_num_landmarks"].tolist() == [len(v.landmark_store.landmarks) for v in msg.vertices]
+    assert got["landmark_id"].tolist() == [list(l.id.uint) for l in lms]
+    assert np.array_equal(got["landmark_p_B"], np.array([list(l.position) for l in lms]).reshape(len(lms), 3))
+    assert got["landmark_quality"].tolist() == [l.quality for l in lms]
+    return got
+
+
+def _toy_map(rng, vertices=3, frames=2, bytes_per_desc=48):
+    import struct
+    msg = vi_map_io._vi_map_class()()
+    for v in range(vertices):
+        msg.vertex_ids.add().uint.extend([int(rng.integers(1, 2 ** 63)), 2 ** 64 - 1 - v])
+        vert = msg.vertices.add()
+        vert.T_M_I.extend(rng.normal(size=7).tolist())
+        vert.mission_id.uint.extend([7, 9])
+        for f in range(frames):
+            fr = vert.n_visual_frame.frames.add()
+            n = int(rng.integers(0, 6)) if (v, f) != (0, 0) else 4
+            fr.timestamp = 1_600_000_000_000_000_000 + 1000 * v + f
+            fr.is_valid = bool((v + f) % 2)
+            fr.keypoint_measurements.extend(rng.uniform(0, 700, 2 * n).tolist())
+            data = rng.integers(0, 256, (n, bytes_per_desc), dtype=np.uint8)
+            fr.keypoint_descriptors = struct.pack("<qiiii", 1, bytes_per_desc, n, 0, 1) + data.tobytes()
+            for i in range(n):
+                lid = fr.landmark_ids.add()
+                if i % 3:
+                    lid.uint.extend([int(rng.integers(1, 2 ** 62)), int(rng.integers(1, 2 ** 62))])
+                else:
+                    lid.uint.extend([0, 0])  # invalid id
+        for _ in range(int(rng.integers(0, 4))):
+            lm = vert.landmark_store.landmarks.add()
+            lm.id.uint.extend([int(rng.integers(1, 2 ** 62)), 5])
+            lm.position.extend(rng.normal(size=3).tolist())
+            lm.quality = int(rng.integers(0, 3))
+    return msg
+
+
+def test_cxx_reader_equals_protobuf_runtime_on_constructed_maps():
+    rng = np.random.default_rng(0)
+    for bytes_per_desc in (48, 64):
+        got = _compare_with_runtime(_toy_map(rng, bytes_per_desc=bytes_per_desc).SerializeToString())
+        assert got["keypoint_descriptor"].shape[1] == bytes_per_desc
+    _compare_with_runtime(b"")  # an empty message is an empty map
+
+
+def test_cxx_reader_rejections():
+    import gzip
+    from maplab_b200 import capi
+    rng = np.random.default_rng(1)
+    msg = _toy_map(rng)
+    good = msg.SerializeToString()
+    with pytest.raises(capi.MlcError, match="gzip"):
+        capi.vi_map_read_vertices(gzip.compress(good))
+    with pytest.raises(capi.MlcError):
+        capi.vi_map_read_vertices(good[:len(good) // 2])
+    broken = vi_map_io._vi_map_class()()
+    broken.CopyFrom(msg)
+    broken.vertices[0].n_visual_frame.frames[0].landmark_ids.add().uint.extend([1, 2])
+    with pytest.raises(capi.MlcError, match="differ in number"):
+        capi.vi_map_read_vertices(broken.SerializeToString())
+    broken.CopyFrom(msg)
+    del broken.vertex_ids[-1]
+    with pytest.raises(capi.MlcError, match="vertex_ids and vertices"):
+        capi.vi_map_read_vertices(broken.SerializeToString())
+    broken.CopyFrom(msg)
+    broken.vertices[0].n_visual_frame.frames[0].keypoint_descriptors = b"\\x00" * 30
+    with pytest.raises(capi.MlcError, match="descriptor matrix"):
+        capi.vi_map_read_vertices(broken.SerializeToString())
+
+
+@needs_reference
+def test_cxx_reader_equals_protobuf_runtime_on_the_reference_map():
+    for name in ("vertices0", "vertices2"):
+        got = _compare_with_runtime(vi_map_io.read_proto_bytes(os.path.join(MAP, name)))
+        assert got["keypoint_descriptor"].shape[1] == 48 and (got["landmark_quality"] == 2).all()
+        assert (got["vertex_num_frames"] == 5).all()
