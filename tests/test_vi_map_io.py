@@ -168,3 +168,34 @@ def test_cxx_reader_equals_protobuf_runtime_on_the_reference_map():
         got = _compare_with_runtime(vi_map_io.read_proto_bytes(os.path.join(MAP, name)))
         assert got["keypoint_descriptor"].shape[1] == 48 and (got["landmark_quality"] == 2).all()
         assert (got["vertex_num_frames"] == 5).all()
+
+
+@needs_reference
+def test_oracle_relocalises_every_query_vertex_with_the_full_rig():
+    # map folder -> vi_map_io -> oracle, all five cameras (the committed fixture keeps two): even vertices are the
+    # database mission, odd vertices the query mission; every query vertex is relocalised within 6 cm of the pose
+    # the bundle-adjusted reference map stores for it (median ~1.3 cm)
+    from maplab_b200 import capi
+    from oracle import pyoracle as po
+    blob = open(os.path.join(GOLDEN, "brisk_quantizer_top10.dat"), "rb").read()
+    vm = vi_map_io.load_vi_map(MAP)
+    x = vi_map_io.loop_closure_inputs(vm)
+    fr = x["frames"]
+    off = np.concatenate([[0], np.cumsum(fr[:, 3])])
+    is_db = fr[:, 1] % 2 == 0
+    ora = po.Engine(blob, po.default_settings())
+    proj = ora.project(x["bits"])
+    for i in np.nonzero(is_db)[0]:
+        s, e = off[i], off[i + 1]
+        ora.insert(int(fr[i, 0]), int(fr[i, 1]), int(fr[i, 2]), 0, proj[s:e], x["landmarks"][s:e])
+    cams = [po.make_camera(c["fu"], c["fv"], c["cu"], c["cv"], c["R_B_C"], c["t_B_C"], c["distortion"], c["dist"])
+            for c in vi_map_io.cameras_of(vm["sensors"])]
+    q = fr[~is_db]
+    rows = np.concatenate([np.arange(off[i], off[i + 1]) for i in np.nonzero(~is_db)[0]])
+    frames = capi.make_frames(q[:, 0], q[:, 1], np.ones(len(q), np.int64), q[:, 2], q[:, 3])
+    exp = po.query_batch(ora, frames, x["bits"][rows], x["keypoints"][rows], x["landmark_xyz"], cams, num_threads=4)
+    acc = exp["accepted"].astype(bool)
+    assert len(acc) == 63 and acc.all()
+    err = np.linalg.norm(exp["T"][:, :, 3] - x["T_G_I"][q[::5, 1]][:, :, 3], axis=1)
+    assert np.median(err) < 0.02 and err.max() < 0.08
+    assert exp["num_inliers"].min() >= 20
