@@ -42,7 +42,9 @@ struct Reader {
     return true;
   }
   // Unknown field (or a known one with an unexpected wire type): skipped like libprotobuf does.
-  bool Skip(uint32_t field, int wire) {
+  // Groups nest; libprotobuf refuses more than 100 levels, so does this (a crafted file must not be able to
+  // overflow the stack).
+  bool Skip(uint32_t field, int wire, int depth = 0) {
     uint64_t v;
     uint32_t w;
     Reader sub;
@@ -54,6 +56,7 @@ struct Reader {
         return true;
       case 2: return Sub(&sub);
       case 3:  // group: skip until the matching end-group key
+        if (depth >= 100) return false;
         while (true) {
           uint64_t key;
           if (!Varint(&key)) return false;
@@ -61,7 +64,7 @@ struct Reader {
           const uint32_t kf = static_cast<uint32_t>(key >> 3);
           if (kf == 0) return false;
           if (kw == 4) return kf == field;
-          if (!Skip(kf, kw)) return false;
+          if (!Skip(kf, kw, depth + 1)) return false;
         }
       case 5: return Fixed32(&w);
       default: return false;  // 4 (stray end-group), 6, 7

@@ -122,6 +122,16 @@ def test_malformed_inputs_are_rejected():
             capi.summary_map_parse(bad)
     with pytest.raises(capi.MlcError, match="Unsupported"):
         capi.summary_map_parse(b"")
+    # a megabyte of nested start-group keys must be refused (libprotobuf's recursion limit is 100), not recursed into
+    deep = bytes([(6 << 3) | 3]) * (1 << 20)
+    with pytest.raises(capi.MlcError, match="malformed"):
+        capi.summary_map_parse(deep)
+    from maplab_b200 import capi as _c
+    with pytest.raises(_c.MlcError):
+        _c.vi_map_read_vertices(deep)
+    nested_ok = bytes([(6 << 3) | 3]) * 50 + bytes([(6 << 3) | 4]) * 50  # 50 levels: skipped as an unknown field
+    with pytest.raises(capi.MlcError, match="Unsupported"):
+        capi.summary_map_parse(nested_ok)
 
 
 def test_file_as_written_with_proto_use_compression(tmp_path):
