@@ -254,6 +254,17 @@ int mlc_transformation_ransac(mlc_detector* d, const double* quats_xyzw, const d
                               const mlc_alignment_settings* settings, double* out_quat_xyzw, double* out_position,
                               int32_t* inlier_indices, int32_t* num_inliers);
 
+/* Tail of LoopDetectorNode::detectLoopClosuresMissionToDatabase after transformationRansac
+ * (LCH/src/loop-detector-node.cc:936-955), host only:
+ * mlc_alignment_enough_inliers: num_inliers >= max(--anchor_transform_min_inlier_count,
+ *   int(num_samples * --anchor_transform_min_inlier_ratio)) -> 1, else 0;
+ * mlc_alignment_yaw_only: "the datasets should be gravity-aligned so only yaw-axis rotation is necessary":
+ *   RotationMatrixToRollPitchYaw (maplab-common/geometry-inl.h:41-61), roll = pitch = 0,
+ *   RollPitchYawToRotationMatrix (:64-84), back to a quaternion as Eigen converts a matrix (x, y, z, w). */
+int mlc_alignment_enough_inliers(int32_t num_inliers, int64_t num_samples, int32_t min_inlier_count,
+                                 double min_inlier_ratio);
+int mlc_alignment_yaw_only(const double quat_xyzw[4], double out_quat_xyzw[4]);
+
 /* Database persistence (no reference counterpart: maplab rebuilds the loop-closure database for
  * every `lc` / `aam` / `relax` invocation and per mission, LCH/src/loop-detector-node.cc:273-339,
  * vi-map-merger.cc:71-78). mlc_save_index writes the built index — keyframe headers, projected

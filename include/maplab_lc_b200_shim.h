@@ -194,6 +194,15 @@ class LoopDetector {
     return num;
   }
 
+  // Tail of detectLoopClosuresMissionToDatabase (loop-detector-node.cc:936-955): inlier gate, yaw-only projection.
+  static bool EnoughAlignmentInliers(int num_inliers, int64_t num_samples, int min_inlier_count = 10,
+                                     double min_inlier_ratio = 0.2) {
+    return mlc_alignment_enough_inliers(num_inliers, num_samples, min_inlier_count, min_inlier_ratio) != 0;
+  }
+  static void YawOnly(const double quat_xyzw[4], double out_quat_xyzw[4]) {
+    Check(mlc_alignment_yaw_only(quat_xyzw, out_quat_xyzw));
+  }
+
   // loop_closure::IndexInterface::GetNNearestNeighborsForFeatures (index-interface.h:27-35).
   void GetNNearestNeighborsForFeatures(const float* query_features, int64_t n, int num_neighbors,
                                        int32_t* indices, float* distances) const {

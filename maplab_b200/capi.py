@@ -23,7 +23,7 @@ EXPORTS = [
     "mlc_score", "mlc_save_index", "mlc_load_index", "mlc_set_query_priors",
     "mlc_default_alignment_settings", "mlc_transformation_ransac",
     "mlc_summary_map_parse", "mlc_summary_map_serialize", "mlc_add_summary_map", "mlc_create_summary_map",
-    "mlc_vi_map_count", "mlc_vi_map_read",
+    "mlc_vi_map_count", "mlc_vi_map_read", "mlc_alignment_enough_inliers", "mlc_alignment_yaw_only",
 ]
 
 
@@ -191,6 +191,19 @@ def vi_map_read_vertices(proto_bytes):
     arrays = ViMapArrays(**{k: (v.ctypes.data if v.size else None) for k, v in out.items()})
     _check(lib().mlc_vi_map_read(blob, C.c_size_t(len(blob)), C.byref(c), C.byref(arrays)))
     return out
+
+
+def alignment_yaw_only(quat_xyzw):
+    """Yaw-only projection of the mission alignment (loop-detector-node.cc:944-955), host only."""
+    q = np.ascontiguousarray(quat_xyzw, np.float64).reshape(4)
+    out = np.zeros(4, np.float64)
+    _check(lib().mlc_alignment_yaw_only(q.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p)))
+    return out
+
+
+def alignment_enough_inliers(num_inliers, num_samples, min_inlier_count=10, min_inlier_ratio=0.2):
+    return bool(lib().mlc_alignment_enough_inliers(C.c_int32(num_inliers), C.c_int64(num_samples),
+                                                   C.c_int32(min_inlier_count), C.c_double(min_inlier_ratio)))
 
 
 def kernel_launch_count():

@@ -1,4 +1,5 @@
 // extern "C" surface of libmaplab_lc_b200.so (include/maplab_lc_b200.h).
+#include <cmath>
 #include <cstring>
 #include <new>
 #include <string>
@@ -425,6 +426,38 @@ int mlc_vi_map_read(const void* proto, size_t size, const mlc_vi_map_counts* cou
   copy(out->landmark_id, m.landmark_id);
   copy(out->landmark_p_B, m.landmark_p_B);
   copy(out->landmark_quality, m.landmark_quality);
+  return 0;
+}
+int mlc_alignment_enough_inliers(int32_t num_inliers, int64_t num_samples, int32_t min_inlier_count,
+                                 double min_inlier_ratio) {
+  const int by_ratio = static_cast<int>(static_cast<double>(num_samples) * min_inlier_ratio);
+  const int threshold = min_inlier_count > by_ratio ? min_inlier_count : by_ratio;
+  return num_inliers >= threshold ? 1 : 0;
+}
+int mlc_alignment_yaw_only(const double quat_xyzw[4], double out_quat_xyzw[4]) {
+  MLC_REQUIRE(quat_xyzw && out_quat_xyzw, "mlc_alignment_yaw_only: null argument");
+  // first column of Eigen's Quaternion::toRotationMatrix
+  const double x = quat_xyzw[0], y = quat_xyzw[1], z = quat_xyzw[2], w = quat_xyzw[3];
+  const double ty = 2.0 * y, tz = 2.0 * z;
+  const double twy = ty * w, twz = tz * w, txy = ty * x, txz = tz * x, tyy = ty * y, tzz = tz * z;
+  const double r00 = 1.0 - (tyy + tzz), r10 = txy + twz, r20 = txz - twy;
+  const double pitch = std::atan2(-r20, std::sqrt(r00 * r00 + r10 * r10));
+  const double cp = std::cos(pitch);
+  const double yaw = std::fabs(cp) > 1.0e-12 ? std::atan2(r10 / cp, r00 / cp) : 0.0;
+  // Rz(yaw) * Ry(0) * Rx(0) = [c -s 0; s c 0; 0 0 1], then Eigen's matrix -> quaternion branches
+  const double c = std::cos(yaw), sn = std::sin(yaw);
+  const double trace = c + c + 1.0;
+  out_quat_xyzw[0] = 0.0;
+  out_quat_xyzw[1] = 0.0;
+  if (trace > 0.0) {
+    const double t = std::sqrt(trace + 1.0);
+    out_quat_xyzw[3] = 0.5 * t;
+    out_quat_xyzw[2] = (sn - (-sn)) * (0.5 / t);
+  } else {  // R22 = 1 is the largest diagonal entry
+    const double t = std::sqrt(1.0 - c - c + 1.0);
+    out_quat_xyzw[2] = 0.5 * t;
+    out_quat_xyzw[3] = (sn - (-sn)) * (0.5 / t);
+  }
   return 0;
 }
 int mlc_save_index(mlc_detector* d, const char* path) {

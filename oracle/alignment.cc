@@ -163,10 +163,24 @@ void YawOnly(const double q[4], double out[4]) {
   }
   (void)R01;
   (void)R11;
+  // Eigen::Quaterniond(RollPitchYawToRotationMatrix(0, 0, yaw)) — Eigen's matrix -> quaternion conversion
+  // (Eigen/src/Geometry/Quaternion.h, quaternionbase_assign_impl<Other, 3, 3>): w >= 0 while the trace is
+  // positive, otherwise the largest diagonal entry (R22 = 1 here) becomes the positive component.
+  const double c = std::cos(yaw), s = std::sin(yaw);
+  double t = c + c + 1.0;
   out[0] = 0.0;
   out[1] = 0.0;
-  out[2] = std::sin(0.5 * yaw);
-  out[3] = std::cos(0.5 * yaw);
+  if (t > 0.0) {
+    t = std::sqrt(t + 1.0);
+    out[3] = 0.5 * t;
+    t = 0.5 / t;
+    out[2] = (s + s) * t;
+  } else {
+    t = std::sqrt(1.0 - c - c + 1.0);
+    out[2] = 0.5 * t;
+    t = 0.5 / t;
+    out[3] = (s + s) * t;
+  }
 }
 
 }  // namespace lc_oracle

@@ -177,3 +177,41 @@ def test_device_passes_the_reference_transformation_ransac_tests():
     det = capi.Detector(blob)
     _expect_geometry(lambda q, p: det.transformation_ransac(q, p, num_iterations=40, seed=42,
                                                             max_orientation_error_rad=0.1, max_position_error_m=0.1))
+
+
+# ---- tail of detectLoopClosuresMissionToDatabase: inlier gate + yaw-only projection (host code of the library)
+def _rpy_matrix(roll, pitch, yaw):
+    cx, sx, cy, sy, cz, sz = np.cos(roll), np.sin(roll), np.cos(pitch), np.sin(pitch), np.cos(yaw), np.sin(yaw)
+    Rx = np.array([[1, 0, 0], [0, cx, -sx], [0, sx, cx]])
+    Ry = np.array([[cy, 0, sy], [0, 1, 0], [-sy, 0, cy]])
+    Rz = np.array([[cz, -sz, 0], [sz, cz, 0], [0, 0, 1]])
+    return Rz @ Ry @ Rx  # RollPitchYawToRotationMatrix (geometry-inl.h:64-84)
+
+
+def _quat_of(R):
+    w = np.sqrt(max(1e-300, 1 + np.trace(R))) / 2
+    if w > 1e-3:
+        return np.array([R[2, 1] - R[1, 2], R[0, 2] - R[2, 0], R[1, 0] - R[0, 1], 4 * w * w]) / (4 * w)
+    z = np.sqrt(max(0.0, 1 - R[0, 0] - R[1, 1] + R[2, 2])) / 2
+    return np.array([(R[0, 2] + R[2, 0]) / (4 * z), (R[1, 2] + R[2, 1]) / (4 * z), z, (R[1, 0] - R[0, 1]) / (4 * z)])
+
+
+def test_yaw_only_projection_and_inlier_gate():
+    from maplab_b200 import capi
+    rng = np.random.default_rng(0)
+    yaws = np.concatenate([rng.uniform(-np.pi, np.pi, 200), [0.0, 2.2, -2.2, 3.1, -3.1, 2 * np.pi / 3 + 1e-9]])
+    for yaw in yaws:
+        roll, pitch = rng.uniform(-0.2, 0.2, 2)
+        q = _quat_of(_rpy_matrix(roll, pitch, yaw))
+        got, exp = capi.alignment_yaw_only(q), po.yaw_only(q)
+        assert np.abs(got - exp).max() <= 1e-15                      # library == oracle (independent restatements)
+        assert got[0] == 0 and got[1] == 0 and abs(np.linalg.norm(got) - 1) < 1e-12
+        # the yaw of the input survives: R = Rz(yaw)
+        assert abs((1 - 2 * got[2] ** 2) - np.cos(yaw)) < 1e-9 and abs(2 * got[2] * got[3] - np.sin(yaw)) < 1e-9
+        # Eigen's matrix -> quaternion sign: w >= 0 while 1 + 2 cos(yaw) > 0, else z > 0
+        assert (got[3] >= 0) if 1 + 2 * np.cos(yaw) > 0 else (got[2] > 0)
+        assert np.array_equal(capi.alignment_yaw_only(-q), got)      # q and -q are the same rotation
+    # kNumInliersThreshold = max(min_inlier_count, int(samples * ratio)), defaults 10 / 0.2
+    assert capi.alignment_enough_inliers(10, 30) and not capi.alignment_enough_inliers(9, 30)
+    assert capi.alignment_enough_inliers(20, 100) and not capi.alignment_enough_inliers(19, 100)
+    assert capi.alignment_enough_inliers(0, 0, 0, 0.0)
