@@ -161,3 +161,24 @@ def test_create_summary_map_equals_reference_construction():
     with pytest.raises(capi.MlcError, match="do not add up"):
         det.create_summary_map(m["landmark_xyz"], counts[::-1] * 0 + 1, m["bits"][order], kf_of_desc[order],
                                m["kf_pos"][kf_of_desc[order]])
+
+
+def test_reference_summary_map_creation_test():
+    # map-structure/localization-summary-map/test/test_localization_summary_map_test.cc:28-86
+    # (LocalizationSummaryCreationFromMapTest): landmark 1 at (0, 0, 1) stored in v1 and observed by v2, v3; landmark 2
+    # at (0, 0, 2) stored in v2 and observed by v3; the summary map of {landmark 1, landmark 2} must hold 5
+    # observations with observation_to_landmark_index = 0 0 0 1 1 and observer indices = 0 1 2 1 2.
+    _, blob, _, _ = small_world()
+    det = capi.Detector(blob, capi.default_settings())
+    v1, v2, v3 = 101, 202, 303
+    bits = np.random.default_rng(0).integers(0, 256, (5, 64), dtype=np.uint8)
+    file_bytes = det.create_summary_map([[0, 0, 1], [0, 0, 2]], [3, 2], bits, [v1, v2, v3, v2, v3], np.zeros((5, 3)))
+    got = capi.summary_map_parse(file_bytes)
+    assert got["G_landmark_position"].shape == (3, 2)                              # ASSERT_EQ(cols, 2)
+    assert got["G_landmark_position"][:, 0].tolist() == [0, 0, 1]
+    assert got["G_landmark_position"][:, 1].tolist() == [0, 0, 2]
+    assert got["descriptors"].shape[1] == 5                                        # projectedDescriptors().cols()
+    assert got["observation_to_landmark_index"].tolist() == [0, 0, 0, 1, 1]
+    assert got["observer_indices"].tolist() == [0, 1, 2, 1, 2]
+    assert got["G_observer_position"].shape == (3, 3) and not got["G_observer_position"].any()
+    assert np.array_equal(got["descriptors"], det.project(bits).T)
