@@ -199,3 +199,64 @@ def test_oracle_relocalises_every_query_vertex_with_the_full_rig():
     err = np.linalg.norm(exp["T"][:, :, 3] - x["T_G_I"][q[::5, 1]][:, :, 3], axis=1)
     assert np.median(err) < 0.02 and err.max() < 0.08
     assert exp["num_inliers"].min() >= 20
+
+
+SUBMAPS = "/root/reference/tools/maplab-test-data/test_maps/submap_test"
+
+
+@pytest.mark.skipif(not os.path.isdir(SUBMAPS), reason="reference checkout not mounted")
+def test_oracle_closes_loops_across_the_reference_submaps():
+    # seven consecutive ~30 s submaps of one real stereo (radial-tangential cameras) session in a common frame:
+    # all of them in one database, each its own mission; every submap queried against it (the time filter only
+    # applies inside a mission). Closures into the neighbouring submaps agree with the stored poses to centimetres;
+    # the last submap closes the loop back to the first ones and exposes the odometry drift (0.5-0.8 m), on which
+    # the mission alignment (transformationRansac on T_G_M samples) finds a consensus.
+    from maplab_b200 import capi
+    from oracle import pyoracle as po
+    blob = open(os.path.join(GOLDEN, "brisk_quantizer_top10.dat"), "rb").read()
+    maps = []
+    for i in range(7):
+        vm = vi_map_io.load_vi_map(os.path.join(SUBMAPS, f"submap_{i}", "vi_map"))
+        maps.append((vm, vi_map_io.loop_closure_inputs(vm)))
+    cam_dicts = vi_map_io.cameras_of(maps[0][0]["sensors"])
+    assert [c["distortion"] for c in cam_dicts] == [2, 2]
+    cams = [po.make_camera(c["fu"], c["fv"], c["cu"], c["cv"], c["R_B_C"], c["t_B_C"], c["distortion"], c["dist"])
+            for c in cam_dicts]
+    ora = po.Engine(blob, po.default_settings())
+    xyz, lm_off = [], 0
+    for i, (_, x) in enumerate(maps):
+        proj, fr = ora.project(x["bits"]), x["frames"]
+        off = np.concatenate([[0], np.cumsum(fr[:, 3])])
+        for f in range(len(fr)):
+            s, e = off[f], off[f + 1]
+            ora.insert(int(fr[f, 0]), 1000 * i + int(fr[f, 1]), int(fr[f, 2]), i, proj[s:e], x["landmarks"][s:e] + lm_off)
+        xyz.append(x["landmark_xyz"])
+        lm_off += len(x["landmark_xyz"])
+    xyz = np.concatenate(xyz)
+    errors = []
+    for i, (_, x) in enumerate(maps):
+        fr = x["frames"]
+        frames = capi.make_frames(fr[:, 0], 1000 * i + fr[:, 1], np.full(len(fr), i, np.int64), fr[:, 2], fr[:, 3])
+        exp = po.query_batch(ora, frames, x["bits"], x["keypoints"], xyz, cams, num_threads=4)
+        acc = exp["accepted"].astype(bool)
+        assert acc.sum() >= 2, i
+        errors.append(np.linalg.norm(exp["T"][acc][:, :, 3] - x["T_G_I"][acc][:, :, 3], axis=1))
+        if i == 6:
+            T_lc, T_map = exp["T"][acc], x["T_G_I"][acc]
+    for i in (2, 3, 4, 5):  # middle of the session: only the neighbouring submaps are in view
+        assert errors[i].max() < 0.1
+    drift = errors[6][errors[6] > 0.3]
+    assert len(drift) >= 3 and drift.max() < 1.0
+    # T_G_M samples of the last submap: T_G_I(loop closure) * T_G_I(stored)^-1 -> consensus of the drifted ones
+    quats, poss = [], []
+    for a, b in zip(T_lc, T_map):
+        R = a[:, :3] @ b[:, :3].T
+        quats.append(_quat(R))
+        poss.append(a[:, 3] - R @ b[:, 3])
+    q, p, inl = po.transformation_ransac(np.array(quats), np.array(poss), 2000, 0.174, 2.0, 42)
+    assert len(inl) >= 3 and 0.3 < np.linalg.norm(p) < 1.5
+
+
+def _quat(R):
+    w = np.sqrt(max(0.0, 1 + np.trace(R))) / 2
+    return np.array([R[2, 1] - R[1, 2], R[0, 2] - R[2, 0], R[1, 0] - R[0, 1], 4 * w * w]) / (4 * w)
