@@ -207,3 +207,61 @@ def loop_closure_inputs(vi_map, camera_indices=None):
                 keypoints=np.concatenate(keypoints), landmarks=np.array(landmarks, np.int64),
                 landmark_xyz=np.array(landmark_xyz), T_G_I=T_G_I[:, :3, :],
                 vertex_ids=[i for i, _ in vertices])
+
+
+def load_vertices_native(folder):
+    """All `vertices<N>` files of a map folder through the library's own C++ reader (mlc_vi_map_count /
+    mlc_vi_map_read, no protobuf runtime): the arrays of capi.vi_map_read_vertices, concatenated."""
+    from . import capi
+    files = sorted(glob.glob(os.path.join(folder, "vertices*")), key=lambda p: int(p.rsplit("vertices", 1)[1]))
+    if not files:
+        raise FileNotFoundError(f"no vertices<N> files under {folder}")
+    parts = [capi.vi_map_read_vertices(read_proto_bytes(p)) for p in files]
+    widths = {p["keypoint_descriptor"].shape[1] for p in parts if p["keypoint_descriptor"].size}
+    if len(widths) > 1:
+        raise ValueError("descriptor sizes differ between the vertices files")
+    width = widths.pop() if widths else 0
+    for p in parts:
+        if not p["keypoint_descriptor"].size:
+            p["keypoint_descriptor"] = np.zeros((0, width), np.uint8)
+    return {k: np.concatenate([p[k] for p in parts]) for k in parts[0]}
+
+
+def loop_closure_inputs_native(arrays, missions, camera_indices=None):
+    """loop_closure_inputs() on the arrays of load_vertices_native; `missions` = {mission id tuple: T_G_M 4x4}
+    (load_vi_map(folder)["missions"]). Same output, same order."""
+    V = len(arrays["vertex_num_frames"])
+    frame_start = np.concatenate([[0], np.cumsum(arrays["vertex_num_frames"])])
+    kp_start = np.concatenate([[0], np.cumsum(arrays["frame_num_keypoints"])])
+    lm_start = np.concatenate([[0], np.cumsum(arrays["vertex_num_landmarks"])])
+    order = sorted(range(V), key=lambda v: arrays["frame_timestamp_ns"][frame_start[v]])
+    T_G_I = np.stack([missions[tuple(int(w) for w in arrays["mission_id"][v])] @ transform(arrays["T_M_I"][v])
+                      for v in order])
+    landmark_number, landmark_xyz = {}, []
+    for vi, v in enumerate(order):
+        for l in range(lm_start[v], lm_start[v + 1]):
+            if arrays["landmark_quality"][l] != 2:
+                continue
+            landmark_number[tuple(int(w) for w in arrays["landmark_id"][l])] = len(landmark_xyz)
+            landmark_xyz.append((T_G_I[vi] @ np.append(arrays["landmark_p_B"][l], 1.0))[:3])
+    mission_numbers = {}
+    frames, mission_of_frame, keep_rows, landmarks = [], [], [], []
+    for vi, v in enumerate(order):
+        mission = mission_numbers.setdefault(tuple(int(w) for w in arrays["mission_id"][v]), len(mission_numbers))
+        cams = range(arrays["vertex_num_frames"][v]) if camera_indices is None else camera_indices
+        for slot, ci in enumerate(cams):
+            f = frame_start[v] + ci
+            kept = 0
+            for k in range(kp_start[f], kp_start[f + 1]):
+                number = landmark_number.get(tuple(int(w) for w in arrays["keypoint_landmark_id"][k]))
+                if number is not None:
+                    keep_rows.append(k)
+                    landmarks.append(number)
+                    kept += 1
+            frames.append((int(arrays["frame_timestamp_ns"][f]), vi, slot, kept))
+            mission_of_frame.append(mission)
+    keep_rows = np.array(keep_rows, np.int64)
+    return dict(frames=np.array(frames, np.int64), missions=np.array(mission_of_frame, np.int64),
+                bits=arrays["keypoint_descriptor"][keep_rows], keypoints=arrays["keypoint_measurement"][keep_rows],
+                landmarks=np.array(landmarks, np.int64), landmark_xyz=np.array(landmark_xyz), T_G_I=T_G_I[:, :3, :],
+                vertex_ids=[tuple(int(w) for w in arrays["vertex_id"][v]) for v in order])

@@ -260,3 +260,16 @@ def test_oracle_closes_loops_across_the_reference_submaps():
 def _quat(R):
     w = np.sqrt(max(0.0, 1 + np.trace(R))) / 2
     return np.array([R[2, 1] - R[1, 2], R[0, 2] - R[2, 0], R[1, 0] - R[0, 1], 4 * w * w]) / (4 * w)
+
+
+@needs_reference
+def test_native_reader_feeds_the_same_inputs_as_the_protobuf_runtime():
+    # map folder -> C++ reader -> detector inputs == map folder -> protobuf runtime -> detector inputs
+    vm = vi_map_io.load_vi_map(MAP)
+    exp = vi_map_io.loop_closure_inputs(vm, (0, 2))
+    got = vi_map_io.loop_closure_inputs_native(vi_map_io.load_vertices_native(MAP), vm["missions"], (0, 2))
+    for key in ("frames", "missions", "bits", "keypoints", "landmarks", "landmark_xyz", "T_G_I"):
+        assert np.array_equal(got[key], exp[key]), key
+    assert got["vertex_ids"] == exp["vertex_ids"]
+    d = np.load(os.path.join(GOLDEN, "real_map_brisk.npz"))
+    assert np.array_equal(got["bits"], d["bits"]) and np.array_equal(got["keypoints"], d["keypoints"])
