@@ -390,6 +390,11 @@ typedef struct mlc_vi_map_arrays { /* caller-allocated from mlc_vi_map_counts; a
 int mlc_vi_map_count(const void* proto, size_t size, mlc_vi_map_counts* counts);
 /* `counts` must be what mlc_vi_map_count returned for the same bytes (checked). */
 int mlc_vi_map_read(const void* proto, size_t size, const mlc_vi_map_counts* counts, const mlc_vi_map_arrays* out);
+/* The `missions` file of the folder (vi_map.proto:102-131: missions and their base frames): up to `capacity`
+ * missions, mission_id 2 words and T_G_M 7 doubles (quaternion x y z w, position) each; *num_missions is always
+ * the number in the file (call with capacity 0 for the count). */
+int mlc_vi_map_missions(const void* proto, size_t size, int64_t capacity, uint64_t* mission_id, double* T_G_M,
+                        int64_t* num_missions);
 
 #ifdef __cplusplus
 }

@@ -23,7 +23,7 @@ EXPORTS = [
     "mlc_score", "mlc_save_index", "mlc_load_index", "mlc_set_query_priors",
     "mlc_default_alignment_settings", "mlc_transformation_ransac",
     "mlc_summary_map_parse", "mlc_summary_map_serialize", "mlc_add_summary_map", "mlc_create_summary_map",
-    "mlc_vi_map_count", "mlc_vi_map_read", "mlc_alignment_enough_inliers", "mlc_alignment_yaw_only",
+    "mlc_vi_map_count", "mlc_vi_map_read", "mlc_vi_map_missions", "mlc_alignment_enough_inliers", "mlc_alignment_yaw_only",
 ]
 
 
@@ -191,6 +191,17 @@ def vi_map_read_vertices(proto_bytes):
     arrays = ViMapArrays(**{k: (v.ctypes.data if v.size else None) for k, v in out.items()})
     _check(lib().mlc_vi_map_read(blob, C.c_size_t(len(blob)), C.byref(c), C.byref(arrays)))
     return out
+
+
+def vi_map_read_missions(proto_bytes):
+    """The `missions` message of a saved vi_map -> (mission ids [M][2] uint64, T_G_M [M][7])."""
+    blob = bytes(proto_bytes)
+    n = C.c_int64(0)
+    _check(lib().mlc_vi_map_missions(blob, C.c_size_t(len(blob)), C.c_int64(0), C.c_void_p(0), C.c_void_p(0),
+                                     C.byref(n)))
+    ids, T = np.zeros((n.value, 2), np.uint64), np.zeros((n.value, 7), np.float64)
+    _check(lib().mlc_vi_map_missions(blob, C.c_size_t(len(blob)), C.c_int64(n.value), _ptr(ids), _ptr(T), C.byref(n)))
+    return ids, T
 
 
 def alignment_yaw_only(quat_xyzw):

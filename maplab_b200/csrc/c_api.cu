@@ -1,4 +1,5 @@
 // extern "C" surface of libmaplab_lc_b200.so (include/maplab_lc_b200.h).
+#include <algorithm>
 #include <cmath>
 #include <cstring>
 #include <new>
@@ -426,6 +427,21 @@ int mlc_vi_map_read(const void* proto, size_t size, const mlc_vi_map_counts* cou
   copy(out->landmark_id, m.landmark_id);
   copy(out->landmark_p_B, m.landmark_p_B);
   copy(out->landmark_quality, m.landmark_quality);
+  return 0;
+}
+int mlc_vi_map_missions(const void* proto, size_t size, int64_t capacity, uint64_t* mission_id, double* T_G_M,
+                        int64_t* num_missions) {
+  MLC_REQUIRE(num_missions && capacity >= 0, "mlc_vi_map_missions: bad argument");
+  mlc::ViMapMissions m;
+  std::string err;
+  if (!m.Parse(proto, size, &err)) return Fail(err);
+  *num_missions = m.num_missions();
+  const int64_t n = std::min<int64_t>(capacity, m.num_missions());
+  if (n > 0) {
+    MLC_REQUIRE(mission_id && T_G_M, "mlc_vi_map_missions: null output");
+    std::memcpy(mission_id, m.mission_id.data(), sizeof(uint64_t) * 2 * n);
+    std::memcpy(T_G_M, m.T_G_M.data(), sizeof(double) * 7 * n);
+  }
   return 0;
 }
 int mlc_alignment_enough_inliers(int32_t num_inliers, int64_t num_samples, int32_t min_inlier_count,

@@ -202,7 +202,90 @@ bool ParseVertex(Reader r, ViMapVertices* m, std::string* err) {
   return true;
 }
 
+// first Id field (number `id_field`) and first repeated-double field (number `vec_field`) of a sub-message
+bool ParseIdAndVector(Reader r, uint32_t id_field, uint32_t vec_field, uint64_t id[2], std::vector<double>* vec) {
+  id[0] = id[1] = 0;
+  uint32_t field;
+  int wt;
+  while (r.p != r.end) {
+    if (!Key(&r, &field, &wt)) return false;
+    bool handled = false;
+    Reader sub;
+    if (id_field != 0 && field == id_field && wt == 2) {
+      if (!r.Sub(&sub) || !ParseId(sub, id)) return false;
+      handled = true;
+    } else if (vec_field != 0 && field == vec_field) {
+      if (!RepeatedDouble(&r, wt, vec, &handled)) return false;
+    }
+    if (!handled && !r.Skip(field, wt)) return false;
+  }
+  return true;
+}
+
 }  // namespace
+
+bool ViMapMissions::Parse(const void* proto, size_t size, std::string* err) {
+  *this = ViMapMissions();
+  if (size > 0 && !proto) {
+    *err = "vi_map: null buffer";
+    return false;
+  }
+  Reader r{static_cast<const uint8_t*>(proto), static_cast<const uint8_t*>(proto) + size};
+  std::vector<uint64_t> ids, base_of_mission, base_ids;
+  std::vector<double> base_T;
+  uint32_t field;
+  int wt;
+  bool ok = true;
+  while (ok && r.p != r.end) {
+    ok = Key(&r, &field, &wt);
+    if (!ok) break;
+    Reader sub;
+    uint64_t id[2];
+    if ((field == 5 || field == 7) && wt == 2) {
+      ok = r.Sub(&sub) && ParseId(sub, id);
+      std::vector<uint64_t>& dst = field == 5 ? ids : base_ids;
+      dst.push_back(id[0]);
+      dst.push_back(id[1]);
+    } else if (field == 6 && wt == 2) {  // Mission: baseframe_id = 1
+      std::vector<double> none;
+      ok = r.Sub(&sub) && ParseIdAndVector(sub, 1, 0, id, &none);
+      base_of_mission.push_back(id[0]);
+      base_of_mission.push_back(id[1]);
+    } else if (field == 8 && wt == 2) {  // MissionBaseframe: T_G_M = 1
+      std::vector<double> T;
+      ok = r.Sub(&sub) && ParseIdAndVector(sub, 0, 1, id, &T);
+      if (ok && T.size() != 7) {
+        *err = "vi_map: T_G_M is not a 7-vector (quaternion + position)";
+        return false;
+      }
+      base_T.insert(base_T.end(), T.begin(), T.end());
+    } else {
+      ok = r.Skip(field, wt);
+    }
+  }
+  if (!ok) {
+    *err = "vi_map: malformed protobuf wire data (is the file still gzip-compressed?)";
+    return false;
+  }
+  if (ids.size() != base_of_mission.size() || base_ids.size() / 2 != base_T.size() / 7) {
+    *err = "vi_map: mission / base frame ids and messages differ in number";
+    return false;
+  }
+  for (size_t m = 0; m < ids.size() / 2; ++m) {
+    size_t b = 0;
+    while (b < base_ids.size() / 2 &&
+           !(base_ids[2 * b] == base_of_mission[2 * m] && base_ids[2 * b + 1] == base_of_mission[2 * m + 1]))
+      ++b;
+    if (b == base_ids.size() / 2) {
+      *err = "vi_map: mission without base frame";
+      return false;
+    }
+    mission_id.push_back(ids[2 * m]);
+    mission_id.push_back(ids[2 * m + 1]);
+    T_G_M.insert(T_G_M.end(), base_T.begin() + 7 * b, base_T.begin() + 7 * (b + 1));
+  }
+  return true;
+}
 
 bool ViMapVertices::Parse(const void* proto, size_t size, std::string* err) {
   *this = ViMapVertices();

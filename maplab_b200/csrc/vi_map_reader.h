@@ -41,4 +41,14 @@ struct ViMapVertices {
   bool Parse(const void* proto, size_t size, std::string* err);
 };
 
+// The `missions` file of the same folder (vi_map.proto:102-131, :161-176: VIMap.mission_ids / missions /
+// mission_base_frame_ids / mission_base_frames): per mission its id and the T_G_M of its base frame
+// (7 doubles: quaternion x y z w, position).
+struct ViMapMissions {
+  std::vector<uint64_t> mission_id;  // 2 words each
+  std::vector<double> T_G_M;         // 7 each
+  int64_t num_missions() const { return static_cast<int64_t>(mission_id.size() / 2); }
+  bool Parse(const void* proto, size_t size, std::string* err);
+};
+
 }  // namespace mlc

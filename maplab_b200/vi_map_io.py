@@ -227,6 +227,13 @@ def load_vertices_native(folder):
     return {k: np.concatenate([p[k] for p in parts]) for k in parts[0]}
 
 
+def load_missions_native(folder):
+    """{mission id tuple: T_G_M 4x4} through the library's C++ reader of the `missions` file."""
+    from . import capi
+    ids, T = capi.vi_map_read_missions(read_proto_bytes(os.path.join(folder, "missions")))
+    return {tuple(int(w) for w in i): transform(t) for i, t in zip(ids, T)}
+
+
 def loop_closure_inputs_native(arrays, missions, camera_indices=None):
     """loop_closure_inputs() on the arrays of load_vertices_native; `missions` = {mission id tuple: T_G_M 4x4}
     (load_vi_map(folder)["missions"]). Same output, same order."""

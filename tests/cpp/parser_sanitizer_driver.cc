@@ -40,6 +40,8 @@ int main(int argc, char** argv) {
     }
     mlc::ViMapVertices vm;
     if (vm.Parse(blob.data(), blob.size(), &err)) ++accepted;
+    mlc::ViMapMissions missions;
+    if (missions.Parse(blob.data(), blob.size(), &err)) ++accepted;
     ++parsed;
   }
   std::printf("%zu blobs, %zu accepted\n", parsed, accepted);

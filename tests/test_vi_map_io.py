@@ -267,9 +267,33 @@ def test_native_reader_feeds_the_same_inputs_as_the_protobuf_runtime():
     # map folder -> C++ reader -> detector inputs == map folder -> protobuf runtime -> detector inputs
     vm = vi_map_io.load_vi_map(MAP)
     exp = vi_map_io.loop_closure_inputs(vm, (0, 2))
-    got = vi_map_io.loop_closure_inputs_native(vi_map_io.load_vertices_native(MAP), vm["missions"], (0, 2))
+    missions = vi_map_io.load_missions_native(MAP)
+    assert missions.keys() == vm["missions"].keys()
+    assert all(np.array_equal(missions[k], vm["missions"][k]) for k in missions)
+    got = vi_map_io.loop_closure_inputs_native(vi_map_io.load_vertices_native(MAP), missions, (0, 2))
     for key in ("frames", "missions", "bits", "keypoints", "landmarks", "landmark_xyz", "T_G_I"):
         assert np.array_equal(got[key], exp[key]), key
     assert got["vertex_ids"] == exp["vertex_ids"]
     d = np.load(os.path.join(GOLDEN, "real_map_brisk.npz"))
     assert np.array_equal(got["bits"], d["bits"]) and np.array_equal(got["keypoints"], d["keypoints"])
+
+
+def test_cxx_missions_reader_on_a_constructed_message():
+    from maplab_b200 import capi
+    msg = vi_map_io._vi_map_class()()
+    rng = np.random.default_rng(2)
+    base_ids = [[11, 12], [21, 22], [31, 32]]
+    Ts = rng.normal(size=(3, 7))
+    for b, T in zip(base_ids, Ts):
+        msg.mission_base_frame_ids.add().uint.extend(b)
+        msg.mission_base_frames.add().T_G_M.extend(T.tolist())
+    for m, b in (([1, 2], 2), ([3, 4], 0)):  # missions point at base frames out of order
+        msg.mission_ids.add().uint.extend(m)
+        msg.missions.add().baseframe_id.uint.extend(base_ids[b])
+    ids, T = capi.vi_map_read_missions(msg.SerializeToString())
+    assert ids.tolist() == [[1, 2], [3, 4]] and np.array_equal(T, Ts[[2, 0]])
+    msg.missions[1].baseframe_id.uint[0] = 99
+    with pytest.raises(capi.MlcError, match="without base frame"):
+        capi.vi_map_read_missions(msg.SerializeToString())
+    ids, T = capi.vi_map_read_missions(b"")
+    assert len(ids) == 0
