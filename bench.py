@@ -313,6 +313,7 @@ def run_b200(args):
     barrier()
     accepted = int(sum_over_ranks(float(out["results"]["accepted"].sum())))
     num_matches = int(sum_over_ranks(float(out["num_matches"])))
+    step_out = out
 
     # ---- timed: device-resident ----
     sampler = ClockSampler(local)
@@ -398,7 +399,8 @@ def run_b200(args):
         out["stage_ms"] = dict(zip(("project", "coarse", "scan", "vote_cluster", "ransac"),
                                    [round(float(x) / max(args.steps, 1), 4) for x in stage_acc]))
     if not args.no_cpu_baseline and world == 1:  # the CPU path is timed beside the N = 1 run only
-        out["cpu_baseline"] = cpu_baseline(args, m, blob, q, proj, frames)
+        out["cpu_baseline"], oracle_result = cpu_baseline(args, m, blob, q, proj, frames)
+        out["parity_checked"] = parity_check(step_out, oracle_result)
     if args.engine != "imi":
         out["config"]["engine"] = args.engine
     if world == 1 and not args.no_scan_probe and args.engine == "imi":
@@ -453,7 +455,26 @@ def cpu_baseline(args, m, blob, q, proj, frames):
                       f"{st['project']:.2f}/{st['find']:.2f}/{st['verify']:.2f}; oracle db build "
                       f"{t_build:.1f}s not included; oracle = CPU restatement of maplab (the real "
                       f"binary cannot be built here)",
-            "accepted": int(r["accepted"].sum())}
+            "accepted": int(r["accepted"].sum())}, r
+
+
+def parity_check(step_out, r):
+    """The GPU step's results against the oracle's on the same query keyframes (the oracle ran on the
+    first len(r) keyframes of the step): verdicts, inlier counts, RANSAC iterations, match counts and
+    poses must be identical. Checker only — after the timed region, never on the measured path."""
+    n = len(r["accepted"])
+    res = step_out["results"][:n]
+    T = res["T_G_I"].reshape(-1, 3, 4)
+    ok = r["ransac_success"].astype(bool)
+    bad = ((res["accepted"] != r["accepted"]) | (res["num_inliers"] != r["num_inliers"]) |
+           (res["iterations"] != r["iterations"]) | (res["ransac_success"] != r["ransac_success"]) |
+           (np.diff(step_out["offsets"])[:n] != r["num_matches"]))
+    pose_bad = np.zeros(n, bool)
+    pose_bad[ok] = (T[ok] != r["T"][ok]).any(axis=(1, 2))
+    return {"keyframes": int(n), "mismatches": int((bad | pose_bad).sum()),
+            "compared": "accepted, num_inliers, iterations, ransac_success, matches per vertex, T_G_I "
+                        "(bit-exact) of the step's keyframes vs the CPU oracle",
+            "max_abs_pose_diff": float(np.abs(T[ok] - r["T"][ok]).max(initial=0.0))}
 
 
 def run_reference(args):

@@ -227,3 +227,74 @@ def make_queries(m, num_queries, seed=11, desc_per_keyframe=500, outlier_frac=0.
 def camera_dict():
     return dict(fu=CAMERA["fu"], fv=CAMERA["fv"], cu=CAMERA["cu"], cv=CAMERA["cv"],
                 R_B_C=np.eye(3), t_B_C=np.zeros(3))
+
+
+# ----------------------------------------------------------------------------- BASELINE config 1
+def _mt19937_canonical(seed, n):
+    """n draws of std::uniform_real_distribution<double>(0, 1) over std::mt19937(seed) as libstdc++
+    computes them (generate_canonical<double, 53>: two 32-bit outputs, low word first)."""
+    raw = np.frombuffer(np.random.RandomState(seed).bytes(8 * n), "<u4").astype(np.float64).reshape(n, 2)
+    return np.minimum((raw[:, 0] + raw[:, 1] * 4294967296.0) / 18446744073709551616.0, np.nextafter(1.0, 0.0))
+
+
+def make_6dof_map(num_vertices=20, num_landmarks=500, seed=10, descriptor_seed=1):
+    """The recipe of maplab's `vi-map-generator-6dof` (BASELINE.json config 1) restated:
+    test/vi-map-generator-6dof/src/6dof-vi-map-gen.cc:25,30 (500 landmarks, 20 vertices),
+    6dof-pose-graph-gen.cc:22-62 (pinhole fu = fv = 100, 640 x 480, zero distortion, camera turned 90 degrees
+    about z against the IMU), :198-201 (one random 48-byte descriptor per landmark), :300-317 (every
+    observation of a landmark carries the SAME descriptor with 30 deterministic bits OR-ed in: bit i % 8
+    of byte i for i < 30), :323 (all frame timestamps 0, one mission — self loop-closure needs
+    --lc_min_image_time_seconds=0), keypoints = exact projections, landmark positions without noise.
+    Landmarks: algorithms/simulation/src/generic-path-generator.cc:326-353 drawn exactly like the
+    reference draws them (std::mt19937(landmark_seed = 10), uniform_real_distribution, circle radius 10 m,
+    5 m to the keypoints, 3 m variance, vertical factor 2). Not restated: the trajectory itself comes from a
+    polynomial path file + RK4 IMU integration (mav_planning_utils, imu-integrator); here the vertices sit
+    on the same 10 m circle, evenly spaced, with the roll / pitch / height excitation of
+    6dof-test-trajectory-gen.cc:66-82 in closed form. Returns a dict like make_map plus keypoints, T_G_I
+    and camera."""
+    u = _mt19937_canonical(seed, 3 * num_landmarks).reshape(num_landmarks, 3)
+    angle = u[:, 0] * 2 * np.pi
+    radius = 10.0 + 5.0 + 3.0 * (u[:, 1] - 0.5)
+    xyz = np.stack([radius * np.cos(angle), radius * np.sin(angle), 2.0 * 3.0 * (u[:, 2] - 0.5)], 1)
+    rng = np.random.default_rng(descriptor_seed)
+    base = rng.integers(0, 256, size=(num_landmarks, 48), dtype=np.uint8)
+    for i in range(30):
+        base[:, i % 48] |= np.uint8(1 << (i % 8))
+    cam = dict(fu=100.0, fv=100.0, cu=320.0, cv=240.0, width=640, height=480)
+    c, s = np.sqrt(0.5), np.sqrt(0.5)
+    R_C_I = np.array([[c * c - s * s, -2 * c * s, 0], [2 * c * s, c * c - s * s, 0], [0, 0, 1.0]])  # C_q_I = (w, z) = (c, s)
+    R_I_C = R_C_I.T
+    duration = 33.0
+    frames_bits, frames_kp, frames_lm, poses, counts = [], [], [], [], []
+    for v in range(num_vertices):
+        t = duration * v / num_vertices
+        theta = 2 * np.pi * v / num_vertices
+        yaw = theta + np.pi / 2
+        roll = 0.75 / (0.5 * np.pi) * (1 - np.cos(0.5 * np.pi * t))     # integral of the x gyro excitation
+        pitch = -0.75 / (0.5 * np.pi) * (1 - np.cos(0.5 * np.pi * t))   # y gyro excitation (phase pi)
+        cz, sz, cr, sr, cp, sp = np.cos(yaw), np.sin(yaw), np.cos(roll), np.sin(roll), np.cos(pitch), np.sin(pitch)
+        Rz = np.array([[cz, -sz, 0], [sz, cz, 0], [0, 0, 1.0]])
+        Ry = np.array([[cp, 0, sp], [0, 1, 0], [-sp, 0, cp]])
+        Rx = np.array([[1, 0, 0], [0, cr, -sr], [0, sr, cr]])
+        R_G_I = Rz @ Ry @ Rx
+        p_G_I = np.array([10 * np.cos(theta), 10 * np.sin(theta), 5.0 / np.pi ** 2 * (1 - np.cos(np.pi * t))])
+        R_G_C = R_G_I @ R_I_C
+        pc = (xyz - p_G_I) @ R_G_C
+        with np.errstate(divide="ignore", invalid="ignore"):
+            uu = cam["fu"] * pc[:, 0] / pc[:, 2] + cam["cu"]
+            vv = cam["fv"] * pc[:, 1] / pc[:, 2] + cam["cv"]
+        vis = (pc[:, 2] > 0) & (uu >= 0) & (uu < cam["width"]) & (vv >= 0) & (vv < cam["height"])
+        ids = np.nonzero(vis)[0]
+        frames_bits.append(base[ids])
+        frames_kp.append(np.stack([uu[ids], vv[ids]], 1))
+        frames_lm.append(ids.astype(np.int64))
+        poses.append(np.concatenate([R_G_I, p_G_I[:, None]], 1))
+        counts.append(len(ids))
+    vid = np.arange(num_vertices, dtype=np.int64)
+    frames = dict(timestamp_ns=np.zeros(num_vertices, np.int64), vertex_id=vid,
+                  mission_id=np.zeros(num_vertices, np.int64), frame_index=np.zeros(num_vertices, np.int32),
+                  num_descriptors=np.asarray(counts, np.int32))
+    camera = dict(fu=cam["fu"], fv=cam["fv"], cu=cam["cu"], cv=cam["cv"], R_B_C=R_I_C, t_B_C=np.zeros(3))
+    return dict(frames=frames, bits=np.concatenate(frames_bits), keypoints=np.concatenate(frames_kp),
+                landmarks=np.concatenate(frames_lm), landmark_xyz=xyz, base=base, T_G_I=np.stack(poses),
+                camera=camera)

@@ -1,12 +1,15 @@
-"""Size-independent properties at BASELINE.json's map size (1 M landmarks, ~4 M database
-descriptors, W = 1000 x 1000 cells) where the CPU oracle is too slow to be the checker:
-determinism, host path == device path, batch-order invariance, sharded merge == single index,
-ground-truth pose recovery."""
+"""BASELINE.json's headline configuration (1 M landmarks, ~4 M database descriptors, W = 1000 x 1000
+cells, 500-descriptor query keyframes, auto-k = 6): the CUDA path diffed against the CPU oracle on
+the same world bench.py measures (visited cells, cell assignment, kNN indices and distances, match
+counts, verdicts, inlier counts, RANSAC iterations and poses — bit-exact), plus size-independent
+properties: determinism, host path == device path, batch-order invariance, sharded merge == single
+index, ground-truth pose recovery."""
 import numpy as np
 import pytest
 
 from maplab_b200 import capi, synthetic
-from helpers import frames_of
+from oracle import pyoracle as po
+from helpers import fill_oracle, frames_of
 
 pytestmark = pytest.mark.gpu
 
@@ -25,6 +28,58 @@ def world():
     det.insert_batch(frames, proj, m["landmarks"])
     det.set_landmark_positions(m["landmark_xyz"])
     return m, blob, q, det, frames, proj
+
+
+@pytest.fixture(scope="module")
+def oracle_world(world):
+    m, blob, q, det, frames, proj = world
+    ora = po.Engine(blob)
+    fill_oracle(ora, frames, proj, m["landmarks"])
+    return ora
+
+
+def test_full_size_matches_oracle(world, oracle_world):
+    """The headline configuration itself against the oracle (W = 1000 trees, ~4-entry lists in a
+    10^6-cell table, auto-k = 6, the persistent scan at full grid): nothing here is property-based."""
+    m, blob, q, det, frames, proj = world
+    ora = oracle_world
+    assert det.num_descriptors() == ora.num_descriptors() == len(proj)
+    k = det.num_neighbors()
+    assert k == ora.num_neighbors() == 6
+    # P1: projection of a database sample and of all query descriptors
+    sample = np.arange(0, len(proj), 37)[:100_000]
+    assert np.array_equal(proj[sample], ora.project(m["bits"][sample]))
+    qp = det.project(q["bits"])
+    assert np.array_equal(qp, ora.project(q["bits"]))
+    assert len(qp) == 80_000
+    # P2 / P3: cell of database descriptors, visited cells of every query descriptor
+    v = synthetic.parse_vocabulary(blob)
+    imi = po.IMI(po.colmajor(v["W1"]), v["W1"].shape[1], po.colmajor(v["W2"]), v["W2"].shape[1], 5, 10)
+    assert np.array_equal(det.coarse_cells(qp, 10), imi.visited_cells(qp, len(qp)))
+    db_sample = proj[sample[:20_000]]
+    assert np.array_equal(det.coarse_cells(db_sample, 1)[:, 0],
+                          np.array([imi.cell_of(d) for d in db_sample]))
+    # P4: kNN indices and distances at the auto-k, all 80 000 query descriptors
+    idx, dist = det.knn(qp, k)
+    oidx, odist = ora.knn(qp, k)
+    assert np.array_equal(idx, oidx)
+    assert np.array_equal(dist, odist)
+    assert (idx >= 0).mean() > 0.5
+    # P5-P9: the fused query of all 160 keyframes
+    cam = synthetic.camera_dict()
+    qframes = frames_of(q["frames"])
+    out = det.query_batch(qframes, q["bits"], q["keypoints"], capi.make_cameras([cam]))
+    exp = po.query_batch(ora, qframes, q["bits"], q["keypoints"], m["landmark_xyz"],
+                         [po.make_camera(cam["fu"], cam["fv"], cam["cu"], cam["cv"])], num_threads=8)
+    res = out["results"]
+    assert np.array_equal(res["accepted"], exp["accepted"])
+    assert np.array_equal(res["num_inliers"], exp["num_inliers"])
+    assert np.array_equal(res["iterations"], exp["iterations"])
+    assert np.array_equal(res["ransac_success"], exp["ransac_success"])
+    assert np.array_equal(np.diff(out["offsets"]), exp["num_matches"])
+    ok = exp["ransac_success"].astype(bool)
+    assert np.array_equal(res["T_G_I"].reshape(-1, 3, 4)[ok], exp["T"][ok])
+    assert res["accepted"].sum() >= 150
 
 
 def test_full_size_determinism_host_device_and_order(world):
