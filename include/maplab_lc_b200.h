@@ -138,11 +138,29 @@ int mlc_project_device(mlc_detector* d, const uint8_t* d_bits, int bytes_per_des
                        float* d_out, void* stream);
 
 /* LoopDetector::Insert(ProjectedImage::Ptr), MBL/src/matching-based-engine.cc:217-253.
- * proj: num_descriptors x dim floats (host); landmarks: num_descriptors ids (may be NULL). */
+ * proj: num_descriptors x dim floats (host); landmarks: num_descriptors ids (may be NULL).
+ * Like the reference's CHECK (:244-252) a keyframe (vertex id, frame index) that is already in the
+ * database is refused (non-zero return, nothing inserted). */
 int mlc_insert(mlc_detector* d, const mlc_frame* frame, const float* proj, const int64_t* landmarks);
 /* Bulk variant: `num_frames` frames whose descriptors are concatenated in `proj`/`landmarks`. */
 int mlc_insert_batch(mlc_detector* d, const mlc_frame* frames, int64_t num_frames, const float* proj,
                      const int64_t* landmarks);
+
+/* Sharded database build (SURVEY.md section 8e "DB build shards trivially too"): descriptor i of the
+ * database lives on shard i % shard_count, so a process only has to project — and hand over — the
+ * descriptors its shard owns. Keyframe headers and landmark numbers cover ALL descriptors of the batch
+ * (they are replicated metadata, like the reference's per-keyframe ProjectedImage copies,
+ * MBL/src/matching-based-engine.cc:227-251); `proj_owned` holds one row per OWNED descriptor of the
+ * batch in ascending global index (mlc_num_owned_in_range(d, mlc_num_descriptors(d), batch total) rows).
+ * With shard_count == 1 these equal mlc_insert_batch. The _device variant takes device pointers
+ * (d_landmarks may be NULL) — the database lives in HBM, nothing is staged on the host. */
+int mlc_insert_batch_owned(mlc_detector* d, const mlc_frame* frames, int64_t num_frames,
+                           const float* proj_owned, const int64_t* landmarks);
+int mlc_insert_batch_device(mlc_detector* d, const mlc_frame* frames, int64_t num_frames,
+                            const float* d_proj_owned, int64_t num_owned, const int64_t* d_landmarks,
+                            void* stream);
+/* Number of global descriptor indices in [first, first + count) owned by this shard. */
+int64_t mlc_num_owned_in_range(const mlc_detector* d, int64_t first, int64_t count);
 
 /* LoopDetector::Initialize (MBL/include/.../matching-based-engine.h:24) — here: freeze the
  * inserted keyframes and build the device index (cell assignment = FindClosestWords(desc, 1),

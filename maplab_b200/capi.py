@@ -16,7 +16,8 @@ EXPORTS = [
     "mlc_last_error", "mlc_version", "mlc_kernel_launch_count", "mlc_default_settings",
     "mlc_default_ransac_settings", "mlc_create", "mlc_destroy", "mlc_clear", "mlc_num_entries",
     "mlc_num_descriptors", "mlc_num_neighbors", "mlc_target_dim", "mlc_project",
-    "mlc_project_device", "mlc_insert", "mlc_insert_batch", "mlc_initialize", "mlc_knn",
+    "mlc_project_device", "mlc_insert", "mlc_insert_batch", "mlc_insert_batch_owned",
+    "mlc_insert_batch_device", "mlc_num_owned_in_range", "mlc_initialize", "mlc_knn",
     "mlc_knn_device", "mlc_coarse_cells", "mlc_merge_topk_device", "mlc_last_scan_stats",
     "mlc_find_batch", "mlc_find_batch_bits", "mlc_find_from_knn_device", "mlc_pnp_ransac_batch",
     "mlc_coarse_device", "mlc_scan_device", "mlc_last_stage_ms", "mlc_set_landmark_positions", "mlc_query_batch", "mlc_query_batch_device", "mlc_query_from_knn_device",
@@ -100,6 +101,7 @@ def lib():
         _lib.mlc_kernel_launch_count.restype = C.c_uint64
         _lib.mlc_num_entries.restype = C.c_int64
         _lib.mlc_num_descriptors.restype = C.c_int64
+        _lib.mlc_num_owned_in_range.restype = C.c_int64
         _lib.mlc_destroy.restype = None
         _lib.mlc_default_settings.restype = None
         _lib.mlc_default_ransac_settings.restype = None
@@ -293,6 +295,25 @@ class Detector:
         lm = None if landmarks is None else np.ascontiguousarray(landmarks, np.int64)
         _check(lib().mlc_insert_batch(self._h, _ptr(frames), C.c_int64(len(frames)), _ptr(proj),
                                       _ptr(lm) if lm is not None else C.c_void_p(0)))
+
+    def num_owned_in_range(self, first, count):
+        return int(lib().mlc_num_owned_in_range(self._h, C.c_int64(first), C.c_int64(count)))
+
+    def insert_batch_owned(self, frames, proj_owned, landmarks=None):
+        """Sharded build: rows of the descriptors this shard owns only (ascending global index)."""
+        frames = np.ascontiguousarray(frames, FRAME_DTYPE)
+        proj = np.ascontiguousarray(proj_owned, np.float32).reshape(-1, self.dim)
+        total = int(frames["num_descriptors"].sum())
+        assert self.num_owned_in_range(self.num_descriptors(), total) == proj.shape[0]
+        lm = None if landmarks is None else np.ascontiguousarray(landmarks, np.int64)
+        _check(lib().mlc_insert_batch_owned(self._h, _ptr(frames), C.c_int64(len(frames)), _ptr(proj),
+                                            _ptr(lm) if lm is not None else C.c_void_p(0)))
+
+    def insert_batch_device(self, frames, proj_owned_ptr, num_owned, landmarks_ptr=0, stream=0):
+        frames = np.ascontiguousarray(frames, FRAME_DTYPE)
+        _check(lib().mlc_insert_batch_device(self._h, _ptr(frames), C.c_int64(len(frames)),
+                                             C.c_void_p(proj_owned_ptr), C.c_int64(num_owned),
+                                             C.c_void_p(landmarks_ptr), C.c_void_p(stream)))
 
     def insert(self, ts, vertex, frame_index, mission, proj, landmarks=None):
         proj = np.ascontiguousarray(proj, np.float32).reshape(-1, self.dim)

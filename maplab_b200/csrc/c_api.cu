@@ -109,7 +109,25 @@ int mlc_insert_batch(mlc_detector* d, const mlc_frame* frames, int64_t num_frame
                      const int64_t* landmarks) {
   MLC_REQUIRE(d && frames && num_frames >= 0, "mlc_insert: null argument");
   std::string err;
-  return d->impl.InsertBatch(frames, num_frames, proj, landmarks, &err) ? 0 : Fail(err);
+  return d->impl.InsertBatch(frames, num_frames, proj, landmarks, false, &err) ? 0 : Fail(err);
+}
+int mlc_insert_batch_owned(mlc_detector* d, const mlc_frame* frames, int64_t num_frames, const float* proj_owned,
+                           const int64_t* landmarks) {
+  MLC_REQUIRE(d && frames && num_frames >= 0, "mlc_insert_batch_owned: null argument");
+  std::string err;
+  return d->impl.InsertBatch(frames, num_frames, proj_owned, landmarks, true, &err) ? 0 : Fail(err);
+}
+int mlc_insert_batch_device(mlc_detector* d, const mlc_frame* frames, int64_t num_frames, const float* d_proj_owned,
+                            int64_t num_owned, const int64_t* d_landmarks, void* stream) {
+  MLC_REQUIRE(d && frames && num_frames >= 0, "mlc_insert_batch_device: null argument");
+  std::string err;
+  return d->impl.InsertBatchDevice(frames, num_frames, d_proj_owned, num_owned, d_landmarks,
+                                   static_cast<cudaStream_t>(stream), &err)
+             ? 0
+             : Fail(err);
+}
+int64_t mlc_num_owned_in_range(const mlc_detector* d, int64_t first, int64_t count) {
+  return d ? d->impl.OwnedInRange(first, count) : -1;
 }
 int mlc_initialize(mlc_detector* d) {
   MLC_REQUIRE(d, "null detector");

@@ -24,9 +24,12 @@ Detector::~Detector() {
   if (d_pq_blob_) cudaFree(d_pq_blob_);
   if (proj_.b_image) cudaFree(proj_.b_image);
   lists_.Free();
-  DevBuf* bufs[] = {&d_db_cells_, &d_desc_kf_, &d_desc_lm_, &d_kf_meta_, &d_q_,    &d_cells_,
+  DevBuf* bufs[] = {&d_db_cells_, &d_desc_kf_, &d_kf_meta_, &d_q_,    &d_cells_,
                     &d_idx_,      &d_dist_,    &d_bits_,    &d_stats_};
   for (DevBuf* b : bufs) b->Free();
+  d_own_desc_.Free();
+  d_own_gidx_.Free();
+  d_desc_lm_.Free();
   for (DevBuf& b : d_covis_) b.Free();
   for (DevBuf& b : d_ransac_) b.Free();
   for (DevBuf& b : d_query_) b.Free();
@@ -211,9 +214,12 @@ bool Detector::UploadTrees(std::string* err) {
 bool Detector::Clear(std::string* err) {
   std::lock_guard<std::recursive_mutex> lock(mu_);
   keyframes_.clear();
-  desc_.clear();
-  landmarks_.clear();
-  desc_kf_.clear();
+  keyframe_keys_.clear();
+  num_desc_ = num_own_ = 0;
+  pend_desc_.clear();
+  pend_gidx_.clear();
+  pend_lm_.clear();
+  d_own_desc_.used = d_own_gidx_.used = d_desc_lm_.used = 0;
   lists_.Free();
   index_dirty_ = true;
   last_valid_ = false;
@@ -277,10 +283,139 @@ bool Detector::Project(const uint8_t* bits, int bytes_per_desc, int64_t n, float
   return Cuda(cudaStreamSynchronize(stream_), "projection", err);
 }
 
+namespace {
+// descriptor -> keyframe number for every descriptor of the database, from the keyframe headers
+// (one CTA per keyframe; the reference keeps this as unordered_map<int, KeypointId>,
+// matching-based-engine.cc:227-238).
+__global__ void expand_desc_kf_kernel(const KeyframeMeta* __restrict__ kf, int32_t* __restrict__ desc_kf) {
+  const KeyframeMeta m = kf[blockIdx.x];
+  for (int i = threadIdx.x; i < m.num_descriptors; i += blockDim.x)
+    desc_kf[static_cast<int64_t>(m.first_descriptor) + i] = static_cast<int32_t>(blockIdx.x);
+}
+__global__ void owned_indices_kernel(int64_t first_owned, int64_t n, int shard_count, int32_t* __restrict__ out) {
+  const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (i < n) out[i] = static_cast<int32_t>(first_owned + i * shard_count);
+}
+__global__ void fill_i64_kernel(int64_t* __restrict__ p, int64_t n, int64_t v) {
+  const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+constexpr size_t kPendingFlushBytes = size_t{64} << 20;  // host staging of Insert is bounded by this
+}  // namespace
+
+// Number of descriptors of [first, first + count) that live on this shard (descriptor i on shard
+// i % shard_count).
+int64_t Detector::OwnedInRange(int64_t first, int64_t count) const {
+  const int64_t G = s_.shard_count, r = s_.shard_rank;
+  auto upto = [&](int64_t x) { return x <= r ? int64_t{0} : (x - r + G - 1) / G; };  // owned in [0, x)
+  return upto(first + count) - upto(first);
+}
+
+// LoopDetector::Insert, matching-based-engine.cc:217-253: consecutive global descriptor indices,
+// keyframe ids must be new (CHECK :244-252).
 bool Detector::InsertBatch(const mlc_frame* frames, int64_t num_frames, const float* proj,
-                           const int64_t* landmarks, std::string* err) {
+                           const int64_t* landmarks, bool proj_is_owned_rows, std::string* err) {
   std::lock_guard<std::recursive_mutex> lock(mu_);
   const int d = dim();
+  int64_t total = 0;
+  for (int64_t f = 0; f < num_frames; ++f) {
+    if (frames[f].num_descriptors < 0) {
+      *err = "negative descriptor count";
+      return false;
+    }
+    total += frames[f].num_descriptors;
+  }
+  if (total > 0 && !proj) {
+    *err = "mlc_insert: null projected descriptors";
+    return false;
+  }
+  if (NumDescriptors() + total > 2147483647LL) {
+    *err = "descriptor indices are int (SURVEY H7): database would exceed 2^31-1 descriptors";
+    return false;
+  }
+  // Insert's CHECK: "keyframe id already in the database" — checked for the whole batch before
+  // anything is changed
+  {
+    std::unordered_set<KeyframeKey, KeyframeKeyHash> batch;
+    for (int64_t f = 0; f < num_frames; ++f) {
+      const KeyframeKey key{frames[f].vertex_id, frames[f].frame_index};
+      if (keyframe_keys_.count(key) || !batch.insert(key).second) {
+        *err = "Insert: keyframe (vertex " + std::to_string(key.vertex) + ", frame " +
+               std::to_string(key.frame_index) + ") is already in the database";
+        return false;
+      }
+    }
+  }
+  const int64_t G = s_.shard_count, r = s_.shard_rank;
+  const int64_t base = num_desc_;
+  for (int64_t f = 0; f < num_frames; ++f) {
+    KeyframeMeta m;
+    m.ts = frames[f].timestamp_ns;
+    m.vertex = frames[f].vertex_id;
+    m.mission = frames[f].mission_id;
+    m.frame_index = frames[f].frame_index;
+    m.first_descriptor = static_cast<int32_t>(num_desc_);
+    m.num_descriptors = frames[f].num_descriptors;
+    keyframes_.push_back(m);
+    keyframe_keys_.insert(KeyframeKey{m.vertex, m.frame_index});
+    num_desc_ += m.num_descriptors;
+  }
+  if (landmarks)
+    pend_lm_.insert(pend_lm_.end(), landmarks, landmarks + total);
+  else
+    pend_lm_.insert(pend_lm_.end(), static_cast<size_t>(total), int64_t{-1});
+  // first owned global index >= base
+  int64_t g = base + ((r - base % G) % G + G) % G;
+  if (proj_is_owned_rows || G == 1) {
+    const int64_t owned = OwnedInRange(base, total);
+    pend_desc_.insert(pend_desc_.end(), proj, proj + static_cast<size_t>(owned) * d);
+    for (int64_t j = 0; j < owned; ++j) pend_gidx_.push_back(static_cast<int32_t>(g + j * G));
+  } else {
+    for (; g < base + total; g += G) {
+      const float* row = proj + static_cast<size_t>(g - base) * d;
+      pend_desc_.insert(pend_desc_.end(), row, row + d);
+      pend_gidx_.push_back(static_cast<int32_t>(g));
+    }
+  }
+  index_dirty_ = true;
+  if (pend_desc_.size() * 4 + pend_lm_.size() * 8 >= kPendingFlushBytes) return FlushPending(err);
+  return true;
+}
+
+// Staged host rows -> device arrays (appended).
+bool Detector::FlushPending(std::string* err) {
+  const size_t nl = pend_lm_.size(), no = pend_gidx_.size();
+  if (nl > 0) {
+    if (!Cuda(d_desc_lm_.Extend(nl * 8, stream_), "grow landmark numbers", err) ||
+        !Cuda(cudaMemcpyAsync(d_desc_lm_.end(), pend_lm_.data(), nl * 8, cudaMemcpyHostToDevice, stream_),
+              "H2D landmark numbers", err))
+      return false;
+    d_desc_lm_.used += nl * 8;
+  }
+  if (no > 0) {
+    const size_t db = no * dim() * 4;
+    if (!Cuda(d_own_desc_.Extend(db, stream_), "grow descriptors", err) ||
+        !Cuda(d_own_gidx_.Extend(no * 4, stream_), "grow descriptor indices", err) ||
+        !Cuda(cudaMemcpyAsync(d_own_desc_.end(), pend_desc_.data(), db, cudaMemcpyHostToDevice, stream_),
+              "H2D descriptors", err) ||
+        !Cuda(cudaMemcpyAsync(d_own_gidx_.end(), pend_gidx_.data(), no * 4, cudaMemcpyHostToDevice, stream_),
+              "H2D descriptor indices", err))
+      return false;
+    d_own_desc_.used += db;
+    d_own_gidx_.used += no * 4;
+    num_own_ += static_cast<int64_t>(no);
+  }
+  if (!Cuda(cudaStreamSynchronize(stream_), "insert", err)) return false;
+  pend_lm_.clear();
+  pend_desc_.clear();
+  pend_gidx_.clear();
+  return true;
+}
+
+bool Detector::InsertBatchDevice(const mlc_frame* frames, int64_t num_frames, const float* d_proj_owned,
+                                 int64_t num_owned, const int64_t* d_landmarks, cudaStream_t stream,
+                                 std::string* err) {
+  std::lock_guard<std::recursive_mutex> lock(mu_);
   int64_t total = 0;
   for (int64_t f = 0; f < num_frames; ++f) {
     if (frames[f].num_descriptors < 0) {
@@ -293,23 +428,72 @@ bool Detector::InsertBatch(const mlc_frame* frames, int64_t num_frames, const fl
     *err = "descriptor indices are int (SURVEY H7): database would exceed 2^31-1 descriptors";
     return false;
   }
-  int64_t at = 0;
+  const int64_t base = num_desc_, G = s_.shard_count, r = s_.shard_rank;
+  const int64_t owned = OwnedInRange(base, total);
+  if (num_owned != owned) {
+    *err = "mlc_insert_batch_device: this shard owns " + std::to_string(owned) + " of the batch's " +
+           std::to_string(total) + " descriptors, got " + std::to_string(num_owned) + " rows";
+    return false;
+  }
+  if (owned > 0 && !d_proj_owned) {
+    *err = "mlc_insert_batch_device: null projected descriptors";
+    return false;
+  }
+  {
+    std::unordered_set<KeyframeKey, KeyframeKeyHash> batch;
+    for (int64_t f = 0; f < num_frames; ++f) {
+      const KeyframeKey key{frames[f].vertex_id, frames[f].frame_index};
+      if (keyframe_keys_.count(key) || !batch.insert(key).second) {
+        *err = "Insert: keyframe (vertex " + std::to_string(key.vertex) + ", frame " +
+               std::to_string(key.frame_index) + ") is already in the database";
+        return false;
+      }
+    }
+  }
+  if (!FlushPending(err)) return false;  // keep the device arrays in insertion order
+  if (!Cuda(cudaStreamSynchronize(stream), "caller stream", err)) return false;
+  const size_t db = static_cast<size_t>(owned) * dim() * 4;
+  if (!Cuda(d_desc_lm_.Extend(static_cast<size_t>(total) * 8, stream_), "grow landmark numbers", err) ||
+      !Cuda(d_own_desc_.Extend(db, stream_), "grow descriptors", err) ||
+      !Cuda(d_own_gidx_.Extend(static_cast<size_t>(owned) * 4, stream_), "grow descriptor indices", err))
+    return false;
+  if (total > 0) {
+    if (d_landmarks) {
+      if (!Cuda(cudaMemcpyAsync(d_desc_lm_.end(), d_landmarks, static_cast<size_t>(total) * 8,
+                                cudaMemcpyDeviceToDevice, stream_), "copy landmark numbers", err))
+        return false;
+    } else {
+      fill_i64_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream_>>>(
+          reinterpret_cast<int64_t*>(d_desc_lm_.end()), total, -1);
+      CountLaunch();
+    }
+  }
+  if (owned > 0) {
+    const int64_t g = base + ((r - base % G) % G + G) % G;
+    if (!Cuda(cudaMemcpyAsync(d_own_desc_.end(), d_proj_owned, db, cudaMemcpyDeviceToDevice, stream_),
+              "copy descriptors", err))
+      return false;
+    owned_indices_kernel<<<static_cast<unsigned>((owned + 255) / 256), 256, 0, stream_>>>(
+        g, owned, static_cast<int>(G), reinterpret_cast<int32_t*>(d_own_gidx_.end()));
+    CountLaunch();
+  }
+  if (!Cuda(cudaStreamSynchronize(stream_), "insert", err)) return false;
+  d_desc_lm_.used += static_cast<size_t>(total) * 8;
+  d_own_desc_.used += db;
+  d_own_gidx_.used += static_cast<size_t>(owned) * 4;
+  num_own_ += owned;
   for (int64_t f = 0; f < num_frames; ++f) {
     KeyframeMeta m;
     m.ts = frames[f].timestamp_ns;
     m.vertex = frames[f].vertex_id;
     m.mission = frames[f].mission_id;
     m.frame_index = frames[f].frame_index;
-    m.first_descriptor = static_cast<int32_t>(desc_kf_.size());
+    m.first_descriptor = static_cast<int32_t>(num_desc_);
     m.num_descriptors = frames[f].num_descriptors;
-    const int32_t kf_number = static_cast<int32_t>(keyframes_.size());
     keyframes_.push_back(m);
-    desc_kf_.insert(desc_kf_.end(), m.num_descriptors, kf_number);
-    for (int i = 0; i < m.num_descriptors; ++i)
-      landmarks_.push_back(landmarks ? landmarks[at + i] : -1);
-    at += m.num_descriptors;
+    keyframe_keys_.insert(KeyframeKey{m.vertex, m.frame_index});
+    num_desc_ += m.num_descriptors;
   }
-  desc_.insert(desc_.end(), proj, proj + static_cast<size_t>(total) * d);
   index_dirty_ = true;
   return true;
 }
@@ -319,63 +503,63 @@ bool Detector::Initialize(std::string* err) {
   return EnsureIndex(err);
 }
 
-// Build the device index: cell of every descriptor = FindClosestWords(desc, 1) (kernel 2a with one
-// word), then cell-sorted block-SoA lists of this shard's descriptors.
+// Build the device index from the device-resident database: cell of every owned descriptor =
+// FindClosestWords(desc, 1) (kernel 2a with one word), then cell-sorted inverted lists; the
+// descriptor -> keyframe replica is regenerated from the keyframe headers.
 bool Detector::EnsureIndex(std::string* err) {
   if (!index_dirty_) return true;
-  const int64_t n = NumDescriptors();
+  if (!FlushPending(err)) return false;
+  const int64_t n = NumDescriptors(), no = num_own_;
   const int d = dim();
   const uint64_t cells64 = static_cast<uint64_t>(vocab_.words1.cols) * vocab_.words2.cols;
   if (cells64 > (1ull << 28)) {
     *err = "too many cells for the dense cell table";
     return false;
   }
-  float* d_desc = nullptr;
-  if (n > 0) {
-    if (!Cuda(cudaMalloc(&d_desc, static_cast<size_t>(n) * d * 4), "alloc db descriptors", err))
-      return false;
-    if (!Cuda(cudaMemcpyAsync(d_desc, desc_.data(), static_cast<size_t>(n) * d * 4,
-                              cudaMemcpyHostToDevice, stream_),
-              "H2D db descriptors", err))
-      return false;
-    if (!Cuda(d_db_cells_.Reserve(static_cast<size_t>(n) * 4), "alloc cells", err)) return false;
-    if (!CoarseChunks(d_desc, n, 1, d_db_cells_.as<int32_t>(), stream_, err)) return false;
+  const float* d_desc = d_own_desc_.as<float>();
+  const int32_t* d_gidx = d_own_gidx_.as<int32_t>();
+  if (no > 0) {
+    if (!Cuda(d_db_cells_.Reserve(static_cast<size_t>(no) * 4), "alloc cells", err)) return false;
+    if (!CoarseChunks(d_desc, no, 1, d_db_cells_.as<int32_t>(), stream_, err)) return false;
   }
   bool ok = true;
   if (s_.engine == 1) {
     // imipq: entries carry the quantised residual (12 code bytes) instead of the coordinates
     uint32_t* d_codes = nullptr;
-    if (n > 0) {
-      ok = Cuda(cudaMalloc(&d_codes, static_cast<size_t>(n) * 12), "alloc pq codes", err) &&
-           Cuda(LaunchPqEncode(pq_, d_desc, d_db_cells_.as<int32_t>(), n, d_codes, stream_), "pq encode", err);
+    if (no > 0) {
+      ok = Cuda(cudaMalloc(&d_codes, static_cast<size_t>(no) * 12), "alloc pq codes", err) &&
+           Cuda(LaunchPqEncode(pq_, d_desc, d_db_cells_.as<int32_t>(), no, d_codes, stream_), "pq encode", err);
     }
-    ok = ok && Cuda(BuildImiLists(d_db_cells_.as<int32_t>(), reinterpret_cast<const float*>(d_codes), n, 3,
-                                  static_cast<uint32_t>(cells64), s_.shard_rank, s_.shard_count, &lists_,
-                                  stream_),
+    ok = ok && Cuda(BuildImiLists(d_db_cells_.as<int32_t>(), reinterpret_cast<const float*>(d_codes), d_gidx, no,
+                                  3, static_cast<uint32_t>(cells64), &lists_, stream_),
                     "build inverted lists", err);
     if (d_codes) cudaFree(d_codes);
   } else {
-    ok = Cuda(BuildImiLists(d_db_cells_.as<int32_t>(), d_desc, n, d, static_cast<uint32_t>(cells64),
-                            s_.shard_rank, s_.shard_count, &lists_, stream_),
+    ok = Cuda(BuildImiLists(d_db_cells_.as<int32_t>(), d_desc, d_gidx, no, d, static_cast<uint32_t>(cells64),
+                            &lists_, stream_),
               "build inverted lists", err);
   }
-  if (d_desc) cudaFree(d_desc);
   if (!ok) return false;
-  // metadata replicas for voting / clustering (kernel 3)
-  if (n > 0) {
-    if (!Cuda(d_desc_kf_.Reserve(static_cast<size_t>(n) * 4), "alloc", err)) return false;
-    if (!Cuda(d_desc_lm_.Reserve(static_cast<size_t>(n) * 8), "alloc", err)) return false;
-    if (!Cuda(d_kf_meta_.Reserve(keyframes_.size() * sizeof(KeyframeMeta)), "alloc", err)) return false;
-    if (!Cuda(cudaMemcpyAsync(d_desc_kf_.p, desc_kf_.data(), static_cast<size_t>(n) * 4,
-                              cudaMemcpyHostToDevice, stream_), "H2D", err)) return false;
-    if (!Cuda(cudaMemcpyAsync(d_desc_lm_.p, landmarks_.data(), static_cast<size_t>(n) * 8,
-                              cudaMemcpyHostToDevice, stream_), "H2D", err)) return false;
-    if (!Cuda(cudaMemcpyAsync(d_kf_meta_.p, keyframes_.data(), keyframes_.size() * sizeof(KeyframeMeta),
-                              cudaMemcpyHostToDevice, stream_), "H2D", err)) return false;
-  }
-  if (!Cuda(cudaStreamSynchronize(stream_), "index build", err)) return false;
+  if (!UploadKeyframeReplicas(err)) return false;
+  (void)n;
   index_dirty_ = false;
   return true;
+}
+
+// Metadata replicas for voting / clustering (kernel 3): keyframe headers and descriptor -> keyframe.
+bool Detector::UploadKeyframeReplicas(std::string* err) {
+  const int64_t n = NumDescriptors();
+  if (n > 0) {
+    if (!Cuda(d_desc_kf_.Reserve(static_cast<size_t>(n) * 4), "alloc", err)) return false;
+    if (!Cuda(d_kf_meta_.Reserve(keyframes_.size() * sizeof(KeyframeMeta)), "alloc", err)) return false;
+    if (!Cuda(cudaMemcpyAsync(d_kf_meta_.p, keyframes_.data(), keyframes_.size() * sizeof(KeyframeMeta),
+                              cudaMemcpyHostToDevice, stream_), "H2D", err)) return false;
+    expand_desc_kf_kernel<<<static_cast<unsigned>(keyframes_.size()), 128, 0, stream_>>>(
+        d_kf_meta_.as<KeyframeMeta>(), d_desc_kf_.as<int32_t>());
+    CountLaunch();
+    if (!Cuda(cudaGetLastError(), "expand descriptor -> keyframe", err)) return false;
+  }
+  return Cuda(cudaStreamSynchronize(stream_), "index build", err);
 }
 
 bool Detector::KnnDevice(const float* d_q, int64_t n_q, int k, int32_t* d_idx, float* d_dist,
@@ -549,16 +733,28 @@ bool Detector::LastScanStats(uint64_t* bytes, uint64_t* entries, double* ms, std
 // ---------------------------------------------------------------------------------------------
 namespace {
 struct IndexFileHeader {
-  char magic[8];  // "MLCIDX01"
+  char magic[8];  // "MLCIDX02"
   uint64_t vocab_hash;
   int32_t engine, dim, shard_rank, shard_count;
   uint32_t num_cells;
   int32_t list_dim;
-  int64_t num_descriptors, num_keyframes, num_landmark_xyz;
+  int64_t num_descriptors, num_owned, num_keyframes, num_landmark_xyz;
   uint64_t list_bytes;
 };
 bool WriteAll(FILE* f, const void* p, size_t bytes) { return bytes == 0 || fwrite(p, 1, bytes, f) == bytes; }
 bool ReadAll(FILE* f, void* p, size_t bytes) { return bytes == 0 || fread(p, 1, bytes, f) == bytes; }
+
+// Every stored descriptor index of the inverted lists must address the metadata replicas.
+__global__ void validate_lists_kernel(const uint2* __restrict__ cell_info, uint32_t num_cells,
+                                      const uint32_t* __restrict__ lists, int words_per_entry, int index_word,
+                                      uint32_t num_descriptors, int* __restrict__ bad) {
+  const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= num_cells) return;
+  const uint2 ci = cell_info[c];
+  const uint32_t* e = lists + (static_cast<size_t>(ci.x) << 2);
+  for (uint32_t i = 0; i < ci.y; ++i)
+    if (e[static_cast<size_t>(i) * words_per_entry + index_word] >= num_descriptors) *bad = 1;
+}
 }  // namespace
 
 bool Detector::SaveIndex(const char* path, std::string* err) {
@@ -570,7 +766,7 @@ bool Detector::SaveIndex(const char* path, std::string* err) {
     return false;
   }
   IndexFileHeader h{};
-  std::memcpy(h.magic, "MLCIDX01", 8);
+  std::memcpy(h.magic, "MLCIDX02", 8);
   h.vocab_hash = vocab_hash_;
   h.engine = s_.engine;
   h.dim = dim();
@@ -579,13 +775,12 @@ bool Detector::SaveIndex(const char* path, std::string* err) {
   h.num_cells = lists_.num_cells;
   h.list_dim = lists_.dim;
   h.num_descriptors = NumDescriptors();
+  h.num_owned = num_own_;
   h.num_keyframes = static_cast<int64_t>(keyframes_.size());
   h.num_landmark_xyz = num_landmark_xyz_;
   h.list_bytes = lists_.list_bytes;
-  const size_t n = static_cast<size_t>(h.num_descriptors);
-  bool ok = WriteAll(f, &h, sizeof(h)) && WriteAll(f, keyframes_.data(), keyframes_.size() * sizeof(KeyframeMeta)) &&
-            WriteAll(f, desc_.data(), desc_.size() * 4) && WriteAll(f, landmarks_.data(), landmarks_.size() * 8) &&
-            WriteAll(f, desc_kf_.data(), desc_kf_.size() * 4);
+  const size_t n = static_cast<size_t>(h.num_descriptors), no = static_cast<size_t>(h.num_owned);
+  bool ok = WriteAll(f, &h, sizeof(h)) && WriteAll(f, keyframes_.data(), keyframes_.size() * sizeof(KeyframeMeta));
   // device-resident parts through a bounded staging buffer
   std::vector<unsigned char> stage(size_t{64} << 20);
   auto dump = [&](const void* dptr, size_t bytes) {
@@ -595,7 +790,10 @@ bool Detector::SaveIndex(const char* path, std::string* err) {
                 "D2H index", err) && WriteAll(f, stage.data(), c);
     }
   };
-  if (ok) dump(d_db_cells_.p, n * 4);
+  if (ok) dump(d_desc_lm_.p, n * 8);
+  if (ok) dump(d_own_gidx_.p, no * 4);
+  if (ok) dump(d_own_desc_.p, no * dim() * 4);
+  if (ok) dump(d_db_cells_.p, no * 4);
   if (ok) dump(lists_.cell_info, static_cast<size_t>(lists_.num_cells) * sizeof(uint2));
   if (ok) dump(lists_.lists, lists_.list_bytes);
   if (ok) dump(d_landmark_xyz_.p, static_cast<size_t>(num_landmark_xyz_) * 24);
@@ -611,63 +809,181 @@ bool Detector::LoadIndex(const char* path, std::string* err) {
     *err = std::string("cannot open ") + path;
     return false;
   }
+  struct Closer {
+    FILE* f;
+    ~Closer() { fclose(f); }
+  } closer{f};
   IndexFileHeader h{};
-  bool ok = ReadAll(f, &h, sizeof(h));
-  if (!ok || std::memcmp(h.magic, "MLCIDX01", 8) != 0) {
-    fclose(f);
+  if (!ReadAll(f, &h, sizeof(h)) || std::memcmp(h.magic, "MLCIDX02", 8) != 0) {
     *err = "not an index file of this library";
     return false;
   }
   const uint64_t cells64 = static_cast<uint64_t>(vocab_.words1.cols) * vocab_.words2.cols;
   if (h.vocab_hash != vocab_hash_ || h.engine != s_.engine || h.dim != dim() || h.num_cells != cells64 ||
-      h.shard_rank != s_.shard_rank || h.shard_count != s_.shard_count || h.num_descriptors < 0 ||
-      h.num_keyframes < 0 || h.num_landmark_xyz < 0) {
-    fclose(f);
+      h.shard_rank != s_.shard_rank || h.shard_count != s_.shard_count) {
     *err = "index file was built with another vocabulary / engine / sharding";
     return false;
   }
-  const size_t n = static_cast<size_t>(h.num_descriptors);
-  std::vector<KeyframeMeta> kfs(static_cast<size_t>(h.num_keyframes));
-  std::vector<float> desc(n * h.dim);
-  std::vector<int64_t> lms(n);
-  std::vector<int32_t> dkf(n);
-  ok = ReadAll(f, kfs.data(), kfs.size() * sizeof(KeyframeMeta)) && ReadAll(f, desc.data(), desc.size() * 4) &&
-       ReadAll(f, lms.data(), lms.size() * 8) && ReadAll(f, dkf.data(), dkf.size() * 4);
+  // ---- the header must describe exactly this file before anything is allocated from it ----
+  const int list_dim = s_.engine == 1 ? 3 : dim();
+  const uint64_t wpe = static_cast<uint64_t>((list_dim + 1 + 3) & ~3);
+  if (h.list_dim != list_dim || h.num_descriptors < 0 || h.num_descriptors > 2147483647LL || h.num_keyframes < 0 ||
+      h.num_keyframes > h.num_descriptors + (int64_t{1} << 24) || h.num_landmark_xyz < 0 ||
+      h.num_landmark_xyz > (int64_t{1} << 40) || h.num_owned != OwnedInRange(0, h.num_descriptors) ||
+      (h.list_bytes & 15) != 0 || h.list_bytes > (uint64_t{1} << 36)) {
+    *err = "corrupt index file header";
+    return false;
+  }
+  const uint64_t n = static_cast<uint64_t>(h.num_descriptors), no = static_cast<uint64_t>(h.num_owned);
+  const uint64_t expect = sizeof(h) + static_cast<uint64_t>(h.num_keyframes) * sizeof(KeyframeMeta) + n * 8 + no * 4 +
+                          no * h.dim * 4 + no * 4 + static_cast<uint64_t>(h.num_cells) * sizeof(uint2) + h.list_bytes +
+                          static_cast<uint64_t>(h.num_landmark_xyz) * 24;
+  if (fseek(f, 0, SEEK_END) != 0 || static_cast<uint64_t>(ftell(f)) != expect ||
+      fseek(f, static_cast<long>(sizeof(h)), SEEK_SET) != 0) {
+    *err = std::string("truncated or oversized index file ") + path;
+    return false;
+  }
+  std::vector<KeyframeMeta> kfs;
+  std::vector<uint2> cell_info;
+  std::vector<int32_t> gidx;
+  try {
+    kfs.resize(static_cast<size_t>(h.num_keyframes));
+    cell_info.resize(h.num_cells);
+    gidx.resize(no);
+  } catch (const std::exception&) {
+    *err = "out of memory reading the index file";
+    return false;
+  }
+  if (!ReadAll(f, kfs.data(), kfs.size() * sizeof(KeyframeMeta))) {
+    *err = std::string("truncated index file ") + path;
+    return false;
+  }
+  std::unordered_set<KeyframeKey, KeyframeKeyHash> keys;
+  {
+    int64_t at = 0;
+    for (const KeyframeMeta& m : kfs) {
+      if (m.num_descriptors < 0 || m.first_descriptor != at || !keys.insert(KeyframeKey{m.vertex, m.frame_index}).second) {
+        *err = "corrupt index file: keyframe table";
+        return false;
+      }
+      at += m.num_descriptors;
+    }
+    if (at != h.num_descriptors) {
+      *err = "corrupt index file: keyframe table does not cover the descriptors";
+      return false;
+    }
+  }
+  // ---- device side: everything is uploaded and checked before the current database is replaced ----
+  GrowBuf lm, own_desc, own_gidx;
+  DevBuf cells, xyz, flag;
   DeviceLists lists;
   lists.num_cells = h.num_cells;
   lists.dim = h.list_dim;
   lists.list_bytes = h.list_bytes;
-  DevBuf cells, xyz;
-  std::vector<unsigned char> stage(size_t{64} << 20);
-  auto fill = [&](void* dptr, size_t bytes) {
+  auto drop = [&]() {
+    lm.Free();
+    own_desc.Free();
+    own_gidx.Free();
+    cells.Free();
+    xyz.Free();
+    flag.Free();
+    lists.Free();
+  };
+  bool ok = true;
+  std::vector<unsigned char> stage;
+  try {
+    stage.resize(size_t{64} << 20);
+  } catch (const std::exception&) {
+    *err = "out of memory reading the index file";
+    return false;
+  }
+  auto fill = [&](void* dptr, size_t bytes, void* host_copy) {
     for (size_t at = 0; ok && at < bytes; at += stage.size()) {
       const size_t c = std::min(stage.size(), bytes - at);
       ok = ReadAll(f, stage.data(), c) &&
            Cuda(cudaMemcpy(static_cast<unsigned char*>(dptr) + at, stage.data(), c, cudaMemcpyHostToDevice),
                 "H2D index", err);
+      if (ok && host_copy) std::memcpy(static_cast<unsigned char*>(host_copy) + at, stage.data(), c);
     }
   };
-  ok = ok && Cuda(cells.Reserve(n * 4 + 16), "alloc", err) &&
+  ok = Cuda(lm.Extend(n * 8 + 16, stream_), "alloc", err) && Cuda(own_gidx.Extend(no * 4 + 16, stream_), "alloc", err) &&
+       Cuda(own_desc.Extend(no * h.dim * 4 + 16, stream_), "alloc", err) && Cuda(cells.Reserve(no * 4 + 16), "alloc", err) &&
        Cuda(cudaMalloc(&lists.cell_info, sizeof(uint2) * static_cast<size_t>(h.num_cells)), "alloc", err) &&
        Cuda(cudaMalloc(&lists.lists, h.list_bytes + 16), "alloc", err) &&
-       Cuda(xyz.Reserve(static_cast<size_t>(h.num_landmark_xyz) * 24 + 16), "alloc", err);
-  if (ok) fill(cells.p, n * 4);
-  if (ok) fill(lists.cell_info, static_cast<size_t>(h.num_cells) * sizeof(uint2));
-  if (ok) fill(lists.lists, h.list_bytes);
-  if (ok) fill(xyz.p, static_cast<size_t>(h.num_landmark_xyz) * 24);
-  fclose(f);
+       Cuda(xyz.Reserve(static_cast<size_t>(h.num_landmark_xyz) * 24 + 16), "alloc", err) &&
+       Cuda(flag.Reserve(16), "alloc", err);
+  if (ok) fill(lm.p, n * 8, nullptr);
+  if (ok) fill(own_gidx.p, no * 4, gidx.data());
+  if (ok) fill(own_desc.p, no * h.dim * 4, nullptr);
+  if (ok) fill(cells.p, no * 4, nullptr);
+  if (ok) fill(lists.cell_info, static_cast<size_t>(h.num_cells) * sizeof(uint2), cell_info.data());
+  if (ok) fill(lists.lists, h.list_bytes, nullptr);
+  if (ok) fill(xyz.p, static_cast<size_t>(h.num_landmark_xyz) * 24, nullptr);
   if (!ok) {
-    lists.Free();
-    cells.Free();
-    xyz.Free();
+    drop();
     if (err->empty()) *err = std::string("truncated index file ") + path;
     return false;
   }
-  // commit: replace the current database
+  // owned rows: ascending global indices of this shard
+  for (uint64_t j = 0; j < no; ++j) {
+    if (gidx[j] != static_cast<int64_t>(s_.shard_rank) + static_cast<int64_t>(j) * s_.shard_count) {
+      drop();
+      *err = "corrupt index file: descriptor indices";
+      return false;
+    }
+  }
+  // cell table: every list inside the list block, no more entries than owned rows
+  {
+    uint64_t entries = 0;
+    for (const uint2& ci : cell_info) {
+      entries += ci.y;
+      if ((static_cast<uint64_t>(ci.x) << 4) + static_cast<uint64_t>(ci.y) * wpe * 4 > h.list_bytes) {
+        drop();
+        *err = "corrupt index file: cell table points outside the inverted lists";
+        return false;
+      }
+    }
+    if (entries > no) {
+      drop();
+      *err = "corrupt index file: cell table holds more entries than descriptors";
+      return false;
+    }
+  }
+  if (h.num_cells > 0) {
+    int bad = 0;
+    ok = Cuda(cudaMemsetAsync(flag.p, 0, 4, stream_), "memset", err);
+    if (ok) {
+      validate_lists_kernel<<<(h.num_cells + 127) / 128, 128, 0, stream_>>>(
+          lists.cell_info, h.num_cells, lists.lists, static_cast<int>(wpe), list_dim,
+          static_cast<uint32_t>(h.num_descriptors), flag.as<int>());
+      CountLaunch();
+      ok = Cuda(cudaMemcpyAsync(&bad, flag.p, 4, cudaMemcpyDeviceToHost, stream_), "D2H", err) &&
+           Cuda(cudaStreamSynchronize(stream_), "validate index", err);
+    }
+    if (!ok || bad) {
+      drop();
+      if (err->empty()) *err = "corrupt index file: inverted lists name descriptors outside the database";
+      return false;
+    }
+  }
+  flag.Free();
+  // ---- commit: replace the current database ----
+  lm.used = n * 8;
+  own_gidx.used = no * 4;
+  own_desc.used = no * h.dim * 4;
   keyframes_.swap(kfs);
-  desc_.swap(desc);
-  landmarks_.swap(lms);
-  desc_kf_.swap(dkf);
+  keyframe_keys_.swap(keys);
+  num_desc_ = h.num_descriptors;
+  num_own_ = h.num_owned;
+  pend_desc_.clear();
+  pend_gidx_.clear();
+  pend_lm_.clear();
+  d_desc_lm_.Free();
+  d_desc_lm_ = lm;
+  d_own_desc_.Free();
+  d_own_desc_ = own_desc;
+  d_own_gidx_.Free();
+  d_own_gidx_ = own_gidx;
   lists_.Free();
   lists_ = lists;
   d_db_cells_.Free();
@@ -676,15 +992,8 @@ bool Detector::LoadIndex(const char* path, std::string* err) {
   d_landmark_xyz_ = xyz;
   num_landmark_xyz_ = h.num_landmark_xyz;
   last_valid_ = false;
-  if (n > 0) {
-    if (!Cuda(d_desc_kf_.Reserve(n * 4), "alloc", err) || !Cuda(d_desc_lm_.Reserve(n * 8), "alloc", err) ||
-        !Cuda(d_kf_meta_.Reserve(keyframes_.size() * sizeof(KeyframeMeta)), "alloc", err) ||
-        !Cuda(cudaMemcpy(d_desc_kf_.p, desc_kf_.data(), n * 4, cudaMemcpyHostToDevice), "H2D", err) ||
-        !Cuda(cudaMemcpy(d_desc_lm_.p, landmarks_.data(), n * 8, cudaMemcpyHostToDevice), "H2D", err) ||
-        !Cuda(cudaMemcpy(d_kf_meta_.p, keyframes_.data(), keyframes_.size() * sizeof(KeyframeMeta),
-                         cudaMemcpyHostToDevice), "H2D", err))
-      return false;
-  }
+  index_dirty_ = true;  // until the replicas below are in place
+  if (!UploadKeyframeReplicas(err)) return false;
   index_dirty_ = false;
   return true;
 }

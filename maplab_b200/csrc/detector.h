@@ -7,6 +7,7 @@
 #include <cstdint>
 #include <mutex>
 #include <string>
+#include <unordered_set>
 #include <vector>
 
 #include "../../include/maplab_lc_b200.h"
@@ -40,6 +41,48 @@ struct DevBuf {
   }
 };
 
+// Growing device array that keeps its contents (the database lives in HBM; the host only stages).
+struct GrowBuf {
+  void* p = nullptr;
+  size_t cap = 0;   // bytes allocated
+  size_t used = 0;  // bytes holding data
+  // Room for `extra` more bytes behind `used`; contents are preserved.
+  cudaError_t Extend(size_t extra, cudaStream_t stream) {
+    const size_t need = used + extra;
+    if (need <= cap) return cudaSuccess;
+    size_t want = need + need / 2 + 256;
+    void* np = nullptr;
+    cudaError_t e = cudaMalloc(&np, want);
+    if (e != cudaSuccess) {  // no room for the slack: try the exact size
+      want = need + 256;
+      e = cudaMalloc(&np, want);
+      if (e != cudaSuccess) return e;
+    }
+    if (used > 0) {
+      e = cudaMemcpyAsync(np, p, used, cudaMemcpyDeviceToDevice, stream);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+      if (e != cudaSuccess) {
+        cudaFree(np);
+        return e;
+      }
+    }
+    if (p) cudaFree(p);
+    p = np;
+    cap = want;
+    return cudaSuccess;
+  }
+  unsigned char* end() const { return static_cast<unsigned char*>(p) + used; }
+  void Free() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = used = 0;
+  }
+  template <typename T>
+  T* as() const {
+    return static_cast<T*>(p);
+  }
+};
+
 struct KeyframeMeta {
   int64_t ts, vertex, mission;
   int32_t frame_index, first_descriptor, num_descriptors;
@@ -53,15 +96,25 @@ class Detector {
 
   bool Clear(std::string* err);
   int64_t NumEntries() const { return static_cast<int64_t>(keyframes_.size()); }
-  int64_t NumDescriptors() const { return static_cast<int64_t>(desc_kf_.size()); }
+  int64_t NumDescriptors() const { return num_desc_; }
+  int64_t NumOwnedDescriptors() const { return num_own_ + static_cast<int64_t>(pend_gidx_.size()); }
   int NumNeighbors() const;
   int dim() const { return vocab_.target_dim; }
 
   bool Project(const uint8_t* bits, int bytes_per_desc, int64_t n, float* out, std::string* err);
   bool ProjectDevice(const uint8_t* d_bits, int bytes_per_desc, int64_t n, float* d_out,
                      cudaStream_t stream, std::string* err);
+  // proj_is_owned_rows: `proj` holds only the rows of the descriptors this shard owns (ascending
+  // global index) instead of one row per descriptor.
   bool InsertBatch(const mlc_frame* frames, int64_t num_frames, const float* proj,
-                   const int64_t* landmarks, std::string* err);
+                   const int64_t* landmarks, bool proj_is_owned_rows, std::string* err);
+  // Same with device pointers: d_proj_owned = the owned rows, d_landmarks = all rows (or null).
+  bool InsertBatchDevice(const mlc_frame* frames, int64_t num_frames, const float* d_proj_owned,
+                         int64_t num_owned, const int64_t* d_landmarks, cudaStream_t stream,
+                         std::string* err);
+  // Global descriptor indices this shard owns among [first, first + count) (descriptor i lives on
+  // shard i % shard_count): count and, if `out` is given, the indices in ascending order.
+  int64_t OwnedInRange(int64_t first, int64_t count) const;
   bool Initialize(std::string* err);
   bool Knn(const float* q, int64_t n_q, int k, int32_t* idx, float* dist, std::string* err);
   bool KnnDevice(const float* d_q, int64_t n_q, int k, int32_t* d_idx, float* d_dist,
@@ -143,6 +196,7 @@ class Detector {
   bool Cuda(cudaError_t e, const char* what, std::string* err) const;
   bool EnsureIndex(std::string* err);
   bool UploadTrees(std::string* err);
+  bool UploadKeyframeReplicas(std::string* err);
 
   mlc_settings s_{};
   VocabularyFile vocab_;
@@ -177,18 +231,37 @@ class Detector {
   cudaError_t LaunchScan(const float* d_q, int64_t n_q, const int32_t* d_cells, int nw, int k,
                          int32_t* d_idx, float* d_dist, cudaStream_t stream);
 
-  // database (host mirror of what Insert keeps, matching-based-engine.cc:227-251)
+  // database. What Insert keeps (matching-based-engine.cc:227-251) lives in HBM; the host holds the
+  // keyframe headers, the uniqueness set of Insert's CHECK (:244-252) and a bounded staging area for
+  // host-side inserts that is flushed to the device in blocks.
   std::vector<KeyframeMeta> keyframes_;
-  std::vector<float> desc_;          // n x dim
-  std::vector<int64_t> landmarks_;   // n
-  std::vector<int32_t> desc_kf_;     // n: descriptor -> keyframe number
+  struct KeyframeKey {
+    int64_t vertex;
+    int32_t frame_index;
+    bool operator==(const KeyframeKey& o) const { return vertex == o.vertex && frame_index == o.frame_index; }
+  };
+  struct KeyframeKeyHash {
+    size_t operator()(const KeyframeKey& k) const {
+      uint64_t h = static_cast<uint64_t>(k.vertex) * 0x9E3779B97F4A7C15ull + static_cast<uint32_t>(k.frame_index);
+      return static_cast<size_t>(h ^ (h >> 29));
+    }
+  };
+  std::unordered_set<KeyframeKey, KeyframeKeyHash> keyframe_keys_;
+  int64_t num_desc_ = 0;  // descriptors in the database (all shards)
+  int64_t num_own_ = 0;   // rows of this shard already on the device
+  std::vector<float> pend_desc_;      // staged owned rows (n x dim)
+  std::vector<int32_t> pend_gidx_;    // their global descriptor indices
+  std::vector<int64_t> pend_lm_;      // staged landmark numbers (all rows since the last flush)
+  bool FlushPending(std::string* err);
   bool index_dirty_ = true;
 
   // database (device)
   DeviceLists lists_;
-  DevBuf d_db_cells_;    // int32 cell per descriptor (P2)
-  DevBuf d_desc_kf_;     // int32
-  DevBuf d_desc_lm_;     // int64
+  GrowBuf d_own_desc_;   // float dim per owned descriptor, ascending global index
+  GrowBuf d_own_gidx_;   // int32 global descriptor index per owned row
+  GrowBuf d_desc_lm_;    // int64 landmark number per descriptor (all shards: replicated)
+  DevBuf d_db_cells_;    // int32 cell per owned row (P2)
+  DevBuf d_desc_kf_;     // int32 keyframe number per descriptor (replicated; rebuilt from the headers)
   DevBuf d_kf_meta_;     // KeyframeMeta
 
   // per-call scratch

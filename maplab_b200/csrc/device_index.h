@@ -51,9 +51,10 @@ struct DeviceLists {
     list_bytes = 0;
   }
 };
-cudaError_t BuildImiLists(const int32_t* d_cells, const float* d_desc, int64_t n, int dim,
-                          uint32_t num_cells, int shard_rank, int shard_count, DeviceLists* out,
-                          cudaStream_t stream);
+// d_cells / d_desc / d_gidx: one row per descriptor of THIS shard (cell, payload, global descriptor
+// index); rows with a negative cell are not indexed.
+cudaError_t BuildImiLists(const int32_t* d_cells, const float* d_desc, const int32_t* d_gidx, int64_t n,
+                          int dim, uint32_t num_cells, DeviceLists* out, cudaStream_t stream);
 cudaError_t LaunchImiScan(int dim, const float* q, int64_t n_q, const int32_t* cells, int nw,
                           const uint2* cell_info, const uint32_t* lists, int k, int32_t* out_idx,
                           float* out_dist, int sm_count, cudaStream_t stream);

@@ -322,7 +322,8 @@ bool Detector::AddSummaryMap(const void* blob, size_t size, int64_t mission_id, 
     frames[o].num_descriptors = images.num_descriptors[o];
   }
   for (int64_t& l : images.landmark_index) l += first_landmark_id;
-  if (!InsertBatch(frames.data(), observers, images.proj.data(), images.landmark_index.data(), err)) return false;
+  if (!InsertBatch(frames.data(), observers, images.proj.data(), images.landmark_index.data(), false, err))
+    return false;
   if (!SetLandmarkPositions(xyz.data(), new_n, err)) return false;
   if (sizes5) {
     sizes5[0] = landmarks;

@@ -783,16 +783,14 @@ cudaError_t LaunchMergeTopk(const int32_t* idx_lists, const float* dist_lists, i
 // =============================================================================================
 namespace {
 
-// cells of this shard's descriptors -> sort keys; descriptors of other shards get the key
-// `num_cells` (sorted to the end and ignored).
-__global__ void shard_keys_kernel(const int32_t* __restrict__ cells, int64_t n, int shard_rank,
-                                  int shard_count, uint32_t num_cells,
+// cells of this shard's rows -> sort keys; rows without a cell (a coarse word missing inside the
+// search radius) get the key `num_cells` (sorted to the end and ignored).
+__global__ void shard_keys_kernel(const int32_t* __restrict__ cells, int64_t n, uint32_t num_cells,
                                   uint32_t* __restrict__ keys, uint32_t* __restrict__ vals) {
   const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
   if (i >= n) return;
   const int32_t c = cells[i];
-  const bool mine = (i % shard_count) == shard_rank && c >= 0;
-  keys[i] = mine ? static_cast<uint32_t>(c) : num_cells;
+  keys[i] = c >= 0 ? static_cast<uint32_t>(c) : num_cells;
   vals[i] = static_cast<uint32_t>(i);
 }
 
@@ -826,7 +824,8 @@ __global__ void cell_info_kernel(uint32_t num_cells, const uint32_t* __restrict_
 __global__ void fill_lists_kernel(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals,
                                   int64_t n, uint32_t num_cells, const uint32_t* __restrict__ first,
                                   const uint2* __restrict__ info, const float* __restrict__ desc,
-                                  int dim, uint32_t* __restrict__ lists) {
+                                  const int32_t* __restrict__ gidx, int dim,
+                                  uint32_t* __restrict__ lists) {
   const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
   if (i >= n) return;
   const uint32_t c = keys[i];
@@ -835,10 +834,10 @@ __global__ void fill_lists_kernel(const uint32_t* __restrict__ keys, const uint3
   const uint2 ci = info[c];
   const int wpe = (dim + 1 + 3) & ~3;
   uint32_t* w = lists + (static_cast<size_t>(ci.x) << 2) + static_cast<size_t>(within) * wpe;
-  const uint32_t id = vals[i];
-  const float* src = desc + static_cast<size_t>(id) * dim;
+  const uint32_t row = vals[i];
+  const float* src = desc + static_cast<size_t>(row) * dim;
   for (int d = 0; d < dim; ++d) w[d] = __float_as_uint(src[d]);
-  w[dim] = id;
+  w[dim] = static_cast<uint32_t>(gidx[row]);
   for (int d = dim + 1; d < wpe; ++d) w[d] = 0u;
 }
 
@@ -850,9 +849,8 @@ __global__ void fill_lists_kernel(const uint32_t* __restrict__ keys, const uint3
     if (e__ != cudaSuccess) return e__; \
   } while (0)
 
-cudaError_t BuildImiLists(const int32_t* d_cells, const float* d_desc, int64_t n, int dim,
-                          uint32_t num_cells, int shard_rank, int shard_count, DeviceLists* out,
-                          cudaStream_t stream) {
+cudaError_t BuildImiLists(const int32_t* d_cells, const float* d_desc, const int32_t* d_gidx, int64_t n,
+                          int dim, uint32_t num_cells, DeviceLists* out, cudaStream_t stream) {
   out->Free();
   out->num_cells = num_cells;
   out->dim = dim;
@@ -898,8 +896,7 @@ cudaError_t BuildImiLists(const int32_t* d_cells, const float* d_desc, int64_t n
   MLC_TRY_C(cudaMalloc(&start16, 4 * static_cast<size_t>(num_cells)));
   const unsigned nb = static_cast<unsigned>((n + 255) / 256);
   const unsigned cb = (num_cells + 255) / 256;
-  shard_keys_kernel<<<nb, 256, 0, stream>>>(d_cells, n, shard_rank, shard_count, num_cells, keys,
-                                            vals);
+  shard_keys_kernel<<<nb, 256, 0, stream>>>(d_cells, n, num_cells, keys, vals);
   CountLaunch();
   int end_bit = 1;
   while ((1ull << end_bit) <= num_cells) ++end_bit;
@@ -931,7 +928,7 @@ cudaError_t BuildImiLists(const int32_t* d_cells, const float* d_desc, int64_t n
   out->list_bytes = (static_cast<size_t>(last_start) + last_size) * 16;
   MLC_TRY_C(cudaMalloc(&out->lists, out->list_bytes + 16));
   fill_lists_kernel<<<nb, 256, 0, stream>>>(keys_s, vals_s, n, num_cells, first, out->cell_info,
-                                            d_desc, dim, out->lists);
+                                            d_desc, d_gidx, dim, out->lists);
   CountLaunch();
   MLC_TRY_C(cudaGetLastError());
   MLC_TRY_C(cudaStreamSynchronize(stream));

@@ -298,8 +298,8 @@ void lco_engine_clear(void* h) { static_cast<LoopDetector*>(h)->Clear(); }
 void lco_engine_project(void* h, const uint8_t* raw, int bytes_per_desc, int n, float* out) {
   static_cast<LoopDetector*>(h)->ProjectDescriptors(raw, bytes_per_desc, n, out);
 }
-void lco_engine_insert(void* h, int64_t ts, int64_t vertex, int frame_index, int64_t mission,
-                       int dim, const float* proj, int n, const int64_t* landmarks) {
+int lco_engine_insert(void* h, int64_t ts, int64_t vertex, int frame_index, int64_t mission,
+                      int dim, const float* proj, int n, const int64_t* landmarks) {
   ProjectedImage im;
   im.timestamp_ns = ts;
   im.vertex_id = vertex;
@@ -308,7 +308,7 @@ void lco_engine_insert(void* h, int64_t ts, int64_t vertex, int frame_index, int
   im.dim = dim;
   im.projected_descriptors.assign(proj, proj + static_cast<size_t>(dim) * n);
   im.landmarks.assign(landmarks, landmarks + n);
-  static_cast<LoopDetector*>(h)->Insert(im);
+  return static_cast<LoopDetector*>(h)->Insert(im) ? 0 : 1;
 }
 int lco_engine_num_descriptors(void* h) { return static_cast<LoopDetector*>(h)->NumDescriptors(); }
 int lco_engine_num_entries(void* h) { return static_cast<int>(static_cast<LoopDetector*>(h)->NumEntries()); }

@@ -100,15 +100,18 @@ int LoopDetector::NumDescriptors() const {
 
 void LoopDetector::Clear() {
   keyframes_.clear();
+  keyframe_ids_.clear();
   desc_to_keyframe_.clear();
   if (imi_) imi_->Clear();
   if (imipq_) imipq_->Clear();
 }
 
 // matching-based-engine.cc:217-253
-void LoopDetector::Insert(const ProjectedImage& image) {
+bool LoopDetector::Insert(const ProjectedImage& image) {
   const int n = image.dim ? static_cast<int>(image.projected_descriptors.size() / image.dim) : 0;
   assert(static_cast<size_t>(n) == image.landmarks.size());
+  // CHECK(emplace(...).second): the keyframe id must be new (matching-based-engine.cc:244-252)
+  if (!keyframe_ids_.insert({image.vertex_id, image.frame_index}).second) return false;
   Keyframe kf;
   kf.ts = image.timestamp_ns;
   kf.vertex = image.vertex_id;
@@ -122,6 +125,7 @@ void LoopDetector::Insert(const ProjectedImage& image) {
   if (imi_) imi_->AddDescriptors(image.projected_descriptors.data(), n);
   if (imipq_) imipq_->AddDescriptors(image.projected_descriptors.data(), n);
   keyframes_.push_back(std::move(kf));
+  return true;
 }
 
 // matching-based-engine.cc:319-338

@@ -22,6 +22,7 @@
 #include <cstdint>
 #include <cstddef>
 #include <limits>
+#include <set>
 #include <string>
 #include <unordered_map>
 #include <utility>
@@ -250,7 +251,9 @@ class LoopDetector {
  public:
   LoopDetector(const EngineSettings& s, const Vocabulary& v);
   void ProjectDescriptors(const uint8_t* raw, int bytes_per_desc, int n, float* out) const;
-  void Insert(const ProjectedImage& image);
+  // false = the CHECK of matching-based-engine.cc:244-252 would abort (keyframe id already in the
+  // database); nothing is inserted then.
+  bool Insert(const ProjectedImage& image);
   void Clear();
   size_t NumEntries() const { return keyframes_.size(); }
   int NumDescriptors() const;
@@ -284,6 +287,7 @@ class LoopDetector {
   Vocabulary v_;
   FixedPointProjection fp_;
   std::vector<Keyframe> keyframes_;
+  std::set<std::pair<int64_t, int>> keyframe_ids_;  // (vertex, frame index): Insert's uniqueness CHECK
   std::vector<int> desc_to_keyframe_;  // global descriptor -> keyframe number
   InvertedMultiIndex* imi_ = nullptr;
   InvertedMultiPQIndex* imipq_ = nullptr;

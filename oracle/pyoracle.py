@@ -320,9 +320,11 @@ class Engine:
     def insert(self, ts, vertex, frame_index, mission, proj, landmarks):
         proj = _f32(proj)
         lm = np.ascontiguousarray(landmarks, np.int64)
-        lib().lco_engine_insert(self.h, C.c_int64(ts), C.c_int64(vertex), frame_index,
-                                C.c_int64(mission), self.dim, _p(proj, c_float_p), len(lm),
-                                _p(lm, c_i64_p))
+        rc = lib().lco_engine_insert(self.h, C.c_int64(ts), C.c_int64(vertex), frame_index,
+                                     C.c_int64(mission), self.dim, _p(proj, c_float_p), len(lm),
+                                     _p(lm, c_i64_p))
+        if rc != 0:
+            raise ValueError("Insert: keyframe id already in the database (matching-based-engine.cc:244-252)")
 
     def add_summary_map(self, arrays, mission_id, first_vertex_id, first_landmark_id):
         """addLocalizationSummaryMapToDatabase on deserialized arrays (Eigen shapes: descriptors

@@ -88,3 +88,70 @@ def test_load_rejects_foreign_or_damaged_files(tmp_path):
         c.load_index(tmp_path / "junk.mlc")
     with pytest.raises(capi.MlcError):
         c.load_index(tmp_path / "missing.mlc")
+
+
+def test_load_validates_what_the_header_claims(tmp_path):
+    """A file whose magic and vocabulary hash match but whose contents were damaged must be refused with
+    an error (no exception through the C boundary, no out-of-bounds device reads later) and must leave
+    the detector's database as it was."""
+    import struct
+    m, blob, _, q = small_world(num_queries=4)
+    a = capi.Detector(blob, capi.default_settings(num_nearest_neighbors=6))
+    _fill(a, m)
+    path = tmp_path / "index.mlc"
+    a.save_index(path)
+    data = bytearray(path.read_bytes())
+    hdr = struct.Struct("<8sQiiiiIiqqqqQ")
+    h = list(hdr.unpack_from(data, 0))
+    n, no, nkf, nxyz, list_bytes = h[8], h[9], h[10], h[11], h[12]
+    num_cells = h[6]
+    kf_bytes = 40 * nkf
+    off_lm = hdr.size + kf_bytes
+    off_gidx = off_lm + 8 * n
+    off_desc = off_gidx + 4 * no
+    off_cells = off_desc + 40 * no
+    off_info = off_cells + 4 * no
+    off_lists = off_info + 8 * num_cells
+    assert off_lists + list_bytes + 24 * nxyz == len(data)
+    qp = a.project(q["bits"])
+    ref = a.knn(qp, 6)
+
+    def damaged(mutate):
+        d = bytearray(data)
+        mutate(d)
+        p = tmp_path / "damaged.mlc"
+        p.write_bytes(bytes(d))
+        c = capi.Detector(blob, capi.default_settings(num_nearest_neighbors=6))
+        _fill(c, m)
+        with pytest.raises(capi.MlcError):
+            c.load_index(p)
+        got = c.knn(qp, 6)   # database untouched and still consistent
+        assert np.array_equal(got[0], ref[0]) and np.array_equal(got[1], ref[1])
+
+    def set_header(i, v):
+        def f(d):
+            hh = list(h)
+            hh[i] = v
+            hdr.pack_into(d, 0, *hh)
+        return f
+
+    damaged(set_header(8, 2**40))            # absurd descriptor count: no bad_alloc, an error
+    damaged(set_header(8, n + 1))            # sizes no longer match the file
+    damaged(set_header(10, nkf - 1))
+    damaged(set_header(7, 3))                # list_dim of the other engine
+    damaged(set_header(12, list_bytes + 16))
+    # a cell whose list would run past the list block
+    nonempty = np.frombuffer(data, "<u4", 2 * num_cells, off_info).reshape(-1, 2)
+    c0 = int(np.nonzero(nonempty[:, 1])[0][0])
+    damaged(lambda d: struct.pack_into("<I", d, off_info + 8 * c0 + 4, 2**30))
+    damaged(lambda d: struct.pack_into("<I", d, off_info + 8 * c0, 2**31))
+    # an inverted-list entry naming a descriptor outside the database
+    start16 = int(nonempty[c0, 0])
+    damaged(lambda d: struct.pack_into("<I", d, off_lists + 16 * start16 + 4 * 10, n + 5))
+    # keyframe table that does not tile the descriptors
+    damaged(lambda d: struct.pack_into("<i", d, hdr.size + 40 * 1 + 28, 3))
+    # the undamaged file still loads
+    c = capi.Detector(blob, capi.default_settings(num_nearest_neighbors=6))
+    c.load_index(path)
+    got = c.knn(qp, 6)
+    assert np.array_equal(got[0], ref[0]) and np.array_equal(got[1], ref[1])
