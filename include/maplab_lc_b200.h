@@ -320,6 +320,45 @@ int mlc_query_from_knn_device(mlc_detector* d, const mlc_frame* frames, int64_t 
                               int64_t* num_vertices, mlc_match* matches, int64_t capacity,
                               int64_t* match_offsets, int64_t* num_matches, uint8_t* inlier_flags);
 
+/* ---- Multi-GPU: the database sharded over the GPUs of one box ----------------
+ * One process per GPU, each with a detector created with shard_rank = its rank and shard_count = the
+ * number of ranks; the inverted lists are sharded (descriptor i on shard i % shard_count), vocabulary
+ * and metadata replicated. This replaces the reference's fan-out of query vertices over host threads
+ * (LoopDetectorNode::detectLoopClosuresVerticesToDatabase, LCH/src/loop-detector-node.cc:819-873;
+ * common::ParallelProcess, common/maplab-common/include/maplab-common/parallel-process.h:49-92): every
+ * rank brings ITS slice of the step's query vertices and gets the verdicts of that slice.
+ *
+ * Communicator: rank 0 calls mlc_comm_unique_id and hands the 128 bytes to the other ranks by any means
+ * (MPI_Bcast, a file, torch.distributed); then every rank calls mlc_comm_init (collective, =
+ * ncclCommInitRank over shard_count ranks). NCCL is bound at run time (libnccl.so.2). */
+#define MLC_COMM_ID_BYTES 128
+int mlc_comm_unique_id(void* id128);
+int mlc_comm_init(mlc_detector* d, const void* id128);
+int mlc_comm_destroy(mlc_detector* d);
+int mlc_comm_nccl_version(const mlc_detector* d); /* ncclGetVersion of the NCCL in use, 0 before init */
+/* queryVertexInDatabase for this rank's slice of a batch against the sharded database — COLLECTIVE:
+ * every rank calls it once per step (a rank without queries passes num_frames = 0). Arguments and
+ * results as mlc_query_batch / mlc_query_batch_device, for the slice. Per step each rank projects and
+ * coarse-searches its slice, one grouped NCCL all-gather carries (projected query, visit list) to all
+ * shards, every shard scans its lists block by block — its own slice first, while the all-gather is in
+ * flight — and each block's per-shard top-k lists leave for their owner (one grouped send/recv per
+ * block) while the next block is scanned; the owner merges the shard lists by (distance, index), which
+ * equals the single-index result, and runs voting / clustering / RANSAC on its slice. */
+int mlc_sharded_query_batch(mlc_detector* d, const mlc_frame* frames, int64_t num_frames, const uint8_t* bits,
+                            int bytes_per_desc, const double* keypoints, const mlc_camera* cams, int num_cams,
+                            const mlc_ransac_settings* rs, mlc_pose_result* results, int64_t* num_vertices,
+                            mlc_match* matches, int64_t capacity, int64_t* match_offsets, int64_t* num_matches,
+                            uint8_t* inlier_flags);
+int mlc_sharded_query_batch_device(mlc_detector* d, const mlc_frame* frames, int64_t num_frames,
+                                   const uint8_t* d_bits, int bytes_per_desc, const double* d_keypoints,
+                                   const mlc_camera* cams, int num_cams, const mlc_ransac_settings* rs,
+                                   mlc_pose_result* results, int64_t* num_vertices, mlc_match* matches,
+                                   int64_t capacity, int64_t* match_offsets, int64_t* num_matches,
+                                   uint8_t* inlier_flags);
+/* IndexInterface::GetNNearestNeighborsForFeatures of this rank's n_q query descriptors (device,
+ * n_q x dim) against the whole sharded database — COLLECTIVE like the call above. */
+int mlc_sharded_knn_device(mlc_detector* d, const float* d_q, int64_t n_q, int k, int32_t* d_idx, float* d_dist);
+
 /* Localization summary maps.
  * File format: proto2 summary_map.proto.LocalizationSummaryMap (map-structure/localization-summary-map/
  * proto/localization-summary-map/localization-summary-map.proto:4-14, common.proto.MatrixXf of

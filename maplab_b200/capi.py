@@ -17,7 +17,9 @@ EXPORTS = [
     "mlc_default_ransac_settings", "mlc_create", "mlc_destroy", "mlc_clear", "mlc_num_entries",
     "mlc_num_descriptors", "mlc_num_neighbors", "mlc_target_dim", "mlc_project",
     "mlc_project_device", "mlc_insert", "mlc_insert_batch", "mlc_insert_batch_owned",
-    "mlc_insert_batch_device", "mlc_num_owned_in_range", "mlc_initialize", "mlc_knn",
+    "mlc_insert_batch_device", "mlc_num_owned_in_range", "mlc_comm_unique_id", "mlc_comm_init",
+    "mlc_comm_destroy", "mlc_comm_nccl_version", "mlc_sharded_query_batch", "mlc_sharded_query_batch_device",
+    "mlc_sharded_knn_device", "mlc_initialize", "mlc_knn",
     "mlc_knn_device", "mlc_coarse_cells", "mlc_merge_topk_device", "mlc_last_scan_stats",
     "mlc_find_batch", "mlc_find_batch_bits", "mlc_find_from_knn_device", "mlc_pnp_ransac_batch",
     "mlc_coarse_device", "mlc_scan_device", "mlc_last_stage_ms", "mlc_set_landmark_positions", "mlc_query_batch", "mlc_query_batch_device", "mlc_query_from_knn_device",
@@ -217,6 +219,13 @@ def alignment_yaw_only(quat_xyzw):
 def alignment_enough_inliers(num_inliers, num_samples, min_inlier_count=10, min_inlier_ratio=0.2):
     return bool(lib().mlc_alignment_enough_inliers(C.c_int32(num_inliers), C.c_int64(num_samples),
                                                    C.c_int32(min_inlier_count), C.c_double(min_inlier_ratio)))
+
+
+def comm_unique_id():
+    """ncclGetUniqueId through the library (rank 0; hand the 128 bytes to the other ranks)."""
+    buf = C.create_string_buffer(128)
+    _check(lib().mlc_comm_unique_id(buf))
+    return buf.raw
 
 
 def kernel_launch_count():
@@ -520,6 +529,48 @@ class Detector:
                            want_matches=False, want_flags=False):
         return self._query(lib().mlc_query_batch_device, frames, C.c_void_p(bits_ptr), bytes_per_desc,
                            C.c_void_p(keypoints_ptr), cams, rs, want_matches, want_flags)
+
+    # -- multi-GPU (one process per GPU; see include/maplab_lc_b200.h "Multi-GPU") ------------
+    def comm_init(self, id128):
+        id128 = bytes(id128)
+        assert len(id128) == 128
+        _check(lib().mlc_comm_init(self._h, id128))
+
+    def comm_init_torch(self, group=None):
+        """Communicator over the ranks of a torch.distributed group (plumbing only: the 128-byte NCCL
+        id travels by a torch broadcast, everything after that is the library's own NCCL traffic)."""
+        import torch
+        import torch.distributed as dist
+        rank = dist.get_rank(group)
+        buf = torch.zeros(128, dtype=torch.uint8)
+        if rank == 0:
+            buf = torch.frombuffer(bytearray(comm_unique_id()), dtype=torch.uint8).clone()
+        if dist.get_backend(group) == "nccl":
+            buf = buf.cuda()
+        dist.broadcast(buf, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+        self.comm_init(buf.cpu().numpy().tobytes())
+
+    def comm_destroy(self):
+        _check(lib().mlc_comm_destroy(self._h))
+
+    def comm_nccl_version(self):
+        return int(lib().mlc_comm_nccl_version(self._h))
+
+    def sharded_query_batch(self, frames, bits, keypoints, cams, rs=None, want_matches=False, want_flags=False):
+        bits = np.ascontiguousarray(bits, np.uint8)
+        kp = np.ascontiguousarray(keypoints, np.float64).reshape(-1, 2)
+        assert len(bits) == len(kp)
+        return self._query(lib().mlc_sharded_query_batch, frames, _ptr(bits), bits.shape[1], _ptr(kp), cams, rs,
+                           want_matches, want_flags)
+
+    def sharded_query_batch_device(self, frames, bits_ptr, bytes_per_desc, keypoints_ptr, cams, rs=None,
+                                   want_matches=False, want_flags=False):
+        return self._query(lib().mlc_sharded_query_batch_device, frames, C.c_void_p(bits_ptr), bytes_per_desc,
+                           C.c_void_p(keypoints_ptr), cams, rs, want_matches, want_flags)
+
+    def sharded_knn_device(self, q_ptr, n, k, idx_ptr, dist_ptr):
+        _check(lib().mlc_sharded_knn_device(self._h, C.c_void_p(q_ptr), C.c_int64(n), k, C.c_void_p(idx_ptr),
+                                            C.c_void_p(dist_ptr)))
 
     def query_from_knn_device(self, frames, idx_ptr, dist_ptr, k, keypoints_ptr, cams, rs=None,
                               want_matches=False, want_flags=False):

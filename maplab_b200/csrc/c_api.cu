@@ -129,6 +129,61 @@ int mlc_insert_batch_device(mlc_detector* d, const mlc_frame* frames, int64_t nu
 int64_t mlc_num_owned_in_range(const mlc_detector* d, int64_t first, int64_t count) {
   return d ? d->impl.OwnedInRange(first, count) : -1;
 }
+int mlc_comm_unique_id(void* id128) {
+  MLC_REQUIRE(id128, "mlc_comm_unique_id: null argument");
+  std::string err;
+  return mlc::CommUniqueId(id128, &err) ? 0 : Fail(err);
+}
+int mlc_comm_init(mlc_detector* d, const void* id128) {
+  MLC_REQUIRE(d && id128, "mlc_comm_init: null argument");
+  std::string err;
+  return d->impl.CommInit(id128, &err) ? 0 : Fail(err);
+}
+int mlc_comm_destroy(mlc_detector* d) {
+  MLC_REQUIRE(d, "null detector");
+  d->impl.CommDestroy();
+  return 0;
+}
+int mlc_comm_nccl_version(const mlc_detector* d) { return d ? d->impl.CommVersion() : -1; }
+int mlc_sharded_knn_device(mlc_detector* d, const float* d_q, int64_t n_q, int k, int32_t* d_idx, float* d_dist) {
+  MLC_REQUIRE(d && (n_q == 0 || (d_q && d_idx && d_dist)), "mlc_sharded_knn_device: null argument");
+  std::string err;
+  return d->impl.ShardedKnnDevice(d_q, n_q, k, d_idx, d_dist, &err) ? 0 : Fail(err);
+}
+static int ShardedQuery(mlc_detector* d, const mlc_frame* frames, int64_t num_frames, const uint8_t* bits,
+                        int bytes_per_desc, const double* keypoints, bool on_device, const mlc_camera* cams,
+                        int num_cams, const mlc_ransac_settings* rs, mlc_pose_result* results,
+                        int64_t* num_vertices, mlc_match* matches, int64_t capacity, int64_t* match_offsets,
+                        int64_t* num_matches, uint8_t* inlier_flags) {
+  MLC_REQUIRE(d && num_vertices && cams && num_cams > 0 && (num_frames == 0 || (frames && results)),
+              "mlc_sharded_query_batch: null argument");
+  MLC_REQUIRE(bytes_per_desc > 0 && bytes_per_desc % 16 == 0, "bytes per descriptor must be a multiple of 16");
+  mlc_ransac_settings def;
+  mlc_default_ransac_settings(&def);
+  std::string err;
+  return d->impl.ShardedQueryBatch(frames, num_frames, bits, bytes_per_desc, keypoints, on_device, cams, num_cams,
+                                   rs ? *rs : def, results, num_vertices, matches, capacity, match_offsets,
+                                   num_matches, inlier_flags, &err)
+             ? 0
+             : Fail(err);
+}
+int mlc_sharded_query_batch(mlc_detector* d, const mlc_frame* frames, int64_t num_frames, const uint8_t* bits,
+                            int bytes_per_desc, const double* keypoints, const mlc_camera* cams, int num_cams,
+                            const mlc_ransac_settings* rs, mlc_pose_result* results, int64_t* num_vertices,
+                            mlc_match* matches, int64_t capacity, int64_t* match_offsets, int64_t* num_matches,
+                            uint8_t* inlier_flags) {
+  return ShardedQuery(d, frames, num_frames, bits, bytes_per_desc, keypoints, false, cams, num_cams, rs, results,
+                      num_vertices, matches, capacity, match_offsets, num_matches, inlier_flags);
+}
+int mlc_sharded_query_batch_device(mlc_detector* d, const mlc_frame* frames, int64_t num_frames,
+                                   const uint8_t* d_bits, int bytes_per_desc, const double* d_keypoints,
+                                   const mlc_camera* cams, int num_cams, const mlc_ransac_settings* rs,
+                                   mlc_pose_result* results, int64_t* num_vertices, mlc_match* matches,
+                                   int64_t capacity, int64_t* match_offsets, int64_t* num_matches,
+                                   uint8_t* inlier_flags) {
+  return ShardedQuery(d, frames, num_frames, d_bits, bytes_per_desc, d_keypoints, true, cams, num_cams, rs, results,
+                      num_vertices, matches, capacity, match_offsets, num_matches, inlier_flags);
+}
 int mlc_initialize(mlc_detector* d) {
   MLC_REQUIRE(d, "null detector");
   std::string err;

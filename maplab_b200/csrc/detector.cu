@@ -46,6 +46,13 @@ Detector::~Detector() {
     if (e) cudaEventDestroy(e);
   for (cudaStream_t st : ransac_stream_)
     if (st) cudaStreamDestroy(st);
+  CommDestroy();
+  for (DevBuf* b : {&sh_counts_, &sh_q_all_, &sh_cells_all_, &sh_pidx_, &sh_pdist_, &sh_ridx_, &sh_rdist_}) b->Free();
+  for (cudaEvent_t e : ev_comm_)
+    if (e) cudaEventDestroy(e);
+  for (cudaEvent_t e : ev_scan_)
+    if (e) cudaEventDestroy(e);
+  if (comm_stream_) cudaStreamDestroy(comm_stream_);
   if (copy_stream_) cudaStreamDestroy(copy_stream_);
   if (stream_) cudaStreamDestroy(stream_);
 }
@@ -53,8 +60,8 @@ Detector::~Detector() {
 bool Detector::Create(const mlc_settings& s, const void* blob, size_t size, std::string* err) {
   s_ = s;
   if (s_.shard_count <= 0) s_.shard_count = 1;
-  if (s_.shard_rank < 0 || s_.shard_rank >= s_.shard_count) {
-    *err = "shard_rank out of range";
+  if (s_.shard_rank < 0 || s_.shard_rank >= s_.shard_count || s_.shard_count > kMaxShards) {
+    *err = "shard_rank out of range (at most 16 shards)";
     return false;
   }
   if (s_.num_closest_words <= 0 || s_.num_closest_words > 16) {
@@ -578,6 +585,8 @@ bool Detector::KnnDevice(const float* d_q, int64_t n_q, int k, int32_t* d_idx, f
   if (!Cuda(LaunchScan(d_q, n_q, d_cells_.as<int32_t>(), nw, k, d_idx, d_dist, stream), "list scan", err))
     return false;
   cudaEventRecord(ev1_, stream);
+  last_cells_ = d_cells_.as<int32_t>();
+  last_scan_launches_ = 0;
   last_nq_ = n_q;
   last_nw_ = nw;
   last_valid_ = true;
@@ -656,16 +665,12 @@ bool Detector::ScanDevice(const float* d_q, const int32_t* d_cells, int64_t n_q,
   if (!EnsureIndex(err)) return false;
   if (n_q == 0) return true;
   const int nw = s_.num_closest_words;
-  // keep a copy of the visit list for mlc_last_scan_stats
-  if (!Cuda(d_cells_.Reserve(static_cast<size_t>(n_q) * nw * 4), "alloc visit list", err)) return false;
-  if (d_cells != d_cells_.as<int32_t>() &&
-      !Cuda(cudaMemcpyAsync(d_cells_.p, d_cells, static_cast<size_t>(n_q) * nw * 4, cudaMemcpyDeviceToDevice, stream),
-            "copy visit list", err))
-    return false;
   cudaEventRecord(ev0_, stream);
   if (!Cuda(LaunchScan(d_q, n_q, d_cells, nw, k, d_idx, d_dist, stream), "list scan", err))
     return false;
   cudaEventRecord(ev1_, stream);
+  last_cells_ = d_cells;  // mlc_last_scan_stats reads the caller's visit list: keep it until then
+  last_scan_launches_ = 0;
   last_nq_ = n_q;
   last_nw_ = nw;
   last_valid_ = true;
@@ -702,7 +707,7 @@ bool Detector::LastScanStats(uint64_t* bytes, uint64_t* entries, double* ms, std
   }
   if (!Cuda(d_stats_.Reserve(8), "alloc", err)) return false;
   if (!Cuda(cudaMemsetAsync(d_stats_.p, 0, 8, stream_), "memset", err)) return false;
-  if (!Cuda(LaunchScanEntries(d_cells_.as<int32_t>(), last_nq_ * last_nw_, lists_.cell_info,
+  if (!Cuda(LaunchScanEntries(last_cells_, last_nq_ * last_nw_, lists_.cell_info,
                               d_stats_.as<unsigned long long>(), stream_),
             "scan stats", err))
     return false;
@@ -710,8 +715,16 @@ bool Detector::LastScanStats(uint64_t* bytes, uint64_t* entries, double* ms, std
   if (!Cuda(cudaMemcpyAsync(&total, d_stats_.p, 8, cudaMemcpyDeviceToHost, stream_), "D2H", err)) return false;
   if (!Cuda(cudaStreamSynchronize(stream_), "scan stats", err)) return false;
   float msf = 0.f;
-  cudaEventSynchronize(ev1_);
-  if (cudaEventElapsedTime(&msf, ev0_, ev1_) != cudaSuccess) msf = 0.f;
+  if (last_scan_launches_ > 0) {  // sharded step: one launch per source rank's block
+    for (int s = 0; s < last_scan_launches_; ++s) {
+      float part = 0.f;
+      cudaEventSynchronize(ev_scan_[2 * s + 1]);
+      if (cudaEventElapsedTime(&part, ev_scan_[2 * s], ev_scan_[2 * s + 1]) == cudaSuccess) msf += part;
+    }
+  } else {
+    cudaEventSynchronize(ev1_);
+    if (cudaEventElapsedTime(&msf, ev0_, ev1_) != cudaSuccess) msf = 0.f;
+  }
   *entries = total;
   if (s_.engine == 1) {
     // algorithmic entry = index + packed codes (9 B at 10 components x 16 centres)

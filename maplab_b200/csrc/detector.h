@@ -88,6 +88,9 @@ struct KeyframeMeta {
   int32_t frame_index, first_descriptor, num_descriptors;
 };
 
+// ncclGetUniqueId through the run-time bound NCCL (sharded.cu); id128: 128 bytes.
+bool CommUniqueId(void* id128, std::string* err);
+
 class Detector {
  public:
   Detector() = default;
@@ -186,6 +189,16 @@ class Detector {
                     int64_t* num_vertices, mlc_match* matches, int64_t capacity,
                     int64_t* match_offsets, int64_t* num_matches, uint8_t* inlier_flags,
                     std::string* err);
+  // ---- multi-GPU (sharded.cu): NCCL communicator over the shard_count ranks ----
+  bool CommInit(const void* id128, std::string* err);
+  void CommDestroy();
+  int CommVersion() const;
+  bool ShardedKnnDevice(const float* d_q, int64_t n_s, int k, int32_t* d_idx, float* d_dist, std::string* err);
+  bool ShardedQueryBatch(const mlc_frame* frames, int64_t num_frames, const uint8_t* bits, int bytes_per_desc,
+                         const double* keypoints, bool inputs_on_device, const mlc_camera* cams, int num_cams,
+                         const mlc_ransac_settings& rs, mlc_pose_result* results, int64_t* num_vertices,
+                         mlc_match* matches, int64_t capacity, int64_t* match_offsets, int64_t* num_matches,
+                         uint8_t* inlier_flags, std::string* err);
   bool PnpRansacBatch(const mlc_ransac_settings& rs, const mlc_camera* cams, int num_cams,
                       int64_t num_problems, const int64_t* offsets, const double* keypoints,
                       const int32_t* camera_index, const int32_t* keypoint_index,
@@ -194,6 +207,17 @@ class Detector {
 
  private:
   bool Cuda(cudaError_t e, const char* what, std::string* err) const;
+  bool Nccl(int result, const char* what, std::string* err) const;
+  bool ShardedSliceSizes(int64_t n_s, int64_t* n_max, std::string* err);
+  bool ShardedKnnOnSlice(int64_t n_s, int64_t n_max, int k, std::string* err);
+  void* comm_ = nullptr;  // ncclComm_t
+  cudaStream_t comm_stream_ = nullptr;
+  cudaEvent_t ev_comm_[4] = {nullptr, nullptr, nullptr, nullptr};
+  static constexpr int kMaxShards = 16;
+  cudaEvent_t ev_scan_[2 * kMaxShards] = {};
+  DevBuf sh_counts_, sh_q_all_, sh_cells_all_, sh_pidx_, sh_pdist_, sh_ridx_, sh_rdist_;
+  const int32_t* last_cells_ = nullptr;  // visit list of the last scan (for mlc_last_scan_stats)
+  int last_scan_launches_ = 0;           // > 0: the scan ran as that many launches timed by ev_scan_
   bool EnsureIndex(std::string* err);
   bool UploadTrees(std::string* err);
   bool UploadKeyframeReplicas(std::string* err);
