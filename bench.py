@@ -45,6 +45,10 @@ def parse_args():
     ap.add_argument("--no-scan-probe", action="store_true",
                     help="skip the extra scan-roofline measurement at the north-star shard size (N = 1 only)")
     ap.add_argument("--probe-landmarks", type=int, default=6_250_000)
+    ap.add_argument("--no-extras", action="store_true",
+                    help="skip the extra configurations (10M / 50M-landmark maps, 100M-descriptor kNN microbench)")
+    ap.add_argument("--max-extra-landmarks", type=int, default=50_000_000)
+    ap.add_argument("--knn-db", type=int, default=100_000_000)
     ap.add_argument("--engine", default="imi", choices=["imi", "imipq"],
                     help="--lc_detector_engine: imipq = product-quantised residuals (10 components x 16 centres)")
     return ap.parse_args()
@@ -192,45 +196,263 @@ def projection_probe(det, m, dev, hbm_peak):
     return out
 
 
-def scan_probe(args, local, hbm_peak):
-    """IMI list scan at the north-star shard size (the per-GPU shard of the 50M-landmark map over 8
-    GPUs: 6.25M landmarks, 25M descriptors, 25 entries per cell on average): same fused step, its
-    scan kernel timed with CUDA events inside the step."""
+def _dist_helpers(world, dev):
+    import torch
+    import torch.distributed as dist
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def reduce(x, op):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=op)
+        return float(t.item())
+
+    return (barrier, lambda x: reduce(x, dist.ReduceOp.MAX), lambda x: reduce(x, dist.ReduceOp.SUM))
+
+
+def hash_world_run(landmarks, total_queries, rank, world, local, args, steps, warmup, hbm_peak, sampler=None):
+    """One configuration on the counter-based world (maplab_b200/synthetic_gpu.py): shard-aware database
+    build on the device (every rank generates, projects and inserts only the descriptors its shard owns),
+    this rank's contiguous slice of the query keyframes, W + K steps of the query path through the C-ABI
+    (mlc_query_batch_device at N = 1, the collective mlc_sharded_query_batch_device at N > 1), then the
+    same through host buffers. Returns the measurements (identical dict on every rank where it matters)."""
+    import hashlib
+    import torch
+    import torch.distributed as dist
+    from maplab_b200 import capi, synthetic, synthetic_gpu as sg
+
+    dev = torch.device("cuda", local)
+    barrier, max_over_ranks, sum_over_ranks = _dist_helpers(world, dev)
+    t0 = time.time()
+    blob, _ = synthetic.make_vocabulary(sg.vocabulary_sample(landmarks, 100_000, dev), num_words=args.words, seed=7)
+    det = capi.Detector(blob, capi.default_settings(device=local, shard_rank=rank, shard_count=world))
+    if world > 1:
+        det.comm_init_torch()
+    t1 = time.time()
+    info = sg.build_database(det, landmarks, rank, world, dev)
+    xyz = sg.all_landmark_xyz(landmarks, dev)
+    det.set_landmark_positions_device(xyz.data_ptr(), landmarks)
+    del xyz
+    torch.cuda.synchronize()
+    t_generate = time.time() - t1
+    t1 = time.time()
+    det.initialize()
+    t_index = time.time() - t1
+    n_db, n_kf = info["num_descriptors"], info["num_keyframes"]
+    k = det.num_neighbors()
+    if total_queries % world:
+        raise ValueError("the query batch must divide evenly over the GPUs")
+    per = total_queries // world
+    q = sg.make_queries(landmarks, rank * per, (rank + 1) * per, dev)
+    qframes = q["frames"]
+    bits_d, kp_d = q["bits"].contiguous(), q["keypoints"].contiguous()
+    bits_h, kp_h = bits_d.cpu().pin_memory(), kp_d.cpu().pin_memory()
+    bits_np, kp_np = bits_h.numpy(), kp_h.numpy()
+    cams = capi.make_cameras([synthetic.camera_dict()])
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+    torch.cuda.empty_cache()
+
+    if world > 1:
+        def step_device():
+            return det.sharded_query_batch_device(qframes, bits_d.data_ptr(), 64, kp_d.data_ptr(), cams)
+
+        def step_e2e():
+            return det.sharded_query_batch(qframes, bits_np, kp_np, cams)
+    else:
+        def step_device():
+            return det.query_batch_device(qframes, bits_d.data_ptr(), 64, kp_d.data_ptr(), cams)
+
+        def step_e2e():
+            return det.query_batch(qframes, bits_np, kp_np, cams)
+
+    for _ in range(warmup):
+        out = step_device()
+    barrier()
+    first = out["results"].tobytes()
+    res = out["results"]
+    acc = res["accepted"].astype(bool)
+    T = res["T_G_I"].reshape(-1, 3, 4)
+    pos_err = float(np.abs(T[acc][:, :, 3] - q["T_G_I"][acc][:, :, 3]).max(initial=0.0))
+    # size-independent properties: determinism, and one checksum over the verdicts of ALL query keyframes in
+    # batch order — the same world gives the same checksum for every GPU count (sharded == single index)
+    deterministic = step_device()["results"].tobytes() == first
+    if world > 1:
+        parts = [None] * world
+        dist.all_gather_object(parts, first)
+    else:
+        parts = [first]
+    checksum = hashlib.sha256(b"".join(parts)).hexdigest()[:16]
+    accepted = int(sum_over_ranks(float(acc.sum())))
+    matches = int(sum_over_ranks(float(out["num_matches"])))
+    max_pos_err = max_over_ranks(pos_err)
+    deterministic = bool(sum_over_ranks(0.0 if deterministic else 1.0) == 0.0)
+
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    stage_acc = np.zeros(5)
+    scan_ms_acc, scan_bytes = 0.0, 0
+    if sampler is not None:
+        sampler.start()
+    launches0 = capi.kernel_launch_count()
+    barrier()
+    for i in range(steps):
+        flush.fill_(i & 0xFF)  # evict L2 between timed iterations
+        barrier()
+        ev[i][0].record()
+        step_device()          # ends with the D2H of the verdicts (stream synchronised)
+        ev[i][1].record()
+        at = capi.kernel_launch_count()
+        stage_acc += np.array(list(det.last_stage_ms().values()))
+        st = det.last_scan_stats()  # CUDA events around the scan launches of this step (+1 counting launch)
+        scan_ms_acc += st["scan_ms"]
+        scan_bytes = st["algorithmic_bytes"]
+        launches0 += capi.kernel_launch_count() - at  # the counting kernel is not part of the step
+    barrier()
+    launches = capi.kernel_launch_count() - launches0
+    clocks = sampler.stop() if sampler is not None else None
+    dev_ms = float(np.sum([a.elapsed_time(b) for a, b in ev]))
+    ms_per_step = max_over_ranks(dev_ms) / max(steps, 1)
+    for _ in range(2):
+        step_e2e()
+    e2e_ms = 0.0
+    for i in range(steps):
+        barrier()
+        ev[i][0].record()
+        step_e2e()
+        ev[i][1].record()
+        torch.cuda.synchronize()
+        e2e_ms += ev[i][0].elapsed_time(ev[i][1])
+    e2e_ms_per_step = max_over_ranks(e2e_ms) / max(steps, 1)
+    scan_ms = max_over_ranks(scan_ms_acc / max(steps, 1))
+    scan_bytes_mean = sum_over_ranks(float(scan_bytes)) / world
+    achieved = scan_bytes_mean / (scan_ms * 1e-3) / 1e9 if scan_ms > 0 else 0.0
+    stage = max_stage = None
+    stage = dict(zip(("project", "coarse", "scan_and_exchange" if world > 1 else "scan", "vote_cluster", "ransac"),
+                     [round(max_over_ranks(float(x) / max(steps, 1)), 4) for x in stage_acc]))
+    nccl = det.comm_nccl_version() if world > 1 else 0
+    if world > 1:
+        det.comm_destroy()
+    det.close()
+    del flush, bits_d, kp_d
+    torch.cuda.empty_cache()
+    return {
+        "value": total_queries / (ms_per_step * 1e-3), "ms_per_step": ms_per_step,
+        "e2e_value": total_queries / (e2e_ms_per_step * 1e-3),
+        "h2d_bytes_per_step": int(bits_h.numel() + kp_h.numel() * 8) * world,
+        "d2h_bytes_per_step": int(total_queries * capi.POSE_DTYPE.itemsize),
+        "workload": workload_string(landmarks, total_queries, args.words, n_db, n_kf, k),
+        "roofline": {"kernel": "imi_scan_kernel", "bound": "hbm", "achieved": achieved, "peak": hbm_peak,
+                     "unit": "GB/s", "frac": achieved / hbm_peak, "algorithmic_bytes_per_launch": scan_bytes_mean,
+                     "launch_ms": scan_ms, "launches_per_step": world, "per": "GPU (mean bytes / max time over ranks)",
+                     "entries_per_visited_cell_per_shard": round(n_db / world / (args.words * args.words), 2),
+                     "traffic": None},
+        "stage_ms_max_over_ranks": stage, "gpu_launches_rank0": int(launches), "clocks": clocks,
+        "db": {"descriptors": n_db, "keyframes": n_kf, "per_gpu_descriptors": n_db // world,
+               "generate_project_insert_s": round(t_generate, 2), "index_build_s": round(t_index, 2),
+               "vocabulary_and_setup_s": round(t1 - t0 - t_generate, 2)},
+        "checks": {"accepted_loop_closures": accepted, "query_keyframes": total_queries, "matches": matches,
+                   "max_position_error_vs_ground_truth_m": max_pos_err, "deterministic": deterministic,
+                   "verdict_checksum": checksum,
+                   "note": "verdict_checksum = sha256 over the pose results of all query keyframes in batch "
+                           "order; the world is a pure function of its size, so the same configuration must "
+                           "give the same checksum at every GPU count (sharded == single index)"},
+        "nccl_version": nccl,
+    }
+
+
+def knn_microbench(rank, world, local, args, hbm_peak, db_total=100_000_000, queries_total=1_000_000, k=10):
+    """BASELINE config 5: IMI kNN over `db_total` projected descriptors (sharded over the GPUs), 1 M query
+    descriptors, k = 10, nw = 10, W = 1000 x 1000 cells. Database and queries are vocabulary-conditioned
+    (a random word pair + Gaussian residual) — the near-uniform ~100 entries per cell SURVEY 8d assumes."""
     import torch
     from maplab_b200 import capi, synthetic
-    lm = args.probe_landmarks
-    m, blob, q = build_world(lm, args.queries, args.words)
-    det = capi.Detector(blob, capi.default_settings(device=local))
-    frames, _, _ = load_database(det, m)
-    n_db = len(m["bits"])
-    k = det.num_neighbors()
-    cams = capi.make_cameras([synthetic.camera_dict()])
-    qframes = frames_array(q["frames"])
     dev = torch.device("cuda", local)
-    qbits_d = torch.from_numpy(q["bits"]).to(dev)
-    kp_d = torch.from_numpy(np.ascontiguousarray(q["keypoints"], np.float64)).to(dev)
+    barrier, max_over_ranks, sum_over_ranks = _dist_helpers(world, dev)
+    rng = np.random.default_rng(1)
+    W1 = (rng.standard_normal((5, 1000)) * 3.0).astype(np.float32)
+    W2 = (rng.standard_normal((5, 1000)) * 3.0).astype(np.float32)
+    blob = synthetic.serialize_vocabulary(np.zeros((10, 512), np.float32), W1, W2, 10)
+    det = capi.Detector(blob, capi.default_settings(device=local, shard_rank=rank, shard_count=world,
+                                                    num_nearest_neighbors=k))
+    if world > 1:
+        det.comm_init_torch()
+    w1_d, w2_d = torch.from_numpy(W1.T.copy()).to(dev), torch.from_numpy(W2.T.copy()).to(dev)
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(1000 + rank)
+
+    def conditioned(n):
+        i1 = torch.randint(0, 1000, (n,), device=dev, generator=gen)
+        i2 = torch.randint(0, 1000, (n,), device=dev, generator=gen)
+        x = torch.cat([w1_d[i1], w2_d[i2]], 1)
+        return (x + 0.15 * torch.randn((n, 10), device=dev, generator=gen)).contiguous()
+
+    t0 = time.time()
+    per_kf, chunk_kf = 500, 8192 * world
+    nkf = db_total // per_kf
+    stream = torch.cuda.current_stream().cuda_stream
+    for kf0 in range(0, nkf, chunk_kf):
+        kf1 = min(nkf, kf0 + chunk_kf)
+        ids = np.arange(kf0, kf1, dtype=np.int64)
+        frames = capi.make_frames(ids * 10**9, ids, np.zeros(len(ids), np.int64), np.zeros(len(ids), np.int32),
+                                  np.full(len(ids), per_kf, np.int32))
+        owned = det.num_owned_in_range(kf0 * per_kf, (kf1 - kf0) * per_kf)
+        rows = conditioned(owned)
+        det.insert_batch_device(frames, rows.data_ptr(), owned, 0, stream)
+    det.initialize()
+    t_build = time.time() - t0
+    n_db = nkf * per_kf
+    nq = queries_total // world
+    q_d = conditioned(nq)
+    idx = torch.empty((nq, k), dtype=torch.int32, device=dev)
+    dst = torch.empty((nq, k), dtype=torch.float32, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    ms, nbytes = [], 0
-    for i in range(3 + 5):
-        flush.fill_(i & 0xFF)
+    W, K = 2, 4
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    tot_ms, scan_ms, st = 0.0, 0.0, None
+    for i in range(W + K):
+        flush.fill_(i)
+        barrier()
+        ev0.record()
+        if world > 1:
+            det.sharded_knn_device(q_d.data_ptr(), nq, k, idx.data_ptr(), dst.data_ptr())
+        else:
+            det.knn_device(q_d.data_ptr(), nq, k, idx.data_ptr(), dst.data_ptr(), stream)
+        ev1.record()
         torch.cuda.synchronize()
-        det.query_batch_device(qframes, qbits_d.data_ptr(), 64, kp_d.data_ptr(), cams)
         st = det.last_scan_stats()
-        if i >= 3:
-            ms.append(st["scan_ms"])
-            nbytes = st["algorithmic_bytes"]
-    launch_ms = float(np.mean(ms))
-    achieved = nbytes / (launch_ms * 1e-3) / 1e9
-    return {"kernel": "imi_scan_kernel", "workload": workload_string(lm, args.queries, args.words, n_db, len(frames), k),
-            "why": "per-GPU shard of BASELINE config 'multi-robot synthetic map, 50M landmarks sharded across 8 B200'",
-            "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-            "algorithmic_bytes_per_launch": float(nbytes), "launch_ms": launch_ms, "steps": 5, "warmup": 3}
+        if i >= W:
+            tot_ms += ev0.elapsed_time(ev1)
+            scan_ms += st["scan_ms"]
+    ms = max_over_ranks(tot_ms / K)
+    scan = max_over_ranks(scan_ms / K)
+    nbytes = sum_over_ranks(float(st["algorithmic_bytes"])) / world
+    found = sum_over_ranks(float((idx[:, k - 1] >= 0).float().mean().item())) / world
+    if world > 1:
+        det.comm_destroy()
+    det.close()
+    del flush, idx, dst, q_d
+    torch.cuda.empty_cache()
+    achieved = nbytes / (scan * 1e-3) / 1e9
+    return {"workload": f"IMI kNN microbench (BASELINE config 5): {n_db} database descriptors sharded over {world} "
+                        f"B200 ({n_db // world} per GPU), {nq * world} query descriptors per step, k={k}, nw=10, "
+                        f"W=1000x1000 cells, vocabulary-conditioned data",
+            "value": nq * world / (ms * 1e-3), "unit": "query descriptors/s (coarse search + scan"
+            + (" + exchange + merge" if world > 1 else "") + ")", "ms_per_step": ms, "steps": K, "warmup": W,
+            "roofline": {"kernel": "imi_scan_kernel", "bound": "hbm", "achieved": achieved, "peak": hbm_peak,
+                         "unit": "GB/s", "frac": achieved / hbm_peak, "algorithmic_bytes_per_launch": nbytes,
+                         "launch_ms": scan, "launches_per_step": world,
+                         "per": "GPU (mean bytes / max time over ranks)"},
+            "entries_per_query_per_gpu": st["entries"] / (nq * world),
+            "queries_with_k_neighbours": found, "generate_insert_build_s": round(t_build, 1)}
 
 
 def run_b200(args):
     import torch
     import torch.distributed as dist
-    from maplab_b200 import capi, sharded, synthetic
+    from maplab_b200 import capi, synthetic
 
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
@@ -241,17 +463,73 @@ def run_b200(args):
         dist.init_process_group("nccl", device_id=dev)
     hbm_peak, peak_src = peaks()
     t_setup = time.time()
-    # weak scaling: per-GPU work is fixed — the map (hence every GPU's shard of the inverted lists) and
-    # the query batch of a step both grow with the GPU count (every rank owns --queries keyframes)
-    landmarks = args.landmarks * (world if args.scaling == "weak" else 1)
-    queries = args.queries * (world if args.scaling == "weak" else 1)
-    m, blob, q = build_world(landmarks, queries, args.words, args.engine)
-    det = capi.Detector(blob, capi.default_settings(device=local, shard_rank=rank, shard_count=world,
-                                                    engine=1 if args.engine == "imipq" else 0))
+    W = max(args.warmup, 3)
+    extras = {}
+
+    def run_extras():
+        """The configurations north_star names beside the headline one (BASELINE.json configs 3-5), each the
+        same fixed workload at every GPU count — map size sweep at a 1 000-keyframe batch + the kNN microbench."""
+        if args.no_extras:
+            return
+        for tag, lm in (("north_star_10m", 10_000_000), ("north_star_50m", 50_000_000)):
+            if lm > args.max_extra_landmarks:
+                continue
+            t0 = time.time()
+            r = hash_world_run(lm, 1000, rank, world, local, args, max(args.steps // 2, 3), 3, hbm_peak)
+            r["config"] = ("BASELINE config 3 (10M landmarks, 1k query keyframes)" if lm == 10_000_000 else
+                           "BASELINE config 4 / north-star target (50M landmarks, 1k query keyframes)")
+            r["unit"], r["n_gpus"], r["wall_s"] = UNIT, world, round(time.time() - t0, 1)
+            extras[tag] = r
+        t0 = time.time()
+        r = knn_microbench(rank, world, local, args, hbm_peak, db_total=args.knn_db)
+        r["n_gpus"], r["wall_s"] = world, round(time.time() - t0, 1)
+        extras["knn_100m"] = r
+
+    if world > 1:
+        # ---- N > 1 headline line: weak scaling, per-GPU work fixed (map AND batch grow with N) ----
+        landmarks = args.landmarks * (world if args.scaling == "weak" else 1)
+        queries = args.queries * (world if args.scaling == "weak" else 1)
+        sampler = ClockSampler(local) if rank == 0 else None
+        r = hash_world_run(landmarks, queries, rank, world, local, args, args.steps, W, hbm_peak, sampler)
+        run_extras()
+        if rank == 0:
+            roof = dict(r["roofline"], peak_source=peak_src)
+            out = {
+                "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": W, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": args.scaling,
+                "vs_baseline": None, "dtype": "u8 x s8 -> s32 (projection), f32 (distances), f64 (RANSAC)",
+                "data": "synthetic",
+                "config": {"workload": r["workload"],
+                           "sharding": (f"inverted lists: descriptor i on rank i % {world}, every rank builds only "
+                                        f"its shard; {args.scaling} scaling: map = {landmarks} landmarks, query "
+                                        f"batch = {queries} keyframes per step ("
+                                        + (f"{args.landmarks} landmarks and {args.queries} query keyframes per GPU"
+                                           if args.scaling == "weak" else "totals fixed") + "); the step is one "
+                                        "collective call through the C-ABI (mlc_sharded_query_batch_device), NCCL "
+                                        f"{r['nccl_version']} inside the library"),
+                           "generator": "counter-based world (maplab_b200/synthetic_gpu.py), same model as the "
+                                        "N = 1 world, generated shard by shard on the GPUs",
+                           "l2": "256 MiB flush buffer written between timed iterations",
+                           "db": r["db"], "accepted_loop_closures_per_step": r["checks"]["accepted_loop_closures"],
+                           "matches_per_step": r["checks"]["matches"]},
+                "roofline": roof,
+                "e2e": {"value": r["e2e_value"], "unit": UNIT, "h2d_bytes_per_step": r["h2d_bytes_per_step"],
+                        "d2h_bytes_per_step": r["d2h_bytes_per_step"]},
+                "gpu_launches": r["gpu_launches_rank0"] * world, "clocks": r["clocks"],
+                "stage_ms": r["stage_ms_max_over_ranks"], "checks": r["checks"],
+                "setup_s": round(time.time() - t_setup, 1),
+            }
+            out.update(extras)
+            print(json.dumps(out), flush=True)
+        dist.destroy_process_group()
+        return
+
+    # ---- N = 1 headline line: BASELINE config 2 on the numpy world (the one the oracle diffs) ----
+    m, blob, q = build_world(args.landmarks, args.queries, args.words, args.engine)
+    det = capi.Detector(blob, capi.default_settings(device=local, engine=1 if args.engine == "imipq" else 0))
     frames, proj, t_build = load_database(det, m)
     n_db = len(m["bits"])
     k = det.num_neighbors()
-    nw = 10
     cams = capi.make_cameras([synthetic.camera_dict()])
     qframes = frames_array(q["frames"])
     nq_kf = len(qframes)
@@ -261,132 +539,83 @@ def run_b200(args):
     kp_h = torch.from_numpy(kp_np).pin_memory()
     qbits_d, kp_d = qbits_h.to(dev), kp_h.to(dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+    h2d_bytes = int(q["bits"].nbytes + kp_np.nbytes)
+    d2h_bytes = int(nq_kf * capi.POSE_DTYPE.itemsize)
 
-    if world > 1:
-        ops = sharded.DetectorOps(det, cams)
-        step = sharded.ShardedQueryStep(ops, qframes, rank, world, det.dim, nw, k, 64, dev)
-        sbits_d, skp_d = step.slice_of(qbits_d), step.slice_of(kp_d)
-        sbits_e, skp_e = torch.empty_like(sbits_d), torch.empty_like(skp_d)
-        sbits_h, skp_h = step.slice_of(qbits_h), step.slice_of(kp_h)
-        h2d_bytes = int(sbits_h.numel() + skp_h.numel() * 8) * world
-        d2h_bytes = int(nq_kf * capi.POSE_DTYPE.itemsize)
+    def step_device():
+        return det.query_batch_device(qframes, qbits_d.data_ptr(), 64, kp_d.data_ptr(), cams)
 
-        def step_device():
-            return step.run(sbits_d, skp_d)
+    qbits_pinned, kp_pinned = qbits_h.numpy(), kp_h.numpy()  # views of the pinned buffers
 
-        def step_e2e():
-            sbits_e.copy_(sbits_h, non_blocking=True)
-            skp_e.copy_(skp_h, non_blocking=True)
-            return step.run(sbits_e, skp_e)
-    else:
-        h2d_bytes = int(q["bits"].nbytes + kp_np.nbytes)
-        d2h_bytes = int(nq_kf * capi.POSE_DTYPE.itemsize)
+    def step_e2e():
+        return det.query_batch(qframes, qbits_pinned, kp_pinned, cams)
 
-        def step_device():
-            return det.query_batch_device(qframes, qbits_d.data_ptr(), 64, kp_d.data_ptr(), cams)
-
-        qbits_pinned, kp_pinned = qbits_h.numpy(), kp_h.numpy()  # views of the pinned buffers
-
-        def step_e2e():
-            return det.query_batch(qframes, qbits_pinned, kp_pinned, cams)
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def max_over_ranks(x):
-        t = torch.tensor([x], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
-    def sum_over_ranks(x):
-        t = torch.tensor([x], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        return float(t.item())
-
-    W = max(args.warmup, 3)
     for _ in range(W):
-        out = step_device()
-    barrier()
-    accepted = int(sum_over_ranks(float(out["results"]["accepted"].sum())))
-    num_matches = int(sum_over_ranks(float(out["num_matches"])))
-    step_out = out
+        step_out = step_device()
+    torch.cuda.synchronize()
+    accepted = int(step_out["results"]["accepted"].sum())
+    num_matches = int(step_out["num_matches"])
 
     # ---- timed: device-resident ----
     sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
+    sampler.start()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     stage_acc = np.zeros(5)
     scan_ms_acc, scan_bytes = 0.0, 0
     launches0 = capi.kernel_launch_count()
-    barrier()
+    torch.cuda.synchronize()
     wall0 = time.perf_counter()
     for i in range(args.steps):
         flush.fill_(i & 0xFF)  # evict L2 between timed iterations
-        barrier()
+        torch.cuda.synchronize()
         ev[i][0].record()
         step_device()          # ends with the D2H of the verdicts (stream synchronised)
         ev[i][1].record()
         launches_step = capi.kernel_launch_count()
-        if world == 1:
-            stage_acc += np.array(list(det.last_stage_ms().values()))
+        stage_acc += np.array(list(det.last_stage_ms().values()))
         st = det.last_scan_stats()  # CUDA events around the scan launch of this step (+1 counting launch)
         scan_ms_acc += st["scan_ms"]
         scan_bytes = st["algorithmic_bytes"]
         launches0 += capi.kernel_launch_count() - launches_step  # the counting kernel is not part of the step
-    barrier()
+    torch.cuda.synchronize()
     wall = time.perf_counter() - wall0
     launches = capi.kernel_launch_count() - launches0
-    clocks = sampler.stop() if rank == 0 else None
-    dev_ms = float(np.sum([a.elapsed_time(b) for a, b in ev]))
-    ms_per_step = max_over_ranks(dev_ms) / max(args.steps, 1)
+    clocks = sampler.stop()
+    ms_per_step = float(np.sum([a.elapsed_time(b) for a, b in ev])) / max(args.steps, 1)
 
     # ---- timed: end to end with host buffers (pinned H2D of the step's inputs, D2H of the verdicts) ----
     for _ in range(2):
         step_e2e()
     e2e_ms = 0.0
     for i in range(args.steps):
-        barrier()
+        torch.cuda.synchronize()
         ev[i][0].record()
         step_e2e()
         ev[i][1].record()
         torch.cuda.synchronize()
         e2e_ms += ev[i][0].elapsed_time(ev[i][1])
-    e2e_s_per_step = max_over_ranks(e2e_ms) * 1e-3 / max(args.steps, 1)
+    e2e_s_per_step = e2e_ms * 1e-3 / max(args.steps, 1)
 
     # ---- roofline of the IMI list scan: CUDA-event time of the launch inside the timed steps ----
     scan_ms = scan_ms_acc / max(args.steps, 1)
-    scan_ms_max = max_over_ranks(scan_ms)
-    scan_bytes_mean = sum_over_ranks(float(scan_bytes)) / world
-    achieved = scan_bytes_mean / (scan_ms_max * 1e-3) / 1e9 if scan_ms_max > 0 else 0.0
-
-    if rank != 0:
-        dist.destroy_process_group()
-        return
+    achieved = scan_bytes / (scan_ms * 1e-3) / 1e9 if scan_ms > 0 else 0.0
     out = {
         "metric": METRIC, "value": nq_kf / (ms_per_step * 1e-3), "unit": UNIT,
-        "n_gpus": world, "steps": args.steps, "warmup": W, "ms_per_step": ms_per_step,
+        "n_gpus": 1, "steps": args.steps, "warmup": W, "ms_per_step": ms_per_step,
         "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
         "dtype": "u8 x s8 -> s32 (projection), f32 (distances), f64 (RANSAC)", "data": "synthetic",
-        "config": {"workload": workload_string(landmarks, queries, args.words, n_db, len(frames), k),
-                   "sharding": (f"inverted lists: descriptor i on rank i % {world}; {args.scaling} scaling: map = "
-                                f"{landmarks} landmarks, query batch = {queries} keyframes per step ("
-                                + (f"{args.landmarks} landmarks and {args.queries} query keyframes per GPU"
-                                   if args.scaling == "weak" else "totals fixed") + ")") if world > 1 else "none",
+        "config": {"workload": workload_string(args.landmarks, args.queries, args.words, n_db, len(frames), k),
+                   "sharding": "none",
                    "l2": "256 MiB flush buffer written between timed iterations",
                    "db_build_s": round(t_build, 3),
                    "accepted_loop_closures_per_step": accepted, "matches_per_step": num_matches},
         "roofline": {"kernel": "imi_scan_kernel" if args.engine == "imi" else "imipq_scan_kernel", "bound": "hbm", "achieved": achieved,
                      "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                      "peak_source": peak_src,
-                     "algorithmic_bytes_per_launch": scan_bytes_mean,
-                     "launch_ms": scan_ms_max, "launches_per_step": 1,
-                     "per": "GPU", "traffic": measured_traffic(n_db, n_q) if world == 1 else None,
-                     "attainable_note": "lists average ~5 entries (240 B) per cell at this map size: "
+                     "algorithmic_bytes_per_launch": float(scan_bytes),
+                     "launch_ms": scan_ms, "launches_per_step": 1,
+                     "per": "GPU", "traffic": measured_traffic(n_db, n_q),
+                     "attainable_note": "lists average ~4 entries (~190 B) per cell at this map size: "
                                         "profiles/microbench/chunk_read_b200.txt measures 4.0-4.4 TB/s as "
                                         "the B200 ceiling for random 240-byte chunks (6.2 TB/s at 1.5 KB)"},
         "e2e": {"value": nq_kf / e2e_s_per_step, "unit": UNIT,
@@ -395,22 +624,24 @@ def run_b200(args):
         "clocks": clocks,
         "setup_s": round(time.time() - t_setup, 1), "timed_wall_s": round(wall, 3),
     }
-    if world == 1:
-        out["stage_ms"] = dict(zip(("project", "coarse", "scan", "vote_cluster", "ransac"),
-                                   [round(float(x) / max(args.steps, 1), 4) for x in stage_acc]))
-    if not args.no_cpu_baseline and world == 1:  # the CPU path is timed beside the N = 1 run only
+    out["stage_ms"] = dict(zip(("project", "coarse", "scan", "vote_cluster", "ransac"),
+                               [round(float(x) / max(args.steps, 1), 4) for x in stage_acc]))
+    if not args.no_cpu_baseline:  # the CPU path is timed beside the N = 1 run only
         out["cpu_baseline"], oracle_result = cpu_baseline(args, m, blob, q, proj, frames)
         out["parity_checked"] = parity_check(step_out, oracle_result)
     if args.engine != "imi":
         out["config"]["engine"] = args.engine
-    if world == 1 and not args.no_scan_probe and args.engine == "imi":
+    if not args.no_scan_probe and args.engine == "imi":
         out["projection"] = projection_probe(det, m, dev, hbm_peak)
-        del det, m, q, proj, qbits_d, kp_d, flush
-        torch.cuda.empty_cache()
-        out["roofline_at_shard_scale"] = scan_probe(args, local, hbm_peak)
+    del det, m, q, proj, qbits_d, kp_d, flush
+    torch.cuda.empty_cache()
+    if args.engine == "imi":
+        run_extras()
+        out.update(extras)
+        if "north_star_50m" in extras:  # the scan at the north-star map size, measured (was a 1-GPU probe)
+            out["roofline_at_north_star_map"] = dict(extras["north_star_50m"]["roofline"],
+                                                      workload=extras["north_star_50m"]["workload"])
     print(json.dumps(out), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
 
 
 def oracle_with_db(m, blob, proj, frames, engine="imi"):
@@ -477,6 +708,33 @@ def parity_check(step_out, r):
             "max_abs_pose_diff": float(np.abs(T[ok] - r["T"][ok]).max(initial=0.0))}
 
 
+def hash_world_host(landmarks, queries, words):
+    """The N > 1 world (maplab_b200/synthetic_gpu.py) materialised on the host for the CPU arm: the same
+    pure function of the map size the GPU ranks generate shard by shard."""
+    import torch
+    from maplab_b200 import synthetic, synthetic_gpu as sg
+    dev = torch.device("cpu")
+    lm_per_kf, num_kf = sg.layout(landmarks)
+    counts, lms, bits = [], [], []
+    base = 0
+    for kf0 in range(0, num_kf, 4096):
+        kf1 = min(num_kf, kf0 + 4096)
+        c, lm = sg.observations(landmarks, kf0, kf1, dev)
+        g = base + torch.arange(lm.shape[0], dtype=torch.int64)
+        bits.append(sg.descriptor_bytes(lm, g).numpy())
+        counts.append(c.numpy())
+        lms.append(lm.numpy())
+        base += lm.shape[0]
+    m = dict(frames=sg.frames_for(0, np.concatenate(counts), 1, num_kf), bits=np.concatenate(bits),
+             landmarks=np.concatenate(lms), landmark_xyz=sg.all_landmark_xyz(landmarks, dev).numpy())
+    blob, _ = synthetic.make_vocabulary(sg.vocabulary_sample(landmarks, 100_000, dev), num_words=words, seed=7)
+    qd = sg.make_queries(landmarks, 0, queries, dev)
+    fr = qd["frames"]
+    q = dict(frames={k2: fr[k2] for k2 in fr.dtype.names}, bits=qd["bits"].numpy(),
+             keypoints=qd["keypoints"].numpy())
+    return m, blob, q
+
+
 def run_reference(args):
     """The reference's own CPU implementation of the path (oracle port; the maplab binary cannot be
     built in this image) on all host threads, bounded sample per step."""
@@ -487,8 +745,12 @@ def run_reference(args):
     threads = os.cpu_count() or 1
     landmarks = args.landmarks * (args.gpus if args.scaling == "weak" else 1)
     queries = args.queries * (args.gpus if args.scaling == "weak" else 1)
-    m, blob, q = build_world(landmarks, queries, args.words, args.engine)
-    frames = frames_array(m["frames"])
+    if args.gpus > 1:
+        m, blob, q = hash_world_host(landmarks, min(queries, args.cpu_queries or 512), args.words)
+        frames = m["frames"]
+    else:
+        m, blob, q = build_world(landmarks, queries, args.words, args.engine)
+        frames = frames_array(m["frames"])
     ora0 = po.Engine(blob)
     n_db = len(m["bits"])
     proj = np.empty((n_db, 10), np.float32)

@@ -242,6 +242,8 @@ int mlc_last_stage_ms(mlc_detector* d, double* ms5);
 /* Landmark positions in the global frame by dense landmark id (what handleLoopClosure reads
  * through vi_map::VIMap::getLandmark_G_p, LCH/src/loop-closure-handler.cc:272-366). xyz: n x 3. */
 int mlc_set_landmark_positions(mlc_detector* d, const double* xyz, int64_t n);
+/* Same from a device array (copied). */
+int mlc_set_landmark_positions_device(mlc_detector* d, const double* d_xyz, int64_t n);
 
 /* Current poses T_G_I (3x4 row-major [R|t], map_->getVertex_T_G_I(query_vertex_id),
  * LCH/src/loop-closure-handler.cc:436-437) of the query vertices of the NEXT mlc_query_* /

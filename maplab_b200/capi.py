@@ -22,7 +22,7 @@ EXPORTS = [
     "mlc_sharded_knn_device", "mlc_initialize", "mlc_knn",
     "mlc_knn_device", "mlc_coarse_cells", "mlc_merge_topk_device", "mlc_last_scan_stats",
     "mlc_find_batch", "mlc_find_batch_bits", "mlc_find_from_knn_device", "mlc_pnp_ransac_batch",
-    "mlc_coarse_device", "mlc_scan_device", "mlc_last_stage_ms", "mlc_set_landmark_positions", "mlc_query_batch", "mlc_query_batch_device", "mlc_query_from_knn_device",
+    "mlc_coarse_device", "mlc_scan_device", "mlc_last_stage_ms", "mlc_set_landmark_positions", "mlc_set_landmark_positions_device", "mlc_query_batch", "mlc_query_batch_device", "mlc_query_from_knn_device",
     "mlc_score", "mlc_save_index", "mlc_load_index", "mlc_set_query_priors",
     "mlc_default_alignment_settings", "mlc_transformation_ransac",
     "mlc_summary_map_parse", "mlc_summary_map_serialize", "mlc_add_summary_map", "mlc_create_summary_map",
@@ -492,6 +492,9 @@ class Detector:
     def set_landmark_positions(self, xyz):
         xyz = np.ascontiguousarray(xyz, np.float64).reshape(-1, 3)
         _check(lib().mlc_set_landmark_positions(self._h, _ptr(xyz), C.c_int64(len(xyz))))
+
+    def set_landmark_positions_device(self, xyz_ptr, n):
+        _check(lib().mlc_set_landmark_positions_device(self._h, C.c_void_p(xyz_ptr), C.c_int64(n)))
 
     def _query(self, fn, frames, a0, a1, a2, cams, rs, want_matches, want_flags, extra=()):
         frames = np.ascontiguousarray(frames, FRAME_DTYPE)

@@ -308,6 +308,11 @@ int mlc_set_landmark_positions(mlc_detector* d, const double* xyz, int64_t n) {
   std::string err;
   return d->impl.SetLandmarkPositions(xyz, n, &err) ? 0 : Fail(err);
 }
+int mlc_set_landmark_positions_device(mlc_detector* d, const double* d_xyz, int64_t n) {
+  MLC_REQUIRE(d, "null detector");
+  std::string err;
+  return d->impl.SetLandmarkPositionsDevice(d_xyz, n, &err) ? 0 : Fail(err);
+}
 
 int mlc_set_query_priors(mlc_detector* d, const double* T_G_I, int64_t num_vertices) {
   MLC_REQUIRE(d && (num_vertices == 0 || T_G_I) && num_vertices >= 0, "mlc_set_query_priors: bad argument");

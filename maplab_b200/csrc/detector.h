@@ -157,6 +157,7 @@ class Detector {
   // Landmark positions in the global frame by dense landmark id (vi_map::Landmark::get_p_G of
   // the landmark store, read by loop-closure-handler.cc:272-366); replicated on every shard.
   bool SetLandmarkPositions(const double* xyz, int64_t n, std::string* err);
+  bool SetLandmarkPositionsDevice(const double* d_xyz, int64_t n, std::string* err);
   // LoopDetectorNode::addLocalizationSummaryMapToDatabase (LCH/src/loop-detector-node.cc:341-432):
   // one database image per observer of a serialized LocalizationSummaryMap (timestamp 0, one
   // mission id for the whole map, frame index 0, pre-projected descriptors), then Initialize().

@@ -286,6 +286,20 @@ bool Detector::SetLandmarkPositions(const double* xyz, int64_t n, std::string* e
   return Cuda(cudaStreamSynchronize(stream_), "landmark upload", err);
 }
 
+bool Detector::SetLandmarkPositionsDevice(const double* d_xyz, int64_t n, std::string* err) {
+  std::lock_guard<std::recursive_mutex> lock(mu_);
+  if (n < 0 || (n > 0 && !d_xyz)) {
+    *err = "bad landmark table";
+    return false;
+  }
+  if (!Cuda(d_landmark_xyz_.Reserve(sizeof(double) * 3 * n + 16), "alloc landmarks", err)) return false;
+  if (n > 0 && !Cuda(cudaMemcpy(d_landmark_xyz_.p, d_xyz, sizeof(double) * 3 * n, cudaMemcpyDeviceToDevice),
+                     "copy landmarks", err))
+    return false;
+  num_landmark_xyz_ = n;
+  return true;
+}
+
 bool Detector::AddSummaryMap(const void* blob, size_t size, int64_t mission_id, int64_t first_vertex_id,
                              int64_t first_landmark_id, int64_t* sizes5, std::string* err) {
   std::lock_guard<std::recursive_mutex> lock(mu_);
