@@ -45,6 +45,8 @@ def parse_args():
     ap.add_argument("--no-scan-probe", action="store_true",
                     help="skip the extra scan-roofline measurement at the north-star shard size (N = 1 only)")
     ap.add_argument("--probe-landmarks", type=int, default=6_250_000)
+    ap.add_argument("--shard-mode", type=int, default=0, choices=[0, 1],
+                    help="N > 1: 0 = descriptor i on rank i %% N (default), 1 = whole cells by hash (experiment)")
     ap.add_argument("--no-extras", action="store_true",
                     help="skip the extra configurations (10M / 50M-landmark maps, 100M-descriptor kNN microbench)")
     ap.add_argument("--max-extra-landmarks", type=int, default=50_000_000)
@@ -229,11 +231,12 @@ def hash_world_run(landmarks, total_queries, rank, world, local, args, steps, wa
     barrier, max_over_ranks, sum_over_ranks = _dist_helpers(world, dev)
     t0 = time.time()
     blob, _ = synthetic.make_vocabulary(sg.vocabulary_sample(landmarks, 100_000, dev), num_words=args.words, seed=7)
-    det = capi.Detector(blob, capi.default_settings(device=local, shard_rank=rank, shard_count=world))
+    det = capi.Detector(blob, capi.default_settings(device=local, shard_rank=rank, shard_count=world,
+                                                    shard_mode=args.shard_mode))
     if world > 1:
         det.comm_init_torch()
     t1 = time.time()
-    info = sg.build_database(det, landmarks, rank, world, dev)
+    info = sg.build_database(det, landmarks, rank, world, dev, all_rows=args.shard_mode == 1)
     xyz = sg.all_landmark_xyz(landmarks, dev)
     det.set_landmark_positions_device(xyz.data_ptr(), landmarks)
     del xyz
@@ -500,8 +503,10 @@ def run_b200(args):
                 "vs_baseline": None, "dtype": "u8 x s8 -> s32 (projection), f32 (distances), f64 (RANSAC)",
                 "data": "synthetic",
                 "config": {"workload": r["workload"],
-                           "sharding": (f"inverted lists: descriptor i on rank i % {world}, every rank builds only "
-                                        f"its shard; {args.scaling} scaling: map = {landmarks} landmarks, query "
+                           "sharding": ((f"inverted lists: descriptor i on rank i % {world}, every rank builds only "
+                                         f"its shard; " if args.shard_mode == 0 else
+                                         f"inverted lists: whole cells, cell c on rank hash(c) % {world} (experiment); ") +
+                                        f"{args.scaling} scaling: map = {landmarks} landmarks, query "
                                         f"batch = {queries} keyframes per step ("
                                         + (f"{args.landmarks} landmarks and {args.queries} query keyframes per GPU"
                                            if args.scaling == "weak" else "totals fixed") + "); the step is one "

@@ -45,6 +45,11 @@ typedef struct mlc_settings {
   int32_t device;                  /* CUDA device ordinal; -1 = current device */
   int32_t shard_rank;              /* this process' shard of the inverted lists (0 .. shard_count-1) */
   int32_t shard_count;             /* number of shards (GPUs); descriptor i lives on shard i % count */
+  int32_t shard_mode;              /* 0: by descriptor index (i % count, the default: perfectly balanced, a shard
+                                      is handed its own descriptors only). 1: by cell (hash(cell) % count — every
+                                      shard keeps whole inverted lists; EXPERIMENTAL: every shard must be handed
+                                      ALL descriptors and keeps the cells it owns) */
+  int32_t pad_;
 } mlc_settings;
 
 /* One query (or database) frame header. */

@@ -36,7 +36,7 @@ class Settings(C.Structure):
                 ("min_image_time_seconds", C.c_double), ("min_verify_matches_num", C.c_uint64),
                 ("fraction_best_scores", C.c_float), ("knn_epsilon", C.c_float),
                 ("knn_max_radius", C.c_float), ("device", C.c_int32), ("shard_rank", C.c_int32),
-                ("shard_count", C.c_int32)]
+                ("shard_count", C.c_int32), ("shard_mode", C.c_int32), ("pad_", C.c_int32)]
 
 
 class Frame(C.Structure):

@@ -47,6 +47,8 @@ void mlc_default_settings(mlc_settings* s) {
   s->device = -1;
   s->shard_rank = 0;
   s->shard_count = 1;
+  s->shard_mode = 0;
+  s->pad_ = 0;
 }
 
 void mlc_default_ransac_settings(mlc_ransac_settings* s) {

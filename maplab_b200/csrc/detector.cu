@@ -72,6 +72,10 @@ bool Detector::Create(const mlc_settings& s, const void* blob, size_t size, std:
     *err = "unknown detector engine (0 imi, 1 imipq)";
     return false;
   }
+  if (s_.shard_mode != 0 && s_.shard_mode != 1) {
+    *err = "unknown shard_mode (0 by descriptor index, 1 by cell)";
+    return false;
+  }
   if (!vocab_.Parse(blob, size, s_.engine == 1, err)) return false;
   vocab_hash_ = 1469598103934665603ull;
   for (size_t i = 0; i < size; ++i)
@@ -307,12 +311,21 @@ __global__ void fill_i64_kernel(int64_t* __restrict__ p, int64_t n, int64_t v) {
   const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
   if (i < n) p[i] = v;
 }
+// Sharding by cell: the owner of a cell is a hash of its number (decorrelated from the word order).
+__global__ void drop_foreign_cells_kernel(int32_t* __restrict__ cells, int64_t n, int shard_rank, int shard_count) {
+  const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (i >= n) return;
+  const int32_t c = cells[i];
+  if (c >= 0 && static_cast<int>(((static_cast<uint32_t>(c) * 2654435761u) >> 8) % static_cast<uint32_t>(shard_count)) != shard_rank)
+    cells[i] = -1;
+}
 constexpr size_t kPendingFlushBytes = size_t{64} << 20;  // host staging of Insert is bounded by this
 }  // namespace
 
 // Number of descriptors of [first, first + count) that live on this shard (descriptor i on shard
 // i % shard_count).
 int64_t Detector::OwnedInRange(int64_t first, int64_t count) const {
+  if (s_.shard_mode == 1) return count;  // by cell: every shard is handed all descriptors
   const int64_t G = s_.shard_count, r = s_.shard_rank;
   auto upto = [&](int64_t x) { return x <= r ? int64_t{0} : (x - r + G - 1) / G; };  // owned in [0, x)
   return upto(first + count) - upto(first);
@@ -353,7 +366,7 @@ bool Detector::InsertBatch(const mlc_frame* frames, int64_t num_frames, const fl
       }
     }
   }
-  const int64_t G = s_.shard_count, r = s_.shard_rank;
+  const int64_t G = s_.shard_mode == 1 ? 1 : s_.shard_count, r = s_.shard_mode == 1 ? 0 : s_.shard_rank;
   const int64_t base = num_desc_;
   for (int64_t f = 0; f < num_frames; ++f) {
     KeyframeMeta m;
@@ -435,7 +448,8 @@ bool Detector::InsertBatchDevice(const mlc_frame* frames, int64_t num_frames, co
     *err = "descriptor indices are int (SURVEY H7): database would exceed 2^31-1 descriptors";
     return false;
   }
-  const int64_t base = num_desc_, G = s_.shard_count, r = s_.shard_rank;
+  const int64_t base = num_desc_, G = s_.shard_mode == 1 ? 1 : s_.shard_count,
+                r = s_.shard_mode == 1 ? 0 : s_.shard_rank;
   const int64_t owned = OwnedInRange(base, total);
   if (num_owned != owned) {
     *err = "mlc_insert_batch_device: this shard owns " + std::to_string(owned) + " of the batch's " +
@@ -528,6 +542,11 @@ bool Detector::EnsureIndex(std::string* err) {
   if (no > 0) {
     if (!Cuda(d_db_cells_.Reserve(static_cast<size_t>(no) * 4), "alloc cells", err)) return false;
     if (!CoarseChunks(d_desc, no, 1, d_db_cells_.as<int32_t>(), stream_, err)) return false;
+    if (s_.shard_mode == 1 && s_.shard_count > 1) {  // by cell: keep the cells this shard owns
+      drop_foreign_cells_kernel<<<static_cast<unsigned>((no + 255) / 256), 256, 0, stream_>>>(
+          d_db_cells_.as<int32_t>(), no, s_.shard_rank, s_.shard_count);
+      CountLaunch();
+    }
   }
   bool ok = true;
   if (s_.engine == 1) {
@@ -772,6 +791,10 @@ __global__ void validate_lists_kernel(const uint2* __restrict__ cell_info, uint3
 
 bool Detector::SaveIndex(const char* path, std::string* err) {
   std::lock_guard<std::recursive_mutex> lock(mu_);
+  if (s_.shard_mode != 0) {
+    *err = "index files are written for shard_mode 0 only";
+    return false;
+  }
   if (!EnsureIndex(err)) return false;
   FILE* f = fopen(path, "wb");
   if (!f) {
@@ -826,6 +849,10 @@ bool Detector::LoadIndex(const char* path, std::string* err) {
     FILE* f;
     ~Closer() { fclose(f); }
   } closer{f};
+  if (s_.shard_mode != 0) {
+    *err = "index files are read for shard_mode 0 only";
+    return false;
+  }
   IndexFileHeader h{};
   if (!ReadAll(f, &h, sizeof(h)) || std::memcmp(h.magic, "MLCIDX02", 8) != 0) {
     *err = "not an index file of this library";

@@ -115,12 +115,13 @@ def descriptor_bytes(lm, gidx, log2_inv_p=6):
     return words_to_bytes(landmark_words(lm) ^ flip_words(gidx, 6, log2_inv_p))
 
 
-def build_database(det, num_landmarks, rank, world, device, chunk_kf=8192, num_missions=1, on_chunk=None):
+def build_database(det, num_landmarks, rank, world, device, chunk_kf=8192, num_missions=1, on_chunk=None,
+                   all_rows=False):
     """Shard-aware build of the synthetic map into `det` (created with shard_rank = rank, shard_count =
     world): every rank walks the keyframe headers and landmark numbers of the whole map (replicated
     metadata), but generates, projects (kernel 1) and inserts only the descriptors its shard owns.
-    Returns dict(num_descriptors, num_keyframes, sample_bits = the first <= 100 k descriptors' bytes on
-    the host for vocabulary training is NOT done here — see vocabulary_sample)."""
+    all_rows: hand every descriptor to the detector (shard_mode 1, sharding by cell).
+    Returns dict(num_descriptors, num_keyframes)."""
     lm_per_kf, num_kf = layout(num_landmarks)
     stream = torch.cuda.current_stream().cuda_stream if device.type == "cuda" else 0
     base = 0
@@ -129,7 +130,7 @@ def build_database(det, num_landmarks, rank, world, device, chunk_kf=8192, num_m
         counts, lm = observations(num_landmarks, kf0, kf1, device)
         n = int(lm.shape[0])
         gidx = base + torch.arange(n, device=device, dtype=torch.int64)
-        own = (gidx % world) == rank
+        own = torch.ones_like(gidx, dtype=torch.bool) if all_rows else (gidx % world) == rank
         bits = descriptor_bytes(lm[own], gidx[own])
         proj = torch.empty((bits.shape[0], det.dim), dtype=torch.float32, device=device)
         if bits.shape[0]:
