@@ -47,6 +47,10 @@ def parse_args():
     ap.add_argument("--probe-landmarks", type=int, default=6_250_000)
     ap.add_argument("--shard-mode", type=int, default=0, choices=[0, 1],
                     help="N > 1: 0 = descriptor i on rank i %% N (default), 1 = whole cells by hash (experiment)")
+    ap.add_argument("--db", default="auto", choices=["auto", "replicated", "sharded"],
+                    help="N > 1 headline line: placement of the index (auto = replicate when it fits a quarter of HBM)")
+    ap.add_argument("--no-other-placement", action="store_true",
+                    help="N > 1: do not measure the placement the policy did not choose")
     ap.add_argument("--no-extras", action="store_true",
                     help="skip the extra configurations (10M / 50M-landmark maps, 100M-descriptor kNN microbench)")
     ap.add_argument("--max-extra-landmarks", type=int, default=50_000_000)
@@ -216,12 +220,15 @@ def _dist_helpers(world, dev):
     return (barrier, lambda x: reduce(x, dist.ReduceOp.MAX), lambda x: reduce(x, dist.ReduceOp.SUM))
 
 
-def hash_world_run(landmarks, total_queries, rank, world, local, args, steps, warmup, hbm_peak, sampler=None):
+def hash_world_run(landmarks, total_queries, rank, world, local, args, steps, warmup, hbm_peak, sampler=None,
+                   replicated=False):
     """One configuration on the counter-based world (maplab_b200/synthetic_gpu.py): shard-aware database
     build on the device (every rank generates, projects and inserts only the descriptors its shard owns),
     this rank's contiguous slice of the query keyframes, W + K steps of the query path through the C-ABI
     (mlc_query_batch_device at N = 1, the collective mlc_sharded_query_batch_device at N > 1), then the
-    same through host buffers. Returns the measurements (identical dict on every rank where it matters)."""
+    same through host buffers. replicated: every GPU holds the WHOLE index and answers its slice of the
+    batch alone (no collective on the data path) instead of a shard of the index.
+    Returns the measurements (identical dict on every rank where it matters)."""
     import hashlib
     import torch
     import torch.distributed as dist
@@ -231,12 +238,18 @@ def hash_world_run(landmarks, total_queries, rank, world, local, args, steps, wa
     barrier, max_over_ranks, sum_over_ranks = _dist_helpers(world, dev)
     t0 = time.time()
     blob, _ = synthetic.make_vocabulary(sg.vocabulary_sample(landmarks, 100_000, dev), num_words=args.words, seed=7)
-    det = capi.Detector(blob, capi.default_settings(device=local, shard_rank=rank, shard_count=world,
-                                                    shard_mode=args.shard_mode))
-    if world > 1:
+    sharded = world > 1 and not replicated
+    if sharded:
+        det = capi.Detector(blob, capi.default_settings(device=local, shard_rank=rank, shard_count=world,
+                                                        shard_mode=args.shard_mode))
         det.comm_init_torch()
+    else:
+        det = capi.Detector(blob, capi.default_settings(device=local))
     t1 = time.time()
-    info = sg.build_database(det, landmarks, rank, world, dev, all_rows=args.shard_mode == 1)
+    if sharded:
+        info = sg.build_database(det, landmarks, rank, world, dev, all_rows=args.shard_mode == 1)
+    else:
+        info = sg.build_database(det, landmarks, 0, 1, dev)
     xyz = sg.all_landmark_xyz(landmarks, dev)
     det.set_landmark_positions_device(xyz.data_ptr(), landmarks)
     del xyz
@@ -259,7 +272,7 @@ def hash_world_run(landmarks, total_queries, rank, world, local, args, steps, wa
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
     torch.cuda.empty_cache()
 
-    if world > 1:
+    if sharded:
         def step_device():
             return det.sharded_query_batch_device(qframes, bits_d.data_ptr(), 64, kp_d.data_ptr(), cams)
 
@@ -333,10 +346,10 @@ def hash_world_run(landmarks, total_queries, rank, world, local, args, steps, wa
     scan_bytes_mean = sum_over_ranks(float(scan_bytes)) / world
     achieved = scan_bytes_mean / (scan_ms * 1e-3) / 1e9 if scan_ms > 0 else 0.0
     stage = max_stage = None
-    stage = dict(zip(("project", "coarse", "scan_and_exchange" if world > 1 else "scan", "vote_cluster", "ransac"),
+    stage = dict(zip(("project", "coarse", "scan_and_exchange" if sharded else "scan", "vote_cluster", "ransac"),
                      [round(max_over_ranks(float(x) / max(steps, 1)), 4) for x in stage_acc]))
-    nccl = det.comm_nccl_version() if world > 1 else 0
-    if world > 1:
+    nccl = det.comm_nccl_version() if sharded else 0
+    if sharded:
         det.comm_destroy()
     det.close()
     del flush, bits_d, kp_d
@@ -349,11 +362,15 @@ def hash_world_run(landmarks, total_queries, rank, world, local, args, steps, wa
         "workload": workload_string(landmarks, total_queries, args.words, n_db, n_kf, k),
         "roofline": {"kernel": "imi_scan_kernel", "bound": "hbm", "achieved": achieved, "peak": hbm_peak,
                      "unit": "GB/s", "frac": achieved / hbm_peak, "algorithmic_bytes_per_launch": scan_bytes_mean,
-                     "launch_ms": scan_ms, "launches_per_step": world, "per": "GPU (mean bytes / max time over ranks)",
-                     "entries_per_visited_cell_per_shard": round(n_db / world / (args.words * args.words), 2),
+                     "launch_ms": scan_ms, "launches_per_step": "1-3 (own block, then the gathered blocks)" if sharded else 1,
+                     "per": "GPU (mean bytes / max time over ranks)",
+                     "entries_per_visited_cell_per_gpu": round(n_db / (world if sharded else 1) / (args.words * args.words), 2),
                      "traffic": None},
         "stage_ms_max_over_ranks": stage, "gpu_launches_rank0": int(launches), "clocks": clocks,
-        "db": {"descriptors": n_db, "keyframes": n_kf, "per_gpu_descriptors": n_db // world,
+        "db_placement": ("sharded: descriptor i on GPU i % N, one collective step through mlc_sharded_query_batch"
+                         if sharded else ("replicated: every GPU holds the whole index and answers its slice of the "
+                                          "batch alone, no collective on the data path" if world > 1 else "one GPU")),
+        "db": {"descriptors": n_db, "keyframes": n_kf, "per_gpu_descriptors": n_db // world if sharded else n_db,
                "generate_project_insert_s": round(t_generate, 2), "index_build_s": round(t_index, 2),
                "vocabulary_and_setup_s": round(t1 - t0 - t_generate, 2)},
         "checks": {"accepted_loop_closures": accepted, "query_keyframes": total_queries, "matches": matches,
@@ -481,6 +498,11 @@ def run_b200(args):
             r = hash_world_run(lm, 1000, rank, world, local, args, max(args.steps // 2, 3), 3, hbm_peak)
             r["config"] = ("BASELINE config 3 (10M landmarks, 1k query keyframes)" if lm == 10_000_000 else
                            "BASELINE config 4 / north-star target (50M landmarks, 1k query keyframes)")
+            if world > 1 and not args.no_other_placement:  # the same fixed workload on the replicated index
+                o = hash_world_run(lm, 1000, rank, world, local, args, max(args.steps // 2, 3), 3, hbm_peak,
+                                   replicated=True)
+                r["replicated_same_workload"] = {kk: o[kk] for kk in ("db_placement", "value", "ms_per_step", "e2e_value",
+                                                                      "roofline", "stage_ms_max_over_ranks", "db", "checks")}
             r["unit"], r["n_gpus"], r["wall_s"] = UNIT, world, round(time.time() - t0, 1)
             extras[tag] = r
         t0 = time.time()
@@ -493,25 +515,43 @@ def run_b200(args):
         landmarks = args.landmarks * (world if args.scaling == "weak" else 1)
         queries = args.queries * (world if args.scaling == "weak" else 1)
         sampler = ClockSampler(local) if rank == 0 else None
-        r = hash_world_run(landmarks, queries, rank, world, local, args, args.steps, W, hbm_peak, sampler)
+        # Placement policy: an index that fits a quarter of one GPU's HBM is REPLICATED (the query keyframes
+        # are independent units: the batch is split over the GPUs and nothing crosses them); larger ones are
+        # sharded. The other placement is measured on the same workload and reported beside it.
+        n_db_est = 4 * landmarks
+        hbm_bytes = torch.cuda.get_device_properties(local).total_memory
+        fits = n_db_est * 60 <= hbm_bytes // 4
+        replicate = fits if args.db == "auto" else args.db == "replicated"
+        r = hash_world_run(landmarks, queries, rank, world, local, args, args.steps, W, hbm_peak, sampler,
+                           replicated=replicate)
+        other = None
+        if not args.no_other_placement:
+            other = hash_world_run(landmarks, queries, rank, world, local, args, max(args.steps // 2, 3), 3, hbm_peak,
+                                   None, replicated=not replicate)
         run_extras()
         if rank == 0:
             roof = dict(r["roofline"], peak_source=peak_src)
+            per_gpu = (f"{args.landmarks} landmarks and {args.queries} query keyframes per GPU"
+                       if args.scaling == "weak" else "totals fixed")
+            scaling_text = (f"{args.scaling} scaling: map = {landmarks} landmarks, query batch = {queries} "
+                            f"keyframes per step ({per_gpu})")
+            if replicate:
+                sharding_text = f"none (replicated index, the batch is split over the GPUs); {scaling_text}"
+            else:
+                how = (f"descriptor i on rank i % {world}, every rank builds only its shard" if args.shard_mode == 0
+                       else f"whole cells, cell c on rank hash(c) % {world} (experiment)")
+                sharding_text = (f"inverted lists: {how}; {scaling_text}; the step is one collective call through "
+                                 f"the C-ABI (mlc_sharded_query_batch_device), NCCL {r['nccl_version']} inside the library")
             out = {
                 "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": W, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": args.scaling,
                 "vs_baseline": None, "dtype": "u8 x s8 -> s32 (projection), f32 (distances), f64 (RANSAC)",
                 "data": "synthetic",
                 "config": {"workload": r["workload"],
-                           "sharding": ((f"inverted lists: descriptor i on rank i % {world}, every rank builds only "
-                                         f"its shard; " if args.shard_mode == 0 else
-                                         f"inverted lists: whole cells, cell c on rank hash(c) % {world} (experiment); ") +
-                                        f"{args.scaling} scaling: map = {landmarks} landmarks, query "
-                                        f"batch = {queries} keyframes per step ("
-                                        + (f"{args.landmarks} landmarks and {args.queries} query keyframes per GPU"
-                                           if args.scaling == "weak" else "totals fixed") + "); the step is one "
-                                        "collective call through the C-ABI (mlc_sharded_query_batch_device), NCCL "
-                                        f"{r['nccl_version']} inside the library"),
+                           "db_placement": r["db_placement"],
+                           "placement_policy": f"--db {args.db}: replicate when 60 B x descriptors <= 25% of HBM "
+                                               f"({n_db_est * 60 / 1e9:.1f} GB of {hbm_bytes / 1e9:.0f} GB here), else shard",
+                           "sharding": sharding_text,
                            "generator": "counter-based world (maplab_b200/synthetic_gpu.py), same model as the "
                                         "N = 1 world, generated shard by shard on the GPUs",
                            "l2": "256 MiB flush buffer written between timed iterations",
@@ -524,6 +564,10 @@ def run_b200(args):
                 "stage_ms": r["stage_ms_max_over_ranks"], "checks": r["checks"],
                 "setup_s": round(time.time() - t_setup, 1),
             }
+            if other is not None:
+                out["other_placement_same_workload"] = {
+                    kk: other[kk] for kk in ("db_placement", "value", "ms_per_step", "e2e_value", "roofline",
+                                             "stage_ms_max_over_ranks", "db", "checks", "nccl_version")}
             out.update(extras)
             print(json.dumps(out), flush=True)
         dist.destroy_process_group()

@@ -24,6 +24,7 @@
 #include <nccl.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 #include "detector.h"
@@ -200,34 +201,91 @@ bool Detector::ShardedKnnOnSlice(int64_t n_s, int64_t n_max, int k, std::string*
       !Nccl(g_nccl.GroupEnd(), "ncclGroupEnd", err))
     return false;
   if (!Cuda(cudaEventRecord(ev_comm_[1], comm_stream_), "event", err)) return false;
-  // ---- 3: scan block by block in ring order; block s leaves while block s+1 is scanned ----
+  // ---- 3: scan + exchange 2. Three schedules (MLC_SHARD_PIPELINE, results identical):
+  //   0  wait for exchange 1, ONE scan launch over all G blocks, one grouped all-to-all
+  //   1  own block scanned while exchange 1 is in flight, the other blocks in one or two launches, one
+  //      grouped all-to-all                                                             (default)
+  //   2  ring: block s leaves (grouped send/recv) while block s+1 is scanned
   unsigned char* pidx = sh_pidx_.as<unsigned char>();
   unsigned char* pdist = sh_pdist_.as<unsigned char>();
   unsigned char* ridx = sh_ridx_.as<unsigned char>();
   unsigned char* rdist = sh_rdist_.as<unsigned char>();
-  for (int s = 0; s < G; ++s) {
-    const int src = (r + s) % G, from = (r - s + G) % G;
-    const float* q_blk_p = s == 0 ? d_q_.as<float>() : reinterpret_cast<const float*>(sh_q_all_.as<unsigned char>() + q_blk * src);
-    const int32_t* c_blk_p = s == 0 ? d_cells_.as<int32_t>()
-                                    : reinterpret_cast<const int32_t*>(sh_cells_all_.as<unsigned char>() + c_blk * src);
-    // the own block goes straight to where the merge reads it
-    int32_t* o_idx = reinterpret_cast<int32_t*>(s == 0 ? ridx + l_blk * r : pidx + l_blk * src);
-    float* o_dist = reinterpret_cast<float*>(s == 0 ? rdist + l_blk * r : pdist + l_blk * src);
-    if (s == 1 && !Cuda(cudaStreamWaitEvent(stream_, ev_comm_[1], 0), "wait", err)) return false;
-    cudaEventRecord(ev_scan_[2 * s], stream_);
-    if (!Cuda(LaunchScan(q_blk_p, n_max, c_blk_p, nw, k, o_idx, o_dist, stream_), "list scan", err)) return false;
-    cudaEventRecord(ev_scan_[2 * s + 1], stream_);
-    if (s == 0) continue;
+  int schedule = 1;
+  if (const char* env = getenv("MLC_SHARD_PIPELINE")) {
+    const int v = atoi(env);
+    if (v >= 0 && v <= 2) schedule = v;
+  }
+  if (G == 1) schedule = 2;  // one block, nothing to exchange
+  int launches = 0;
+  auto scan_blocks = [&](int b0, int b1, bool from_gathered) -> bool {  // blocks [b0, b1) of the gathered order
+    if (b1 <= b0) return true;
+    const float* qp = from_gathered ? reinterpret_cast<const float*>(sh_q_all_.as<unsigned char>() + q_blk * b0) : d_q_.as<float>();
+    const int32_t* cp = from_gathered ? reinterpret_cast<const int32_t*>(sh_cells_all_.as<unsigned char>() + c_blk * b0)
+                                      : d_cells_.as<int32_t>();
+    cudaEventRecord(ev_scan_[2 * launches], stream_);
+    if (!Cuda(LaunchScan(qp, n_max * (b1 - b0), cp, nw, k, reinterpret_cast<int32_t*>(pidx + l_blk * b0),
+                         reinterpret_cast<float*>(pdist + l_blk * b0), stream_), "list scan", err))
+      return false;
+    cudaEventRecord(ev_scan_[2 * launches + 1], stream_);
+    ++launches;
+    return true;
+  };
+  auto all_to_all = [&]() -> bool {  // block p of my lists -> rank p; my slice's lists from every shard
     if (!Cuda(cudaEventRecord(ev_comm_[2], stream_), "event", err) ||
         !Cuda(cudaStreamWaitEvent(comm_stream_, ev_comm_[2], 0), "wait", err))
       return false;
-    if (!Nccl(g_nccl.GroupStart(), "ncclGroupStart", err) ||
-        !Nccl(g_nccl.Send(pidx + l_blk * src, l_blk, ncclChar, src, comm, comm_stream_), "ncclSend", err) ||
-        !Nccl(g_nccl.Send(pdist + l_blk * src, l_blk, ncclChar, src, comm, comm_stream_), "ncclSend", err) ||
-        !Nccl(g_nccl.Recv(ridx + l_blk * from, l_blk, ncclChar, from, comm, comm_stream_), "ncclRecv", err) ||
-        !Nccl(g_nccl.Recv(rdist + l_blk * from, l_blk, ncclChar, from, comm, comm_stream_), "ncclRecv", err) ||
-        !Nccl(g_nccl.GroupEnd(), "ncclGroupEnd", err))
+    if (!Nccl(g_nccl.GroupStart(), "ncclGroupStart", err)) return false;
+    for (int p = 0; p < G; ++p) {
+      if (p == r) continue;
+      if (!Nccl(g_nccl.Send(pidx + l_blk * p, l_blk, ncclChar, p, comm, comm_stream_), "ncclSend", err) ||
+          !Nccl(g_nccl.Send(pdist + l_blk * p, l_blk, ncclChar, p, comm, comm_stream_), "ncclSend", err) ||
+          !Nccl(g_nccl.Recv(ridx + l_blk * p, l_blk, ncclChar, p, comm, comm_stream_), "ncclRecv", err) ||
+          !Nccl(g_nccl.Recv(rdist + l_blk * p, l_blk, ncclChar, p, comm, comm_stream_), "ncclRecv", err))
+        return false;
+    }
+    if (!Nccl(g_nccl.GroupEnd(), "ncclGroupEnd", err)) return false;
+    // the own block goes straight to where the merge reads it
+    return Cuda(cudaMemcpyAsync(ridx + l_blk * r, pidx + l_blk * r, l_blk, cudaMemcpyDeviceToDevice, stream_), "copy", err) &&
+           Cuda(cudaMemcpyAsync(rdist + l_blk * r, pdist + l_blk * r, l_blk, cudaMemcpyDeviceToDevice, stream_), "copy", err);
+  };
+  if (schedule == 0) {
+    if (!Cuda(cudaStreamWaitEvent(stream_, ev_comm_[1], 0), "wait", err)) return false;
+    if (!scan_blocks(0, G, true) || !all_to_all()) return false;
+  } else if (schedule == 1) {
+    // own block from the local buffers into its place of the per-shard lists
+    cudaEventRecord(ev_scan_[0], stream_);
+    if (!Cuda(LaunchScan(d_q_.as<float>(), n_max, d_cells_.as<int32_t>(), nw, k, reinterpret_cast<int32_t*>(pidx + l_blk * r),
+                         reinterpret_cast<float*>(pdist + l_blk * r), stream_), "list scan", err))
       return false;
+    cudaEventRecord(ev_scan_[1], stream_);
+    launches = 1;
+    if (!Cuda(cudaStreamWaitEvent(stream_, ev_comm_[1], 0), "wait", err)) return false;
+    if (!scan_blocks(0, r, true) || !scan_blocks(r + 1, G, true) || !all_to_all()) return false;
+  } else {
+    for (int s = 0; s < G; ++s) {
+      const int src = (r + s) % G, from = (r - s + G) % G;
+      const float* q_blk_p = s == 0 ? d_q_.as<float>() : reinterpret_cast<const float*>(sh_q_all_.as<unsigned char>() + q_blk * src);
+      const int32_t* c_blk_p = s == 0 ? d_cells_.as<int32_t>()
+                                      : reinterpret_cast<const int32_t*>(sh_cells_all_.as<unsigned char>() + c_blk * src);
+      int32_t* o_idx = reinterpret_cast<int32_t*>(s == 0 ? ridx + l_blk * r : pidx + l_blk * src);
+      float* o_dist = reinterpret_cast<float*>(s == 0 ? rdist + l_blk * r : pdist + l_blk * src);
+      if (s == 1 && !Cuda(cudaStreamWaitEvent(stream_, ev_comm_[1], 0), "wait", err)) return false;
+      cudaEventRecord(ev_scan_[2 * s], stream_);
+      if (!Cuda(LaunchScan(q_blk_p, n_max, c_blk_p, nw, k, o_idx, o_dist, stream_), "list scan", err)) return false;
+      cudaEventRecord(ev_scan_[2 * s + 1], stream_);
+      ++launches;
+      if (s == 0) continue;
+      if (!Cuda(cudaEventRecord(ev_comm_[2], stream_), "event", err) ||
+          !Cuda(cudaStreamWaitEvent(comm_stream_, ev_comm_[2], 0), "wait", err))
+        return false;
+      if (!Nccl(g_nccl.GroupStart(), "ncclGroupStart", err) ||
+          !Nccl(g_nccl.Send(pidx + l_blk * src, l_blk, ncclChar, src, comm, comm_stream_), "ncclSend", err) ||
+          !Nccl(g_nccl.Send(pdist + l_blk * src, l_blk, ncclChar, src, comm, comm_stream_), "ncclSend", err) ||
+          !Nccl(g_nccl.Recv(ridx + l_blk * from, l_blk, ncclChar, from, comm, comm_stream_), "ncclRecv", err) ||
+          !Nccl(g_nccl.Recv(rdist + l_blk * from, l_blk, ncclChar, from, comm, comm_stream_), "ncclRecv", err) ||
+          !Nccl(g_nccl.GroupEnd(), "ncclGroupEnd", err))
+        return false;
+    }
   }
   if (!Cuda(cudaEventRecord(ev_comm_[3], comm_stream_), "event", err) ||
       !Cuda(cudaStreamWaitEvent(stream_, ev_comm_[3], 0), "wait", err))
@@ -240,7 +298,7 @@ bool Detector::ShardedKnnOnSlice(int64_t n_s, int64_t n_max, int k, std::string*
   last_cells_ = sh_cells_all_.as<int32_t>();
   last_nq_ = n_max * G;
   last_nw_ = nw;
-  last_scan_launches_ = G;
+  last_scan_launches_ = launches;
   last_valid_ = true;
   return true;
 }
