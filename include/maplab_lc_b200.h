@@ -443,7 +443,8 @@ typedef struct mlc_vi_map_arrays { /* caller-allocated from mlc_vi_map_counts; a
   int32_t* vertex_num_landmarks;   /* per vertex: size of its landmark store */
   int64_t* frame_timestamp_ns;     /* per visual frame, vertex-major */
   int32_t* frame_num_keypoints;
-  uint8_t* frame_is_valid;
+  uint8_t* frame_is_valid;         /* 1 = the frame is set (valid frame id) and not invalidated: what
+                                      addVertexToDatabase / queryVertexInDatabase require of a frame */
   double* keypoint_measurement;    /* 2 per keypoint, frame-major */
   uint8_t* keypoint_descriptor;    /* descriptor_bytes per keypoint */
   uint64_t* keypoint_landmark_id;  /* 2 per keypoint; (0, 0) = no landmark */

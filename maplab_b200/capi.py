@@ -496,13 +496,13 @@ class Detector:
     def set_landmark_positions_device(self, xyz_ptr, n):
         _check(lib().mlc_set_landmark_positions_device(self._h, C.c_void_p(xyz_ptr), C.c_int64(n)))
 
-    def _query(self, fn, frames, a0, a1, a2, cams, rs, want_matches, want_flags, extra=()):
+    def _query(self, fn, frames, a0, a1, a2, cams, rs, want_matches, want_flags, extra=(), k=None):
         frames = np.ascontiguousarray(frames, FRAME_DTYPE)
         cams = np.ascontiguousarray(cams, CAMERA_DTYPE)
         rs = rs or default_ransac_settings()
         nf = len(frames)
         total = int(frames["num_descriptors"].sum())
-        k = max(self.num_neighbors(), 1)
+        k = max(k if k is not None else self.num_neighbors(), 1)  # the buffers must hold total * k matches
         res = np.zeros(max(nf, 1), POSE_DTYPE)
         nv, nm = C.c_int64(), C.c_int64()
         cap = total * k + 16 if want_matches else 0
@@ -579,7 +579,7 @@ class Detector:
                               want_matches=False, want_flags=False):
         return self._query(lib().mlc_query_from_knn_device, frames, C.c_void_p(idx_ptr),
                            C.c_void_p(dist_ptr), k, cams, rs, want_matches, want_flags,
-                           extra=(C.c_void_p(keypoints_ptr),))
+                           extra=(C.c_void_p(keypoints_ptr),), k=k)
 
     def pnp_ransac_batch(self, cams, offsets, keypoints, camera_index, keypoint_index, landmarks,
                          rs=None, want_flags=True):

@@ -406,6 +406,8 @@ int mlc_create_summary_map(mlc_detector* d, int64_t num_landmarks, const double*
               "mlc_create_summary_map: null argument or no landmarks (CHECK(!landmark_ids.empty()))");
   MLC_REQUIRE(num_observations > 0 && num_observations <= 0x7FFFFFFFLL && bits && observer_key && G_observer_position,
               "mlc_create_summary_map: no landmark observations for summary map");
+  MLC_REQUIRE(bytes_per_desc > 0 && bytes_per_desc % 16 == 0,
+              "mlc_create_summary_map: bytes per descriptor must be a positive multiple of 16");
   mlc::SummaryMap m;
   m.has_uncompressed_map = true;
   m.G_landmark_position.resize(static_cast<size_t>(num_landmarks) * 3);

@@ -112,6 +112,10 @@ bool Detector::FindOnDevice(const mlc_frame* frames, int64_t num_frames, const i
       }
       vertices.push_back(Vertex{static_cast<int>(f), 0, 0});
     }
+    if (frames[f].num_descriptors < 0) {
+      *err = "negative descriptor count";
+      return false;
+    }
     Vertex& v = vertices.back();
     ++v.num_frames;
     const int64_t slots = static_cast<int64_t>(frames[f].num_descriptors) * k;
@@ -365,7 +369,13 @@ bool Detector::QueryBatch(const mlc_frame* frames, int64_t num_frames, const uin
   }
   if (!EnsureIndex(err)) return false;
   int64_t n = 0;
-  for (int64_t f = 0; f < num_frames; ++f) n += frames[f].num_descriptors;
+  for (int64_t f = 0; f < num_frames; ++f) {
+    if (frames[f].num_descriptors < 0) {
+      *err = "negative descriptor count";
+      return false;
+    }
+    n += frames[f].num_descriptors;
+  }
   const int k = NumNeighbors();
   const size_t qb = static_cast<size_t>(n) * dim() * 4, rb = static_cast<size_t>(n) * k * 4;
   if (!Cuda(d_q_.Reserve(qb + 16), "alloc", err) || !Cuda(d_idx_.Reserve(rb + 16), "alloc", err) ||

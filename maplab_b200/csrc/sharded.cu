@@ -202,15 +202,15 @@ bool Detector::ShardedKnnOnSlice(int64_t n_s, int64_t n_max, int k, std::string*
     return false;
   if (!Cuda(cudaEventRecord(ev_comm_[1], comm_stream_), "event", err)) return false;
   // ---- 3: scan + exchange 2. Three schedules (MLC_SHARD_PIPELINE, results identical):
-  //   0  wait for exchange 1, ONE scan launch over all G blocks, one grouped all-to-all
+  //   0  wait for exchange 1, ONE scan launch over all G blocks, one grouped all-to-all          (default)
   //   1  own block scanned while exchange 1 is in flight, the other blocks in one or two launches, one
-  //      grouped all-to-all                                                             (default)
+  //      grouped all-to-all
   //   2  ring: block s leaves (grouped send/recv) while block s+1 is scanned
   unsigned char* pidx = sh_pidx_.as<unsigned char>();
   unsigned char* pdist = sh_pdist_.as<unsigned char>();
   unsigned char* ridx = sh_ridx_.as<unsigned char>();
   unsigned char* rdist = sh_rdist_.as<unsigned char>();
-  int schedule = 1;
+  int schedule = 0;
   if (const char* env = getenv("MLC_SHARD_PIPELINE")) {
     const int v = atoi(env);
     if (v >= 0 && v <= 2) schedule = v;

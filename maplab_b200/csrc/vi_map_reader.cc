@@ -31,7 +31,10 @@ bool ParseFrame(Reader r, ViMapVertices* m, std::string* err) {
   const uint8_t* desc = nullptr;
   size_t desc_size = 0;
   int64_t timestamp = 0;
-  uint8_t is_valid = 0;
+  // deserializeVisualFrame (aslam-serialization/src/visual-frame-serialization.cc:88-168): a frame whose id
+  // is invalid "has been un-set"; a frame is valid unless is_valid is PRESENT and false
+  uint8_t is_valid = 1;
+  uint64_t frame_id[2] = {0, 0};
   uint32_t field;
   int wt;
   while (r.p != r.end) {
@@ -39,7 +42,10 @@ bool ParseFrame(Reader r, ViMapVertices* m, std::string* err) {
     bool handled = false;
     uint64_t v;
     Reader sub;
-    if (field == 2 && wt == 0) {
+    if (field == 1 && wt == 2) {
+      if (!r.Sub(&sub) || !ParseId(sub, frame_id)) return false;
+      handled = true;
+    } else if (field == 2 && wt == 0) {
       if (!r.Varint(&v)) return false;
       timestamp = static_cast<int64_t>(v);
       handled = true;
@@ -76,11 +82,17 @@ bool ParseFrame(Reader r, ViMapVertices* m, std::string* err) {
     // aslam's descriptor matrix: 24-byte header with int32 rows at byte 8 and int32 cols at byte 12, then the
     // column-major uchar data (one descriptor per column)
     int32_t rows = 0, cols = 0;
+    uint64_t blocks = 0;  // the DESCRIPTORS channel is a vector of matrices: leading size_t = their number
     if (desc_size >= 24) {
+      std::memcpy(&blocks, desc, 8);
       std::memcpy(&rows, desc + 8, 4);
       std::memcpy(&cols, desc + 12, 4);
+      if (blocks > 1) {
+        *err = "vi_map: frames with several descriptor types (descriptor blocks) are not supported";
+        return false;
+      }
     }
-    if (desc_size < 24 || rows <= 0 || cols < 0 || static_cast<size_t>(rows) * cols + 24 != desc_size ||
+    if (desc_size < 24 || blocks != 1 || rows <= 0 || cols < 0 || static_cast<size_t>(rows) * cols + 24 != desc_size ||
         static_cast<size_t>(cols) != n) {
       *err = "vi_map: descriptor matrix does not match the keypoints";
       return false;
@@ -96,7 +108,7 @@ bool ParseFrame(Reader r, ViMapVertices* m, std::string* err) {
   m->keypoint_landmark_id.insert(m->keypoint_landmark_id.end(), landmark_ids.begin(), landmark_ids.end());
   m->frame_timestamp_ns.push_back(timestamp);
   m->frame_num_keypoints.push_back(static_cast<int32_t>(n));
-  m->frame_is_valid.push_back(is_valid);
+  m->frame_is_valid.push_back((frame_id[0] != 0 || frame_id[1] != 0) ? is_valid : 0);
   return true;
 }
 
@@ -243,12 +255,14 @@ bool ViMapMissions::Parse(const void* proto, size_t size, std::string* err) {
     uint64_t id[2];
     if ((field == 5 || field == 7) && wt == 2) {
       ok = r.Sub(&sub) && ParseId(sub, id);
+      if (!ok) break;
       std::vector<uint64_t>& dst = field == 5 ? ids : base_ids;
       dst.push_back(id[0]);
       dst.push_back(id[1]);
     } else if (field == 6 && wt == 2) {  // Mission: baseframe_id = 1
       std::vector<double> none;
       ok = r.Sub(&sub) && ParseIdAndVector(sub, 1, 0, id, &none);
+      if (!ok) break;
       base_of_mission.push_back(id[0]);
       base_of_mission.push_back(id[1]);
     } else if (field == 8 && wt == 2) {  // MissionBaseframe: T_G_M = 1

@@ -50,6 +50,7 @@ def _vi_map_class():
     m = fd.message_type.add(); m.name = "Id"                      # aslam.proto.Id
     fld(m, "uint", 1, F.TYPE_UINT64, R)
     m = fd.message_type.add(); m.name = "VisualFrame"             # aslam.proto.VisualFrame
+    fld(m, "id", 1, F.TYPE_MESSAGE, O, ".mlc_vi_map.Id")
     fld(m, "timestamp", 2, F.TYPE_INT64, O)
     fld(m, "keypoint_measurements", 3, F.TYPE_DOUBLE, R)
     fld(m, "keypoint_descriptors", 5, F.TYPE_BYTES, O)
@@ -168,6 +169,13 @@ def cameras_of(sensors, camera_indices=None):
     return cams
 
 
+def frame_is_usable(fr):
+    """isVisualFrameSet && isVisualFrameValid of addVertexToDatabase / queryVertexInDatabase
+    (loop-detector-node.cc:279-280, :694-695): a frame without a valid id has been un-set, and a frame is
+    valid unless `is_valid` is present and false (visual-frame-serialization.cc:95-96, :166-168)."""
+    return any(fr.id.uint) and not (fr.HasField("is_valid") and not fr.is_valid)
+
+
 def loop_closure_inputs(vi_map, camera_indices=None):
     """Arrays for mlc_insert_batch / mlc_query_batch over all vertices in pose-graph (time) order.
     frames: [F][4] int64 (timestamp_ns, vertex number, frame index within `camera_indices`, descriptors)."""
@@ -190,6 +198,8 @@ def loop_closure_inputs(vi_map, camera_indices=None):
         cams = range(len(v.n_visual_frame.frames)) if camera_indices is None else camera_indices
         for slot, ci in enumerate(cams):
             fr = v.n_visual_frame.frames[ci]
+            if not frame_is_usable(fr):
+                continue
             desc = descriptors_of(fr)
             kp = np.array(fr.keypoint_measurements).reshape(-1, 2)
             if not (len(desc) == len(kp) == len(fr.landmark_ids)):
@@ -258,6 +268,8 @@ def loop_closure_inputs_native(arrays, missions, camera_indices=None):
         cams = range(arrays["vertex_num_frames"][v]) if camera_indices is None else camera_indices
         for slot, ci in enumerate(cams):
             f = frame_start[v] + ci
+            if not arrays["frame_is_valid"][f]:  # un-set or invalidated frame: not in the database, not queried
+                continue
             kept = 0
             for k in range(kp_start[f], kp_start[f + 1]):
                 number = landmark_number.get(tuple(int(w) for w in arrays["keypoint_landmark_id"][k]))

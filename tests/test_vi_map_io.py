@@ -81,7 +81,7 @@ def _compare_with_runtime(proto_bytes):
     frames = [f for v in msg.vertices for f in v.n_visual_frame.frames]
     assert got["vertex_num_frames"].tolist() == [len(v.n_visual_frame.frames) for v in msg.vertices]
     assert got["frame_timestamp_ns"].tolist() == [f.timestamp for f in frames]
-    assert got["frame_is_valid"].tolist() == [int(f.is_valid) for f in frames]
+    assert got["frame_is_valid"].tolist() == [int(vi_map_io.frame_is_usable(f)) for f in frames]
     assert got["frame_num_keypoints"].tolist() == [len(f.keypoint_measurements) // 2 for f in frames]
     kp = np.concatenate([np.zeros((0, 2))] + [np.array(f.keypoint_measurements).reshape(-1, 2) for f in frames])
     assert np.array_equal(got["keypoint_measurement"], kp)
@@ -111,7 +111,12 @@ def _toy_map(rng, vertices=3, frames=2, bytes_per_desc=48):
             fr = vert.n_visual_frame.frames.add()
             n = int(rng.integers(0, 6)) if (v, f) != (0, 0) else 4
             fr.timestamp = 1_600_000_000_000_000_000 + 1000 * v + f
-            fr.is_valid = bool((v + f) % 2)
+            # frame validity as the reference reads it: (v + f) % 4 == 0: is_valid absent (= valid), 1: present and
+            # true, 2: present and false (invalidated), 3: no frame id (the frame "has been un-set")
+            if (v + f) % 4 != 3:
+                fr.id.uint.extend([int(rng.integers(1, 2 ** 62)), 77])
+            if (v + f) % 4 in (1, 2):
+                fr.is_valid = (v + f) % 4 == 1
             fr.keypoint_measurements.extend(rng.uniform(0, 700, 2 * n).tolist())
             data = rng.integers(0, 256, (n, bytes_per_desc), dtype=np.uint8)
             fr.keypoint_descriptors = struct.pack("<qiiii", 1, bytes_per_desc, n, 0, 1) + data.tobytes()
@@ -137,6 +142,32 @@ def test_cxx_reader_equals_protobuf_runtime_on_constructed_maps():
     _compare_with_runtime(b"")  # an empty message is an empty map
 
 
+def test_unset_and_invalidated_frames_stay_out_of_the_detector_inputs():
+    """addVertexToDatabase / queryVertexInDatabase only take frames with isVisualFrameSet && isVisualFrameValid
+    (loop-detector-node.cc:279-280, :694-695); both readers must drop the others and agree."""
+    from maplab_b200 import capi
+    rng = np.random.default_rng(5)
+    msg = _toy_map(rng, vertices=6, frames=2)
+    for v in msg.vertices:  # make every keypoint's landmark a good landmark of its vertex
+        del v.landmark_store.landmarks[:]
+        for fr in v.n_visual_frame.frames:
+            for lid in fr.landmark_ids:
+                if any(lid.uint):
+                    lm = v.landmark_store.landmarks.add()
+                    lm.id.uint.extend(list(lid.uint))
+                    lm.position.extend(rng.normal(size=3).tolist())
+                    lm.quality = 2
+    missions = {(7, 9): np.eye(4)}
+    ids = [tuple(i.uint) for i in msg.vertex_ids]
+    exp = vi_map_io.loop_closure_inputs(dict(vertices=list(zip(ids, msg.vertices)), missions=missions, sensors=None))
+    usable = [vi_map_io.frame_is_usable(f) for v in msg.vertices for f in v.n_visual_frame.frames]
+    assert 0 < sum(usable) < len(usable) and len(exp["frames"]) == sum(usable)
+    got = vi_map_io.loop_closure_inputs_native(capi.vi_map_read_vertices(msg.SerializeToString()), missions)
+    for key in ("frames", "missions", "bits", "keypoints", "landmarks", "landmark_xyz", "T_G_I"):
+        assert np.array_equal(got[key], exp[key]), key
+    assert len(exp["bits"]) > 0
+
+
 def test_cxx_reader_rejections():
     import gzip
     from maplab_b200 import capi
@@ -155,6 +186,11 @@ def test_cxx_reader_rejections():
     broken.CopyFrom(msg)
     del broken.vertex_ids[-1]
     with pytest.raises(capi.MlcError, match="vertex_ids and vertices"):
+        capi.vi_map_read_vertices(broken.SerializeToString())
+    broken.CopyFrom(msg)
+    fr0 = broken.vertices[0].n_visual_frame.frames[0]
+    fr0.keypoint_descriptors = (2).to_bytes(8, "little") + fr0.keypoint_descriptors[8:]
+    with pytest.raises(capi.MlcError, match="several descriptor types"):
         capi.vi_map_read_vertices(broken.SerializeToString())
     broken.CopyFrom(msg)
     broken.vertices[0].n_visual_frame.frames[0].keypoint_descriptors = b"\\x00" * 30
