@@ -193,7 +193,7 @@ def test_cxx_reader_rejections():
     with pytest.raises(capi.MlcError, match="several descriptor types"):
         capi.vi_map_read_vertices(broken.SerializeToString())
     broken.CopyFrom(msg)
-    broken.vertices[0].n_visual_frame.frames[0].keypoint_descriptors = b"\\x00" * 30
+    broken.vertices[0].n_visual_frame.frames[0].keypoint_descriptors = b"\x00" * 30
     with pytest.raises(capi.MlcError, match="descriptor matrix"):
         capi.vi_map_read_vertices(broken.SerializeToString())
 
