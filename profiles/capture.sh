@@ -7,7 +7,7 @@ set -u
 TAG=${1:-rX}
 KERN=${2:-imi_scan_kernel}
 mkdir -p gpurun_out
-CMD="python bench.py --steps 2 --warmup 3 --no-cpu-baseline"
+CMD="python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-extras --no-scan-probe"
 ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv \
     --log-file gpurun_out/${TAG}_launches.csv $CMD > gpurun_out/${TAG}_launches.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:${KERN} -s 4 -c 2 \
