@@ -44,6 +44,7 @@ struct CovisArgs {
 };
 
 size_t CovisScratchMatches(int max_matches, int grid);
+int CovisCtasPerSm(int max_matches);
 cudaError_t LaunchCovis(const CovisArgs& a, int max_matches, int grid, cudaStream_t stream);
 cudaError_t LaunchScore(const unsigned long long* votes, const unsigned long long* num_desc, int n,
                         long long num_db, int scoring, float* out, cudaStream_t stream);

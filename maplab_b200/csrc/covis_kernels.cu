@@ -13,6 +13,8 @@
 // smallest database descriptor, output sorted by (query frame, keypoint, database descriptor).
 #include <cub/cub.cuh>
 
+#include <cstdlib>
+
 #include "covis.h"
 
 namespace mlc {
@@ -29,11 +31,16 @@ struct CovisSmem {
   int bcast[4];
 };
 
+// Bitonic sort of keys[0, p2) in shared memory (p2 a power of two); every thread of the block must call
+// it. One compare-exchange per pair and step. Pair t of a step with stride j touches the elements
+// i = ((t & ~(j-1)) << 1) | (t & (j-1)) and i | j: for j <= 32 the 32 pairs of a warp stay inside one
+// 64-element span that no other warp touches, so those steps only need a warp barrier; a block barrier is
+// needed only around the steps with larger strides (20 instead of 66 block barriers at 2048 keys).
 template <int THREADS>
 __device__ __forceinline__ void BitonicSort(unsigned long long* keys, int p2) {
   for (int k2 = 2; k2 <= p2; k2 <<= 1) {
     for (int j = k2 >> 1; j > 0; j >>= 1) {
-      for (int t = threadIdx.x; t < (p2 >> 1); t += THREADS) {  // one compare-exchange per pair
+      for (int t = threadIdx.x; t < (p2 >> 1); t += THREADS) {
         const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
         const int ixj = i | j;
         const bool asc = (i & k2) == 0;
@@ -43,9 +50,14 @@ __device__ __forceinline__ void BitonicSort(unsigned long long* keys, int p2) {
           keys[ixj] = a;
         }
       }
-      __syncthreads();
+      const int next_j = j > 1 ? (j >> 1) : k2;  // first stride of the next merge: (2 * k2) / 2
+      if (j > 32 || next_j > 32)
+        __syncthreads();
+      else
+        __syncwarp();
     }
   }
+  __syncthreads();
 }
 
 __device__ __forceinline__ int NextPow2(int n) {
@@ -359,15 +371,21 @@ __global__ void __launch_bounds__(THREADS, (THREADS <= 512 ? 2 : 1)) covis_kerne
       // ---------------------------------------------------------------- E: distinct matches, sizes
       // Duplicates (same query keypoint, keyframe and landmark, different database descriptor)
       // can only sit among the <= k neighbours of one keypoint, which are adjacent in `rec`.
+      // (the records live in global scratch: the shared-memory ids — selected group a1, dense landmark a4,
+      // query keypoint a5 — rule a neighbour out before its record is fetched)
+      uint16_t* qkp = s.a5;  // offA is no longer needed
+      for (int i = tid; i < R; i += THREADS) qkp[i] = static_cast<uint16_t>(rec[i].query_keypoint);
+      __syncthreads();
       for (int i = tid; i < R; i += THREADS) {
         uint8_t distinct = 0;
-        if (s.a1[i] != kNone16) {
+        const uint16_t g = s.a1[i];
+        if (g != kNone16) {
           distinct = 1;
-          const mlc_match me = rec[i];
+          const uint16_t la = s.a4[i], kp = qkp[i];
           for (int d = -(a.k - 1); d <= a.k - 1; ++d) {
             const int j = i + d;
-            if (d == 0 || j < 0 || j >= R || s.a1[j] == kNone16) continue;
-            const mlc_match o = rec[j];
+            if (d == 0 || j < 0 || j >= R || s.a1[j] != g || s.a4[j] != la || qkp[j] != kp) continue;
+            const mlc_match me = rec[i], o = rec[j];
             if (o.query_frame == me.query_frame && o.query_keypoint == me.query_keypoint &&
                 o.db_keyframe == me.db_keyframe && o.landmark == me.landmark &&
                 o.db_descriptor < me.db_descriptor)
@@ -384,12 +402,20 @@ __global__ void __launch_bounds__(THREADS, (THREADS <= 512 ? 2 : 1)) covis_kerne
         cnt[b] = static_cast<uint16_t>(c);
       }
       __syncthreads();
+      // most roots are singletons (a keyframe that shares no landmark with another): only roots that some
+      // other group points at walk the groups for their members
+      for (int b = tid; b < n_eval; b += THREADS) s.f1[b] = 0;
+      __syncthreads();
+      for (int b = tid; b < n_eval; b += THREADS)
+        if (K[b] != b) s.f1[K[b]] = 1;  // same value from every writer
+      __syncthreads();
       unsigned long long best = 0;
       for (int r = tid; r < n_eval; r += THREADS) {
         if (K[r] != r) continue;  // not a root
-        unsigned size = 0;
-        for (int b = r; b < n_eval; ++b)
-          if (K[b] == r) size += cnt[b];
+        unsigned size = cnt[r];
+        if (s.f1[r])
+          for (int b = r + 1; b < n_eval; ++b)
+            if (K[b] == r) size += cnt[b];
         // larger size wins; ties -> smaller root
         const unsigned long long cand = (static_cast<unsigned long long>(size) << 16) | (0xFFFFu - r);
         if (cand > best) best = cand;
@@ -412,11 +438,11 @@ __global__ void __launch_bounds__(THREADS, (THREADS <= 512 ? 2 : 1)) covis_kerne
         for (int i = tid; i < R; i += THREADS) {
           uint8_t keep = s.f1[i];
           if (keep && unique) {
-            const mlc_match me = rec[i];
+            const uint16_t la = s.a4[i], kp = qkp[i];
             for (int d = -(a.k - 1); d <= a.k - 1; ++d) {
               const int o_i = i + d;
-              if (d == 0 || o_i < 0 || o_i >= R || !s.f1[o_i]) continue;
-              const mlc_match o = rec[o_i];
+              if (d == 0 || o_i < 0 || o_i >= R || !s.f1[o_i] || s.a4[o_i] != la || qkp[o_i] != kp) continue;
+              const mlc_match me = rec[i], o = rec[o_i];
               if (o.query_frame == me.query_frame && o.query_keypoint == me.query_keypoint &&
                   o.landmark == me.landmark && o.db_descriptor < me.db_descriptor)
                 keep = 0;
@@ -434,10 +460,11 @@ __global__ void __launch_bounds__(THREADS, (THREADS <= 512 ? 2 : 1)) covis_kerne
             [&](int i, int pos, bool f) {
               if (!f) return;
               const mlc_match me = rec[i];
+              const uint16_t kp = qkp[i];
               int before = 0, smaller = 0;
               for (int d = -(a.k - 1); d <= a.k - 1; ++d) {
                 const int o_i = i + d;
-                if (d == 0 || o_i < 0 || o_i >= R || !s.f2[o_i]) continue;
+                if (d == 0 || o_i < 0 || o_i >= R || !s.f2[o_i] || qkp[o_i] != kp) continue;
                 const mlc_match o = rec[o_i];
                 if (o.query_frame != me.query_frame || o.query_keypoint != me.query_keypoint) continue;
                 if (d < 0) ++before;
@@ -507,6 +534,17 @@ __global__ void compact_matches_kernel(const mlc_match* __restrict__ in, const C
 
 }  // namespace
 
+// Resident CTAs per SM of the kernel LaunchCovis picks (the caller sizes its grid with it).
+int CovisCtasPerSm(int max_matches) {
+  // one 1024-thread CTA per SM (measured on the headline step: 0.92 ms against 1.02 ms with two 512-thread
+  // CTAs: the frame finishes sooner and the last wave is finer); MLC_COVIS_THREADS=512 selects the latter
+  static const bool narrow = [] {
+    const char* env = getenv("MLC_COVIS_THREADS");
+    return env && atoi(env) == 512;
+  }();
+  return (max_matches > 4096 || !narrow) ? 1 : 2;
+}
+
 size_t CovisScratchMatches(int max_matches, int grid) {
   return static_cast<size_t>(max_matches > 4096 ? 8192 : 4096) * grid;
 }
@@ -515,7 +553,13 @@ cudaError_t LaunchCovis(const CovisArgs& a, int max_matches, int grid, cudaStrea
   if (a.num_items <= 0) return cudaSuccess;
   if (max_matches > 8192 || a.k > 16) return cudaErrorInvalidValue;
   cudaError_t e;
-  if (max_matches <= 4096) {
+  if (max_matches <= 4096 && CovisCtasPerSm(max_matches) == 1) {
+    auto fn = covis_kernel<4096, 1024>;
+    e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             static_cast<int>(sizeof(CovisSmem<4096>)));
+    if (e != cudaSuccess) return e;
+    fn<<<grid, 1024, sizeof(CovisSmem<4096>), stream>>>(a);
+  } else if (max_matches <= 4096) {
     auto fn = covis_kernel<4096, 512>;
     e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              static_cast<int>(sizeof(CovisSmem<4096>)));

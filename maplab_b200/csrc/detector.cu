@@ -22,7 +22,8 @@ bool Detector::Cuda(cudaError_t e, const char* what, std::string* err) const {
 Detector::~Detector() {
   if (d_tree_blob_) cudaFree(d_tree_blob_);
   if (d_pq_blob_) cudaFree(d_pq_blob_);
-  if (proj_.b_image) cudaFree(proj_.b_image);
+  for (int8_t* p : proj_.b_image)
+    if (p) cudaFree(p);
   lists_.Free();
   DevBuf* bufs[] = {&d_db_cells_, &d_desc_kf_, &d_kf_meta_, &d_q_,    &d_cells_,
                     &d_idx_,      &d_dist_,    &d_bits_,    &d_stats_};
@@ -259,7 +260,7 @@ int Detector::NumNeighbors() const {
 
 bool Detector::ProjectDevice(const uint8_t* d_bits, int bytes_per_desc, int64_t n, float* d_out,
                              cudaStream_t stream, std::string* err) {
-  if (!proj_.b_image) {
+  if (!proj_.fp) {
     *err = "projection matrix shape unsupported by the tensor-core kernel (need <= 512 columns, <= 12 rows)";
     return false;
   }

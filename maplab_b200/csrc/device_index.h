@@ -82,14 +82,14 @@ cudaError_t LaunchMergeTopk(const int32_t* idx_lists, const float* dist_lists, i
 // B operand image of the projection GEMM: kProjNPad rows x (kp_padded bytes), already arranged in
 // the shared-memory core-matrix layout the kernel uses (see projection_kernel.cu).
 struct ProjectionDevice {
-  int8_t* b_image = nullptr;  // device
-  uint32_t b_bytes = 0;
+  int8_t* b_image[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // device; index = 16-byte chunks per descriptor
+  const FixedProjection* fp = nullptr;  // host copy the images are built from (outlives this struct's users)
   int dim = 0;
   int kp = 0;               // descriptor bits consumed
   int32_t shift[16] = {0};  // per output dim
 };
 cudaError_t BuildProjectionDevice(const FixedProjection& fp, ProjectionDevice* out);
-cudaError_t LaunchProjection(const ProjectionDevice& pd, const uint8_t* d_bits, int bytes_per_desc,
+cudaError_t LaunchProjection(ProjectionDevice& pd, const uint8_t* d_bits, int bytes_per_desc,
                              int64_t n, float* d_out, int sm_count, cudaStream_t stream);
 
 }  // namespace mlc

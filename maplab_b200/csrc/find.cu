@@ -151,7 +151,7 @@ bool Detector::FindOnDevice(const mlc_frame* frames, int64_t num_frames, const i
   }
   const int nf = static_cast<int>(num_frames);
   const int nv2 = static_cast<int>(vitems.size());
-  const int grid = std::min(nf, sm_count_ * 2);
+  const int grid = std::min(nf, sm_count_ * CovisCtasPerSm(max_slots));
   // device buffers: [0] items, [1] pass-1 matches, [2] counts (pass 1 then pass 2), [3] scratch,
   // [4] pass-1 offsets as long long, [5] final matches, [6] final offsets / vertex items
   DevBuf &b_items = d_covis_[0], &b_out = d_covis_[1], &b_cnt = d_covis_[2], &b_scr = d_covis_[3],
@@ -204,7 +204,7 @@ bool Detector::FindOnDevice(const mlc_frame* frames, int64_t num_frames, const i
     b.in_offsets = b_off.as<long long>();
     b.out_counts = b_cnt.as<int>() + nf;
     // the offsets upload must not be overwritten before the kernel ran: offs lives until the sync below
-    if (!Cuda(LaunchCovis(b, max_slots, std::min(nv2, sm_count_ * 2), stream_), "vertex covisibility kernel", err))
+    if (!Cuda(LaunchCovis(b, max_slots, std::min(nv2, sm_count_ * CovisCtasPerSm(max_slots)), stream_), "vertex covisibility kernel", err))
       return false;
     if (!Cuda(cudaStreamSynchronize(stream_), "covisibility", err)) return false;
   }

@@ -3,14 +3,23 @@
 // descriptor-projection/include/descriptor-projection/descriptor-projection.h:92-115).
 //
 // Y[n][d] = sum_k P[d][k] * bit_k(desc n) as an exact integer GEMM on the 5th-gen tensor cores:
-//   A (128 x K)  = descriptor bits expanded to u8 {0,1} by the producer warps, written straight
-//                  into shared memory in the UMMA K-major core-matrix layout;
-//   B (48 x K)   = the fixed-point projection matrix split into 4 balanced base-256 s8 digits
-//                  (row 4*d + j = digit j of output dim d; rows >= 4*dim are zero);
-//   D (128 x 48) = s32 accumulators in TMEM (tcgen05.mma kind::i8), double buffered;
-//   epilogue     = tcgen05.ld, recombine the digits in int64, ONE rounding to fp32, store.
-// Persistent CTAs (one per SM), warp-specialised: 4 epilogue warps, 1 MMA/TMEM warp,
-// 8 bit-expansion warps; mbarrier pipelines between the roles.
+//   A (128 x K)  = the descriptor bytes, once per bit plane i = 0..7, each copy masked with 1 << i: the u8
+//                  element of (plane i, byte j) is (byte_j & (1 << i)) in {0, 2^i}. K = 8 planes x bytes per
+//                  descriptor (512 for FREAK), written by the producer warps straight into the UMMA K-major
+//                  core-matrix layout — one AND per 4 bytes and plane instead of a bit-to-byte expansion;
+//   B (64 x K)   = the fixed-point projection matrix: the element of (plane i, byte j) is
+//                  P_int[d][8 j + i] * 2^(7 - i), so that a * b = 2^7 * bit * P_int for every plane, split into
+//                  5 balanced base-256 s8 digits (row 5 d + t = digit t of output dim d; other rows zero);
+//   D (128 x 64) = s32 accumulators in TMEM (tcgen05.mma kind::i8), double buffered;
+//   epilogue     = tcgen05.ld, recombine the digits in int64, ONE rounding to fp32 (the 2^-7 and the
+//                  fixed-point scale are exact powers of two), bulk store.
+// Data movement is TMA: the raw 128-descriptor tile (contiguous in global memory) arrives with one
+// cp.async.bulk into a 4-stage shared-memory ring (mbarrier complete_tx), the projected tile leaves with one
+// cp.async.bulk store from shared memory.
+// Persistent CTAs (one per SM), warp-specialised: 4 epilogue warps, 1 MMA/TMEM warp, 8 producer warps,
+// 1 TMA load warp; mbarrier pipelines between the roles.
+#include <mutex>
+
 #include "device_index.h"
 #include "ptx.cuh"
 
@@ -18,31 +27,42 @@ namespace mlc {
 namespace {
 
 constexpr int kTileM = 128;
-constexpr int kMaxKBytes = 512;                 // descriptor bits (<= 512)
-constexpr int kASlotBytes = kTileM * kMaxKBytes;  // 64 KB: u8 per bit
-constexpr int kASlots = 3;
+constexpr int kMaxDescBytes = 64;               // descriptor bytes (<= 512 bits)
+constexpr int kMaxK = 8 * kMaxDescBytes;        // 512 u8 elements per row
+constexpr int kASlotBytes = kTileM * kMaxK;     // 64 KB
+constexpr int kASlots = 2;
 constexpr int kALbo = 16 * 128;                 // K-adjacent core matrices: 16 row groups apart
 constexpr int kASbo = 128;                      // M-adjacent 8-row groups
-constexpr int kBRowGroups = kProjNPad / 8;      // 6
-constexpr int kBLbo = kBRowGroups * 128;        // 768
+constexpr int kN = 64;                          // UMMA N: >= dim * digits, multiple of 16
+constexpr int kDigits = 5;                      // |P_int * 2^7| <= 2^33: five balanced base-256 digits
+constexpr int kBRowGroups = kN / 8;             // 8
+constexpr int kBLbo = kBRowGroups * 128;        // 1024
 constexpr int kBSbo = 128;
-constexpr int kBBytes = (kMaxKBytes / 16) * kBLbo;  // 24576
+constexpr int kBBytes = (kMaxK / 16) * kBLbo;   // 32 KB
+constexpr int kRawStages = 4;
+constexpr int kRawBytes = kTileM * kMaxDescBytes;  // 8 KB
 constexpr int kEpilogueWarps = 4;
 constexpr int kMmaWarp = 4;
 constexpr int kProducerWarps = 8;
 constexpr int kRowGroupsPerWarp = (kTileM / 8) / kProducerWarps;  // 8-row core-matrix groups per producer warp
 constexpr int kFirstProducerWarp = 5;
-constexpr int kThreads = (kFirstProducerWarp + kProducerWarps) * 32;  // 416
+constexpr int kLoadWarp = kFirstProducerWarp + kProducerWarps;    // 13
+constexpr int kThreads = (kLoadWarp + 1) * 32;                    // 448
 constexpr int kAccStages = 2;
 constexpr int kAccCols = 64;                    // TMEM columns per accumulator stage
 constexpr int kTmemCols = 128;
-constexpr int kMaxDim = kProjNPad / kProjDigits;  // 12
+constexpr int kMaxDim = kN / kDigits;           // 12
+
 
 struct Smem {
   alignas(128) uint8_t a[kASlots][kASlotBytes];
   alignas(128) int8_t b[kBBytes];
+  alignas(128) uint8_t raw[kRawStages][kRawBytes];
+  alignas(128) float out[kAccStages][kTileM * kMaxDim];
   alignas(8) uint64_t full[kASlots];
   uint64_t empty[kASlots];
+  uint64_t raw_full[kRawStages];
+  uint64_t raw_empty[kRawStages];
   uint64_t acc_full[kAccStages];
   uint64_t acc_empty[kAccStages];
   uint32_t tmem_base;
@@ -54,21 +74,16 @@ struct ProjArgs {
   float* out;
   int64_t n;
   int bytes_per_desc;  // 16-byte multiple, <= 64
-  int k_steps;         // MMAs per tile = 8 * bytes_per_desc / 32
+  int k_steps;         // MMAs per tile = (8 planes * bytes_per_desc) / 32
   int dim;
-  float scale[kMaxDim];  // 2^-shift[d]
+  int bulk_io;         // pointers are 16-byte aligned: tiles move with cp.async.bulk
+  float scale[kMaxDim];  // 2^-(shift[d] + 7)
 };
 
-// u8 instruction descriptor: D = s32, A = u8, B = s8, both K-major, N = 48, M = 128.
+// u8 x s8 instruction descriptor: D = s32, A = u8, B = s8, both K-major, N = 64, M = 128.
 constexpr uint32_t kIdesc = (2u << 4) | (0u << 7) | (1u << 10) |
-                            (static_cast<uint32_t>(kProjNPad >> 3) << 17) |
+                            (static_cast<uint32_t>(kN >> 3) << 17) |
                             (static_cast<uint32_t>(kTileM >> 4) << 24);
-
-// 4 descriptor bits -> 4 bytes {0,1}, LSB first: bit i lands at bit 8*i (no carries since the
-// partial products i + 7*j are distinct for i, j in 0..3).
-__device__ __forceinline__ uint32_t Expand4(uint32_t nibble) {
-  return (nibble * 0x00204081u) & 0x01010101u;
-}
 
 __global__ void __launch_bounds__(kThreads, 1) projection_kernel(ProjArgs args) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -77,6 +92,8 @@ __global__ void __launch_bounds__(kThreads, 1) projection_kernel(ProjArgs args) 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int64_t num_tiles = (args.n + kTileM - 1) / kTileM;
+  const int nkq = args.bytes_per_desc >> 4;  // 16-byte chunks per descriptor
+  const uint32_t tile_bytes = static_cast<uint32_t>(kTileM) * args.bytes_per_desc;
 
   // ---- one-time setup ----
   for (int i = threadIdx.x * 16; i < kBBytes; i += kThreads * 16)
@@ -86,6 +103,10 @@ __global__ void __launch_bounds__(kThreads, 1) projection_kernel(ProjArgs args) 
       for (int i = 0; i < kASlots; ++i) {
         ptx::mbar_init(&s.full[i], kProducerWarps * 32);
         ptx::mbar_init(&s.empty[i], 1);
+      }
+      for (int i = 0; i < kRawStages; ++i) {
+        ptx::mbar_init(&s.raw_full[i], 1);
+        ptx::mbar_init(&s.raw_empty[i], kProducerWarps * 32);
       }
       for (int i = 0; i < kAccStages; ++i) {
         ptx::mbar_init(&s.acc_full[i], 1);
@@ -103,67 +124,68 @@ __global__ void __launch_bounds__(kThreads, 1) projection_kernel(ProjArgs args) 
   ptx::tc_fence_after();
   const uint32_t tmem_base = s.tmem_base;
 
-  if (warp >= kFirstProducerWarp) {
-    // ================= bit-expansion producers =================
+  if (warp == kLoadWarp) {
+    // ================= TMA loads: one bulk copy per 128-descriptor tile =================
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        const uint32_t st = it % kRawStages;
+        const uint32_t phase = (it / kRawStages) & 1u;
+        ptx::mbar_wait(&s.raw_empty[st], phase ^ 1u);
+        const int64_t row0 = tile * kTileM;
+        const int64_t rows = (args.n - row0) < kTileM ? (args.n - row0) : kTileM;
+        const uint32_t bytes = static_cast<uint32_t>(rows) * args.bytes_per_desc;  // multiple of 16
+        const uint8_t* src = args.bits + row0 * args.bytes_per_desc;
+        if (args.bulk_io) {
+          ptx::mbar_arrive_expect_tx(&s.raw_full[st], bytes);
+          ptx::bulk_load(s.raw[st], src, bytes, &s.raw_full[st]);
+        } else {
+          // unaligned caller buffer: plain 4-byte copies by this thread (correct, slow; never the bench path)
+          for (uint32_t i = 0; i < bytes; ++i) s.raw[st][i] = src[i];
+          ptx::mbar_arrive(&s.raw_full[st]);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp >= kFirstProducerWarp) {
+    // ================= plane-mask producers =================
     const int pw = warp - kFirstProducerWarp;
     const int r = lane & 7;    // row inside the 8-row core matrix
-    const int kq = lane >> 3;  // 128-bit quarter of the descriptor
-    const int nkq = args.bytes_per_desc >> 4;
-    // The descriptor words of kPrefetch tiles are in flight per warp (registers): with one tile
-    // the producers were bound by the latency of their own loads (ncu r1r: long-scoreboard 4.7,
-    // DRAM 12 %).
-    constexpr int kPrefetch = 4;
-    uint4 w[kPrefetch][kRowGroupsPerWarp];
-    auto load_tile = [&](int64_t tile, uint4 (&ww)[kRowGroupsPerWarp]) {
+    const int kq = lane >> 3;  // 16-byte chunk of the descriptor
+    uint32_t it = 0;
+    for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const uint32_t slot = it % kASlots;
+      const uint32_t phase = (it / kASlots) & 1u;
+      const uint32_t st = it % kRawStages;
+      const uint32_t raw_phase = (it / kRawStages) & 1u;
+      const int64_t rows_left = args.n - tile * kTileM;
+      ptx::mbar_wait(&s.raw_full[st], raw_phase);
+      uint4 w[kRowGroupsPerWarp];
 #pragma unroll
       for (int h = 0; h < kRowGroupsPerWarp; ++h) {
-        const int rg = pw + h * kProducerWarps;
-        const int64_t row = tile * kTileM + rg * 8 + r;
-        ww[h] = make_uint4(0, 0, 0, 0);
-        if (row < args.n && kq < nkq)
-          ww[h] = ptx::ldg_nc_v4(args.bits + row * args.bytes_per_desc + kq * 16);
+        const int row = (pw + h * kProducerWarps) * 8 + r;
+        w[h] = make_uint4(0, 0, 0, 0);
+        if (row < rows_left && kq < nkq)
+          w[h] = *reinterpret_cast<const uint4*>(s.raw[st] + row * args.bytes_per_desc + kq * 16);
       }
-    };
+      ptx::mbar_arrive(&s.raw_empty[st]);  // the raw stage is in registers
+      ptx::mbar_wait(&s.empty[slot], phase ^ 1u);
+      if (kq < nkq) {
 #pragma unroll
-    for (int p = 0; p < kPrefetch; ++p) load_tile(blockIdx.x + static_cast<int64_t>(p) * gridDim.x, w[p]);
-    uint32_t it = 0;
-    for (int64_t tile0 = blockIdx.x; tile0 < num_tiles; tile0 += static_cast<int64_t>(kPrefetch) * gridDim.x) {
+        for (int h = 0; h < kRowGroupsPerWarp; ++h) {
+          const int rg = pw + h * kProducerWarps;
+          uint8_t* dst = s.a[slot] + kq * kALbo + rg * kASbo + r * 16;
 #pragma unroll
-      for (int p = 0; p < kPrefetch; ++p) {
-        const int64_t tile = tile0 + static_cast<int64_t>(p) * gridDim.x;
-        if (tile >= num_tiles) break;
-        const uint32_t slot = it % kASlots;
-        const uint32_t phase = (it / kASlots) & 1u;
-        ++it;
-        ptx::mbar_wait(&s.empty[slot], phase ^ 1u);
-        if (kq < nkq) {
-#pragma unroll
-          for (int h = 0; h < kRowGroupsPerWarp; ++h) {
-            const int rg = pw + h * kProducerWarps;
-            uint8_t* dst = s.a[slot] + (kq * 8) * kALbo + rg * kASbo + r * 16;
-            const uint32_t words[4] = {w[p][h].x, w[p][h].y, w[p][h].z, w[p][h].w};
-#pragma unroll
-            for (int wi = 0; wi < 4; ++wi) {
-              const uint32_t x = words[wi];
-              const uint32_t even = x & 0x0F0F0F0Fu;         // nibbles 0,2,4,6 in bytes 0..3
-              const uint32_t odd = (x >> 4) & 0x0F0F0F0Fu;   // nibbles 1,3,5,7
-              // 16 bits -> 16 bytes -> one 16-byte store; two stores per 32-bit word
-#pragma unroll
-              for (int half = 0; half < 2; ++half) {
-                uint4 o;
-                o.x = Expand4(__byte_perm(even, 0, 0x4440 + (2 * half)));
-                o.y = Expand4(__byte_perm(odd, 0, 0x4440 + (2 * half)));
-                o.z = Expand4(__byte_perm(even, 0, 0x4441 + (2 * half)));
-                o.w = Expand4(__byte_perm(odd, 0, 0x4441 + (2 * half)));
-                *reinterpret_cast<uint4*>(dst + (wi * 2 + half) * kALbo) = o;
-              }
-            }
+          for (int i = 0; i < 8; ++i) {
+            const uint32_t m = 0x01010101u << i;
+            *reinterpret_cast<uint4*>(dst + i * nkq * kALbo) =
+                make_uint4(w[h].x & m, w[h].y & m, w[h].z & m, w[h].w & m);
           }
         }
-        ptx::fence_proxy_async_smem();
-        ptx::mbar_arrive(&s.full[slot]);
-        load_tile(tile + static_cast<int64_t>(kPrefetch) * gridDim.x, w[p]);  // refill this register slot
       }
+      ptx::fence_proxy_async_smem();
+      ptx::mbar_arrive(&s.full[slot]);
+      (void)tile_bytes;
     }
   } else if (warp == kMmaWarp) {
     // ================= MMA issuer =================
@@ -198,10 +220,10 @@ __global__ void __launch_bounds__(kThreads, 1) projection_kernel(ProjArgs args) 
       const uint32_t acc_phase = (it / kAccStages) & 1u;
       ptx::mbar_wait(&s.acc_full[acc], acc_phase);
       ptx::tc_fence_after();
-      uint32_t v[kProjNPad];
+      uint32_t v[kN];
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + acc * kAccCols;
 #pragma unroll
-      for (int c = 0; c < kProjNPad / 8; ++c) {
+      for (int c = 0; c < kN / 8; ++c) {
         uint32_t t8[8];
         ptx::tmem_ld_32x32b_x8(taddr + c * 8, t8);
 #pragma unroll
@@ -210,29 +232,41 @@ __global__ void __launch_bounds__(kThreads, 1) projection_kernel(ProjArgs args) 
       ptx::tmem_ld_wait();
       ptx::tc_fence_before();
       ptx::mbar_arrive(&s.acc_empty[acc]);
-      const int64_t row = tile * kTileM + warp * 32 + lane;
-      if (row < args.n) {
-        float y[kMaxDim];
+      float y[kMaxDim];
 #pragma unroll
-        for (int d = 0; d < kMaxDim; ++d) {
-          long long accv = 0;
+      for (int d = 0; d < kMaxDim; ++d) {
+        long long accv = 0;
 #pragma unroll
-          for (int j = kProjDigits - 1; j >= 0; --j)
-            accv = accv * 256 + static_cast<int>(v[d * kProjDigits + j]);
-          y[d] = __ll2float_rn(accv) * args.scale[d];  // exact power-of-two scaling
+        for (int j = kDigits - 1; j >= 0; --j)
+          accv = accv * 256 + static_cast<int>(v[d * kDigits + j]);
+        y[d] = __ll2float_rn(accv) * args.scale[d];  // exact power-of-two scaling
+      }
+      const int64_t row0 = tile * kTileM;
+      const int64_t rows_left = args.n - row0;
+      const int row_in_tile = warp * 32 + lane;
+      const bool bulk = args.bulk_io && rows_left >= kTileM;  // whole tile: leaves with one bulk store
+      if (bulk) {
+        // the staging buffer of this accumulator stage was handed to the TMA two tiles ago
+        if (warp == 0 && lane == 0) ptx::bulk_wait_read<1>();
+        ptx::named_barrier_sync(1, kEpilogueWarps * 32);
+        float* o = s.out[acc] + row_in_tile * args.dim;
+#pragma unroll
+        for (int d = 0; d < kMaxDim; ++d)
+          if (d < args.dim) o[d] = y[d];
+        ptx::fence_proxy_async_smem();
+        ptx::named_barrier_sync(1, kEpilogueWarps * 32);
+        if (warp == 0 && lane == 0) {
+          ptx::bulk_store(args.out + row0 * args.dim, s.out[acc], static_cast<uint32_t>(kTileM) * args.dim * 4u);
+          ptx::bulk_commit();
         }
-        float* o = args.out + row * args.dim;
-        if ((args.dim & 1) == 0) {
+      } else if (row_in_tile < rows_left) {
+        float* o = args.out + (row0 + row_in_tile) * args.dim;
 #pragma unroll
-          for (int d = 0; d < kMaxDim; d += 2)
-            if (d < args.dim) *reinterpret_cast<float2*>(o + d) = make_float2(y[d], y[d + 1]);
-        } else {
-#pragma unroll
-          for (int d = 0; d < kMaxDim; ++d)
-            if (d < args.dim) o[d] = y[d];
-        }
+        for (int d = 0; d < kMaxDim; ++d)
+          if (d < args.dim) o[d] = y[d];
       }
     }
+    if (warp == 0 && lane == 0) ptx::bulk_wait_all();  // the bulk stores read shared memory until they retire
   }
 
   // ---- teardown ----
@@ -244,52 +278,88 @@ __global__ void __launch_bounds__(kThreads, 1) projection_kernel(ProjArgs args) 
   }
 }
 
+// v -> kDigits balanced base-256 digits (|digit| <= 128 except the last, which takes the rest).
+void SplitDigits(int64_t v, int8_t d[kDigits]) {
+  int64_t rest = v;
+  for (int j = 0; j < kDigits - 1; ++j) {
+    int64_t low = ((rest % 256) + 256) % 256;
+    if (low >= 128) low -= 256;
+    d[j] = static_cast<int8_t>(low);
+    rest = (rest - low) / 256;
+  }
+  d[kDigits - 1] = static_cast<int8_t>(rest);  // |v| <= 2^33 => |rest| <= 3
+}
+
 }  // namespace
 
-cudaError_t BuildProjectionDevice(const FixedProjection& fp, ProjectionDevice* out) {
-  if (fp.dim > kMaxDim || fp.dim > 16 || fp.kp > kMaxKBytes || fp.kp <= 0)
+// B operand image for descriptors of `nkq` 16-byte chunks: K block (plane i, chunk kq) = i * nkq + kq.
+cudaError_t BuildProjectionImage(const FixedProjection& fp, int nkq, int8_t** d_image) {
+  if (fp.dim > kMaxDim || fp.kp > 8 * 16 * nkq || fp.kp <= 0 || nkq < 1 || nkq > kMaxDescBytes / 16)
     return cudaErrorInvalidValue;
   std::vector<int8_t> img(kBBytes, 0);
   for (int d = 0; d < fp.dim; ++d) {
-    for (int k = 0; k < fp.kp; ++k) {
-      int8_t dig[kProjDigits];
-      SplitDigitsBase256(fp.p_int[static_cast<size_t>(d) * fp.kp + k], dig);
-      for (int j = 0; j < kProjDigits; ++j) {
-        const int n = d * kProjDigits + j;  // B row
+    for (int bit = 0; bit < fp.kp; ++bit) {
+      const int byte = bit >> 3, plane = bit & 7;
+      const int kb = plane * nkq + (byte >> 4);   // K block of 16 elements
+      const int k = kb * 16 + (byte & 15);
+      int8_t dig[kDigits];
+      SplitDigits(static_cast<int64_t>(fp.p_int[static_cast<size_t>(d) * fp.kp + bit]) << (7 - plane), dig);
+      for (int j = 0; j < kDigits; ++j) {
+        const int n = d * kDigits + j;  // B row
         const size_t at = static_cast<size_t>(k / 16) * kBLbo + (n / 8) * kBSbo + (n % 8) * 16 + (k % 16);
         img[at] = dig[j];
       }
     }
   }
-  if (out->b_image) cudaFree(out->b_image);
-  out->b_image = nullptr;
-  cudaError_t e = cudaMalloc(&out->b_image, kBBytes);
+  cudaError_t e = cudaMalloc(d_image, kBBytes);
   if (e != cudaSuccess) return e;
-  e = cudaMemcpy(out->b_image, img.data(), kBBytes, cudaMemcpyHostToDevice);
-  if (e != cudaSuccess) return e;
-  out->b_bytes = kBBytes;
+  return cudaMemcpy(*d_image, img.data(), kBBytes, cudaMemcpyHostToDevice);
+}
+
+cudaError_t BuildProjectionDevice(const FixedProjection& fp, ProjectionDevice* out) {
+  if (fp.dim > kMaxDim || fp.dim > 16 || fp.kp > kMaxK || fp.kp <= 0) return cudaErrorInvalidValue;
+  for (int8_t*& p : out->b_image) {
+    if (p) cudaFree(p);
+    p = nullptr;
+  }
+  out->fp = &fp;
   out->dim = fp.dim;
   out->kp = fp.kp;
   for (int d = 0; d < fp.dim; ++d) out->shift[d] = fp.shift[d];
-  return cudaSuccess;
+  // the image of the natural descriptor size now, other sizes on first use
+  const int nkq = (fp.kp + 127) / 128;
+  return BuildProjectionImage(fp, nkq, &out->b_image[nkq]);
 }
 
-cudaError_t LaunchProjection(const ProjectionDevice& pd, const uint8_t* d_bits, int bytes_per_desc,
+cudaError_t LaunchProjection(ProjectionDevice& pd, const uint8_t* d_bits, int bytes_per_desc,
                              int64_t n, float* d_out, int sm_count, cudaStream_t stream) {
   if (n <= 0) return cudaSuccess;
-  if (bytes_per_desc % 16 != 0 || bytes_per_desc <= 0 || bytes_per_desc > kMaxKBytes / 8)
+  if (bytes_per_desc % 16 != 0 || bytes_per_desc <= 0 || bytes_per_desc > kMaxDescBytes)
     return cudaErrorInvalidValue;
   if (pd.kp > bytes_per_desc * 8) return cudaErrorInvalidValue;
+  const int nkq = bytes_per_desc / 16;
+  if (!pd.b_image[nkq]) {
+    static std::mutex mu;
+    std::lock_guard<std::mutex> lock(mu);
+    if (!pd.b_image[nkq]) {
+      cudaError_t e = BuildProjectionImage(*pd.fp, nkq, &pd.b_image[nkq]);
+      if (e != cudaSuccess) return e;
+    }
+  }
   ProjArgs a;
   a.bits = d_bits;
-  a.b_image = pd.b_image;
+  a.b_image = pd.b_image[nkq];
   a.out = d_out;
   a.n = n;
   a.bytes_per_desc = bytes_per_desc;
-  a.k_steps = bytes_per_desc * 8 / 32;
+  a.k_steps = 8 * bytes_per_desc / 32;
   a.dim = pd.dim;
+  a.bulk_io = (reinterpret_cast<uintptr_t>(d_bits) % 16 == 0 && reinterpret_cast<uintptr_t>(d_out) % 16 == 0 &&
+               (static_cast<size_t>(kTileM) * pd.dim * 4) % 16 == 0)
+                  ? 1
+                  : 0;
   for (int d = 0; d < kMaxDim; ++d)
-    a.scale[d] = d < pd.dim ? ldexpf(1.0f, -pd.shift[d]) : 0.f;
+    a.scale[d] = d < pd.dim ? ldexpf(1.0f, -(pd.shift[d] + 7)) : 0.f;
   cudaError_t e = cudaFuncSetAttribute(projection_kernel,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        static_cast<int>(sizeof(Smem) + 128));
