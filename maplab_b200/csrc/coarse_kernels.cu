@@ -12,6 +12,10 @@
 // execute the same code most of the time; lanes that finish pull the next work item of their
 // warp's range (persistent lanes). Blocks with even/odd index own half 0 / 1 and stage only that
 // half's tree in shared memory; the per-lane result heaps live in registers.
+#include <cub/cub.cuh>
+
+#include <cstdlib>
+
 #include "device_index.h"
 #include "ptx.cuh"
 
@@ -44,7 +48,7 @@ __device__ __forceinline__ void Put(float (&v)[D], uint32_t d, float x) {
 template <int D, int KK>
 __global__ void __launch_bounds__(kThreads, 4)
 kd_search_kernel(CoarseParams p, const float* __restrict__ q, int64_t n, int kk1, int kk2,
-                 int32_t* __restrict__ out_idx, float* __restrict__ out_val) {
+                 const uint32_t* __restrict__ order, int32_t* __restrict__ out_idx, float* __restrict__ out_val) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int half = blockIdx.x & 1;
   const int kk = half ? kk2 : kk1;
@@ -100,7 +104,11 @@ kd_search_kernel(CoarseParams p, const float* __restrict__ q, int64_t n, int kk1
     if (idle) {
       if (state == kIdle) {
         item = warp_next + __popc(idle & lanemask_lt);
-        if (item < warp_end) {
+        const bool have = item < warp_end;
+        // processing order: queries that fall into the same leaf first are neighbours, so the lanes of a
+        // warp walk (nearly) the same path; results go to the query's own row
+        if (have && order) item = order[static_cast<size_t>(half) * n + item];
+        if (have) {
           const float* src = q + item * (2 * D) + half * D;
 #pragma unroll
           for (int d = 0; d < D; ++d) {
@@ -232,6 +240,31 @@ kd_search_kernel(CoarseParams p, const float* __restrict__ q, int64_t n, int kk1
   }
 }
 
+// Leaf a query reaches by plain descent (no backtracking) in its half's tree: the sort key that makes
+// neighbouring work items traverse alike. keys[half * n + i], vals[half * n + i] = i.
+template <int D>
+__global__ void __launch_bounds__(256) kd_leaf_key_kernel(CoarseParams p, const float* __restrict__ q, int64_t n,
+                                                          uint32_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+  const int64_t t = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (t >= 2 * n) return;
+  const int half = t >= n ? 1 : 0;
+  const int64_t i = t - static_cast<int64_t>(half) * n;
+  const KdNodeDev* nodes = half ? p.nodes2 : p.nodes1;
+  const float* src = q + i * (2 * D) + half * D;
+  float qv[D];
+#pragma unroll
+  for (int d = 0; d < D; ++d) qv[d] = __ldg(src + d);
+  uint32_t node = 0;
+  for (int depth = 0; depth < kMaxStack; ++depth) {
+    const KdNodeDev nd = nodes[node];
+    if (nd.dim == static_cast<uint32_t>(D)) break;
+    const float off = __fsub_rn(Pick<D>(qv, nd.dim), __uint_as_float(nd.cut_or_bucket));
+    node = (off > 0.f) ? nd.child_or_size : node + 1;
+  }
+  keys[t] = (static_cast<uint32_t>(half) << 16) | node;  // < 2^16 nodes per tree (checked on the host)
+  vals[t] = static_cast<uint32_t>(i);
+}
+
 // MultiSequenceAlgorithm: pop the pairs (i1, i2) in ascending (d1[i1] + d2[i2], i1, i2).
 __global__ void __launch_bounds__(128)
 multi_sequence_kernel(const int32_t* __restrict__ h_idx, const float* __restrict__ h_val, int64_t n,
@@ -301,7 +334,7 @@ multi_sequence_kernel(const int32_t* __restrict__ h_idx, const float* __restrict
 
 template <int D, int KK>
 cudaError_t LaunchSearchK(const CoarseParams& p, const float* d_q, int64_t n, int kk1, int kk2,
-                          int32_t* h_idx, float* h_val, int sm_count, cudaStream_t stream) {
+                          const uint32_t* order, int32_t* h_idx, float* h_val, int sm_count, cudaStream_t stream) {
   const uint32_t tree_bytes =
       p.stage_in_smem ? max(p.off_nodes2, p.packed_bytes - p.off_nodes2) : 0u;
   const size_t smem = tree_bytes;
@@ -317,25 +350,68 @@ cudaError_t LaunchSearchK(const CoarseParams& p, const float* d_q, int64_t n, in
   if (blocks_per_half > needed) blocks_per_half = needed;
   if (blocks_per_half < 1) blocks_per_half = 1;
   kd_search_kernel<D, KK><<<static_cast<unsigned>(2 * blocks_per_half), kThreads, smem, stream>>>(
-      p, d_q, n, kk1, kk2, h_idx, h_val);
+      p, d_q, n, kk1, kk2, order, h_idx, h_val);
   CountLaunch();
   return cudaGetLastError();
 }
 
+// Experiment, off by default (MLC_COARSE_SORT=1 switches it on; results do not depend on it): work items
+// sorted by the leaf their query falls into, so that the lanes of a warp start on the same path. Measured
+// on the headline step (500 k queries x 2 halves): 1.02 ms with the sort against 0.90 ms without — the
+// descent + radix sort cost more than the better convergence gains. Sort buffers: keys / values, in and
+// out, behind the word lists in `scratch`.
+constexpr int64_t kSortMinItems = 8192;
+bool SortEnabled() {
+  static const bool on = [] {
+    const char* env = getenv("MLC_COARSE_SORT");
+    return env && atoi(env) == 1;
+  }();
+  return on;
+}
+size_t SortTempBytes(int64_t n) {
+  size_t bytes = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, bytes, static_cast<const uint32_t*>(nullptr), static_cast<uint32_t*>(nullptr),
+                                  static_cast<const uint32_t*>(nullptr), static_cast<uint32_t*>(nullptr),
+                                  static_cast<int>(2 * n), 0, 17);
+  return bytes;
+}
+
 template <int D>
 cudaError_t LaunchSearch(const CoarseParams& p, const float* d_q, int64_t n, int kk1, int kk2,
-                         int32_t* h_idx, float* h_val, int sm_count, cudaStream_t stream) {
+                         int32_t* h_idx, float* h_val, void* sort_scratch, int sm_count, cudaStream_t stream) {
+  const uint32_t* order = nullptr;
+  if (sort_scratch) {
+    uint32_t* keys = static_cast<uint32_t*>(sort_scratch);
+    uint32_t* vals = keys + 2 * n;
+    uint32_t* keys_out = vals + 2 * n;
+    uint32_t* vals_out = keys_out + 2 * n;
+    void* tmp = vals_out + 2 * n;
+    size_t tmp_bytes = SortTempBytes(n);
+    kd_leaf_key_kernel<D><<<static_cast<unsigned>((2 * n + 255) / 256), 256, 0, stream>>>(p, d_q, n, keys, vals);
+    CountLaunch();
+    cudaError_t e = cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, keys, keys_out, vals, vals_out,
+                                                    static_cast<int>(2 * n), 0, 17, stream);
+    if (e != cudaSuccess) return e;
+    CountLaunch();
+    order = vals_out;
+  }
   const int kk_max = max(kk1, kk2);
-  if (kk_max <= 1) return LaunchSearchK<D, 1>(p, d_q, n, kk1, kk2, h_idx, h_val, sm_count, stream);
-  if (kk_max <= 10) return LaunchSearchK<D, 10>(p, d_q, n, kk1, kk2, h_idx, h_val, sm_count, stream);
-  return LaunchSearchK<D, 16>(p, d_q, n, kk1, kk2, h_idx, h_val, sm_count, stream);
+  if (kk_max <= 1) return LaunchSearchK<D, 1>(p, d_q, n, kk1, kk2, order, h_idx, h_val, sm_count, stream);
+  if (kk_max <= 10) return LaunchSearchK<D, 10>(p, d_q, n, kk1, kk2, order, h_idx, h_val, sm_count, stream);
+  return LaunchSearchK<D, 16>(p, d_q, n, kk1, kk2, order, h_idx, h_val, sm_count, stream);
+}
+
+size_t WordListBytes(int64_t n, int kk1, int kk2) {
+  return ((static_cast<size_t>(n) * (kk1 + kk2) * 4 + 127) & ~static_cast<size_t>(127)) * 2;
 }
 
 }  // namespace
 
 size_t CoarseScratchBytes(const CoarseParams& p, int64_t n, int num_words) {
   const int kk1 = min(p.num_words1, num_words), kk2 = min(p.num_words2, num_words);
-  return static_cast<size_t>(n) * (kk1 + kk2) * 8 + 256;
+  size_t bytes = WordListBytes(n, kk1, kk2) + 256;
+  if (SortEnabled() && n >= kSortMinItems) bytes += static_cast<size_t>(n) * 2 * 4 * 4 + SortTempBytes(n) + 256;
+  return bytes;
 }
 
 cudaError_t LaunchCoarseWords(const CoarseParams& p, const float* d_q, int64_t n, int num_words,
@@ -346,11 +422,14 @@ cudaError_t LaunchCoarseWords(const CoarseParams& p, const float* d_q, int64_t n
   int32_t* h_idx = static_cast<int32_t*>(scratch);
   float* h_val = reinterpret_cast<float*>(static_cast<unsigned char*>(scratch) +
                                           ((static_cast<size_t>(n) * (kk1 + kk2) * 4 + 127) & ~static_cast<size_t>(127)));
+  void* sort_scratch = nullptr;
+  if (SortEnabled() && n >= kSortMinItems && p.num_words1 < 65536 && p.num_words2 < 65536)
+    sort_scratch = static_cast<unsigned char*>(scratch) + ((WordListBytes(n, kk1, kk2) + 255) & ~static_cast<size_t>(255));
   cudaError_t e;
   switch (p.sub_dim) {
 #define MLC_CASE(D)                                                                     \
   case D:                                                                               \
-    e = LaunchSearch<D>(p, d_q, n, kk1, kk2, h_idx, h_val, sm_count, stream);           \
+    e = LaunchSearch<D>(p, d_q, n, kk1, kk2, h_idx, h_val, sort_scratch, sm_count, stream); \
     break;
     MLC_CASE(1) MLC_CASE(2) MLC_CASE(3) MLC_CASE(4) MLC_CASE(5) MLC_CASE(6) MLC_CASE(7) MLC_CASE(8)
 #undef MLC_CASE
