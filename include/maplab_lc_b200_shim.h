@@ -129,27 +129,38 @@ class LoopDetector {
                   const double* keypoints_uv, const std::vector<mlc_camera>& cameras,
                   const mlc_ransac_settings& ransac, std::vector<mlc_pose_result>* verdicts,
                   std::vector<std::vector<mlc_match>>* inlier_matches = nullptr) const {
-    int64_t n = 0;
-    for (const mlc_frame& f : frames) n += f.num_descriptors;
-    verdicts->assign(frames.size(), mlc_pose_result{});
-    const int64_t cap = n * 16 + 16;
-    std::vector<mlc_match> matches(inlier_matches ? static_cast<size_t>(cap) : 0);
-    std::vector<uint8_t> flags(inlier_matches ? static_cast<size_t>(cap) : 0);
-    std::vector<int64_t> offsets(frames.size() + 1, 0);
-    int64_t nv = 0, nm = 0;
-    Check(mlc_query_batch(d_, frames.data(), static_cast<int64_t>(frames.size()), descriptors,
-                          bytes_per_descriptor, keypoints_uv, cameras.data(), static_cast<int>(cameras.size()),
-                          &ransac, verdicts->data(), &nv, inlier_matches ? matches.data() : nullptr, cap,
-                          offsets.data(), &nm, inlier_matches ? flags.data() : nullptr));
-    verdicts->resize(static_cast<size_t>(nv));
-    if (inlier_matches) {
-      inlier_matches->assign(static_cast<size_t>(nv), {});
-      for (int64_t v = 0; v < nv; ++v) {
-        if (!(*verdicts)[static_cast<size_t>(v)].accepted) continue;
-        for (int64_t i = offsets[v]; i < offsets[v + 1]; ++i)
-          if (flags[static_cast<size_t>(i)] == 3) (*inlier_matches)[static_cast<size_t>(v)].push_back(matches[static_cast<size_t>(i)]);
-      }
-    }
+    QueryImpl(&mlc_query_batch, frames, descriptors, bytes_per_descriptor, keypoints_uv, cameras, ransac, verdicts,
+              inlier_matches);
+  }
+
+  // ---- the database sharded over the GPUs of one box: one process (and one LoopDetector created with
+  // shard_rank / shard_count) per GPU ----
+  // Rank 0 makes the communicator id and hands the 128 bytes to the other ranks (MPI_Bcast, a file, ...).
+  static std::vector<char> MakeCommunicatorId() {
+    std::vector<char> id(MLC_COMM_ID_BYTES);
+    Check(mlc_comm_unique_id(id.data()));
+    return id;
+  }
+  void InitCommunicator(const std::vector<char>& id) {  // collective over the shard_count ranks
+    if (id.size() != MLC_COMM_ID_BYTES) Check(Fail("InitCommunicator: the id is 128 bytes"));
+    Check(mlc_comm_init(d_, id.data()));
+  }
+  // Sharded build: `image` describes ALL descriptors of the keyframe, `owned_projected` holds the rows of the
+  // descriptors this shard owns (NumOwnedInRange(NumDescriptors(), n) rows, ascending keypoint index).
+  int64_t NumOwnedInRange(int64_t first, int64_t count) const { return mlc_num_owned_in_range(d_, first, count); }
+  void InsertOwned(const ProjectedImage& image, int64_t num_keypoints, const float* owned_projected) {
+    mlc_frame f{image.timestamp_nanoseconds, image.vertex_id, image.mission_id, image.frame_index,
+                static_cast<int32_t>(num_keypoints)};
+    Check(mlc_insert_batch_owned(d_, &f, 1, owned_projected, image.landmarks.empty() ? nullptr : image.landmarks.data()));
+  }
+  // QueryBatch for THIS rank's slice of the step's query vertices against the whole sharded database
+  // (collective: every rank calls it once per step, possibly with no frames).
+  void ShardedQueryBatch(const std::vector<mlc_frame>& frames, const uint8_t* descriptors, int bytes_per_descriptor,
+                         const double* keypoints_uv, const std::vector<mlc_camera>& cameras,
+                         const mlc_ransac_settings& ransac, std::vector<mlc_pose_result>* verdicts,
+                         std::vector<std::vector<mlc_match>>* inlier_matches = nullptr) const {
+    QueryImpl(&mlc_sharded_query_batch, frames, descriptors, bytes_per_descriptor, keypoints_uv, cameras, ransac,
+              verdicts, inlier_matches);
   }
   // map_->getVertex_T_G_I of the query vertices of the next QueryBatch (loop-closure-handler.cc:436-437);
   // needed only with --lc_max_delta_position_m / --lc_max_delta_rotation_deg.
@@ -210,6 +221,36 @@ class LoopDetector {
   }
 
  private:
+  using QueryFn = int (*)(mlc_detector*, const mlc_frame*, int64_t, const uint8_t*, int, const double*,
+                          const mlc_camera*, int, const mlc_ransac_settings*, mlc_pose_result*, int64_t*, mlc_match*,
+                          int64_t, int64_t*, int64_t*, uint8_t*);
+  void QueryImpl(QueryFn fn, const std::vector<mlc_frame>& frames, const uint8_t* descriptors,
+                 int bytes_per_descriptor, const double* keypoints_uv, const std::vector<mlc_camera>& cameras,
+                 const mlc_ransac_settings& ransac, std::vector<mlc_pose_result>* verdicts,
+                 std::vector<std::vector<mlc_match>>* inlier_matches) const {
+    int64_t n = 0;
+    for (const mlc_frame& f : frames) n += f.num_descriptors;
+    verdicts->assign(frames.size() + 1, mlc_pose_result{});
+    const int64_t cap = n * 16 + 16;
+    std::vector<mlc_match> matches(inlier_matches ? static_cast<size_t>(cap) : 0);
+    std::vector<uint8_t> flags(inlier_matches ? static_cast<size_t>(cap) : 0);
+    std::vector<int64_t> offsets(frames.size() + 1, 0);
+    int64_t nv = 0, nm = 0;
+    Check(fn(d_, frames.data(), static_cast<int64_t>(frames.size()), descriptors, bytes_per_descriptor, keypoints_uv,
+             cameras.data(), static_cast<int>(cameras.size()), &ransac, verdicts->data(), &nv,
+             inlier_matches ? matches.data() : nullptr, cap, offsets.data(), &nm,
+             inlier_matches ? flags.data() : nullptr));
+    verdicts->resize(static_cast<size_t>(nv));
+    if (inlier_matches) {
+      inlier_matches->assign(static_cast<size_t>(nv), {});
+      for (int64_t v = 0; v < nv; ++v) {
+        if (!(*verdicts)[static_cast<size_t>(v)].accepted) continue;
+        for (int64_t i = offsets[v]; i < offsets[v + 1]; ++i)
+          if (flags[static_cast<size_t>(i)] == 3)
+            (*inlier_matches)[static_cast<size_t>(v)].push_back(matches[static_cast<size_t>(i)]);
+      }
+    }
+  }
   static int Fail(const char* msg) {
     last_shim_error() = msg;
     throw std::runtime_error(msg);

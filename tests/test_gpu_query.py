@@ -120,3 +120,39 @@ def test_large_host_batch_chunked_copies_equal_device_path():
     assert np.array_equal(host["offsets"], devr["offsets"])
     assert host["matches"].tobytes() == devr["matches"].tobytes()
     assert host["results"]["accepted"].sum() > 60
+
+
+def test_concurrent_queries_from_eight_threads_equal_sequential_ones():
+    """The reference calls Find / queryVertexInDatabase from getNumHardwareThreads() threads at once
+    (loop-detector-node.cc:867-873, read lock of matching-based-engine.cc:60). Calls into one detector are
+    re-entrant: they serialise on its stream (measured: a second query step side by side on the same GPU
+    gains 3 %, profiles/r2_3_concurrent.json) and every caller gets exactly the sequential answer."""
+    import threading
+    m, q, det, _ = _setup(num_queries=16, num_nearest_neighbors=6)
+    cams = capi.make_cameras([synthetic.camera_dict()])
+    qframes = frames_of(q["frames"])
+    kp = np.ascontiguousarray(q["keypoints"], np.float64)
+    n = 500
+    expected = [det.query_batch(qframes[i:i + 2].copy(), q["bits"][i * n:(i + 2) * n], kp[i * n:(i + 2) * n], cams,
+                                want_matches=True) for i in range(0, 16, 2)]
+    got = [None] * 8
+    errors = []
+
+    def work(t):
+        try:
+            for _ in range(5):
+                i = 2 * t
+                got[t] = det.query_batch(qframes[i:i + 2].copy(), q["bits"][i * n:(i + 2) * n],
+                                         kp[i * n:(i + 2) * n], cams, want_matches=True)
+                idx, dist = det.knn(det.project(q["bits"][i * n:(i + 1) * n]), 6)
+                assert idx.shape == (n, 6)
+        except Exception as e:  # noqa: BLE001
+            errors.append(e)
+
+    threads = [threading.Thread(target=work, args=(t,)) for t in range(8)]
+    [t.start() for t in threads]
+    [t.join() for t in threads]
+    assert not errors, errors
+    for t in range(8):
+        assert got[t]["results"].tobytes() == expected[t]["results"].tobytes()
+        assert got[t]["matches"].tobytes() == expected[t]["matches"].tobytes()

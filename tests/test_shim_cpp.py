@@ -71,3 +71,29 @@ def test_shim_program_matches_python_binding(tmp_path):
                                                 int(res["iterations"][v]))
         T = res["T_G_I"][v].reshape(3, 4)
         assert (float(tx), float(ty), float(tz)) == (T[0, 3], T[1, 3], T[2, 3])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("world", [1, 2])
+def test_shim_program_multi_gpu_equals_single_gpu(tmp_path, world):
+    """A C++ host per GPU — no Python, no torch — builds its shard, joins the NCCL communicator through the
+    C-ABI (mlc_comm_*) and answers its slice with ShardedQueryBatch: the slices together must be the
+    single-GPU program's output."""
+    import torch
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    exe = _build(tmp_path)
+    m, blob, _, q = small_world(num_queries=12)
+    _write_world(tmp_path / "world.bin", m, blob, q)
+    single = subprocess.check_output([str(exe), str(tmp_path / "world.bin")], text=True).split("\n")
+    procs = [subprocess.Popen([str(exe), str(tmp_path / "world.bin"), str(r), str(world), str(tmp_path / "comm.id")],
+                              stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True) for r in range(world)]
+    outs = []
+    for p in procs:
+        o, e = p.communicate(timeout=300)
+        assert p.returncode == 0, e[-2000:]
+        outs.append([ln for ln in o.split("\n") if not ln.startswith("NCCL version")])  # NCCL's banner is on stdout
+    lines = [ln for o in outs for ln in o[1:] if ln]
+    assert lines == [ln for ln in single[1:] if ln]
+    assert sum(int(o[0].split()[1]) for o in outs) == int(single[0].split()[1])      # accepted
+    assert all(int(o[0].split()[3]) == int(single[0].split()[3]) for o in outs)      # NumDescriptors: whole database
