@@ -36,6 +36,7 @@ struct CovisArgs {
   unsigned long long min_verify_matches_num;
   float fraction_best_scores;
   int group_bits;                // 2^group_bits > number of database keyframes
+  int landmark_bits;             // 2^landmark_bits > every (landmark number + 1) of the database
   int scoring;                   // 0 accumulation, 1 probabilistic (scoring.h)
   long long num_db_descriptors;  // whole database (all shards)
   mlc_match* scratch;  // grid * (4096 | 8192) records

@@ -313,9 +313,30 @@ __global__ void __launch_bounds__(THREADS, (THREADS <= 512 ? 2 : 1)) covis_kerne
           },
           scan_tmp);
       const int ps = NextPow2(S);
-      for (int j = S + tid; j < ps; j += THREADS) s.keys[j] = ~0ull;
-      __syncthreads();
-      BitonicSort<THREADS>(s.keys, ps);
+      if (S > 1024 && a.landmark_bits <= 30) {
+        // many selected matches: stable LSD radix sort over the landmark bits only (the slot bits already
+        // ascend in the blocked arrangement), like stage A; its scratch aliases a2..a7, dead until the
+        // scans below
+        for (int j = S + tid; j < MAXM; j += THREADS) s.keys[j] = ~0ull;
+        __syncthreads();
+        typedef cub::BlockRadixSort<unsigned long long, THREADS, IPT> RadixSort;
+        static_assert(sizeof(typename RadixSort::TempStorage) + 16 <= 6 * sizeof(s.a2), "radix scratch");
+        typename RadixSort::TempStorage& radix_tmp = *reinterpret_cast<typename RadixSort::TempStorage*>(
+            (reinterpret_cast<uintptr_t>(s.a2) + 15) & ~static_cast<uintptr_t>(15));
+        unsigned long long kreg[IPT];
+#pragma unroll
+        for (int i = 0; i < IPT; ++i) kreg[i] = s.keys[tid * IPT + i];
+        __syncthreads();
+        RadixSort(radix_tmp).Sort(kreg, SLOT_BITS, SLOT_BITS + a.landmark_bits);
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < IPT; ++i) s.keys[tid * IPT + i] = kreg[i];
+        __syncthreads();
+      } else {
+        for (int j = S + tid; j < ps; j += THREADS) s.keys[j] = ~0ull;
+        __syncthreads();
+        BitonicSort<THREADS>(s.keys, ps);
+      }
       // landmark dense id a4[match]; offA (a5), listA (a6) = group of the match at sorted position
       const int nL = FlagScan<THREADS, IPT>(
           S, [&](int i) { return i == 0 || (s.keys[i] >> SLOT_BITS) != (s.keys[i - 1] >> SLOT_BITS); },

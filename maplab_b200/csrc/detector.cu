@@ -227,6 +227,7 @@ bool Detector::Clear(std::string* err) {
   std::lock_guard<std::recursive_mutex> lock(mu_);
   keyframes_.clear();
   keyframe_keys_.clear();
+  max_lm_key_ = 0;
   num_desc_ = num_own_ = 0;
   pend_desc_.clear();
   pend_gidx_.clear();
@@ -320,6 +321,19 @@ __global__ void drop_foreign_cells_kernel(int32_t* __restrict__ cells, int64_t n
   if (c >= 0 && static_cast<int>(((static_cast<uint32_t>(c) * 2654435761u) >> 8) % static_cast<uint32_t>(shard_count)) != shard_rank)
     cells[i] = -1;
 }
+__global__ void max_landmark_key_kernel(const int64_t* __restrict__ lm, int64_t n, unsigned long long* __restrict__ out) {
+  unsigned long long local = 0;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const unsigned long long key = static_cast<unsigned long long>(lm[i] + 1);
+    local = key > local ? key : local;
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    const unsigned long long other = __shfl_xor_sync(0xffffffffu, local, o);
+    local = other > local ? other : local;
+  }
+  if ((threadIdx.x & 31) == 0 && local) atomicMax(out, local);  // build-time bookkeeping, not on the query path
+}
 constexpr size_t kPendingFlushBytes = size_t{64} << 20;  // host staging of Insert is bounded by this
 }  // namespace
 
@@ -381,10 +395,13 @@ bool Detector::InsertBatch(const mlc_frame* frames, int64_t num_frames, const fl
     keyframe_keys_.insert(KeyframeKey{m.vertex, m.frame_index});
     num_desc_ += m.num_descriptors;
   }
-  if (landmarks)
+  if (landmarks) {
     pend_lm_.insert(pend_lm_.end(), landmarks, landmarks + total);
-  else
+    for (int64_t i = 0; i < total; ++i)
+      max_lm_key_ = std::max<uint64_t>(max_lm_key_, static_cast<uint64_t>(landmarks[i] + 1));
+  } else {
     pend_lm_.insert(pend_lm_.end(), static_cast<size_t>(total), int64_t{-1});
+  }
   // first owned global index >= base
   int64_t g = base + ((r - base % G) % G + G) % G;
   if (proj_is_owned_rows || G == 1) {
@@ -400,6 +417,21 @@ bool Detector::InsertBatch(const mlc_frame* frames, int64_t num_frames, const fl
   }
   index_dirty_ = true;
   if (pend_desc_.size() * 4 + pend_lm_.size() * 8 >= kPendingFlushBytes) return FlushPending(err);
+  return true;
+}
+
+bool Detector::UpdateMaxLandmarkDevice(const int64_t* d_lm, int64_t n, std::string* err) {
+  if (n <= 0) return true;
+  if (!Cuda(d_stats_.Reserve(8), "alloc", err) || !Cuda(cudaMemsetAsync(d_stats_.p, 0, 8, stream_), "memset", err))
+    return false;
+  const unsigned blocks = static_cast<unsigned>(std::min<int64_t>((n + 255) / 256, 1184));
+  max_landmark_key_kernel<<<blocks, 256, 0, stream_>>>(d_lm, n, d_stats_.as<unsigned long long>());
+  CountLaunch();
+  unsigned long long v = 0;
+  if (!Cuda(cudaMemcpyAsync(&v, d_stats_.p, 8, cudaMemcpyDeviceToHost, stream_), "D2H", err) ||
+      !Cuda(cudaStreamSynchronize(stream_), "max landmark", err))
+    return false;
+  max_lm_key_ = std::max<uint64_t>(max_lm_key_, v);
   return true;
 }
 
@@ -500,6 +532,7 @@ bool Detector::InsertBatchDevice(const mlc_frame* frames, int64_t num_frames, co
     CountLaunch();
   }
   if (!Cuda(cudaStreamSynchronize(stream_), "insert", err)) return false;
+  if (d_landmarks && !UpdateMaxLandmarkDevice(reinterpret_cast<const int64_t*>(d_desc_lm_.end()), total, err)) return false;
   d_desc_lm_.used += static_cast<size_t>(total) * 8;
   d_own_desc_.used += db;
   d_own_gidx_.used += static_cast<size_t>(owned) * 4;
@@ -1034,6 +1067,8 @@ bool Detector::LoadIndex(const char* path, std::string* err) {
   num_landmark_xyz_ = h.num_landmark_xyz;
   last_valid_ = false;
   index_dirty_ = true;  // until the replicas below are in place
+  max_lm_key_ = 0;
+  if (!UpdateMaxLandmarkDevice(d_desc_lm_.as<int64_t>(), num_desc_, err)) return false;
   if (!UploadKeyframeReplicas(err)) return false;
   index_dirty_ = false;
   return true;

@@ -272,6 +272,8 @@ class Detector {
     }
   };
   std::unordered_set<KeyframeKey, KeyframeKeyHash> keyframe_keys_;
+  uint64_t max_lm_key_ = 0;  // max over (uint64)(landmark number + 1): bit budget of kernel 3's landmark sort
+  bool UpdateMaxLandmarkDevice(const int64_t* d_lm, int64_t n, std::string* err);
   int64_t num_desc_ = 0;  // descriptors in the database (all shards)
   int64_t num_own_ = 0;   // rows of this shard already on the device
   std::vector<float> pend_desc_;      // staged owned rows (n x dim)

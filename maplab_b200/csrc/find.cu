@@ -184,6 +184,8 @@ bool Detector::FindOnDevice(const mlc_frame* frames, int64_t num_frames, const i
   a.scoring = s_.scoring;
   a.group_bits = 1;
   while ((1ull << a.group_bits) <= keyframes_.size()) ++a.group_bits;
+  a.landmark_bits = 1;
+  while (a.landmark_bits < 64 && (max_lm_key_ >> a.landmark_bits) != 0) ++a.landmark_bits;
   a.num_db_descriptors = NumDescriptors();
   a.scratch = b_scr.as<mlc_match>();
   a.out_matches = b_out.as<mlc_match>();
