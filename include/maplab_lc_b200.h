@@ -36,7 +36,8 @@ typedef struct mlc_settings {
   int32_t num_closest_words;       /* --lc_num_words_for_nn_search (10), MBL/src/detector-settings.cc:40 */
   int32_t num_nearest_neighbors;   /* --lc_num_neighbors (-1 = auto), MBL/src/detector-settings.cc:36 */
   int32_t scoring;                 /* --lc_scoring_function: 0 accumulation, 1 probabilistic */
-  int32_t engine;                  /* --lc_detector_engine: 0 imi, 1 imipq */
+  int32_t engine;                  /* --lc_detector_engine: 0 imi, 1 imipq, 2 hnsw (float descriptors; the search is
+                                      EXACT on the device, see hnsw_* below) */
   double min_image_time_seconds;   /* --lc_min_image_time_seconds (10.0) */
   uint64_t min_verify_matches_num; /* --lc_min_verify_matches_num (10) */
   float fraction_best_scores;      /* --lc_fraction_best_scores (0.25) */
@@ -49,6 +50,16 @@ typedef struct mlc_settings {
                                       is handed its own descriptors only). 1: by cell (hash(cell) % count — every
                                       shard keeps whole inverted lists; EXPERIMENTAL: every shard must be handed
                                       ALL descriptors and keeps the cells it owns) */
+  /* engine 2 (loop_closure::HSNWIndexInterface, MBL/include/.../hnsw-index-interface.h; flags at
+   * MBL/src/detector-settings.cc:36-47): descriptors are `float_descriptor_dim` floats (the reference reinterprets
+   * the descriptor bytes, :155-163 — mlc_project does the same); no vocabulary file is read (vocab_blob may be NULL).
+   * The device search is exhaustive, so hnsw_m / hnsw_ef_construction do not change results; hnsw_ef_query keeps the
+   * reference's CHECK_LT(num_neighbors, ef_query). Neighbours come back as the reference interface returns them:
+   * farthest first (popped from a max-heap, :141-151). */
+  int32_t float_descriptor_dim;
+  int32_t hnsw_m;                  /* --lc_hnsw_m (12) */
+  int32_t hnsw_ef_construction;    /* --lc_hnsw_ef_construction (50) */
+  int32_t hnsw_ef_query;           /* --lc_hnsw_ef_query (50) */
   int32_t pad_;
 } mlc_settings;
 

@@ -36,7 +36,9 @@ class Settings(C.Structure):
                 ("min_image_time_seconds", C.c_double), ("min_verify_matches_num", C.c_uint64),
                 ("fraction_best_scores", C.c_float), ("knn_epsilon", C.c_float),
                 ("knn_max_radius", C.c_float), ("device", C.c_int32), ("shard_rank", C.c_int32),
-                ("shard_count", C.c_int32), ("shard_mode", C.c_int32), ("pad_", C.c_int32)]
+                ("shard_count", C.c_int32), ("shard_mode", C.c_int32), ("float_descriptor_dim", C.c_int32),
+                ("hnsw_m", C.c_int32), ("hnsw_ef_construction", C.c_int32), ("hnsw_ef_query", C.c_int32),
+                ("pad_", C.c_int32)]
 
 
 class Frame(C.Structure):
@@ -260,7 +262,7 @@ class Detector:
 
     def __init__(self, vocab_blob, settings=None):
         self.settings = settings or default_settings()
-        blob = bytes(vocab_blob)
+        blob = bytes(vocab_blob) if vocab_blob is not None else b""
         self._h = C.c_void_p()
         _check(lib().mlc_create(C.byref(self.settings), blob, C.c_size_t(len(blob)),
                                 C.byref(self._h)))

@@ -48,6 +48,10 @@ void mlc_default_settings(mlc_settings* s) {
   s->shard_rank = 0;
   s->shard_count = 1;
   s->shard_mode = 0;
+  s->float_descriptor_dim = 0;
+  s->hnsw_m = 12;
+  s->hnsw_ef_construction = 50;
+  s->hnsw_ef_query = 50;
   s->pad_ = 0;
 }
 
@@ -64,7 +68,7 @@ void mlc_default_ransac_settings(mlc_ransac_settings* s) {
 
 int mlc_create(const mlc_settings* settings, const void* vocab_blob, size_t vocab_size,
                mlc_detector** out) {
-  MLC_REQUIRE(settings && vocab_blob && out, "mlc_create: null argument");
+  MLC_REQUIRE(settings && out && (vocab_blob || settings->engine == 2), "mlc_create: null argument");
   *out = nullptr;
   mlc_detector* d = new (std::nothrow) mlc_detector();
   MLC_REQUIRE(d, "out of memory");
@@ -97,7 +101,8 @@ int mlc_project(mlc_detector* d, const uint8_t* bits, int bytes_per_desc, int64_
 int mlc_project_device(mlc_detector* d, const uint8_t* d_bits, int bytes_per_desc, int64_t n,
                        float* d_out, void* stream) {
   MLC_REQUIRE(d && (n == 0 || (d_bits && d_out)), "mlc_project_device: null argument");
-  MLC_REQUIRE(bytes_per_desc > 0 && bytes_per_desc % 16 == 0, "bytes per descriptor must be a multiple of 16");
+  MLC_REQUIRE(bytes_per_desc > 0 && (bytes_per_desc % 16 == 0 || d->impl.exact_engine()),
+              "bytes per descriptor must be a multiple of 16");
   std::string err;
   return d->impl.ProjectDevice(d_bits, bytes_per_desc, n, d_out, static_cast<cudaStream_t>(stream), &err)
              ? 0
@@ -268,7 +273,8 @@ int mlc_find_batch_bits(mlc_detector* d, const mlc_frame* frames, int64_t num_fr
                         int64_t* num_matches) {
   MLC_REQUIRE(d && num_vertices && num_matches && (num_frames == 0 || (frames && match_offsets)),
               "mlc_find_batch_bits: null argument");
-  MLC_REQUIRE(bytes_per_desc > 0 && bytes_per_desc % 16 == 0, "bytes per descriptor must be a multiple of 16");
+  MLC_REQUIRE(bytes_per_desc > 0 && (bytes_per_desc % 16 == 0 || d->impl.exact_engine()),
+              "bytes per descriptor must be a multiple of 16");
   std::string err;
   return d->impl.FindBatch(frames, num_frames, nullptr, bits, bytes_per_desc, matches, capacity,
                            match_offsets, num_vertices, num_matches, &err)
@@ -577,7 +583,8 @@ static int QueryImpl(mlc_detector* d, const mlc_frame* frames, int64_t num_frame
                      uint8_t* inlier_flags) {
   MLC_REQUIRE(d && rs && cams && num_cams > 0 && num_vertices, "mlc_query_batch: null argument");
   MLC_REQUIRE(num_frames == 0 || (frames && bits && keypoints && results), "mlc_query_batch: null argument");
-  MLC_REQUIRE(bytes_per_desc > 0 && bytes_per_desc % 16 == 0, "bytes per descriptor must be a multiple of 16");
+  MLC_REQUIRE(bytes_per_desc > 0 && (bytes_per_desc % 16 == 0 || d->impl.exact_engine()),
+              "bytes per descriptor must be a multiple of 16");
   std::string err;
   return d->impl.QueryBatch(frames, num_frames, bits, bytes_per_desc, keypoints, on_device, cams,
                             num_cams, *rs, results, num_vertices, matches, capacity, match_offsets,

@@ -69,19 +69,25 @@ bool Detector::Create(const mlc_settings& s, const void* blob, size_t size, std:
     *err = "num_closest_words must be in 1..16";
     return false;
   }
-  if (s_.engine != 0 && s_.engine != 1) {
-    *err = "unknown detector engine (0 imi, 1 imipq)";
+  if (s_.engine != 0 && s_.engine != 1 && s_.engine != 2) {
+    *err = "unknown detector engine (0 imi, 1 imipq, 2 hnsw)";
+    return false;
+  }
+  if (s_.engine == 2 && (s_.float_descriptor_dim <= 0 || s_.float_descriptor_dim > 4096 || s_.shard_count > 1 ||
+                         s_.hnsw_m <= 0 || s_.hnsw_ef_construction <= 0 || s_.hnsw_ef_query <= 0)) {
+    *err = "hnsw engine: needs float_descriptor_dim in 1..4096, positive hnsw_* settings (detector-settings.cc:69-71) "
+           "and a single shard";
     return false;
   }
   if (s_.shard_mode != 0 && s_.shard_mode != 1) {
     *err = "unknown shard_mode (0 by descriptor index, 1 by cell)";
     return false;
   }
-  if (!vocab_.Parse(blob, size, s_.engine == 1, err)) return false;
+  if (s_.engine != 2 && !vocab_.Parse(blob, size, s_.engine == 1, err)) return false;
   vocab_hash_ = 1469598103934665603ull;
-  for (size_t i = 0; i < size; ++i)
+  for (size_t i = 0; s_.engine != 2 && i < size; ++i)
     vocab_hash_ = (vocab_hash_ ^ static_cast<const unsigned char*>(blob)[i]) * 1099511628211ull;
-  if (vocab_.target_dim / 2 > 8) {
+  if (s_.engine != 2 && vocab_.target_dim / 2 > 8) {
     *err = "target dimensionality > 16 is not supported";
     return false;
   }
@@ -117,6 +123,7 @@ bool Detector::Create(const mlc_settings& s, const void* blob, size_t size, std:
   for (cudaEvent_t& e : ev_stage_)
     if (!Cuda(cudaEventCreate(&e), "cudaEventCreate", err)) return false;
 
+  if (s_.engine == 2) return true;  // no vocabulary: the descriptors are floats, the search exhaustive
   fp_.Build(vocab_.projection, vocab_.target_dim);
   if (fp_.kp <= 512 && fp_.dim <= 12) {
     if (!Cuda(BuildProjectionDevice(fp_, &proj_), "BuildProjectionDevice", err)) return false;
@@ -261,6 +268,15 @@ int Detector::NumNeighbors() const {
 
 bool Detector::ProjectDevice(const uint8_t* d_bits, int bytes_per_desc, int64_t n, float* d_out,
                              cudaStream_t stream, std::string* err) {
+  if (s_.engine == 2) {
+    // HSNWIndexInterface::ProjectDescriptors (hnsw-index-interface.h:155-163): the descriptor bytes ARE the floats
+    if (bytes_per_desc != 4 * dim()) {
+      *err = "hnsw engine: descriptors must be float_descriptor_dim floats";
+      return false;
+    }
+    return n == 0 || Cuda(cudaMemcpyAsync(d_out, d_bits, static_cast<size_t>(n) * bytes_per_desc,
+                                          cudaMemcpyDeviceToDevice, stream), "reinterpret descriptors", err);
+  }
   if (!proj_.fp) {
     *err = "projection matrix shape unsupported by the tensor-core kernel (need <= 512 columns, <= 12 rows)";
     return false;
@@ -279,7 +295,7 @@ bool Detector::Project(const uint8_t* bits, int bytes_per_desc, int64_t n, float
                        std::string* err) {
   std::lock_guard<std::recursive_mutex> lock(mu_);
   if (n == 0) return true;  // descriptor-projection.cc:20-22
-  if (n < 0 || bytes_per_desc <= 0 || bytes_per_desc % 16 != 0) {
+  if (n < 0 || bytes_per_desc <= 0 || (s_.engine != 2 && bytes_per_desc % 16 != 0)) {
     *err = "bad descriptor block shape (bytes per descriptor must be a multiple of 16)";
     return false;
   }
@@ -573,6 +589,11 @@ bool Detector::EnsureIndex(std::string* err) {
   }
   const float* d_desc = d_own_desc_.as<float>();
   const int32_t* d_gidx = d_own_gidx_.as<int32_t>();
+  if (s_.engine == 2) {  // exhaustive search: the descriptor rows are the index
+    if (!UploadKeyframeReplicas(err)) return false;
+    index_dirty_ = false;
+    return true;
+  }
   if (no > 0) {
     if (!Cuda(d_db_cells_.Reserve(static_cast<size_t>(no) * 4), "alloc cells", err)) return false;
     if (!CoarseChunks(d_desc, no, 1, d_db_cells_.as<int32_t>(), stream_, err)) return false;
@@ -631,6 +652,18 @@ bool Detector::KnnDevice(const float* d_q, int64_t n_q, int k, int32_t* d_idx, f
   }
   if (!EnsureIndex(err)) return false;
   if (n_q == 0) return true;
+  if (s_.engine == 2) {
+    // CHECK_LT(num_neighbors, ef_query_) and CHECK_EQ(result.size(), num_neighbors), hnsw-index-interface.h:128, :143
+    if (k >= s_.hnsw_ef_query || k > NumDescriptors()) {
+      *err = "hnsw engine: num_neighbors must be < hnsw_ef_query and <= the number of descriptors in the index";
+      return false;
+    }
+    const int splits = ExactKnnSplits(n_q, num_own_, sm_count_);
+    if (!Cuda(d_coarse_scratch_.Reserve(ExactKnnScratchBytes(n_q, k, splits)), "alloc knn scratch", err)) return false;
+    last_valid_ = false;
+    return Cuda(LaunchExactKnn(d_own_desc_.as<float>(), num_own_, d_q, n_q, dim(), k, splits, d_coarse_scratch_.p, d_idx,
+                               d_dist, stream), "exact kNN", err);
+  }
   const int nw = s_.num_closest_words;
   if (!Cuda(d_cells_.Reserve(static_cast<size_t>(n_q) * nw * 4), "alloc visit list", err)) return false;
   if (!CoarseChunks(d_q, n_q, nw, d_cells_.as<int32_t>(), stream, err)) return false;
@@ -672,6 +705,10 @@ bool Detector::CoarseCells(const float* q, int64_t n, int nw, int32_t* cells, st
     *err = "bad arguments";
     return false;
   }
+  if (s_.engine == 2) {
+    *err = "the hnsw engine has no coarse quantiser";
+    return false;
+  }
   if (n == 0) return true;
   const size_t qb = static_cast<size_t>(n) * dim() * 4, cb = static_cast<size_t>(n) * nw * 4;
   if (!Cuda(d_q_.Reserve(qb), "alloc", err) || !Cuda(d_cells_.Reserve(cb), "alloc", err)) return false;
@@ -687,6 +724,10 @@ bool Detector::CoarseDevice(const float* d_q, int64_t n, int nw, int32_t* d_cell
   std::lock_guard<std::recursive_mutex> lock(mu_);
   if (nw <= 0 || nw > 16) {
     *err = "nw must be in 1..16";
+    return false;
+  }
+  if (s_.engine == 2) {
+    *err = "the hnsw engine has no coarse quantiser";
     return false;
   }
   return CoarseChunks(d_q, n, nw, d_cells, stream, err);
@@ -713,6 +754,10 @@ bool Detector::ScanDevice(const float* d_q, const int32_t* d_cells, int64_t n_q,
   std::lock_guard<std::recursive_mutex> lock(mu_);
   if (k <= 0 || k > 16) {
     *err = "k must be in 1..16";
+    return false;
+  }
+  if (s_.engine == 2) {
+    *err = "the hnsw engine has no inverted lists";
     return false;
   }
   if (!EnsureIndex(err)) return false;
@@ -825,6 +870,10 @@ __global__ void validate_lists_kernel(const uint2* __restrict__ cell_info, uint3
 
 bool Detector::SaveIndex(const char* path, std::string* err) {
   std::lock_guard<std::recursive_mutex> lock(mu_);
+  if (s_.engine == 2) {
+    *err = "index files hold inverted lists: not available for the hnsw engine";
+    return false;
+  }
   if (s_.shard_mode != 0) {
     *err = "index files are written for shard_mode 0 only";
     return false;
@@ -883,8 +932,8 @@ bool Detector::LoadIndex(const char* path, std::string* err) {
     FILE* f;
     ~Closer() { fclose(f); }
   } closer{f};
-  if (s_.shard_mode != 0) {
-    *err = "index files are read for shard_mode 0 only";
+  if (s_.shard_mode != 0 || s_.engine == 2) {
+    *err = "index files are read for shard_mode 0 and the imi / imipq engines only";
     return false;
   }
   IndexFileHeader h{};

@@ -102,7 +102,8 @@ class Detector {
   int64_t NumDescriptors() const { return num_desc_; }
   int64_t NumOwnedDescriptors() const { return num_own_ + static_cast<int64_t>(pend_gidx_.size()); }
   int NumNeighbors() const;
-  int dim() const { return vocab_.target_dim; }
+  int dim() const { return s_.engine == 2 ? s_.float_descriptor_dim : vocab_.target_dim; }
+  bool exact_engine() const { return s_.engine == 2; }
 
   bool Project(const uint8_t* bits, int bytes_per_desc, int64_t n, float* out, std::string* err);
   bool ProjectDevice(const uint8_t* d_bits, int bytes_per_desc, int64_t n, float* d_out,

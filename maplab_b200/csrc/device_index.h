@@ -78,6 +78,12 @@ cudaError_t LaunchMergeTopk(const int32_t* idx_lists, const float* dist_lists, i
                             int64_t n_q, int k, int32_t* out_idx, float* out_dist,
                             cudaStream_t stream);
 
+// ---- engine `hnsw` slot: exact search over float descriptors (exact_knn_kernel.cu) ---------------
+int ExactKnnSplits(int64_t n_q, int64_t n_db, int sm_count);
+size_t ExactKnnScratchBytes(int64_t n_q, int k, int splits);
+cudaError_t LaunchExactKnn(const float* d_db, int64_t n_db, const float* d_q, int64_t n_q, int dim, int k, int splits,
+                           void* scratch, int32_t* d_idx, float* d_dist, cudaStream_t stream);
+
 // ---- kernel 1 --------------------------------------------------------------------------------
 // B operand image of the projection GEMM: kProjNPad rows x (kp_padded bytes), already arranged in
 // the shared-memory core-matrix layout the kernel uses (see projection_kernel.cu).

@@ -421,7 +421,17 @@ bool Detector::QueryBatch(const mlc_frame* frames, int64_t num_frames, const uin
   }
   stage_valid_ = false;
   cudaEventRecord(ev_stage_[0], stream_);
-  if (n > 0) {
+  if (n > 0 && s_.engine == 2) {
+    // hnsw engine: the descriptor bytes are the floats; exhaustive kNN instead of coarse search + list scan
+    for (int c = 0; c < chunks && !inputs_on_device; ++c)
+      if (!Cuda(cudaStreamWaitEvent(stream_, ev_copy_[c], 0), "wait", err)) return false;
+    if (!ProjectDevice(d_bits, bytes_per_desc, n, d_q_.as<float>(), stream_, err)) return false;
+    cudaEventRecord(ev_stage_[1], stream_);
+    cudaEventRecord(ev_stage_[2], stream_);
+    if (!KnnDevice(d_q_.as<float>(), n, k, d_idx_.as<int32_t>(), d_dist_.as<float>(), stream_, err)) return false;
+    if (!inputs_on_device && !Cuda(cudaStreamWaitEvent(stream_, ev_copy_[kCopyChunks], 0), "wait", err))
+      return false;
+  } else if (n > 0) {
     const int nw = s_.num_closest_words;
     if (!Cuda(d_cells_.Reserve(static_cast<size_t>(n) * nw * 4), "alloc visit list", err)) return false;
     for (int c = 0; c < chunks; ++c) {

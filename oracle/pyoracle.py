@@ -541,3 +541,17 @@ def yaw_only(q_xyzw):
     out = np.zeros(4, np.float64)
     lib().lco_yaw_only(_p(q, c_double_p), _p(out, c_double_p))
     return out
+
+
+# ------------------------------------------------------------------ hnsw engine slot
+def exact_knn(db, q, k):
+    """Exact k nearest neighbours of float descriptors (ground truth of the `hnsw` engine slot), in the order
+    the reference interface returns them: descending (distance, index). Raises if k > len(db)."""
+    db, q = _f32(db), _f32(q)
+    idx = np.zeros((len(q), k), np.int32)
+    dist = np.zeros((len(q), k), np.float32)
+    rc = lib().lco_exact_knn(_p(db, c_float_p), C.c_int64(len(db)), _p(q, c_float_p), C.c_int64(len(q)),
+                             db.shape[1], k, _p(idx, c_int_p), _p(dist, c_float_p))
+    if rc != 0:
+        raise ValueError("fewer than k descriptors in the index (the reference CHECKs result.size() == k)")
+    return idx, dist

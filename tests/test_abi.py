@@ -30,7 +30,7 @@ def test_library_exports_every_declared_symbol():
 
 
 def test_struct_layouts_match_header():
-    assert ctypes.sizeof(capi.Settings) == 64  # + shard_mode, pad_
+    assert ctypes.sizeof(capi.Settings) == 80  # + shard_mode, float_descriptor_dim, hnsw_*
     assert capi.FRAME_DTYPE.itemsize == ctypes.sizeof(capi.Frame) == 32
     assert capi.MATCH_DTYPE.itemsize == 32
     assert capi.CAMERA_DTYPE.itemsize == 8 * 4 + 8 + 8 * 4 + 8 * 9 + 8 * 3
