@@ -18,6 +18,7 @@
 // cp.async.bulk store from shared memory.
 // Persistent CTAs (one per SM), warp-specialised: 4 epilogue warps, 1 MMA/TMEM warp, 8 producer warps,
 // 1 TMA load warp; mbarrier pipelines between the roles.
+#include <cstdlib>
 #include <mutex>
 
 #include "device_index.h"
@@ -278,6 +279,209 @@ __global__ void __launch_bounds__(kThreads, 1) projection_kernel(ProjArgs args) 
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Variant with the A operand in TENSOR MEMORY (tcgen05.mma with [a_tmem]): the plane-masked bytes never touch
+// shared memory. The smem-A kernel above moves 64 KB of A per 128-descriptor tile through shared memory twice
+// (producer stores, tensor-core reads); here a producer thread owns one descriptor ROW (TMEM lane), ANDs its
+// 16 words with the plane masks and writes 16 columns per plane with tcgen05.st. K is padded to 64 bytes per
+// plane (descriptors shorter than 64 bytes leave zero columns), so the B image is always the 64-byte one.
+// TMEM columns: accumulators 2 x 64, A tiles 2 x 128.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kTmemColsA = 512;
+constexpr int kAColsPerTile = 128;   // 8 planes x 16 columns (4 u8 per column)
+constexpr int kATmemBase = kAccStages * kAccCols;  // 128
+
+struct SmemT {
+  alignas(128) int8_t b[kBBytes];
+  alignas(128) uint8_t raw[kRawStages][kRawBytes];
+  alignas(128) float out[kAccStages][kTileM * kMaxDim];
+  alignas(8) uint64_t full[kASlots];
+  uint64_t empty[kASlots];
+  uint64_t raw_full[kRawStages];
+  uint64_t raw_empty[kRawStages];
+  uint64_t acc_full[kAccStages];
+  uint64_t acc_empty[kAccStages];
+  uint32_t tmem_base;
+};
+
+__global__ void __launch_bounds__(kThreads, 1) projection_tmem_kernel(ProjArgs args) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  SmemT& s = *reinterpret_cast<SmemT*>(
+      smem_raw + ((128u - (ptx::smem_u32(smem_raw) & 127u)) & 127u));
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int64_t num_tiles = (args.n + kTileM - 1) / kTileM;
+  const int nkq = args.bytes_per_desc >> 4;
+
+  for (int i = threadIdx.x * 16; i < kBBytes; i += kThreads * 16)
+    *reinterpret_cast<uint4*>(s.b + i) = *reinterpret_cast<const uint4*>(args.b_image + i);
+  if (warp == kMmaWarp) {
+    if (lane == 0) {
+      for (int i = 0; i < kASlots; ++i) {
+        ptx::mbar_init(&s.full[i], kProducerWarps * 32);
+        ptx::mbar_init(&s.empty[i], 1);
+      }
+      for (int i = 0; i < kRawStages; ++i) {
+        ptx::mbar_init(&s.raw_full[i], 1);
+        ptx::mbar_init(&s.raw_empty[i], kProducerWarps * 32);
+      }
+      for (int i = 0; i < kAccStages; ++i) {
+        ptx::mbar_init(&s.acc_full[i], 1);
+        ptx::mbar_init(&s.acc_empty[i], kEpilogueWarps * 32);
+      }
+      ptx::fence_mbar_init();
+    }
+    __syncwarp();
+    ptx::tmem_alloc(&s.tmem_base, kTmemColsA);
+    ptx::tmem_relinquish();
+  }
+  ptx::fence_proxy_async_smem();
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = s.tmem_base;
+
+  if (warp == kLoadWarp) {
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        const uint32_t st = it % kRawStages;
+        const uint32_t phase = (it / kRawStages) & 1u;
+        ptx::mbar_wait(&s.raw_empty[st], phase ^ 1u);
+        const int64_t row0 = tile * kTileM;
+        const int64_t rows = (args.n - row0) < kTileM ? (args.n - row0) : kTileM;
+        const uint32_t bytes = static_cast<uint32_t>(rows) * args.bytes_per_desc;
+        ptx::mbar_arrive_expect_tx(&s.raw_full[st], bytes);
+        ptx::bulk_load(s.raw[st], args.bits + row0 * args.bytes_per_desc, bytes, &s.raw_full[st]);
+      }
+    }
+    __syncwarp();
+  } else if (warp >= kFirstProducerWarp) {
+    // ================= producers: one TMEM lane (descriptor row) per thread =================
+    const int quadrant = warp & 3;                          // the TMEM lanes this warp may access
+    const int plane0 = ((warp - kFirstProducerWarp) >> 2) * 4;  // warps 5-8: planes 0-3, warps 9-12: planes 4-7
+    const int row = quadrant * 32 + lane;
+    uint32_t it = 0;
+    for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const uint32_t slot = it % kASlots;
+      const uint32_t phase = (it / kASlots) & 1u;
+      const uint32_t st = it % kRawStages;
+      const uint32_t raw_phase = (it / kRawStages) & 1u;
+      const int64_t rows_left = args.n - tile * kTileM;
+      ptx::mbar_wait(&s.raw_full[st], raw_phase);
+      uint32_t w[16];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (row < rows_left && c < nkq)
+          v = *reinterpret_cast<const uint4*>(s.raw[st] + row * args.bytes_per_desc + c * 16);
+        w[4 * c + 0] = v.x;
+        w[4 * c + 1] = v.y;
+        w[4 * c + 2] = v.z;
+        w[4 * c + 3] = v.w;
+      }
+      ptx::mbar_arrive(&s.raw_empty[st]);
+      ptx::mbar_wait(&s.empty[slot], phase ^ 1u);
+      ptx::tc_fence_after();
+      const uint32_t a_tmem = tmem_base + (static_cast<uint32_t>(quadrant * 32) << 16) + kATmemBase + slot * kAColsPerTile;
+#pragma unroll
+      for (int pl = 0; pl < 4; ++pl) {
+        const uint32_t m = 0x01010101u << (plane0 + pl);
+        uint32_t v[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = w[j] & m;
+        ptx::tmem_st_32x32b_x16(a_tmem + (plane0 + pl) * 16, v);
+      }
+      ptx::tmem_st_wait();
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(&s.full[slot]);
+    }
+  } else if (warp == kMmaWarp) {
+    if (lane == 0) {
+      const uint32_t b_addr = ptx::smem_u32(s.b);
+      uint32_t it = 0;
+      for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        const uint32_t slot = it % kASlots;
+        const uint32_t phase = (it / kASlots) & 1u;
+        const uint32_t acc = it % kAccStages;
+        const uint32_t acc_phase = (it / kAccStages) & 1u;
+        ptx::mbar_wait(&s.acc_empty[acc], acc_phase ^ 1u);
+        ptx::mbar_wait(&s.full[slot], phase);
+        ptx::tc_fence_after();
+        const uint32_t a_tmem = tmem_base + kATmemBase + slot * kAColsPerTile;
+        const uint32_t d_tmem = tmem_base + acc * kAccCols;
+        for (int ks = 0; ks < 16; ++ks) {   // K = 8 planes x 64 bytes, 32 per MMA = 8 columns of A
+          const uint64_t b_desc = ptx::make_smem_desc(b_addr + ks * 2 * kBLbo, kBLbo, kBSbo);
+          ptx::mma_i8_ts(d_tmem, a_tmem + ks * 8, b_desc, kIdesc, ks > 0 ? 1u : 0u);
+        }
+        ptx::tc_commit(&s.empty[slot]);
+        ptx::tc_commit(&s.acc_full[acc]);
+      }
+    }
+    __syncwarp();
+  } else {
+    // ================= epilogue (as in the smem-A kernel) =================
+    uint32_t it = 0;
+    for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const uint32_t acc = it % kAccStages;
+      const uint32_t acc_phase = (it / kAccStages) & 1u;
+      ptx::mbar_wait(&s.acc_full[acc], acc_phase);
+      ptx::tc_fence_after();
+      uint32_t v[kN];
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + acc * kAccCols;
+#pragma unroll
+      for (int c = 0; c < kN / 8; ++c) {
+        uint32_t t8[8];
+        ptx::tmem_ld_32x32b_x8(taddr + c * 8, t8);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[c * 8 + i] = t8[i];
+      }
+      ptx::tmem_ld_wait();
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(&s.acc_empty[acc]);
+      float y[kMaxDim];
+#pragma unroll
+      for (int d = 0; d < kMaxDim; ++d) {
+        long long accv = 0;
+#pragma unroll
+        for (int j = kDigits - 1; j >= 0; --j)
+          accv = accv * 256 + static_cast<int>(v[d * kDigits + j]);
+        y[d] = __ll2float_rn(accv) * args.scale[d];
+      }
+      const int64_t row0 = tile * kTileM;
+      const int64_t rows_left = args.n - row0;
+      const int row_in_tile = warp * 32 + lane;
+      if (rows_left >= kTileM) {
+        if (warp == 0 && lane == 0) ptx::bulk_wait_read<1>();
+        ptx::named_barrier_sync(1, kEpilogueWarps * 32);
+        float* o = s.out[acc] + row_in_tile * args.dim;
+#pragma unroll
+        for (int d = 0; d < kMaxDim; ++d)
+          if (d < args.dim) o[d] = y[d];
+        ptx::fence_proxy_async_smem();
+        ptx::named_barrier_sync(1, kEpilogueWarps * 32);
+        if (warp == 0 && lane == 0) {
+          ptx::bulk_store(args.out + row0 * args.dim, s.out[acc], static_cast<uint32_t>(kTileM) * args.dim * 4u);
+          ptx::bulk_commit();
+        }
+      } else if (row_in_tile < rows_left) {
+        float* o = args.out + (row0 + row_in_tile) * args.dim;
+#pragma unroll
+        for (int d = 0; d < kMaxDim; ++d)
+          if (d < args.dim) o[d] = y[d];
+      }
+    }
+    if (warp == 0 && lane == 0) ptx::bulk_wait_all();
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == kMmaWarp) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, kTmemColsA);
+  }
+}
+
 // v -> kDigits balanced base-256 digits (|digit| <= 128 except the last, which takes the rest).
 void SplitDigits(int64_t v, int8_t d[kDigits]) {
   int64_t rest = v;
@@ -337,7 +541,16 @@ cudaError_t LaunchProjection(ProjectionDevice& pd, const uint8_t* d_bits, int by
   if (bytes_per_desc % 16 != 0 || bytes_per_desc <= 0 || bytes_per_desc > kMaxDescBytes)
     return cudaErrorInvalidValue;
   if (pd.kp > bytes_per_desc * 8) return cudaErrorInvalidValue;
-  const int nkq = bytes_per_desc / 16;
+  // A operand through tensor memory when the tiles can move with TMA (MLC_PROJ_TMEM=0 selects the smem-A kernel);
+  // it always uses the B image of 64-byte descriptors (K padded to 64 bytes per plane)
+  static const bool tmem_allowed = [] {
+    const char* env = getenv("MLC_PROJ_TMEM");
+    return !(env && atoi(env) == 0);
+  }();
+  const bool aligned = reinterpret_cast<uintptr_t>(d_bits) % 16 == 0 && reinterpret_cast<uintptr_t>(d_out) % 16 == 0 &&
+                       (static_cast<size_t>(kTileM) * pd.dim * 4) % 16 == 0;
+  const bool use_tmem = tmem_allowed && aligned;
+  const int nkq = use_tmem ? kMaxDescBytes / 16 : bytes_per_desc / 16;
   if (!pd.b_image[nkq]) {
     static std::mutex mu;
     std::lock_guard<std::mutex> lock(mu);
@@ -354,19 +567,23 @@ cudaError_t LaunchProjection(ProjectionDevice& pd, const uint8_t* d_bits, int by
   a.bytes_per_desc = bytes_per_desc;
   a.k_steps = 8 * bytes_per_desc / 32;
   a.dim = pd.dim;
-  a.bulk_io = (reinterpret_cast<uintptr_t>(d_bits) % 16 == 0 && reinterpret_cast<uintptr_t>(d_out) % 16 == 0 &&
-               (static_cast<size_t>(kTileM) * pd.dim * 4) % 16 == 0)
-                  ? 1
-                  : 0;
+  a.bulk_io = aligned ? 1 : 0;
   for (int d = 0; d < kMaxDim; ++d)
     a.scale[d] = d < pd.dim ? ldexpf(1.0f, -(pd.shift[d] + 7)) : 0.f;
-  cudaError_t e = cudaFuncSetAttribute(projection_kernel,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       static_cast<int>(sizeof(Smem) + 128));
-  if (e != cudaSuccess) return e;
   const int64_t tiles = (n + kTileM - 1) / kTileM;
   const unsigned grid = static_cast<unsigned>(tiles < sm_count ? tiles : sm_count);
-  projection_kernel<<<grid, kThreads, sizeof(Smem) + 128, stream>>>(a);
+  cudaError_t e;
+  if (use_tmem) {
+    e = cudaFuncSetAttribute(projection_tmem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             static_cast<int>(sizeof(SmemT) + 128));
+    if (e != cudaSuccess) return e;
+    projection_tmem_kernel<<<grid, kThreads, sizeof(SmemT) + 128, stream>>>(a);
+  } else {
+    e = cudaFuncSetAttribute(projection_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             static_cast<int>(sizeof(Smem) + 128));
+    if (e != cudaSuccess) return e;
+    projection_kernel<<<grid, kThreads, sizeof(Smem) + 128, stream>>>(a);
+  }
   CountLaunch();
   return cudaGetLastError();
 }
