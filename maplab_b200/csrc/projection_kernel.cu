@@ -285,18 +285,19 @@ __global__ void __launch_bounds__(kThreads, 1) projection_kernel(ProjArgs args) 
 // (producer stores, tensor-core reads); here a producer thread owns one descriptor ROW (TMEM lane), ANDs its
 // 16 words with the plane masks and writes 16 columns per plane with tcgen05.st. K is padded to 64 bytes per
 // plane (descriptors shorter than 64 bytes leave zero columns), so the B image is always the 64-byte one.
-// TMEM columns: accumulators 2 x 64, A tiles 2 x 128.
+// TMEM columns: accumulators 2 x 64, A tiles 3 x 128 (the producers of tile t + 2 do not wait for the MMAs of tile t).
 // ---------------------------------------------------------------------------------------------------------
 constexpr int kTmemColsA = 512;
 constexpr int kAColsPerTile = 128;   // 8 planes x 16 columns (4 u8 per column)
 constexpr int kATmemBase = kAccStages * kAccCols;  // 128
+constexpr int kASlotsT = 3;          // A tiles in flight: 128 + 3 x 128 = 512 columns, all of TMEM
 
 struct SmemT {
   alignas(128) int8_t b[kBBytes];
   alignas(128) uint8_t raw[kRawStages][kRawBytes];
   alignas(128) float out[kAccStages][kTileM * kMaxDim];
-  alignas(8) uint64_t full[kASlots];
-  uint64_t empty[kASlots];
+  alignas(8) uint64_t full[kASlotsT];
+  uint64_t empty[kASlotsT];
   uint64_t raw_full[kRawStages];
   uint64_t raw_empty[kRawStages];
   uint64_t acc_full[kAccStages];
@@ -317,7 +318,7 @@ __global__ void __launch_bounds__(kThreads, 1) projection_tmem_kernel(ProjArgs a
     *reinterpret_cast<uint4*>(s.b + i) = *reinterpret_cast<const uint4*>(args.b_image + i);
   if (warp == kMmaWarp) {
     if (lane == 0) {
-      for (int i = 0; i < kASlots; ++i) {
+      for (int i = 0; i < kASlotsT; ++i) {
         ptx::mbar_init(&s.full[i], kProducerWarps * 32);
         ptx::mbar_init(&s.empty[i], 1);
       }
@@ -363,8 +364,8 @@ __global__ void __launch_bounds__(kThreads, 1) projection_tmem_kernel(ProjArgs a
     const int row = quadrant * 32 + lane;
     uint32_t it = 0;
     for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-      const uint32_t slot = it % kASlots;
-      const uint32_t phase = (it / kASlots) & 1u;
+      const uint32_t slot = it % kASlotsT;
+      const uint32_t phase = (it / kASlotsT) & 1u;
       const uint32_t st = it % kRawStages;
       const uint32_t raw_phase = (it / kRawStages) & 1u;
       const int64_t rows_left = args.n - tile * kTileM;
@@ -401,8 +402,8 @@ __global__ void __launch_bounds__(kThreads, 1) projection_tmem_kernel(ProjArgs a
       const uint32_t b_addr = ptx::smem_u32(s.b);
       uint32_t it = 0;
       for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-        const uint32_t slot = it % kASlots;
-        const uint32_t phase = (it / kASlots) & 1u;
+        const uint32_t slot = it % kASlotsT;
+        const uint32_t phase = (it / kASlotsT) & 1u;
         const uint32_t acc = it % kAccStages;
         const uint32_t acc_phase = (it / kAccStages) & 1u;
         ptx::mbar_wait(&s.acc_empty[acc], acc_phase ^ 1u);
