@@ -4,11 +4,19 @@
 One step = one batch of query keyframes through the whole hot path: descriptor projection
 (kernel 1) -> IMI kNN (kernels 2a/2b) -> covisibility voting/clustering (kernel 3) -> correspondence
 gather + GP3P-RANSAC verdicts (kernel 4). `value` is measured with the batch resident in HBM, `e2e`
-through the C-ABI with host buffers (H2D/D2H inside the timed region). N > 1: the inverted lists
-are sharded over the ranks (maplab_b200/sharded.py; weak scaling by default: --landmarks AND --queries
-are per GPU, so the map and the query batch of a step both grow with N), visit lists and per-shard top-k lists are exchanged over NCCL. At N = 1 the line
-also carries `roofline_at_shard_scale`: the same step on the per-GPU shard of the 50M-landmark /
-8-GPU configuration. One JSON line on stdout from rank 0. See DESIGN.md "Measurement".
+through the C-ABI with host buffers (H2D/D2H inside the timed region).
+
+N = 1: BASELINE config 2 (1 M landmarks, 1 000 query keyframes) on the numpy world the oracle diffs; the line
+carries `cpu_baseline` (the oracle on the same step) and `parity_checked` (GPU verdicts == oracle verdicts).
+N > 1 (torchrun, one rank per GPU): weak scaling — `--landmarks` AND `--queries` are per GPU — on the
+counter-based world generated on the GPUs (maplab_b200/synthetic_gpu.py). The index is replicated when it fits
+a quarter of one GPU's HBM (the batch is split, nothing crosses the GPUs) and sharded otherwise
+(mlc_sharded_query_batch: NCCL all-gather + all-to-all inside the library); the placement the policy did not
+choose is measured on the same workload and reported as `other_placement_same_workload`.
+Every line also carries the configurations north_star names beside the headline one, the same fixed workload at
+every N: `north_star_10m` / `north_star_50m` (1 000 query keyframes against the 10 M / 50 M-landmark map, sharded as
+north_star specifies, replicated beside it) and `knn_100m` (BASELINE config 5), each with its scan roofline and a
+verdict checksum that must be identical at every N. One JSON line on stdout from rank 0. See DESIGN.md §5-6.
 """
 import argparse
 import json

@@ -1,5 +1,13 @@
-"""Sharded loop-closure query step: one process per GPU, the inverted lists of the
-database sharded over the ranks (descriptor i lives on rank i % G), everything else replicated.
+"""Host-side mirror of the sharded loop-closure query step over torch.distributed.
+
+The PRODUCT path of this step is inside the library: mlc_comm_* + mlc_sharded_query_batch (csrc/sharded.cu, NCCL
+bound at run time; capi.Detector.sharded_query_batch) — bench.py and the multi-GPU tests go through that. This
+module keeps the same schedule in Python so that the exchange logic can be exercised on CPU at world size 2 over
+gloo (tests/test_sharded_gloo.py, with the oracle as per-rank compute), and as a reference for hosts that drive
+the per-stage entry points themselves (mlc_coarse_device / mlc_scan_device / mlc_merge_topk_device).
+
+One process per GPU, the inverted lists of the database sharded over the ranks (descriptor i lives on rank
+i % G), everything else replicated.
 
 Per step every rank
   1. projects and coarse-searches ITS slice of the query keyframes (kernels 1, 2a),
