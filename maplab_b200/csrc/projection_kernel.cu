@@ -127,7 +127,7 @@ __global__ void __launch_bounds__(kThreads, 1) projection_kernel(ProjArgs args) 
 
   if (warp == kLoadWarp) {
     // ================= TMA loads: one bulk copy per 128-descriptor tile =================
-    if (lane == 0) {
+    if (ptx::elect_one()) {
       uint32_t it = 0;
       for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
         const uint32_t st = it % kRawStages;
@@ -192,7 +192,7 @@ __global__ void __launch_bounds__(kThreads, 1) projection_kernel(ProjArgs args) 
     }
   } else if (warp == kMmaWarp) {
     // ================= MMA issuer =================
-    if (lane == 0) {
+    if (ptx::elect_one()) {
       const uint32_t b_addr = ptx::smem_u32(s.b);
       uint32_t it = 0;
       for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
@@ -225,6 +225,9 @@ __global__ void __launch_bounds__(kThreads, 1) projection_kernel(ProjArgs args) 
       ptx::tc_fence_after();
       uint32_t v[kN];
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + acc * kAccCols;
+      // x8 loads, which ptxas interleaves with the arithmetic below: with ONE epilogue group that hides more than
+      // the later release of the accumulator costs (22.9 against 20.0 G descriptors/s for the batched form of
+      // projection_tmem_kernel)
 #pragma unroll
       for (int c = 0; c < kN / 8; ++c) {
         uint32_t t8[8];
@@ -293,21 +296,32 @@ constexpr int kTmemColsA = 512;
 constexpr int kAColsPerTile = 128;   // 8 planes x 16 columns (4 u8 per column)
 constexpr int kATmemBase = kAccStages * kAccCols;  // 128
 constexpr int kASlotsT = 3;          // A tiles in flight: 128 + 3 x 128 = 512 columns, all of TMEM
+// Warp roles: two epilogue groups of 4 warps (group g drains accumulator g = the tiles with it % 2 == g; one
+// group alone is a serial chain of ~1 500 cycles per tile — tcgen05.ld, int64 recombination, staging, bulk
+// store — and paced the kernel), MMA issuer, TMA loader, 8 producers.
+constexpr int kEpiGroupsT = 2;
+constexpr int kMmaWarpT = 4 * kEpiGroupsT;                 // 8
+constexpr int kLoadWarpT = kMmaWarpT + 1;                  // 9
+constexpr int kFirstProducerWarpT = kLoadWarpT + 1;        // 10
+constexpr int kThreadsT = (kFirstProducerWarpT + kProducerWarps) * 32;  // 576
+constexpr int kRawStagesT = 8;       // 64 KB of descriptor tiles in flight per SM (4 stages cap the loads at 3 TB/s)
+static_assert(kAccStages == kEpiGroupsT, "one accumulator per epilogue group");
 
 struct SmemT {
   alignas(128) int8_t b[kBBytes];
-  alignas(128) uint8_t raw[kRawStages][kRawBytes];
-  alignas(128) float out[kAccStages][kTileM * kMaxDim];
+  alignas(128) uint8_t raw[kRawStagesT][kRawBytes];
+  alignas(128) float out[kEpiGroupsT][kTileM * kMaxDim];
   alignas(8) uint64_t full[kASlotsT];
   uint64_t empty[kASlotsT];
-  uint64_t raw_full[kRawStages];
-  uint64_t raw_empty[kRawStages];
+  uint64_t raw_full[kRawStagesT];
+  uint64_t raw_empty[kRawStagesT];
   uint64_t acc_full[kAccStages];
   uint64_t acc_empty[kAccStages];
   uint32_t tmem_base;
+  uint32_t zero;   // see the epilogue
 };
 
-__global__ void __launch_bounds__(kThreads, 1) projection_tmem_kernel(ProjArgs args) {
+__global__ void __launch_bounds__(kThreadsT, 1) projection_tmem_kernel(ProjArgs args) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   SmemT& s = *reinterpret_cast<SmemT*>(
       smem_raw + ((128u - (ptx::smem_u32(smem_raw) & 127u)) & 127u));
@@ -316,23 +330,24 @@ __global__ void __launch_bounds__(kThreads, 1) projection_tmem_kernel(ProjArgs a
   const int64_t num_tiles = (args.n + kTileM - 1) / kTileM;
   const int nkq = args.bytes_per_desc >> 4;
 
-  for (int i = threadIdx.x * 16; i < kBBytes; i += kThreads * 16)
+  for (int i = threadIdx.x * 16; i < kBBytes; i += kThreadsT * 16)
     *reinterpret_cast<uint4*>(s.b + i) = *reinterpret_cast<const uint4*>(args.b_image + i);
-  if (warp == kMmaWarp) {
+  if (warp == kMmaWarpT) {
     if (lane == 0) {
       for (int i = 0; i < kASlotsT; ++i) {
         ptx::mbar_init(&s.full[i], kProducerWarps * 32);
         ptx::mbar_init(&s.empty[i], 1);
       }
-      for (int i = 0; i < kRawStages; ++i) {
+      for (int i = 0; i < kRawStagesT; ++i) {
         ptx::mbar_init(&s.raw_full[i], 1);
         ptx::mbar_init(&s.raw_empty[i], kProducerWarps * 32);
       }
       for (int i = 0; i < kAccStages; ++i) {
         ptx::mbar_init(&s.acc_full[i], 1);
-        ptx::mbar_init(&s.acc_empty[i], kEpilogueWarps * 32);
+        ptx::mbar_init(&s.acc_empty[i], 4 * 32);
       }
       ptx::fence_mbar_init();
+      s.zero = 0;
     }
     __syncwarp();
     ptx::tmem_alloc(&s.tmem_base, kTmemColsA);
@@ -344,12 +359,12 @@ __global__ void __launch_bounds__(kThreads, 1) projection_tmem_kernel(ProjArgs a
   ptx::tc_fence_after();
   const uint32_t tmem_base = s.tmem_base;
 
-  if (warp == kLoadWarp) {
-    if (lane == 0) {
+  if (warp == kLoadWarpT) {
+    if (ptx::elect_one()) {
       uint32_t it = 0;
       for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-        const uint32_t st = it % kRawStages;
-        const uint32_t phase = (it / kRawStages) & 1u;
+        const uint32_t st = it % kRawStagesT;
+        const uint32_t phase = (it / kRawStagesT) & 1u;
         ptx::mbar_wait(&s.raw_empty[st], phase ^ 1u);
         const int64_t row0 = tile * kTileM;
         const int64_t rows = (args.n - row0) < kTileM ? (args.n - row0) : kTileM;
@@ -359,17 +374,17 @@ __global__ void __launch_bounds__(kThreads, 1) projection_tmem_kernel(ProjArgs a
       }
     }
     __syncwarp();
-  } else if (warp >= kFirstProducerWarp) {
+  } else if (warp >= kFirstProducerWarpT) {
     // ================= producers: one TMEM lane (descriptor row) per thread =================
-    const int quadrant = warp & 3;                          // the TMEM lanes this warp may access
-    const int plane0 = ((warp - kFirstProducerWarp) >> 2) * 4;  // warps 5-8: planes 0-3, warps 9-12: planes 4-7
+    const int quadrant = warp & 3;                               // the TMEM lanes this warp may access
+    const int plane0 = ((warp - kFirstProducerWarpT) >> 2) * 4;  // first four warps: planes 0-3, the others 4-7
     const int row = quadrant * 32 + lane;
     uint32_t it = 0;
     for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const uint32_t slot = it % kASlotsT;
       const uint32_t phase = (it / kASlotsT) & 1u;
-      const uint32_t st = it % kRawStages;
-      const uint32_t raw_phase = (it / kRawStages) & 1u;
+      const uint32_t st = it % kRawStagesT;
+      const uint32_t raw_phase = (it / kRawStagesT) & 1u;
       const int64_t rows_left = args.n - tile * kTileM;
       ptx::mbar_wait(&s.raw_full[st], raw_phase);
       uint32_t w[16];
@@ -402,8 +417,8 @@ __global__ void __launch_bounds__(kThreads, 1) projection_tmem_kernel(ProjArgs a
       ptx::tc_fence_before();
       ptx::mbar_arrive(&s.full[slot]);
     }
-  } else if (warp == kMmaWarp) {
-    if (lane == 0) {
+  } else if (warp == kMmaWarpT) {
+    if (ptx::elect_one()) {   // not `lane == 0`: see ptx::elect_one
       const uint32_t b_addr = ptx::smem_u32(s.b);
       uint32_t it = 0;
       for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
@@ -416,6 +431,7 @@ __global__ void __launch_bounds__(kThreads, 1) projection_tmem_kernel(ProjArgs a
         ptx::tc_fence_after();
         const uint32_t a_tmem = tmem_base + kATmemBase + slot * kAColsPerTile;
         const uint32_t d_tmem = tmem_base + acc * kAccCols;
+#pragma unroll
         for (int ks = 0; ks < 16; ++ks) {   // K = 8 planes x 64 bytes, 32 per MMA = 8 columns of A
           const uint64_t b_desc = ptx::make_smem_desc(b_addr + ks * 2 * kBLbo, kBLbo, kBSbo);
           ptx::mma_i8_ts(d_tmem, a_tmem + ks * 8, b_desc, kIdesc, ks > 0 ? 1u : 0u);
@@ -426,48 +442,53 @@ __global__ void __launch_bounds__(kThreads, 1) projection_tmem_kernel(ProjArgs a
     }
     __syncwarp();
   } else {
-    // ================= epilogue (as in the smem-A kernel) =================
-    uint32_t it = 0;
-    for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-      const uint32_t acc = it % kAccStages;
-      const uint32_t acc_phase = (it / kAccStages) & 1u;
-      ptx::mbar_wait(&s.acc_full[acc], acc_phase);
+    // ================= epilogue: group g = warp / 4 drains accumulator g =================
+    const int group = warp >> 2;
+    const int quadrant = warp & 3;
+    const bool issuer = quadrant == 0 && lane == 0;   // bulk groups are per-thread state: always the same thread
+    uint32_t round = 0;
+    for (int64_t tile = blockIdx.x + static_cast<int64_t>(group) * gridDim.x; tile < num_tiles;
+         tile += static_cast<int64_t>(kEpiGroupsT) * gridDim.x, ++round) {
+      ptx::mbar_wait(&s.acc_full[group], round & 1u);
       ptx::tc_fence_after();
       uint32_t v[kN];
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + acc * kAccCols;
-#pragma unroll
-      for (int c = 0; c < kN / 8; ++c) {
-        uint32_t t8[8];
-        ptx::tmem_ld_32x32b_x8(taddr + c * 8, t8);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) v[c * 8 + i] = t8[i];
-      }
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quadrant * 32) << 16) + group * kAccCols;
+      static_assert(kN == 64, "the accumulator row is 64 columns");
+      ptx::tmem_ld_32x32b_64cols<4>(taddr, v);
       ptx::tmem_ld_wait();
       ptx::tc_fence_before();
-      ptx::mbar_arrive(&s.acc_empty[acc]);
+      ptx::mbar_arrive(&s.acc_empty[group]);
+      {
+        // s.zero is 0. The volatile load sits behind the arrive, so no arithmetic on v[] can be scheduled between
+        // the four tcgen05.ld (ptx::tmem_ld_32x32b_64cols).
+        const uint32_t z = *reinterpret_cast<volatile uint32_t*>(&s.zero);
+#pragma unroll
+        for (int c = 0; c < kN; ++c) v[c] ^= z;
+      }
       float y[kMaxDim];
 #pragma unroll
       for (int d = 0; d < kMaxDim; ++d) {
-        long long accv = 0;
+        // sum_j digit_j * 256^j, |.| < 2^43: 32 x 32 -> 64-bit multiply-adds, digit 4 lands in the high word
+        long long accv = static_cast<long long>(static_cast<int>(v[d * kDigits + 0]));
 #pragma unroll
-        for (int j = kDigits - 1; j >= 0; --j)
-          accv = accv * 256 + static_cast<int>(v[d * kDigits + j]);
+        for (int j = 1; j < kDigits; ++j)
+          accv += static_cast<long long>(static_cast<int>(v[d * kDigits + j])) * (1ll << (8 * j));
         y[d] = __ll2float_rn(accv) * args.scale[d];
       }
       const int64_t row0 = tile * kTileM;
       const int64_t rows_left = args.n - row0;
-      const int row_in_tile = warp * 32 + lane;
+      const int row_in_tile = quadrant * 32 + lane;
       if (rows_left >= kTileM) {
-        if (warp == 0 && lane == 0) ptx::bulk_wait_read<1>();
-        ptx::named_barrier_sync(1, kEpilogueWarps * 32);
-        float* o = s.out[acc] + row_in_tile * args.dim;
+        if (issuer) ptx::bulk_wait_read<0>();      // the group's previous store has read s.out[group]
+        ptx::named_barrier_sync(1 + group, 4 * 32);
+        float* o = s.out[group] + row_in_tile * args.dim;
 #pragma unroll
         for (int d = 0; d < kMaxDim; ++d)
           if (d < args.dim) o[d] = y[d];
         ptx::fence_proxy_async_smem();
-        ptx::named_barrier_sync(1, kEpilogueWarps * 32);
-        if (warp == 0 && lane == 0) {
-          ptx::bulk_store(args.out + row0 * args.dim, s.out[acc], static_cast<uint32_t>(kTileM) * args.dim * 4u);
+        ptx::named_barrier_sync(1 + group, 4 * 32);
+        if (issuer) {
+          ptx::bulk_store(args.out + row0 * args.dim, s.out[group], static_cast<uint32_t>(kTileM) * args.dim * 4u);
           ptx::bulk_commit();
         }
       } else if (row_in_tile < rows_left) {
@@ -477,12 +498,12 @@ __global__ void __launch_bounds__(kThreads, 1) projection_tmem_kernel(ProjArgs a
           if (d < args.dim) o[d] = y[d];
       }
     }
-    if (warp == 0 && lane == 0) ptx::bulk_wait_all();
+    if (issuer) ptx::bulk_wait_all();
   }
 
   ptx::tc_fence_before();
   __syncthreads();
-  if (warp == kMmaWarp) {
+  if (warp == kMmaWarpT) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc(tmem_base, kTmemColsA);
   }
@@ -583,7 +604,7 @@ cudaError_t LaunchProjection(ProjectionDevice& pd, const uint8_t* d_bits, int by
     e = cudaFuncSetAttribute(projection_tmem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              static_cast<int>(sizeof(SmemT) + 128));
     if (e != cudaSuccess) return e;
-    projection_tmem_kernel<<<grid, kThreads, sizeof(SmemT) + 128, stream>>>(a);
+    projection_tmem_kernel<<<grid, kThreadsT, sizeof(SmemT) + 128, stream>>>(a);
   } else {
     e = cudaFuncSetAttribute(projection_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              static_cast<int>(sizeof(Smem) + 128));
