@@ -587,22 +587,31 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) gp3p_eliminate_kernel(Ran
 }
 
 // Eigenvalues of the 8x8 action matrix: EIGHT lanes per hypothesis. The matrix lives in shared
-// memory; every scalar quantity of orthes/hqr is evaluated redundantly by the 8 lanes (same
-// operations, same order), the row/column update loops — whose iterations are independent — are
-// dealt one row or column per lane. Bit-identical to the sequential Hessenberg()/HqrEigenvalues().
+// memory; the row/column update loops — whose iterations are independent — are dealt one row or column per
+// lane. The SCALAR work of orthes/hqr is dealt to the lanes too wherever its pieces are independent (same
+// operations on the same operands, only evaluated by another lane, so still bit-identical to the sequential
+// Hessenberg()/HqrEigenvalues()): the divisions of one step (p/x q/x r/x; p/s q/s r/s q/p r/p; the
+// Householder vector a(i,m-1)/scale) run as ONE division over the lanes and are handed round with shuffles,
+// and the two searches (small subdiagonal l, start row m of the double shift) test all candidates at once and
+// take the first hit in the order of the sequential loop. fp64 division and sqrt are ~15-instruction sequences;
+// the redundant version spent most of its instructions there.
 #define A_(i, j) a[(i) * 8 + (j)]
+#define GSHFL(v, src) __shfl_sync(gm, (v), (src), 8)
 __device__ void HessenbergGroup(double* a, int L, unsigned gm) {
-  double ort[N8];
   const int high = N8 - 1;
+#pragma unroll
   for (int m = 1; m <= high - 1; ++m) {
     double scale = 0.0;
+#pragma unroll
     for (int i = m; i <= high; ++i) scale += fabs(A_(i, m - 1));
     if (scale != 0.0) {
+      const double mine = (L >= m) ? A_(L, m - 1) / scale : 0.0;  // ort[L]
+      double ort[N8];
+#pragma unroll
+      for (int i = 0; i < N8; ++i) ort[i] = (i >= m) ? GSHFL(mine, i) : 0.0;
       double h = 0.0;
-      for (int i = high; i >= m; --i) {
-        ort[i] = A_(i, m - 1) / scale;
-        h += ort[i] * ort[i];
-      }
+#pragma unroll
+      for (int i = high; i >= m; --i) h += ort[i] * ort[i];
       double g = sqrt(h);
       if (ort[m] > 0) g = -g;
       h -= ort[m] * g;
@@ -611,16 +620,20 @@ __device__ void HessenbergGroup(double* a, int L, unsigned gm) {
       if (L >= m) {    // column L
         const int j = L;
         double fsum = 0.0;
+#pragma unroll
         for (int i = high; i >= m; --i) fsum += ort[i] * A_(i, j);
         fsum /= h;
+#pragma unroll
         for (int i = m; i <= high; ++i) A_(i, j) -= fsum * ort[i];
       }
       __syncwarp(gm);
       {  // row L
         const int i = L;
         double fsum = 0.0;
+#pragma unroll
         for (int j = high; j >= m; --j) fsum += ort[j] * A_(i, j);
         fsum /= h;
+#pragma unroll
         for (int j = m; j <= high; ++j) A_(i, j) -= fsum * ort[j];
       }
       __syncwarp(gm);
@@ -634,8 +647,9 @@ __device__ void HessenbergGroup(double* a, int L, unsigned gm) {
 }
 
 __device__ bool HqrGroup(double* a, double* wr, double* wi, int L, unsigned gm) {
+  const int base = __ffs(gm) - 1;  // first lane of the group
   int nn, m, l, k, j, its, i, mmin;
-  double z, y, x, w, v, u, t, s, r = 0, q = 0, p = 0, anorm = 0.0;
+  double z, y, x, w, t, s, r = 0, q = 0, p = 0, anorm = 0.0;
   for (i = 0; i < N8; i++)
     for (j = (i - 1 > 0 ? i - 1 : 0); j < N8; j++) anorm += fabs(A_(i, j));
   nn = N8 - 1;
@@ -643,14 +657,22 @@ __device__ bool HqrGroup(double* a, double* wr, double* wi, int L, unsigned gm) 
   while (nn >= 0) {
     its = 0;
     do {
-      for (l = nn; l >= 1; l--) {
-        s = fabs(A_(l - 1, l - 1)) + fabs(A_(l, l));
-        if (s == 0.0) s = anorm;
-        if (fabs(A_(l, l - 1)) + s == s) {
+      {
+        // small subdiagonal element: candidates l = nn, nn-1, .. 1 on lanes 0, 1, ..; the first hit counts
+        const int lj = nn - L;
+        bool hit = false;
+        if (lj >= 1) {
+          double ss = fabs(A_(lj - 1, lj - 1)) + fabs(A_(lj, lj));
+          if (ss == 0.0) ss = anorm;
+          hit = fabs(A_(lj, lj - 1)) + ss == ss;
+        }
+        const unsigned hits = (__ballot_sync(gm, hit) >> base) & 0xFFu;
+        l = 0;
+        if (hits) {
+          l = nn - (__ffs(hits) - 1);
           __syncwarp(gm);
           if (L == 0) A_(l, l - 1) = 0.0;
           __syncwarp(gm);
-          break;
         }
       }
       x = A_(nn, nn);
@@ -692,21 +714,37 @@ __device__ bool HqrGroup(double* a, double* wr, double* wi, int L, unsigned gm) 
             w = -0.4375 * s * s;
           }
           ++its;
-          for (m = (nn - 2); m >= l; m--) {
-            z = A_(m, m);
-            r = x - z;
-            s = y - z;
-            p = (r * s - w) / A_(m + 1, m) + A_(m, m + 1);
-            q = A_(m + 1, m + 1) - z - r - s;
-            r = A_(m + 2, m + 1);
-            s = fabs(p) + fabs(q) + fabs(r);
-            p /= s;
-            q /= s;
-            r /= s;
-            if (m == l) break;
-            u = fabs(A_(m, m - 1)) * (fabs(q) + fabs(r));
-            v = fabs(p) * (fabs(A_(m - 1, m - 1)) + fabs(z) + fabs(A_(m + 1, m + 1)));
-            if (u + v == v) break;
+          {
+            // start row of the double shift: candidates m = nn-2, nn-3, .. l on lanes 0, 1, ..; the sequential
+            // loop stops at the first (largest) m with m == l or a negligible subdiagonal product
+            const int mj = nn - 2 - L;
+            bool stop = false;
+            double pj = 0.0, qj = 0.0, rj = 0.0;
+            if (mj >= l) {
+              const double zz = A_(mj, mj);
+              const double rr = x - zz;
+              double ss = y - zz;
+              pj = (rr * ss - w) / A_(mj + 1, mj) + A_(mj, mj + 1);
+              qj = A_(mj + 1, mj + 1) - zz - rr - ss;
+              rj = A_(mj + 2, mj + 1);
+              ss = fabs(pj) + fabs(qj) + fabs(rj);
+              pj /= ss;
+              qj /= ss;
+              rj /= ss;
+              if (mj == l) {
+                stop = true;
+              } else {
+                const double uu = fabs(A_(mj, mj - 1)) * (fabs(qj) + fabs(rj));
+                const double vv = fabs(pj) * (fabs(A_(mj - 1, mj - 1)) + fabs(zz) + fabs(A_(mj + 1, mj + 1)));
+                stop = uu + vv == vv;
+              }
+            }
+            const unsigned stops = (__ballot_sync(gm, stop) >> base) & 0xFFu;
+            const int js = __ffs(stops) - 1;  // the lane with m == l always stops
+            m = nn - 2 - js;
+            p = GSHFL(pj, js);
+            q = GSHFL(qj, js);
+            r = GSHFL(rj, js);
           }
           __syncwarp(gm);
           if (L >= m + 2 && L <= nn) {
@@ -721,9 +759,11 @@ __device__ bool HqrGroup(double* a, double* wr, double* wi, int L, unsigned gm) 
               r = 0.0;
               if (k != (nn - 1)) r = A_(k + 2, k - 1);
               if ((x = fabs(p) + fabs(q) + fabs(r)) != 0.0) {
-                p /= x;
-                q /= x;
-                r /= x;
+                // p /= x, q /= x, r /= x on lanes 0, 1, 2
+                const double quo = (L == 0 ? p : (L == 1 ? q : r)) / x;
+                p = GSHFL(quo, 0);
+                q = GSHFL(quo, 1);
+                r = GSHFL(quo, 2);
               }
             }
             if ((s = SignOf(sqrt(p * p + q * q + r * r), p)) != 0.0) {
@@ -736,11 +776,17 @@ __device__ bool HqrGroup(double* a, double* wr, double* wi, int L, unsigned gm) 
                 }
               }
               p += s;
-              x = p / s;
-              y = q / s;
-              z = r / s;
-              q /= p;
-              r /= p;
+              {
+                // x = p / s, y = q / s, z = r / s, q /= p, r /= p on lanes 0 .. 4
+                const double num = (L == 0 ? p : ((L == 1 || L == 3) ? q : r));
+                const double den = L < 3 ? s : p;
+                const double quo = num / den;
+                x = GSHFL(quo, 0);
+                y = GSHFL(quo, 1);
+                z = GSHFL(quo, 2);
+                q = GSHFL(quo, 3);
+                r = GSHFL(quo, 4);
+              }
               __syncwarp(gm);
               if (L >= k && L <= nn) {  // row modification, column L
                 j = L;
@@ -773,6 +819,7 @@ __device__ bool HqrGroup(double* a, double* wr, double* wi, int L, unsigned gm) 
   }
   return true;
 }
+#undef GSHFL
 #undef A_
 
 // GPW = hypotheses (8-lane groups) per warp. The QR iteration is data dependent, so the groups of
