@@ -235,7 +235,7 @@ class Detector {
   // coarse search of chunk i overlap the copy of chunk i+1
   cudaStream_t copy_stream_ = nullptr;
   cudaStream_t ransac_stream_[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // extra streams of the RANSAC problem groups
-  cudaEvent_t ev_ransac_[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev_ransac_[13] = {};  // [0, 5): group g + 1 joined; [6]: fork; [7, 13): last enqueued round of group g done
   int* h_remaining_ = nullptr;  // pinned round counters
   std::vector<double> priors_;  // T_G_I of the query vertices of the next call (delta-pose gate)
   bool have_priors_ = false;

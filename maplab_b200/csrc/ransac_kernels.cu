@@ -1350,34 +1350,49 @@ bool Detector::RansacOnDevice(const mlc_ransac_settings& rs, const mlc_camera* c
     if (v == 1 || v == 2 || v == 4) eigen_gpw = v;
   }
   const int max_rounds = 11 * rs.num_ransac_iters + 4;  // >= one consumed sample per round
-  for (int round = 0; round < max_rounds; ++round) {
-    bool any = false;
+  // One round of one group: six kernels, the count of its still-running problems to the host, an event.
+  auto enqueue_round = [&](int g) -> bool {
+    const int64_t np = ga[g].num_problems, nh = np * hyp_slots;
+    cudaStream_t st = g_stream[g];
+    const unsigned elim_blocks = static_cast<unsigned>(std::min<int64_t>(
+        (nh + kWarpsPerBlock - 1) / kWarpsPerBlock, static_cast<int64_t>(sm_count_) * elim_per_sm));
+    if (!Cuda(cudaMemsetAsync(d_remaining_all + g, 0, sizeof(int), st), "memset", err)) return false;
+    ransac_sample_kernel<<<blocks_of(np, 128), 128, 0, st>>>(ga[g], g_state[g], g_hyp[g]);
+    gp3p_eliminate_kernel<<<elim_blocks, kWarpsPerBlock * 32, smem, st>>>(ga[g], g_hyp[g], nh);
+    if (eigen_gpw == 1) gp3p_eigen_kernel<1><<<blocks_of(nh, 4), 128, 0, st>>>(g_hyp[g], nh);
+    else if (eigen_gpw == 2) gp3p_eigen_kernel<2><<<blocks_of(nh, 8), 128, 0, st>>>(g_hyp[g], nh);
+    else gp3p_eigen_kernel<4><<<blocks_of(nh, 16), 128, 0, st>>>(g_hyp[g], nh);
+    gp3p_candidate_kernel<<<blocks_of(nh * 8, 64), 64, 0, st>>>(ga[g], g_hyp[g], nh);
+    ransac_score_kernel<<<blocks_of(nh * 32, 128), 128, 0, st>>>(ga[g], g_hyp[g], nh);
+    ransac_update_kernel<<<blocks_of(np, 128), 128, 0, st>>>(ga[g], g_state[g], g_hyp[g], d_remaining_all + g);
+    for (int i = 0; i < 6; ++i) CountLaunch();
+    return Cuda(cudaMemcpyAsync(&remaining_h[g], d_remaining_all + g, sizeof(int), cudaMemcpyDeviceToHost, st), "D2H", err) &&
+           Cuda(cudaEventRecord(ev_ransac_[7 + g], st), "event", err);
+  };
+  // The groups advance independently: the host polls the groups' round events, and a group whose round is
+  // through either gets its next round or is finalized at once — no group waits for another one's round. A
+  // large batch practically always needs a second round (the first one speculates first_hyp < k hypotheses
+  // for most problems), so two rounds are enqueued up front: a round that finds every problem done costs six
+  // near-empty launches, a host round trip between the rounds costs the idle GPU more.
+  const int upfront = (groups >= 2 && a.first_hyp < hyp_slots) ? 2 : 1;
+  int rounds[kRansacGroups] = {};
+  int live = 0;
+  for (int r = 0; r < upfront; ++r)
     for (int g = 0; g < groups; ++g) {
       if (!active[g]) continue;
-      any = true;
-      const int64_t np = ga[g].num_problems, nh = np * hyp_slots;
-      cudaStream_t st = g_stream[g];
-      const unsigned elim_blocks = static_cast<unsigned>(std::min<int64_t>(
-          (nh + kWarpsPerBlock - 1) / kWarpsPerBlock, static_cast<int64_t>(sm_count_) * elim_per_sm));
-      if (!Cuda(cudaMemsetAsync(d_remaining_all + g, 0, sizeof(int), st), "memset", err)) return false;
-      ransac_sample_kernel<<<blocks_of(np, 128), 128, 0, st>>>(ga[g], g_state[g], g_hyp[g]);
-      gp3p_eliminate_kernel<<<elim_blocks, kWarpsPerBlock * 32, smem, st>>>(ga[g], g_hyp[g], nh);
-      if (eigen_gpw == 1) gp3p_eigen_kernel<1><<<blocks_of(nh, 4), 128, 0, st>>>(g_hyp[g], nh);
-      else if (eigen_gpw == 2) gp3p_eigen_kernel<2><<<blocks_of(nh, 8), 128, 0, st>>>(g_hyp[g], nh);
-      else gp3p_eigen_kernel<4><<<blocks_of(nh, 16), 128, 0, st>>>(g_hyp[g], nh);
-      gp3p_candidate_kernel<<<blocks_of(nh * 8, 64), 64, 0, st>>>(ga[g], g_hyp[g], nh);
-      ransac_score_kernel<<<blocks_of(nh * 32, 128), 128, 0, st>>>(ga[g], g_hyp[g], nh);
-      ransac_update_kernel<<<blocks_of(np, 128), 128, 0, st>>>(ga[g], g_state[g], g_hyp[g], d_remaining_all + g);
-      for (int i = 0; i < 6; ++i) CountLaunch();
-      if (!Cuda(cudaMemcpyAsync(&remaining_h[g], d_remaining_all + g, sizeof(int), cudaMemcpyDeviceToHost, st), "D2H", err))
-        return false;
+      if (!enqueue_round(g)) return false;
+      ++rounds[g];
+      if (r == 0) ++live;
     }
-    if (!any) break;
+  while (live > 0) {
     for (int g = 0; g < groups; ++g) {
       if (!active[g]) continue;
-      if (!Cuda(cudaStreamSynchronize(g_stream[g]), "ransac round", err)) return false;
+      const cudaError_t q = cudaEventQuery(ev_ransac_[7 + g]);
+      if (q == cudaErrorNotReady) continue;
+      if (!Cuda(q, "ransac round", err)) return false;
       if (remaining_h[g] == 0) {
         active[g] = false;  // this group is done: finalize it right away on its stream
+        --live;
         ransac_finalize_kernel<<<blocks_of(ga[g].num_problems * 32, 128), 128, 0, g_stream[g]>>>(ga[g], g_state[g]);
         CountLaunch();
         if (g > 0) {
@@ -1385,13 +1400,13 @@ bool Detector::RansacOnDevice(const mlc_ransac_settings& rs, const mlc_camera* c
               !Cuda(cudaStreamWaitEvent(stream_, ev_ransac_[g - 1], 0), "wait", err))
             return false;
         }
+      } else {
+        if (++rounds[g] > max_rounds) {  // cannot happen: every round consumes a sample
+          *err = "RANSAC round limit reached";
+          return false;
+        }
+        if (!enqueue_round(g)) return false;
       }
-    }
-  }
-  for (int g = 0; g < groups; ++g) {
-    if (active[g]) {  // round limit reached (cannot happen: every round consumes a sample)
-      *err = "RANSAC round limit reached";
-      return false;
     }
   }
   cudaEventRecord(ev_stage_[5], stream_);
