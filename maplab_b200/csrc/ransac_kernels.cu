@@ -49,7 +49,7 @@ constexpr int kWarpsPerBlock = 4;
 constexpr int kHyp = 16;      // hypothesis slots per problem (default)
 constexpr int kHypMax = 32;   // ... when the batch is small enough to speculate deeper for free
 constexpr int kRansacGroups = 6;  // problem groups pipelined on separate streams
-constexpr int kHypFirst = 12; // speculated in the first round (k is still unknown) when the batch fills the GPU
+constexpr int kHypFirst = 10; // speculated in the first round (k is still unknown) when the batch fills the GPU; 8 / 9 / 10 / 11 / 12 / 14: 1.39 / 1.23 / 1.24 / 1.25 / 1.26 / 1.33 ms per 1000 problems
 
 struct RansacArgs {
   int first_hyp;                // hypotheses speculated per problem in the first round
@@ -1374,7 +1374,11 @@ bool Detector::RansacOnDevice(const mlc_ransac_settings& rs, const mlc_camera* c
   // large batch practically always needs a second round (the first one speculates first_hyp < k hypotheses
   // for most problems), so two rounds are enqueued up front: a round that finds every problem done costs six
   // near-empty launches, a host round trip between the rounds costs the idle GPU more.
-  const int upfront = (groups >= 2 && a.first_hyp < hyp_slots) ? 2 : 1;
+  int upfront = (groups >= 2 && a.first_hyp < hyp_slots) ? 2 : 1;
+  if (const char* env = getenv("MLC_RANSAC_UPFRONT")) {
+    const int v = atoi(env);
+    if (v >= 1 && v <= 4) upfront = v;
+  }
   int rounds[kRansacGroups] = {};
   int live = 0;
   for (int r = 0; r < upfront; ++r)
