@@ -376,9 +376,15 @@ __global__ void __launch_bounds__(kThreadsT, 1) projection_tmem_kernel(ProjArgs 
     __syncwarp();
   } else if (warp >= kFirstProducerWarpT) {
     // ================= producers: one TMEM lane (descriptor row) per thread =================
+    // The two warps of a lane quadrant split the row: 32 bytes (two 16-byte chunks) x 8 planes each. Rows are
+    // 64 bytes apart, so eight lanes reading the same chunk of their rows hit two bank groups (4-way conflict,
+    // and the shared-memory pipe was the busiest unit of the kernel: 77 %); here odd row PAIRS read their two
+    // chunks in the other order (2-way) and swap them back in registers.
     const int quadrant = warp & 3;                               // the TMEM lanes this warp may access
-    const int plane0 = ((warp - kFirstProducerWarpT) >> 2) * 4;  // first four warps: planes 0-3, the others 4-7
+    const int chunk0 = ((warp - kFirstProducerWarpT) >> 2) * 2;  // first four warps: chunks 0-1, the others 2-3
     const int row = quadrant * 32 + lane;
+    const bool swapped = (row >> 1) & 1;
+    const int ca = chunk0 + (swapped ? 1 : 0), cb = chunk0 + (swapped ? 0 : 1);
     uint32_t it = 0;
     for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const uint32_t slot = it % kASlotsT;
@@ -387,27 +393,25 @@ __global__ void __launch_bounds__(kThreadsT, 1) projection_tmem_kernel(ProjArgs 
       const uint32_t raw_phase = (it / kRawStagesT) & 1u;
       const int64_t rows_left = args.n - tile * kTileM;
       ptx::mbar_wait(&s.raw_full[st], raw_phase);
-      uint32_t w[16];
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        uint4 v = make_uint4(0, 0, 0, 0);
-        if (row < rows_left && c < nkq)
-          v = *reinterpret_cast<const uint4*>(s.raw[st] + row * args.bytes_per_desc + c * 16);
-        w[4 * c + 0] = v.x;
-        w[4 * c + 1] = v.y;
-        w[4 * c + 2] = v.z;
-        w[4 * c + 3] = v.w;
+      uint4 va = make_uint4(0, 0, 0, 0), vb = make_uint4(0, 0, 0, 0);
+      if (row < rows_left) {
+        const uint8_t* src = s.raw[st] + row * args.bytes_per_desc;
+        if (ca < nkq) va = *reinterpret_cast<const uint4*>(src + ca * 16);
+        if (cb < nkq) vb = *reinterpret_cast<const uint4*>(src + cb * 16);
       }
+      const uint4 lo = swapped ? vb : va, hi = swapped ? va : vb;
+      const uint32_t w[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
       ptx::mbar_wait(&s.empty[slot], phase ^ 1u);
       ptx::tc_fence_after();
-      const uint32_t a_tmem = tmem_base + (static_cast<uint32_t>(quadrant * 32) << 16) + kATmemBase + slot * kAColsPerTile;
+      const uint32_t a_tmem = tmem_base + (static_cast<uint32_t>(quadrant * 32) << 16) + kATmemBase +
+                              slot * kAColsPerTile + chunk0 * 4;
 #pragma unroll
-      for (int pl = 0; pl < 4; ++pl) {
-        const uint32_t m = 0x01010101u << (plane0 + pl);
-        uint32_t v[16];
+      for (int pl = 0; pl < 8; ++pl) {
+        const uint32_t m = 0x01010101u << pl;
+        uint32_t v[8];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = w[j] & m;
-        ptx::tmem_st_32x32b_x16(a_tmem + (plane0 + pl) * 16, v);
+        for (int j = 0; j < 8; ++j) v[j] = w[j] & m;
+        ptx::tmem_st_32x32b_x8(a_tmem + pl * 16, v);
       }
       // Release the raw stage only now: the stores above consumed w[], so the ld.shared have RETURNED. An arrive
       // right behind the loads issues while they are in flight and the next bulk copy overwrites the stage under
