@@ -95,4 +95,4 @@ int main() {
       }
   return 0;
 }
-// nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o gpurun_out/mma_rate profiles/microbench/mma_rate.cu && gpurun_out/mma_rate
+// nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o profiles/microbench/mma_rate.bin profiles/microbench/mma_rate.cu (here), then profiles/microbench/mma_rate.bin on the GPU box
