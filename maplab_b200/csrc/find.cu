@@ -388,7 +388,10 @@ bool Detector::QueryBatch(const mlc_frame* frames, int64_t num_frames, const uin
   // Host buffers: copy in chunks on copy_stream_ (bits first, keypoints — needed only by kernel 4 —
   // last); stream_ waits for chunk i right before it projects / coarse-searches it, so the PCIe
   // transfer of the later chunks hides behind kernels 1 and 2a of the earlier ones.
-  int chunks = (!inputs_on_device && n >= 65536) ? 2 : 1;  // 1/2/4/8 chunks measured: 207k/216k/211k/190k keyframes/s
+  // 1/2/4/8 equal chunks measured: 207k/216k/211k/190k keyframes/s (round 1); geometric chunk sizes (1/8, 1/8, 1/4,
+  // 1/2, so that only a small first copy is exposed): 250k against 254k for two halves (round 2) — the coarse
+  // search loses more on small launches than the earlier start gains
+  int chunks = (!inputs_on_device && n >= 65536) ? 2 : 1;
   if (const char* env = getenv("MLC_COPY_CHUNKS")) {
     const int v = atoi(env);
     if (v >= 1 && v <= kCopyChunks && !inputs_on_device) chunks = v;
