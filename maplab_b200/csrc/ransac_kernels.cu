@@ -1351,16 +1351,21 @@ bool Detector::RansacOnDevice(const mlc_ransac_settings& rs, const mlc_camera* c
   }
   const int max_rounds = 11 * rs.num_ransac_iters + 4;  // >= one consumed sample per round
   // One round of one group: six kernels, the count of its still-running problems to the host, an event.
-  auto enqueue_round = [&](int g) -> bool {
+  auto enqueue_round = [&](int g, int round) -> bool {
     const int64_t np = ga[g].num_problems, nh = np * hyp_slots;
+    // later rounds hold few running problems: one hypothesis per warp then (no group of the warp waits for the
+    // data-dependent control flow of another, and the GPU has idle warps to spare)
+    int later = 1;
+    if (const char* env = getenv("MLC_EIGEN_GPW_LATER")) later = atoi(env);
+    const int gpw = (round == 0 || (later != 1 && later != 2 && later != 4)) ? eigen_gpw : later;
     cudaStream_t st = g_stream[g];
     const unsigned elim_blocks = static_cast<unsigned>(std::min<int64_t>(
         (nh + kWarpsPerBlock - 1) / kWarpsPerBlock, static_cast<int64_t>(sm_count_) * elim_per_sm));
     if (!Cuda(cudaMemsetAsync(d_remaining_all + g, 0, sizeof(int), st), "memset", err)) return false;
     ransac_sample_kernel<<<blocks_of(np, 128), 128, 0, st>>>(ga[g], g_state[g], g_hyp[g]);
     gp3p_eliminate_kernel<<<elim_blocks, kWarpsPerBlock * 32, smem, st>>>(ga[g], g_hyp[g], nh);
-    if (eigen_gpw == 1) gp3p_eigen_kernel<1><<<blocks_of(nh, 4), 128, 0, st>>>(g_hyp[g], nh);
-    else if (eigen_gpw == 2) gp3p_eigen_kernel<2><<<blocks_of(nh, 8), 128, 0, st>>>(g_hyp[g], nh);
+    if (gpw == 1) gp3p_eigen_kernel<1><<<blocks_of(nh, 4), 128, 0, st>>>(g_hyp[g], nh);
+    else if (gpw == 2) gp3p_eigen_kernel<2><<<blocks_of(nh, 8), 128, 0, st>>>(g_hyp[g], nh);
     else gp3p_eigen_kernel<4><<<blocks_of(nh, 16), 128, 0, st>>>(g_hyp[g], nh);
     gp3p_candidate_kernel<<<blocks_of(nh * 8, 64), 64, 0, st>>>(ga[g], g_hyp[g], nh);
     ransac_score_kernel<<<blocks_of(nh * 32, 128), 128, 0, st>>>(ga[g], g_hyp[g], nh);
@@ -1384,7 +1389,7 @@ bool Detector::RansacOnDevice(const mlc_ransac_settings& rs, const mlc_camera* c
   for (int r = 0; r < upfront; ++r)
     for (int g = 0; g < groups; ++g) {
       if (!active[g]) continue;
-      if (!enqueue_round(g)) return false;
+      if (!enqueue_round(g, rounds[g])) return false;
       ++rounds[g];
       if (r == 0) ++live;
     }
@@ -1405,11 +1410,12 @@ bool Detector::RansacOnDevice(const mlc_ransac_settings& rs, const mlc_camera* c
             return false;
         }
       } else {
-        if (++rounds[g] > max_rounds) {  // cannot happen: every round consumes a sample
+        if (rounds[g] >= max_rounds) {  // cannot happen: every round consumes a sample
           *err = "RANSAC round limit reached";
           return false;
         }
-        if (!enqueue_round(g)) return false;
+        if (!enqueue_round(g, rounds[g])) return false;
+        ++rounds[g];
       }
     }
   }
