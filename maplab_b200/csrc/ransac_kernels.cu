@@ -845,6 +845,7 @@ __global__ void __launch_bounds__(128) gp3p_eigen_kernel(Hypothesis* hyp, int64_
     a[L * 8 + c] = v;
     if (!isfinite(v)) finite = false;
   }
+  __syncwarp(gm);  // the rows written above are read by the other lanes of the group (a vote is no memory barrier)
   const bool ok_in = __all_sync(gm, finite);
   bool ok = ok_in;
   if (ok) {
