@@ -131,6 +131,7 @@ __global__ void __launch_bounds__(THREADS, (THREADS <= 512 ? 2 : 1)) covis_kerne
   __shared__ typename cub::BlockScan<int, THREADS>::TempStorage scan_tmp;
   typedef cub::BlockReduce<unsigned long long, THREADS> BlockMax;
   __shared__ typename BlockMax::TempStorage red_tmp;
+  __shared__ int s_count[2][32];
   mlc_match* rec = a.scratch + static_cast<size_t>(blockIdx.x) * MAXM;
   const int tid = threadIdx.x;
 
@@ -240,7 +241,6 @@ __global__ void __launch_bounds__(THREADS, (THREADS <= 512 ? 2 : 1)) covis_kerne
         int want = static_cast<int>(__fmul_rn(static_cast<float>(Cn), a.fraction_best_scores));
         if (want < 4) want = 4;
         n_eval = want < Cn ? want : Cn;
-        const int pc = NextPow2(Cn);
         unsigned* prob_score = reinterpret_cast<unsigned*>(s.a5);  // a5/a6 are free until stage C
         if (a.scoring == 1) {
           // computeProbabilisticScore (scoring.h:92-187), candidates in ascending keyframe number
@@ -276,22 +276,54 @@ __global__ void __launch_bounds__(THREADS, (THREADS <= 512 ? 2 : 1)) covis_kerne
             __syncthreads();
           }
         }
-        for (int b = tid; b < pc; b += THREADS) {
-          unsigned long long key = ~0ull;
+        // The n_eval best candidates by (score descending, keyframe number ascending) — a SELECTION, the order
+        // among them is never used: find the n_eval-th largest score T bit by bit (block-wide counts), take every
+        // candidate above T and the first ones in keyframe order that equal T. (The bitonic sort this replaces
+        // ran over next_pow2(candidates) 64-bit keys — ~1 500 candidates per frame at k = 6 — and was the largest
+        // single piece of the kernel.)
+        unsigned kreg[IPT];
+#pragma unroll
+        for (int i = 0; i < IPT; ++i) {
+          const int b = tid + i * THREADS;
+          unsigned key = 0;
+          if (b < Cn)  // accumulation score = votes (ordered like its float); probabilistic scores are >= 0:
+            key = a.scoring == 1 ? prob_score[b] : static_cast<unsigned>(s.a2[b + 1] - s.a2[b]);  // bits order them
+          kreg[i] = key;
+        }
+        __syncthreads();  // prob_score (a5/a6) has been read; count_tmp of a previous frame is free
+        auto block_count = [&](int local, int buf) -> int {  // one barrier per call, buffers alternate
+          const int wsum = __reduce_add_sync(0xffffffffu, local);
+          if ((tid & 31) == 0) s_count[buf][tid >> 5] = wsum;
+          __syncthreads();
+          const int v = (tid & 31) < THREADS / 32 ? s_count[buf][tid & 31] : 0;
+          return __reduce_add_sync(0xffffffffu, v);
+        };
+        unsigned T = 0;
+        int buf = 0;
+        for (int bit = (a.scoring == 1 ? 30 : SLOT_BITS); bit >= 0; --bit) {  // votes <= R <= MAXM = 2^SLOT_BITS
+          const unsigned cand = T | (1u << bit);
+          int local = 0;
+#pragma unroll
+          for (int i = 0; i < IPT; ++i) local += (kreg[i] >= cand) ? 1 : 0;  // padding keys are 0 < cand
+          if (block_count(local, buf) >= n_eval) T = cand;
+          buf ^= 1;
+        }
+        int above = 0;
+#pragma unroll
+        for (int i = 0; i < IPT; ++i) above += (kreg[i] > T) ? 1 : 0;
+        const int room = n_eval - block_count(above, buf);  // >= 1 candidates equal to T are taken, in keyframe order
+#pragma unroll
+        for (int i = 0; i < IPT; ++i) {
+          const int b = tid + i * THREADS;
           if (b < Cn) {
-            float score = static_cast<float>(s.a2[b + 1] - s.a2[b]);  // accumulation score
-            if (a.scoring == 1) score = __uint_as_float(prob_score[b]);
-            const unsigned ord = __float_as_uint(score);              // scores are >= 0
-            key = (static_cast<unsigned long long>(0xFFFFFFFFu - ord) << SLOT_BITS) | static_cast<unsigned>(b);
+            s.f1[b] = kreg[i] > T ? 1 : 0;
+            s.f2[b] = kreg[i] == T ? 1 : 0;
           }
-          s.keys[b] = key;
         }
         __syncthreads();
-        BitonicSort<THREADS>(s.keys, pc);
-        for (int b = tid; b < Cn; b += THREADS) s.f1[b] = 0;
-        __syncthreads();
-        for (int r = tid; r < n_eval; r += THREADS) s.f1[s.keys[r] & SLOT_MASK] = 1;
-        __syncthreads();
+        FlagScan<THREADS, IPT>(
+            Cn, [&](int b) { return s.f2[b] != 0; },
+            [&](int b, int pos, bool f) { if (f && pos < room) s.f1[b] = 1; }, scan_tmp);
       } else {
         for (int b = tid; b < Cn; b += THREADS) s.f1[b] = 1;
         __syncthreads();
