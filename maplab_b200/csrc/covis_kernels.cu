@@ -1,7 +1,7 @@
 // Kernel 3 of the loop-closure path: match gathering with the time/mission filter, per-keyframe
 // vote counting, top-fraction selection and landmark-covisibility clustering — one CTA per query
 // frame (pass 1) or per multi-camera query vertex (pass 2). Everything is sort / scan / segmented
-// reduction in shared memory; no atomics.
+// reduction in shared memory; no atomics except one order-independent integer add (component sizes).
 //
 // Reference: matching-based-loopclosure/src/matching-based-engine.cc:101-123 (neighbour walk with
 // `break`), :170-215 (getMatchForDescriptorIndex), :147-165 (vertex pass);
@@ -455,22 +455,21 @@ __global__ void __launch_bounds__(THREADS, (THREADS <= 512 ? 2 : 1)) covis_kerne
         cnt[b] = static_cast<uint16_t>(c);
       }
       __syncthreads();
-      // most roots are singletons (a keyframe that shares no landmark with another): only roots that some
-      // other group points at walk the groups for their members
-      for (int b = tid; b < n_eval; b += THREADS) s.f1[b] = 0;
+      // component sizes: every group adds its distinct matches to its root. Integer adds in shared memory — the
+      // sums do not depend on the order, so the result stays deterministic (the only atomics of the kernel; a
+      // root walking all groups for its members was a 400-iteration serial loop per root). The sort keys are
+      // dead from here on: their storage holds the sizes.
+      int* size = reinterpret_cast<int*>(s.keys);  // (cnt is complete and the keys have been read: barrier above)
+      for (int b = tid; b < n_eval; b += THREADS) size[b] = K[b] == b ? cnt[b] : 0;
       __syncthreads();
       for (int b = tid; b < n_eval; b += THREADS)
-        if (K[b] != b) s.f1[K[b]] = 1;  // same value from every writer
+        if (K[b] != b) atomicAdd(&size[K[b]], static_cast<int>(cnt[b]));
       __syncthreads();
       unsigned long long best = 0;
       for (int r = tid; r < n_eval; r += THREADS) {
         if (K[r] != r) continue;  // not a root
-        unsigned size = cnt[r];
-        if (s.f1[r])
-          for (int b = r + 1; b < n_eval; ++b)
-            if (K[b] == r) size += cnt[b];
         // larger size wins; ties -> smaller root
-        const unsigned long long cand = (static_cast<unsigned long long>(size) << 16) | (0xFFFFu - r);
+        const unsigned long long cand = (static_cast<unsigned long long>(size[r]) << 16) | (0xFFFFu - r);
         if (cand > best) best = cand;
       }
       best = BlockMax(red_tmp).Reduce(best, cub::Max());
