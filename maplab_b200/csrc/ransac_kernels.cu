@@ -826,7 +826,8 @@ __device__ bool HqrGroup(double* a, double* wr, double* wi, int L, unsigned gm) 
 // one warp serialise each other's control flow; the kernel is latency bound with idle issue slots,
 // hence fewer groups per warp (idle lanes) finish sooner.
 template <int GPW>
-__global__ void __launch_bounds__(128) gp3p_eigen_kernel(Hypothesis* hyp, int64_t num_hyp) {
+__global__ void __launch_bounds__(128) gp3p_eigen_kernel(Hypothesis* hyp, int64_t num_hyp, int* task_count,
+                                                         int32_t* tasks) {
   __shared__ double s_a[4 * GPW][64];
   __shared__ double s_w[4 * GPW][16];
   const int lane = threadIdx.x & 31;
@@ -858,26 +859,34 @@ __global__ void __launch_bounds__(128) gp3p_eigen_kernel(Hypothesis* hyp, int64_
     }
   }
   if (L == 0) h.eig_ok = ok ? 1 : 0;
+  // The eigenvalues that yield a candidate pose (main.cpp:400: imag < 1e-4, no fabs) go to a compact task list:
+  // they are ~a quarter of the (hypothesis, eigenvalue) pairs, and a candidate kernel over all pairs ran every
+  // warp through the long solve for a few live lanes. The order of the list varies from run to run, the results
+  // do not (a task only writes its own slot).
+  const bool valid = ok && s_w[g][8 + L] < 0.0001;
+  h.cand_valid[L] = valid ? 1 : 0;
+  const int base_lane = lane & 24;
+  const unsigned vmask = (__ballot_sync(gm, valid) >> base_lane) & 0xFFu;
+  int first = 0;
+  if (L == 0 && vmask) first = atomicAdd(task_count, __popc(vmask));
+  first = __shfl_sync(gm, first, 0, 8);
+  if (valid) tasks[first + __popc(vmask & ((1u << L) - 1u))] = static_cast<int32_t>(hi * 8 + L);
 }
 
-// Candidate pose + disambiguation score: one thread per (hypothesis, eigenvalue).
-__global__ void __launch_bounds__(64) gp3p_candidate_kernel(RansacArgs a, Hypothesis* hyp, int64_t num_hyp) {
-  const int64_t task = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+// Candidate pose + disambiguation score: one thread per task = (hypothesis, eigenvalue) listed by the eigenvalue kernel.
+__global__ void __launch_bounds__(64) gp3p_candidate_kernel(RansacArgs a, Hypothesis* hyp, const int* task_count,
+                                                            const int32_t* tasks) {
+  const int64_t t = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (t >= *task_count) return;
+  const int32_t task = tasks[t];
   const int64_t hi = task >> 3;
-  const int c = static_cast<int>(task & 7);
-  if (hi >= num_hyp) return;
+  const int c = task & 7;
   Hypothesis& h = hyp[hi];
-  if (!h.active) return;
-  int valid = 0;
-  if (h.eig_ok && (h.wi[c] < 0.0001)) {  // main.cpp:400 (no fabs: negative imaginary parts pass)
-    const Problem pb = MakeProblem(a, hi / a.hyp_slots);
-    double sol[12], score;
-    SolutionForEigenvalue(pb, h.M, h.wr[c], h.wi[c], h.fvp, h.sel[3], sol, &score);
-    for (int i = 0; i < 12; ++i) h.cand_T[c][i] = sol[i];
-    h.cand_score[c] = score;
-    valid = 1;
-  }
-  h.cand_valid[c] = valid;
+  const Problem pb = MakeProblem(a, hi / a.hyp_slots);
+  double sol[12], score;
+  SolutionForEigenvalue(pb, h.M, h.wr[c], h.wi[c], h.fvp, h.sel[3], sol, &score);
+  for (int i = 0; i < 12; ++i) h.cand_T[c][i] = sol[i];
+  h.cand_score[c] = score;
 }
 
 // Disambiguation (AbsolutePoseSacProblem.cpp:133-163) + countWithinDistance: one warp per hypothesis.
@@ -1252,7 +1261,8 @@ bool Detector::RansacOnDevice(const mlc_ransac_settings& rs, const mlc_camera* c
   const size_t o_bear = (o_rnd + sizeof(int32_t) * rnd_len + 255) & ~static_cast<size_t>(255);
   const size_t o_shuf = (o_bear + sizeof(double) * 3 * total + 255) & ~static_cast<size_t>(255);
   if (!Cuda(b_scr.Reserve(o_shuf + sizeof(int32_t) * total + 256), "alloc", err) ||
-      !Cuda(b_hyp.Reserve(sizeof(Hypothesis) * num_hyp + sizeof(ProblemState) * num_problems + 256)  /* + group counters */, "alloc", err) ||
+      !Cuda(b_hyp.Reserve(sizeof(Hypothesis) * num_hyp + sizeof(ProblemState) * num_problems + 256 /* group counters */ +
+                          sizeof(int32_t) * 8 * num_hyp /* candidate tasks */), "alloc", err) ||
       !Cuda(b_out.Reserve(sizeof(mlc_pose_result) * num_problems + total + 512), "alloc", err))
     return false;
   unsigned char* scr = b_scr.as<unsigned char>();
@@ -1316,7 +1326,8 @@ bool Detector::RansacOnDevice(const mlc_ransac_settings& rs, const mlc_camera* c
     if (v >= 1 && v <= kRansacGroups) groups = v;
   }
   if (groups > num_problems) groups = static_cast<int>(num_problems);
-  int* d_remaining_all = d_remaining;  // one counter per group (room reserved below)
+  int* d_remaining_all = d_remaining;  // two counters per group: [2 g] running problems, [2 g + 1] candidate tasks
+  int32_t* d_tasks = reinterpret_cast<int32_t*>(reinterpret_cast<unsigned char*>(d_remaining) + 256);
   // pinned, so that the per-round read-back does not block the host while it enqueues the other groups
   if (!h_remaining_ && !Cuda(cudaHostAlloc(&h_remaining_, sizeof(int) * 8, cudaHostAllocDefault), "pinned alloc", err))
     return false;
@@ -1362,17 +1373,20 @@ bool Detector::RansacOnDevice(const mlc_ransac_settings& rs, const mlc_camera* c
     cudaStream_t st = g_stream[g];
     const unsigned elim_blocks = static_cast<unsigned>(std::min<int64_t>(
         (nh + kWarpsPerBlock - 1) / kWarpsPerBlock, static_cast<int64_t>(sm_count_) * elim_per_sm));
-    if (!Cuda(cudaMemsetAsync(d_remaining_all + g, 0, sizeof(int), st), "memset", err)) return false;
+    int* counters = d_remaining_all + 2 * g;
+    int32_t* tasks = d_tasks + (g_hyp[g] - d_hyp) * 8;
+    if (!Cuda(cudaMemsetAsync(counters, 0, 2 * sizeof(int), st), "memset", err)) return false;
     ransac_sample_kernel<<<blocks_of(np, 128), 128, 0, st>>>(ga[g], g_state[g], g_hyp[g]);
     gp3p_eliminate_kernel<<<elim_blocks, kWarpsPerBlock * 32, smem, st>>>(ga[g], g_hyp[g], nh);
-    if (gpw == 1) gp3p_eigen_kernel<1><<<blocks_of(nh, 4), 128, 0, st>>>(g_hyp[g], nh);
-    else if (gpw == 2) gp3p_eigen_kernel<2><<<blocks_of(nh, 8), 128, 0, st>>>(g_hyp[g], nh);
-    else gp3p_eigen_kernel<4><<<blocks_of(nh, 16), 128, 0, st>>>(g_hyp[g], nh);
-    gp3p_candidate_kernel<<<blocks_of(nh * 8, 64), 64, 0, st>>>(ga[g], g_hyp[g], nh);
+    if (gpw == 1) gp3p_eigen_kernel<1><<<blocks_of(nh, 4), 128, 0, st>>>(g_hyp[g], nh, counters + 1, tasks);
+    else if (gpw == 2) gp3p_eigen_kernel<2><<<blocks_of(nh, 8), 128, 0, st>>>(g_hyp[g], nh, counters + 1, tasks);
+    else gp3p_eigen_kernel<4><<<blocks_of(nh, 16), 128, 0, st>>>(g_hyp[g], nh, counters + 1, tasks);
+    // sized for the worst case; blocks beyond the task count leave at once
+    gp3p_candidate_kernel<<<blocks_of(nh * 8, 64), 64, 0, st>>>(ga[g], g_hyp[g], counters + 1, tasks);
     ransac_score_kernel<<<blocks_of(nh * 32, 128), 128, 0, st>>>(ga[g], g_hyp[g], nh);
-    ransac_update_kernel<<<blocks_of(np, 128), 128, 0, st>>>(ga[g], g_state[g], g_hyp[g], d_remaining_all + g);
+    ransac_update_kernel<<<blocks_of(np, 128), 128, 0, st>>>(ga[g], g_state[g], g_hyp[g], counters);
     for (int i = 0; i < 6; ++i) CountLaunch();
-    return Cuda(cudaMemcpyAsync(&remaining_h[g], d_remaining_all + g, sizeof(int), cudaMemcpyDeviceToHost, st), "D2H", err) &&
+    return Cuda(cudaMemcpyAsync(&remaining_h[g], counters, sizeof(int), cudaMemcpyDeviceToHost, st), "D2H", err) &&
            Cuda(cudaEventRecord(ev_ransac_[7 + g], st), "event", err);
   };
   // The groups advance independently: the host polls the groups' round events, and a group whose round is
