@@ -48,7 +48,8 @@ __device__ __forceinline__ void Put(float (&v)[D], uint32_t d, float x) {
 template <int D, int KK>
 __global__ void __launch_bounds__(kThreads, 4)
 kd_search_kernel(CoarseParams p, const float* __restrict__ q, int64_t n, int kk1, int kk2,
-                 const uint32_t* __restrict__ order, int32_t* __restrict__ out_idx, float* __restrict__ out_val) {
+                 const uint32_t* __restrict__ order, uint32_t* __restrict__ next_item, int32_t* __restrict__ out_idx,
+                 float* __restrict__ out_val) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int half = blockIdx.x & 1;
   const int kk = half ? kk2 : kk1;
@@ -72,13 +73,9 @@ kd_search_kernel(CoarseParams p, const float* __restrict__ q, int64_t n, int kk1
   const int lane = tid & 31;
   const uint32_t lanemask_lt = (1u << lane) - 1u;
   constexpr uint32_t kAll = 0xffffffffu;
-  // contiguous range of queries for this warp
-  const int64_t warps_total = static_cast<int64_t>(gridDim.x >> 1) * (kThreads / 32);
-  const int64_t warp_id = static_cast<int64_t>(blockIdx.x >> 1) * (kThreads / 32) + (tid >> 5);
-  const int64_t per_warp = (n + warps_total - 1) / warps_total;
-  int64_t warp_next = warp_id * per_warp;
-  const int64_t warp_end = min(n, warp_next + per_warp);
-
+  // Work items are handed out from one counter per half (next_item[half], zeroed by the launcher): a lane that
+  // finishes takes the next unprocessed query of the whole half, so no warp runs dry while another still has a
+  // range to work through (with static per-warp ranges of ~200 items 15 % of the resident warp time was idle).
   const float inf = __int_as_float(0x7f800000);
   // query coordinates and the per-dimension offsets of the traversal are indexed by the cut
   // dimension of the node: [dimension][thread] in shared memory (one LDS / STS instead of a select
@@ -102,9 +99,12 @@ kd_search_kernel(CoarseParams p, const float* __restrict__ q, int64_t n, int kk1
     // ---- refill idle lanes from the warp's range ----
     const uint32_t idle = __ballot_sync(kAll, state == kIdle);
     if (idle) {
+      uint32_t base = 0;
+      if (lane == 0) base = atomicAdd(next_item + half, static_cast<uint32_t>(__popc(idle)));
+      base = __shfl_sync(kAll, base, 0);
       if (state == kIdle) {
-        item = warp_next + __popc(idle & lanemask_lt);
-        const bool have = item < warp_end;
+        item = static_cast<int64_t>(base) + __popc(idle & lanemask_lt);
+        const bool have = item < n;
         // processing order: queries that fall into the same leaf first are neighbours, so the lanes of a
         // warp walk (nearly) the same path; results go to the query's own row
         if (have && order) item = order[static_cast<size_t>(half) * n + item];
@@ -129,7 +129,6 @@ kd_search_kernel(CoarseParams p, const float* __restrict__ q, int64_t n, int kk1
           state = kDone;
         }
       }
-      warp_next += __popc(idle);
     }
     if (__all_sync(kAll, state == kDone)) break;
 
@@ -334,7 +333,8 @@ multi_sequence_kernel(const int32_t* __restrict__ h_idx, const float* __restrict
 
 template <int D, int KK>
 cudaError_t LaunchSearchK(const CoarseParams& p, const float* d_q, int64_t n, int kk1, int kk2,
-                          const uint32_t* order, int32_t* h_idx, float* h_val, int sm_count, cudaStream_t stream) {
+                          const uint32_t* order, uint32_t* next_item, int32_t* h_idx, float* h_val, int sm_count,
+                          cudaStream_t stream) {
   const uint32_t tree_bytes =
       p.stage_in_smem ? max(p.off_nodes2, p.packed_bytes - p.off_nodes2) : 0u;
   const size_t smem = tree_bytes;
@@ -349,8 +349,10 @@ cudaError_t LaunchSearchK(const CoarseParams& p, const float* d_q, int64_t n, in
   const int64_t needed = (n + kThreads - 1) / kThreads;  // at least one query per lane to start with
   if (blocks_per_half > needed) blocks_per_half = needed;
   if (blocks_per_half < 1) blocks_per_half = 1;
+  e = cudaMemsetAsync(next_item, 0, 2 * sizeof(uint32_t), stream);
+  if (e != cudaSuccess) return e;
   kd_search_kernel<D, KK><<<static_cast<unsigned>(2 * blocks_per_half), kThreads, smem, stream>>>(
-      p, d_q, n, kk1, kk2, order, h_idx, h_val);
+      p, d_q, n, kk1, kk2, order, next_item, h_idx, h_val);
   CountLaunch();
   return cudaGetLastError();
 }
@@ -378,7 +380,8 @@ size_t SortTempBytes(int64_t n) {
 
 template <int D>
 cudaError_t LaunchSearch(const CoarseParams& p, const float* d_q, int64_t n, int kk1, int kk2,
-                         int32_t* h_idx, float* h_val, void* sort_scratch, int sm_count, cudaStream_t stream) {
+                         int32_t* h_idx, float* h_val, void* sort_scratch, uint32_t* next_item, int sm_count,
+                         cudaStream_t stream) {
   const uint32_t* order = nullptr;
   if (sort_scratch) {
     uint32_t* keys = static_cast<uint32_t*>(sort_scratch);
@@ -396,9 +399,9 @@ cudaError_t LaunchSearch(const CoarseParams& p, const float* d_q, int64_t n, int
     order = vals_out;
   }
   const int kk_max = max(kk1, kk2);
-  if (kk_max <= 1) return LaunchSearchK<D, 1>(p, d_q, n, kk1, kk2, order, h_idx, h_val, sm_count, stream);
-  if (kk_max <= 10) return LaunchSearchK<D, 10>(p, d_q, n, kk1, kk2, order, h_idx, h_val, sm_count, stream);
-  return LaunchSearchK<D, 16>(p, d_q, n, kk1, kk2, order, h_idx, h_val, sm_count, stream);
+  if (kk_max <= 1) return LaunchSearchK<D, 1>(p, d_q, n, kk1, kk2, order, next_item, h_idx, h_val, sm_count, stream);
+  if (kk_max <= 10) return LaunchSearchK<D, 10>(p, d_q, n, kk1, kk2, order, next_item, h_idx, h_val, sm_count, stream);
+  return LaunchSearchK<D, 16>(p, d_q, n, kk1, kk2, order, next_item, h_idx, h_val, sm_count, stream);
 }
 
 size_t WordListBytes(int64_t n, int kk1, int kk2) {
@@ -411,7 +414,7 @@ size_t CoarseScratchBytes(const CoarseParams& p, int64_t n, int num_words) {
   const int kk1 = min(p.num_words1, num_words), kk2 = min(p.num_words2, num_words);
   size_t bytes = WordListBytes(n, kk1, kk2) + 256;
   if (SortEnabled() && n >= kSortMinItems) bytes += static_cast<size_t>(n) * 2 * 4 * 4 + SortTempBytes(n) + 256;
-  return bytes;
+  return ((bytes + 255) & ~static_cast<size_t>(255)) + 256;  // the last 256 bytes: work-item counters of the search
 }
 
 cudaError_t LaunchCoarseWords(const CoarseParams& p, const float* d_q, int64_t n, int num_words,
@@ -425,11 +428,13 @@ cudaError_t LaunchCoarseWords(const CoarseParams& p, const float* d_q, int64_t n
   void* sort_scratch = nullptr;
   if (SortEnabled() && n >= kSortMinItems && p.num_words1 < 65536 && p.num_words2 < 65536)
     sort_scratch = static_cast<unsigned char*>(scratch) + ((WordListBytes(n, kk1, kk2) + 255) & ~static_cast<size_t>(255));
+  uint32_t* next_item = reinterpret_cast<uint32_t*>(static_cast<unsigned char*>(scratch) +
+                                                    CoarseScratchBytes(p, n, num_words) - 256);
   cudaError_t e;
   switch (p.sub_dim) {
-#define MLC_CASE(D)                                                                     \
-  case D:                                                                               \
-    e = LaunchSearch<D>(p, d_q, n, kk1, kk2, h_idx, h_val, sort_scratch, sm_count, stream); \
+#define MLC_CASE(D)                                                                                \
+  case D:                                                                                          \
+    e = LaunchSearch<D>(p, d_q, n, kk1, kk2, h_idx, h_val, sort_scratch, next_item, sm_count, stream); \
     break;
     MLC_CASE(1) MLC_CASE(2) MLC_CASE(3) MLC_CASE(4) MLC_CASE(5) MLC_CASE(6) MLC_CASE(7) MLC_CASE(8)
 #undef MLC_CASE
